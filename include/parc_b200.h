@@ -1,0 +1,252 @@
+/*
+ * parc_b200.h -- C ABI of libparc_b200.so: PARC's batched kinematic motion-query path on B200 (sm_100a).
+ *
+ * The reference (ZhengmaoHe/PARC) has no FFI layer: its "operator interface" for this path is a set of
+ * Python methods taking torch tensors.  Each entry point below names the reference method it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Contract (all entry points)
+ *   - Plain C: pointers, sizes, PODs.  No torch / C++ types cross the boundary.
+ *   - OWNERSHIP: the caller allocates every input, output and workspace buffer (device memory unless a
+ *     parameter says "host").  The library never allocates, frees or retains a pointer past return.
+ *   - ASYNC: work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     of the CURRENT device; the call returns without synchronising.
+ *   - ERRORS: returns 0 on success, a positive cudaError_t if the launch failed, or a negative
+ *     PARC_E_* code if an argument was rejected before anything was enqueued.  Nothing throws or exits.
+ *   - THREADS: re-entrant; no global mutable state.  ParcCharModel is an immutable host POD passed by
+ *     pointer and copied into the kernel's parameter space at launch.
+ *   - dtypes follow the reference: fp32 values, int64 clip ids / frame indices, quaternions xyzw.
+ */
+#ifndef PARC_B200_H_
+#define PARC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARC_ABI_VERSION 1
+#define PARC_MAX_BODIES 24   /* pose part of a packed row must fit one warp: 1 + J + ceil(J/4) <= 32 */
+#define PARC_MAX_DOF 96
+
+/* negative = argument rejected; positive = cudaError_t */
+enum {
+  PARC_OK = 0,
+  PARC_E_NULL = -1,       /* a required pointer is NULL */
+  PARC_E_SIZE = -2,       /* negative / inconsistent size */
+  PARC_E_MODEL = -3,      /* character model unsupported (J > PARC_MAX_BODIES, bad parents, ...) */
+  PARC_E_ALIGN = -4,      /* pointer not aligned for vector access (16 B) */
+  PARC_E_LAYOUT = -5      /* row_floats does not match the model's packed-row layout */
+};
+
+/* joint types -- anim/kin_char_model.py:11-15 */
+enum { PARC_JOINT_ROOT = 0, PARC_JOINT_HINGE = 1, PARC_JOINT_SPHERICAL = 2, PARC_JOINT_FIXED = 3 };
+/* loop modes -- anim/motion_lib.py:11-13 */
+enum { PARC_LOOP_CLAMP = 0, PARC_LOOP_WRAP = 1 };
+
+/* Kinematic tree: the arrays KinCharModel.init keeps (anim/kin_char_model.py:147-178).
+ * parent[b] < b for b > 0 and parent[0] == -1 (the MJCF loader's DFS order guarantees it). */
+typedef struct ParcCharModel {
+  int32_t num_bodies;                         /* J */
+  int32_t dof_size;                           /* D = sum of dof_dim */
+  int32_t max_depth;                          /* longest root->leaf chain, root = 0 */
+  int32_t reserved;
+  int32_t parent[PARC_MAX_BODIES];
+  int32_t depth[PARC_MAX_BODIES];
+  int32_t joint_type[PARC_MAX_BODIES];
+  int32_t dof_idx[PARC_MAX_BODIES];
+  float local_trans[PARC_MAX_BODIES][3];
+  float local_rot[PARC_MAX_BODIES][4];        /* xyzw */
+  float joint_axis[PARC_MAX_BODIES][3];       /* hinge axis, zeros otherwise */
+} ParcCharModel;
+
+/* Packed frame row (one row per table frame, all float4 slots, 32 B-aligned stride):
+ *   slot 0            root_pos.xyz, pad
+ *   slot 1            root_rot xyzw
+ *   slot 2 .. J       joint_rot[0..J-2] xyzw
+ *   slot J+1 ..       contacts[0..J-1], zero padded to a multiple of 4
+ *   vel part          root_vel(3) root_ang_vel(3) dof_vel(D), zero padded
+ * Replaces the eight separate MotionLib tables (anim/motion_lib.py:349-375). */
+typedef struct ParcRowLayout {
+  int32_t row_floats;      /* stride in floats (multiple of 8) */
+  int32_t pose_slots;      /* float4 slots read at BOTH key frames: 2 + (J-1) + ceil(J/4) */
+  int32_t contact_slot;    /* first contact slot = J + 1 */
+  int32_t vel_slot;        /* first velocity slot = pose_slots */
+  int32_t vel_slots;       /* ceil((6 + D) / 4) */
+  int32_t reserved[3];
+} ParcRowLayout;
+
+/* Per-clip metadata, 32 B (anim/motion_lib.py:352-358, :373-375). */
+typedef struct ParcClipMeta {
+  int32_t num_frames;
+  int32_t loop_mode;
+  int64_t start_idx;       /* exclusive cumsum of num_frames */
+  float length;            /* fp32((n-1)/fps) exactly as the reference stores it */
+  float root_pos_delta[3]; /* last - first root position, z zeroed */
+} ParcClipMeta;
+
+typedef struct ParcMotionTables {
+  const float* rows;            /* device [total_frames, row_floats] */
+  const ParcClipMeta* clips;    /* device [num_clips] */
+  int64_t total_frames;
+  int64_t num_clips;
+  int32_t row_floats;
+  int32_t reserved;
+} ParcMotionTables;
+
+/* Outputs of a frame query; any pointer may be NULL (= not wanted).  Shapes as the tuple returned by
+ * MotionLib.calc_motion_frame (anim/motion_lib.py:106-112). */
+typedef struct ParcFrameOut {
+  float* root_pos;       /* [N,3] */
+  float* root_rot;       /* [N,4] */
+  float* root_vel;       /* [N,3] */
+  float* root_ang_vel;   /* [N,3] */
+  float* joint_rot;      /* [N,J-1,4] */
+  float* dof_vel;        /* [N,D] */
+  float* contacts;       /* [N,J] */
+  int64_t* frame_idx0;   /* [N] absolute table rows, as MotionLib._calc_frame_blend returns */
+  int64_t* frame_idx1;   /* [N] */
+  float* blend;          /* [N] */
+} ParcFrameOut;
+
+typedef struct ParcFkOut {
+  float* body_pos;       /* [N,J,3] */
+  float* body_rot;       /* [N,J,4] */
+} ParcFkOut;
+
+/* SubTerrain's sampled fields (util/terrain_util.py:21-39): hf is [dim_x, dim_y] row-major. */
+typedef struct ParcHeightfield {
+  const float* hf;
+  int32_t dim_x, dim_y;
+  float min_x, min_y;
+  float dx, dy;
+} ParcHeightfield;
+
+/* Heightmap observation: out[n,k] = hf(R(heading_n) * tmpl[k] + root_xy_n), then if relative != 0
+ * clamp(z - root_z_n, min_h, max_h)  (envs/ig_parkour/mgdm_dm_util.py:158-179; template from
+ * util/geom_util.py:249-270 or :210-221). */
+typedef struct ParcObsSpec {
+  const float* tmpl_xy;  /* device [num_points,2] */
+  int32_t num_points;
+  int32_t relative;
+  float min_h, max_h;
+} ParcObsSpec;
+
+int parc_abi_version(void);
+const char* parc_error_string(int code);
+
+/* Host-only helpers: derive the packed-row layout; validate a model. */
+int parc_row_layout(const ParcCharModel* model, ParcRowLayout* out);
+int parc_validate_model(const ParcCharModel* model);
+
+/* a1: interleave the reference's per-frame tables into packed rows.  contacts may be NULL (zeros).
+ * Replaces the layout built by MotionLib._load_motions (anim/motion_lib.py:349-375). */
+int parc_pack_frames(const float* root_pos, const float* root_rot, const float* joint_rot,
+                     const float* contacts, const float* root_vel, const float* root_ang_vel,
+                     const float* dof_vel, int64_t total_frames, const ParcCharModel* model,
+                     float* rows_out, void* stream);
+
+/* a2+a3 (+a6, +a10 fused): MotionLib.calc_motion_frame (anim/motion_lib.py:80-112) for N
+ * (clip id, time) queries; if `fk` is non-NULL also KinCharModel.forward_kinematics
+ * (anim/kin_char_model.py:509-541) of the blended pose; if `obs_out` is non-NULL also the heightmap
+ * observation [N,num_points] around the blended root with heading = calc_heading(root_rot)
+ * (util/torch_util.py:470-479).  One warp per query, a single launch. */
+int parc_motion_query(const ParcMotionTables* tables, const int64_t* motion_ids, const float* motion_times,
+                      int64_t n, const ParcCharModel* model, const ParcFrameOut* frame,
+                      const ParcFkOut* fk, const ParcHeightfield* hf, const ParcObsSpec* obs,
+                      float* obs_out, void* stream);
+
+/* a4: MotionLib.get_motion_frame (anim/motion_lib.py:114-131): integer frame lookup, no blending. */
+int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
+                          const int64_t* frame_idxs, int64_t n, const ParcCharModel* model,
+                          const ParcFrameOut* frame, const ParcFkOut* fk, void* stream);
+
+/* a6: KinCharModel.forward_kinematics (anim/kin_char_model.py:509-541) on caller-supplied poses. */
+int parc_fk_fwd(const float* root_pos, const float* root_rot, const float* joint_rot, int64_t n,
+                const ParcCharModel* model, float* body_pos, float* body_rot, void* stream);
+
+/* a6 backward: vector-Jacobian product of the above (what autograd computes through
+ * anim/kin_char_model.py:517-539).  The forward pass is recomputed in registers from (root_rot,
+ * joint_rot).  g_body_pos / g_body_rot may be NULL (= zero); outputs are overwritten, any may be NULL. */
+int parc_fk_bwd(const float* root_rot, const float* joint_rot, const float* g_body_pos,
+                const float* g_body_rot, int64_t n, const ParcCharModel* model, float* g_root_pos,
+                float* g_root_rot, float* g_joint_rot, void* stream);
+
+/* a8: KinCharModel.dof_to_rot (anim/kin_char_model.py:478-491, Joint.dof_to_rot :57-77). */
+int parc_dof_to_rot_fwd(const float* dof, int64_t n, const ParcCharModel* model, float* joint_rot,
+                        void* stream);
+int parc_dof_to_rot_bwd(const float* dof, const float* g_joint_rot, int64_t n, const ParcCharModel* model,
+                        float* g_dof, void* stream);
+
+/* util/torch_util.py:414-419 exp_map_to_quat and its VJP (root rotation leaf of the optimiser). */
+int parc_exp_map_to_quat_fwd(const float* exp_map, int64_t n, float* quat, void* stream);
+int parc_exp_map_to_quat_bwd(const float* exp_map, const float* g_quat, int64_t n, float* g_exp_map,
+                             void* stream);
+
+/* a9: SubTerrain.get_hf_val_from_points / get_local_hf_from_terrain (util/terrain_util.py:113-130,
+ * :1329-1346).  grid_idx_out (int64 [N,2]) may be NULL. */
+int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_t n, float* z_out,
+                   int64_t* grid_idx_out, void* stream);
+
+/* a10/a11: RefCharEnv._refresh_ray_obs_hfs (envs/ig_parkour/mgdm_dm_util.py:158-179) and
+ * sample_hf_z_on_terrain (util/terrain_util.py:2049-2082) with caller-supplied root and heading.
+ * root is [N,root_stride] floats (xy at 0,1 and z at 2 when obs->relative). */
+int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* root, int32_t root_stride,
+                const float* heading, int64_t n, float* obs_out, void* stream);
+
+/* One terrain per sample (hf_batch_stride = X*Y, min_center_stride = 2, base_z_stride = 1) or one
+ * terrain shared by the whole batch (strides 0).  x_nodes[X] / y_nodes[Y] are the torch.linspace node
+ * offsets the reference adds to min_center (util/terrain_util.py:1855-1860); they are passed in rather
+ * than recomputed because linspace's fp32 values are not i*dx.  base_z: device pointer (so that
+ * "min(hf) - 10" of tools/procgen/mdm_path.py:77 never has to visit the host) or NULL to use
+ * base_z_value. */
+typedef struct ParcTerrainBatch {
+  const float* hf;            /* device [B or 1, X, Y] */
+  int64_t hf_batch_stride;
+  const float* min_center;    /* device [B or 1, 2] */
+  const float* x_nodes;       /* device [X] */
+  const float* y_nodes;       /* device [Y] */
+  const float* base_z;        /* device [B or 1] or NULL */
+  int32_t dim_x, dim_y;
+  int32_t min_center_stride;
+  int32_t base_z_stride;
+  float half_dx, half_dy;
+  float base_z_value;
+  int32_t reserved;
+} ParcTerrainBatch;
+
+/* a13: terrain_util.points_hf_sdf (util/terrain_util.py:1835-1893): exact min over ALL cells of the
+ * box SDF (util/geom_util.py:122-143); solid columns [base_z, hf] or, if inverted, air columns
+ * [hf, -base_z] with the result negated.  points [B,N,3] -> sdf_out [B,N]; arg_out (int32 [B,N], flat
+ * cell index ix*Y+iy of the minimum, first index on ties) may be NULL. */
+int parc_points_hf_sdf(const float* points, int64_t batch, int64_t n_points, const ParcTerrainBatch* terrain,
+                       int32_t inverted, float* sdf_out, int32_t* arg_out, void* stream);
+
+/* Body surface samples: concatenated local points [S,3] (body-major) and per-body offsets
+ * point_start[J+1] -- util/geom_util.py:788-870 produces the per-body lists. */
+typedef struct ParcBodyPoints {
+  const float* points;          /* device [S,3] */
+  const int32_t* point_start;   /* device [J+1] */
+  int32_t num_points;           /* S */
+  int32_t reserved;
+} ParcBodyPoints;
+
+/* a14/a15: the body-point penetration and contact terms, forward AND gradient in one launch.
+ * Per (sample b, frame f), with FK of (root_pos, root_rot, joint_rot)[b,f] done in-kernel:
+ *   pen_out[b,f]     = sum_points max(0, -sdf_inverted(point))
+ *   contact_out[b,f] = sum_body contacts[b,f,body] * min_{p in body} max(0, sdf_solid(p))
+ * (tools/procgen/mdm_path.py:79-110; tools/motion_opt/motion_optimization.py:241-272); both are
+ * UNWEIGHTED per-frame partial sums (sum over f is the reference's loss term).
+ * If any g_* pointer is non-NULL they receive d(w_pen*pen + w_contact*contact)/d(input)[b,f]:
+ * g_root_pos [B,F,3], g_root_rot [B,F,4], g_joint_rot [B,F,J-1,4] (what autograd yields through
+ * the reference's FK + quat_rotate + points_hf_sdf graph, same sub-gradient/tie conventions). */
+int parc_body_loss(const float* root_pos, const float* root_rot, const float* joint_rot, const float* contacts,
+                   int64_t batch, int64_t frames, const ParcCharModel* model, const ParcBodyPoints* pts,
+                   const ParcTerrainBatch* terrain, float w_pen, float w_contact, float* pen_out,
+                   float* contact_out, float* g_root_pos, float* g_root_rot, float* g_joint_rot, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARC_B200_H_ */

@@ -1,0 +1,328 @@
+// Forward kinematics (forward + VJP) and DoF -> quaternion conversion (forward + VJP), sm_100a.
+//
+// FK: one warp per character, lane b owns body b; the chain is resolved level by level with warp
+// shuffles (fk_warp in parc_common.cuh).  The VJP recomputes the forward pass in registers (cheaper
+// than re-reading body_rot from HBM) and then walks the bodies in reverse index order, each body
+// pushing its contribution into its parent's lane by shuffle -- no atomics, deterministic.
+//
+// Reference: anim/kin_char_model.py:509-541 (FK), :478-491 + :57-77 (dof_to_rot),
+// util/torch_util.py:311-317, :394-419 (axis-angle / exp-map -> quaternion).
+#include "parc_common.cuh"
+
+namespace parc {
+
+// ------------------------------------------------------------------------------------------------
+// axis-angle / exp-map -> quaternion, with VJPs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 normalize4(const float4& u, float& nrm_out) {
+  const float n = sqrtf(u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w);
+  const float d = fmaxf(n, 1e-9f);                  // util/torch_util.py:12 clamp(min=eps)
+  nrm_out = d;
+  return make_float4(u.x / d, u.y / d, u.z / d, u.w / d);
+}
+
+__device__ __forceinline__ float3 normalize3(const float3& a, float& nrm_out) {
+  const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+  const float d = fmaxf(n, 1e-9f);
+  nrm_out = d;
+  return make_float3(a.x / d, a.y / d, a.z / d);
+}
+
+// util/torch_util.py:311-317
+__device__ __forceinline__ float4 axis_angle_to_quat(const float3& axis, float angle) {
+  const float th = angle / 2.0f;
+  float an, un;
+  const float3 n = normalize3(axis, an);
+  const float s = sinf(th), c = cosf(th);
+  return normalize4(make_float4(n.x * s, n.y * s, n.z * s, c), un);
+}
+
+// VJP wrt (axis, angle) of axis_angle_to_quat for upstream g.
+__device__ __forceinline__ void axis_angle_to_quat_vjp(const float3& axis, float angle, const float4& g,
+                                                       float3& g_axis, float& g_angle) {
+  const float th = angle / 2.0f;
+  float an, un;
+  const float3 n = normalize3(axis, an);
+  const float s = sinf(th), c = cosf(th);
+  const float4 u = make_float4(n.x * s, n.y * s, n.z * s, c);
+  const float4 q = normalize4(u, un);
+  // q = u / |u|
+  const float qg = q.x * g.x + q.y * g.y + q.z * g.z + q.w * g.w;
+  const float4 gu = make_float4((g.x - q.x * qg) / un, (g.y - q.y * qg) / un, (g.z - q.z * qg) / un,
+                                (g.w - q.w * qg) / un);
+  const float g_th = (gu.x * n.x + gu.y * n.y + gu.z * n.z) * c - gu.w * s;
+  g_angle = 0.5f * g_th;
+  // n = axis / |axis|
+  const float3 gn = make_float3(gu.x * s, gu.y * s, gu.z * s);
+  const float ngn = n.x * gn.x + n.y * gn.y + n.z * gn.z;
+  g_axis = make_float3((gn.x - n.x * ngn) / an, (gn.y - n.y * ngn) / an, (gn.z - n.z * ngn) / an);
+}
+
+// util/torch_util.py:394-419
+__device__ __forceinline__ float4 exp_map_to_quat(const float3& e) {
+  const float a = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
+  float3 axis = make_float3(e.x / a, e.y / a, e.z / a);
+  float ang = atan2f(sinf(a), cosf(a));
+  if (!(fabsf(ang) > 1e-5f)) {
+    ang = 0.0f;
+    axis = make_float3(0.0f, 0.0f, 1.0f);
+  }
+  return axis_angle_to_quat(axis, ang);
+}
+
+// VJP of exp_map_to_quat.  At e == 0 the reference's autograd yields NaN (0/0 behind torch.where,
+// SURVEY F8d); here the masked branch returns a zero gradient instead (documented divergence).
+__device__ __forceinline__ float3 exp_map_to_quat_vjp(const float3& e, const float4& g) {
+  const float a = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
+  const float sa = sinf(a), ca = cosf(a);
+  const float ang = atan2f(sa, ca);
+  if (!(fabsf(ang) > 1e-5f)) return make_float3(0.0f, 0.0f, 0.0f);
+  const float3 axis = make_float3(e.x / a, e.y / a, e.z / a);
+  float3 g_axis;
+  float g_ang;
+  axis_angle_to_quat_vjp(axis, ang, g, g_axis, g_ang);
+  // ang = atan2(sin a, cos a): d ang / d a = (ca*ca + sa*sa) / (sa*sa + ca*ca)
+  const float den = sa * sa + ca * ca;
+  float g_a = g_ang * (ca / den) * ca + g_ang * (sa / den) * sa;
+  // axis = e / a
+  g_a -= (g_axis.x * e.x + g_axis.y * e.y + g_axis.z * e.z) / (a * a);
+  return make_float3(g_axis.x / a + g_a * e.x / a, g_axis.y / a + g_a * e.y / a, g_axis.z / a + g_a * e.z / a);
+}
+
+__global__ void __launch_bounds__(256) exp_map_fwd_kernel(const float* __restrict__ e, int64_t n,
+                                                          float* __restrict__ q) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float3 v = make_float3(e[i * 3], e[i * 3 + 1], e[i * 3 + 2]);
+    reinterpret_cast<float4*>(q)[i] = exp_map_to_quat(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) exp_map_bwd_kernel(const float* __restrict__ e, const float* __restrict__ g,
+                                                          int64_t n, float* __restrict__ ge) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float3 v = make_float3(e[i * 3], e[i * 3 + 1], e[i * 3 + 2]);
+    const float4 gq = reinterpret_cast<const float4*>(g)[i];
+    const float3 r = exp_map_to_quat_vjp(v, gq);
+    ge[i * 3] = r.x; ge[i * 3 + 1] = r.y; ge[i * 3 + 2] = r.z;
+  }
+}
+
+// One thread per (pose, joint).  dof [N,D] -> joint_rot [N,J-1,4].
+__global__ void __launch_bounds__(256)
+dof_to_rot_fwd_kernel(const float* __restrict__ dof, int64_t n, const __grid_constant__ ParcCharModel m,
+                      float* __restrict__ jr) {
+  const int Jm1 = m.num_bodies - 1;
+  const int64_t total = n * Jm1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / Jm1;
+    const int j = (int)(i - f * Jm1) + 1;
+    const float* d = dof + f * m.dof_size + m.dof_idx[j];
+    float4 q = make_float4(0.f, 0.f, 0.f, 1.f);
+    const int jt = m.joint_type[j];
+    if (jt == PARC_JOINT_HINGE) {
+      q = axis_angle_to_quat(make_float3(m.joint_axis[j][0], m.joint_axis[j][1], m.joint_axis[j][2]), d[0]);
+    } else if (jt == PARC_JOINT_SPHERICAL) {
+      q = exp_map_to_quat(make_float3(d[0], d[1], d[2]));
+    }
+    reinterpret_cast<float4*>(jr)[i] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dof_to_rot_bwd_kernel(const float* __restrict__ dof, const float* __restrict__ gjr, int64_t n,
+                      const __grid_constant__ ParcCharModel m, float* __restrict__ gdof) {
+  const int Jm1 = m.num_bodies - 1;
+  const int64_t total = n * Jm1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / Jm1;
+    const int j = (int)(i - f * Jm1) + 1;
+    const int jt = m.joint_type[j];
+    if (jt != PARC_JOINT_HINGE && jt != PARC_JOINT_SPHERICAL) continue;
+    const float* d = dof + f * m.dof_size + m.dof_idx[j];
+    float* o = gdof + f * m.dof_size + m.dof_idx[j];
+    const float4 g = reinterpret_cast<const float4*>(gjr)[i];
+    if (jt == PARC_JOINT_HINGE) {
+      float3 ga;
+      float gang;
+      axis_angle_to_quat_vjp(make_float3(m.joint_axis[j][0], m.joint_axis[j][1], m.joint_axis[j][2]), d[0], g, ga,
+                             gang);
+      o[0] = gang;
+    } else {
+      const float3 r = exp_map_to_quat_vjp(make_float3(d[0], d[1], d[2]), g);
+      o[0] = r.x; o[1] = r.y; o[2] = r.z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FK forward / VJP, one warp per character, lane b = body b
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PARC_CTA_THREADS)
+fk_fwd_kernel(const float* __restrict__ root_pos, const float* __restrict__ root_rot,
+              const float* __restrict__ joint_rot, int64_t n, const __grid_constant__ ParcCharModel model_param,
+              float* __restrict__ body_pos, float* __restrict__ body_rot) {
+  __shared__ ParcCharModel sm;
+  stage_model(&sm, model_param);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int J = sm.num_bodies;
+  const LaneBody lb = load_lane_body(sm, lane, 0);
+  const int max_depth = sm.max_depth;
+  const int64_t warp0 = (int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * PARC_WARPS_PER_CTA;
+  for (int64_t q = warp0; q < n; q += nwarps) {
+    float3 pos = make_float3(0.f, 0.f, 0.f);
+    float4 rot = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (lane == 0) {
+      pos = make_float3(__ldg(root_pos + q * 3), __ldg(root_pos + q * 3 + 1), __ldg(root_pos + q * 3 + 2));
+      rot = __ldg(reinterpret_cast<const float4*>(root_rot) + q);
+    } else if (lane < J) {
+      rot = __ldg(reinterpret_cast<const float4*>(joint_rot) + q * (J - 1) + (lane - 1));
+    }
+    fk_warp(lb, max_depth, pos, rot);
+    if (lane < J) {
+      if (body_pos) {
+        float* o = body_pos + (q * J + lane) * 3;
+        o[0] = pos.x; o[1] = pos.y; o[2] = pos.z;
+      }
+      if (body_rot) reinterpret_cast<float4*>(body_rot)[q * J + lane] = rot;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PARC_CTA_THREADS)
+fk_bwd_kernel(const float* __restrict__ root_rot, const float* __restrict__ joint_rot,
+              const float* __restrict__ g_body_pos, const float* __restrict__ g_body_rot, int64_t n,
+              const __grid_constant__ ParcCharModel model_param, float* __restrict__ g_root_pos,
+              float* __restrict__ g_root_rot, float* __restrict__ g_joint_rot) {
+  __shared__ ParcCharModel sm;
+  stage_model(&sm, model_param);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int J = sm.num_bodies;
+  const LaneBody lb = load_lane_body(sm, lane, 0);
+  const int max_depth = sm.max_depth;
+  const int64_t warp0 = (int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * PARC_WARPS_PER_CTA;
+  for (int64_t q = warp0; q < n; q += nwarps) {
+    float3 pos = make_float3(0.f, 0.f, 0.f);
+    float4 rot = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (lane == 0) rot = __ldg(reinterpret_cast<const float4*>(root_rot) + q);
+    else if (lane < J) rot = __ldg(reinterpret_cast<const float4*>(joint_rot) + q * (J - 1) + (lane - 1));
+    float4 prot, local;
+    fk_warp_keep(lb, max_depth, pos, rot, prot, local);
+
+    float3 gp = make_float3(0.f, 0.f, 0.f);
+    float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < J) {
+      if (g_body_pos) {
+        const float* s = g_body_pos + (q * J + lane) * 3;
+        gp = make_float3(__ldg(s), __ldg(s + 1), __ldg(s + 2));
+      }
+      if (g_body_rot) gr = __ldg(reinterpret_cast<const float4*>(g_body_rot) + q * J + lane);
+    }
+    float4 gj;
+    fk_warp_vjp(lb, J, lane, prot, local, gp, gr, gj);
+    if (lane == 0) {
+      if (g_root_pos) { g_root_pos[q * 3] = gp.x; g_root_pos[q * 3 + 1] = gp.y; g_root_pos[q * 3 + 2] = gp.z; }
+      if (g_root_rot) reinterpret_cast<float4*>(g_root_rot)[q] = gr;
+    } else if (lane < J) {
+      if (g_joint_rot) reinterpret_cast<float4*>(g_joint_rot)[q * (J - 1) + (lane - 1)] = gj;
+    }
+  }
+}
+
+static int warp_grid(int64_t n) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n + PARC_WARPS_PER_CTA - 1) / PARC_WARPS_PER_CTA;
+  const int64_t cap = (int64_t)sms * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+static int flat_grid(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)(b > 0 ? b : 1);
+}
+
+}  // namespace parc
+
+using namespace parc;
+
+extern "C" int parc_fk_fwd(const float* root_pos, const float* root_rot, const float* joint_rot, int64_t n,
+                           const ParcCharModel* model, float* body_pos, float* body_rot, void* stream) {
+  if (!root_pos || !root_rot || !model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
+  if (n < 0) return PARC_E_SIZE;
+  if (!aligned16(root_rot) || !aligned16(joint_rot) || !aligned16(body_rot)) return PARC_E_ALIGN;
+  if (n == 0) return PARC_OK;
+  fk_fwd_kernel<<<warp_grid(n), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(root_pos, root_rot, joint_rot, n,
+                                                                             *model, body_pos, body_rot);
+  return check_launch();
+}
+
+extern "C" int parc_fk_bwd(const float* root_rot, const float* joint_rot, const float* g_body_pos,
+                           const float* g_body_rot, int64_t n, const ParcCharModel* model, float* g_root_pos,
+                           float* g_root_rot, float* g_joint_rot, void* stream) {
+  if (!root_rot || !model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
+  if (n < 0) return PARC_E_SIZE;
+  if (!aligned16(root_rot) || !aligned16(joint_rot) || !aligned16(g_body_rot) || !aligned16(g_root_rot) ||
+      !aligned16(g_joint_rot))
+    return PARC_E_ALIGN;
+  if (n == 0) return PARC_OK;
+  fk_bwd_kernel<<<warp_grid(n), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(
+      root_rot, joint_rot, g_body_pos, g_body_rot, n, *model, g_root_pos, g_root_rot, g_joint_rot);
+  return check_launch();
+}
+
+extern "C" int parc_dof_to_rot_fwd(const float* dof, int64_t n, const ParcCharModel* model, float* joint_rot,
+                                   void* stream) {
+  if (!dof || !joint_rot || !model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (n < 0) return PARC_E_SIZE;
+  if (!aligned16(joint_rot)) return PARC_E_ALIGN;
+  if (n == 0 || model->num_bodies < 2) return PARC_OK;
+  dof_to_rot_fwd_kernel<<<flat_grid(n * (model->num_bodies - 1)), 256, 0, (cudaStream_t)stream>>>(dof, n, *model,
+                                                                                                 joint_rot);
+  return check_launch();
+}
+
+extern "C" int parc_dof_to_rot_bwd(const float* dof, const float* g_joint_rot, int64_t n,
+                                   const ParcCharModel* model, float* g_dof, void* stream) {
+  if (!dof || !g_joint_rot || !g_dof || !model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (n < 0) return PARC_E_SIZE;
+  if (!aligned16(g_joint_rot)) return PARC_E_ALIGN;
+  if (n == 0 || model->num_bodies < 2) return PARC_OK;
+  dof_to_rot_bwd_kernel<<<flat_grid(n * (model->num_bodies - 1)), 256, 0, (cudaStream_t)stream>>>(
+      dof, g_joint_rot, n, *model, g_dof);
+  return check_launch();
+}
+
+extern "C" int parc_exp_map_to_quat_fwd(const float* exp_map, int64_t n, float* quat, void* stream) {
+  if (!exp_map || !quat) return PARC_E_NULL;
+  if (n < 0) return PARC_E_SIZE;
+  if (!aligned16(quat)) return PARC_E_ALIGN;
+  if (n == 0) return PARC_OK;
+  exp_map_fwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(exp_map, n, quat);
+  return check_launch();
+}
+
+extern "C" int parc_exp_map_to_quat_bwd(const float* exp_map, const float* g_quat, int64_t n, float* g_exp_map,
+                                        void* stream) {
+  if (!exp_map || !g_quat || !g_exp_map) return PARC_E_NULL;
+  if (n < 0) return PARC_E_SIZE;
+  if (!aligned16(g_quat)) return PARC_E_ALIGN;
+  if (n == 0) return PARC_OK;
+  exp_map_bwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(exp_map, g_quat, n, g_exp_map);
+  return check_launch();
+}

@@ -1,0 +1,87 @@
+// Nearest-cell heightfield sampling and heightmap observations with caller-supplied root/heading.
+//
+// Reference: util/terrain_util.py:113-130, :1329-1346 (sampling), :2049-2082 (grid observation),
+// envs/ig_parkour/mgdm_dm_util.py:158-179 (ray observation).  The fused query+FK+obs kernel lives
+// in motion_query.cu; these are the stand-alone operators the simulated character's observation
+// (root state from the simulator, not from the motion table) goes through.
+#include "parc_common.cuh"
+
+namespace parc {
+
+__global__ void __launch_bounds__(256)
+hf_sample_kernel(const __grid_constant__ ParcHeightfield t, const float* __restrict__ xy, int64_t n,
+                 float* __restrict__ z, int64_t* __restrict__ gidx) {
+  const float2* __restrict__ p2 = reinterpret_cast<const float2*>(xy);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 p = __ldg(p2 + i);
+    const int ix = grid_index_1d(p.x, t.min_x, t.dx, t.dim_x);
+    const int iy = grid_index_1d(p.y, t.min_y, t.dy, t.dim_y);
+    if (z) z[i] = __ldg(t.hf + (size_t)ix * t.dim_y + iy);
+    if (gidx) {
+      gidx[i * 2] = ix;
+      gidx[i * 2 + 1] = iy;
+    }
+  }
+}
+
+// One thread per (env, template point): consecutive threads write consecutive outputs.
+__global__ void __launch_bounds__(256)
+hf_obs_kernel(const __grid_constant__ ParcHeightfield t, const __grid_constant__ ParcObsSpec obs,
+              const float* __restrict__ root, int root_stride, const float* __restrict__ heading, int64_t n,
+              float* __restrict__ out) {
+  const int P = obs.num_points;
+  const int64_t total = n * P;
+  const float2* __restrict__ tmpl = reinterpret_cast<const float2*>(obs.tmpl_xy);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / P;
+    const int k = (int)(i - e * P);
+    const float* r = root + e * root_stride;
+    const float h = __ldg(heading + e);
+    const float sn = sinf(h), cs = cosf(h);
+    const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, __ldg(r), __ldg(r + 1));
+    float z = hf_lookup(t, w.x, w.y);
+    if (obs.relative) z = fminf(fmaxf(sub_rn(z, __ldg(r + 2)), obs.min_h), obs.max_h);
+    out[i] = z;
+  }
+}
+
+static int flat_grid(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)(b > 0 ? b : 1);
+}
+
+}  // namespace parc
+
+using namespace parc;
+
+static int check_hf(const ParcHeightfield* hf) {
+  if (!hf || !hf->hf) return PARC_E_NULL;
+  if (hf->dim_x <= 0 || hf->dim_y <= 0) return PARC_E_SIZE;
+  return PARC_OK;
+}
+
+extern "C" int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_t n, float* z_out,
+                              int64_t* grid_idx_out, void* stream) {
+  int rc = check_hf(hf);
+  if (rc) return rc;
+  if (!xy || (!z_out && !grid_idx_out)) return PARC_E_NULL;
+  if (n < 0) return PARC_E_SIZE;
+  if ((reinterpret_cast<uintptr_t>(xy) & 7u) != 0) return PARC_E_ALIGN;
+  if (n == 0) return PARC_OK;
+  hf_sample_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(*hf, xy, n, z_out, grid_idx_out);
+  return check_launch();
+}
+
+extern "C" int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* root,
+                           int32_t root_stride, const float* heading, int64_t n, float* obs_out, void* stream) {
+  int rc = check_hf(hf);
+  if (rc) return rc;
+  if (!obs || !obs->tmpl_xy || !root || !heading || !obs_out) return PARC_E_NULL;
+  if (n < 0 || obs->num_points < 0 || root_stride < (obs->relative ? 3 : 2)) return PARC_E_SIZE;
+  if ((reinterpret_cast<uintptr_t>(obs->tmpl_xy) & 7u) != 0) return PARC_E_ALIGN;
+  if (n == 0 || obs->num_points == 0) return PARC_OK;
+  hf_obs_kernel<<<flat_grid(n * obs->num_points), 256, 0, (cudaStream_t)stream>>>(*hf, *obs, root, root_stride,
+                                                                                 heading, n, obs_out);
+  return check_launch();
+}
