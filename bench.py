@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- body-frames/s of the fused MotionLib query + FK + heightmap-observation path.
+
+Workload (BASELINE.json configs[1], "tracker-shaped batch"): per GPU, ENVS (default 4096) environments
+each ask for one (clip id, time) frame of a library of CLIPS (default 2048) synthetic 265-frame 34-DoF
+humanoid clips (packed table 2048*265*480 B = 260 MB > the 126 MB L2), get the 15-body forward
+kinematics of the blended pose and the 441-point ray heightmap observation on a 1536x1536-cell global
+heightfield.  1 character-frame = 15 body-frames.  One "step" = one pass over the batch = ONE launch of
+`motion_query_kernel` (csrc/motion_query.cu).  N > 1: every rank runs the same per-GPU workload on its
+own GPU (weak scaling, no data-path collective); NCCL only carries the barrier and the max-reduce of the
+elapsed time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--clips M] [--impl reference]
+
+Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FK+heightfield-obs body-frames/sec"
+UNIT = "body-frames/s"
+BODIES = 15
+RAY_POINTS = 441
+# algorithmic bytes of the fused query+FK+obs per character-frame
+BYTES_PER_CHAR_FRAME = 12 + 36 + 624 + 136 + 448 + 420 + 1764 + 1764   # = 5204
+HF_DIM = 1536
+HF_DX = 0.4
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--clips", type=int, default=2048)
+    ap.add_argument("--impl", default="parc_b200", choices=["parc_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"cfg2 tracker batch: {args.envs} envs/GPU x (frame query + FK 15 bodies + {RAY_POINTS}-pt ray "
+            f"heightmap obs), {args.clips} synthetic 265-frame clips, {HF_DIM}x{HF_DIM} hf @0.4m")
+
+
+def make_inputs(args, char_model, seed):
+    """Host-side synthetic inputs (numpy): clips, contacts, heightfield, ray template params."""
+    from parc_b200.util import synth
+    rng = np.random.default_rng(seed)
+    hf = synth.rolling_terrain(rng, HF_DIM, HF_DIM, num_boxes=6000)
+    frames, contacts = synth.synth_clips(char_model, args.clips, seed=seed + 1, hf=hf, min_xy=(0.0, 0.0),
+                                         dxdy=(HF_DX, HF_DX))
+    return hf, frames, contacts
+
+
+def query_batches(num_batches, envs, num_clips, clip_len, seed):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, num_clips, (num_batches, envs), generator=g, dtype=torch.int64)
+    times = torch.rand((num_batches, envs), generator=g, dtype=torch.float32) * clip_len
+    return ids, times
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = the upper half of the samples (the soak loop keeps the GPU busy for most of them)
+        busy = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(args, frames, contacts, hf, sample_clips=64):
+    """Returns (fn(ids, times) -> None, description).  The oracle (oracle/parc_oracle.py) is the CPU
+    restatement of the reference's torch op chain: calc_motion_frame -> forward_kinematics ->
+    _refresh_ray_obs_hfs, fp32 torch CPU tensors, all host threads."""
+    from oracle import parc_oracle as O
+    model = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
+    m = min(sample_clips, frames.shape[0])
+    tb = O.build_tables(model, [O.Clip(frames[i], contacts[i], 30.0, O.CLAMP, 1.0) for i in range(m)])
+    terr = O.Terrain(hf=torch.from_numpy(hf), min_point=torch.zeros(2), dxdy=torch.tensor([HF_DX, HF_DX]))
+    tmpl = O.cone_template(0.05, 2, 60, 3, 3, 0.26179938779)
+
+    def step(ids, times):
+        fr = O.calc_motion_frame(tb, ids % m, times)
+        bp, br = O.forward_kinematics(model, fr[0], fr[1], fr[4])
+        obs = O.ray_obs(terr, fr[0], O.calc_heading(fr[1]), tmpl)
+        return bp, br, obs
+
+    return step, f"oracle port, clip ids folded onto the first {m} clips (tables are gather-only)"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from parc_b200.anim.kin_char_model import KinCharModel
+    km = KinCharModel("cpu")
+    km.load_char_file(os.path.join(ROOT, "parc_b200", "assets", "humanoid.xml"))
+    small = argparse.Namespace(**vars(args))
+    small.clips = min(args.clips, 64)
+    hf, frames, contacts = make_inputs(small, km, seed=1234)
+    step, desc = cpu_reference_step_fn(small, frames, contacts, hf)
+    ids, times = query_batches(8, args.envs, small.clips, 264.0 / 30.0, seed=77)
+    steps = min(args.steps, 40)          # bounded: each step is a full ENVS-env pass (~0.1 s on 8 cores)
+    for w in range(min(args.warmup, 3)):
+        step(ids[w % 8], times[w % 8])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        step(ids[s % 8], times[s % 8])
+    dt = time.perf_counter() - t0
+    value = args.envs * BODIES * steps / dt
+    sample = f"{steps} steps of {args.envs} envs (full per-GPU batch) on CPU; {desc}"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "arm": "reference CPU path (oracle port; the reference is "
+                   "pure Python/torch and /root/reference is absent on the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    import __graft_entry__ as entry
+    from parc_b200 import ops
+    from parc_b200.anim.kin_char_model import KinCharModel
+    from parc_b200.anim.motion_lib import LoopMode, MotionLib
+    from parc_b200.util import geom_util
+    from parc_b200.util.terrain_util import SubTerrain
+    entry.ensure_built()
+
+    km = KinCharModel(dev)
+    km.load_char_file(os.path.join(ROOT, "parc_b200", "assets", "humanoid.xml"))
+    hf_np, frames, contacts = make_inputs(args, km, seed=1234)
+    mlib = MotionLib(torch.from_numpy(frames), km, dev, init_type="motion_frames", loop_mode=LoopMode.CLAMP, fps=30,
+                     contact_info=True, contacts=torch.from_numpy(contacts))
+    terrain = SubTerrain("global", x_dim=HF_DIM, y_dim=HF_DIM, dx=HF_DX, dy=HF_DX, min_x=0.0, min_y=0.0, device=dev)
+    terrain.hf = torch.from_numpy(hf_np).to(dev)
+    hfd = terrain.hf_desc()
+    tmpl = geom_util.get_xy_points_cone(center=torch.zeros(2, device=dev), dx=0.05, num_neg=2, num_pos=60,
+                                        num_rays_neg=3, num_rays_pos=3, angle_between_rays=0.26179938779)
+    assert tmpl.shape[0] == RAY_POINTS
+
+    NB = 16                                           # distinct query batches, resident in HBM
+    ids_h, times_h = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77 + rank)
+    ids_d, times_d = ids_h.to(dev), times_h.to(dev)
+    out = {}
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        mlib.calc_motion_frame_fk_obs(ids_d[i % NB], times_d[i % NB], hf_desc=hfd, obs_tmpl=tmpl, out=out)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    for w in range(max(args.warmup, 3)):
+        flush.zero_()
+        step(w)
+
+    # ---- kernel-resident timing: inputs in HBM, L2 flushed between steps, CUDA events per step ----
+    K = args.steps
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    launches0 = ops_launch_count()
+    for s in range(K):
+        flush.zero_()                                  # evict L2 (not timed)
+        starts[s].record(stream)
+        step(s)
+        stops[s].record(stream)
+    launches = ops_launch_count() - launches0
+    barrier()
+    per_step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    elapsed_ms = sum(per_step_ms)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms_max = t.item()
+    total_envs = args.envs * world
+    value = total_envs * BODIES * K / (elapsed_ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the region ----
+    ids_p, times_p = ids_h.pin_memory(), times_h.pin_memory()
+    ids_in = torch.empty(args.envs, dtype=torch.int64, device=dev)
+    times_in = torch.empty(args.envs, dtype=torch.float32, device=dev)
+    e2e_out = {}
+    keys = ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts", "body_pos",
+            "body_rot", "obs")
+    host_out = None
+
+    def e2e_step(i):
+        nonlocal host_out
+        ids_in.copy_(ids_p[i % NB], non_blocking=True)
+        times_in.copy_(times_p[i % NB], non_blocking=True)
+        r = mlib.calc_motion_frame_fk_obs(ids_in, times_in, hf_desc=hfd, obs_tmpl=tmpl, out=e2e_out)
+        if host_out is None:
+            host_out = {k: torch.empty(r[k].shape, dtype=r[k].dtype).pin_memory() for k in keys}
+        for k in keys:
+            host_out[k].copy_(r[k], non_blocking=True)
+        stream.synchronize()                            # the caller reads the result on the host
+
+    for w in range(3):
+        e2e_step(w)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        e2e_step(s)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_envs * BODIES * K / t.item()
+    h2d = args.envs * (8 + 4)
+    d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in keys)
+
+    # ---- soak: keep the kernel running ~1.5 s so the clock sampler sees the GPU under this load ----
+    t_end = time.perf_counter() + 1.5
+    i = 0
+    while time.perf_counter() < t_end:
+        for _ in range(200):
+            step(i)
+            i += 1
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth, burst)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    avg_launch_s = (sum(per_step_ms) / K) * 1e-3
+    alg_bytes = args.envs * BYTES_PER_CHAR_FRAME
+    achieved = alg_bytes / avg_launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("envs") == args.envs:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "parc::motion_query_kernel<true>",
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "median_launch_us": statistics.median(per_step_ms) * 1e3}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        fn, desc = cpu_reference_step_fn(args, frames, contacts, hf_np)
+        fn(ids_h[0], times_h[0])
+        best = float("inf")
+        reps = 5
+        for r in range(reps):
+            t0 = time.perf_counter()
+            fn(ids_h[r % NB], times_h[r % NB])
+            best = min(best, time.perf_counter() - t0)
+        cpu_baseline = {"value": args.envs * BODIES / best, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"best of {reps} full {args.envs}-env steps after 1 warm-up; {desc}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "envs_per_gpu": args.envs, "clips": args.clips,
+                   "frames_per_clip": 265, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write); "
+                   "frame table 260 MB > L2", "timing": "CUDA events per step on the launch stream, max over ranks"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ops_launch_count():
+    from parc_b200 import _lib
+    return _lib.LAUNCHES[0]
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,348 @@
+"""Generate tests/golden/*.npz from the REAL reference and pin the oracle against it.
+
+TEST INFRASTRUCTURE; runs only in the authoring container (needs /root/reference):
+    python -m oracle.make_golden
+Every fixture below is an output of the imported reference's own functions on CPU (torch fp32).  While
+generating, the oracle restatement (oracle/parc_oracle.py) is run on the same inputs and must match the
+reference BIT-EXACTLY (torch.equal); any mismatch aborts.  The summary is written to
+tests/golden/PIN_REPORT.txt.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.activate()
+import anim.kin_char_model as ref_kcm  # noqa: E402
+import anim.motion_lib as ref_mlib  # noqa: E402
+import util.geom_util as ref_geom  # noqa: E402
+import util.terrain_util as ref_terrain  # noqa: E402
+import util.torch_util as ref_tu  # noqa: E402
+import util.motion_util as ref_mu  # noqa: E402
+import tools.procgen.mdm_path as ref_mdm_path  # noqa: E402
+import tools.motion_opt.motion_optimization as ref_mopt  # noqa: E402
+
+from oracle import parc_oracle as O  # noqa: E402
+
+REPORT = []
+
+
+def pin(name, ref, mine):
+    ref = torch.as_tensor(ref)
+    mine = torch.as_tensor(mine)
+    same = ref.shape == mine.shape and torch.equal(ref, mine)
+    if not same:
+        both_nan = torch.isnan(ref) & torch.isnan(mine) if ref.is_floating_point() else torch.zeros_like(ref, dtype=torch.bool)
+        same = ref.shape == mine.shape and bool(((ref == mine) | both_nan).all())
+    REPORT.append(f"{'OK ' if same else 'FAIL'} {name} shape={tuple(ref.shape)}")
+    if not same:
+        diff = (ref.double() - mine.double()).abs().max().item() if ref.shape == mine.shape else float('nan')
+        print("\n".join(REPORT))
+        raise SystemExit(f"oracle != reference for {name}: max abs diff {diff}")
+
+
+def npf(t):
+    return t.detach().cpu().numpy()
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    os.makedirs(GOLD, exist_ok=True)
+    ref_root = ref_shim.REFERENCE_ROOT
+
+    # ------------------------------------------------------------------ 1. character model
+    km = ref_kcm.KinCharModel("cpu")
+    km.load_char_file(os.path.join(ref_root, "data/assets/humanoid.xml"))
+    body_points = ref_geom.get_char_point_samples(km)
+    min_points = ref_geom.get_minimal_char_point_samples(km)
+    J = km.get_num_joints()
+    jt = [km._joints[j].joint_type.value for j in range(J)]
+    axes = np.zeros((J, 3), np.float32)
+    for j in range(J):
+        if km._joints[j].axis is not None:
+            axes[j] = npf(km._joints[j].axis)
+    geom_rows = []
+    for b in range(J):
+        for g in km.get_geoms(b):
+            d = npf(g._dims).reshape(-1)
+            d3 = np.zeros(3, np.float32)
+            d3[:d.shape[0]] = d
+            geom_rows.append([b, g._shape_type.value, *npf(g._offset).tolist(), *d3.tolist(),
+                              -1.0 if g._radius is None else float(g._radius)])
+    np.savez_compressed(
+        os.path.join(GOLD, "humanoid_model.npz"),
+        body_names=np.array(km._body_names), parents=npf(km._parent_indices),
+        local_translation=npf(km._local_translation), local_rotation=npf(km._local_rotation),
+        joint_type=np.array(jt, np.int64), joint_axis=axes,
+        dof_idx=np.array([km._joints[j].dof_idx for j in range(J)], np.int64),
+        dof_dim=np.array([km._joints[j].get_dof_dim() for j in range(J)], np.int64),
+        lower_dof_limits=npf(km._lower_dof_limits), upper_dof_limits=npf(km._upper_dof_limits),
+        body_points=npf(torch.cat(body_points, 0)), body_point_counts=np.array([p.shape[0] for p in body_points]),
+        min_body_points=npf(torch.cat(min_points, 0)),
+        min_body_point_counts=np.array([p.shape[0] for p in min_points]),
+        geoms=np.array(geom_rows, np.float32))
+    model = O.CharModel.from_npz(os.path.join(GOLD, "humanoid_model.npz"))
+
+    # ------------------------------------------------------------------ 2. the two in-repo clips
+    clips_raw = {}
+    for name in ("civilization", "TEASER_TERRAIN"):
+        with open(os.path.join(ref_root, "data/terrains", name + ".pkl"), "rb") as f:
+            d = pickle.load(f)
+        t = d["terrain"]
+        t.update_old()
+        t.to_torch("cpu")
+        fps = d.get("fps", 30)
+        fps = fps.item() if isinstance(fps, np.ndarray) else fps
+        clips_raw[name] = dict(frames=np.asarray(d["frames"], np.float32), contacts=np.asarray(d["contacts"], np.float32),
+                               hf=npf(t.hf), min_point=npf(t.min_point), dxdy=npf(t.dxdy), fps=float(fps),
+                               loop_mode=d.get("loop_mode", "CLAMP"))
+        np.savez_compressed(os.path.join(GOLD, f"clip_{name.lower()}.npz"), **{
+            k: (np.array(v) if not isinstance(v, np.ndarray) else v) for k, v in clips_raw[name].items()})
+
+    # a library of 3 clips: civilization (CLAMP), teaser played as WRAP, civilization's first 40 frames as WRAP@60fps
+    tmp = tempfile.mkdtemp()
+    lib_spec = [("civilization", clips_raw["civilization"]["frames"], clips_raw["civilization"]["contacts"], 30.0, "CLAMP", 1.0),
+                ("teaser_wrap", clips_raw["TEASER_TERRAIN"]["frames"], clips_raw["TEASER_TERRAIN"]["contacts"], 30.0, "WRAP", 2.0),
+                ("civ_short", clips_raw["civilization"]["frames"][:40], clips_raw["civilization"]["contacts"][:40], 60.0, "WRAP", 0.5)]
+    yaml_lines = ["motions:"]
+    for nm, fr, ct, fps, loop, w in lib_spec:
+        path = os.path.join(tmp, nm + ".pkl")
+        with open(path, "wb") as f:
+            pickle.dump({"frames": fr, "contacts": ct, "fps": fps, "loop_mode": loop}, f)
+        yaml_lines += [f"- file: {path}", f"  weight: {w}"]
+    ypath = os.path.join(tmp, "lib.yaml")
+    with open(ypath, "w") as f:
+        f.write("\n".join(yaml_lines) + "\n")
+    mlib = ref_mlib.MotionLib(ypath, km, "cpu", init_type="motion_file", contact_info=True)
+
+    tb = O.build_tables(model, [O.Clip(fr, ct, fps, O.WRAP if loop == "WRAP" else O.CLAMP, w)
+                                for _, fr, ct, fps, loop, w in lib_spec])
+    for k_ref, k_o in [("_frame_root_pos", "root_pos"), ("_frame_root_rot", "root_rot"), ("_frame_joint_rot", "joint_rot"),
+                       ("_frame_root_vel", "root_vel"), ("_frame_root_ang_vel", "root_ang_vel"),
+                       ("_frame_dof_vel", "dof_vel"), ("_frame_contacts", "contacts"), ("_motion_frames", "frames"),
+                       ("_motion_num_frames", "num_frames"), ("_motion_start_idx", "start_idx"),
+                       ("_motion_lengths", "lengths"), ("_motion_loop_modes", "loop_modes"),
+                       ("_motion_root_pos_delta", "root_pos_delta"), ("_motion_weights", "weights")]:
+        pin("tables." + k_o, getattr(mlib, k_ref), getattr(tb, k_o))
+    np.savez_compressed(os.path.join(GOLD, "tables_golden.npz"),
+                        lib_fps=np.array([s[3] for s in lib_spec]), lib_loop=np.array([s[4] for s in lib_spec]),
+                        lib_weight=np.array([s[5] for s in lib_spec]), lib_short_frames=np.array(40),
+                        root_rot=npf(mlib._frame_root_rot), joint_rot=npf(mlib._frame_joint_rot),
+                        root_vel=npf(mlib._frame_root_vel), root_ang_vel=npf(mlib._frame_root_ang_vel),
+                        dof_vel=npf(mlib._frame_dof_vel), lengths=npf(mlib._motion_lengths),
+                        start_idx=npf(mlib._motion_start_idx), root_pos_delta=npf(mlib._motion_root_pos_delta),
+                        weights=npf(mlib._motion_weights))
+
+    # the motion_frames loader (with its fps-as-dt quirk, anim/motion_lib.py:178)
+    mf = torch.tensor(np.stack([clips_raw["civilization"]["frames"][:30], clips_raw["civilization"]["frames"][100:130]]))
+    mc = torch.tensor(np.stack([clips_raw["civilization"]["contacts"][:30], clips_raw["civilization"]["contacts"][100:130]]))
+    mlib2 = ref_mlib.MotionLib(mf, km, "cpu", init_type="motion_frames", loop_mode=ref_mlib.LoopMode.CLAMP, fps=30,
+                               contact_info=True, contacts=mc)
+    np.savez_compressed(os.path.join(GOLD, "tables_motion_frames_golden.npz"), frames=npf(mf), contacts=npf(mc),
+                        root_rot=npf(mlib2._frame_root_rot), joint_rot=npf(mlib2._frame_joint_rot),
+                        root_vel=npf(mlib2._frame_root_vel), root_ang_vel=npf(mlib2._frame_root_ang_vel),
+                        dof_vel=npf(mlib2._frame_dof_vel), root_pos_delta=npf(mlib2._motion_root_pos_delta),
+                        lengths=npf(mlib2._motion_lengths))
+
+    # ------------------------------------------------------------------ 3. frame queries + FK
+    g = torch.Generator().manual_seed(7)
+    lens = mlib._motion_lengths
+    edge_ids = torch.tensor([0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2], dtype=torch.long)
+    edge_t = torch.tensor([0.0, 8.4333, 8.5, 100.0, -1.0, 4.2,
+                           0.0, lens[1].item(), lens[1].item() * 2.5, -0.7, 1.0 / 30.0,
+                           0.0, lens[2].item() * 7.25, -lens[2].item() * 1.5, 0.3], dtype=torch.float32)
+    rnd_ids = torch.randint(0, 3, (241,), generator=g)
+    rnd_t = (torch.rand(241, generator=g) * 1.6 - 0.3) * lens[rnd_ids]
+    # exact key-frame times (blend == 0 and the i/fps rounding cases)
+    key_ids = torch.zeros(44, dtype=torch.long)
+    key_t = torch.arange(44, dtype=torch.float32) * 6.0 / 30.0
+    ids = torch.cat([edge_ids, rnd_ids, key_ids])
+    times = torch.cat([edge_t, rnd_t, key_t])
+    i0, i1, bl = mlib._calc_frame_blend(ids, times)
+    fr = mlib.calc_motion_frame(ids, times)
+    body_pos, body_rot = km.forward_kinematics(fr[0], fr[1], fr[4])
+    o_i0, o_i1, o_bl = O.frame_blend(tb, ids, times)
+    o_fr = O.calc_motion_frame(tb, ids, times)
+    o_bp, o_br = O.forward_kinematics(model, o_fr[0], o_fr[1], o_fr[4])
+    pin("query.idx0", i0, o_i0); pin("query.idx1", i1, o_i1); pin("query.blend", bl, o_bl)
+    for nm, a, b in zip(("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts"), fr, o_fr):
+        pin("query." + nm, a, b)
+    pin("fk.body_pos", body_pos, o_bp); pin("fk.body_rot", body_rot, o_br)
+    pin("query.phase", mlib.calc_motion_phase(ids, times), O.motion_phase(tb, ids, times))
+    fidx = torch.randint(0, 40, (64,), generator=g)
+    fids = torch.randint(0, 3, (64,), generator=g)
+    gf = mlib.get_motion_frame(fids, fidx)
+    for nm, a, b in zip(("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts"), gf,
+                        O.get_motion_frame(tb, fids, fidx)):
+        pin("get_frame." + nm, a, b)
+    np.savez_compressed(os.path.join(GOLD, "query_golden.npz"), ids=npf(ids), times=npf(times), idx0=npf(i0), idx1=npf(i1),
+                        blend=npf(bl), root_pos=npf(fr[0]), root_rot=npf(fr[1]), root_vel=npf(fr[2]),
+                        root_ang_vel=npf(fr[3]), joint_rot=npf(fr[4]), dof_vel=npf(fr[5]), contacts=npf(fr[6]),
+                        body_pos=npf(body_pos), body_rot=npf(body_rot), get_ids=npf(fids), get_fidx=npf(fidx),
+                        get_root_pos=npf(gf[0]), get_joint_rot=npf(gf[4]), get_dof_vel=npf(gf[5]),
+                        get_contacts=npf(gf[6]))
+
+    # dof_to_rot / rot_to_dof / exp_map_to_quat on the clip's own frames
+    frames_t = torch.tensor(clips_raw["civilization"]["frames"])
+    jr = km.dof_to_rot(frames_t[:, 6:])
+    pin("dof_to_rot", jr, O.dof_to_rot(model, frames_t[:, 6:]))
+    pin("rot_to_dof", km.rot_to_dof(jr), O.rot_to_dof(model, jr))
+    rq = ref_tu.exp_map_to_quat(frames_t[:, 3:6])
+    pin("exp_map_to_quat", rq, O.exp_map_to_quat(frames_t[:, 3:6]))
+    np.savez_compressed(os.path.join(GOLD, "dof_golden.npz"), joint_rot=npf(jr), root_quat=npf(rq),
+                        dof_back=npf(km.rot_to_dof(jr)))
+
+    # ------------------------------------------------------------------ 4. heightfield observations
+    civ = clips_raw["civilization"]
+    terr = ref_terrain.SubTerrain("t", x_dim=50, y_dim=50, dx=0.4, dy=0.4, min_x=0.0, min_y=0.0, device="cpu")
+    terr.hf = torch.tensor(civ["hf"]); terr.min_point = torch.tensor(civ["min_point"]); terr.dxdy = torch.tensor(civ["dxdy"])
+    ot = O.Terrain(hf=terr.hf, min_point=terr.min_point, dxdy=terr.dxdy)
+    tmpl = ref_geom.get_xy_points_cone(center=torch.zeros(2), dx=0.05, num_neg=2, num_pos=60, num_rays_neg=3,
+                                       num_rays_pos=3, angle_between_rays=0.26179938779)
+    pin("cone_template", tmpl, O.cone_template(0.05, 2, 60, 3, 3, 0.26179938779))
+    sel = torch.arange(0, 254, 4)
+    root_pos_sel = fr_root = torch.tensor(civ["frames"][sel.numpy(), 0:3])
+    root_q_sel = ref_tu.exp_map_to_quat(torch.tensor(civ["frames"][sel.numpy(), 3:6]))
+    heading = ref_tu.calc_heading(root_q_sel)
+    pin("calc_heading", heading, O.calc_heading(root_q_sel))
+
+    # restated env method (envs/ig_parkour/mgdm_dm_util.py:158-179) composed from the REAL reference functions
+    def ref_ray_obs(root_xyz, hd):
+        n = root_xyz.shape[0]
+        rp = tmpl.unsqueeze(0).expand(n, -1, -1)
+        h = hd.unsqueeze(-1).expand(-1, rp.shape[1])
+        xy = ref_tu.rotate_2d_vec(rp, h) + root_xyz[..., 0:2].unsqueeze(1)
+        xy = xy.view(-1, 2)
+        z = ref_terrain.get_local_hf_from_terrain(xy, terr).view(n, -1)
+        return torch.clamp(z - root_xyz[..., 2].unsqueeze(-1), min=-3.0, max=3.0), xy
+
+    obs, obs_xy = ref_ray_obs(root_pos_sel, heading)
+    pin("ray_obs", obs, O.ray_obs(ot, root_pos_sel, heading, tmpl))
+    gi = terr.get_grid_index(obs_xy)
+    pin("grid_index", gi, O.grid_index(ot, obs_xy))
+    probe_xy = torch.tensor([[0.2, 0.6], [-5.0, 3.0], [100.0, 0.19999], [0.6, 1.0], [19.6, 19.8], [1.0, 1.4]])
+    pin("grid_index.probe", terr.get_grid_index(probe_xy), O.grid_index(ot, probe_xy))
+    gobs = ref_terrain.sample_hf_z_on_terrain(terr, root_pos_sel[:16, 0:2], heading[:16], 0.2, 0.2, 15, 15, 15, 15)
+    gt = O.grid_template(0.2, 0.2, 15, 15, 15, 15)
+    pin("grid_obs", gobs, O.grid_obs(ot, root_pos_sel[:16, 0:2], heading[:16], gt))
+    np.savez_compressed(os.path.join(GOLD, "obs_golden.npz"), tmpl=npf(tmpl), root_pos=npf(root_pos_sel),
+                        root_quat=npf(root_q_sel), heading=npf(heading), ray_obs=npf(obs), ray_xy=npf(obs_xy),
+                        ray_grid_index=npf(gi), ray_grid_coord=npf(O.grid_coord(ot, obs_xy)),
+                        probe_xy=npf(probe_xy), probe_index=npf(terr.get_grid_index(probe_xy)),
+                        grid_obs=npf(gobs), grid_tmpl=npf(gt))
+
+    # ------------------------------------------------------------------ 5. SDF + losses
+    # (a) the survey's 4x4 probe
+    hf4 = torch.zeros(1, 4, 4); hf4[0, 2, 2] = 1.0
+    pts4 = torch.tensor([[[0.8, 0.8, 0.5], [0.8, 0.8, 1.5], [0.0, 0.0, -0.3], [5.0, 5.0, 0.5], [0.4, 0.6, 0.2]]])
+    mc4 = torch.zeros(1, 2); dxdy = torch.tensor([0.4, 0.4])
+    sd4_inv = ref_terrain.points_hf_sdf(pts4, hf4, mc4, dxdy, base_z=-10.0, inverted=True)
+    sd4_sol = ref_terrain.points_hf_sdf(pts4, hf4, mc4, dxdy, base_z=-10.0, inverted=False)
+    pin("sdf.probe.inv", sd4_inv, O.points_hf_sdf(pts4, hf4, mc4, dxdy, -10.0, True))
+    pin("sdf.probe.sol", sd4_sol, O.points_hf_sdf(pts4, hf4, mc4, dxdy, -10.0, False))
+    # (b) body points of 6 clip frames against the clip's 50x50 terrain
+    fsel = [0, 50, 100, 150, 200, 250]
+    rp6 = torch.tensor(civ["frames"][fsel, 0:3]); rq6 = ref_tu.exp_map_to_quat(torch.tensor(civ["frames"][fsel, 3:6]))
+    jr6 = km.dof_to_rot(torch.tensor(civ["frames"][fsel, 6:]))
+    bp6, br6 = km.forward_kinematics(rp6, rq6, jr6)
+    wp = torch.cat([ref_tu.quat_rotate(br6[:, b].unsqueeze(1), body_points[b].unsqueeze(0)) + bp6[:, b].unsqueeze(1)
+                    for b in range(J)], dim=1).reshape(1, -1, 3)
+    hfb = terr.hf.unsqueeze(0); mcb = terr.min_point.unsqueeze(0)
+    sdf_inv = ref_terrain.points_hf_sdf(wp, hfb, mcb, terr.dxdy, base_z=-10.0, inverted=True)
+    sdf_sol = ref_terrain.points_hf_sdf(wp, hfb, mcb, terr.dxdy, base_z=-10.0, inverted=False)
+    pin("sdf.clip.inv", sdf_inv, O.points_hf_sdf(wp, hfb, mcb, terr.dxdy, -10.0, True))
+    pin("sdf.clip.sol", sdf_sol, O.points_hf_sdf(wp, hfb, mcb, terr.dxdy, -10.0, False))
+    np.savez_compressed(os.path.join(GOLD, "sdf_golden.npz"), probe_points=npf(pts4), probe_hf=npf(hf4),
+                        probe_inv=npf(sd4_inv), probe_sol=npf(sd4_sol), clip_points=npf(wp), clip_inv=npf(sdf_inv),
+                        clip_sol=npf(sdf_sol))
+
+    # (c) compute_motion_loss, B=2, F=10 (frames 60..69 and 200..209, second one sunk 0.15 m so it penetrates)
+    def mf_batch(starts, F, dz):
+        rp = torch.stack([torch.tensor(civ["frames"][s:s + F, 0:3]) for s in starts])
+        for i, d in enumerate(dz):
+            rp[i, :, 2] += d
+        rq = torch.stack([ref_tu.exp_map_to_quat(torch.tensor(civ["frames"][s:s + F, 3:6])) for s in starts])
+        jr = torch.stack([km.dof_to_rot(torch.tensor(civ["frames"][s:s + F, 6:])) for s in starts])
+        ct = torch.stack([torch.tensor(civ["contacts"][s:s + F]) for s in starts])
+        return rp, rq, jr, ct
+
+    rp, rq, jr, ct = mf_batch([60, 200], 10, [0.0, -0.15])
+    ct = ct.clone(); ct[0, 3, 11] = -0.02          # a small negative contact, as MDM output can have
+    mframes = ref_mu.MotionFrames(root_pos=rp, root_rot=rq, joint_rot=jr, contacts=ct)
+    ml = ref_mdm_path.compute_motion_loss(mframes, None, terr, km, body_points, w_contact=0.1, w_pen=0.1, w_path=0.0,
+                                          verbose=False)
+    oml = O.compute_motion_loss(model, rp, rq, jr, ct, terr.hf, terr.min_point, terr.dxdy, 0.1, 0.1)
+    for k in ("total_loss", "contact_loss", "pen_loss"):
+        pin("compute_motion_loss." + k, ml[k], oml[k])
+
+    # (d) motion_terrain_contact_loss, F=8 frames 200..207 sunk by 0.12 m: value + gradients of the leaves
+    F = 8
+    s = 200
+    tgt_rp = torch.tensor(civ["frames"][s:s + F, 0:3]).clone(); tgt_rp[:, 2] -= 0.12
+    tgt_re = torch.tensor(civ["frames"][s:s + F, 3:6]).clone()
+    tgt_jd = torch.tensor(civ["frames"][s:s + F, 6:]).clone()
+    cts = torch.tensor(civ["contacts"][s:s + F]).clone()
+    src_rp = tgt_rp.clone() + 0.01
+    src_rq = ref_tu.exp_map_to_quat(tgt_re * 1.05)
+    src_jr = km.dof_to_rot(tgt_jd * 0.97)
+    sbp, sbr = km.forward_kinematics(src_rp, src_rq, src_jr)
+    src_bv = sbp[1:] - sbp[:-1]
+    src_brv = ref_tu.quat_diff_angle(sbr[1:], sbr[:-1])
+
+    def run_ref(w_pen, w_con, others):
+        a, b, c = (t.clone().requires_grad_(True) for t in (tgt_rp, tgt_re, tgt_jd))
+        loss, ld = ref_mopt.motion_terrain_contact_loss(
+            a, b, c, src_rp, src_rq, src_jr, src_bv, src_brv, cts, terr, body_points, km,
+            w_root_pos=others, w_root_rot=others, w_joint_rot=others, w_smoothness=others, w_penetration=w_pen,
+            w_contact=w_con, w_sliding=others, w_body_constraints=0.0, w_jerk=others, body_constraints=None,
+            max_jerk=1000.0)
+        loss.backward()
+        return loss.detach(), ld, a.grad, b.grad, c.grad
+
+    loss_pc, ld_pc, g_rp, g_re, g_jd = run_ref(1000.0, 1000.0, 0.0)
+    a, b, c = (t.clone().requires_grad_(True) for t in (tgt_rp, tgt_re, tgt_jd))
+    o_loss, o_pen, o_con = O.motion_opt_pen_contact(model, a, b, c, cts, terr.hf, terr.min_point, terr.dxdy, 1000.0, 1000.0)
+    o_loss.backward()
+    pin("motion_opt.loss(pen+contact)", loss_pc, o_loss.detach())
+    pin("motion_opt.pen", torch.tensor(ld_pc[ref_mopt.LossType.PENETRATION_LOSS]), o_pen.detach())
+    pin("motion_opt.grad_root_pos", g_rp, a.grad); pin("motion_opt.grad_root_rot", g_re, b.grad)
+    pin("motion_opt.grad_joint_dof", g_jd, c.grad)
+    loss_all, ld_all, ga_rp, ga_re, ga_jd = run_ref(1000.0, 1000.0, 1.0)
+    np.savez_compressed(
+        os.path.join(GOLD, "loss_golden.npz"),
+        ml_root_pos=npf(rp), ml_root_rot=npf(rq), ml_joint_rot=npf(jr), ml_contacts=npf(ct),
+        ml_total=npf(ml["total_loss"]), ml_contact=npf(ml["contact_loss"]), ml_pen=npf(ml["pen_loss"]),
+        mo_root_pos=npf(tgt_rp), mo_root_exp=npf(tgt_re), mo_joint_dof=npf(tgt_jd), mo_contacts=npf(cts),
+        mo_src_root_pos=npf(src_rp), mo_src_root_quat=npf(src_rq), mo_src_joint_rot=npf(src_jr),
+        mo_src_body_vels=npf(src_bv), mo_src_body_rot_vels=npf(src_brv),
+        mo_loss_pc=npf(loss_pc), mo_pen=np.array(ld_pc[ref_mopt.LossType.PENETRATION_LOSS]),
+        mo_contact=np.array(float(ld_pc[ref_mopt.LossType.CONTACT_LOSS])),
+        mo_grad_root_pos=npf(g_rp), mo_grad_root_exp=npf(g_re), mo_grad_joint_dof=npf(g_jd),
+        mo_loss_all=npf(loss_all), mo_all_grad_root_pos=npf(ga_rp), mo_all_grad_root_exp=npf(ga_re),
+        mo_all_grad_joint_dof=npf(ga_jd),
+        mo_all_terms=np.array([float(ld_all[k]) for k in ref_mopt.LossType if k in ld_all], np.float64),
+        mo_all_term_names=np.array([k.name for k in ref_mopt.LossType if k in ld_all]))
+
+    with open(os.path.join(GOLD, "PIN_REPORT.txt"), "w") as f:
+        f.write("oracle/parc_oracle.py vs the imported reference (torch %s, CPU, fp32) -- torch.equal on every line\n"
+                % torch.__version__)
+        f.write("\n".join(REPORT) + "\n")
+    print("\n".join(REPORT))
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

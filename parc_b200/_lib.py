@@ -1,0 +1,172 @@
+"""ctypes binding of libparc_b200.so (the C ABI declared in include/parc_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or an operator is handed a
+tensor that is not on a CUDA device, the call raises.  PyTorch is used for device memory and streams
+only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libparc_b200.so")
+
+PARC_MAX_BODIES = 24
+PARC_MAX_DOF = 96
+
+JOINT_ROOT, JOINT_HINGE, JOINT_SPHERICAL, JOINT_FIXED = 0, 1, 2, 3
+LOOP_CLAMP, LOOP_WRAP = 0, 1
+
+c_float_p = C.POINTER(C.c_float)
+c_i64_p = C.POINTER(C.c_int64)
+c_i32_p = C.POINTER(C.c_int32)
+
+
+class ParcCharModel(C.Structure):
+    _fields_ = [
+        ("num_bodies", C.c_int32), ("dof_size", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32),
+        ("parent", C.c_int32 * PARC_MAX_BODIES), ("depth", C.c_int32 * PARC_MAX_BODIES),
+        ("joint_type", C.c_int32 * PARC_MAX_BODIES), ("dof_idx", C.c_int32 * PARC_MAX_BODIES),
+        ("local_trans", (C.c_float * 3) * PARC_MAX_BODIES),
+        ("local_rot", (C.c_float * 4) * PARC_MAX_BODIES),
+        ("joint_axis", (C.c_float * 3) * PARC_MAX_BODIES),
+    ]
+
+
+class ParcRowLayout(C.Structure):
+    _fields_ = [("row_floats", C.c_int32), ("pose_slots", C.c_int32), ("contact_slot", C.c_int32),
+                ("vel_slot", C.c_int32), ("vel_slots", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class ParcClipMeta(C.Structure):
+    _fields_ = [("num_frames", C.c_int32), ("loop_mode", C.c_int32), ("start_idx", C.c_int64),
+                ("length", C.c_float), ("root_pos_delta", C.c_float * 3)]
+
+
+class ParcMotionTables(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("clips", C.c_void_p), ("total_frames", C.c_int64),
+                ("num_clips", C.c_int64), ("row_floats", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ParcFrameOut(C.Structure):
+    _fields_ = [("root_pos", C.c_void_p), ("root_rot", C.c_void_p), ("root_vel", C.c_void_p),
+                ("root_ang_vel", C.c_void_p), ("joint_rot", C.c_void_p), ("dof_vel", C.c_void_p),
+                ("contacts", C.c_void_p), ("frame_idx0", C.c_void_p), ("frame_idx1", C.c_void_p),
+                ("blend", C.c_void_p)]
+
+
+class ParcFkOut(C.Structure):
+    _fields_ = [("body_pos", C.c_void_p), ("body_rot", C.c_void_p)]
+
+
+class ParcHeightfield(C.Structure):
+    _fields_ = [("hf", C.c_void_p), ("dim_x", C.c_int32), ("dim_y", C.c_int32), ("min_x", C.c_float),
+                ("min_y", C.c_float), ("dx", C.c_float), ("dy", C.c_float)]
+
+
+class ParcObsSpec(C.Structure):
+    _fields_ = [("tmpl_xy", C.c_void_p), ("num_points", C.c_int32), ("relative", C.c_int32),
+                ("min_h", C.c_float), ("max_h", C.c_float)]
+
+
+class ParcTerrainBatch(C.Structure):
+    _fields_ = [("hf", C.c_void_p), ("hf_batch_stride", C.c_int64), ("min_center", C.c_void_p),
+                ("x_nodes", C.c_void_p), ("y_nodes", C.c_void_p), ("base_z", C.c_void_p),
+                ("dim_x", C.c_int32), ("dim_y", C.c_int32), ("min_center_stride", C.c_int32),
+                ("base_z_stride", C.c_int32), ("half_dx", C.c_float), ("half_dy", C.c_float),
+                ("base_z_value", C.c_float), ("reserved", C.c_int32)]
+
+
+class ParcBodyPoints(C.Structure):
+    _fields_ = [("points", C.c_void_p), ("point_start", C.c_void_p), ("num_points", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/parc_b200.h declares
+_V, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+_P = C.POINTER
+SIGNATURES = {
+    "parc_abi_version": (C.c_int, []),
+    "parc_error_string": (C.c_char_p, [C.c_int]),
+    "parc_row_layout": (C.c_int, [_P(ParcCharModel), _P(ParcRowLayout)]),
+    "parc_validate_model": (C.c_int, [_P(ParcCharModel)]),
+    "parc_pack_frames": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V]),
+    "parc_motion_query": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel), _P(ParcFrameOut),
+                                    _P(ParcFkOut), _P(ParcHeightfield), _P(ParcObsSpec), _V, _V]),
+    "parc_get_motion_frame": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel),
+                                        _P(ParcFrameOut), _P(ParcFkOut), _V]),
+    "parc_fk_fwd": (C.c_int, [_V, _V, _V, _I64, _P(ParcCharModel), _V, _V, _V]),
+    "parc_fk_bwd": (C.c_int, [_V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V, _V, _V]),
+    "parc_dof_to_rot_fwd": (C.c_int, [_V, _I64, _P(ParcCharModel), _V, _V]),
+    "parc_dof_to_rot_bwd": (C.c_int, [_V, _V, _I64, _P(ParcCharModel), _V, _V]),
+    "parc_exp_map_to_quat_fwd": (C.c_int, [_V, _I64, _V, _V]),
+    "parc_exp_map_to_quat_bwd": (C.c_int, [_V, _V, _I64, _V, _V]),
+    "parc_hf_sample": (C.c_int, [_P(ParcHeightfield), _V, _I64, _V, _V, _V]),
+    "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _I64, _V, _V]),
+    "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
+    "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
+                                 _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class ParcLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen libparc_b200.so and bind every declared symbol.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ParcLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or parc_b200/csrc/build.sh -- there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+# number of kernel-launching C-ABI calls made by this process (bench.py reports it as gpu_launches)
+LAUNCHES = [0]
+_HOST_ONLY = {"parc_validate_model", "parc_row_layout"}
+
+
+def check(rc: int, what: str):
+    if what not in _HOST_ONLY:
+        LAUNCHES[0] += 1
+    if rc != 0:
+        msg = load().parc_error_string(rc).decode()
+        raise ParcLibraryError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ParcLibraryError("parc_b200 operators need CUDA tensors (no CPU fallback); got a "
+                                   f"{t.device} tensor")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()

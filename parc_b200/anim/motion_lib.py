@@ -1,0 +1,374 @@
+"""MotionLib: packed per-frame tables for all clips + batched (clip id, time) -> frame queries.
+
+Drop-in for the reference's `anim/motion_lib.py` (class `MotionLib`, `LoopMode`): same constructor
+signature, method names, return tuples and public attributes (:22-40, :48-131, :443-475).  What differs
+is underneath: the eight per-frame tables are interleaved into one row of float4 slots per frame
+(include/parc_b200.h, ParcRowLayout) and a query is ONE launch of the fused sm_100a kernel in
+csrc/motion_query.cu (one warp per query) instead of ~180 eager torch ops.
+
+Loading (`_load_motions`, `_load_motion_frames`) is host-side: tables are built with torch ops on the
+CPU, in the reference's operation order, then uploaded and packed on the GPU.
+"""
+from __future__ import annotations
+
+import copy
+import enum
+import io
+import os
+import pickle
+
+import numpy as np
+import torch
+import yaml
+
+from .. import ops
+from ..util import torch_util
+from .kin_char_model import KinCharModel
+
+
+class LoopMode(enum.Enum):
+    CLAMP = 0
+    WRAP = 1
+
+
+def extract_pose_data(frame):
+    """[...,6+D] -> root_pos, root_rot (exp-map), joint_dof.  Ref anim/motion_lib.py:15-19."""
+    return frame[..., 0:3], frame[..., 3:6], frame[..., 6:]
+
+
+class _RefUnpickler(pickle.Unpickler):
+    """Clip pickles written by the reference name its own modules (`util.terrain_util.SubTerrain`);
+    resolve those to this package so the files load without the reference on sys.path."""
+    _REMAP = {("util.terrain_util", "SubTerrain"): ("parc_b200.util.terrain_util", "SubTerrain")}
+
+    def find_class(self, module, name):
+        module, name = self._REMAP.get((module, name), (module, name))
+        return super().find_class(module, name)
+
+
+def load_clip_file(path):
+    with open(path, "rb") as f:
+        return _RefUnpickler(io.BytesIO(f.read())).load()
+
+
+class MotionLib:
+    def __init__(self, motion_input, kin_char_model: KinCharModel, device, init_type="motion_file",
+                 loop_mode=None, fps=None, contact_info=False, contacts=None):
+        self._device = device
+        self._kin_char_model = kin_char_model
+        self._contact_info = contact_info
+        self._hf_mask_inds = None
+        self._packed = None
+        # table building runs on the host; the model is mirrored there once
+        self._host_model = kin_char_model if torch.device(kin_char_model._device).type == "cpu" \
+            else kin_char_model.get_copy("cpu")
+
+        if init_type == "motion_file":
+            self._load_motions(motion_input)
+        elif init_type == "motion_frames":   # (num motions, num_frames, dofs)
+            self._load_motion_frames(motion_input, loop_mode, fps, frame_contacts=contacts if contact_info else None)
+        else:
+            # the reference's "diffusion_file" branch calls a method that does not exist (:30-31)
+            raise ValueError(f"unsupported init_type {init_type!r}")
+
+    # ------------------------------------------------------------------ simple accessors
+    def num_motions(self):
+        return self._motion_lengths.shape[0]
+
+    def get_total_length(self):
+        return torch.sum(self._motion_lengths).item()
+
+    def sample_motions(self, n, motion_weights=None):
+        """Ref :48-52."""
+        w = self._motion_weights if motion_weights is None else motion_weights
+        return torch.multinomial(w, num_samples=n, replacement=True)
+
+    def sample_time(self, motion_ids, truncate_time=None):
+        """Ref :54-63."""
+        phase = torch.rand(motion_ids.shape, device=self._device)
+        motion_len = self._motion_lengths[motion_ids]
+        if truncate_time is not None:
+            assert truncate_time >= 0.0
+            motion_len = motion_len - truncate_time
+        return phase * motion_len
+
+    def get_motion_length(self, motion_ids):
+        return self._motion_lengths[motion_ids]
+
+    def get_motion_loop_mode(self, motion_ids):
+        return self._motion_loop_modes[motion_ids]
+
+    def get_motion_loop_mode_enum(self, motion_id):
+        return LoopMode(self._motion_loop_modes[motion_id].item())
+
+    def get_motion_names(self):
+        assert hasattr(self, "_motion_names")
+        return self._motion_names
+
+    def calc_motion_phase(self, motion_ids, times):
+        """Ref :74-78 + calc_phase :527-538 (elementwise; stays in torch on the tensors' device)."""
+        phase = times / self._motion_lengths[motion_ids]
+        wrap = self._motion_loop_modes[motion_ids] == LoopMode.WRAP.value
+        phase = torch.where(wrap, phase - torch.floor(phase), phase)
+        return torch.clip(phase, 0.0, 1.0)
+
+    # ------------------------------------------------------------------ the hot path
+    def calc_motion_frame(self, motion_ids, motion_times):
+        """(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel[, contacts]).  Ref :80-112."""
+        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times=motion_times,
+                             want_contacts=self._contact_info)
+        return self._as_tuple(r)
+
+    def get_motion_frame(self, motion_ids, frame_idxs):
+        """Integer-frame lookup, no blending.  Ref :114-131."""
+        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, frame_idxs=frame_idxs,
+                             want_contacts=self._contact_info)
+        return self._as_tuple(r)
+
+    def _as_tuple(self, r):
+        ret = [r["root_pos"], r["root_rot"], r["root_vel"], r["root_ang_vel"], r["joint_rot"], r["dof_vel"]]
+        if self._contact_info:
+            ret.append(r["contacts"])
+        return tuple(ret)
+
+    def _calc_frame_blend(self, motion_ids, times):
+        """(frame_idx0, frame_idx1, blend), absolute table rows.  Ref :443-456."""
+        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times=times,
+                             want_frame=False, want_index=True)
+        return r["frame_idx0"], r["frame_idx1"], r["blend"]
+
+    def calc_motion_frame_fk_obs(self, motion_ids, motion_times, hf_desc=None, obs_tmpl=None, obs_relative=True,
+                                 min_obs_h=-3.0, max_obs_h=3.0, out=None):
+        """Fused extension (no reference counterpart as ONE call): the frame query, the forward
+        kinematics of the blended pose and the heightmap observation around it in a single launch --
+        what dm_env.py:570-595 + ig_parkour_env.py:636-656 do in ~1500 eager ops.  Returns a dict."""
+        return ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times=motion_times,
+                                want_contacts=self._contact_info, want_fk=True, hf=hf_desc, obs_tmpl=obs_tmpl,
+                                obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out)
+
+    def joint_rot_to_dof(self, joint_rot):
+        return self._kin_char_model.rot_to_dof(joint_rot)
+
+    def calc_motion_frame_dofs(self, motion_ids, motion_times):
+        """Ref :477-489."""
+        fr = self.calc_motion_frame(motion_ids, motion_times)
+        parts = [fr[0], torch_util.quat_to_exp_map(fr[1]), self.joint_rot_to_dof(fr[4])]
+        if self._contact_info:
+            parts.append(fr[6])
+        return torch.cat(parts, dim=-1)
+
+    def get_frame_data(self, motion_id, frame_start, frame_end):
+        """Ref :425-441."""
+        assert frame_start < frame_end, "frame_start must be less than frame_end"
+        assert motion_id < self.num_motions(), "motion_id out of range"
+        s = self._motion_start_idx[motion_id] + frame_start
+        e = self._motion_start_idx[motion_id] + frame_end
+        ret = [self._frame_root_pos[s:e], self._frame_root_rot[s:e], self._frame_joint_rot[s:e]]
+        if self._contact_info:
+            ret.append(self._frame_contacts[s:e])
+        return tuple(ret)
+
+    def get_frames_for_id(self, id):
+        """Ref :503-513."""
+        n = self._motion_num_frames[id]
+        s = self._motion_start_idx[id]
+        sl = slice(s, s + n)
+        root_pos, root_rot, joint_rot = self._frame_root_pos[sl], self._frame_root_rot[sl], self._frame_joint_rot[sl]
+        body_pos, body_rot = self._kin_char_model.forward_kinematics(root_pos, root_rot, joint_rot)
+        return root_pos, root_rot, joint_rot, body_pos, body_rot
+
+    def maxpool_contacts(self, kernel_size):
+        """Ref :491-497."""
+        return torch.max_pool1d(self._frame_contacts.unsqueeze(0), kernel_size=kernel_size, stride=1,
+                                padding=kernel_size // 2).squeeze(0)
+
+    def clone(self, device):
+        """Ref :515-524."""
+        new = copy.copy(self)
+        new._device = device
+        for k, v in vars(self).items():
+            if isinstance(v, torch.Tensor):
+                setattr(new, k, v.to(device))
+        new._kin_char_model = self._kin_char_model.get_copy(device)
+        new._packed = None
+        new._finalize_device_tables()
+        return new
+
+    # ------------------------------------------------------------------ loading (host side)
+    def _extract_frame_data(self, frame):
+        """frames -> root_pos, root_rot quat, joint_rot (w >= 0), computed on the host.  Ref :405-423."""
+        fr = torch.as_tensor(frame, dtype=torch.float32).detach().cpu()
+        root_pos, root_exp, joint_dof = extract_pose_data(fr)
+        root_pos = root_pos.clone()
+        root_rot = torch_util.exp_map_to_quat(root_exp.clone())
+        joint_rot = torch_util.quat_pos(self._host_model.host_dof_to_rot(joint_dof.clone()))
+        return root_pos, root_rot, joint_rot
+
+    @staticmethod
+    def _finite_diff_vels(root_pos, root_rot, fps):
+        """Root linear / angular velocity by forward differences, last frame repeated.  Ref :281-288."""
+        root_vel = torch.zeros_like(root_pos)
+        root_vel[..., :-1, :] = fps * (root_pos[..., 1:, :] - root_pos[..., :-1, :])
+        root_vel[..., -1, :] = root_vel[..., -2, :]
+        root_ang_vel = torch.zeros_like(root_pos)
+        drot = torch_util.quat_diff(root_rot[..., :-1, :], root_rot[..., 1:, :])
+        root_ang_vel[..., :-1, :] = fps * torch_util.quat_to_exp_map(drot)
+        root_ang_vel[..., -1, :] = root_ang_vel[..., -2, :]
+        return root_vel, root_ang_vel
+
+    def _load_motion_frames(self, motion_frames, loop_mode, fps, frame_contacts=None):
+        """All clips share one length.  Ref :137-202 -- including its quirk of handing `fps` to
+        compute_frame_dof_vel where a time step is expected (:178), which parity requires."""
+        if motion_frames.dim() == 2:
+            motion_frames = motion_frames.unsqueeze(0)
+        if frame_contacts is not None and frame_contacts.dim() == 2:
+            frame_contacts = frame_contacts.unsqueeze(0)
+        if frame_contacts is not None:
+            assert motion_frames.dim() == frame_contacts.dim() == 3, frame_contacts.shape
+        M, F = motion_frames.shape[0], motion_frames.shape[1]
+        root_pos, root_rot, joint_rot = self._extract_frame_data(motion_frames)
+        delta = root_pos[:, -1] - root_pos[:, 0]
+        delta[..., -1] = 0.0
+        root_vel, root_ang_vel = self._finite_diff_vels(root_pos, root_rot, fps)
+        dof_vel = self._host_model.compute_frame_dof_vel(joint_rot, fps)
+        J = self._host_model.get_num_joints()
+
+        dev = self._device
+        self._motion_fps = fps * torch.ones(M, dtype=torch.float32, device=dev)
+        self._motion_dt = 1.0 / fps * torch.ones(M, dtype=torch.float32, device=dev)
+        self._motion_num_frames = F * torch.ones(M, dtype=torch.long, device=dev)
+        self._motion_lengths = (1.0 / fps * (F - 1)) * torch.ones(M, dtype=torch.float32, device=dev)
+        self._motion_loop_modes = loop_mode.value * torch.ones(M, dtype=torch.int, device=dev)
+        self._motion_root_pos_delta = delta.to(dev)
+        self._motion_weights = torch.ones(M, dtype=torch.float32, device=dev)
+        self._host_tables = dict(
+            root_pos=root_pos.reshape(-1, 3), root_rot=root_rot.reshape(-1, 4),
+            joint_rot=joint_rot.reshape(-1, J - 1, 4), root_vel=root_vel.reshape(-1, 3),
+            root_ang_vel=root_ang_vel.reshape(-1, 3), dof_vel=dof_vel.reshape(-1, dof_vel.shape[-1]),
+            contacts=None if frame_contacts is None else
+            torch.as_tensor(frame_contacts, dtype=torch.float32).detach().cpu().reshape(-1, frame_contacts.shape[-1]),
+            frames=torch.as_tensor(motion_frames, dtype=torch.float32).detach().cpu().reshape(-1, motion_frames.shape[-1]))
+        self._finish_load()
+
+    def _load_motions(self, motion_file):
+        """yaml list of clip pickles (or a single pickle).  Ref :204-380."""
+        files, weights = self._fetch_motion_files(motion_file)
+        acc = {k: [] for k in ("root_pos", "root_rot", "joint_rot", "root_vel", "root_ang_vel", "dof_vel",
+                               "contacts", "frames", "delta")}
+        meta = {k: [] for k in ("fps", "dt", "n", "len", "loop")}
+        self._motion_files, self._motion_names, self._motion_extras = [], [], []
+        self._terrains, self._hf_mask_inds = [], []
+        D = self._host_model.get_dof_size()
+        J = self._host_model.get_num_joints()
+        for f, path in enumerate(files):
+            if len(files) < 1000 or f % 500 == 0:
+                print("Loading {:d}/{:d} motion files: {:s}".format(f + 1, len(files), path))
+            clip = load_clip_file(path)
+            fps = clip.get("fps", 30)
+            if isinstance(fps, np.ndarray):
+                fps = fps.item()
+            frames = clip.get("frames")
+            if frames is None:
+                frames = np.zeros([3, 6 + D], dtype=np.float32)
+            elif frames.ndim == 3 and frames.shape[0] == 1:
+                frames = np.squeeze(frames)
+            name = os.path.basename(os.path.splitext(path)[0])
+            assert name not in self._motion_names
+            self._motion_names.append(name)
+            n = frames.shape[0]
+            root_pos, root_rot, joint_rot = self._extract_frame_data(frames)
+            delta = root_pos[-1] - root_pos[0]
+            delta[..., -1] = 0.0
+            root_vel, root_ang_vel = self._finite_diff_vels(root_pos, root_rot, fps)
+            acc["root_pos"].append(root_pos)
+            acc["root_rot"].append(root_rot)
+            acc["joint_rot"].append(joint_rot)
+            acc["root_vel"].append(root_vel)
+            acc["root_ang_vel"].append(root_ang_vel)
+            acc["dof_vel"].append(self._host_model.compute_frame_dof_vel(joint_rot, 1.0 / fps))
+            acc["delta"].append(delta)
+            acc["frames"].append(torch.as_tensor(np.asarray(frames), dtype=torch.float32))
+            if self._contact_info:
+                if "contacts" in clip:
+                    c = torch.tensor(np.asarray(clip["contacts"]), dtype=torch.float32)
+                    if c.dim() == 3 and c.shape[0] == 1:
+                        c = torch.squeeze(c)
+                else:
+                    c = torch.zeros([n, J], dtype=torch.float32)
+                acc["contacts"].append(c)
+            meta["fps"].append(fps)
+            meta["dt"].append(1.0 / fps)
+            meta["n"].append(n)
+            meta["len"].append(1.0 / fps * (n - 1))
+            meta["loop"].append(LoopMode[clip.get("loop_mode", "CLAMP")].value)
+            self._motion_files.append(path)
+            self._motion_extras.append(clip.get("extra"))
+            terrain = clip.get("terrain")
+            if terrain is not None:
+                terrain.update_old()
+                terrain.to_torch(self._device)
+            self._terrains.append(terrain)
+            inds = clip.get("hf_mask_inds")
+            if inds is not None:
+                inds = [t.to(device=self._device) for t in inds]
+            self._hf_mask_inds.append(inds)
+
+        dev = self._device
+        w = torch.tensor(weights, dtype=torch.float32, device=dev)
+        self._motion_weights = w / w.sum()
+        self._motion_fps = torch.tensor(meta["fps"], dtype=torch.float32, device=dev)
+        self._motion_dt = torch.tensor(meta["dt"], dtype=torch.float32, device=dev)
+        self._motion_num_frames = torch.tensor(meta["n"], dtype=torch.long, device=dev)
+        self._motion_lengths = torch.tensor(meta["len"], dtype=torch.float32, device=dev)
+        self._motion_loop_modes = torch.tensor(meta["loop"], dtype=torch.int, device=dev)
+        self._motion_root_pos_delta = torch.stack(acc["delta"], dim=0).to(dev)
+        self._host_tables = {k: torch.cat(acc[k], dim=0) for k in
+                             ("root_pos", "root_rot", "joint_rot", "root_vel", "root_ang_vel", "dof_vel", "frames")}
+        self._host_tables["contacts"] = torch.cat(acc["contacts"], dim=0) if self._contact_info else None
+        self._finish_load()
+        print("Loaded {:d} motions with a total length of {:.3f}s.".format(self.num_motions(), self.get_total_length()))
+
+    def _fetch_motion_files(self, motion_file):
+        """Ref :382-403."""
+        if os.path.splitext(motion_file)[1] == ".yaml":
+            with open(motion_file, "r") as f:
+                entries = yaml.load(f, Loader=yaml.SafeLoader)["motions"]
+            for e in entries:
+                assert e["weight"] >= 0
+            return [e["file"] for e in entries], [e["weight"] for e in entries]
+        return [motion_file], [1.0]
+
+    def _finish_load(self):
+        dev = self._device
+        M = self.num_motions()
+        self._motion_ids = torch.arange(M, dtype=torch.long, device=dev)
+        shifted = self._motion_num_frames.roll(1)
+        shifted[0] = 0
+        self._motion_start_idx = shifted.cumsum(0)
+        h = self._host_tables
+        self._frame_root_pos = h["root_pos"].to(dev)
+        self._frame_root_rot = h["root_rot"].to(dev)
+        self._frame_joint_rot = h["joint_rot"].to(dev)
+        self._frame_root_vel = h["root_vel"].to(dev)
+        self._frame_root_ang_vel = h["root_ang_vel"].to(dev)
+        self._frame_dof_vel = h["dof_vel"].to(dev)
+        self._motion_frames = h["frames"].to(dev)
+        if h["contacts"] is not None:
+            self._frame_contacts = h["contacts"].to(dev)
+        del self._host_tables
+        self._finalize_device_tables()
+
+    def _finalize_device_tables(self):
+        """Pack the device tables into float4 rows (GPU kernel).  On a CPU device (host-logic tests) the
+        unpacked tables exist but queries are unavailable -- there is no CPU fallback."""
+        if torch.device(self._device).type != "cuda":
+            self._packed = None
+            return
+        model = self._kin_char_model.c_model()
+        contacts = getattr(self, "_frame_contacts", None)
+        rows, lay = ops.pack_frames(model, self._frame_root_pos, self._frame_root_rot, self._frame_joint_rot,
+                                    contacts, self._frame_root_vel, self._frame_root_ang_vel, self._frame_dof_vel)
+        clips = ops.build_clip_meta(self._motion_num_frames, self._motion_loop_modes, self._motion_start_idx,
+                                    self._motion_lengths, self._motion_root_pos_delta, self._device)
+        self._packed = ops.PackedTables(rows=rows, clips=clips, total_frames=int(rows.shape[0]),
+                                        num_clips=self.num_motions(), layout=lay)

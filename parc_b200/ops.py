@@ -1,0 +1,522 @@
+"""Operator layer: torch tensors in, libparc_b200 C-ABI calls, torch tensors out.
+
+Every function here launches hand-written sm_100a kernels on the current CUDA stream through the C ABI
+of include/parc_b200.h.  Tensors must live on a CUDA device -- there is no CPU path.  Differentiable
+operators are `torch.autograd.Function`s whose backward calls the matching VJP kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ParcBodyPoints, ParcCharModel, ParcClipMeta, ParcFkOut, ParcFrameOut, ParcHeightfield,
+                   ParcMotionTables, ParcObsSpec, ParcRowLayout, ParcTerrainBatch, check, f32c, ptr,
+                   require_cuda, stream_ptr)
+
+
+# ----------------------------------------------------------------------------------------------
+# model / layout helpers (host only)
+# ----------------------------------------------------------------------------------------------
+def make_char_model(parents, local_trans, local_rot, joint_types, joint_axes, dof_idx) -> ParcCharModel:
+    """Fill the POD the kernels take.  Arguments are python lists / nested lists (host values)."""
+    J = len(parents)
+    if J > _lib.PARC_MAX_BODIES:
+        raise _lib.ParcLibraryError(f"character has {J} bodies; libparc_b200 supports <= {_lib.PARC_MAX_BODIES}")
+    m = ParcCharModel()
+    m.num_bodies = J
+    depth = [0] * J
+    dof = 0
+    for b in range(J):
+        m.parent[b] = int(parents[b])
+        if b > 0:
+            depth[b] = depth[int(parents[b])] + 1
+        m.depth[b] = depth[b]
+        jt = int(joint_types[b])
+        m.joint_type[b] = jt
+        m.dof_idx[b] = int(dof_idx[b])
+        dof += 1 if jt == _lib.JOINT_HINGE else (3 if jt == _lib.JOINT_SPHERICAL else 0)
+        for k in range(3):
+            m.local_trans[b][k] = float(local_trans[b][k])
+            m.joint_axis[b][k] = float(joint_axes[b][k])
+        for k in range(4):
+            m.local_rot[b][k] = float(local_rot[b][k])
+    m.dof_size = dof
+    m.max_depth = max(depth)
+    check(_lib.load().parc_validate_model(C.byref(m)), "parc_validate_model")
+    return m
+
+
+def row_layout(model: ParcCharModel) -> ParcRowLayout:
+    lay = ParcRowLayout()
+    check(_lib.load().parc_row_layout(C.byref(model), C.byref(lay)), "parc_row_layout")
+    return lay
+
+
+@dataclass
+class PackedTables:
+    """Device-resident packed frame rows + clip metadata (include/parc_b200.h: ParcMotionTables)."""
+    rows: torch.Tensor        # f32 [T, row_floats]
+    clips: torch.Tensor       # uint8 [M, 32] (ParcClipMeta records)
+    total_frames: int
+    num_clips: int
+    layout: ParcRowLayout
+
+    def c_struct(self) -> ParcMotionTables:
+        t = ParcMotionTables()
+        t.rows = self.rows.data_ptr()
+        t.clips = self.clips.data_ptr()
+        t.total_frames = self.total_frames
+        t.num_clips = self.num_clips
+        t.row_floats = self.layout.row_floats
+        return t
+
+
+def build_clip_meta(num_frames, loop_modes, start_idx, lengths, root_pos_delta, device) -> torch.Tensor:
+    """Host tensors -> [M,32] uint8 device tensor of ParcClipMeta records."""
+    import numpy as np
+    M = int(num_frames.shape[0])
+    rec = np.zeros(M, dtype=np.dtype([("num_frames", "<i4"), ("loop_mode", "<i4"), ("start_idx", "<i8"),
+                                      ("length", "<f4"), ("delta", "<f4", (3,))]))
+    assert rec.dtype.itemsize == C.sizeof(ParcClipMeta) == 32
+    rec["num_frames"] = num_frames.cpu().numpy()
+    rec["loop_mode"] = loop_modes.cpu().numpy()
+    rec["start_idx"] = start_idx.cpu().numpy()
+    rec["length"] = lengths.cpu().numpy()
+    rec["delta"] = root_pos_delta.cpu().numpy().reshape(M, 3)
+    raw = torch.from_numpy(rec.view(np.uint8).reshape(M, 32).copy())
+    return raw.to(device)
+
+
+def pack_frames(model: ParcCharModel, root_pos, root_rot, joint_rot, contacts, root_vel, root_ang_vel,
+                dof_vel) -> Tuple[torch.Tensor, ParcRowLayout]:
+    """a1: interleave the per-frame tables (device tensors) into packed rows on the GPU."""
+    require_cuda(root_pos, root_rot, joint_rot, root_vel, root_ang_vel, dof_vel, contacts)
+    lay = row_layout(model)
+    T = root_pos.shape[0]
+    rows = torch.empty((T, lay.row_floats), dtype=torch.float32, device=root_pos.device)
+    args = [f32c(t) if t is not None else None
+            for t in (root_pos, root_rot, joint_rot, contacts, root_vel, root_ang_vel, dof_vel)]
+    with torch.cuda.device(root_pos.device):
+        rc = _lib.load().parc_pack_frames(*[ptr(a) for a in args], T, C.byref(model), rows.data_ptr(),
+                                          stream_ptr(root_pos.device))
+    check(rc, "parc_pack_frames")
+    return rows, lay
+
+
+# ----------------------------------------------------------------------------------------------
+# heightfield descriptors
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class HeightfieldDesc:
+    """Host copy of SubTerrain's scalars + the device hf tensor, so launches never sync."""
+    hf: torch.Tensor
+    min_x: float
+    min_y: float
+    dx: float
+    dy: float
+
+    def c_struct(self) -> ParcHeightfield:
+        h = ParcHeightfield()
+        h.hf = self.hf.data_ptr()
+        h.dim_x, h.dim_y = int(self.hf.shape[0]), int(self.hf.shape[1])
+        h.min_x, h.min_y, h.dx, h.dy = self.min_x, self.min_y, self.dx, self.dy
+        return h
+
+
+def _obs_struct(tmpl_xy: torch.Tensor, relative: bool, min_h: float, max_h: float) -> ParcObsSpec:
+    o = ParcObsSpec()
+    o.tmpl_xy = tmpl_xy.data_ptr()
+    o.num_points = int(tmpl_xy.shape[0])
+    o.relative = 1 if relative else 0
+    o.min_h, o.max_h = float(min_h), float(max_h)
+    return o
+
+
+# ----------------------------------------------------------------------------------------------
+# a2-a4 (+a6, +a10): frame query, optionally fused with FK and the heightmap observation
+# ----------------------------------------------------------------------------------------------
+def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.Tensor,
+                 motion_times: Optional[torch.Tensor] = None, frame_idxs: Optional[torch.Tensor] = None, *,
+                 want_frame: bool = True, want_contacts: bool = True, want_index: bool = False,
+                 want_fk: bool = False, hf: Optional[HeightfieldDesc] = None,
+                 obs_tmpl: Optional[torch.Tensor] = None, obs_relative: bool = True, obs_min_h: float = -3.0,
+                 obs_max_h: float = 3.0, out: Optional[dict] = None) -> dict:
+    """One launch of the fused kernel.  Exactly one of motion_times (blended query,
+    MotionLib.calc_motion_frame) or frame_idxs (MotionLib.get_motion_frame) must be given.
+    Returns a dict of output tensors; `out` may carry preallocated tensors to reuse."""
+    require_cuda(motion_ids, motion_times, frame_idxs)
+    dev = motion_ids.device
+    N = int(motion_ids.shape[0])
+    J, D = model.num_bodies, model.dof_size
+    ids = motion_ids.to(torch.int64).contiguous()
+    res = {} if out is None else out
+
+    def buf(name, shape, dtype=torch.float32):
+        t = res.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            res[name] = t
+        return t
+
+    fo = ParcFrameOut()
+    if want_frame:
+        fo.root_pos = buf("root_pos", (N, 3)).data_ptr()
+        fo.root_rot = buf("root_rot", (N, 4)).data_ptr()
+        fo.root_vel = buf("root_vel", (N, 3)).data_ptr()
+        fo.root_ang_vel = buf("root_ang_vel", (N, 3)).data_ptr()
+        fo.joint_rot = buf("joint_rot", (N, J - 1, 4)).data_ptr()
+        fo.dof_vel = buf("dof_vel", (N, D)).data_ptr()
+        if want_contacts:
+            fo.contacts = buf("contacts", (N, J)).data_ptr()
+    if want_index:
+        fo.frame_idx0 = buf("frame_idx0", (N,), torch.int64).data_ptr()
+        fo.frame_idx1 = buf("frame_idx1", (N,), torch.int64).data_ptr()
+        fo.blend = buf("blend", (N,)).data_ptr()
+    fk = ParcFkOut()
+    if want_fk:
+        fk.body_pos = buf("body_pos", (N, J, 3)).data_ptr()
+        fk.body_rot = buf("body_rot", (N, J, 4)).data_ptr()
+    tb = tables.c_struct()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        if motion_times is not None:
+            assert frame_idxs is None
+            times = f32c(motion_times)
+            obs_ptr, hfs, obs = None, None, None
+            if obs_tmpl is not None:
+                assert hf is not None
+                require_cuda(hf.hf, obs_tmpl)
+                tm = f32c(obs_tmpl)
+                res["_tmpl_keepalive"] = tm
+                hfs, obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
+                obs_ptr = buf("obs", (N, int(tm.shape[0]))).data_ptr()
+            rc = lib.parc_motion_query(C.byref(tb), ids.data_ptr(), times.data_ptr(), N, C.byref(model),
+                                       C.byref(fo), C.byref(fk) if want_fk else None,
+                                       C.byref(hfs) if hfs is not None else None,
+                                       C.byref(obs) if obs is not None else None, obs_ptr, stream_ptr(dev))
+            check(rc, "parc_motion_query")
+        else:
+            fi = frame_idxs.to(torch.int64).contiguous()
+            rc = lib.parc_get_motion_frame(C.byref(tb), ids.data_ptr(), fi.data_ptr(), N, C.byref(model),
+                                           C.byref(fo), C.byref(fk) if want_fk else None, stream_ptr(dev))
+            check(rc, "parc_get_motion_frame")
+    res.pop("_tmpl_keepalive", None)
+    return res
+
+
+# ----------------------------------------------------------------------------------------------
+# a6: forward kinematics (differentiable)
+# ----------------------------------------------------------------------------------------------
+class _ForwardKinematics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, root_pos, root_rot, joint_rot, model):
+        require_cuda(root_pos, root_rot, joint_rot)
+        lead = root_pos.shape[:-1]
+        J = model.num_bodies
+        rp = f32c(root_pos).reshape(-1, 3)
+        rr = f32c(root_rot).reshape(-1, 4)
+        jr = f32c(joint_rot).reshape(-1, max(J - 1, 0), 4)
+        n = rp.shape[0]
+        body_pos = torch.empty((n, J, 3), dtype=torch.float32, device=rp.device)
+        body_rot = torch.empty((n, J, 4), dtype=torch.float32, device=rp.device)
+        with torch.cuda.device(rp.device):
+            rc = _lib.load().parc_fk_fwd(rp.data_ptr(), rr.data_ptr(), jr.data_ptr(), n, C.byref(model),
+                                         body_pos.data_ptr(), body_rot.data_ptr(), stream_ptr(rp.device))
+        check(rc, "parc_fk_fwd")
+        ctx.model = model
+        ctx.lead = lead
+        ctx.save_for_backward(rr, jr)
+        return body_pos.reshape(*lead, J, 3), body_rot.reshape(*lead, J, 4)
+
+    @staticmethod
+    def backward(ctx, g_pos, g_rot):
+        rr, jr = ctx.saved_tensors
+        model = ctx.model
+        J = model.num_bodies
+        n = rr.shape[0]
+        gp = f32c(g_pos).reshape(n, J, 3) if g_pos is not None else None
+        gr = f32c(g_rot).reshape(n, J, 4) if g_rot is not None else None
+        g_root_pos = torch.empty((n, 3), dtype=torch.float32, device=rr.device)
+        g_root_rot = torch.empty((n, 4), dtype=torch.float32, device=rr.device)
+        g_joint = torch.empty((n, max(J - 1, 0), 4), dtype=torch.float32, device=rr.device)
+        with torch.cuda.device(rr.device):
+            rc = _lib.load().parc_fk_bwd(rr.data_ptr(), jr.data_ptr(), ptr(gp), ptr(gr), n, C.byref(model),
+                                         g_root_pos.data_ptr(), g_root_rot.data_ptr(), g_joint.data_ptr(),
+                                         stream_ptr(rr.device))
+        check(rc, "parc_fk_bwd")
+        lead = ctx.lead
+        return (g_root_pos.reshape(*lead, 3), g_root_rot.reshape(*lead, 4),
+                g_joint.reshape(*lead, max(J - 1, 0), 4), None)
+
+
+def forward_kinematics(model: ParcCharModel, root_pos, root_rot, joint_rot):
+    return _ForwardKinematics.apply(root_pos, root_rot, joint_rot, model)
+
+
+# ----------------------------------------------------------------------------------------------
+# a8: DoF -> joint quaternions, exp-map -> quaternion (differentiable)
+# ----------------------------------------------------------------------------------------------
+class _DofToRot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dof, model):
+        require_cuda(dof)
+        lead = dof.shape[:-1]
+        d = f32c(dof).reshape(-1, model.dof_size)
+        n = d.shape[0]
+        J = model.num_bodies
+        out = torch.empty((n, J - 1, 4), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            rc = _lib.load().parc_dof_to_rot_fwd(d.data_ptr(), n, C.byref(model), out.data_ptr(),
+                                                 stream_ptr(d.device))
+        check(rc, "parc_dof_to_rot_fwd")
+        ctx.model, ctx.lead = model, lead
+        ctx.save_for_backward(d)
+        return out.reshape(*lead, J - 1, 4)
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        model = ctx.model
+        n = d.shape[0]
+        gq = f32c(g).reshape(n, model.num_bodies - 1, 4)
+        gd = torch.zeros((n, model.dof_size), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            rc = _lib.load().parc_dof_to_rot_bwd(d.data_ptr(), gq.data_ptr(), n, C.byref(model), gd.data_ptr(),
+                                                 stream_ptr(d.device))
+        check(rc, "parc_dof_to_rot_bwd")
+        return gd.reshape(*ctx.lead, model.dof_size), None
+
+
+def dof_to_rot(model: ParcCharModel, dof):
+    return _DofToRot.apply(dof, model)
+
+
+class _ExpMapToQuat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e):
+        require_cuda(e)
+        lead = e.shape[:-1]
+        ee = f32c(e).reshape(-1, 3)
+        n = ee.shape[0]
+        q = torch.empty((n, 4), dtype=torch.float32, device=ee.device)
+        with torch.cuda.device(ee.device):
+            rc = _lib.load().parc_exp_map_to_quat_fwd(ee.data_ptr(), n, q.data_ptr(), stream_ptr(ee.device))
+        check(rc, "parc_exp_map_to_quat_fwd")
+        ctx.lead = lead
+        ctx.save_for_backward(ee)
+        return q.reshape(*lead, 4)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ee,) = ctx.saved_tensors
+        n = ee.shape[0]
+        gq = f32c(g).reshape(n, 4)
+        ge = torch.empty((n, 3), dtype=torch.float32, device=ee.device)
+        with torch.cuda.device(ee.device):
+            rc = _lib.load().parc_exp_map_to_quat_bwd(ee.data_ptr(), gq.data_ptr(), n, ge.data_ptr(),
+                                                      stream_ptr(ee.device))
+        check(rc, "parc_exp_map_to_quat_bwd")
+        return ge.reshape(*ctx.lead, 3)
+
+
+def exp_map_to_quat(exp_map):
+    return _ExpMapToQuat.apply(exp_map)
+
+
+# ----------------------------------------------------------------------------------------------
+# a9-a11: heightfield sampling / observations
+# ----------------------------------------------------------------------------------------------
+def hf_sample(hf: HeightfieldDesc, xy: torch.Tensor, want_index: bool = False):
+    """xy [...,2] -> z [...] (and int64 grid indices [...,2] if want_index)."""
+    require_cuda(hf.hf, xy)
+    lead = xy.shape[:-1]
+    p = f32c(xy).reshape(-1, 2)
+    n = p.shape[0]
+    z = torch.empty((n,), dtype=torch.float32, device=p.device)
+    gi = torch.empty((n, 2), dtype=torch.int64, device=p.device) if want_index else None
+    h = hf.c_struct()
+    with torch.cuda.device(p.device):
+        rc = _lib.load().parc_hf_sample(C.byref(h), p.data_ptr(), n, z.data_ptr(), ptr(gi), stream_ptr(p.device))
+    check(rc, "parc_hf_sample")
+    if want_index:
+        return z.reshape(lead), gi.reshape(*lead, 2)
+    return z.reshape(lead)
+
+
+def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, heading: torch.Tensor, *,
+           relative: bool, min_h: float = -3.0, max_h: float = 3.0, out: Optional[torch.Tensor] = None):
+    """root [N,>=2 (3 if relative)], heading [N], tmpl [P,2] -> [N,P]."""
+    require_cuda(hf.hf, tmpl_xy, root, heading)
+    r = f32c(root)
+    assert r.dim() == 2
+    hd = f32c(heading).reshape(-1)
+    tm = f32c(tmpl_xy).reshape(-1, 2)
+    n, P = r.shape[0], tm.shape[0]
+    if out is None:
+        out = torch.empty((n, P), dtype=torch.float32, device=r.device)
+    h, o = hf.c_struct(), _obs_struct(tm, relative, min_h, max_h)
+    with torch.cuda.device(r.device):
+        rc = _lib.load().parc_hf_obs(C.byref(h), C.byref(o), r.data_ptr(), int(r.shape[1]), hd.data_ptr(), n,
+                                     out.data_ptr(), stream_ptr(r.device))
+    check(rc, "parc_hf_obs")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a13-a15: point <-> heightfield SDF, fused body-point loss
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class TerrainBatchDesc:
+    hf: torch.Tensor            # [B or 1, X, Y]
+    min_center: torch.Tensor    # [B or 1, 2]
+    x_nodes: torch.Tensor       # [X]
+    y_nodes: torch.Tensor       # [Y]
+    half_dx: float
+    half_dy: float
+    base_z: Optional[torch.Tensor] = None   # [B or 1] device, or None -> base_z_value
+    base_z_value: float = -10.0
+
+    def c_struct(self, batch: int) -> ParcTerrainBatch:
+        t = ParcTerrainBatch()
+        hb = int(self.hf.shape[0])
+        X, Y = int(self.hf.shape[1]), int(self.hf.shape[2])
+        assert hb in (1, batch) and self.min_center.shape[0] in (1, batch)
+        t.hf = self.hf.data_ptr()
+        t.hf_batch_stride = X * Y if hb > 1 else 0
+        t.min_center = self.min_center.data_ptr()
+        t.min_center_stride = 2 if self.min_center.shape[0] > 1 else 0
+        t.x_nodes, t.y_nodes = self.x_nodes.data_ptr(), self.y_nodes.data_ptr()
+        t.dim_x, t.dim_y = X, Y
+        t.half_dx, t.half_dy = float(self.half_dx), float(self.half_dy)
+        if self.base_z is not None:
+            t.base_z = self.base_z.data_ptr()
+            t.base_z_stride = 1 if self.base_z.numel() > 1 else 0
+        else:
+            t.base_z = None
+            t.base_z_stride = 0
+        t.base_z_value = float(self.base_z_value)
+        return t
+
+
+def make_terrain_batch(hf: torch.Tensor, min_center: torch.Tensor, dxdy_host: Tuple[float, float],
+                       base_z=None) -> TerrainBatchDesc:
+    """hf [B,X,Y] (or [X,Y]); min_center [B,2] (or [2]); dxdy as python floats.  The node offsets are
+    computed with torch.linspace on the device exactly as util/terrain_util.py:1855-1856 does."""
+    require_cuda(hf, min_center)
+    if hf.dim() == 2:
+        hf = hf.unsqueeze(0)
+    if min_center.dim() == 1:
+        min_center = min_center.unsqueeze(0)
+    if hf.stride(0) == 0:
+        hf = hf[:1]
+    if min_center.stride(0) == 0:
+        min_center = min_center[:1]
+    hf = f32c(hf)
+    min_center = f32c(min_center)
+    X, Y = hf.shape[1], hf.shape[2]
+    dx, dy = float(dxdy_host[0]), float(dxdy_host[1])
+    xs = torch.linspace(0.0, (X - 1.0) * dx, X, device=hf.device)
+    ys = torch.linspace(0.0, (Y - 1.0) * dy, Y, device=hf.device)
+    half = torch.tensor([dx, dy], dtype=torch.float32) / 2.0     # fp32 halving as in :1881
+    desc = TerrainBatchDesc(hf=hf, min_center=min_center, x_nodes=xs, y_nodes=ys, half_dx=half[0].item(),
+                            half_dy=half[1].item())
+    if isinstance(base_z, torch.Tensor):
+        desc.base_z = f32c(base_z).reshape(-1)
+    elif base_z is not None:
+        desc.base_z_value = float(base_z)
+    return desc
+
+
+def points_hf_sdf(points: torch.Tensor, terrain: TerrainBatchDesc, inverted: bool, want_arg: bool = False):
+    """points [B,N,3] -> sdf [B,N] (exact min over all cells)."""
+    require_cuda(points)
+    p = f32c(points)
+    assert p.dim() == 3
+    B, N = p.shape[0], p.shape[1]
+    out = torch.empty((B, N), dtype=torch.float32, device=p.device)
+    arg = torch.empty((B, N), dtype=torch.int32, device=p.device) if want_arg else None
+    t = terrain.c_struct(B)
+    with torch.cuda.device(p.device):
+        rc = _lib.load().parc_points_hf_sdf(p.data_ptr(), B, N, C.byref(t), 1 if inverted else 0, out.data_ptr(),
+                                            ptr(arg), stream_ptr(p.device))
+    check(rc, "parc_points_hf_sdf")
+    return (out, arg) if want_arg else out
+
+
+@dataclass
+class BodyPointsDesc:
+    points: torch.Tensor        # [S,3] device
+    point_start: torch.Tensor   # int32 [J+1] device
+
+    def c_struct(self) -> ParcBodyPoints:
+        b = ParcBodyPoints()
+        b.points = self.points.data_ptr()
+        b.point_start = self.point_start.data_ptr()
+        b.num_points = int(self.points.shape[0])
+        return b
+
+
+def make_body_points(body_points, device) -> BodyPointsDesc:
+    counts = [int(p.shape[0]) for p in body_points]
+    starts = [0]
+    for c in counts:
+        starts.append(starts[-1] + c)
+    pts = torch.cat([f32c(p.detach()).reshape(-1, 3) for p in body_points], dim=0).to(device)
+    return BodyPointsDesc(points=pts.contiguous(),
+                          point_start=torch.tensor(starts, dtype=torch.int32, device=device))
+
+
+def _body_loss_launch(model, pts, terrain, root_pos, root_rot, joint_rot, contacts, w_pen, w_contact, want_grad):
+    B, F = root_pos.shape[0], root_pos.shape[1]
+    J = model.num_bodies
+    dev = root_pos.device
+    pen = torch.empty((B, F), dtype=torch.float32, device=dev)
+    con = torch.empty((B, F), dtype=torch.float32, device=dev)
+    g_rp = g_rr = g_jr = None
+    if want_grad:
+        g_rp = torch.empty((B, F, 3), dtype=torch.float32, device=dev)
+        g_rr = torch.empty((B, F, 4), dtype=torch.float32, device=dev)
+        g_jr = torch.empty((B, F, J - 1, 4), dtype=torch.float32, device=dev)
+    t = terrain.c_struct(B)
+    bp = pts.c_struct()
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_body_loss(root_pos.data_ptr(), root_rot.data_ptr(), joint_rot.data_ptr(),
+                                        contacts.data_ptr(), B, F, C.byref(model), C.byref(bp), C.byref(t),
+                                        float(w_pen), float(w_contact), pen.data_ptr(), con.data_ptr(), ptr(g_rp),
+                                        ptr(g_rr), ptr(g_jr), stream_ptr(dev))
+    check(rc, "parc_body_loss")
+    return pen, con, g_rp, g_rr, g_jr
+
+
+class _BodyLoss(torch.autograd.Function):
+    """total[b] = w_pen * pen[b] + w_contact * contact[b]; pen / contact are returned detached."""
+
+    @staticmethod
+    def forward(ctx, root_pos, root_rot, joint_rot, contacts, model, pts, terrain, w_pen, w_contact):
+        require_cuda(root_pos, root_rot, joint_rot, contacts)
+        rp, rr, jr, ct = f32c(root_pos), f32c(root_rot), f32c(joint_rot), f32c(contacts)
+        need = any(ctx.needs_input_grad[:3])
+        pen_bf, con_bf, g_rp, g_rr, g_jr = _body_loss_launch(model, pts, terrain, rp, rr, jr, ct, w_pen, w_contact,
+                                                            need)
+        pen, con = pen_bf.sum(dim=-1), con_bf.sum(dim=-1)
+        total = w_pen * pen + w_contact * con
+        if need:
+            ctx.save_for_backward(g_rp, g_rr, g_jr)
+        ctx.mark_non_differentiable(pen, con)
+        return total, pen, con
+
+    @staticmethod
+    def backward(ctx, g_total, _g_pen, _g_con):
+        g_rp, g_rr, g_jr = ctx.saved_tensors
+        s = g_total.reshape(-1, 1, 1)
+        return (g_rp * s, g_rr * s, g_jr * s.unsqueeze(-1), None, None, None, None, None, None)
+
+
+def body_loss(model: ParcCharModel, pts: BodyPointsDesc, terrain: TerrainBatchDesc, root_pos, root_rot, joint_rot,
+              contacts, w_pen: float, w_contact: float):
+    """[B,F,...] pose + contacts -> (total[B], pen[B], contact[B]); differentiable wrt the pose."""
+    return _BodyLoss.apply(root_pos, root_rot, joint_rot, contacts, model, pts, terrain, w_pen, w_contact)

@@ -1,0 +1,425 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (north_star): frame indices / grid indices bit-exact; fp32 values within 1e-5 relative
+(assert_close: atol 1e-6 + rtol 1e-5); gradients 1e-5 of the tensor's max magnitude (norm-wise).
+Heightmap observations are exact except where the sample lands within a few ulps of a cell border,
+where sin/cos of the GPU and of the host may legitimately round the coordinate to the other cell.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import (assert_close, assert_close_normwise, golden, lib_clips_from_golden, write_clip_library)
+
+pytestmark = pytest.mark.gpu
+
+FRAME_KEYS = ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import parc_oracle
+    return parc_oracle
+
+
+@pytest.fixture(scope="module")
+def golden_lib(gpu_model, tmp_path_factory):
+    from parc_b200.anim.motion_lib import MotionLib
+    y = write_clip_library(tmp_path_factory.mktemp("lib"), lib_clips_from_golden())
+    return MotionLib(y, gpu_model, "cuda:0", init_type="motion_file", contact_info=True)
+
+
+@pytest.fixture(scope="module")
+def oracle_tables(O, oracle_model):
+    return O.build_tables(oracle_model, lib_clips_from_golden())
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.asarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to("cuda:0")
+
+
+# ----------------------------------------------------------------------------------------- tables
+def test_packed_tables_match_golden(golden_lib):
+    g = golden("tables_golden.npz")
+    assert torch.equal(golden_lib._frame_root_rot.cpu(), torch.tensor(g["root_rot"]))
+    assert torch.equal(golden_lib._frame_joint_rot.cpu(), torch.tensor(g["joint_rot"]))
+    assert torch.equal(golden_lib._frame_dof_vel.cpu(), torch.tensor(g["dof_vel"]))
+    assert torch.equal(golden_lib._motion_lengths.cpu(), torch.tensor(g["lengths"]))
+    lay = golden_lib._packed.layout
+    rows = golden_lib._packed.rows.cpu()
+    assert rows.shape == (352, lay.row_floats) and lay.row_floats % 8 == 0
+    assert torch.equal(rows[:, 4:8], torch.tensor(g["root_rot"]))
+    assert torch.equal(rows[:, 8:64].reshape(-1, 14, 4), torch.tensor(g["joint_rot"]))
+    v0 = lay.vel_slot * 4
+    assert torch.equal(rows[:, v0:v0 + 3], torch.tensor(g["root_vel"]))
+    assert torch.equal(rows[:, v0 + 3:v0 + 6], torch.tensor(g["root_ang_vel"]))
+    assert torch.equal(rows[:, v0 + 6:v0 + 34], torch.tensor(g["dof_vel"]))
+
+
+# ----------------------------------------------------------------------------------------- query
+def test_frame_index_bit_exact_vs_golden(golden_lib):
+    g = golden("query_golden.npz")
+    i0, i1, bl = golden_lib._calc_frame_blend(dev(g["ids"]), dev(g["times"]))
+    assert torch.equal(i0.cpu(), torch.tensor(g["idx0"]))
+    assert torch.equal(i1.cpu(), torch.tensor(g["idx1"]))
+    assert torch.equal(bl.cpu(), torch.tensor(g["blend"]))          # blend is exact too (IEEE ops only)
+
+
+def test_calc_motion_frame_vs_golden(golden_lib):
+    g = golden("query_golden.npz")
+    out = golden_lib.calc_motion_frame(dev(g["ids"]), dev(g["times"]))
+    assert len(out) == 7
+    for k, t in zip(FRAME_KEYS, out):
+        assert_close(t, g[k], what=f"calc_motion_frame.{k}")
+    # gathers and lerps involve IEEE ops only -> exact
+    assert torch.equal(out[2].cpu(), torch.tensor(g["root_vel"]))
+    assert torch.equal(out[5].cpu(), torch.tensor(g["dof_vel"]))
+    assert torch.equal(out[0].cpu(), torch.tensor(g["root_pos"]))
+    assert torch.equal(out[6].cpu(), torch.tensor(g["contacts"]))
+
+
+def test_get_motion_frame_vs_golden(golden_lib):
+    g = golden("query_golden.npz")
+    out = golden_lib.get_motion_frame(dev(g["get_ids"]), dev(g["get_fidx"]))
+    assert torch.equal(out[0].cpu(), torch.tensor(g["get_root_pos"]))
+    assert torch.equal(out[4].cpu(), torch.tensor(g["get_joint_rot"]))
+    assert torch.equal(out[5].cpu(), torch.tensor(g["get_dof_vel"]))
+    assert torch.equal(out[6].cpu(), torch.tensor(g["get_contacts"]))
+
+
+def test_fk_vs_golden(golden_lib, gpu_model):
+    g = golden("query_golden.npz")
+    bp, br = gpu_model.forward_kinematics(dev(g["root_pos"]), dev(g["root_rot"]), dev(g["joint_rot"]))
+    assert_close(bp, g["body_pos"], what="fk.body_pos")
+    assert_close(br, g["body_rot"], what="fk.body_rot")
+    # arbitrary leading dims
+    bp2, br2 = gpu_model.forward_kinematics(dev(g["root_pos"]).view(3, 100, 3), dev(g["root_rot"]).view(3, 100, 4),
+                                            dev(g["joint_rot"]).view(3, 100, 14, 4))
+    assert bp2.shape == (3, 100, 15, 3) and torch.equal(bp2.view(300, 15, 3), bp)
+    assert torch.equal(br2.view(300, 15, 4), br)
+
+
+def test_fused_query_fk_matches_separate(golden_lib, gpu_model):
+    g = golden("query_golden.npz")
+    r = golden_lib.calc_motion_frame_fk_obs(dev(g["ids"]), dev(g["times"]))
+    assert_close(r["body_pos"], g["body_pos"], what="fused.body_pos")
+    assert_close(r["body_rot"], g["body_rot"], what="fused.body_rot")
+    bp, br = gpu_model.forward_kinematics(r["root_pos"], r["root_rot"], r["joint_rot"])
+    assert torch.equal(bp, r["body_pos"]) and torch.equal(br, r["body_rot"])
+
+
+def test_query_vs_oracle_random_and_edges(golden_lib, O, oracle_tables, oracle_model):
+    gen = torch.Generator().manual_seed(2024)
+    n = 20000
+    ids = torch.randint(0, 3, (n,), generator=gen)
+    lens = oracle_tables.lengths[ids]
+    times = (torch.rand(n, generator=gen) * 3.0 - 1.0) * lens
+    # exact multiples of the frame period and of the clip length (blend == 0 / wrap boundaries)
+    k = torch.arange(n) % 400
+    times[::7] = (k[::7].float() / 30.0)
+    times[::11] = lens[::11] * (k[::11] % 5).float()
+    i0, i1, bl = O.frame_blend(oracle_tables, ids, times)
+    ref = O.calc_motion_frame(oracle_tables, ids, times)
+    rbp, rbr = O.forward_kinematics(oracle_model, ref[0], ref[1], ref[4])
+    r = golden_lib.calc_motion_frame_fk_obs(ids.cuda(), times.cuda())
+    g0, g1, gb = golden_lib._calc_frame_blend(ids.cuda(), times.cuda())
+    assert torch.equal(g0.cpu(), i0) and torch.equal(g1.cpu(), i1) and torch.equal(gb.cpu(), bl)
+    for k_, t in zip(FRAME_KEYS, ref):
+        assert_close(r[k_], t, what=f"query.{k_}")
+    assert_close(r["body_pos"], rbp, what="query.body_pos")
+    assert_close(r["body_rot"], rbr, what="query.body_rot")
+
+
+def test_slerp_branches_bit_exact_decisions(golden_lib, O, oracle_tables):
+    """FIXED joints (identical key frames: |cos| >= 1 -> q0) and slow joints (sin < 1e-3 -> midpoint)
+    take the same branch as the reference: these outputs involve IEEE ops only, so they are exact."""
+    gen = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 3, (4096,), generator=gen)
+    times = torch.rand(4096, generator=gen) * oracle_tables.lengths[ids]
+    ref = O.calc_motion_frame(oracle_tables, ids, times)
+    out = golden_lib.calc_motion_frame(ids.cuda(), times.cuda())
+    i0, i1, bl = O.frame_blend(oracle_tables, ids, times)
+    q0, q1 = oracle_tables.joint_rot[i0], oracle_tables.joint_rot[i1]
+    c = torch.sum(q0 * q1, dim=-1).abs()
+    s = torch.sqrt(1.0 - c * c)
+    non_slerp = (c >= 1) | (s < 0.001)
+    assert non_slerp.any()
+    assert torch.equal(out[4].cpu()[non_slerp], ref[4][non_slerp])
+
+
+def test_empty_and_single_query(golden_lib):
+    e = golden_lib.calc_motion_frame(torch.zeros(0, dtype=torch.long, device="cuda"), torch.zeros(0, device="cuda"))
+    assert e[0].shape == (0, 3) and e[4].shape == (0, 14, 4)
+    one = golden_lib.calc_motion_frame(torch.tensor([1], device="cuda"), torch.tensor([0.5], device="cuda"))
+    assert one[4].shape == (1, 14, 4) and torch.isfinite(one[4]).all()
+
+
+def test_cpu_tensor_raises(golden_lib):
+    from parc_b200._lib import ParcLibraryError
+    with pytest.raises(ParcLibraryError):
+        golden_lib.calc_motion_frame(torch.tensor([0]), torch.tensor([0.1]))
+
+
+def test_motion_frames_loader_quirk(gpu_model):
+    """init_type="motion_frames" reproduces the reference's fps-as-dt dof_vel (anim/motion_lib.py:178)."""
+    from parc_b200.anim.motion_lib import LoopMode, MotionLib
+    g = golden("tables_motion_frames_golden.npz")
+    lib = MotionLib(dev(g["frames"]), gpu_model, "cuda:0", init_type="motion_frames", loop_mode=LoopMode.CLAMP, fps=30,
+                    contact_info=True, contacts=dev(g["contacts"]))
+    assert torch.equal(lib._frame_dof_vel.cpu(), torch.tensor(g["dof_vel"]))
+    assert torch.equal(lib._frame_root_ang_vel.cpu(), torch.tensor(g["root_ang_vel"]))
+    assert torch.equal(lib._frame_joint_rot.cpu(), torch.tensor(g["joint_rot"]))
+    out = lib.calc_motion_frame(torch.tensor([0, 1], device="cuda"), torch.tensor([0.5, 0.25], device="cuda"))
+    assert out[5].shape == (2, 28)
+
+
+# ----------------------------------------------------------------------------------------- dof <-> rot
+def test_dof_to_rot_and_back(gpu_model):
+    civ, g = golden("clip_civilization.npz"), golden("dof_golden.npz")
+    dof = dev(civ["frames"][:, 6:])
+    jr = gpu_model.dof_to_rot(dof)
+    assert_close(jr, g["joint_rot"], what="dof_to_rot")
+    assert_close(gpu_model.rot_to_dof(dev(g["joint_rot"])), g["dof_back"], atol=2e-6, what="rot_to_dof")
+    from parc_b200 import ops
+    assert_close(ops.exp_map_to_quat(dev(civ["frames"][:, 3:6])), g["root_quat"], what="exp_map_to_quat")
+    z = gpu_model.dof_to_rot(torch.zeros(2, 28, device="cuda"))       # exact zeros: identity, no NaN
+    assert torch.equal(z[..., 3], torch.ones(2, 14, device="cuda")) and (z[..., :3] == 0).all()
+
+
+def test_fk_and_dof_gradients_vs_oracle(gpu_model, O, oracle_model):
+    civ = golden("clip_civilization.npz")
+    fr = torch.tensor(civ["frames"][40:72])
+    gen = torch.Generator().manual_seed(3)
+    wp = torch.randn(32, 15, 3, generator=gen)
+    wr = torch.randn(32, 15, 4, generator=gen)
+
+    def run(fk, d2r, e2q, to):
+        a, b, c = (fr[:, 0:3].clone().to(to).requires_grad_(True), fr[:, 3:6].clone().to(to).requires_grad_(True),
+                   fr[:, 6:].clone().to(to).requires_grad_(True))
+        bp, br = fk(a, e2q(b), d2r(c))
+        loss = (bp * wp.to(to)).sum() + (br * wr.to(to)).sum()
+        loss.backward()
+        return loss.detach(), a.grad, b.grad, c.grad
+
+    from parc_b200 import ops
+    ref = run(lambda p, q, j: O.forward_kinematics(oracle_model, p, q, j), lambda d: O.dof_to_rot(oracle_model, d),
+              O.exp_map_to_quat, "cpu")
+    got = run(gpu_model.forward_kinematics, gpu_model.dof_to_rot, ops.exp_map_to_quat, "cuda:0")
+    assert_close(got[0], ref[0], rtol=1e-5, what="fk loss")
+    for nm, a, b in zip(("root_pos", "root_exp", "joint_dof"), got[1:], ref[1:]):
+        assert_close_normwise(a, b, what=f"fk grad {nm}")
+
+
+# ----------------------------------------------------------------------------------------- heightfield
+def _civ_terrain():
+    from parc_b200.util.terrain_util import SubTerrain
+    civ = golden("clip_civilization.npz")
+    t = SubTerrain("civ", x_dim=50, y_dim=50, dx=0.4, dy=0.4, min_x=0.0, min_y=0.0, device="cuda:0")
+    t.hf = dev(civ["hf"])
+    t.min_point = dev(civ["min_point"])
+    t.dxdy = dev(civ["dxdy"])
+    return t
+
+
+def test_grid_index_bit_exact():
+    g = golden("obs_golden.npz")
+    t = _civ_terrain()
+    assert torch.equal(t.get_grid_index(dev(g["ray_xy"])).cpu(), torch.tensor(g["ray_grid_index"]))
+    assert torch.equal(t.get_grid_index(dev(g["probe_xy"])).cpu(), torch.tensor(g["probe_index"]))
+    from parc_b200.util.terrain_util import get_local_hf_from_terrain
+    z = get_local_hf_from_terrain(dev(g["ray_xy"]), t).cpu()
+    hf = torch.tensor(golden("clip_civilization.npz")["hf"])
+    gi = torch.tensor(g["ray_grid_index"])
+    assert torch.equal(z, hf[gi[:, 0], gi[:, 1]])
+    assert torch.equal(t.get_hf_val_from_points(dev(g["ray_xy"]).view(64, 441, 2)).cpu(), z.view(64, 441))
+
+
+def _border_mask(coord, ulps=8):
+    """True where the pre-rounding grid coordinate is within a few fp32 ulps of a half-integer."""
+    c = torch.as_tensor(coord).double()
+    frac = (c - torch.floor(c) - 0.5).abs()
+    tol = ulps * 1.2e-7 * c.abs().clamp(min=1.0)
+    return (frac <= tol).any(dim=-1)
+
+
+def test_ray_obs_vs_golden():
+    from parc_b200.envs.ig_parkour.mgdm_dm_util import refresh_ray_obs_hfs
+    g = golden("obs_golden.npz")
+    t = _civ_terrain()
+    obs = refresh_ray_obs_hfs(dev(g["root_pos"]), dev(g["heading"]), dev(g["tmpl"]), t, -3.0, 3.0).cpu()
+    exp = torch.tensor(g["ray_obs"])
+    mism = (obs != exp)
+    border = _border_mask(g["ray_grid_coord"]).view(64, 441)
+    assert not (mism & ~border).any(), f"{int((mism & ~border).sum())} mismatches away from cell borders"
+    assert mism.float().mean() < 1e-3
+
+
+def test_grid_obs_vs_golden():
+    from parc_b200.util.terrain_util import sample_hf_z_on_terrain
+    g = golden("obs_golden.npz")
+    t = _civ_terrain()
+    z = sample_hf_z_on_terrain(t, dev(g["root_pos"][:16, 0:2]), dev(g["heading"][:16]), 0.2, 0.2, 15, 15, 15, 15).cpu()
+    exp = torch.tensor(g["grid_obs"])
+    assert z.shape == (16, 31, 31)
+    assert (z != exp).float().mean() < 2e-3      # only cell-border samples may differ
+
+
+def test_fused_obs_vs_oracle(golden_lib, O, oracle_tables):
+    g = golden("obs_golden.npz")
+    t = _civ_terrain()
+    gen = torch.Generator().manual_seed(11)
+    n = 2048
+    ids = torch.zeros(n, dtype=torch.long)
+    times = torch.rand(n, generator=gen) * oracle_tables.lengths[0]
+    r = golden_lib.calc_motion_frame_fk_obs(ids.cuda(), times.cuda(), hf_desc=t.hf_desc(), obs_tmpl=dev(g["tmpl"]))
+    ref = O.calc_motion_frame(oracle_tables, ids, times)
+    ot = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
+    heading = O.calc_heading(ref[1])
+    tmpl = torch.tensor(g["tmpl"])
+    exp = O.ray_obs(ot, ref[0], heading, tmpl)
+    coord = O.grid_coord(ot, O.ray_obs_points(ref[0], heading, tmpl))
+    obs = r["obs"].cpu()
+    mism = obs != exp
+    border = _border_mask(coord, ulps=64).view(n, 441)   # heading itself is an atan2 of GPU-vs-host values
+    assert not (mism & ~border).any(), f"{int((mism & ~border).sum())} mismatches away from cell borders"
+    assert mism.float().mean() < 1e-3
+    assert_close(r["body_pos"], O.forward_kinematics(O.CharModel.from_npz(__import__("os").path.join(
+        __import__("conftest").GOLDEN, "humanoid_model.npz")), ref[0], ref[1], ref[4])[0], what="fused body_pos")
+
+
+# ----------------------------------------------------------------------------------------- SDF + losses
+def test_points_hf_sdf_vs_golden():
+    from parc_b200.util.terrain_util import points_hf_sdf
+    g = golden("sdf_golden.npz")
+    dxdy = torch.tensor([0.4, 0.4], device="cuda")
+    for inv, key in ((True, "probe_inv"), (False, "probe_sol")):
+        sd = points_hf_sdf(dev(g["probe_points"]), dev(g["probe_hf"]), torch.zeros(1, 2, device="cuda"), dxdy,
+                           base_z=-10.0, inverted=inv)
+        assert_close(sd, g[key], what=key)
+    t = _civ_terrain()
+    for inv, key in ((True, "clip_inv"), (False, "clip_sol")):
+        sd = points_hf_sdf(dev(g["clip_points"]), t.hf.unsqueeze(0), t.min_point.unsqueeze(0), t.dxdy, base_z=-10.0,
+                           inverted=inv)
+        assert_close(sd, g[key], what=key)
+
+
+def test_compute_motion_loss_vs_golden(gpu_model):
+    from parc_b200.tools.procgen.mdm_path import compute_motion_loss
+    from parc_b200.util import geom_util
+    from parc_b200.util.motion_util import MotionFrames
+    g = golden("loss_golden.npz")
+    mf = MotionFrames(root_pos=dev(g["ml_root_pos"]), root_rot=dev(g["ml_root_rot"]), joint_rot=dev(g["ml_joint_rot"]),
+                      contacts=dev(g["ml_contacts"]))
+    pts = geom_util.get_char_point_samples(gpu_model)
+    out = compute_motion_loss(mf, None, _civ_terrain(), gpu_model, pts, w_contact=0.1, w_pen=0.1, w_path=0.0)
+    assert_close(out["pen_loss"], g["ml_pen"], what="pen_loss")
+    assert_close(out["contact_loss"], g["ml_contact"], what="contact_loss")
+    assert_close(out["total_loss"], g["ml_total"], what="total_loss")
+
+
+def test_motion_opt_loss_and_gradients_vs_golden(gpu_model):
+    from parc_b200.tools.motion_opt.motion_optimization import LossType, motion_terrain_contact_loss
+    from parc_b200.util import geom_util
+    g = golden("loss_golden.npz")
+    pts = geom_util.get_char_point_samples(gpu_model)
+    t = _civ_terrain()
+
+    def run(others):
+        a, b, c = (dev(g[k]).clone().requires_grad_(True) for k in ("mo_root_pos", "mo_root_exp", "mo_joint_dof"))
+        loss, ld = motion_terrain_contact_loss(
+            a, b, c, dev(g["mo_src_root_pos"]), dev(g["mo_src_root_quat"]), dev(g["mo_src_joint_rot"]),
+            dev(g["mo_src_body_vels"]), dev(g["mo_src_body_rot_vels"]), dev(g["mo_contacts"]), t, pts, gpu_model,
+            w_root_pos=others, w_root_rot=others, w_joint_rot=others, w_smoothness=others, w_penetration=1000.0,
+            w_contact=1000.0, w_sliding=others, w_body_constraints=0.0, w_jerk=others, body_constraints=None,
+            max_jerk=1000.0)
+        loss.backward()
+        return loss.detach(), ld, a.grad, b.grad, c.grad
+
+    loss, ld, ga, gb, gc = run(0.0)
+    assert_close(loss, g["mo_loss_pc"], what="loss (pen+contact)")
+    assert_close(torch.tensor(ld[LossType.PENETRATION_LOSS]), g["mo_pen"], what="pen term")
+    assert_close(torch.tensor(float(ld[LossType.CONTACT_LOSS])), g["mo_contact"], what="contact term")
+    assert_close_normwise(ga, g["mo_grad_root_pos"], what="grad root_pos")
+    assert_close_normwise(gb, g["mo_grad_root_exp"], what="grad root_rot")
+    assert_close_normwise(gc, g["mo_grad_joint_dof"], what="grad joint_dof")
+    # all terms on (tracking, smoothness, sliding, jerk): same bar
+    loss, ld, ga, gb, gc = run(1.0)
+    assert_close(loss, g["mo_loss_all"], what="loss (all terms)")
+    assert_close_normwise(ga, g["mo_all_grad_root_pos"], what="grad root_pos (all)")
+    assert_close_normwise(gb, g["mo_all_grad_root_exp"], what="grad root_rot (all)")
+    assert_close_normwise(gc, g["mo_all_grad_joint_dof"], what="grad joint_dof (all)")
+
+
+def test_body_loss_vs_oracle_synthetic(gpu_model, O, oracle_model):
+    """Config-3-shaped inputs at a size the oracle finishes in seconds: B=3 samples x F=6 frames on
+    three different 16x16 box / stair terrains (per-sample terrain), fwd + bwd."""
+    from parc_b200 import ops
+    from parc_b200.tools.procgen.mdm_path import body_points_desc
+    from parc_b200.util import geom_util, synth
+    rng = np.random.default_rng(42)
+    B, F = 3, 6
+    hfs = np.stack([synth.box_terrain(rng), synth.stairs_terrain(rng), synth.box_terrain(rng, h_range=(-0.5, 0.6))])
+    smp = [synth.synth_motion_samples(gpu_model, 1, F, hfs[i], (0.0, 0.0), (0.4, 0.4), seed=100 + i) for i in range(B)]
+    cat = lambda k: torch.tensor(np.concatenate([s[k] for s in smp], axis=0))
+    root_pos, root_exp, joint_dof, contacts = cat("root_pos"), cat("root_exp"), cat("joint_dof"), cat("contacts")
+    dxdy = torch.tensor([0.4, 0.4])
+    mins = torch.zeros(B, 2)
+
+    # oracle: per-sample terrain -> loop over samples
+    leaves = [t.clone().requires_grad_(True) for t in (root_pos, root_exp, joint_dof)]
+    tot = 0.0
+    pens, cons = [], []
+    for i in range(B):
+        rq = O.exp_map_to_quat(leaves[1][i])
+        jr = O.dof_to_rot(oracle_model, leaves[2][i])
+        bp, br = O.forward_kinematics(oracle_model, leaves[0][i], rq, jr)
+        pen, con = O.pen_contact_terms(bp.unsqueeze(0), br.unsqueeze(0), contacts[i].unsqueeze(0),
+                                       oracle_model.body_points, torch.tensor(hfs[i]), mins[i], dxdy, -10.0)
+        pens.append(pen[0]); cons.append(con[0])
+        tot = tot + 0.7 * pen[0] + 1.3 * con[0]
+    tot.backward()
+
+    g_leaves = [t.clone().cuda().requires_grad_(True) for t in (root_pos, root_exp, joint_dof)]
+    pts = body_points_desc(gpu_model, geom_util.get_char_point_samples(gpu_model))
+    tb = ops.make_terrain_batch(torch.tensor(hfs).cuda(), mins.cuda(), (0.4, 0.4), base_z=-10.0)
+    rq = ops.exp_map_to_quat(g_leaves[1])
+    jr = gpu_model.dof_to_rot(g_leaves[2])
+    total, pen, con = ops.body_loss(gpu_model.c_model(), pts, tb, g_leaves[0], rq, jr, contacts.cuda(), 0.7, 1.3)
+    total.sum().backward()
+    assert_close(pen, torch.stack(pens).detach(), what="pen")
+    assert_close(con, torch.stack(cons).detach(), what="contact")
+    assert float(torch.stack(pens).sum()) > 0 and float(torch.stack(cons).abs().sum()) > 0
+    for nm, a, b in zip(("root_pos", "root_exp", "joint_dof"), g_leaves, leaves):
+        assert_close_normwise(a.grad, b.grad, what=f"body_loss grad {nm}")
+
+
+def test_body_loss_linearity_full_size(gpu_model):
+    """Size-independent property at config-3 scale (B=64 here x F=150): the loss is a sum over frames, so
+    evaluating two halves of the frames separately and adding must reproduce the whole; and gradients of
+    frame f do not depend on other frames."""
+    from parc_b200 import ops
+    from parc_b200.tools.procgen.mdm_path import body_points_desc
+    from parc_b200.util import geom_util, synth
+    rng = np.random.default_rng(1)
+    B, F = 64, 150
+    hf = synth.box_terrain(rng)
+    s = synth.synth_motion_samples(gpu_model, B, F, hf, (0.0, 0.0), (0.4, 0.4), seed=5)
+    rp = torch.tensor(s["root_pos"]).cuda()
+    rq = ops.exp_map_to_quat(torch.tensor(s["root_exp"]).cuda())
+    jr = gpu_model.dof_to_rot(torch.tensor(s["joint_dof"]).cuda())
+    ct = torch.tensor(s["contacts"]).cuda()
+    pts = body_points_desc(gpu_model, geom_util.get_char_point_samples(gpu_model))
+    tb = ops.make_terrain_batch(torch.tensor(hf).cuda(), torch.zeros(2).cuda(), (0.4, 0.4), base_z=-10.0)
+    m = gpu_model.c_model()
+    _, pen, con = ops.body_loss(m, pts, tb, rp, rq, jr, ct, 1.0, 1.0)
+    h = F // 2
+    _, pen_a, con_a = ops.body_loss(m, pts, tb, rp[:, :h].contiguous(), rq[:, :h].contiguous(), jr[:, :h].contiguous(),
+                                    ct[:, :h].contiguous(), 1.0, 1.0)
+    _, pen_b, con_b = ops.body_loss(m, pts, tb, rp[:, h:].contiguous(), rq[:, h:].contiguous(), jr[:, h:].contiguous(),
+                                    ct[:, h:].contiguous(), 1.0, 1.0)
+    assert_close(pen_a + pen_b, pen, rtol=1e-5, what="pen additivity")
+    assert_close(con_a + con_b, con, rtol=1e-5, atol=1e-5, what="contact additivity")
+    assert (pen >= 0).all() and torch.isfinite(pen).all() and torch.isfinite(con).all()
