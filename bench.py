@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--clips", type=int, default=2048)
     ap.add_argument("--impl", default="parc_b200", choices=["parc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-soak", action="store_true", help="skip the clock-sampling soak loop (profiler runs)")
     return ap.parse_args()
 
 
@@ -238,8 +239,12 @@ def main():
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    # one prebuilt launch per resident input batch, all writing the same output buffers
+    plans = [mlib.make_query_plan(ids_d[b], times_d[b], hf_desc=hfd, obs_tmpl=tmpl, out=out) for b in range(NB)]
+    raw_stream = stream.cuda_stream
+
     def step(i):
-        mlib.calc_motion_frame_fk_obs(ids_d[i % NB], times_d[i % NB], hf_desc=hfd, obs_tmpl=tmpl, out=out)
+        plans[i % NB].launch(raw_stream)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -281,7 +286,7 @@ def main():
     ids_p, times_p = ids_h.pin_memory(), times_h.pin_memory()
     ids_in = torch.empty(args.envs, dtype=torch.int64, device=dev)
     times_in = torch.empty(args.envs, dtype=torch.float32, device=dev)
-    e2e_out = {}
+    e2e_plan = mlib.make_query_plan(ids_in, times_in, hf_desc=hfd, obs_tmpl=tmpl, out={})
     keys = ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts", "body_pos",
             "body_rot", "obs")
     host_out = None
@@ -290,7 +295,7 @@ def main():
         nonlocal host_out
         ids_in.copy_(ids_p[i % NB], non_blocking=True)
         times_in.copy_(times_p[i % NB], non_blocking=True)
-        r = mlib.calc_motion_frame_fk_obs(ids_in, times_in, hf_desc=hfd, obs_tmpl=tmpl, out=e2e_out)
+        r = e2e_plan.launch(raw_stream)
         if host_out is None:
             host_out = {k: torch.empty(r[k].shape, dtype=r[k].dtype).pin_memory() for k in keys}
         for k in keys:
@@ -313,7 +318,7 @@ def main():
     d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in keys)
 
     # ---- soak: keep the kernel running ~1.5 s so the clock sampler sees the GPU under this load ----
-    t_end = time.perf_counter() + 1.5
+    t_end = time.perf_counter() + (0.0 if args.no_soak else 1.5)
     i = 0
     while time.perf_counter() < t_end:
         for _ in range(200):

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define PARC_ABI_VERSION 1
-#define PARC_MAX_BODIES 24   /* pose part of a packed row must fit one warp: 1 + J + ceil(J/4) <= 32 */
+#define PARC_MAX_BODIES 24   /* position + rotation slots of a packed row must fit one warp: J + 1 <= 32 */
 #define PARC_MAX_DOF 96
 
 /* negative = argument rejected; positive = cudaError_t */
@@ -66,14 +66,14 @@ typedef struct ParcCharModel {
  *   slot 1            root_rot xyzw
  *   slot 2 .. J       joint_rot[0..J-2] xyzw
  *   slot J+1 ..       contacts[0..J-1], zero padded to a multiple of 4
- *   vel part          root_vel(3) root_ang_vel(3) dof_vel(D), zero padded
+ *   vel part          slot 0 root_vel.xyz,pad; slot 1 root_ang_vel.xyz,pad; slots 2.. dof_vel(D), zero padded
  * Replaces the eight separate MotionLib tables (anim/motion_lib.py:349-375). */
 typedef struct ParcRowLayout {
   int32_t row_floats;      /* stride in floats (multiple of 8) */
   int32_t pose_slots;      /* float4 slots read at BOTH key frames: 2 + (J-1) + ceil(J/4) */
   int32_t contact_slot;    /* first contact slot = J + 1 */
   int32_t vel_slot;        /* first velocity slot = pose_slots */
-  int32_t vel_slots;       /* ceil((6 + D) / 4) */
+  int32_t vel_slots;       /* 2 + ceil(D / 4) */
   int32_t reserved[3];
 } ParcRowLayout;
 
@@ -188,6 +188,13 @@ int parc_exp_map_to_quat_bwd(const float* exp_map, const float* g_quat, int64_t 
  * :1329-1346).  grid_idx_out (int64 [N,2]) may be NULL. */
 int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_t n, float* z_out,
                    int64_t* grid_idx_out, void* stream);
+
+/* Self test of the hoisted-reciprocal grid index used in the observation loops: compares it with the
+ * reference form clamp(rint((p - min) / cell) ...) using a true IEEE division, for EVERY float bit
+ * pattern of p (2^32 inputs), and adds the number of differing indices to *mismatches_dev (device
+ * uint64, caller-zeroed).  Expected: 0. */
+int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint64_t* mismatches_dev,
+                             void* stream);
 
 /* a10/a11: RefCharEnv._refresh_ray_obs_hfs (envs/ig_parkour/mgdm_dm_util.py:158-179) and
  * sample_hf_z_on_terrain (util/terrain_util.py:2049-2082) with caller-supplied root and heading.

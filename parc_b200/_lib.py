@@ -106,6 +106,7 @@ SIGNATURES = {
     "parc_exp_map_to_quat_fwd": (C.c_int, [_V, _I64, _V, _V]),
     "parc_exp_map_to_quat_bwd": (C.c_int, [_V, _V, _I64, _V, _V]),
     "parc_hf_sample": (C.c_int, [_P(ParcHeightfield), _V, _I64, _V, _V, _V]),
+    "parc_selftest_grid_index": (C.c_int, [_F, _F, _I32, _V, _V]),
     "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _I64, _V, _V]),
     "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),

@@ -146,6 +146,15 @@ class MotionLib:
                                 want_contacts=self._contact_info, want_fk=True, hf=hf_desc, obs_tmpl=obs_tmpl,
                                 obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out)
 
+    def make_query_plan(self, motion_ids, motion_times, hf_desc=None, obs_tmpl=None, obs_relative=True,
+                        min_obs_h=-3.0, max_obs_h=3.0, want_fk=True, out=None):
+        """Prebuilt launch of `calc_motion_frame_fk_obs` over fixed input/output buffers: returns an
+        `ops.MotionQueryPlan` whose `.launch()` costs one C call.  Update `motion_ids` / `motion_times`
+        in place between launches (as the tracker does with its time buffer)."""
+        return ops.MotionQueryPlan(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times,
+                                   want_contacts=self._contact_info, want_fk=want_fk, hf=hf_desc, obs_tmpl=obs_tmpl,
+                                   obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out)
+
     def joint_rot_to_dof(self, joint_rot):
         return self._kin_char_model.rot_to_dof(joint_rot)
 

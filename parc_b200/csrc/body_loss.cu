@@ -344,11 +344,11 @@ using namespace parc;
 extern "C" int parc_points_hf_sdf(const float* points, int64_t batch, int64_t n_points,
                                   const ParcTerrainBatch* terrain, int32_t inverted, float* sdf_out,
                                   int32_t* arg_out, void* stream) {
+  if (batch < 0 || n_points < 0 || batch > 65535) return PARC_E_SIZE;
+  if (batch == 0 || n_points == 0) return PARC_OK;
   if (!points || !sdf_out) return PARC_E_NULL;
   int rc = check_terrain(terrain);
   if (rc) return rc;
-  if (batch < 0 || n_points < 0 || batch > 65535) return PARC_E_SIZE;
-  if (batch == 0 || n_points == 0) return PARC_OK;
   const size_t smem = terrain_smem_bytes(terrain);
   if (smem > 200 * 1024) return PARC_E_SIZE;          // terrain tile must fit one SM's shared memory
   if (smem > 48 * 1024) {
@@ -368,13 +368,15 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
                               const ParcBodyPoints* pts, const ParcTerrainBatch* terrain, float w_pen,
                               float w_contact, float* pen_out, float* contact_out, float* g_root_pos,
                               float* g_root_rot, float* g_joint_rot, void* stream) {
-  if (!root_pos || !root_rot || !contacts || !model || !pts || !pts->points || !pts->point_start) return PARC_E_NULL;
+  if (!model || !pts) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
+  if (batch < 0 || frames < 0 || batch > 65535 || pts->num_points <= 0) return PARC_E_SIZE;
+  if (batch == 0 || frames == 0) return PARC_OK;
+  if (!root_pos || !root_rot || !contacts || !pts->points || !pts->point_start) return PARC_E_NULL;
   if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
   rc = check_terrain(terrain);
   if (rc) return rc;
-  if (batch < 0 || frames < 0 || batch > 65535 || pts->num_points <= 0) return PARC_E_SIZE;
   if (!aligned16(root_rot) || !aligned16(joint_rot) || !aligned16(g_root_rot) || !aligned16(g_joint_rot))
     return PARC_E_ALIGN;
   if (batch == 0 || frames == 0) return PARC_OK;

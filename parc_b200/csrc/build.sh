@@ -6,12 +6,11 @@ out="${here}/../libparc_b200.so"
 NVCC="${NVCC:-nvcc}"
 COMMON="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 mkdir -p "${here}/build"
-# motion_query / fk / heightfield: no FMA contraction, so separate mul/add round like the reference's
-# eager fp32 op chain (decision-critical spots additionally use explicit *_rn intrinsics).
+# FMA contraction stays enabled: every rounding that decides an index or a branch uses explicit *_rn
+# intrinsics (parc_common.cuh), which never contract.
 for f in motion_query fk heightfield api; do
-  "${NVCC}" ${COMMON} -fmad=false ${EXTRA_NVCC_FLAGS:-} -c "${here}/${f}.cu" -o "${here}/build/${f}.o" &
+  "${NVCC}" ${COMMON} ${EXTRA_NVCC_FLAGS:-} -c "${here}/${f}.cu" -o "${here}/build/${f}.o" &
 done
-# body_loss is ALU-bound (brute-force SDF scan): FMA contraction allowed.
 "${NVCC}" ${COMMON} ${EXTRA_NVCC_FLAGS:-} -c "${here}/body_loss.cu" -o "${here}/build/body_loss.o" &
 wait
 "${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -o "${out}" "${here}"/build/{motion_query,fk,heightfield,api,body_loss}.o

@@ -253,11 +253,13 @@ using namespace parc;
 
 extern "C" int parc_fk_fwd(const float* root_pos, const float* root_rot, const float* joint_rot, int64_t n,
                            const ParcCharModel* model, float* body_pos, float* body_rot, void* stream) {
-  if (!root_pos || !root_rot || !model) return PARC_E_NULL;
+  if (!model) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
-  if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!root_pos || !root_rot) return PARC_E_NULL;
+  if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
   if (!aligned16(root_rot) || !aligned16(joint_rot) || !aligned16(body_rot)) return PARC_E_ALIGN;
   if (n == 0) return PARC_OK;
   fk_fwd_kernel<<<warp_grid(n), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(root_pos, root_rot, joint_rot, n,
@@ -268,11 +270,13 @@ extern "C" int parc_fk_fwd(const float* root_pos, const float* root_rot, const f
 extern "C" int parc_fk_bwd(const float* root_rot, const float* joint_rot, const float* g_body_pos,
                            const float* g_body_rot, int64_t n, const ParcCharModel* model, float* g_root_pos,
                            float* g_root_rot, float* g_joint_rot, void* stream) {
-  if (!root_rot || !model) return PARC_E_NULL;
+  if (!model) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
-  if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!root_rot) return PARC_E_NULL;
+  if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
   if (!aligned16(root_rot) || !aligned16(joint_rot) || !aligned16(g_body_rot) || !aligned16(g_root_rot) ||
       !aligned16(g_joint_rot))
     return PARC_E_ALIGN;
@@ -284,10 +288,12 @@ extern "C" int parc_fk_bwd(const float* root_rot, const float* joint_rot, const 
 
 extern "C" int parc_dof_to_rot_fwd(const float* dof, int64_t n, const ParcCharModel* model, float* joint_rot,
                                    void* stream) {
-  if (!dof || !joint_rot || !model) return PARC_E_NULL;
+  if (!model) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!dof || !joint_rot) return PARC_E_NULL;
   if (!aligned16(joint_rot)) return PARC_E_ALIGN;
   if (n == 0 || model->num_bodies < 2) return PARC_OK;
   dof_to_rot_fwd_kernel<<<flat_grid(n * (model->num_bodies - 1)), 256, 0, (cudaStream_t)stream>>>(dof, n, *model,
@@ -297,10 +303,12 @@ extern "C" int parc_dof_to_rot_fwd(const float* dof, int64_t n, const ParcCharMo
 
 extern "C" int parc_dof_to_rot_bwd(const float* dof, const float* g_joint_rot, int64_t n,
                                    const ParcCharModel* model, float* g_dof, void* stream) {
-  if (!dof || !g_joint_rot || !g_dof || !model) return PARC_E_NULL;
+  if (!model) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!dof || !g_joint_rot || !g_dof) return PARC_E_NULL;
   if (!aligned16(g_joint_rot)) return PARC_E_ALIGN;
   if (n == 0 || model->num_bodies < 2) return PARC_OK;
   dof_to_rot_bwd_kernel<<<flat_grid(n * (model->num_bodies - 1)), 256, 0, (cudaStream_t)stream>>>(
@@ -309,8 +317,9 @@ extern "C" int parc_dof_to_rot_bwd(const float* dof, const float* g_joint_rot, i
 }
 
 extern "C" int parc_exp_map_to_quat_fwd(const float* exp_map, int64_t n, float* quat, void* stream) {
-  if (!exp_map || !quat) return PARC_E_NULL;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!exp_map || !quat) return PARC_E_NULL;
   if (!aligned16(quat)) return PARC_E_ALIGN;
   if (n == 0) return PARC_OK;
   exp_map_fwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(exp_map, n, quat);
@@ -319,8 +328,9 @@ extern "C" int parc_exp_map_to_quat_fwd(const float* exp_map, int64_t n, float* 
 
 extern "C" int parc_exp_map_to_quat_bwd(const float* exp_map, const float* g_quat, int64_t n, float* g_exp_map,
                                         void* stream) {
-  if (!exp_map || !g_quat || !g_exp_map) return PARC_E_NULL;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!exp_map || !g_quat || !g_exp_map) return PARC_E_NULL;
   if (!aligned16(g_quat)) return PARC_E_ALIGN;
   if (n == 0) return PARC_OK;
   exp_map_bwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(exp_map, g_quat, n, g_exp_map);

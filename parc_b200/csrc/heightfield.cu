@@ -65,8 +65,9 @@ extern "C" int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_
                               int64_t* grid_idx_out, void* stream) {
   int rc = check_hf(hf);
   if (rc) return rc;
-  if (!xy || (!z_out && !grid_idx_out)) return PARC_E_NULL;
   if (n < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!xy || (!z_out && !grid_idx_out)) return PARC_E_NULL;
   if ((reinterpret_cast<uintptr_t>(xy) & 7u) != 0) return PARC_E_ALIGN;
   if (n == 0) return PARC_OK;
   hf_sample_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(*hf, xy, n, z_out, grid_idx_out);
@@ -77,8 +78,10 @@ extern "C" int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, co
                            int32_t root_stride, const float* heading, int64_t n, float* obs_out, void* stream) {
   int rc = check_hf(hf);
   if (rc) return rc;
-  if (!obs || !obs->tmpl_xy || !root || !heading || !obs_out) return PARC_E_NULL;
+  if (!obs) return PARC_E_NULL;
   if (n < 0 || obs->num_points < 0 || root_stride < (obs->relative ? 3 : 2)) return PARC_E_SIZE;
+  if (n == 0 || obs->num_points == 0) return PARC_OK;
+  if (!obs->tmpl_xy || !root || !heading || !obs_out) return PARC_E_NULL;
   if ((reinterpret_cast<uintptr_t>(obs->tmpl_xy) & 7u) != 0) return PARC_E_ALIGN;
   if (n == 0 || obs->num_points == 0) return PARC_OK;
   hf_obs_kernel<<<flat_grid(n * obs->num_points), 256, 0, (cudaStream_t)stream>>>(*hf, *obs, root, root_stride,

@@ -46,31 +46,100 @@ __device__ __forceinline__ void frame_blend(const ParcClipMeta& cm, float t, int
   i1 = cm.start_idx + f1;
 }
 
-template <bool BLEND>
-__global__ void __launch_bounds__(PARC_CTA_THREADS)
+// heightfield gathers kept in flight per lane: INFLIGHT * G covers the 441-point ray template in one sweep
+#define PARC_TMPL_SMEM_MAX 2048  // observation templates up to this many points are staged in shared memory
+
+__device__ __forceinline__ float shfl_g(float v, int src, int width) {
+  return __shfl_sync(PARC_FULL_MASK, v, src, width);
+}
+
+// Per-query constants of the observation sweep (packed f32x2 operands).
+struct ObsCtx {
+  float2 cc, ss, off, neg_min, inv2, neg_d;
+  int hix, hiy, dim_y;
+};
+
+// World cell of template point tp: the same individually-rounded operations as the reference's
+// rotate_2d_vec + root offset + (p - min) / dxdy + round + clamp, in packed FMUL2 / FADD2 / FFMA2.
+__device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
+  const float2 t1 = __fmul2_rn(tp, c.cc);                       // (x cos, y cos)
+  const float2 t2 = __fmul2_rn(tp, c.ss);                       // (x sin, y sin)
+  float2 w = make_float2(sub_rn(t1.x, t2.y), add_rn(t2.x, t1.y));
+  w = __fadd2_rn(w, c.off);
+  const float2 v = __fadd2_rn(w, c.neg_min);                    // p - min
+  const float2 q0 = __fmul2_rn(v, c.inv2);
+  const float2 r = __ffma2_rn(c.neg_d, q0, v);
+  const float2 qd = __ffma2_rn(r, c.inv2, q0);                  // == (p - min) / d, IEEE (see GridAxis)
+  int ix = min(max(__float2int_rn(qd.x), 0), c.hix);
+  int iy = min(max(__float2int_rn(qd.y), 0), c.hiy);
+  if (qd.x >= 9.2e18f) ix = 0;                                  // int64 wrap of the reference
+  if (qd.y >= 9.2e18f) iy = 0;
+  return ix * c.dim_y + iy;
+}
+
+// One GROUP of G lanes per query: G = 32 is the general layout, G = 16 packs two characters into a warp
+// (the humanoid's 1 position + 15 rotation slots fill exactly 16 lanes), which halves the issue cost of
+// everything except the observation sweep.  Requires J + 1 <= G.
+//   group lane 0        root position (float4 slot 0)
+//   group lanes 1..J    root / joint rotations (slots 1..J), later the bodies of the FK chain
+//   contacts            slots J+1.. are fetched in a second pass by the first lanes of the group
+//   velocities          slots vel_slot.. by the first vel_slots lanes (looped if vel_slots > G)
+// Latency structure per query: [ids, times | template + tree staging] -> clip meta -> frame rows ->
+// heightfield gathers; the gathers of the first INFLIGHT * G template points are all issued
+// BEFORE the FK chain and consumed after it, so that round trip hides behind the FK math.
+template <bool BLEND, int G, int INFLIGHT>
+__global__ void __launch_bounds__(PARC_CTA_THREADS, 4)   // <= 128 registers: 16 warps (4 CTAs) per SM
 motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant__ ParcCharModel model_param) {
-  __shared__ ParcCharModel sm;
-  stage_model(&sm, model_param);
+  __shared__ TreeSmem sm;
+  extern __shared__ float2 s_tmpl[];
+  constexpr int GROUPS = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int l = lane & (G - 1);
+  const int grp = lane / G;
+  const int64_t first = ((int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5)) * GROUPS;
+  const int64_t stride = (int64_t)gridDim.x * PARC_WARPS_PER_CTA * GROUPS;
+  const int P = p.obs.num_points;
+  const bool tmpl_in_smem = p.want_obs && P <= PARC_TMPL_SMEM_MAX;
+
+  // Prologue: everything that does not depend on anything else is requested up front so the cold misses
+  // overlap -- this group's first id / time, the observation template, the kinematic tree.
+  int64_t id_pre = 0;
+  float t_pre = 0.0f;
+  int64_t f_pre = 0;
+  {
+    const int64_t q0 = first + grp < p.n ? first + grp : p.n - 1;
+    id_pre = __ldg(p.ids + q0);
+    if (BLEND) t_pre = __ldg(p.times + q0); else f_pre = __ldg(p.frame_idx + q0);
+  }
+  if (tmpl_in_smem) {
+    const float2* __restrict__ g = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_tmpl[i] = __ldg(g + i);
+  }
+  stage_tree(&sm, model_param);
   __syncthreads();
 
-  const int lane = threadIdx.x & 31;
   const int J = sm.num_bodies;
   const int D = sm.dof_size;
-  const LaneBody lb = load_lane_body(sm, lane, /*lane_of_body0=*/1);
+  const LaneBody lb = load_lane_body(sm, l, /*lane_of_body0=*/1);
   const int max_depth = sm.max_depth;
   const int row_f4 = p.lay.row_floats >> 2;
-  const int pose_slots = p.lay.pose_slots;
-  const int contact_slot = p.lay.contact_slot;
-  const int vel_slot = p.lay.vel_slot;
-  const int vel_slots = p.lay.vel_slots;
   const float4* __restrict__ rows = reinterpret_cast<const float4*>(p.tb.rows);
+  const float2* __restrict__ tmpl = tmpl_in_smem ? s_tmpl : reinterpret_cast<const float2*>(p.obs.tmpl_xy);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool relative = p.obs.relative != 0;
 
-  const int64_t warp0 = (int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * PARC_WARPS_PER_CTA;
-
-  for (int64_t q = warp0; q < p.n; q += nwarps) {
-    // ---- clip metadata + frame indices (warp-uniform; every lane computes the same values) ----
-    int64_t id = __ldg(p.ids + q);
+  for (int64_t base = first; base < p.n; base += stride) {
+    const int64_t qq = base + grp;
+    const bool active = qq < p.n;
+    const int64_t q = active ? qq : p.n - 1;
+    // ---- clip metadata + frame indices (uniform within the group) ----
+    int64_t id = id_pre;
+    float t_q = t_pre;
+    int64_t f_q = f_pre;
+    if (base != first) {
+      id = __ldg(p.ids + q);
+      if (BLEND) t_q = __ldg(p.times + q); else f_q = __ldg(p.frame_idx + q);
+    }
     if (id < 0 || id >= p.tb.num_clips) id = 0;   // reference would raise an index error
     const int4* cmp = reinterpret_cast<const int4*>(p.tb.clips + id);
     const int4 c0 = __ldg(cmp);
@@ -87,26 +156,30 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     int64_t i0, i1;
     float blend = 0.0f, cycles = 0.0f;
     if (BLEND) {
-      frame_blend(cm, __ldg(p.times + q), i0, i1, blend, cycles);
+      frame_blend(cm, t_q, i0, i1, blend, cycles);
     } else {
-      i0 = i1 = cm.start_idx + __ldg(p.frame_idx + q);
+      i0 = i1 = cm.start_idx + f_q;
     }
-
-    // ---- gather: one float4 per lane per key frame, plus the velocity slots of frame 0 ----
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* r0 = rows + i0 * row_f4;
-    const float4 A = lane < pose_slots ? __ldg(r0 + lane) : zero4;
-    float4 B = A;
-    if (BLEND) {
-      const float4* r1 = rows + i1 * row_f4;
-      B = lane < pose_slots ? __ldg(r1 + lane) : zero4;
-    }
-    const float4 V = lane < vel_slots ? __ldg(r0 + vel_slot + lane) : zero4;
+    const float4* r1 = rows + i1 * row_f4;
 
-    // ---- blend by role ----
-    float4 R = A;  // result of this lane's slot
+    // ---- all row loads of this query are issued together ----
+    const bool own = l <= J;
+    const float4 A = own ? __ldg(r0 + l) : zero4;
+    const float4 B = (BLEND && own) ? __ldg(r1 + l) : A;
+    const int cs_ = p.lay.contact_slot + l;                  // contacts: first lanes of the group
+    const bool has_c = p.out.contacts != nullptr && cs_ < p.lay.pose_slots;
+    const float4 CA = has_c ? __ldg(r0 + cs_) : zero4;
+    const float4 CB = (BLEND && has_c) ? __ldg(r1 + cs_) : CA;
+    const bool has_v = l < p.lay.vel_slots && (p.out.root_vel || p.out.root_ang_vel || p.out.dof_vel);
+    const float4 V = has_v ? __ldg(r0 + p.lay.vel_slot + l) : zero4;
+
+    // ---- blend position (lane 0) / rotations (lanes 1..J) ----
+    float4 R = A;
     if (BLEND) {
-      if (lane == 0) {
+      if (l >= 1) {
+        R = slerp(A, B, blend);
+      } else {
         R.x = lerp_rn(A.x, B.x, blend);
         R.y = lerp_rn(A.y, B.y, blend);
         R.z = lerp_rn(A.z, B.z, blend);
@@ -115,84 +188,104 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
           R.y = add_rn(R.y, mul_rn(cycles, cm.root_pos_delta[1]));
           R.z = add_rn(R.z, mul_rn(cycles, cm.root_pos_delta[2]));
         }
-      } else if (lane <= J) {
-        R = slerp(A, B, blend);
-      } else if (lane < pose_slots) {
-        R.x = lerp_rn(A.x, B.x, blend);
-        R.y = lerp_rn(A.y, B.y, blend);
-        R.z = lerp_rn(A.z, B.z, blend);
-        R.w = lerp_rn(A.w, B.w, blend);
       }
     }
-
-    // ---- frame outputs ----
-    if (lane == 0) {
-      if (p.out.root_pos) {
-        float* o = p.out.root_pos + q * 3;
-        o[0] = R.x; o[1] = R.y; o[2] = R.z;
+    if (active) {
+      if (l == 0) {
+        if (p.out.root_pos) {
+          float* o = p.out.root_pos + q * 3;
+          o[0] = R.x; o[1] = R.y; o[2] = R.z;
+        }
+        if (p.out.frame_idx0) p.out.frame_idx0[q] = i0;
+        if (p.out.frame_idx1) p.out.frame_idx1[q] = i1;
+        if (p.out.blend) p.out.blend[q] = blend;
+      } else if (l == 1) {
+        if (p.out.root_rot) reinterpret_cast<float4*>(p.out.root_rot)[q] = R;
+      } else if (own) {
+        if (p.out.joint_rot) reinterpret_cast<float4*>(p.out.joint_rot)[q * (J - 1) + (l - 2)] = R;
       }
-      if (p.out.frame_idx0) p.out.frame_idx0[q] = i0;
-      if (p.out.frame_idx1) p.out.frame_idx1[q] = i1;
-      if (p.out.blend) p.out.blend[q] = blend;
-    } else if (lane == 1) {
-      if (p.out.root_rot) reinterpret_cast<float4*>(p.out.root_rot)[q] = R;
-    } else if (lane <= J) {
-      if (p.out.joint_rot) reinterpret_cast<float4*>(p.out.joint_rot)[q * (J - 1) + (lane - 2)] = R;
-    } else if (lane < pose_slots) {
-      if (p.out.contacts) {
-        const int k = (lane - contact_slot) * 4;
-        float* o = p.out.contacts + q * J + k;
-        if (k + 0 < J) o[0] = R.x;
-        if (k + 1 < J) o[1] = R.y;
-        if (k + 2 < J) o[2] = R.z;
-        if (k + 3 < J) o[3] = R.w;
+      // contacts, lerped (anim/motion_lib.py:109)
+      if (has_c) {
+        float4 c = CA;
+        if (BLEND) {
+          c.x = lerp_rn(CA.x, CB.x, blend); c.y = lerp_rn(CA.y, CB.y, blend);
+          c.z = lerp_rn(CA.z, CB.z, blend); c.w = lerp_rn(CA.w, CB.w, blend);
+        }
+        const int ck = l * 4;
+        float* o = p.out.contacts + q * J + ck;
+        o[0] = c.x;
+        if (ck + 1 < J) o[1] = c.y;
+        if (ck + 2 < J) o[2] = c.z;
+        if (ck + 3 < J) o[3] = c.w;
       }
-    }
-    if (lane < vel_slots) {
-      const float v[4] = {V.x, V.y, V.z, V.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int k = lane * 4 + c;
-        if (k < 3) {
-          if (p.out.root_vel) p.out.root_vel[q * 3 + k] = v[c];
-        } else if (k < 6) {
-          if (p.out.root_ang_vel) p.out.root_ang_vel[q * 3 + (k - 3)] = v[c];
-        } else if (k - 6 < D) {
-          if (p.out.dof_vel) p.out.dof_vel[q * D + (k - 6)] = v[c];
+      // velocities of key frame 0, un-blended (anim/motion_lib.py:89-95):
+      // vel slot 0 = root_vel.xyz, 1 = root_ang_vel.xyz, 2.. = dof_vel in groups of 4
+      if (has_v) {
+        if (l == 0) {
+          if (p.out.root_vel) { float* o = p.out.root_vel + q * 3; o[0] = V.x; o[1] = V.y; o[2] = V.z; }
+        } else if (l == 1) {
+          if (p.out.root_ang_vel) { float* o = p.out.root_ang_vel + q * 3; o[0] = V.x; o[1] = V.y; o[2] = V.z; }
+        } else if (p.out.dof_vel) {
+          const int k = (l - 2) * 4;
+          float* o = p.out.dof_vel + q * D + k;
+          if ((D & 3) == 0) {
+            *reinterpret_cast<float4*>(o) = V;
+          } else {
+            o[0] = V.x;
+            if (k + 1 < D) o[1] = V.y;
+            if (k + 2 < D) o[2] = V.z;
+            if (k + 3 < D) o[3] = V.w;
+          }
         }
       }
     }
 
     if (!p.want_fk && !p.want_obs) continue;
 
-    // root position lives in lane 0, root rotation in lane 1 (= body 0's lane)
-    const float3 rp = shfl3(make_float3(R.x, R.y, R.z), 0);
+    // root position lives in group lane 0, root rotation in group lane 1 (= body 0's lane)
+    const float3 rp = make_float3(shfl_g(R.x, 0, G), shfl_g(R.y, 0, G), shfl_g(R.z, 0, G));
 
-    // ---- heightmap observation: issue the gathers before the FK math so they overlap ----
+    // ---- heightmap observation, part 1: cells of the first G * INFLIGHT points, gathers issued ----
+    ObsCtx oc;
+    float z[INFLIGHT];
+    const float* __restrict__ hfp = p.hf.hf;
     if (p.want_obs) {
-      const float4 rr = shfl4(R, 1);
+      const float4 rr = make_float4(shfl_g(R.x, 1, G), shfl_g(R.y, 1, G), shfl_g(R.z, 1, G), shfl_g(R.w, 1, G));
       const float heading = calc_heading(rr);
       float sn, cs;
-      sn = sinf(heading);
-      cs = cosf(heading);
-      const float2* __restrict__ tmpl = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
-      float* __restrict__ o = p.obs_out + q * p.obs.num_points;
-      const int P = p.obs.num_points;
-#pragma unroll 4
-      for (int k = lane; k < P; k += 32) {
-        const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, rp.x, rp.y);
-        float z = hf_lookup(p.hf, w.x, w.y);
-        if (p.obs.relative) z = fminf(fmaxf(sub_rn(z, rp.z), p.obs.min_h), p.obs.max_h);
-        o[k] = z;
+      sincosf(heading, &sn, &cs);
+      const GridAxis gx = make_grid_axis(p.hf.min_x, p.hf.dx, p.hf.dim_x);
+      const GridAxis gy = make_grid_axis(p.hf.min_y, p.hf.dy, p.hf.dim_y);
+      oc.cc = make_float2(cs, cs); oc.ss = make_float2(sn, sn); oc.off = make_float2(rp.x, rp.y);
+      oc.neg_min = make_float2(-gx.mn, -gy.mn); oc.inv2 = make_float2(gx.inv, gy.inv);
+      oc.neg_d = make_float2(-gx.d, -gy.d);
+      oc.hix = p.hf.dim_x - 1; oc.hiy = p.hf.dim_y - 1; oc.dim_y = p.hf.dim_y;
+#pragma unroll
+      for (int u = 0; u < INFLIGHT; ++u) {
+        const int k = l + G * u;
+        z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
       }
     }
 
-    // ---- forward kinematics down the tree ----
+    // ---- forward kinematics down the tree (shuffles stay inside the group) ----
     if (p.want_fk) {
       float3 pos = rp;
       float4 rot = R;
-      fk_warp(lb, max_depth, pos, rot);
-      if (lb.body >= 0) {
+      float4 local = rot;
+      if (lb.body > 0) local = quat_mul_plain(lb.lr, rot);
+#pragma unroll 1
+      for (int d = 1; d <= max_depth; ++d) {
+        const float3 pp = make_float3(shfl_g(pos.x, lb.parent_lane, G), shfl_g(pos.y, lb.parent_lane, G),
+                                      shfl_g(pos.z, lb.parent_lane, G));
+        const float4 pr = make_float4(shfl_g(rot.x, lb.parent_lane, G), shfl_g(rot.y, lb.parent_lane, G),
+                                      shfl_g(rot.z, lb.parent_lane, G), shfl_g(rot.w, lb.parent_lane, G));
+        if (lb.depth == d) {
+          const float3 wt = quat_rotate(pr, lb.lt);
+          pos = make_float3(pp.x + wt.x, pp.y + wt.y, pp.z + wt.z);
+          rot = quat_mul_plain(pr, local);
+        }
+      }
+      if (active && lb.body >= 0) {
         if (p.fk.body_pos) {
           float* o = p.fk.body_pos + (q * J + lb.body) * 3;
           o[0] = pos.x; o[1] = pos.y; o[2] = pos.z;
@@ -200,7 +293,58 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
         if (p.fk.body_rot) reinterpret_cast<float4*>(p.fk.body_rot)[q * J + lb.body] = rot;
       }
     }
+
+    // ---- heightmap observation, part 2: consume the gathers; then any further points ----
+    if (p.want_obs && active) {
+      float* __restrict__ o = p.obs_out + q * P + l;          // lane's first output; u-th is o[G * u]
+      const float root_z = rp.z, lo = p.obs.min_h, hi = p.obs.max_h;
+#pragma unroll
+      for (int u = 0; u < INFLIGHT; ++u) {
+        float v = z[u];
+        if (relative) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+        if (l + G * u < P) o[G * u] = v;
+      }
+      for (int k0 = G * INFLIGHT; k0 < P; k0 += G * INFLIGHT) {
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+          const int k = k0 + l + G * u;
+          z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
+        }
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+          float v = z[u];
+          if (relative) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+          if (k0 + l + G * u < P) o[k0 + G * u] = v;
+        }
+      }
+    }
   }
+}
+
+// grid_index_fast's packed twin used in the observation loop, one axis at a time, for the self test
+__device__ __forceinline__ int grid_index_packed_form(float p, const GridAxis& a, int hi) {
+  // drive obs_cell with an identity rotation and zero offset so that w == (p, p)
+  ObsCtx c;
+  c.cc = make_float2(1.0f, 1.0f); c.ss = make_float2(0.0f, 0.0f); c.off = make_float2(0.0f, 0.0f);
+  c.neg_min = make_float2(-a.mn, -a.mn); c.inv2 = make_float2(a.inv, a.inv); c.neg_d = make_float2(-a.d, -a.d);
+  c.hix = hi; c.hiy = 0; c.dim_y = 1;
+  // x*1 - 0*0 = x and 0*... exact; (p + 0) == p except -0 -> +0, which indexes identically
+  return obs_cell(c, make_float2(p, 0.0f));
+}
+
+// Exhaustive check of grid_index_fast against the reference-form IEEE division, over every float bit
+// pattern of the coordinate, for one axis description.  mismatches[0] += number of differing indices.
+__global__ void __launch_bounds__(256)
+selftest_grid_index_kernel(float mn, float d, int dim, unsigned long long* mismatches) {
+  const GridAxis a = make_grid_axis(mn, d, dim);
+  unsigned long long bad = 0;
+  const uint64_t total = 1ull << 32;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((uint32_t)i);
+    const int ref = grid_index_1d(x, mn, d, dim);
+    bad += (grid_index_fast(x, a) != ref) || (grid_index_packed_form(x, a, dim - 1) != ref);
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 // ---- a1: pack the reference's separate tables into rows ---------------------------------------
@@ -232,18 +376,17 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const __grid_constant_
     } else {
       const int c = k - pose_floats;
       if (c < 3) v = p.root_vel[f * 3 + c];
-      else if (c < 6) v = p.root_ang_vel[f * 3 + (c - 3)];
-      else if (c - 6 < p.D) v = p.dof_vel[f * p.D + (c - 6)];
+      else if (c < 4) v = 0.0f;
+      else if (c < 7) v = p.root_ang_vel[f * 3 + (c - 4)];
+      else if (c < 8) v = 0.0f;
+      else if (c - 8 < p.D) v = p.dof_vel[f * p.D + (c - 8)];
     }
     p.rows[i] = v;
   }
 }
 
-static int query_grid(int64_t n) {
-  // one warp per query; cap the grid at a few resident waves and let the warps stride
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+static int query_grid(int64_t n, int sms) {
+  // one warp per n; cap the grid at a few resident waves and let the warps stride
   const int64_t want = (n + PARC_WARPS_PER_CTA - 1) / PARC_WARPS_PER_CTA;
   const int64_t cap = (int64_t)sms * 8;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
@@ -284,11 +427,11 @@ extern "C" int parc_row_layout(const ParcCharModel* m, ParcRowLayout* out) {
   out->contact_slot = J + 1;
   out->pose_slots = J + 1 + (J + 3) / 4;
   out->vel_slot = out->pose_slots;
-  out->vel_slots = (6 + m->dof_size + 3) / 4;
+  out->vel_slots = 2 + (m->dof_size + 3) / 4;
   const int floats = (out->pose_slots + out->vel_slots) * 4;
   out->row_floats = (floats + 7) / 8 * 8;
   out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
-  if (out->pose_slots > 32 || out->vel_slots > 32) return PARC_E_MODEL;
+  if (m->num_bodies + 1 > 32) return PARC_E_MODEL;
   return PARC_OK;
 }
 
@@ -296,9 +439,11 @@ extern "C" int parc_pack_frames(const float* root_pos, const float* root_rot, co
                                 const float* contacts, const float* root_vel, const float* root_ang_vel,
                                 const float* dof_vel, int64_t total_frames, const ParcCharModel* model,
                                 float* rows_out, void* stream) {
-  if (!root_pos || !root_rot || !joint_rot || !root_vel || !root_ang_vel || !dof_vel || !rows_out || !model)
-    return PARC_E_NULL;
+  if (!model) return PARC_E_NULL;
   if (total_frames < 0) return PARC_E_SIZE;
+  if (total_frames > 0 &&
+      (!root_pos || !root_rot || !joint_rot || !root_vel || !root_ang_vel || !dof_vel || !rows_out))
+    return PARC_E_NULL;
   PackParams p;
   int rc = parc_row_layout(model, &p.lay);
   if (rc) return rc;
@@ -317,10 +462,10 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
                         const int64_t* frame_idx, int64_t n, const ParcCharModel* model,
                         const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                         const ParcObsSpec* obs, float* obs_out, void* stream) {
-  if (!tables || !ids || !model) return PARC_E_NULL;
-  if (blend ? !times : !frame_idx) return PARC_E_NULL;
+  if (!tables || !model) return PARC_E_NULL;
   if (!tables->rows || !tables->clips) return PARC_E_NULL;
   if (n < 0 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
+  if (n > 0 && (!ids || (blend ? !times : !frame_idx))) return PARC_E_NULL;
   QueryParams p;
   int rc = parc_row_layout(model, &p.lay);
   if (rc) return rc;
@@ -344,14 +489,27 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
     if (!hf || !obs || !hf->hf || !obs->tmpl_xy) return PARC_E_NULL;
     if (hf->dim_x <= 0 || hf->dim_y <= 0 || obs->num_points < 0) return PARC_E_SIZE;
     if ((reinterpret_cast<uintptr_t>(obs->tmpl_xy) & 7u) != 0) return PARC_E_ALIGN;
+    if ((int64_t)hf->dim_x * hf->dim_y >= (1ll << 31)) return PARC_E_SIZE;
     p.hf = *hf; p.obs = *obs;
   }
   if (n == 0) return PARC_OK;
-  const int grid = query_grid(n);
-  if (blend)
-    motion_query_kernel<true><<<grid, PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(p, *model);
-  else
-    motion_query_kernel<false><<<grid, PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(p, *model);
+  if (!aligned16(p.out.dof_vel)) return PARC_E_ALIGN;
+  // Group size: two characters per warp (G = 16) whenever position + rotations fit 16 lanes; it halves
+  // the instruction count of everything but the observation sweep.
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool half = model->num_bodies + 1 <= 16;
+  const int grid = query_grid(half ? (n + 1) / 2 : n, sms);
+  const size_t smem = (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) ? (size_t)p.obs.num_points * 8 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (blend) {
+    if (half) motion_query_kernel<true, 16, 28><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
+    else motion_query_kernel<true, 32, 14><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
+  } else {
+    if (half) motion_query_kernel<false, 16, 28><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
+    else motion_query_kernel<false, 32, 14><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
+  }
   return check_launch();
 }
 
@@ -368,4 +526,13 @@ extern "C" int parc_get_motion_frame(const ParcMotionTables* tables, const int64
                                      const ParcFrameOut* frame, const ParcFkOut* fk, void* stream) {
   return launch_query(false, tables, motion_ids, nullptr, frame_idxs, n, model, frame, fk, nullptr, nullptr,
                       nullptr, stream);
+}
+
+extern "C" int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint64_t* mismatches_dev,
+                                        void* stream) {
+  if (!mismatches_dev) return PARC_E_NULL;
+  if (dim <= 0 || !(cell_size > 0.0f)) return PARC_E_SIZE;
+  selftest_grid_index_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(
+      min_coord, cell_size, dim, reinterpret_cast<unsigned long long*>(mismatches_dev));
+  return check_launch();
 }

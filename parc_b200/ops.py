@@ -208,6 +208,71 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
     return res
 
 
+class MotionQueryPlan:
+    """A fused query(+FK)(+obs) launch with every argument struct prebuilt: `launch()` is one ctypes call
+    (~2 us of host time instead of ~40 us of Python), for callers that step the same buffers every control
+    tick -- the tracker's per-step query is exactly that.  Inputs are read from `ids` / `times` (write new
+    values into them in place, or build one plan per input buffer); outputs land in `self.out`."""
+
+    def __init__(self, tables: PackedTables, model: ParcCharModel, ids: torch.Tensor, times: torch.Tensor, *,
+                 want_contacts: bool = True, want_fk: bool = True, hf: Optional[HeightfieldDesc] = None,
+                 obs_tmpl: Optional[torch.Tensor] = None, obs_relative: bool = True, obs_min_h: float = -3.0,
+                 obs_max_h: float = 3.0, out: Optional[dict] = None):
+        require_cuda(ids, times, tables.rows)
+        assert ids.dtype == torch.int64 and times.dtype == torch.float32 and ids.is_contiguous() and times.is_contiguous()
+        self._keep = (tables, model, ids, times, hf, obs_tmpl)
+        self.device = ids.device
+        N, J, D = int(ids.shape[0]), model.num_bodies, model.dof_size
+        self.n = N
+        self.out = {} if out is None else out
+
+        def buf(name, shape):
+            t = self.out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.device != self.device:
+                t = torch.empty(shape, dtype=torch.float32, device=self.device)
+                self.out[name] = t
+            return t
+
+        self._fo = ParcFrameOut()
+        self._fo.root_pos = buf("root_pos", (N, 3)).data_ptr()
+        self._fo.root_rot = buf("root_rot", (N, 4)).data_ptr()
+        self._fo.root_vel = buf("root_vel", (N, 3)).data_ptr()
+        self._fo.root_ang_vel = buf("root_ang_vel", (N, 3)).data_ptr()
+        self._fo.joint_rot = buf("joint_rot", (N, J - 1, 4)).data_ptr()
+        self._fo.dof_vel = buf("dof_vel", (N, D)).data_ptr()
+        if want_contacts:
+            self._fo.contacts = buf("contacts", (N, J)).data_ptr()
+        self._fk = ParcFkOut()
+        if want_fk:
+            self._fk.body_pos = buf("body_pos", (N, J, 3)).data_ptr()
+            self._fk.body_rot = buf("body_rot", (N, J, 4)).data_ptr()
+        self._tb = tables.c_struct()
+        self._hf = self._obs = None
+        self._obs_ptr = None
+        if obs_tmpl is not None:
+            assert hf is not None
+            tm = f32c(obs_tmpl)
+            self._keep += (tm,)
+            self._hf, self._obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
+            self._obs_ptr = buf("obs", (N, int(tm.shape[0]))).data_ptr()
+        lib = _lib.load()
+        self._fn = lib.parc_motion_query
+        self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), N, C.byref(model), C.byref(self._fo),
+                      C.byref(self._fk) if want_fk else None, C.byref(self._hf) if self._hf is not None else None,
+                      C.byref(self._obs) if self._obs is not None else None, self._obs_ptr)
+
+    def launch(self, stream: Optional[int] = None) -> dict:
+        """Enqueue on `stream` (a raw cudaStream_t; default = torch's current stream of the plan's
+        device).  The caller is responsible for the current device being the plan's."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._fn(*self._args, stream)
+        _lib.LAUNCHES[0] += 1
+        if rc != 0:
+            check(rc, "parc_motion_query")
+        return self.out
+
+
 # ----------------------------------------------------------------------------------------------
 # a6: forward kinematics (differentiable)
 # ----------------------------------------------------------------------------------------------
@@ -345,6 +410,17 @@ def hf_sample(hf: HeightfieldDesc, xy: torch.Tensor, want_index: bool = False):
     if want_index:
         return z.reshape(lead), gi.reshape(*lead, 2)
     return z.reshape(lead)
+
+
+def selftest_grid_index(min_coord: float, cell_size: float, dim: int, device="cuda") -> int:
+    """Number of float inputs (out of all 2^32 bit patterns) for which the hoisted-reciprocal grid index of
+    the observation loops differs from the reference form with a true IEEE division.  Expected 0."""
+    cnt = torch.zeros(1, dtype=torch.int64, device=device)
+    with torch.cuda.device(cnt.device):
+        rc = _lib.load().parc_selftest_grid_index(float(min_coord), float(cell_size), int(dim), cnt.data_ptr(),
+                                                  stream_ptr(cnt.device))
+    check(rc, "parc_selftest_grid_index")
+    return int(cnt.item())
 
 
 def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, heading: torch.Tensor, *,

@@ -1,0 +1,127 @@
+"""Multi-GPU layer: one process per GPU, queries / samples / clips sharded contiguously across ranks.
+
+The path has no exchange step: every (clip id, time) query, every loss sample
+and every clip is independent, the frame tables and the global heightfield are replicated.  So the data
+path runs with NO collective; `torch.distributed` (NCCL over NVLink on the GPUs, gloo in the CPU tests)
+is used only
+  * to gather results onto one rank / all ranks when a caller wants them in one place, and
+  * to reduce loss statistics (sum / min / max / count in fp64), mirroring what the reference's logger
+    does with its all-reduce (util/logger.py:164-183, util/mp_util.py:90-105).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of `n` items owned by `rank`; the first n % world ranks get one extra."""
+    assert 0 <= rank < world_size
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(t: torch.Tensor, rank: Optional[int] = None, world_size: Optional[int] = None) -> torch.Tensor:
+    """This rank's contiguous slice of dim 0 (a view)."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    lo, hi = shard_bounds(t.shape[0], rank, world_size)
+    return t[lo:hi]
+
+
+def all_gather_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Inverse of `shard`: every rank ends up with the full [n_total, ...] tensor.  Shards may differ by
+    one row, so they are padded to the largest shard for a single all_gather_into_tensor call."""
+    rank, w = world()
+    if w == 1:
+        assert local.shape[0] == n_total
+        return local
+    per = (n_total + w - 1) // w
+    rest = tuple(local.shape[1:])
+    padded = local.new_zeros((per,) + rest)
+    padded[:local.shape[0]] = local
+    out = local.new_empty((w * per,) + rest)
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    pieces = []
+    for r in range(w):
+        lo, hi = shard_bounds(n_total, r, w)
+        pieces.append(out[r * per:r * per + (hi - lo)])
+    return torch.cat(pieces, dim=0)
+
+
+def gather_shards_to(local: torch.Tensor, n_total: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Like all_gather_shards but only `dst` receives the result (others get None)."""
+    rank, w = world()
+    if w == 1:
+        return local
+    per = (n_total + w - 1) // w
+    rest = tuple(local.shape[1:])
+    padded = local.new_zeros((per,) + rest)
+    padded[:local.shape[0]] = local
+    bufs = [local.new_empty((per,) + rest) for _ in range(w)] if rank == dst else None
+    dist.gather(padded.contiguous(), bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][:shard_bounds(n_total, r, w)[1] - shard_bounds(n_total, r, w)[0]] for r in range(w)], dim=0)
+
+
+def reduce_loss_stats(values: Dict[str, torch.Tensor], group=None) -> Dict[str, Dict[str, float]]:
+    """Per key: global sum / mean / min / max / count over every rank's local [n_local] tensor.
+    Three collectives in total regardless of the number of keys (sum+count, min, max), in fp64."""
+    keys = sorted(values)
+    _, w = world()
+    dev = values[keys[0]].device if keys else torch.device("cpu")
+    sums = torch.zeros(2 * len(keys), dtype=torch.float64, device=dev)
+    mins = torch.full((len(keys),), float("inf"), dtype=torch.float64, device=dev)
+    maxs = torch.full((len(keys),), float("-inf"), dtype=torch.float64, device=dev)
+    for i, k in enumerate(keys):
+        v = values[k].detach().to(torch.float64).reshape(-1)
+        sums[2 * i] = v.sum()
+        sums[2 * i + 1] = v.numel()
+        if v.numel() > 0:
+            mins[i], maxs[i] = v.min(), v.max()
+    if w > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    sums, mins, maxs = sums.cpu(), mins.cpu(), maxs.cpu()
+    out = {}
+    for i, k in enumerate(keys):
+        cnt = sums[2 * i + 1].item()
+        out[k] = {"sum": sums[2 * i].item(), "count": int(cnt), "mean": sums[2 * i].item() / max(cnt, 1.0),
+                  "min": mins[i].item(), "max": maxs[i].item()}
+    return out
+
+
+class ShardedMotionQuery:
+    """Tracker-shaped sharding (configs 2 and 4): the global batch of environments is split
+    contiguously across ranks; each rank queries only its slice on its own GPU."""
+
+    def __init__(self, motion_lib, hf_desc=None, obs_tmpl=None):
+        self.mlib = motion_lib
+        self.hf_desc = hf_desc
+        self.obs_tmpl = obs_tmpl
+        self._out = {}
+
+    def query_local(self, global_ids: torch.Tensor, global_times: torch.Tensor) -> dict:
+        """Inputs are the GLOBAL [N] tensors (replicated on every rank, already on this rank's device);
+        returns this rank's outputs only.  No communication."""
+        return self.mlib.calc_motion_frame_fk_obs(shard(global_ids).contiguous(), shard(global_times).contiguous(),
+                                                  hf_desc=self.hf_desc, obs_tmpl=self.obs_tmpl, out=self._out)
+
+    def query_gathered(self, global_ids, global_times, keys=("body_pos", "obs")) -> dict:
+        """query_local + one all-gather per requested output."""
+        local = self.query_local(global_ids, global_times)
+        n = int(global_ids.shape[0])
+        return {k: all_gather_shards(local[k], n) for k in keys if k in local}

@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# One GPU round: parity tests, smoke, bench at the two batch sizes, ncu launch list + full capture.
+# usage (from the repo root, under gpurun): bash scripts/gpu_round.sh [tag]
+mkdir -p gpurun_out
+TAG="${1:-r1}"
+python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+python bench.py --steps 200 --warmup 10 > gpurun_out/bench.log 2> gpurun_out/bench.err
+python bench.py --steps 100 --warmup 10 --envs 65536 --no-cpu-baseline > gpurun_out/bench_65k.log 2>> gpurun_out/bench.err
+CMD="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-soak"
+$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list.log 2>&1
+$CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:motion_query -s 5 -c 3 -f -o gpurun_out/prof_${TAG}_query $CMD > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log
+python - <<'PY'
+import json
+for f in ("bench.log", "bench_65k.log"):
+    try:
+        j = json.loads(open("gpurun_out/" + f).read().strip().splitlines()[-1])
+        r = j["roofline"]
+        print(f, "value %.3e  ms/step %.4f  frac %.3f  achieved %.0f GB/s  e2e %.3e  cpu %s" % (
+            j["value"], j["ms_per_step"], r["frac"], r["achieved"], j["e2e"]["value"],
+            (j.get("cpu_baseline") or {}).get("value")))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
+tail -2 gpurun_out/bench.err; tail -2 gpurun_out/ncu_full.log

@@ -55,8 +55,8 @@ def test_packed_tables_match_golden(golden_lib):
     assert torch.equal(rows[:, 8:64].reshape(-1, 14, 4), torch.tensor(g["joint_rot"]))
     v0 = lay.vel_slot * 4
     assert torch.equal(rows[:, v0:v0 + 3], torch.tensor(g["root_vel"]))
-    assert torch.equal(rows[:, v0 + 3:v0 + 6], torch.tensor(g["root_ang_vel"]))
-    assert torch.equal(rows[:, v0 + 6:v0 + 34], torch.tensor(g["dof_vel"]))
+    assert torch.equal(rows[:, v0 + 4:v0 + 7], torch.tensor(g["root_ang_vel"]))
+    assert torch.equal(rows[:, v0 + 8:v0 + 36], torch.tensor(g["dof_vel"]))
 
 
 # ----------------------------------------------------------------------------------------- query
@@ -235,6 +235,15 @@ def test_grid_index_bit_exact():
     gi = torch.tensor(g["ray_grid_index"])
     assert torch.equal(z, hf[gi[:, 0], gi[:, 1]])
     assert torch.equal(t.get_hf_val_from_points(dev(g["ray_xy"]).view(64, 441, 2)).cpu(), z.view(64, 441))
+
+
+@pytest.mark.parametrize("mn,d,dim", [(0.0, 0.4, 1536), (0.0, 0.4, 50), (-3.2, 0.4, 16), (0.0, 0.05, 4000),
+                                       (1.7, 0.2, 31), (0.0, 1.0, 256), (-100.5, 0.3, 977), (12.0, 0.7, 1)])
+def test_fast_grid_index_equals_ieee_division_for_every_float(mn, d, dim):
+    """The observation loops divide by the (loop-invariant) cell size with a hoisted reciprocal + 3 FMAs;
+    the resulting cell index must equal the reference form (true IEEE division) for ALL 2^32 inputs."""
+    from parc_b200 import ops
+    assert ops.selftest_grid_index(mn, d, dim) == 0
 
 
 def _border_mask(coord, ulps=8):

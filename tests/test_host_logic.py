@@ -1,0 +1,262 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, rejects bad arguments
+before touching the GPU, and the host logic (MJCF parser, table building, point sampling, synthetic
+generators) reproduces the reference's golden values.  No compute kernels are launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ASSET, ROOT, golden, lib_clips_from_golden, write_clip_library
+
+
+def T(x):
+    return torch.as_tensor(np.asarray(x))
+
+
+# ------------------------------------------------------------------ C ABI
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "parc_b200.h")).read()
+    return sorted(set(re.findall(r"\b(parc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from parc_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/parc_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.parc_abi_version() == 1
+    assert lib.parc_error_string(-1).decode() == "a required pointer is NULL"
+
+
+def test_struct_sizes_match_header():
+    from parc_b200 import _lib
+    assert C.sizeof(_lib.ParcClipMeta) == 32
+    assert C.sizeof(_lib.ParcRowLayout) == 32
+    assert C.sizeof(_lib.ParcCharModel) == 16 + 4 * 24 * 4 + 24 * (3 + 4 + 3) * 4
+    assert C.sizeof(_lib.ParcMotionTables) == 40 and C.sizeof(_lib.ParcFrameOut) == 80
+    assert C.sizeof(_lib.ParcHeightfield) == 32 and C.sizeof(_lib.ParcTerrainBatch) == 80
+
+
+def test_row_layout_and_model_validation(cpu_model):
+    from parc_b200 import _lib, ops
+    m = cpu_model.c_model()
+    lay = ops.row_layout(m)
+    assert (lay.pose_slots, lay.contact_slot, lay.vel_slot, lay.vel_slots, lay.row_floats) == (20, 16, 20, 9, 120)
+    assert m.max_depth == 4 and list(m.depth)[:15] == [0, 1, 2, 2, 3, 4, 2, 3, 4, 1, 2, 3, 1, 2, 3]
+    bad = _lib.ParcCharModel.from_buffer_copy(m)
+    bad.parent[3] = 7                               # parent after child
+    assert _lib.load().parc_validate_model(C.byref(bad)) == -3
+    bad = _lib.ParcCharModel.from_buffer_copy(m)
+    bad.num_bodies = 25
+    assert _lib.load().parc_validate_model(C.byref(bad)) == -3
+
+
+def test_argument_errors_are_returned_not_thrown(cpu_model):
+    """NULL / negative-size / misaligned arguments come back as negative codes; nothing is launched."""
+    from parc_b200 import _lib
+    lib = _lib.load()
+    m = cpu_model.c_model()
+    assert lib.parc_motion_query(None, None, None, 0, C.byref(m), None, None, None, None, None, None) == -1
+    tb = _lib.ParcMotionTables()
+    tb.rows, tb.clips, tb.total_frames, tb.num_clips, tb.row_floats = 256, 512, 10, 1, 120
+    fo = _lib.ParcFrameOut()
+    assert lib.parc_motion_query(C.byref(tb), 64, 64, -5, C.byref(m), C.byref(fo), None, None, None, None, None) == -2
+    tb.row_floats = 116
+    assert lib.parc_motion_query(C.byref(tb), 64, 64, 0, C.byref(m), C.byref(fo), None, None, None, None, None) == -5
+    tb.row_floats, tb.rows = 120, 260                # rows not 16-byte aligned
+    assert lib.parc_motion_query(C.byref(tb), 64, 64, 0, C.byref(m), C.byref(fo), None, None, None, None, None) == -4
+    assert lib.parc_fk_fwd(None, None, None, 4, C.byref(m), None, None, None) == -1
+    assert lib.parc_hf_sample(None, None, 4, None, None, None) == -1
+    assert lib.parc_points_hf_sdf(None, 1, 1, None, 1, None, None, None) == -1
+    assert lib.parc_exp_map_to_quat_fwd(64, -1, 64, None) == -2
+    # n == 0 is a valid no-op
+    tb.rows = 256
+    assert lib.parc_motion_query(C.byref(tb), 64, 64, 0, C.byref(m), C.byref(fo), None, None, None, None, None) == 0
+
+
+def test_ops_refuse_cpu_tensors(cpu_model):
+    from parc_b200 import ops
+    from parc_b200._lib import ParcLibraryError
+    with pytest.raises(ParcLibraryError):
+        cpu_model.forward_kinematics(torch.zeros(2, 3), torch.zeros(2, 4), torch.zeros(2, 14, 4))
+    with pytest.raises(ParcLibraryError):
+        cpu_model.dof_to_rot(torch.zeros(2, 28))
+    with pytest.raises(ParcLibraryError):
+        ops.exp_map_to_quat(torch.zeros(2, 3))
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import parc_b200.anim.motion_lib, parc_b200.tools.procgen.mdm_path, "
+            "parc_b200.tools.motion_opt.motion_optimization, parc_b200.envs.ig_parkour.mgdm_dm_util, parc_b200.sharding; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "parc_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+# ------------------------------------------------------------------ character model
+def test_mjcf_parser_matches_reference_model(cpu_model):
+    g = golden("humanoid_model.npz")
+    assert cpu_model.get_body_names() == [str(s) for s in g["body_names"]]
+    assert cpu_model._parent_indices.tolist() == g["parents"].tolist()
+    assert torch.equal(cpu_model._local_translation, T(g["local_translation"]))
+    assert torch.equal(cpu_model._local_rotation, T(g["local_rotation"]))
+    assert [j.joint_type.value for j in cpu_model._joints] == g["joint_type"].tolist()
+    assert [j.dof_idx for j in cpu_model._joints] == g["dof_idx"].tolist()
+    assert cpu_model.get_dof_size() == 28 and cpu_model.get_num_joints() == 15
+    assert torch.equal(cpu_model._lower_dof_limits, T(g["lower_dof_limits"]))
+    assert torch.equal(cpu_model._upper_dof_limits, T(g["upper_dof_limits"]))
+    for j, jt in enumerate(cpu_model._joints):
+        if jt.axis is not None:
+            assert torch.equal(jt.axis, T(g["joint_axis"][j]))
+    assert cpu_model.get_body_id("left_foot") == 14 and cpu_model.get_joint_id("torso") == 0
+    rows = []
+    for b in range(15):
+        for ge in cpu_model.get_geoms(b):
+            d = np.zeros(3, np.float32)
+            dd = ge._dims.numpy().reshape(-1)
+            d[:dd.shape[0]] = dd
+            rows.append([b, ge._shape_type.value, *ge._offset.tolist(), *d.tolist(), -1.0 if ge._radius is None else ge._radius])
+    assert np.array_equal(np.array(rows, np.float32), g["geoms"])
+
+
+def test_body_point_samples_match_reference(cpu_model):
+    from parc_b200.util import geom_util
+    g = golden("humanoid_model.npz")
+    pts = geom_util.get_char_point_samples(cpu_model)
+    assert [p.shape[0] for p in pts] == g["body_point_counts"].tolist() and sum(p.shape[0] for p in pts) == 304
+    assert torch.equal(torch.cat(pts), T(g["body_points"]))
+    mp = geom_util.get_minimal_char_point_samples(cpu_model)
+    assert torch.equal(torch.cat(mp), T(g["min_body_points"]))
+    # foot sole = first 18 points at z = offset_z - half_z (motion_optimization.py:320 relies on it)
+    assert torch.allclose(pts[11][:18, 2], torch.full((18,), -0.05))
+
+
+def test_templates_match_reference():
+    from parc_b200.util import geom_util
+    g = golden("obs_golden.npz")
+    tm = geom_util.get_xy_points_cone(torch.zeros(2), 0.05, 2, 60, 3, 3, 0.26179938779)
+    assert tm.shape == (441, 2) and torch.equal(tm, T(g["tmpl"]))
+    gt = geom_util.get_xy_grid_points(torch.zeros(2), 0.2, 0.2, 15, 15, 15, 15)
+    assert gt.shape == (31, 31, 2) and torch.equal(gt, T(g["grid_tmpl"]))
+
+
+def test_host_quaternion_helpers_match_reference(cpu_model):
+    from parc_b200.util import torch_util
+    civ, g = golden("clip_civilization.npz"), golden("dof_golden.npz")
+    assert torch.equal(torch_util.exp_map_to_quat(T(civ["frames"][:, 3:6])), T(g["root_quat"]))
+    assert torch.equal(cpu_model.host_dof_to_rot(T(civ["frames"][:, 6:])), T(g["joint_rot"]))
+    assert torch.equal(cpu_model.rot_to_dof(T(g["joint_rot"])), T(g["dof_back"]))
+    og = golden("obs_golden.npz")
+    assert torch.equal(torch_util.calc_heading(T(og["root_quat"])), T(og["heading"]))
+
+
+# ------------------------------------------------------------------ MotionLib loading
+def test_motion_file_loader_builds_reference_tables(cpu_model, tmp_path):
+    from parc_b200.anim.motion_lib import MotionLib
+    g = golden("tables_golden.npz")
+    lib = MotionLib(write_clip_library(tmp_path, lib_clips_from_golden()), cpu_model, "cpu", init_type="motion_file",
+                    contact_info=True)
+    assert lib.num_motions() == 3 and lib._motion_num_frames.tolist() == [254, 58, 40]
+    for k, a in (("root_rot", lib._frame_root_rot), ("joint_rot", lib._frame_joint_rot), ("root_vel", lib._frame_root_vel),
+                 ("root_ang_vel", lib._frame_root_ang_vel), ("dof_vel", lib._frame_dof_vel), ("lengths", lib._motion_lengths),
+                 ("start_idx", lib._motion_start_idx), ("root_pos_delta", lib._motion_root_pos_delta),
+                 ("weights", lib._motion_weights)):
+        assert torch.equal(a, T(g[k])), k
+    assert lib._frame_contacts.shape == (352, 15) and lib._motion_frames.shape == (352, 34)
+    assert lib.get_motion_names() == ["clip_00000", "clip_00001", "clip_00002"]
+    assert lib.get_motion_loop_mode(torch.tensor([0, 1])).tolist() == [0, 1]
+    ph = lib.calc_motion_phase(torch.tensor([0, 1, 1]), torch.tensor([100.0, 2.85, -0.5]))
+    assert ph[0] == 1.0 and 0 <= ph[1] < 1 and 0 <= ph[2] < 1
+    assert lib._packed is None                       # no CUDA device: tables exist, queries do not
+    from parc_b200._lib import ParcLibraryError
+    with pytest.raises(ParcLibraryError):
+        lib.calc_motion_frame(torch.tensor([0]), torch.tensor([0.0]))
+
+
+def test_motion_frames_loader_reproduces_reference_quirk(cpu_model):
+    from parc_b200.anim.motion_lib import LoopMode, MotionLib
+    g = golden("tables_motion_frames_golden.npz")
+    lib = MotionLib(T(g["frames"]), cpu_model, "cpu", init_type="motion_frames", loop_mode=LoopMode.CLAMP, fps=30,
+                    contact_info=True, contacts=T(g["contacts"]))
+    assert torch.equal(lib._frame_dof_vel, T(g["dof_vel"]))       # fps passed as dt: 900x too small
+    assert torch.equal(lib._frame_root_ang_vel, T(g["root_ang_vel"]))
+    assert torch.equal(lib._motion_lengths, T(g["lengths"]))
+    with pytest.raises(ValueError):
+        MotionLib("x", cpu_model, "cpu", init_type="diffusion_file")
+
+
+def test_reference_pickles_with_terrain_load(cpu_model, tmp_path):
+    """A clip pickle that names the reference's SubTerrain class resolves to ours."""
+    import pickle
+    import sys
+    import types
+    from parc_b200.anim.motion_lib import load_clip_file
+    from parc_b200.util.terrain_util import SubTerrain
+    civ = golden("clip_civilization.npz")
+    fake_pkg, fake_mod = types.ModuleType("util"), types.ModuleType("util.terrain_util")
+
+    class _Ref:
+        pass
+    _Ref.__name__ = _Ref.__qualname__ = "SubTerrain"
+    _Ref.__module__ = "util.terrain_util"
+    fake_mod.SubTerrain = _Ref
+    saved = {k: sys.modules.get(k) for k in ("util", "util.terrain_util")}
+    sys.modules["util"], sys.modules["util.terrain_util"] = fake_pkg, fake_mod
+    try:
+        t = _Ref()
+        t.terrain_name, t.hf, t.dims = "t", civ["hf"], np.array([50, 50])
+        t.min_point, t.dxdy, t.hf_mask = civ["min_point"], civ["dxdy"], np.zeros((50, 50), bool)
+        p = tmp_path / "c.pkl"
+        with open(p, "wb") as f:
+            pickle.dump({"frames": civ["frames"], "contacts": civ["contacts"], "fps": 30.0, "loop_mode": "CLAMP",
+                         "terrain": t}, f)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    clip = load_clip_file(str(p))
+    terr = clip["terrain"]
+    assert isinstance(terr, SubTerrain)
+    terr.update_old()
+    terr.to_torch("cpu")
+    assert terr.hf.shape == (50, 50) and terr.hf_maxmin.shape == (50, 50, 2) and terr.dims.tolist() == [50, 50]
+
+
+# ------------------------------------------------------------------ synthetic inputs
+def test_synthetic_generators_are_seeded_and_in_spec(cpu_model):
+    from parc_b200.util import synth
+    rng = np.random.default_rng(0)
+    hf = synth.box_terrain(rng)
+    assert hf.shape == (16, 16) and hf.dtype == np.float32
+    st = synth.stairs_terrain(np.random.default_rng(1))
+    assert (np.diff(st[:, 0]) >= 0).all() and st.max() > 0
+    f1, c1 = synth.synth_clips(cpu_model, 3, seed=5, hf=hf)
+    f2, c2 = synth.synth_clips(cpu_model, 3, seed=5, hf=hf)
+    assert np.array_equal(f1, f2) and np.array_equal(c1, c2)
+    assert f1.shape == (3, 265, 34) and c1.shape == (3, 265, 15) and f1.dtype == np.float32
+    lo, hi = synth.dof_limits(cpu_model)
+    assert (f1[..., 6:] >= lo - 1e-6).all() and (f1[..., 6:] <= hi + 1e-6).all()
+    assert (np.abs(f1[..., 6:]) >= 1e-3 - 1e-9).all()                      # never exactly zero (F8d)
+    n = np.linalg.norm(f1[..., 3:6], axis=-1)
+    assert (n > 1e-3).all() and (n <= 0.5 + 1e-6).all()
+    speed = np.linalg.norm(np.diff(f1[..., 0:2], axis=1), axis=-1) * 30.0
+    assert speed.max() <= 3.0 + 1e-3
+    assert set(np.unique(c1)) <= {0.0, 1.0}
+    s = synth.synth_motion_samples(cpu_model, 2, 10, hf, (0.0, 0.0), (0.4, 0.4))
+    assert s["contacts"].min() < 0 or s["contacts"].min() == 0
+    assert s["root_pos"].shape == (2, 10, 3) and s["joint_dof"].shape == (2, 10, 28)

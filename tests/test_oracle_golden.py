@@ -1,0 +1,108 @@
+"""The oracle (oracle/parc_oracle.py) against the committed golden vectors.
+
+The vectors are outputs of the REAL reference run in the authoring container by oracle/make_golden.py
+(which also asserted torch.equal there).  Here they are re-checked wherever the suite runs: integer /
+index results and IEEE-only arithmetic bit-exactly, transcendental-bearing values to 1e-6 (the host CPU's
+vector math library may differ from the authoring container's).
+"""
+import numpy as np
+import torch
+
+from conftest import assert_close, golden, lib_clips_from_golden
+from oracle import parc_oracle as O
+
+
+def T(x):
+    return torch.as_tensor(np.asarray(x))
+
+
+def test_pin_report_is_all_ok():
+    import os
+    from conftest import GOLDEN
+    lines = open(os.path.join(GOLDEN, "PIN_REPORT.txt")).read().splitlines()[1:]
+    assert len(lines) >= 50 and all(l.startswith("OK") for l in lines)
+
+
+def test_tables(oracle_model):
+    g = golden("tables_golden.npz")
+    tb = O.build_tables(oracle_model, lib_clips_from_golden())
+    assert torch.equal(tb.start_idx, T(g["start_idx"])) and torch.equal(tb.lengths, T(g["lengths"]))
+    assert torch.equal(tb.weights, T(g["weights"])) and torch.equal(tb.root_pos_delta, T(g["root_pos_delta"]))
+    for k in ("root_rot", "joint_rot", "root_vel", "root_ang_vel", "dof_vel"):
+        assert_close(getattr(tb, k), g[k], rtol=1e-6, atol=1e-6, what=k)
+
+
+def test_query_indices_bit_exact_and_values(oracle_model):
+    g = golden("query_golden.npz")
+    tg = golden("tables_golden.npz")
+    tb = O.build_tables(oracle_model, lib_clips_from_golden())
+    # decouple from the host's libm: query on the golden tables themselves
+    tb.root_rot, tb.joint_rot = T(tg["root_rot"]), T(tg["joint_rot"])
+    tb.root_vel, tb.root_ang_vel, tb.dof_vel = T(tg["root_vel"]), T(tg["root_ang_vel"]), T(tg["dof_vel"])
+    ids, times = T(g["ids"]), T(g["times"])
+    i0, i1, bl = O.frame_blend(tb, ids, times)
+    assert torch.equal(i0, T(g["idx0"])) and torch.equal(i1, T(g["idx1"])) and torch.equal(bl, T(g["blend"]))
+    fr = O.calc_motion_frame(tb, ids, times)
+    for k, t in zip(("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts"), fr):
+        assert_close(t, g[k], rtol=1e-6, atol=1e-6, what=k)
+    assert torch.equal(fr[0], T(g["root_pos"])) and torch.equal(fr[6], T(g["contacts"]))
+    bp, br = O.forward_kinematics(oracle_model, T(g["root_pos"]), T(g["root_rot"]), T(g["joint_rot"]))
+    assert_close(bp, g["body_pos"], rtol=1e-6, atol=1e-6, what="body_pos")
+    assert_close(br, g["body_rot"], rtol=1e-6, atol=1e-6, what="body_rot")
+    gf = O.get_motion_frame(tb, T(g["get_ids"]), T(g["get_fidx"]))
+    assert torch.equal(gf[4], T(g["get_joint_rot"])) and torch.equal(gf[6], T(g["get_contacts"]))
+
+
+def test_known_answers_from_survey(oracle_model):
+    """SURVEY.md appendix A1 probe on the 254-frame clip."""
+    tb = O.build_tables(oracle_model, lib_clips_from_golden()[:1])
+    t = torch.tensor([0, 8.4333, 8.5, 100, -1, 4.2], dtype=torch.float32)
+    i0, i1, bl = O.frame_blend(tb, torch.zeros(6, dtype=torch.long), t)
+    assert i0.tolist() == [0, 252, 253, 253, 0, 125] and i1.tolist() == [1, 253, 253, 253, 1, 126]
+    assert_close(bl, torch.tensor([0, 0.99900818, 0, 0, 0, 0.99999237]), rtol=0, atol=1e-7, what="blend")
+
+
+def test_dof_conversions(oracle_model):
+    civ, g = golden("clip_civilization.npz"), golden("dof_golden.npz")
+    assert_close(O.dof_to_rot(oracle_model, T(civ["frames"][:, 6:])), g["joint_rot"], rtol=1e-6, atol=1e-6, what="dof_to_rot")
+    assert_close(O.rot_to_dof(oracle_model, T(g["joint_rot"])), g["dof_back"], rtol=1e-6, atol=2e-6, what="rot_to_dof")
+    assert_close(O.exp_map_to_quat(T(civ["frames"][:, 3:6])), g["root_quat"], rtol=1e-6, atol=1e-6, what="exp_map")
+
+
+def test_heightfield(oracle_model):
+    civ, g = golden("clip_civilization.npz"), golden("obs_golden.npz")
+    t = O.Terrain(hf=T(civ["hf"]), min_point=T(civ["min_point"]), dxdy=T(civ["dxdy"]))
+    assert torch.equal(O.grid_index(t, T(g["ray_xy"])), T(g["ray_grid_index"]))
+    assert torch.equal(O.grid_index(t, T(g["probe_xy"])), T(g["probe_index"]))
+    assert O.grid_index(t, torch.tensor([[0.2, 0.6]])).tolist() == [[0, 2]]     # half-to-even
+    assert_close(O.cone_template(0.05, 2, 60, 3, 3, 0.26179938779), g["tmpl"], rtol=1e-6, atol=1e-7, what="template")
+    obs = O.ray_obs(t, T(g["root_pos"]), T(g["heading"]), T(g["tmpl"]))
+    assert (obs != T(g["ray_obs"])).float().mean() < 1e-3
+    gobs = O.grid_obs(t, T(g["root_pos"][:16, 0:2]), T(g["heading"][:16]), T(g["grid_tmpl"]))
+    assert (gobs != T(g["grid_obs"])).float().mean() < 2e-3
+    assert_close(O.calc_heading(T(g["root_quat"])), g["heading"], rtol=1e-6, atol=1e-6, what="heading")
+
+
+def test_sdf_and_losses(oracle_model):
+    civ, g, L = golden("clip_civilization.npz"), golden("sdf_golden.npz"), golden("loss_golden.npz")
+    dxdy = torch.tensor([0.4, 0.4])
+    # SURVEY A8 probe values
+    inv = O.points_hf_sdf(T(g["probe_points"]), T(g["probe_hf"]), torch.zeros(1, 2), dxdy, -10.0, True)
+    sol = O.points_hf_sdf(T(g["probe_points"]), T(g["probe_hf"]), torch.zeros(1, 2), dxdy, -10.0, False)
+    assert torch.equal(inv, T(g["probe_inv"])) and torch.equal(sol, T(g["probe_sol"]))
+    assert_close(inv[0, :3], torch.tensor([-0.2, 0.2, -0.3]), rtol=1e-5, what="probe inverted")
+    assert_close(sol[0, :2], torch.tensor([-0.2, 0.5]), rtol=1e-5, what="probe solid")
+    hf, mp = T(civ["hf"]), T(civ["min_point"])
+    assert torch.equal(O.points_hf_sdf(T(g["clip_points"]), hf[None], mp[None], dxdy, -10.0, True), T(g["clip_inv"]))
+    assert torch.equal(O.points_hf_sdf(T(g["clip_points"]), hf[None], mp[None], dxdy, -10.0, False), T(g["clip_sol"]))
+    out = O.compute_motion_loss(oracle_model, T(L["ml_root_pos"]), T(L["ml_root_rot"]), T(L["ml_joint_rot"]),
+                                T(L["ml_contacts"]), hf, mp, dxdy, 0.1, 0.1)
+    assert_close(out["total_loss"], L["ml_total"], rtol=1e-6, what="total")
+    assert_close(out["pen_loss"], L["ml_pen"], rtol=1e-6, what="pen")
+    a, b, c = (T(L[k]).clone().requires_grad_(True) for k in ("mo_root_pos", "mo_root_exp", "mo_joint_dof"))
+    loss, pen, con = O.motion_opt_pen_contact(oracle_model, a, b, c, T(L["mo_contacts"]), hf, mp, dxdy, 1000.0, 1000.0)
+    loss.backward()
+    assert_close(loss, L["mo_loss_pc"], rtol=1e-6, what="motion-opt loss")
+    assert_close(a.grad, L["mo_grad_root_pos"], rtol=1e-5, atol=1e-3, what="grad root_pos")
+    assert_close(b.grad, L["mo_grad_root_exp"], rtol=1e-5, atol=1e-3, what="grad root_exp")
+    assert_close(c.grad, L["mo_grad_joint_dof"], rtol=1e-5, atol=1e-3, what="grad joint_dof")
