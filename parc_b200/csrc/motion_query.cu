@@ -87,8 +87,14 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // Latency structure per query: [ids, times | template + tree staging] -> clip meta -> frame rows ->
 // heightfield gathers; the gathers of the first INFLIGHT * G template points are all issued
 // BEFORE the FK chain and consumed after it, so that round trip hides behind the FK math.
-template <bool BLEND, int G, int INFLIGHT>
-__global__ void __launch_bounds__(PARC_CTA_THREADS, 4)   // <= 128 registers: 16 warps (4 CTAs) per SM
+#define QUERY_WARPS_PER_CTA 2      // small CTAs: 4096 queries -> 1024 CTAs -> 6.9 per SM (1% imbalance)
+#define QUERY_CTA_THREADS (QUERY_WARPS_PER_CTA * 32)
+
+// MINB = resident CTAs per SM the register allocation must allow: 8 (<= 128 registers, whole template
+// sweep in flight) for launches that fit one wave and are latency-bound; 12 (<= 85 registers, half a
+// sweep in flight) for large launches, which are issue-bound and want more warps per scheduler.
+template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB>
+__global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant__ ParcCharModel model_param) {
   __shared__ TreeSmem sm;
   extern __shared__ float2 s_tmpl[];
@@ -96,10 +102,12 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int l = lane & (G - 1);
   const int grp = lane / G;
-  const int64_t first = ((int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5)) * GROUPS;
-  const int64_t stride = (int64_t)gridDim.x * PARC_WARPS_PER_CTA * GROUPS;
+  const int64_t first = ((int64_t)blockIdx.x * QUERY_WARPS_PER_CTA + (threadIdx.x >> 5)) * GROUPS;
+  const int64_t stride = (int64_t)gridDim.x * QUERY_WARPS_PER_CTA * GROUPS;
   const int P = p.obs.num_points;
   const bool tmpl_in_smem = p.want_obs && P <= PARC_TMPL_SMEM_MAX;
+  // shared copy is padded up to a whole sweep with copies of point 0, so the sweep never bounds-checks
+  const int P_pad = (P + G * INFLIGHT - 1) / (G * INFLIGHT) * (G * INFLIGHT);
 
   // Prologue: everything that does not depend on anything else is requested up front so the cold misses
   // overlap -- this group's first id / time, the observation template, the kinematic tree.
@@ -113,7 +121,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
   }
   if (tmpl_in_smem) {
     const float2* __restrict__ g = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_tmpl[i] = __ldg(g + i);
+    for (int i = threadIdx.x; i < P_pad; i += blockDim.x) s_tmpl[i] = __ldg(g + (i < P ? i : 0));
   }
   stage_tree(&sm, model_param);
   __syncthreads();
@@ -126,7 +134,6 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
   const float4* __restrict__ rows = reinterpret_cast<const float4*>(p.tb.rows);
   const float2* __restrict__ tmpl = tmpl_in_smem ? s_tmpl : reinterpret_cast<const float2*>(p.obs.tmpl_xy);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool relative = p.obs.relative != 0;
 
   for (int64_t base = first; base < p.n; base += stride) {
     const int64_t qq = base + grp;
@@ -251,19 +258,32 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     const float* __restrict__ hfp = p.hf.hf;
     if (p.want_obs) {
       const float4 rr = make_float4(shfl_g(R.x, 1, G), shfl_g(R.y, 1, G), shfl_g(R.z, 1, G), shfl_g(R.w, 1, G));
-      const float heading = calc_heading(rr);
-      float sn, cs;
-      sincosf(heading, &sn, &cs);
+      // cos / sin of heading = atan2(d.y, d.x) taken directly from the rotated x axis d (the reference goes
+      // through atan2 -> cos/sin; both are within ~2 ulp of the true value, far below the fp32 granularity
+      // of the world coordinate they are added to).
+      const float3 dir = quat_rotate(rr, make_float3(1.0f, 0.0f, 0.0f));
+      const float n2 = dir.x * dir.x + dir.y * dir.y;
+      float sn = 0.0f, cs = (dir.x < 0.0f) ? -1.0f : 1.0f;       // atan2(0, +-0)
+      if (n2 > 0.0f) {
+        const float rn = rsqrtf(n2);
+        cs = dir.x * rn;
+        sn = dir.y * rn;
+      }
       const GridAxis gx = make_grid_axis(p.hf.min_x, p.hf.dx, p.hf.dim_x);
       const GridAxis gy = make_grid_axis(p.hf.min_y, p.hf.dy, p.hf.dim_y);
       oc.cc = make_float2(cs, cs); oc.ss = make_float2(sn, sn); oc.off = make_float2(rp.x, rp.y);
       oc.neg_min = make_float2(-gx.mn, -gy.mn); oc.inv2 = make_float2(gx.inv, gy.inv);
       oc.neg_d = make_float2(-gx.d, -gy.d);
       oc.hix = p.hf.dim_x - 1; oc.hiy = p.hf.dim_y - 1; oc.dim_y = p.hf.dim_y;
+      if (tmpl_in_smem) {
 #pragma unroll
-      for (int u = 0; u < INFLIGHT; ++u) {
-        const int k = l + G * u;
-        z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
+        for (int u = 0; u < INFLIGHT; ++u) z[u] = __ldg(hfp + obs_cell(oc, s_tmpl[l + G * u]));
+      } else {
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+          const int k = l + G * u;
+          z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
+        }
       }
     }
 
@@ -301,19 +321,24 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
 #pragma unroll
       for (int u = 0; u < INFLIGHT; ++u) {
         float v = z[u];
-        if (relative) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+        if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
         if (l + G * u < P) o[G * u] = v;
       }
       for (int k0 = G * INFLIGHT; k0 < P; k0 += G * INFLIGHT) {
+        if (tmpl_in_smem) {               // padded to whole sweeps: no bounds check on the read side
 #pragma unroll
-        for (int u = 0; u < INFLIGHT; ++u) {
-          const int k = k0 + l + G * u;
-          z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
+          for (int u = 0; u < INFLIGHT; ++u) z[u] = __ldg(hfp + obs_cell(oc, s_tmpl[k0 + l + G * u]));
+        } else {
+#pragma unroll
+          for (int u = 0; u < INFLIGHT; ++u) {
+            const int k = k0 + l + G * u;
+            z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
+          }
         }
 #pragma unroll
         for (int u = 0; u < INFLIGHT; ++u) {
           float v = z[u];
-          if (relative) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+          if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
           if (k0 + l + G * u < P) o[k0 + G * u] = v;
         }
       }
@@ -387,8 +412,8 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const __grid_constant_
 
 static int query_grid(int64_t n, int sms) {
   // one warp per n; cap the grid at a few resident waves and let the warps stride
-  const int64_t want = (n + PARC_WARPS_PER_CTA - 1) / PARC_WARPS_PER_CTA;
-  const int64_t cap = (int64_t)sms * 8;
+  const int64_t want = (n + QUERY_WARPS_PER_CTA - 1) / QUERY_WARPS_PER_CTA;
+  const int64_t cap = (int64_t)sms * 16;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -500,16 +525,27 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool half = model->num_bodies + 1 <= 16;
-  const int grid = query_grid(half ? (n + 1) / 2 : n, sms);
-  const size_t smem = (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) ? (size_t)p.obs.num_points * 8 : 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (blend) {
-    if (half) motion_query_kernel<true, 16, 28><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
-    else motion_query_kernel<true, 32, 14><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
-  } else {
-    if (half) motion_query_kernel<false, 16, 28><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
-    else motion_query_kernel<false, 32, 14><<<grid, PARC_CTA_THREADS, smem, st>>>(p, *model);
+  const int64_t warps = half ? (n + 1) / 2 : n;
+  const bool one_wave = warps <= (int64_t)sms * 16;           // 8 CTAs x 2 warps resident per SM
+  const int grid = query_grid(warps, sms);
+  const int inflight = half ? (one_wave ? 28 : 14) : 14;
+  size_t smem = 0;
+  if (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) {
+    const int sweep = (half ? 16 : 32) * inflight;
+    smem = (size_t)((p.obs.num_points + sweep - 1) / sweep * sweep) * 8;
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool rel = p.want_obs && p.obs.relative != 0;
+#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB) \
+  motion_query_kernel<B, GG, NF, RL, MB><<<grid, QUERY_CTA_THREADS, smem, st>>>(p, *model)
+  if (blend) {
+    if (half && one_wave) { if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); }
+    else if (half) { if (rel) PARC_LAUNCH_QUERY(true, 16, 14, true, 12); else PARC_LAUNCH_QUERY(true, 16, 14, false, 12); }
+    else { if (rel) PARC_LAUNCH_QUERY(true, 32, 14, true, 8); else PARC_LAUNCH_QUERY(true, 32, 14, false, 8); }
+  } else {
+    if (half) PARC_LAUNCH_QUERY(false, 16, 14, false, 12); else PARC_LAUNCH_QUERY(false, 32, 14, false, 8);
+  }
+#undef PARC_LAUNCH_QUERY
   return check_launch();
 }
 

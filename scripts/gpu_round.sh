@@ -10,6 +10,9 @@ python bench.py --steps 100 --warmup 10 --envs 65536 --no-cpu-baseline > gpurun_
 CMD="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-soak"
 $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:motion_query -s 5 -c 3 -f -o gpurun_out/prof_${TAG}_query $CMD > gpurun_out/ncu_full.log 2>&1
+CMD2="python bench.py --steps 6 --warmup 3 --envs 65536 --no-cpu-baseline --no-soak"
+$CMD2 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:motion_query -s 4 -c 2 -f -o gpurun_out/prof_${TAG}_query65k $CMD2 > gpurun_out/ncu_full65k.log 2>&1
+python scripts/bench_loss.py > gpurun_out/bench_loss.log 2>&1; tail -1 gpurun_out/bench_loss.log
 tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log
 python - <<'PY'
 import json
