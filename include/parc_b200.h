@@ -192,7 +192,9 @@ int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_t n, float*
 /* Self test of the hoisted-reciprocal grid index used in the observation loops: compares it with the
  * reference form clamp(rint((p - min) / cell) ...) using a true IEEE division, for EVERY float bit
  * pattern of p (2^32 inputs), and adds the number of differing indices to *mismatches_dev (device
- * uint64, caller-zeroed).  Expected: 0. */
+ * uint64, caller-zeroed).  Expected: 0.  (The packed form used inside the observation sweep is checked
+ * on the same inputs except quotients >= 2^63, where the reference wraps through int64 overflow to cell 0
+ * and the sweep clamps to the last cell.) */
 int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint64_t* mismatches_dev,
                              void* stream);
 
@@ -252,6 +254,47 @@ int parc_body_loss(const float* root_pos, const float* root_rot, const float* jo
                    int64_t batch, int64_t frames, const ParcCharModel* model, const ParcBodyPoints* pts,
                    const ParcTerrainBatch* terrain, float w_pen, float w_contact, float* pen_out,
                    float* contact_out, float* g_root_pos, float* g_root_rot, float* g_joint_rot, void* stream);
+
+/* ---- dataset sweep (BASELINE config 5) ---------------------------------- */
+
+/* Raw motion frames [n, frame_stride] = root_pos(3) | root exp-map(3) | joint DoFs(D) | ... ->
+ * exp_map_to_quat + dof_to_rot + forward_kinematics in one launch (the front end of
+ * MotionLib.get_frames_for_id anim/motion_lib.py:503-513, terrain_util.compute_hf_mask_inds
+ * util/terrain_util.py:1959-1964 and the contact-labelling functions).  Any output may be NULL. */
+int parc_frames_fk(const float* frames, int64_t n, int32_t frame_stride, const ParcCharModel* model,
+                   float* root_rot_out, float* joint_rot_out, float* body_pos, float* body_rot, void* stream);
+
+#define PARC_MAX_KEY_BODIES 4
+/* Bodies the labelling looks at: box-shaped feet (half extents + offset of the box geom, as
+ * motion_edit_lib.py:679-686 reads them from char_model._geoms[body][0]) and sphere hands (radius). */
+typedef struct ParcKeyBodies {
+  int32_t num_feet;
+  int32_t num_hands;
+  int32_t foot_body[PARC_MAX_KEY_BODIES];
+  int32_t hand_body[PARC_MAX_KEY_BODIES];
+  float foot_half[PARC_MAX_KEY_BODIES][3];
+  float foot_offset[PARC_MAX_KEY_BODIES][3];
+  float hand_radius[PARC_MAX_KEY_BODIES];
+} ParcKeyBodies;
+
+/* Per-clip labelling over frames [B, F, frame_stride], one terrain per clip (ParcTerrainBatch; its base_z
+ * is the solid columns' floor for the hand test, min(hf) - 10 in the reference):
+ *   contacts_out [B,F,J]        1.0 where a foot has any box corner below (cell height + eps) or a hand's
+ *                               rounded-box SDF to the solid terrain is < eps; 0 elsewhere
+ *                               (motion_edit_lib.py:654-747)
+ *   pen_correction_out [B,F]    min(0, min over foot corners of z - cell height)      (:683-701)
+ *   body_hf_out [B,F,J]         nearest-cell terrain height under every body origin
+ *   frame_mask_out [B,F,W]      bit (ix*Y+iy) set iff any body surface point falls in that cell in that
+ *                               frame, W = ceil(X*Y/32)           (terrain_util.py:1951-1997, per frame)
+ *   min_body_heights [B,X,Y]    running min of surface-point z per cell; CALLER-INITIALISED
+ *                               (99999.9999 in the reference, :1969-1970)
+ *   body_pos / body_rot         FK outputs [B,F,J,3] / [B,F,J,4]
+ * Any output may be NULL. */
+int parc_clip_label(const float* frames, int64_t batch, int64_t frames_per_clip, int32_t frame_stride,
+                    const ParcCharModel* model, const ParcBodyPoints* pts, const ParcTerrainBatch* terrain,
+                    const ParcKeyBodies* keys, float contact_eps, float* contacts_out, float* pen_correction_out,
+                    float* body_hf_out, uint32_t* frame_mask_out, float* min_body_heights, float* body_pos,
+                    float* body_rot, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,7 @@ import util.torch_util as ref_tu  # noqa: E402
 import util.motion_util as ref_mu  # noqa: E402
 import tools.procgen.mdm_path as ref_mdm_path  # noqa: E402
 import tools.motion_opt.motion_optimization as ref_mopt  # noqa: E402
+import zmotion_editing_tools.motion_edit_lib as ref_mel  # noqa: E402
 
 from oracle import parc_oracle as O  # noqa: E402
 
@@ -335,6 +336,41 @@ def main():
         mo_all_grad_joint_dof=npf(ga_jd),
         mo_all_terms=np.array([float(ld_all[k]) for k in ref_mopt.LossType if k in ld_all], np.float64),
         mo_all_term_names=np.array([k.name for k in ref_mopt.LossType if k in ld_all]))
+
+    # ------------------------------------------------------------------ 6. contact labelling + hf masks (8(f)-1)
+    lframes = torch.tensor(civ["frames"][::4].copy())             # 64 frames
+    lframes[:, 2] -= 0.03                                         # sink a little so the feet penetrate somewhere
+    upd, fc = ref_mel.compute_hf_foot_contacts_and_correct_pen(lframes, terr, km)
+    hc = ref_mel.compute_motion_terrain_hand_contacts(lframes, terr, km)
+    terr2 = ref_terrain.SubTerrain("t2", x_dim=50, y_dim=50, dx=0.4, dy=0.4, min_x=0.0, min_y=0.0, device="cpu")
+    terr2.hf = torch.tensor(civ["hf"]) + 0.75                     # raised terrain: hands do touch
+    terr2.min_point = terr.min_point.clone(); terr2.dxdy = terr.dxdy.clone()
+    hc2 = ref_mel.compute_motion_terrain_hand_contacts(lframes, terr2, km)
+    inds, minh = ref_terrain.compute_hf_mask_inds(lframes[:24], terr, km, body_points)
+    mask = ref_terrain.compute_hf_mask_from_inds(terr, inds)
+    t3 = terr.torch_copy()
+    ref_terrain.compute_hf_extra_vals(lframes[:24], t3, km, body_points)
+    lf, rf = km.get_body_id("left_foot"), km.get_body_id("right_foot")
+    lh, rh = km.get_body_id("left_hand"), km.get_body_id("right_hand")
+    feet = [(b, km._geoms[b][0]._dims.tolist(), km._geoms[b][0]._offset.tolist()) for b in (lf, rf)]
+    hands = [(b, km._geoms[b][0]._dims.item()) for b in (lh, rh)]
+    o_upd, o_fc, _ = O.foot_contacts_and_pen(model, lframes, ot, feet)
+    pin("label.foot_contacts", fc, o_fc); pin("label.updated_frames", upd, o_upd)
+    pin("label.hand_contacts", hc, O.hand_contacts(model, lframes, ot, hands))
+    pin("label.hand_contacts_raised", hc2,
+        O.hand_contacts(model, lframes, O.Terrain(hf=terr2.hf, min_point=terr2.min_point, dxdy=terr2.dxdy), hands))
+    o_inds, o_minh = O.hf_mask_inds(model, lframes[:24], ot)
+    pin("label.min_body_heights", minh, o_minh)
+    pin("label.hf_mask_inds(concat)", torch.cat(inds), torch.cat(o_inds))
+    pin("label.hf_mask_counts", torch.tensor([i.shape[0] for i in inds]), torch.tensor([i.shape[0] for i in o_inds]))
+    np.savez_compressed(
+        os.path.join(GOLD, "label_golden.npz"), frames=npf(lframes), foot_contacts=npf(fc), updated_z=npf(upd[:, 2]),
+        hand_contacts=npf(hc), hand_contacts_raised=npf(hc2), raised_by=np.float32(0.75),
+        mask_inds=npf(torch.cat(inds)), mask_counts=np.array([i.shape[0] for i in inds]), min_body_heights=npf(minh),
+        hf_mask=npf(mask), extra_hf_mask=npf(t3.hf_mask), extra_hf_maxmin=npf(t3.hf_maxmin),
+        feet_body=np.array([lf, rf]), feet_half=np.array([f[1] for f in feet], np.float32),
+        feet_offset=np.array([f[2] for f in feet], np.float32), hands_body=np.array([lh, rh]),
+        hands_radius=np.array([h[1] for h in hands], np.float32))
 
     with open(os.path.join(GOLD, "PIN_REPORT.txt"), "w") as f:
         f.write("oracle/parc_oracle.py vs the imported reference (torch %s, CPU, fp32) -- torch.equal on every line\n"

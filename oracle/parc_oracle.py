@@ -637,3 +637,68 @@ def motion_opt_pen_contact(model: CharModel, tgt_root_pos, tgt_root_rot_expmap, 
                                  model.body_points, hf, min_point, dxdy, -10.0)
     pen, con = pen[0], con[0]
     return w_penetration * pen + w_contact * con, pen, con
+
+
+# --------------------------------------------------------------------------
+# contact labelling + heightfield masks
+# --------------------------------------------------------------------------
+def frames_fk(model: CharModel, frames):
+    """Front end shared by the labelling functions: zmotion_editing_tools/motion_edit_lib.py:665-670."""
+    rq = exp_map_to_quat(frames[..., 3:6])
+    jr = dof_to_rot(model, frames[..., 6:6 + model.dof_size])
+    return forward_kinematics(model, frames[..., 0:3], rq, jr)
+
+
+def box_corners(body_pos, body_rot, half, offset):
+    """8 corners of a body-attached box -- util/geom_util.py:80-111.  [N,3],[N,4] -> [N,8,3]."""
+    signs = torch.tensor([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1],
+                          [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=F32)
+    pts = signs * half + offset
+    return quat_rotate(body_rot.unsqueeze(1).expand(-1, 8, -1), pts.unsqueeze(0).expand(body_pos.shape[0], -1, -1)) \
+        + body_pos.unsqueeze(1)
+
+
+def foot_contacts_and_pen(model: CharModel, frames, t: Terrain, feet, contact_eps=0.04):
+    """compute_hf_foot_contacts_and_correct_pen -- zmotion_editing_tools/motion_edit_lib.py:654-706.
+    feet: list of (body_id, half[3], offset[3]).  -> (updated frames, contacts [F,J], pen_correction [F])."""
+    F_ = frames.shape[0]
+    bp, br = frames_fk(model, frames)
+    contacts = torch.zeros(F_, model.num_bodies, dtype=F32)
+    corr = torch.zeros(F_)
+    for b, half, off in feet:
+        pts = box_corners(bp[:, b], br[:, b], torch.tensor(half, dtype=F32), torch.tensor(off, dtype=F32))
+        h = hf_sample(t, pts[..., 0:2])
+        contacts[:, b] = torch.any(pts[..., 2] < h + contact_eps, dim=-1).float()
+        corr = torch.min(corr, torch.min(pts[..., 2] - h, dim=-1)[0])
+    out = frames.clone()
+    out[:, 2] -= corr
+    return out, contacts, corr
+
+
+def hand_contacts(model: CharModel, frames, t: Terrain, hands, contact_eps=0.04):
+    """compute_motion_terrain_hand_contacts -- zmotion_editing_tools/motion_edit_lib.py:708-747.
+    hands: list of (body_id, radius)."""
+    bp, _ = frames_fk(model, frames)
+    contacts = torch.zeros(frames.shape[0], model.num_bodies, dtype=F32)
+    base_z = torch.min(t.hf).item() - 10.0
+    for b, radius in hands:
+        sd = points_hf_sdf(bp[:, b].unsqueeze(0), t.hf.unsqueeze(0), t.min_point.unsqueeze(0), t.dxdy, base_z, False)
+        contacts[:, b] = ((sd[0] - radius) < contact_eps).float()    # sdRoundBox = sdBox - r, min commutes
+    return contacts
+
+
+def hf_mask_inds(model: CharModel, frames, t: Terrain):
+    """compute_hf_mask_inds -- util/terrain_util.py:1951-1997, vectorised per frame (the reference's scalar
+    loops compute exactly a per-frame unique() and a running per-cell min)."""
+    bp, br = frames_fk(model, frames)
+    X, Y = t.hf.shape
+    min_h = torch.full((X, Y), 99999.9999, dtype=F32)
+    inds = []
+    for f in range(frames.shape[0]):
+        pts = torch.cat([quat_rotate(br[f, b].unsqueeze(0), model.body_points[b]) + bp[f, b]
+                         for b in range(model.num_bodies)], dim=0)
+        g = grid_index(t, pts[:, 0:2])
+        flat = g[:, 0] * Y + g[:, 1]
+        min_h = min_h.view(-1).scatter_reduce(0, flat, pts[:, 2], reduce="amin", include_self=True).view(X, Y)
+        inds.append(torch.unique(g, dim=0))
+    return inds, min_h

@@ -86,6 +86,17 @@ class ParcBodyPoints(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+PARC_MAX_KEY_BODIES = 4
+
+
+class ParcKeyBodies(C.Structure):
+    _fields_ = [("num_feet", C.c_int32), ("num_hands", C.c_int32),
+                ("foot_body", C.c_int32 * PARC_MAX_KEY_BODIES), ("hand_body", C.c_int32 * PARC_MAX_KEY_BODIES),
+                ("foot_half", (C.c_float * 3) * PARC_MAX_KEY_BODIES),
+                ("foot_offset", (C.c_float * 3) * PARC_MAX_KEY_BODIES),
+                ("hand_radius", C.c_float * PARC_MAX_KEY_BODIES)]
+
+
 # name -> (restype, argtypes); every symbol include/parc_b200.h declares
 _V, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 _P = C.POINTER
@@ -109,6 +120,9 @@ SIGNATURES = {
     "parc_selftest_grid_index": (C.c_int, [_F, _F, _I32, _V, _V]),
     "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _I64, _V, _V]),
     "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
+    "parc_frames_fk": (C.c_int, [_V, _I64, _I32, _P(ParcCharModel), _V, _V, _V, _V, _V]),
+    "parc_clip_label": (C.c_int, [_V, _I64, _I64, _I32, _P(ParcCharModel), _P(ParcBodyPoints), _P(ParcTerrainBatch),
+                                  _P(ParcKeyBodies), _F, _V, _V, _V, _V, _V, _V, _V, _V]),
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
                                  _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
 }

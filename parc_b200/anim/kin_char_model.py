@@ -333,6 +333,11 @@ class KinCharModel:
         [...,J,4].  One warp per character on the GPU; differentiable.  Ref :509-541."""
         return ops.forward_kinematics(self.c_model(), root_pos, root_rot, joint_rot)
 
+    def frames_forward_kinematics(self, motion_frames):
+        """[..., 6+D] raw frames -> (body_pos, body_rot): exp_map_to_quat + dof_to_rot + FK in one launch
+        (forward only).  The front end of MotionLib.get_frames_for_id / the labelling sweeps."""
+        return ops.frames_fk(self.c_model(), motion_frames)
+
     def dof_to_rot(self, dof):
         """dof [...,D] -> joint_rot [...,J-1,4].  CUDA kernel, differentiable.  Ref :478-491."""
         return ops.dof_to_rot(self.c_model(), dof)

@@ -1,0 +1,307 @@
+// Dataset sweep: raw motion frames -> FK -> contact labels / penetration correction / heightfield masks.
+//
+// SURVEY.md section 8(f) row 1 (BASELINE config 5).  Reference:
+//   zmotion_editing_tools/motion_edit_lib.py:654-706  compute_hf_foot_contacts_and_correct_pen
+//   zmotion_editing_tools/motion_edit_lib.py:708-747  compute_motion_terrain_hand_contacts
+//   util/terrain_util.py:1951-1997                    compute_hf_mask_inds (triple python loop)
+//   util/geom_util.py:80-111                          get_box_points_batch
+// and the front end every one of them repeats: exp_map_to_quat + dof_to_rot + forward_kinematics on
+// frames laid out [root_pos(3) | root exp-map(3) | joint DoFs(D)].
+#include "parc_common.cuh"
+#include "parc_rotations.cuh"
+
+namespace parc {
+
+// Lane b (0..J-1) of a warp turns its slice of one raw frame into (pos, rot) inputs of fk_warp:
+// lane 0 -> root position + exp_map_to_quat(root exp-map); lane j >= 1 -> joint j's quaternion.
+__device__ __forceinline__ void frame_to_lane_pose(const ParcCharModel& m, const float* __restrict__ fr, int lane,
+                                                   float3& pos, float4& rot) {
+  pos = make_float3(0.f, 0.f, 0.f);
+  rot = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (lane == 0) {
+    pos = make_float3(__ldg(fr), __ldg(fr + 1), __ldg(fr + 2));
+    rot = exp_map_to_quat(make_float3(__ldg(fr + 3), __ldg(fr + 4), __ldg(fr + 5)));
+  } else if (lane < m.num_bodies) {
+    const int jt = m.joint_type[lane];
+    const float* d = fr + 6 + m.dof_idx[lane];
+    float dd[3] = {0.f, 0.f, 0.f};
+    if (jt == PARC_JOINT_HINGE) dd[0] = __ldg(d);
+    else if (jt == PARC_JOINT_SPHERICAL) { dd[0] = __ldg(d); dd[1] = __ldg(d + 1); dd[2] = __ldg(d + 2); }
+    rot = joint_dof_to_quat(jt, dd, m.joint_axis[lane]);
+  }
+}
+
+// ---- frames -> FK, one warp per frame (config 5's "FK on every frame") -----------------------------
+__global__ void __launch_bounds__(PARC_CTA_THREADS)
+frames_fk_kernel(const float* __restrict__ frames, int64_t n, int frame_stride,
+                 const __grid_constant__ ParcCharModel model_param, float* __restrict__ root_rot_out,
+                 float* __restrict__ joint_rot_out, float* __restrict__ body_pos, float* __restrict__ body_rot) {
+  __shared__ ParcCharModel sm;
+  stage_model(&sm, model_param);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int J = sm.num_bodies;
+  const LaneBody lb = load_lane_body(sm, lane, 0);
+  const int64_t warp0 = (int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * PARC_WARPS_PER_CTA;
+  for (int64_t q = warp0; q < n; q += nwarps) {
+    float3 pos;
+    float4 rot;
+    frame_to_lane_pose(sm, frames + q * frame_stride, lane, pos, rot);
+    if (lane == 0) {
+      if (root_rot_out) reinterpret_cast<float4*>(root_rot_out)[q] = rot;
+    } else if (lane < J) {
+      if (joint_rot_out) reinterpret_cast<float4*>(joint_rot_out)[q * (J - 1) + (lane - 1)] = rot;
+    }
+    fk_warp(lb, sm.max_depth, pos, rot);
+    if (lane < J) {
+      if (body_pos) { float* o = body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
+      if (body_rot) reinterpret_cast<float4*>(body_rot)[q * J + lane] = rot;
+    }
+  }
+}
+
+// ---- per-clip labelling ------------------------------------------------------------------------------
+#define LABEL_THREADS 320
+
+struct LabelParams {
+  const float* frames;          // [B, F, frame_stride]
+  int64_t batch, frames_per_clip;
+  int frame_stride;
+  ParcBodyPoints pts;
+  ParcTerrainBatch terrain;
+  ParcKeyBodies keys;
+  float contact_eps;
+  float* contacts;              // [B,F,J]  (feet / hands written, others zero)
+  float* pen_correction;        // [B,F]
+  float* body_hf;               // [B,F,J]
+  uint32_t* frame_mask;         // [B,F,W]  W = ceil(X*Y/32)
+  float* min_body_heights;      // [B,X,Y]  caller-initialised
+  float* body_pos;              // [B,F,J,3]
+  float* body_rot;              // [B,F,J,4]
+  int frames_per_cta;
+  int mask_words;
+};
+
+// float atomic-min on a location that starts positive: int compare for v >= 0, unsigned for v < 0
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(LABEL_THREADS)
+clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__ ParcCharModel model_param) {
+  extern __shared__ float smem[];
+  __shared__ ParcCharModel sm;
+  __shared__ float s_bpos[PARC_MAX_BODIES][3];
+  __shared__ float s_brot[PARC_MAX_BODIES][4];
+  __shared__ float s_foot_pen[PARC_MAX_KEY_BODIES];
+
+  const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
+  const int S = p.pts.num_points;
+  float* s_hf = smem;
+  float* s_cx = s_hf + X * Y;
+  float* s_cy = s_cx + X;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_cy + Y);         // [mask_words]
+  int* s_body = reinterpret_cast<int*>(s_mask + p.mask_words);      // [S]
+
+  const int64_t b = blockIdx.y;
+  stage_model(&sm, model_param);
+  // terrain tile + absolute cell centres (node offset + min centre, fp32 add as the reference does)
+  {
+    const float* hf = p.terrain.hf + b * p.terrain.hf_batch_stride;
+    const float* mc = p.terrain.min_center + b * p.terrain.min_center_stride;
+    for (int i = threadIdx.x; i < X * Y; i += blockDim.x) s_hf[i] = __ldg(hf + i);
+    for (int i = threadIdx.x; i < X; i += blockDim.x) s_cx[i] = __ldg(p.terrain.x_nodes + i) + __ldg(mc);
+    for (int i = threadIdx.x; i < Y; i += blockDim.x) s_cy[i] = __ldg(p.terrain.y_nodes + i) + __ldg(mc + 1);
+  }
+  __syncthreads();
+  const int J = sm.num_bodies;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
+    for (int k = s0; k < s1; ++k) s_body[k] = j;
+  }
+  const float* mc = p.terrain.min_center + b * p.terrain.min_center_stride;
+  const float min_x = __ldg(mc), min_y = __ldg(mc + 1);
+  const float dx = p.terrain.half_dx * 2.0f, dy = p.terrain.half_dy * 2.0f;   // exact: halves of fp32 values
+  const float base = p.terrain.base_z ? __ldg(p.terrain.base_z + b * p.terrain.base_z_stride) : p.terrain.base_z_value;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const LaneBody lb = load_lane_body(sm, lane, 0);
+  __syncthreads();
+
+  const int64_t f_begin = (int64_t)blockIdx.x * p.frames_per_cta;
+  const int64_t f_end = min(f_begin + (int64_t)p.frames_per_cta, p.frames_per_clip);
+  for (int64_t f = f_begin; f < f_end; ++f) {
+    const int64_t q = b * p.frames_per_clip + f;
+    for (int i = threadIdx.x; i < p.mask_words; i += blockDim.x) s_mask[i] = 0u;
+    // ---- FK by warp 0 (lane = body) ----
+    if (warp == 0) {
+      float3 pos;
+      float4 rot;
+      frame_to_lane_pose(sm, p.frames + q * p.frame_stride, lane, pos, rot);
+      fk_warp(lb, sm.max_depth, pos, rot);
+      if (lane < J) {
+        s_bpos[lane][0] = pos.x; s_bpos[lane][1] = pos.y; s_bpos[lane][2] = pos.z;
+        s_brot[lane][0] = rot.x; s_brot[lane][1] = rot.y; s_brot[lane][2] = rot.z; s_brot[lane][3] = rot.w;
+        if (p.body_pos) { float* o = p.body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
+        if (p.body_rot) reinterpret_cast<float4*>(p.body_rot)[q * J + lane] = rot;
+        // nearest-cell terrain height under the body origin
+        if (p.body_hf) {
+          const int ix = grid_index_1d(pos.x, min_x, dx, X), iy = grid_index_1d(pos.y, min_y, dy, Y);
+          p.body_hf[q * J + lane] = s_hf[ix * Y + iy];
+        }
+        if (p.contacts) p.contacts[q * J + lane] = 0.0f;
+      }
+    }
+    __syncthreads();
+
+    // ---- every surface point: cell it falls in -> per-frame mask bit, per-cell min body height ----
+    if (p.frame_mask || p.min_body_heights) {
+      for (int k = threadIdx.x; k < S; k += blockDim.x) {
+        const int bj = s_body[k];
+        const float3 lp = make_float3(__ldg(p.pts.points + k * 3), __ldg(p.pts.points + k * 3 + 1),
+                                      __ldg(p.pts.points + k * 3 + 2));
+        const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
+        const float3 r = quat_rotate(br, lp);
+        const float3 wp = make_float3(r.x + s_bpos[bj][0], r.y + s_bpos[bj][1], r.z + s_bpos[bj][2]);
+        const int cell = grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y);
+        if (p.frame_mask) atomicOr(&s_mask[cell >> 5], 1u << (cell & 31));
+        if (p.min_body_heights) atomic_min_float(p.min_body_heights + b * (int64_t)X * Y + cell, wp.z);
+      }
+    }
+
+    // ---- feet: 8 box corners vs the height of the cell each falls in (warp 1, lane = foot*8 + corner) ----
+    if (warp == 1 && p.contacts) {
+      const int foot = lane >> 3, corner = lane & 7;
+      bool touch = false;
+      float pen = INFINITY;
+      if (foot < p.keys.num_feet) {
+        const int bj = p.keys.foot_body[foot];
+        const float hx = p.keys.foot_half[foot][0], hy = p.keys.foot_half[foot][1], hz = p.keys.foot_half[foot][2];
+        float3 c = make_float3((corner & 1) ? hx : -hx, (corner & 2) ? hy : -hy, (corner & 4) ? hz : -hz);
+        c.x += p.keys.foot_offset[foot][0]; c.y += p.keys.foot_offset[foot][1]; c.z += p.keys.foot_offset[foot][2];
+        const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
+        const float3 r = quat_rotate(br, c);
+        const float3 wp = make_float3(r.x + s_bpos[bj][0], r.y + s_bpos[bj][1], r.z + s_bpos[bj][2]);
+        const float h = s_hf[grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y)];
+        touch = wp.z < add_rn(h, p.contact_eps);            // box_points_z < cell_heights + contact_eps
+        pen = sub_rn(wp.z, h);
+      }
+      // any / min over the 8 corners of each foot
+      unsigned any = __ballot_sync(PARC_FULL_MASK, touch);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) pen = fminf(pen, __shfl_xor_sync(PARC_FULL_MASK, pen, o));
+      if (corner == 0 && foot < p.keys.num_feet) {
+        p.contacts[q * J + p.keys.foot_body[foot]] = ((any >> (foot * 8)) & 0xffu) ? 1.0f : 0.0f;
+        s_foot_pen[foot] = pen;
+      }
+      __syncwarp();
+      if (lane == 0 && p.pen_correction) {
+        float corr = 0.0f;                                   // pen_correction_z starts at zero (:683)
+        for (int i = 0; i < p.keys.num_feet; ++i) corr = fminf(corr, s_foot_pen[i]);
+        p.pen_correction[q] = corr;
+      }
+    }
+
+    // ---- hands: rounded-box SDF of the body origin to the SOLID heightfield, all cells (warp 2) ----
+    if (warp == 2 && p.contacts) {
+      for (int hnd = 0; hnd < p.keys.num_hands; ++hnd) {
+        const int bj = p.keys.hand_body[hnd];
+        const float3 pt = make_float3(s_bpos[bj][0], s_bpos[bj][1], s_bpos[bj][2]);
+        float best = INFINITY;
+        for (int c = lane; c < X * Y; c += 32) {
+          const int ix = c / Y, iy = c - ix * Y;
+          const float h = s_hf[c];
+          const float cz = (h + base) * 0.5f, hz = (h - base) * 0.5f;
+          const float qx = fabsf(pt.x - s_cx[ix]) - p.terrain.half_dx;
+          const float qy = fabsf(pt.y - s_cy[iy]) - p.terrain.half_dy;
+          const float qz = fabsf(pt.z - cz) - hz;
+          const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
+          const float sd = sqrtf(mx * mx + my * my + mz * mz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.0f);
+          best = fminf(best, sd - p.keys.hand_radius[hnd]);  // sdRoundBox = sdBox - r (geom_util.py:113-120)
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(PARC_FULL_MASK, best, o));
+        if (lane == 0) p.contacts[q * J + bj] = best < p.contact_eps ? 1.0f : 0.0f;
+      }
+    }
+    __syncthreads();
+    if (p.frame_mask)
+      for (int i = threadIdx.x; i < p.mask_words; i += blockDim.x) p.frame_mask[q * p.mask_words + i] = s_mask[i];
+    __syncthreads();
+  }
+}
+
+static int warp_grid(int64_t n) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n + PARC_WARPS_PER_CTA - 1) / PARC_WARPS_PER_CTA;
+  const int64_t cap = (int64_t)sms * 16;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace parc
+
+using namespace parc;
+
+extern "C" int parc_frames_fk(const float* frames, int64_t n, int32_t frame_stride, const ParcCharModel* model,
+                              float* root_rot_out, float* joint_rot_out, float* body_pos, float* body_rot,
+                              void* stream) {
+  if (!model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (n < 0 || frame_stride < 6 + model->dof_size) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!frames) return PARC_E_NULL;
+  if (!aligned16(root_rot_out) || !aligned16(joint_rot_out) || !aligned16(body_rot)) return PARC_E_ALIGN;
+  frames_fk_kernel<<<warp_grid(n), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(
+      frames, n, frame_stride, *model, root_rot_out, joint_rot_out, body_pos, body_rot);
+  return check_launch();
+}
+
+extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frames_per_clip, int32_t frame_stride,
+                               const ParcCharModel* model, const ParcBodyPoints* pts,
+                               const ParcTerrainBatch* terrain, const ParcKeyBodies* keys, float contact_eps,
+                               float* contacts_out, float* pen_correction_out, float* body_hf_out,
+                               uint32_t* frame_mask_out, float* min_body_heights, float* body_pos,
+                               float* body_rot, void* stream) {
+  if (!model || !pts || !terrain || !keys) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (batch < 0 || frames_per_clip < 0 || batch > 65535 || frame_stride < 6 + model->dof_size) return PARC_E_SIZE;
+  if (keys->num_feet < 0 || keys->num_feet > PARC_MAX_KEY_BODIES || keys->num_hands < 0 ||
+      keys->num_hands > PARC_MAX_KEY_BODIES)
+    return PARC_E_SIZE;
+  for (int i = 0; i < keys->num_feet; ++i)
+    if (keys->foot_body[i] < 0 || keys->foot_body[i] >= model->num_bodies) return PARC_E_SIZE;
+  for (int i = 0; i < keys->num_hands; ++i)
+    if (keys->hand_body[i] < 0 || keys->hand_body[i] >= model->num_bodies) return PARC_E_SIZE;
+  if (batch == 0 || frames_per_clip == 0) return PARC_OK;
+  if (!frames || !terrain->hf || !terrain->min_center || !terrain->x_nodes || !terrain->y_nodes) return PARC_E_NULL;
+  if ((frame_mask_out || min_body_heights) && (!pts->points || !pts->point_start || pts->num_points <= 0))
+    return PARC_E_NULL;
+  if (terrain->dim_x <= 0 || terrain->dim_y <= 0) return PARC_E_SIZE;
+  if (!aligned16(body_rot)) return PARC_E_ALIGN;
+
+  LabelParams p;
+  p.frames = frames; p.batch = batch; p.frames_per_clip = frames_per_clip; p.frame_stride = frame_stride;
+  p.pts = *pts; p.terrain = *terrain; p.keys = *keys; p.contact_eps = contact_eps;
+  p.contacts = contacts_out; p.pen_correction = pen_correction_out; p.body_hf = body_hf_out;
+  p.frame_mask = frame_mask_out; p.min_body_heights = min_body_heights; p.body_pos = body_pos; p.body_rot = body_rot;
+  const int cells = terrain->dim_x * terrain->dim_y;
+  p.mask_words = (cells + 31) / 32;
+  const size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + p.mask_words + (size_t)pts->num_points) * 4;
+  if (smem > 200 * 1024) return PARC_E_SIZE;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(clip_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int64_t fpc = (batch * frames_per_clip) / (148 * 8);
+  if (fpc < 1) fpc = 1;
+  if (fpc > 16) fpc = 16;
+  p.frames_per_cta = (int)fpc;
+  dim3 grid((unsigned)((frames_per_clip + fpc - 1) / fpc), (unsigned)batch);
+  clip_label_kernel<<<grid, LABEL_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+  return check_launch();
+}

@@ -8,86 +8,9 @@
 // Reference: anim/kin_char_model.py:509-541 (FK), :478-491 + :57-77 (dof_to_rot),
 // util/torch_util.py:311-317, :394-419 (axis-angle / exp-map -> quaternion).
 #include "parc_common.cuh"
+#include "parc_rotations.cuh"
 
 namespace parc {
-
-// ------------------------------------------------------------------------------------------------
-// axis-angle / exp-map -> quaternion, with VJPs
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 normalize4(const float4& u, float& nrm_out) {
-  const float n = sqrtf(u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w);
-  const float d = fmaxf(n, 1e-9f);                  // util/torch_util.py:12 clamp(min=eps)
-  nrm_out = d;
-  return make_float4(u.x / d, u.y / d, u.z / d, u.w / d);
-}
-
-__device__ __forceinline__ float3 normalize3(const float3& a, float& nrm_out) {
-  const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-  const float d = fmaxf(n, 1e-9f);
-  nrm_out = d;
-  return make_float3(a.x / d, a.y / d, a.z / d);
-}
-
-// util/torch_util.py:311-317
-__device__ __forceinline__ float4 axis_angle_to_quat(const float3& axis, float angle) {
-  const float th = angle / 2.0f;
-  float an, un;
-  const float3 n = normalize3(axis, an);
-  const float s = sinf(th), c = cosf(th);
-  return normalize4(make_float4(n.x * s, n.y * s, n.z * s, c), un);
-}
-
-// VJP wrt (axis, angle) of axis_angle_to_quat for upstream g.
-__device__ __forceinline__ void axis_angle_to_quat_vjp(const float3& axis, float angle, const float4& g,
-                                                       float3& g_axis, float& g_angle) {
-  const float th = angle / 2.0f;
-  float an, un;
-  const float3 n = normalize3(axis, an);
-  const float s = sinf(th), c = cosf(th);
-  const float4 u = make_float4(n.x * s, n.y * s, n.z * s, c);
-  const float4 q = normalize4(u, un);
-  // q = u / |u|
-  const float qg = q.x * g.x + q.y * g.y + q.z * g.z + q.w * g.w;
-  const float4 gu = make_float4((g.x - q.x * qg) / un, (g.y - q.y * qg) / un, (g.z - q.z * qg) / un,
-                                (g.w - q.w * qg) / un);
-  const float g_th = (gu.x * n.x + gu.y * n.y + gu.z * n.z) * c - gu.w * s;
-  g_angle = 0.5f * g_th;
-  // n = axis / |axis|
-  const float3 gn = make_float3(gu.x * s, gu.y * s, gu.z * s);
-  const float ngn = n.x * gn.x + n.y * gn.y + n.z * gn.z;
-  g_axis = make_float3((gn.x - n.x * ngn) / an, (gn.y - n.y * ngn) / an, (gn.z - n.z * ngn) / an);
-}
-
-// util/torch_util.py:394-419
-__device__ __forceinline__ float4 exp_map_to_quat(const float3& e) {
-  const float a = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
-  float3 axis = make_float3(e.x / a, e.y / a, e.z / a);
-  float ang = atan2f(sinf(a), cosf(a));
-  if (!(fabsf(ang) > 1e-5f)) {
-    ang = 0.0f;
-    axis = make_float3(0.0f, 0.0f, 1.0f);
-  }
-  return axis_angle_to_quat(axis, ang);
-}
-
-// VJP of exp_map_to_quat.  At e == 0 the reference's autograd yields NaN (0/0 behind torch.where,
-// SURVEY F8d); here the masked branch returns a zero gradient instead (documented divergence).
-__device__ __forceinline__ float3 exp_map_to_quat_vjp(const float3& e, const float4& g) {
-  const float a = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
-  const float sa = sinf(a), ca = cosf(a);
-  const float ang = atan2f(sa, ca);
-  if (!(fabsf(ang) > 1e-5f)) return make_float3(0.0f, 0.0f, 0.0f);
-  const float3 axis = make_float3(e.x / a, e.y / a, e.z / a);
-  float3 g_axis;
-  float g_ang;
-  axis_angle_to_quat_vjp(axis, ang, g, g_axis, g_ang);
-  // ang = atan2(sin a, cos a): d ang / d a = (ca*ca + sa*sa) / (sa*sa + ca*ca)
-  const float den = sa * sa + ca * ca;
-  float g_a = g_ang * (ca / den) * ca + g_ang * (sa / den) * sa;
-  // axis = e / a
-  g_a -= (g_axis.x * e.x + g_axis.y * e.y + g_axis.z * e.z) / (a * a);
-  return make_float3(g_axis.x / a + g_a * e.x / a, g_axis.y / a + g_a * e.y / a, g_axis.z / a + g_a * e.z / a);
-}
 
 __global__ void __launch_bounds__(256) exp_map_fwd_kernel(const float* __restrict__ e, int64_t n,
                                                           float* __restrict__ q) {

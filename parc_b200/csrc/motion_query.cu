@@ -56,7 +56,8 @@ __device__ __forceinline__ float shfl_g(float v, int src, int width) {
 // Per-query constants of the observation sweep (packed f32x2 operands).
 struct ObsCtx {
   float2 cc, ss, off, neg_min, inv2, neg_d;
-  int hix, hiy, dim_y;
+  float hixf, hiyf;
+  int dim_y;
 };
 
 // World cell of template point tp: the same individually-rounded operations as the reference's
@@ -70,11 +71,12 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
   const float2 q0 = __fmul2_rn(v, c.inv2);
   const float2 r = __ffma2_rn(c.neg_d, q0, v);
   const float2 qd = __ffma2_rn(r, c.inv2, q0);                  // == (p - min) / d, IEEE (see GridAxis)
-  int ix = min(max(__float2int_rn(qd.x), 0), c.hix);
-  int iy = min(max(__float2int_rn(qd.y), 0), c.hiy);
-  if (qd.x >= 9.2e18f) ix = 0;                                  // int64 wrap of the reference
-  if (qd.y >= 9.2e18f) iy = 0;
-  return ix * c.dim_y + iy;
+  // clamp(rint(q), 0, dim-1): upper clamp in float (dim-1 < 2^24 is exact), then one saturating
+  // round-to-nearest-even conversion to u32 (negatives and NaN -> 0, as the reference's clamp gives).
+  // Not emulated: the reference's int64 wrap-around for q >= 2^63 (|coordinate| > 3.6e18 cells).
+  const unsigned ix = __float2uint_rn(fminf(qd.x, c.hixf));
+  const unsigned iy = __float2uint_rn(fminf(qd.y, c.hiyf));
+  return (int)(ix * (unsigned)c.dim_y + iy);
 }
 
 // One GROUP of G lanes per query: G = 32 is the general layout, G = 16 packs two characters into a warp
@@ -274,7 +276,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
       oc.cc = make_float2(cs, cs); oc.ss = make_float2(sn, sn); oc.off = make_float2(rp.x, rp.y);
       oc.neg_min = make_float2(-gx.mn, -gy.mn); oc.inv2 = make_float2(gx.inv, gy.inv);
       oc.neg_d = make_float2(-gx.d, -gy.d);
-      oc.hix = p.hf.dim_x - 1; oc.hiy = p.hf.dim_y - 1; oc.dim_y = p.hf.dim_y;
+      oc.hixf = (float)(p.hf.dim_x - 1); oc.hiyf = (float)(p.hf.dim_y - 1); oc.dim_y = p.hf.dim_y;
       if (tmpl_in_smem) {
 #pragma unroll
         for (int u = 0; u < INFLIGHT; ++u) z[u] = __ldg(hfp + obs_cell(oc, s_tmpl[l + G * u]));
@@ -352,7 +354,7 @@ __device__ __forceinline__ int grid_index_packed_form(float p, const GridAxis& a
   ObsCtx c;
   c.cc = make_float2(1.0f, 1.0f); c.ss = make_float2(0.0f, 0.0f); c.off = make_float2(0.0f, 0.0f);
   c.neg_min = make_float2(-a.mn, -a.mn); c.inv2 = make_float2(a.inv, a.inv); c.neg_d = make_float2(-a.d, -a.d);
-  c.hix = hi; c.hiy = 0; c.dim_y = 1;
+  c.hixf = (float)hi; c.hiyf = 0.0f; c.dim_y = 1;
   // x*1 - 0*0 = x and 0*... exact; (p + 0) == p except -0 -> +0, which indexes identically
   return obs_cell(c, make_float2(p, 0.0f));
 }
@@ -367,7 +369,9 @@ selftest_grid_index_kernel(float mn, float d, int dim, unsigned long long* misma
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     const float x = __uint_as_float((uint32_t)i);
     const int ref = grid_index_1d(x, mn, d, dim);
-    bad += (grid_index_fast(x, a) != ref) || (grid_index_packed_form(x, a, dim - 1) != ref);
+    const float gq = div_rn(sub_rn(x, mn), d);
+    const bool wraps = gq >= 9.2e18f;               // reference wraps through int64 here; sweep form clamps
+    bad += (grid_index_fast(x, a) != ref) || (!wraps && grid_index_packed_form(x, a, dim - 1) != ref);
   }
   if (bad) atomicAdd(mismatches, bad);
 }

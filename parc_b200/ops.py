@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ParcBodyPoints, ParcCharModel, ParcClipMeta, ParcFkOut, ParcFrameOut, ParcHeightfield,
+from ._lib import (ParcBodyPoints, ParcCharModel, ParcKeyBodies, ParcClipMeta, ParcFkOut, ParcFrameOut, ParcHeightfield,
                    ParcMotionTables, ParcObsSpec, ParcRowLayout, ParcTerrainBatch, check, f32c, ptr,
                    require_cuda, stream_ptr)
 
@@ -596,3 +596,88 @@ def body_loss(model: ParcCharModel, pts: BodyPointsDesc, terrain: TerrainBatchDe
               contacts, w_pen: float, w_contact: float):
     """[B,F,...] pose + contacts -> (total[B], pen[B], contact[B]); differentiable wrt the pose."""
     return _BodyLoss.apply(root_pos, root_rot, joint_rot, contacts, model, pts, terrain, w_pen, w_contact)
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY section 8(f) row 1: dataset sweep -- raw frames -> FK, contact labels, heightfield masks
+# ----------------------------------------------------------------------------------------------
+def frames_fk(model: ParcCharModel, frames: torch.Tensor, want_rot: bool = False):
+    """frames [..., >= 6+D] (root_pos | root exp-map | joint DoFs) -> body_pos [...,J,3], body_rot [...,J,4]
+    (and root_rot [...,4], joint_rot [...,J-1,4] if want_rot).  One launch; forward only."""
+    require_cuda(frames)
+    lead = frames.shape[:-1]
+    fr = f32c(frames).reshape(-1, frames.shape[-1])
+    n, J = fr.shape[0], model.num_bodies
+    dev = fr.device
+    bp = torch.empty((n, J, 3), dtype=torch.float32, device=dev)
+    br = torch.empty((n, J, 4), dtype=torch.float32, device=dev)
+    rr = torch.empty((n, 4), dtype=torch.float32, device=dev) if want_rot else None
+    jr = torch.empty((n, J - 1, 4), dtype=torch.float32, device=dev) if want_rot else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_frames_fk(fr.data_ptr(), n, int(fr.shape[1]), C.byref(model), ptr(rr), ptr(jr),
+                                        bp.data_ptr(), br.data_ptr(), stream_ptr(dev))
+    check(rc, "parc_frames_fk")
+    out = (bp.reshape(*lead, J, 3), br.reshape(*lead, J, 4))
+    if want_rot:
+        out += (rr.reshape(*lead, 4), jr.reshape(*lead, J - 1, 4))
+    return out
+
+
+def make_key_bodies(feet, hands) -> ParcKeyBodies:
+    """feet: list of (body_id, half_extents[3], offset[3]); hands: list of (body_id, radius)."""
+    k = ParcKeyBodies()
+    assert len(feet) <= _lib.PARC_MAX_KEY_BODIES and len(hands) <= _lib.PARC_MAX_KEY_BODIES
+    k.num_feet, k.num_hands = len(feet), len(hands)
+    for i, (b, half, off) in enumerate(feet):
+        k.foot_body[i] = int(b)
+        for c in range(3):
+            k.foot_half[i][c] = float(half[c])
+            k.foot_offset[i][c] = float(off[c])
+    for i, (b, r) in enumerate(hands):
+        k.hand_body[i] = int(b)
+        k.hand_radius[i] = float(r)
+    return k
+
+
+def clip_label(model: ParcCharModel, pts: Optional[BodyPointsDesc], terrain: TerrainBatchDesc, keys: ParcKeyBodies,
+               frames: torch.Tensor, contact_eps: float = 0.04, *, want_contacts=True, want_body_hf=False,
+               want_masks=False, want_fk=False, min_body_heights_init: float = 99999.9999) -> dict:
+    """frames [B,F,>=6+D] with one terrain per clip (or one shared) -> dict of label tensors; see
+    include/parc_b200.h::parc_clip_label.  One launch."""
+    require_cuda(frames)
+    fr = f32c(frames)
+    assert fr.dim() == 3
+    B, F, J = fr.shape[0], fr.shape[1], model.num_bodies
+    dev = fr.device
+    X, Y = int(terrain.hf.shape[1]), int(terrain.hf.shape[2])
+    W = (X * Y + 31) // 32
+    out = {}
+    if want_contacts:
+        out["contacts"] = torch.empty((B, F, J), dtype=torch.float32, device=dev)
+        out["pen_correction"] = torch.empty((B, F), dtype=torch.float32, device=dev)
+    if want_body_hf:
+        out["body_hf"] = torch.empty((B, F, J), dtype=torch.float32, device=dev)
+    if want_masks:
+        assert pts is not None
+        out["frame_mask_bits"] = torch.empty((B, F, W), dtype=torch.int32, device=dev)
+        out["min_body_heights"] = torch.full((B, X, Y), min_body_heights_init, dtype=torch.float32, device=dev)
+    if want_fk:
+        out["body_pos"] = torch.empty((B, F, J, 3), dtype=torch.float32, device=dev)
+        out["body_rot"] = torch.empty((B, F, J, 4), dtype=torch.float32, device=dev)
+    t = terrain.c_struct(B)
+    bp = pts.c_struct() if pts is not None else ParcBodyPoints()
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_clip_label(fr.data_ptr(), B, F, int(fr.shape[2]), C.byref(model), C.byref(bp), C.byref(t),
+                                         C.byref(keys), float(contact_eps), ptr(out.get("contacts")),
+                                         ptr(out.get("pen_correction")), ptr(out.get("body_hf")),
+                                         ptr(out.get("frame_mask_bits")), ptr(out.get("min_body_heights")),
+                                         ptr(out.get("body_pos")), ptr(out.get("body_rot")), stream_ptr(dev))
+    check(rc, "parc_clip_label")
+    return out
+
+
+def unpack_frame_masks(bits: torch.Tensor, X: int, Y: int) -> torch.Tensor:
+    """[..., W] int32 bit words -> [..., X, Y] bool (bit ix*Y+iy)."""
+    shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+    b = ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
+    return b.reshape(*bits.shape[:-1], -1)[..., :X * Y].reshape(*bits.shape[:-1], X, Y)

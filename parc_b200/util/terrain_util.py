@@ -187,3 +187,58 @@ def points_hf_sdf(points: torch.Tensor, hf: torch.Tensor, hf_min_box_center: tor
         assert isinstance(radius, float) and radius > 0.0
         sdf = sdf + radius if inverted else sdf - radius
     return sdf
+
+
+# ---- heightfield masks of a motion ---------------------------------------
+def _mask_sweep(motion_frames, terrain: SubTerrain, char_model, char_body_points):
+    from ..tools.procgen.mdm_path import body_points_desc
+    tb = ops.make_terrain_batch(terrain.hf, terrain.min_point, terrain.dxdy.detach().cpu().tolist(), base_z=-10.0)
+    keys = ops.make_key_bodies([], [])
+    out = ops.clip_label(char_model.c_model(), body_points_desc(char_model, char_body_points), tb, keys,
+                         motion_frames.unsqueeze(0), want_contacts=False, want_masks=True)
+    X, Y = int(terrain.hf.shape[0]), int(terrain.hf.shape[1])
+    return ops.unpack_frame_masks(out["frame_mask_bits"][0], X, Y), out["min_body_heights"][0]
+
+
+def compute_hf_mask_inds(motion_frames: torch.Tensor, terrain: SubTerrain, char_model, char_body_points):
+    """Per frame, the unique grid cells any body surface point falls in, plus the per-cell minimum body
+    height.  -> (list of int64 [K_t, 2] tensors sorted like torch.unique(dim=0), min_body_heights [X, Y]).
+    Replaces the frame x body x point python loop of util/terrain_util.py:1951-1997 by one launch (FK, point
+    transform, cell index, per-frame bit mask, atomic per-cell min) plus one nonzero()."""
+    terrain.hf_mask[...] = False                                   # side effect of the reference (:1966)
+    masks, min_h = _mask_sweep(motion_frames, terrain, char_model, char_body_points)
+    nz = torch.nonzero(masks)                                      # [K, 3] rows (t, ix, iy), lexicographic
+    counts = torch.bincount(nz[:, 0], minlength=masks.shape[0]).tolist()
+    return list(torch.split(nz[:, 1:], counts)), min_h
+
+
+def compute_hf_mask_from_inds(terrain: SubTerrain, mask_grid_inds):
+    """Ref util/terrain_util.py:1999-2006."""
+    hf_mask = torch.zeros_like(terrain.hf_mask)
+    if len(mask_grid_inds) > 0:
+        allc = torch.cat(list(mask_grid_inds), dim=0)
+        hf_mask[allc[..., 0], allc[..., 1]] = True
+    return hf_mask
+
+
+def compute_hf_mask(motion_frames, terrain: SubTerrain, char_model, char_body_points):
+    """Ref util/terrain_util.py:2008-2014."""
+    inds, _ = compute_hf_mask_inds(motion_frames, terrain, char_model, char_body_points)
+    return compute_hf_mask_from_inds(terrain, inds)
+
+
+def compute_hf_extra_vals(motion_frames, terrain: SubTerrain, char_model, char_body_points, z_buf=3.0, jump_buf=0.8):
+    """Fill terrain.hf_mask / terrain.hf_maxmin from a motion.  Ref util/terrain_util.py:2017-2047."""
+    mask_grid_inds, min_body_heights = compute_hf_mask_inds(motion_frames, terrain, char_model, char_body_points)
+    terrain.hf_mask = compute_hf_mask_from_inds(terrain, mask_grid_inds)
+    max_h = torch.max(motion_frames[:, 2]).item()
+    min_h = torch.min(terrain.hf).item()
+    terrain.hf_maxmin[..., 0] = max_h + z_buf
+    terrain.hf_maxmin[..., 1] = min_h - z_buf
+    hf_vals = terrain.hf[terrain.hf_mask]
+    terrain.hf_maxmin[..., 0][terrain.hf_mask] = hf_vals
+    terrain.hf_maxmin[..., 1][terrain.hf_mask] = hf_vals
+    jump = torch.logical_and((min_body_heights - terrain.hf) >= jump_buf, terrain.hf_mask)
+    terrain.hf_maxmin[..., 0][jump] = min_body_heights[jump] - jump_buf
+    terrain.hf_maxmin[..., 1][jump] = min_h - z_buf
+    return mask_grid_inds

@@ -432,3 +432,106 @@ def test_body_loss_linearity_full_size(gpu_model):
     assert_close(pen_a + pen_b, pen, rtol=1e-5, what="pen additivity")
     assert_close(con_a + con_b, con, rtol=1e-5, atol=1e-5, what="contact additivity")
     assert (pen >= 0).all() and torch.isfinite(pen).all() and torch.isfinite(con).all()
+
+
+# ----------------------------------------------------------------------------------------- dataset sweep (8(f)-1)
+def test_frames_fk_matches_three_step_path(gpu_model):
+    from parc_b200 import ops
+    civ, q = golden("clip_civilization.npz"), golden("dof_golden.npz")
+    fr = dev(civ["frames"])
+    bp, br, rr, jr = ops.frames_fk(gpu_model.c_model(), fr, want_rot=True)
+    assert_close(rr, q["root_quat"], what="frames_fk root_rot")
+    assert_close(jr, q["joint_rot"], what="frames_fk joint_rot")
+    bp2, br2 = gpu_model.forward_kinematics(fr[:, 0:3], ops.exp_map_to_quat(fr[:, 3:6]), gpu_model.dof_to_rot(fr[:, 6:]))
+    assert torch.equal(bp, bp2) and torch.equal(br, br2)
+    bp3, _ = gpu_model.frames_forward_kinematics(fr.view(2, 127, 34))
+    assert bp3.shape == (2, 127, 15, 3) and torch.equal(bp3.view(254, 15, 3), bp)
+
+
+def test_contact_labelling_vs_golden(gpu_model):
+    from parc_b200.zmotion_editing_tools.motion_edit_lib import (compute_hf_foot_contacts_and_correct_pen,
+                                                                 compute_motion_terrain_hand_contacts)
+    g = golden("label_golden.npz")
+    t = _civ_terrain()
+    frames = dev(g["frames"])
+    upd, fc = compute_hf_foot_contacts_and_correct_pen(frames, t, gpu_model)
+    assert fc.shape == (64, 15)
+    assert (fc.cpu() != torch.tensor(g["foot_contacts"])).sum() <= 1        # thresholded; 1 borderline frame allowed
+    assert fc[:, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13]].abs().sum() == 0
+    assert_close(upd[:, 2], g["updated_z"], atol=2e-6, what="penetration-corrected root z")
+    assert torch.equal(upd[:, :2], frames[:, :2]) and torch.equal(upd[:, 3:], frames[:, 3:])
+    hc = compute_motion_terrain_hand_contacts(frames, t, gpu_model)
+    assert (hc.cpu() != torch.tensor(g["hand_contacts"])).sum() <= 1
+    t.hf = t.hf + float(g["raised_by"])
+    hc2 = compute_motion_terrain_hand_contacts(frames, t, gpu_model)
+    assert (hc2.cpu() != torch.tensor(g["hand_contacts_raised"])).sum() <= 1
+    assert hc2.sum() > 10
+
+
+def test_hf_mask_inds_vs_golden(gpu_model):
+    from parc_b200.util import geom_util
+    from parc_b200.util.terrain_util import compute_hf_extra_vals, compute_hf_mask_from_inds, compute_hf_mask_inds
+    g = golden("label_golden.npz")
+    t = _civ_terrain()
+    frames = dev(g["frames"][:24])
+    pts = geom_util.get_char_point_samples(gpu_model)
+    inds, minh = compute_hf_mask_inds(frames, t, gpu_model, pts)
+    assert len(inds) == 24 and all(i.dtype == torch.int64 and i.shape[1] == 2 for i in inds)
+    # cell membership is exact except for surface points within an ulp of a cell border
+    exp_counts = g["mask_counts"].tolist()
+    got = torch.cat(inds).cpu()
+    if [i.shape[0] for i in inds] == exp_counts:
+        assert (got != torch.tensor(g["mask_inds"])).any(dim=1).float().mean() < 0.01
+    else:
+        assert sum(abs(a.shape[0] - b) for a, b in zip(inds, exp_counts)) <= 3
+    mask = compute_hf_mask_from_inds(t, inds).cpu()
+    assert (mask != torch.tensor(g["hf_mask"])).sum() <= 2
+    exp_minh = torch.tensor(g["min_body_heights"])
+    same = (minh.cpu() - exp_minh).abs() <= 1e-5 * exp_minh.abs().clamp(min=1.0)
+    assert (~same).sum() <= 2
+    compute_hf_extra_vals(frames, t, gpu_model, pts)
+    assert (t.hf_mask.cpu() != torch.tensor(g["extra_hf_mask"])).sum() <= 2
+    mm = (t.hf_maxmin.cpu() - torch.tensor(g["extra_hf_maxmin"])).abs() > 1e-4
+    assert mm.sum() <= 4
+
+
+def test_label_clips_batched_vs_oracle(gpu_model, O, oracle_model):
+    """Config-5-shaped: a batch of clips, one 16x16 terrain per clip, feet + hands + body hf in one launch."""
+    from parc_b200 import ops
+    from parc_b200.util import geom_util, synth
+    from parc_b200.zmotion_editing_tools.motion_edit_lib import label_clips
+    g = golden("label_golden.npz")
+    rng = np.random.default_rng(8)
+    B, F = 5, 40
+    hfs = np.stack([synth.box_terrain(rng, h_range=(-0.4, 0.7)) if i % 2 else synth.stairs_terrain(rng) for i in range(B)])
+    fr = np.concatenate([synth.synth_clips(gpu_model, 1, seed=50 + i, num_frames=F, hf=hfs[i])[0] for i in range(B)])
+    fr[..., 2] -= 0.02
+    tb = ops.make_terrain_batch(torch.tensor(hfs).cuda(), torch.zeros(B, 2).cuda(), (0.4, 0.4),
+                                base_z=(torch.tensor(hfs).amin(dim=(1, 2)) - 10.0).cuda())
+    pts = geom_util.get_char_point_samples(gpu_model)
+    out = label_clips(torch.tensor(fr).cuda(), tb, gpu_model, body_points=pts, want_masks=True, want_fk=True)
+    feet = [(int(b), h.tolist(), o.tolist()) for b, h, o in zip(g["feet_body"], g["feet_half"], g["feet_offset"])]
+    hands = [(int(b), float(r)) for b, r in zip(g["hands_body"], g["hands_radius"])]
+    bad = 0
+    for i in range(B):
+        t = O.Terrain(hf=torch.tensor(hfs[i]), min_point=torch.zeros(2), dxdy=torch.tensor([0.4, 0.4]))
+        f_i = torch.tensor(fr[i])
+        _, fc, corr = O.foot_contacts_and_pen(oracle_model, f_i, t, feet)
+        hc = O.hand_contacts(oracle_model, f_i, t, hands)
+        exp = fc + hc
+        bad += int((out["contacts"][i].cpu() != exp).sum())
+        assert_close(out["pen_correction"][i], corr, atol=2e-6, what=f"pen_correction clip {i}")
+        bp, _ = O.frames_fk(oracle_model, f_i)
+        assert_close(out["body_pos"][i], bp, what="label body_pos")
+        bhf = O.hf_sample(t, bp[..., 0:2])
+        assert (out["body_hf"][i].cpu() != bhf).float().mean() < 0.01
+        inds, minh = O.hf_mask_inds(oracle_model, f_i, t)
+        masks = ops.unpack_frame_masks(out["frame_mask_bits"][i], 16, 16).cpu()
+        exp_m = torch.zeros(F, 16, 16, dtype=torch.bool)
+        for f, ind in enumerate(inds):
+            exp_m[f, ind[:, 0], ind[:, 1]] = True
+        assert (masks != exp_m).float().mean() < 1e-3
+        same = (out["min_body_heights"][i].cpu() - minh).abs() <= 1e-5 * minh.abs().clamp(min=1.0)
+        assert (~same).sum() <= 2
+    assert bad <= 3, f"{bad} contact labels differ"
+    assert out["contacts"].sum() > 0

@@ -106,3 +106,21 @@ def test_sdf_and_losses(oracle_model):
     assert_close(a.grad, L["mo_grad_root_pos"], rtol=1e-5, atol=1e-3, what="grad root_pos")
     assert_close(b.grad, L["mo_grad_root_exp"], rtol=1e-5, atol=1e-3, what="grad root_exp")
     assert_close(c.grad, L["mo_grad_joint_dof"], rtol=1e-5, atol=1e-3, what="grad joint_dof")
+
+
+def test_contact_labelling_and_masks(oracle_model):
+    civ, g = golden("clip_civilization.npz"), golden("label_golden.npz")
+    t = O.Terrain(hf=T(civ["hf"]), min_point=T(civ["min_point"]), dxdy=T(civ["dxdy"]))
+    frames = T(g["frames"])
+    feet = [(int(b), h.tolist(), o.tolist()) for b, h, o in zip(g["feet_body"], g["feet_half"], g["feet_offset"])]
+    hands = [(int(b), float(r)) for b, r in zip(g["hands_body"], g["hands_radius"])]
+    upd, fc, _ = O.foot_contacts_and_pen(oracle_model, frames, t, feet)
+    assert (fc != T(g["foot_contacts"])).sum() <= 1               # thresholded: tolerate one borderline frame
+    assert_close(upd[:, 2], g["updated_z"], rtol=1e-6, atol=1e-6, what="updated root z")
+    t2 = O.Terrain(hf=t.hf + float(g["raised_by"]), min_point=t.min_point, dxdy=t.dxdy)
+    assert (O.hand_contacts(oracle_model, frames, t2, hands) != T(g["hand_contacts_raised"])).sum() <= 1
+    assert (O.hand_contacts(oracle_model, frames, t, hands) != T(g["hand_contacts"])).sum() <= 1
+    inds, minh = O.hf_mask_inds(oracle_model, frames[:24], t)
+    assert [i.shape[0] for i in inds] == g["mask_counts"].tolist()
+    assert torch.equal(torch.cat(inds), T(g["mask_inds"]))
+    assert_close(minh, g["min_body_heights"], rtol=1e-6, atol=1e-6, what="min body heights")
