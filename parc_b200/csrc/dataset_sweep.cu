@@ -117,9 +117,11 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
   }
   __syncthreads();
   const int J = sm.num_bodies;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
-    for (int k = s0; k < s1; ++k) s_body[k] = j;
+  if (S > 0) {
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
+      for (int k = s0; k < s1; ++k) s_body[k] = j;
+    }
   }
   const float* mc = p.terrain.min_center + b * p.terrain.min_center_stride;
   const float min_x = __ldg(mc), min_y = __ldg(mc + 1);
@@ -156,7 +158,7 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
     __syncthreads();
 
     // ---- every surface point: cell it falls in -> per-frame mask bit, per-cell min body height ----
-    if (p.frame_mask || p.min_body_heights) {
+    if ((p.frame_mask || p.min_body_heights) && S > 0) {
       for (int k = threadIdx.x; k < S; k += blockDim.x) {
         const int bj = s_body[k];
         const float3 lp = make_float3(__ldg(p.pts.points + k * 3), __ldg(p.pts.points + k * 3 + 1),

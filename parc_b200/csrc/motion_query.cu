@@ -56,7 +56,7 @@ __device__ __forceinline__ float shfl_g(float v, int src, int width) {
 // Per-query constants of the observation sweep (packed f32x2 operands).
 struct ObsCtx {
   float2 cc, ss, off, neg_min, inv2, neg_d;
-  float hixf, hiyf;
+  unsigned hix, hiy;
   int dim_y;
 };
 
@@ -71,11 +71,11 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
   const float2 q0 = __fmul2_rn(v, c.inv2);
   const float2 r = __ffma2_rn(c.neg_d, q0, v);
   const float2 qd = __ffma2_rn(r, c.inv2, q0);                  // == (p - min) / d, IEEE (see GridAxis)
-  // clamp(rint(q), 0, dim-1): upper clamp in float (dim-1 < 2^24 is exact), then one saturating
-  // round-to-nearest-even conversion to u32 (negatives and NaN -> 0, as the reference's clamp gives).
-  // Not emulated: the reference's int64 wrap-around for q >= 2^63 (|coordinate| > 3.6e18 cells).
-  const unsigned ix = __float2uint_rn(fminf(qd.x, c.hixf));
-  const unsigned iy = __float2uint_rn(fminf(qd.y, c.hiyf));
+  // clamp(rint(q), 0, dim-1): one saturating round-to-nearest-even conversion to u32 (negatives and NaN
+  // -> 0, as the reference's clamp gives; >= 2^32 -> UINT_MAX), then an unsigned min with dim-1.
+  // Not emulated: the reference's int64 wrap-around to cell 0 for q >= 2^63 (|coordinate| > 3.6e18 cells).
+  const unsigned ix = min(__float2uint_rn(qd.x), c.hix);
+  const unsigned iy = min(__float2uint_rn(qd.y), c.hiy);
   return (int)(ix * (unsigned)c.dim_y + iy);
 }
 
@@ -276,7 +276,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
       oc.cc = make_float2(cs, cs); oc.ss = make_float2(sn, sn); oc.off = make_float2(rp.x, rp.y);
       oc.neg_min = make_float2(-gx.mn, -gy.mn); oc.inv2 = make_float2(gx.inv, gy.inv);
       oc.neg_d = make_float2(-gx.d, -gy.d);
-      oc.hixf = (float)(p.hf.dim_x - 1); oc.hiyf = (float)(p.hf.dim_y - 1); oc.dim_y = p.hf.dim_y;
+      oc.hix = (unsigned)(p.hf.dim_x - 1); oc.hiy = (unsigned)(p.hf.dim_y - 1); oc.dim_y = p.hf.dim_y;
       if (tmpl_in_smem) {
 #pragma unroll
         for (int u = 0; u < INFLIGHT; ++u) z[u] = __ldg(hfp + obs_cell(oc, s_tmpl[l + G * u]));
@@ -354,7 +354,7 @@ __device__ __forceinline__ int grid_index_packed_form(float p, const GridAxis& a
   ObsCtx c;
   c.cc = make_float2(1.0f, 1.0f); c.ss = make_float2(0.0f, 0.0f); c.off = make_float2(0.0f, 0.0f);
   c.neg_min = make_float2(-a.mn, -a.mn); c.inv2 = make_float2(a.inv, a.inv); c.neg_d = make_float2(-a.d, -a.d);
-  c.hixf = (float)hi; c.hiyf = 0.0f; c.dim_y = 1;
+  c.hix = (unsigned)hi; c.hiy = 0u; c.dim_y = 1;
   // x*1 - 0*0 = x and 0*... exact; (p + 0) == p except -0 -> +0, which indexes identically
   return obs_cell(c, make_float2(p, 0.0f));
 }
