@@ -282,6 +282,38 @@ def main():
     total_envs = args.envs * world
     value = total_envs * BODIES * K / (elapsed_ms_max * 1e-3)
 
+    # ---- extra: the tracker's real per-step shape (reference frame + 6 tar_obs_steps look-aheads per env in ONE
+    #      launch, observation at the current frame) -- reported beside the headline, not instead of it ----
+    tar_steps = torch.tensor([0, 1, 2, 3, 10, 20, 30], dtype=torch.float32)
+    offsets = ((1.0 / 30.0) * tar_steps).to(dev)
+    step_out = {}
+    step_plans = [mlib.make_query_plan(ids_d[b], times_d[b], hf_desc=hfd, obs_tmpl=tmpl, out=step_out,
+                                       time_offsets=offsets) for b in range(NB)]
+    for w in range(3):
+        flush.zero_()
+        step_plans[w].launch(raw_stream)
+    KS = min(K, 100)
+    s_starts = [torch.cuda.Event(enable_timing=True) for _ in range(KS)]
+    s_stops = [torch.cuda.Event(enable_timing=True) for _ in range(KS)]
+    barrier()
+    for s in range(KS):
+        flush.zero_()
+        s_starts[s].record(stream)
+        step_plans[s % NB].launch(raw_stream)
+        s_stops[s].record(stream)
+    barrier()
+    step_ms = sum(a.elapsed_time(b) for a, b in zip(s_starts, s_stops)) / KS
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = t.item()
+    S = int(tar_steps.shape[0])
+    step_bytes = args.envs * (12 + S * (36 + 624 + 136 + 448 + 420) + 1764 + 1764)
+    tracker_step = {"what": f"{args.envs} envs x {S} frame queries + FK (current + tar_obs_steps 1,2,3,10,20,30) + "
+                            f"{RAY_POINTS}-pt obs at the current frame, one launch",
+                    "value": total_envs * S * BODIES / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms,
+                    "algorithmic_bytes_per_launch": step_bytes}
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the region ----
     ids_p, times_p = ids_h.pin_memory(), times_h.pin_memory()
     ids_in = torch.empty(args.envs, dtype=torch.int64, device=dev)
@@ -377,8 +409,9 @@ def main():
                    "frame table 260 MB > L2", "timing": "CUDA events per step on the launch stream, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "tracker_step": tracker_step,
     }
+    tracker_step["roofline_frac"] = step_bytes / (step_ms * 1e-3) / 1e9 / peak
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -157,6 +157,17 @@ int parc_motion_query(const ParcMotionTables* tables, const int64_t* motion_ids,
                       const ParcFkOut* fk, const ParcHeightfield* hf, const ParcObsSpec* obs,
                       float* obs_out, void* stream);
 
+/* Tracker-step form: every (id, time) entry e is queried at num_steps times  t_e + time_offsets[k]
+ * (query q = e * num_steps + k; outputs are [n, num_steps, ...], i.e. [n * num_steps, ...] rows) -- what the
+ * tracker does every control step: the reference frame (dm_env.py:570-595) plus the future targets of
+ * fetch_tar_obs_data (envs/ig_parkour/mgdm_dm_util.py:279-302: ids tiled, motion_times + timestep *
+ * tar_obs_steps, one fp32 add as there).  Pass time_offsets[0] = 0 for the current frame.  The heightmap
+ * observation, if requested, is produced for step 0 of each entry only: obs_out is [n, num_points]. */
+int parc_motion_query_steps(const ParcMotionTables* tables, const int64_t* motion_ids, const float* motion_times,
+                            int64_t n, const float* time_offsets, int32_t num_steps, const ParcCharModel* model,
+                            const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
+                            const ParcObsSpec* obs, float* obs_out, void* stream);
+
 /* a4: MotionLib.get_motion_frame (anim/motion_lib.py:114-131): integer frame lookup, no blending. */
 int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
                           const int64_t* frame_idxs, int64_t n, const ParcCharModel* model,

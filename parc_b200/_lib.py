@@ -108,6 +108,9 @@ SIGNATURES = {
     "parc_pack_frames": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V]),
     "parc_motion_query": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel), _P(ParcFrameOut),
                                     _P(ParcFkOut), _P(ParcHeightfield), _P(ParcObsSpec), _V, _V]),
+    "parc_motion_query_steps": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _V, _I32, _P(ParcCharModel),
+                                          _P(ParcFrameOut), _P(ParcFkOut), _P(ParcHeightfield), _P(ParcObsSpec),
+                                          _V, _V]),
     "parc_get_motion_frame": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel),
                                         _P(ParcFrameOut), _P(ParcFkOut), _V]),
     "parc_fk_fwd": (C.c_int, [_V, _V, _V, _I64, _P(ParcCharModel), _V, _V, _V]),

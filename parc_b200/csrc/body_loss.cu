@@ -22,43 +22,106 @@ struct SdfBest {
   int arg_sol;
 };
 
-// Scan every cell.  hf/cx/cy are shared-memory (or global) arrays; all threads of a warp read the
-// same cell at the same time, so shared reads are broadcasts.
+// Exact min over ALL cells of the box SDF, with pruning that cannot change the result.
+//
+// For a cell whose xy footprint does not contain the point (mx > 0 or my > 0, m = max(|p - c| - half, 0))
+// the SDF is sqrt(mx^2 + my^2 + mz^2) >= sqrt(mx^2 + my^2) =: bound.  A cell (or a whole row ix, bound mx)
+// whose bound is STRICTLY greater than the best value found so far can neither be the minimum nor tie
+// with it, so it is skipped; cells whose footprint contains the point are always evaluated (their SDF can
+// be negative).  The scan is seeded with the cell under the point.  Because evaluation order is no longer
+// index order, the first-index tie rule of torch.min is kept explicitly: a candidate replaces the best
+// iff it is smaller, or equal with a smaller flat index.  The bound test carries a 1e-6 relative margin
+// for the rounding of best^2 (evaluating too many cells is always safe).
+// hf/cx/cy are shared-memory arrays; a warp's threads are points of the same body, so their skip patterns
+// mostly coincide.
+template <bool WANT_INV, bool WANT_SOL>
+__device__ __forceinline__ void eval_cell(const float* __restrict__ hf, int cell, float mxy2, float qxy, float pz,
+                                          float base, float top, SdfBest& b) {
+  const float h = hf[cell];
+  if (WANT_INV) {
+    const float cz = (h + top) * 0.5f;
+    const float hz = (top - h) * 0.5f;
+    const float qz = fabsf(pz - cz) - hz;
+    const float mz = fmaxf(qz, 0.0f);
+    const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
+    if (sd < b.inv || (sd == b.inv && cell < b.arg_inv)) { b.inv = sd; b.arg_inv = cell; }
+  }
+  if (WANT_SOL) {
+    const float cz = (h + base) * 0.5f;
+    const float hz = (h - base) * 0.5f;
+    const float qz = fabsf(pz - cz) - hz;
+    const float mz = fmaxf(qz, 0.0f);
+    const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
+    if (sd < b.sol || (sd == b.sol && cell < b.arg_sol)) { b.sol = sd; b.arg_sol = cell; }
+  }
+}
+
+// squared pruning threshold for a current best value (negative best: every outside cell is > best)
+__device__ __forceinline__ float prune_thr(float best) {
+  return best < 0.0f ? 0.0f : best * best * 1.000001f;
+}
+
+// Effective squared xy-reach for the wanted modes.  Every solid column tops out at or below the tile's
+// maximum height H and every air column starts at or above the tile's minimum height L, so for a cell whose
+// footprint does not contain the point
+//     sdf_solid >= sqrt(mxy^2 + vz_sol^2),  vz_sol = max(pz - H, base - pz, 0)
+//     sdf_air   >= sqrt(mxy^2 + vz_inv^2),  vz_inv = max(L - pz, pz - top, 0)
+// and the cell can be skipped when mxy^2 > best^2 - vz^2 for every wanted mode.
+template <bool WANT_INV, bool WANT_SOL>
+__device__ __forceinline__ float prune_thr2(const SdfBest& b, float vz_inv2, float vz_sol2) {
+  return fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, WANT_SOL ? prune_thr(b.sol) - vz_sol2 : -1.0f);
+}
+
+// clamp-then-convert so that huge / NaN intermediate values cannot overflow the int conversion
+__device__ __forceinline__ int to_index(float v, int hi) {
+  return (int)fminf(fmaxf(v, 0.0f), (float)hi);
+}
+
 template <bool WANT_INV, bool WANT_SOL>
 __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, const float* __restrict__ cx,
                                               const float* __restrict__ cy, int X, int Y, float hx, float hy,
-                                              float base, float3 p) {
+                                              float base, float hf_min, float hf_max, float3 p) {
   SdfBest b;
-  b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0; b.arg_sol = 0;
+  b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0x7fffffff; b.arg_sol = 0x7fffffff;
   const float top = -base;
-  for (int ix = 0; ix < X; ++ix) {
+  // vertical lower bounds, shrunk by a relative 1e-6 so rounding in the per-cell evaluation cannot beat them
+  const float vzs = fmaxf(fmaxf(p.z - hf_max, base - p.z), 0.0f) * 0.999999f;
+  const float vzi = fmaxf(fmaxf(hf_min - p.z, p.z - top), 0.0f) * 0.999999f;
+  const float vz_sol2 = vzs * vzs, vz_inv2 = vzi * vzi;
+  // cells are evenly spaced (torch.linspace nodes): spacing from the end points
+  const float sx = X > 1 ? (cx[X - 1] - cx[0]) / (float)(X - 1) : 1.0f;
+  const float sy = Y > 1 ? (cy[Y - 1] - cy[0]) / (float)(Y - 1) : 1.0f;
+  const float isx = 1.0f / sx, isy = 1.0f / sy;
+  // seed: the cell whose centre is nearest in xy
+  {
+    const int ix = to_index(rintf((p.x - cx[0]) * isx), X - 1);
+    const int iy = to_index(rintf((p.y - cy[0]) * isy), Y - 1);
+    const float qx = fabsf(p.x - cx[ix]) - hx, qy = fabsf(p.y - cy[iy]) - hy;
+    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b);
+  }
+  float thr = prune_thr2<WANT_INV, WANT_SOL>(b, vz_inv2, vz_sol2);
+  // Index window that is a SUPERSET of every cell that can still matter: a cell further than r = sqrt(thr)
+  // (+ its half width) from the point in x or in y is out of reach.  One extra cell of margin on each side
+  // absorbs the rounding of the spacing; cells inside the window are still bound-checked one by one.
+  const float r = sqrtf(fmaxf(thr, 0.0f));
+  const int ix_lo = to_index(floorf((p.x - r - hx - cx[0]) * isx) - 1.0f, X - 1);
+  const int ix_hi = to_index(ceilf((p.x + r + hx - cx[0]) * isx) + 1.0f, X - 1);
+  const int iy_lo = to_index(floorf((p.y - r - hy - cy[0]) * isy) - 1.0f, Y - 1);
+  const int iy_hi = to_index(ceilf((p.y + r + hy - cy[0]) * isy) + 1.0f, Y - 1);
+  for (int ix = ix_lo; ix <= ix_hi; ++ix) {
     const float qx = fabsf(p.x - cx[ix]) - hx;
     const float mx = fmaxf(qx, 0.0f);
     const float mx2 = mx * mx;
-    const float* __restrict__ col = hf + ix * Y;
-#pragma unroll 4
-    for (int iy = 0; iy < Y; ++iy) {
+    if (mx2 > 0.0f && mx2 > thr) continue;         // whole row out of reach
+    for (int iy = iy_lo; iy <= iy_hi; ++iy) {
       const float qy = fabsf(p.y - cy[iy]) - hy;
       const float my = fmaxf(qy, 0.0f);
       const float mxy2 = mx2 + my * my;
-      const float qxy = fmaxf(qx, qy);
-      const float h = col[iy];
-      if (WANT_INV) {
-        const float cz = (h + top) * 0.5f;
-        const float hz = (top - h) * 0.5f;
-        const float qz = fabsf(p.z - cz) - hz;
-        const float mz = fmaxf(qz, 0.0f);
-        const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
-        if (sd < b.inv) { b.inv = sd; b.arg_inv = ix * Y + iy; }
-      }
-      if (WANT_SOL) {
-        const float cz = (h + base) * 0.5f;
-        const float hz = (h - base) * 0.5f;
-        const float qz = fabsf(p.z - cz) - hz;
-        const float mz = fmaxf(qz, 0.0f);
-        const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
-        if (sd < b.sol) { b.sol = sd; b.arg_sol = ix * Y + iy; }
-      }
+      if (mxy2 > 0.0f && mxy2 > thr) continue;     // outside the footprint and strictly out of reach
+      const float old_inv = b.inv, old_sol = b.sol;
+      eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b);
+      if (b.inv < old_inv || b.sol < old_sol) thr = prune_thr2<WANT_INV, WANT_SOL>(b, vz_inv2, vz_sol2);
     }
   }
   return b;
@@ -98,14 +161,34 @@ __device__ __forceinline__ float3 cell_grad(const float* hf, const float* cx, co
   return sd_box_grad(make_float3(p.x - cx[ix], p.y - cy[iy], p.z - cz), make_float3(hx, hy, hz));
 }
 
-// Stage one sample's terrain: hf tile, absolute cell-centre coordinates (node offset + min centre,
-// added in fp32 as util/terrain_util.py:1859-1860 does).
+// Stage one sample's terrain: hf tile, absolute cell-centre coordinates (node offset + min centre, added
+// in fp32 as util/terrain_util.py:1859-1860 does), and the tile's min / max height for the pruning bounds
+// (s_minmax[0] = min, [1] = max; must be followed by __syncthreads()).
 __device__ __forceinline__ void stage_terrain(const ParcTerrainBatch& t, int64_t b, float* s_hf, float* s_cx,
-                                              float* s_cy) {
+                                              float* s_cy, float* s_minmax) {
   const int X = t.dim_x, Y = t.dim_y;
   const float* hf = t.hf + b * t.hf_batch_stride;
   const float* mc = t.min_center + b * t.min_center_stride;
-  for (int i = threadIdx.x; i < X * Y; i += blockDim.x) s_hf[i] = __ldg(hf + i);
+  if (threadIdx.x == 0) { s_minmax[0] = INFINITY; s_minmax[1] = -INFINITY; }
+  __syncthreads();
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < X * Y; i += blockDim.x) {
+    const float h = __ldg(hf + i);
+    s_hf[i] = h;
+    lo = fminf(lo, h); hi = fmaxf(hi, h);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(PARC_FULL_MASK, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(PARC_FULL_MASK, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // float min / max through the int-ordered trick (values may be negative)
+    if (lo >= 0.0f) atomicMin(reinterpret_cast<int*>(&s_minmax[0]), __float_as_int(lo));
+    else atomicMax(reinterpret_cast<unsigned int*>(&s_minmax[0]), __float_as_uint(lo));
+    if (hi >= 0.0f) atomicMax(reinterpret_cast<int*>(&s_minmax[1]), __float_as_int(hi));
+    else atomicMin(reinterpret_cast<unsigned int*>(&s_minmax[1]), __float_as_uint(hi));
+  }
   for (int i = threadIdx.x; i < X; i += blockDim.x) s_cx[i] = __ldg(t.x_nodes + i) + __ldg(mc);
   for (int i = threadIdx.x; i < Y; i += blockDim.x) s_cy[i] = __ldg(t.y_nodes + i) + __ldg(mc + 1);
 }
@@ -125,20 +208,22 @@ points_hf_sdf_kernel(const float* __restrict__ points, int64_t n_points, const _
   float* s_hf = smem;
   float* s_cx = s_hf + X * Y;
   float* s_cy = s_cx + X;
+  __shared__ float s_minmax[2];
   const int64_t b = blockIdx.y;
-  stage_terrain(t, b, s_hf, s_cx, s_cy);
+  stage_terrain(t, b, s_hf, s_cx, s_cy, s_minmax);
   __syncthreads();
   const float base = sample_base_z(t, b);
+  const float hf_min = s_minmax[0], hf_max = s_minmax[1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += (int64_t)gridDim.x * blockDim.x) {
     const float* pp = points + (b * n_points + i) * 3;
     const float3 p = make_float3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2));
     float v;
     int a;
     if (inverted) {
-      const SdfBest r = scan_cells<true, false>(s_hf, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, p);
+      const SdfBest r = scan_cells<true, false>(s_hf, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
       v = -1.0f * r.inv; a = r.arg_inv;
     } else {
-      const SdfBest r = scan_cells<false, true>(s_hf, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, p);
+      const SdfBest r = scan_cells<false, true>(s_hf, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
       v = r.sol; a = r.arg_sol;
     }
     sdf[b * n_points + i] = v;
@@ -163,7 +248,7 @@ struct BodyLossParams {
   int want_grad;
 };
 
-__global__ void __launch_bounds__(LOSS_THREADS)
+__global__ void __launch_bounds__(LOSS_THREADS, 3)   // <= 64 registers: 3 CTAs (30 warps) per SM
 body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
   __shared__ ParcCharModel sm;
@@ -172,6 +257,9 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
   __shared__ float s_warp_sum[LOSS_THREADS / 32];
   __shared__ int s_winner[PARC_MAX_BODIES];
   __shared__ float s_contact_w[PARC_MAX_BODIES];   // w_contact * contacts[f,b] if the winner's clamp passes
+  __shared__ float s_cterm[PARC_MAX_BODIES];
+  __shared__ float s_contact[PARC_MAX_BODIES];     // contacts[b,f,:] of the current frame
+  __shared__ float s_gbody[PARC_MAX_BODIES][7];
 
   const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
   const int S = p.pts.num_points;
@@ -183,9 +271,11 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
   int* s_body = reinterpret_cast<int*>(s_g + (size_t)S * 7);   // [S] body of point
 
   const int64_t b = blockIdx.y;
+  __shared__ float s_minmax[2];
   stage_model(&sm, model_param);
-  stage_terrain(p.terrain, b, s_hf, s_cx, s_cy);
+  stage_terrain(p.terrain, b, s_hf, s_cx, s_cy, s_minmax);
   __syncthreads();
+  const float hf_min = s_minmax[0], hf_max = s_minmax[1];
   const int J = sm.num_bodies;
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
@@ -216,6 +306,7 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
       if (lane < J) {
         s_bpos[lane][0] = pos.x; s_bpos[lane][1] = pos.y; s_bpos[lane][2] = pos.z;
         s_brot[lane][0] = rot.x; s_brot[lane][1] = rot.y; s_brot[lane][2] = rot.z; s_brot[lane][3] = rot.w;
+        s_contact[lane] = __ldg(p.contacts + q * J + lane);
       }
     }
     __syncthreads();
@@ -229,7 +320,15 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
       const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
       const float3 r = quat_rotate(br, lp);
       const float3 wp = make_float3(r.x + s_bpos[bj][0], r.y + s_bpos[bj][1], r.z + s_bpos[bj][2]);
-      const SdfBest best = scan_cells<true, true>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, wp);
+      // A body whose contact weight is exactly 0 contributes exactly 0 to the contact term and to its
+      // gradient (closest * 0), so its solid-column scan is skipped.
+      SdfBest best;
+      if (s_contact[bj] != 0.0f) {
+        best = scan_cells<true, true>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp);
+      } else {
+        best = scan_cells<true, false>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp);
+        best.sol = 0.0f; best.arg_sol = 0;
+      }
       // penetration: sdf = -best.inv ; neg = min(sdf, 0) ; pen += -neg
       const float sdf_inv = -1.0f * best.inv;
       pen_local += -fminf(sdf_inv, 0.0f);
@@ -255,34 +354,37 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
     if (lane == 0) s_warp_sum[warp] = pen_local;
     __syncthreads();
 
-    // ---- (3) per-body first-index min over the body's points (contact term) ----
-    float contact_f = 0.0f;
-    if (warp == 0) {
-      float cterm = 0.0f;
-      if (lane < J) {
-        const int s0 = __ldg(p.pts.point_start + lane), s1 = __ldg(p.pts.point_start + lane + 1);
-        float best = INFINITY;
-        int win = s0;
-        for (int k = s0; k < s1; ++k) {
-          const float v = s_sol[k];
-          if (v < best) { best = v; win = k; }
-        }
-        const float c = __ldg(p.contacts + q * J + lane);
-        cterm = best * c;                              // closest_distances * contacts[..., b]
-        s_winner[lane] = win;
-        s_contact_w[lane] = p.w_contact * c;
+    // ---- (3) per-body first-index min over the body's points (contact term): warp w takes bodies w, w+nw ----
+    for (int j = warp; j < J; j += LOSS_THREADS / 32) {
+      const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
+      float best = INFINITY;
+      int win = 0x7fffffff;
+      for (int k = s0 + lane; k < s1; k += 32) {
+        const float v = s_sol[k];
+        if (v < best) { best = v; win = k; }        // k increases: first index within the lane's stride
       }
-      // sum over bodies in index order (as the reference's python loop accumulates)
-      for (int j = 0; j < J; ++j) contact_f += __shfl_sync(PARC_FULL_MASK, cterm, j);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(PARC_FULL_MASK, best, o);
+        const int ow = __shfl_xor_sync(PARC_FULL_MASK, win, o);
+        if (ov < best || (ov == best && ow < win)) { best = ov; win = ow; }
+      }
       if (lane == 0) {
-        float pen_f = 0.0f;
-        for (int w = 0; w < LOSS_THREADS / 32; ++w) pen_f += s_warp_sum[w];
-        if (p.pen_out) p.pen_out[q] = pen_f;
-        if (p.contact_out) p.contact_out[q] = contact_f;
+        const float c = s_contact[j];
+        s_cterm[j] = best * c;                       // closest_distances * contacts[..., b]
+        s_winner[j] = win;
+        s_contact_w[j] = p.w_contact * c;
       }
     }
-    if (!p.want_grad) { __syncthreads(); continue; }
     __syncthreads();
+    if (warp == 0 && lane == 0) {
+      float pen_f = 0.0f, contact_f = 0.0f;
+      for (int w = 0; w < LOSS_THREADS / 32; ++w) pen_f += s_warp_sum[w];
+      for (int j = 0; j < J; ++j) contact_f += s_cterm[j];   // body order, as the reference's python loop
+      if (p.pen_out) p.pen_out[q] = pen_f;
+      if (p.contact_out) p.contact_out[q] = contact_f;
+    }
+    if (!p.want_grad) { __syncthreads(); continue; }
 
     // ---- (4) chain d/d world-point through wp = rotate(body_rot, lp) + body_pos ----
     for (int k = threadIdx.x; k < S; k += blockDim.x) {
@@ -302,17 +404,29 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
     }
     __syncthreads();
 
-    // ---- (5) per-body sums, then the FK VJP, by warp 0 ----
+    // ---- (5) per-body gradient sums (fixed-shape tree, deterministic), all warps; then the FK VJP by warp 0 ----
+    for (int j = warp; j < J; j += LOSS_THREADS / 32) {
+      const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
+      float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k = s0 + lane; k < s1; k += 32) {
+        const float* g7 = s_g + (size_t)k * 7;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) acc[c] += g7[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(PARC_FULL_MASK, acc[c], o);
+      }
+      if (lane < 7) s_gbody[j][lane] = acc[lane];
+    }
+    __syncthreads();
     if (warp == 0) {
       float3 gp = make_float3(0.f, 0.f, 0.f);
       float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
       if (lane < J) {
-        const int s0 = __ldg(p.pts.point_start + lane), s1 = __ldg(p.pts.point_start + lane + 1);
-        for (int k = s0; k < s1; ++k) {
-          const float* g7 = s_g + (size_t)k * 7;
-          gp.x += g7[0]; gp.y += g7[1]; gp.z += g7[2];
-          gr.x += g7[3]; gr.y += g7[4]; gr.z += g7[5]; gr.w += g7[6];
-        }
+        gp = make_float3(s_gbody[lane][0], s_gbody[lane][1], s_gbody[lane][2]);
+        gr = make_float4(s_gbody[lane][3], s_gbody[lane][4], s_gbody[lane][5], s_gbody[lane][6]);
       }
       float4 gj;
       fk_warp_vjp(lb, J, lane, prot, local, gp, gr, gj);

@@ -31,7 +31,8 @@ __device__ __forceinline__ void frame_to_lane_pose(const ParcCharModel& m, const
   }
 }
 
-// ---- frames -> FK, one warp per frame (config 5's "FK on every frame") -----------------------------
+// ---- frames -> FK (config 5's "FK on every frame"): G lanes per frame, two frames per warp when J <= 16 ----
+template <int G>
 __global__ void __launch_bounds__(PARC_CTA_THREADS)
 frames_fk_kernel(const float* __restrict__ frames, int64_t n, int frame_stride,
                  const __grid_constant__ ParcCharModel model_param, float* __restrict__ root_rot_out,
@@ -39,24 +40,30 @@ frames_fk_kernel(const float* __restrict__ frames, int64_t n, int frame_stride,
   __shared__ ParcCharModel sm;
   stage_model(&sm, model_param);
   __syncthreads();
+  constexpr int GROUPS = 32 / G;
   const int lane = threadIdx.x & 31;
+  const int l = lane & (G - 1), grp = lane / G;
   const int J = sm.num_bodies;
-  const LaneBody lb = load_lane_body(sm, lane, 0);
-  const int64_t warp0 = (int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * PARC_WARPS_PER_CTA;
-  for (int64_t q = warp0; q < n; q += nwarps) {
+  const LaneBody lb = load_lane_body(sm, l, 0);
+  const int64_t first = ((int64_t)blockIdx.x * PARC_WARPS_PER_CTA + (threadIdx.x >> 5)) * GROUPS;
+  const int64_t stride = (int64_t)gridDim.x * PARC_WARPS_PER_CTA * GROUPS;
+  for (int64_t base = first; base < n; base += stride) {
+    const bool active = base + grp < n;
+    const int64_t q = active ? base + grp : n - 1;
     float3 pos;
     float4 rot;
-    frame_to_lane_pose(sm, frames + q * frame_stride, lane, pos, rot);
-    if (lane == 0) {
-      if (root_rot_out) reinterpret_cast<float4*>(root_rot_out)[q] = rot;
-    } else if (lane < J) {
-      if (joint_rot_out) reinterpret_cast<float4*>(joint_rot_out)[q * (J - 1) + (lane - 1)] = rot;
+    frame_to_lane_pose(sm, frames + q * frame_stride, l, pos, rot);
+    if (active) {
+      if (l == 0) {
+        if (root_rot_out) reinterpret_cast<float4*>(root_rot_out)[q] = rot;
+      } else if (l < J) {
+        if (joint_rot_out) reinterpret_cast<float4*>(joint_rot_out)[q * (J - 1) + (l - 1)] = rot;
+      }
     }
-    fk_warp(lb, sm.max_depth, pos, rot);
-    if (lane < J) {
-      if (body_pos) { float* o = body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
-      if (body_rot) reinterpret_cast<float4*>(body_rot)[q * J + lane] = rot;
+    fk_group(lb, sm.max_depth, G, pos, rot);
+    if (active && l < J) {
+      if (body_pos) { float* o = body_pos + (q * J + l) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
+      if (body_rot) reinterpret_cast<float4*>(body_rot)[q * J + l] = rot;
     }
   }
 }
@@ -257,8 +264,12 @@ extern "C" int parc_frames_fk(const float* frames, int64_t n, int32_t frame_stri
   if (n == 0) return PARC_OK;
   if (!frames) return PARC_E_NULL;
   if (!aligned16(root_rot_out) || !aligned16(joint_rot_out) || !aligned16(body_rot)) return PARC_E_ALIGN;
-  frames_fk_kernel<<<warp_grid(n), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(
-      frames, n, frame_stride, *model, root_rot_out, joint_rot_out, body_pos, body_rot);
+  if (model->num_bodies <= 16)
+    frames_fk_kernel<16><<<warp_grid((n + 1) / 2), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        frames, n, frame_stride, *model, root_rot_out, joint_rot_out, body_pos, body_rot);
+  else
+    frames_fk_kernel<32><<<warp_grid(n), PARC_CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        frames, n, frame_stride, *model, root_rot_out, joint_rot_out, body_pos, body_rot);
   return check_launch();
 }
 

@@ -18,7 +18,9 @@ struct QueryParams {
   const int64_t* ids;
   const float* times;       // calc_motion_frame
   const int64_t* frame_idx; // get_motion_frame
-  int64_t n;
+  const float* offsets;     // [num_steps] time offsets (tracker step form) or nullptr
+  int num_steps;            // queries per (id, time) entry; query q = entry * num_steps + step
+  int64_t n;                // total queries = entries * num_steps
   ParcRowLayout lay;
   ParcFrameOut out;
   ParcFkOut fk;
@@ -118,8 +120,9 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
   int64_t f_pre = 0;
   {
     const int64_t q0 = first + grp < p.n ? first + grp : p.n - 1;
-    id_pre = __ldg(p.ids + q0);
-    if (BLEND) t_pre = __ldg(p.times + q0); else f_pre = __ldg(p.frame_idx + q0);
+    const int64_t e0 = p.num_steps > 1 ? q0 / p.num_steps : q0;
+    id_pre = __ldg(p.ids + e0);
+    if (BLEND) t_pre = __ldg(p.times + e0); else f_pre = __ldg(p.frame_idx + e0);
   }
   if (tmpl_in_smem) {
     const float2* __restrict__ g = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
@@ -142,13 +145,18 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     const bool active = qq < p.n;
     const int64_t q = active ? qq : p.n - 1;
     // ---- clip metadata + frame indices (uniform within the group) ----
+    // entry (env) and step of this query: q = entry * num_steps + step
+    const int64_t entry = p.num_steps > 1 ? q / p.num_steps : q;
+    const int step = (int)(q - entry * p.num_steps);
     int64_t id = id_pre;
     float t_q = t_pre;
     int64_t f_q = f_pre;
     if (base != first) {
-      id = __ldg(p.ids + q);
-      if (BLEND) t_q = __ldg(p.times + q); else f_q = __ldg(p.frame_idx + q);
+      id = __ldg(p.ids + entry);
+      if (BLEND) t_q = __ldg(p.times + entry); else f_q = __ldg(p.frame_idx + entry);
     }
+    // motion_times + timestep * tar_obs_steps (envs/ig_parkour/mgdm_dm_util.py:289-291): one fp32 add
+    if (BLEND && p.offsets) t_q = add_rn(t_q, __ldg(p.offsets + step));
     if (id < 0 || id >= p.tb.num_clips) id = 0;   // reference would raise an index error
     const int4* cmp = reinterpret_cast<const int4*>(p.tb.clips + id);
     const int4 c0 = __ldg(cmp);
@@ -258,8 +266,11 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     ObsCtx oc;
     float z[INFLIGHT];
     const float* __restrict__ hfp = p.hf.hf;
-    if (p.want_obs) {
-      const float4 rr = make_float4(shfl_g(R.x, 1, G), shfl_g(R.y, 1, G), shfl_g(R.z, 1, G), shfl_g(R.w, 1, G));
+    // observations belong to step 0 of an entry (the current frame); shuffles are done by the whole warp
+    const bool grp_obs = p.want_obs && step == 0;
+    float4 rr = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (p.want_obs) rr = make_float4(shfl_g(R.x, 1, G), shfl_g(R.y, 1, G), shfl_g(R.z, 1, G), shfl_g(R.w, 1, G));
+    if (grp_obs) {
       // cos / sin of heading = atan2(d.y, d.x) taken directly from the rotated x axis d (the reference goes
       // through atan2 -> cos/sin; both are within ~2 ulp of the true value, far below the fp32 granularity
       // of the world coordinate they are added to).
@@ -317,8 +328,8 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     }
 
     // ---- heightmap observation, part 2: consume the gathers; then any further points ----
-    if (p.want_obs && active) {
-      float* __restrict__ o = p.obs_out + q * P + l;          // lane's first output; u-th is o[G * u]
+    if (grp_obs && active) {
+      float* __restrict__ o = p.obs_out + entry * P + l;      // lane's first output; u-th is o[G * u]
       const float root_z = rp.z, lo = p.obs.min_h, hi = p.obs.max_h;
 #pragma unroll
       for (int u = 0; u < INFLIGHT; ++u) {
@@ -488,12 +499,15 @@ extern "C" int parc_pack_frames(const float* root_pos, const float* root_rot, co
 }
 
 static int launch_query(bool blend, const ParcMotionTables* tables, const int64_t* ids, const float* times,
-                        const int64_t* frame_idx, int64_t n, const ParcCharModel* model,
+                        const int64_t* frame_idx, const float* offsets, int num_steps, int64_t n_entries,
+                        const ParcCharModel* model,
                         const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                         const ParcObsSpec* obs, float* obs_out, void* stream) {
   if (!tables || !model) return PARC_E_NULL;
   if (!tables->rows || !tables->clips) return PARC_E_NULL;
-  if (n < 0 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
+  if (n_entries < 0 || num_steps < 1 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
+  if (num_steps > 1 && !offsets) return PARC_E_NULL;
+  const int64_t n = n_entries * num_steps;
   if (n > 0 && (!ids || (blend ? !times : !frame_idx))) return PARC_E_NULL;
   QueryParams p;
   int rc = parc_row_layout(model, &p.lay);
@@ -502,6 +516,7 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   if (!aligned16(tables->rows) || !aligned16(tables->clips)) return PARC_E_ALIGN;
   p.tb = *tables;
   p.ids = ids; p.times = times; p.frame_idx = frame_idx; p.n = n;
+  p.offsets = offsets; p.num_steps = num_steps;
   ParcFrameOut none = {};
   p.out = frame ? *frame : none;
   if (!aligned16(p.out.root_rot) || !aligned16(p.out.joint_rot)) return PARC_E_ALIGN;
@@ -557,15 +572,24 @@ extern "C" int parc_motion_query(const ParcMotionTables* tables, const int64_t* 
                                  const float* motion_times, int64_t n, const ParcCharModel* model,
                                  const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                                  const ParcObsSpec* obs, float* obs_out, void* stream) {
-  return launch_query(true, tables, motion_ids, motion_times, nullptr, n, model, frame, fk, hf, obs, obs_out,
-                      stream);
+  return launch_query(true, tables, motion_ids, motion_times, nullptr, nullptr, 1, n, model, frame, fk, hf, obs,
+                      obs_out, stream);
+}
+
+extern "C" int parc_motion_query_steps(const ParcMotionTables* tables, const int64_t* motion_ids,
+                                       const float* motion_times, int64_t n, const float* time_offsets,
+                                       int32_t num_steps, const ParcCharModel* model, const ParcFrameOut* frame,
+                                       const ParcFkOut* fk, const ParcHeightfield* hf, const ParcObsSpec* obs,
+                                       float* obs_out, void* stream) {
+  return launch_query(true, tables, motion_ids, motion_times, nullptr, time_offsets, num_steps, n, model, frame, fk,
+                      hf, obs, obs_out, stream);
 }
 
 extern "C" int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
                                      const int64_t* frame_idxs, int64_t n, const ParcCharModel* model,
                                      const ParcFrameOut* frame, const ParcFkOut* fk, void* stream) {
-  return launch_query(false, tables, motion_ids, nullptr, frame_idxs, n, model, frame, fk, nullptr, nullptr,
-                      nullptr, stream);
+  return launch_query(false, tables, motion_ids, nullptr, frame_idxs, nullptr, 1, n, model, frame, fk, nullptr,
+                      nullptr, nullptr, stream);
 }
 
 extern "C" int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint64_t* mismatches_dev,

@@ -217,12 +217,14 @@ class MotionQueryPlan:
     def __init__(self, tables: PackedTables, model: ParcCharModel, ids: torch.Tensor, times: torch.Tensor, *,
                  want_contacts: bool = True, want_fk: bool = True, hf: Optional[HeightfieldDesc] = None,
                  obs_tmpl: Optional[torch.Tensor] = None, obs_relative: bool = True, obs_min_h: float = -3.0,
-                 obs_max_h: float = 3.0, out: Optional[dict] = None):
-        require_cuda(ids, times, tables.rows)
+                 obs_max_h: float = 3.0, out: Optional[dict] = None, time_offsets: Optional[torch.Tensor] = None):
+        require_cuda(ids, times, tables.rows, time_offsets)
         assert ids.dtype == torch.int64 and times.dtype == torch.float32 and ids.is_contiguous() and times.is_contiguous()
-        self._keep = (tables, model, ids, times, hf, obs_tmpl)
+        self._keep = (tables, model, ids, times, hf, obs_tmpl, time_offsets)
         self.device = ids.device
-        N, J, D = int(ids.shape[0]), model.num_bodies, model.dof_size
+        E = int(ids.shape[0])                    # entries (environments)
+        S = 1 if time_offsets is None else int(time_offsets.shape[0])
+        N, J, D = E * S, model.num_bodies, model.dof_size
         self.n = N
         self.out = {} if out is None else out
 
@@ -254,12 +256,18 @@ class MotionQueryPlan:
             tm = f32c(obs_tmpl)
             self._keep += (tm,)
             self._hf, self._obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
-            self._obs_ptr = buf("obs", (N, int(tm.shape[0]))).data_ptr()
+            self._obs_ptr = buf("obs", (E, int(tm.shape[0]))).data_ptr()
         lib = _lib.load()
-        self._fn = lib.parc_motion_query
-        self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), N, C.byref(model), C.byref(self._fo),
-                      C.byref(self._fk) if want_fk else None, C.byref(self._hf) if self._hf is not None else None,
-                      C.byref(self._obs) if self._obs is not None else None, self._obs_ptr)
+        tail = (C.byref(model), C.byref(self._fo), C.byref(self._fk) if want_fk else None,
+                C.byref(self._hf) if self._hf is not None else None,
+                C.byref(self._obs) if self._obs is not None else None, self._obs_ptr)
+        if time_offsets is None:
+            self._fn = lib.parc_motion_query
+            self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E) + tail
+        else:
+            assert time_offsets.dtype == torch.float32 and time_offsets.is_contiguous()
+            self._fn = lib.parc_motion_query_steps
+            self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E, time_offsets.data_ptr(), S) + tail
 
     def launch(self, stream: Optional[int] = None) -> dict:
         """Enqueue on `stream` (a raw cudaStream_t; default = torch's current stream of the plan's

@@ -13,6 +13,7 @@ $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --impor
 CMD2="python bench.py --steps 6 --warmup 3 --envs 65536 --no-cpu-baseline --no-soak"
 $CMD2 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:motion_query -s 4 -c 2 -f -o gpurun_out/prof_${TAG}_query65k $CMD2 > gpurun_out/ncu_full65k.log 2>&1
 python scripts/bench_loss.py > gpurun_out/bench_loss.log 2>&1; tail -1 gpurun_out/bench_loss.log
+python scripts/bench_sweep.py > gpurun_out/bench_sweep.log 2>&1; tail -1 gpurun_out/bench_sweep.log
 tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log
 python - <<'PY'
 import json
@@ -20,9 +21,10 @@ for f in ("bench.log", "bench_65k.log"):
     try:
         j = json.loads(open("gpurun_out/" + f).read().strip().splitlines()[-1])
         r = j["roofline"]
-        print(f, "value %.3e  ms/step %.4f  frac %.3f  achieved %.0f GB/s  e2e %.3e  cpu %s" % (
+        ts = j.get("tracker_step") or {}
+        print(f, "value %.3e  ms/step %.4f  frac %.3f  achieved %.0f GB/s  e2e %.3e  cpu %s | step: %.3e bf/s %.4f ms frac %.3f" % (
             j["value"], j["ms_per_step"], r["frac"], r["achieved"], j["e2e"]["value"],
-            (j.get("cpu_baseline") or {}).get("value")))
+            (j.get("cpu_baseline") or {}).get("value"), ts.get("value", 0), ts.get("ms_per_step", 0), ts.get("roofline_frac", 0)))
     except Exception as e:
         print(f, "unreadable", e)
 PY

@@ -133,6 +133,33 @@ def test_query_vs_oracle_random_and_edges(golden_lib, O, oracle_tables, oracle_m
     assert_close(r["body_rot"], rbr, what="query.body_rot")
 
 
+def test_tracker_step_form_matches_separate_queries(golden_lib, O, oracle_tables):
+    """parc_motion_query_steps: N envs x 7 time offsets (current + tar_obs_steps look-aheads) in one launch ==
+    the reference's tiled ids / `motion_times + timestep * tar_obs_steps` (mgdm_dm_util.py:279-302)."""
+    g = golden("obs_golden.npz")
+    t = _civ_terrain()
+    gen = torch.Generator().manual_seed(31)
+    n = 1001                                                        # odd: exercises the half-empty last warp
+    ids = torch.randint(0, 3, (n,), generator=gen)
+    times = torch.rand(n, generator=gen) * oracle_tables.lengths[ids]
+    timestep = 1.0 / 30.0
+    steps = torch.tensor([0, 1, 2, 3, 10, 20, 30], dtype=torch.float32)
+    offsets = timestep * steps                                       # fp32, as the reference computes it
+    plan = golden_lib.make_query_plan(ids.cuda(), times.cuda(), hf_desc=t.hf_desc(), obs_tmpl=dev(g["tmpl"]),
+                                      time_offsets=offsets.cuda())
+    out = plan.launch()
+    ids_t = torch.broadcast_to(ids.unsqueeze(-1), (n, 7)).flatten()
+    times_t = (times.unsqueeze(-1) + offsets).flatten()
+    sep = golden_lib.calc_motion_frame_fk_obs(ids_t.cuda(), times_t.cuda(), hf_desc=t.hf_desc(), obs_tmpl=dev(g["tmpl"]))
+    for k in FRAME_KEYS + ("body_pos", "body_rot"):
+        assert torch.equal(out[k], sep[k]), k
+    assert out["obs"].shape == (n, 441)
+    assert torch.equal(out["obs"], sep["obs"].view(n, 7, 441)[:, 0])
+    ref = O.calc_motion_frame(oracle_tables, ids_t, times_t)
+    assert torch.equal(out["root_pos"].cpu(), ref[0]) and torch.equal(out["contacts"].cpu(), ref[6])
+    assert_close(out["joint_rot"], ref[4], what="steps joint_rot")
+
+
 def test_slerp_branches_bit_exact_decisions(golden_lib, O, oracle_tables):
     """FIXED joints (identical key frames: |cos| >= 1 -> q0) and slow joints (sin < 1e-3 -> midpoint)
     take the same branch as the reference: these outputs involve IEEE ops only, so they are exact."""
