@@ -97,6 +97,7 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // MINB = resident CTAs per SM the register allocation must allow: 8 (<= 128 registers, whole template
 // sweep in flight) for launches that fit one wave and are latency-bound; 12 (<= 85 registers, half a
 // sweep in flight) for large launches, which are issue-bound and want more warps per scheduler.
+// (A middle point, whole sweep at <= 102 registers, spills and measured slower: profiles/README.md.)
 template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant__ ParcCharModel model_param) {
@@ -331,11 +332,32 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     if (grp_obs && active) {
       float* __restrict__ o = p.obs_out + entry * P + l;      // lane's first output; u-th is o[G * u]
       const float root_z = rp.z, lo = p.obs.min_h, hi = p.obs.max_h;
+      if (P >= G * (INFLIGHT - 1) + G) {
+        // every lane is in range for the whole sweep (uniform branch): no per-element bounds predicate
 #pragma unroll
-      for (int u = 0; u < INFLIGHT; ++u) {
-        float v = z[u];
+        for (int u = 0; u < INFLIGHT; ++u) {
+          float v = z[u];
+          if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+          o[G * u] = v;
+        }
+      } else if (P >= G * (INFLIGHT - 1)) {
+        // only the last iteration is partial (the 441-point ray fan: 27 full iterations of 16 + 9)
+#pragma unroll
+        for (int u = 0; u < INFLIGHT - 1; ++u) {
+          float v = z[u];
+          if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+          o[G * u] = v;
+        }
+        float v = z[INFLIGHT - 1];
         if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
-        if (l + G * u < P) o[G * u] = v;
+        if (l + G * (INFLIGHT - 1) < P) o[G * (INFLIGHT - 1)] = v;
+      } else {
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+          float v = z[u];
+          if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+          if (l + G * u < P) o[G * u] = v;
+        }
       }
       for (int k0 = G * INFLIGHT; k0 < P; k0 += G * INFLIGHT) {
         if (tmpl_in_smem) {               // padded to whole sweeps: no bounds check on the read side
