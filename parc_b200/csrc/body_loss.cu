@@ -233,8 +233,18 @@ points_hf_sdf_kernel(const float* __restrict__ points, int64_t n_points, const _
 
 // ------------------------------------------------------------------------------------------------
 // a14/a15 fused: FK -> body points -> SDF -> pen / contact (+ gradients wrt the pose)
+//
+// ONE WARP PER FRAME, no block-level barrier inside the frame loop:
+//   FK            lane = body (fk_warp_keep), transforms parked in the warp's shared-memory slab
+//   sweep         lane = surface point (10 rounds for 304 points): world point, exact pruned SDF scan of the
+//                 CTA's terrain tile, d/d(world point) of both terms -> slab
+//   contact min   lane = body: first-index min over the body's points (sequential, <= 44 reads)
+//   chain rule    lane = point: add the winner's contact gradient, VJP through rotate(body_rot, local) -> slab
+//   body sums     lane = body: fixed-order sums of its points' 7 floats; then the FK VJP in-warp
+// The warps of a CTA share one sample's terrain tile (read-only after staging).
 // ------------------------------------------------------------------------------------------------
-#define LOSS_THREADS 320
+#define LOSS_WARPS 4
+#define LOSS_THREADS (LOSS_WARPS * 32)
 
 struct BodyLossParams {
   const float *root_pos, *root_rot, *joint_rot, *contacts;
@@ -248,30 +258,25 @@ struct BodyLossParams {
   int want_grad;
 };
 
-__global__ void __launch_bounds__(LOSS_THREADS, 3)   // <= 64 registers: 3 CTAs (30 warps) per SM
+__global__ void __launch_bounds__(LOSS_THREADS)
 body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
   __shared__ ParcCharModel sm;
-  __shared__ float s_bpos[PARC_MAX_BODIES][3];
-  __shared__ float s_brot[PARC_MAX_BODIES][4];
-  __shared__ float s_warp_sum[LOSS_THREADS / 32];
-  __shared__ int s_winner[PARC_MAX_BODIES];
-  __shared__ float s_contact_w[PARC_MAX_BODIES];   // w_contact * contacts[f,b] if the winner's clamp passes
-  __shared__ float s_cterm[PARC_MAX_BODIES];
-  __shared__ float s_contact[PARC_MAX_BODIES];     // contacts[b,f,:] of the current frame
-  __shared__ float s_gbody[PARC_MAX_BODIES][7];
+  __shared__ float s_minmax[2];
 
   const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
   const int S = p.pts.num_points;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* s_hf = smem;
   float* s_cx = s_hf + X * Y;
   float* s_cy = s_cx + X;
-  float* s_sol = s_cy + Y;                         // [S] clamp(sdf_solid, min=0)
-  float* s_g = s_sol + S;                          // [S][7]: d/d body_pos (3), d/d body_rot (4)
-  int* s_body = reinterpret_cast<int*>(s_g + (size_t)S * 7);   // [S] body of point
+  int* s_body = reinterpret_cast<int*>(s_cy + Y);                    // [S] body of point
+  float* s_lp = reinterpret_cast<float*>(s_body + S);                // [S][3] local points
+  float* slab = s_lp + (size_t)S * 3 + (size_t)warp * ((size_t)S * 7 + PARC_MAX_BODIES * 9);
+  float* s_bt = slab;                                                // [J][9] pos(3) rot(4) contact(1) winner(1)
+  float* s_pt = slab + PARC_MAX_BODIES * 9;                          // [S][7]
 
   const int64_t b = blockIdx.y;
-  __shared__ float s_minmax[2];
   stage_model(&sm, model_param);
   stage_terrain(p.terrain, b, s_hf, s_cx, s_cy, s_minmax);
   __syncthreads();
@@ -281,49 +286,51 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
     const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
     for (int k = s0; k < s1; ++k) s_body[k] = j;
   }
+  for (int i = threadIdx.x; i < S * 3; i += blockDim.x) s_lp[i] = __ldg(p.pts.points + i);
   const float base = sample_base_z(p.terrain, b);
   const float hx = p.terrain.half_dx, hy = p.terrain.half_dy;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const LaneBody lb = load_lane_body(sm, lane, 0);
   const int max_depth = sm.max_depth;
+  const int my_s0 = lane < J ? __ldg(p.pts.point_start + lane) : 0;
+  const int my_s1 = lane < J ? __ldg(p.pts.point_start + lane + 1) : 0;
   __syncthreads();
 
   const int64_t f_begin = (int64_t)blockIdx.x * p.frames_per_cta;
   const int64_t f_end = min(f_begin + (int64_t)p.frames_per_cta, p.frames);
-  for (int64_t f = f_begin; f < f_end; ++f) {
+  for (int64_t f = f_begin + warp; f < f_end; f += LOSS_WARPS) {
     const int64_t q = b * p.frames + f;
-    // ---- (1) FK by warp 0 ----
-    float4 prot = make_float4(0.f, 0.f, 0.f, 1.f), local = prot, rot = prot;
+    // ---- FK, lane = body ----
+    float4 prot, local, rot = make_float4(0.f, 0.f, 0.f, 1.f);
     float3 pos = make_float3(0.f, 0.f, 0.f);
-    if (warp == 0) {
-      if (lane == 0) {
-        pos = make_float3(__ldg(p.root_pos + q * 3), __ldg(p.root_pos + q * 3 + 1), __ldg(p.root_pos + q * 3 + 2));
-        rot = __ldg(reinterpret_cast<const float4*>(p.root_rot) + q);
-      } else if (lane < J) {
-        rot = __ldg(reinterpret_cast<const float4*>(p.joint_rot) + q * (J - 1) + (lane - 1));
-      }
-      fk_warp_keep(lb, max_depth, pos, rot, prot, local);
-      if (lane < J) {
-        s_bpos[lane][0] = pos.x; s_bpos[lane][1] = pos.y; s_bpos[lane][2] = pos.z;
-        s_brot[lane][0] = rot.x; s_brot[lane][1] = rot.y; s_brot[lane][2] = rot.z; s_brot[lane][3] = rot.w;
-        s_contact[lane] = __ldg(p.contacts + q * J + lane);
-      }
+    if (lane == 0) {
+      pos = make_float3(__ldg(p.root_pos + q * 3), __ldg(p.root_pos + q * 3 + 1), __ldg(p.root_pos + q * 3 + 2));
+      rot = __ldg(reinterpret_cast<const float4*>(p.root_rot) + q);
+    } else if (lane < J) {
+      rot = __ldg(reinterpret_cast<const float4*>(p.joint_rot) + q * (J - 1) + (lane - 1));
     }
-    __syncthreads();
+    fk_warp_keep(lb, max_depth, pos, rot, prot, local);
+    float my_contact = 0.0f;
+    if (lane < J) {
+      my_contact = __ldg(p.contacts + q * J + lane);
+      float* t = s_bt + lane * 9;
+      t[0] = pos.x; t[1] = pos.y; t[2] = pos.z; t[3] = rot.x; t[4] = rot.y; t[5] = rot.z; t[6] = rot.w;
+      t[7] = my_contact;
+    }
+    __syncwarp();
 
-    // ---- (2) every surface point against every cell ----
+    // ---- sweep, lane = surface point ----
     float pen_local = 0.0f;
-    for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    for (int k = lane; k < S; k += 32) {
       const int bj = s_body[k];
-      const float3 lp = make_float3(__ldg(p.pts.points + k * 3), __ldg(p.pts.points + k * 3 + 1),
-                                    __ldg(p.pts.points + k * 3 + 2));
-      const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
+      const float* t = s_bt + bj * 9;
+      const float3 lp = make_float3(s_lp[k * 3], s_lp[k * 3 + 1], s_lp[k * 3 + 2]);
+      const float4 br = make_float4(t[3], t[4], t[5], t[6]);
       const float3 r = quat_rotate(br, lp);
-      const float3 wp = make_float3(r.x + s_bpos[bj][0], r.y + s_bpos[bj][1], r.z + s_bpos[bj][2]);
+      const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
       // A body whose contact weight is exactly 0 contributes exactly 0 to the contact term and to its
       // gradient (closest * 0), so its solid-column scan is skipped.
       SdfBest best;
-      if (s_contact[bj] != 0.0f) {
+      if (t[7] != 0.0f) {
         best = scan_cells<true, true>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp);
       } else {
         best = scan_cells<true, false>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp);
@@ -332,112 +339,81 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
       // penetration: sdf = -best.inv ; neg = min(sdf, 0) ; pen += -neg
       const float sdf_inv = -1.0f * best.inv;
       pen_local += -fminf(sdf_inv, 0.0f);
-      s_sol[k] = fmaxf(best.sol, 0.0f);
+      float* g7 = s_pt + (size_t)k * 7;
+      g7[6] = fmaxf(best.sol, 0.0f);                 // clamp(sdf_solid, min=0)
       if (p.want_grad) {
-        // d pen / d wp = [sdf_inv <= 0] * grad sdBox(air cell)
+        // d pen / d wp = [sdf_inv <= 0] * grad sdBox(air cell), already weighted
         float3 gp = make_float3(0.f, 0.f, 0.f);
         if (sdf_inv <= 0.0f) {
           const float3 g = cell_grad(s_hf, s_cx, s_cy, Y, hx, hy, base, true, best.arg_inv, wp);
           gp = make_float3(p.w_pen * g.x, p.w_pen * g.y, p.w_pen * g.z);
         }
-        // stash the solid-cell gradient (used only if this point wins its body's min)
+        // solid-cell gradient, used only if this point wins its body's min and the clamp passes
         float3 gs = make_float3(0.f, 0.f, 0.f);
-        if (best.sol >= 0.0f) gs = cell_grad(s_hf, s_cx, s_cy, Y, hx, hy, base, false, best.arg_sol, wp);
-        float* g7 = s_g + (size_t)k * 7;
+        if (best.sol >= 0.0f && t[7] != 0.0f) gs = cell_grad(s_hf, s_cx, s_cy, Y, hx, hy, base, false, best.arg_sol, wp);
         g7[0] = gp.x; g7[1] = gp.y; g7[2] = gp.z;
         g7[3] = gs.x; g7[4] = gs.y; g7[5] = gs.z;
       }
     }
-    // block sum of the penetration terms (fixed tree -> deterministic)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pen_local += __shfl_xor_sync(PARC_FULL_MASK, pen_local, o);
-    if (lane == 0) s_warp_sum[warp] = pen_local;
-    __syncthreads();
+    __syncwarp();
 
-    // ---- (3) per-body first-index min over the body's points (contact term): warp w takes bodies w, w+nw ----
-    for (int j = warp; j < J; j += LOSS_THREADS / 32) {
-      const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
-      float best = INFINITY;
-      int win = 0x7fffffff;
-      for (int k = s0 + lane; k < s1; k += 32) {
-        const float v = s_sol[k];
-        if (v < best) { best = v; win = k; }        // k increases: first index within the lane's stride
+    // ---- contact term, lane = body: first-index min over the body's points ----
+    float cterm = 0.0f;
+    int win = -1;
+    if (lane < J) {
+      float bestv = INFINITY;
+      for (int k = my_s0; k < my_s1; ++k) {
+        const float v = s_pt[(size_t)k * 7 + 6];
+        if (v < bestv) { bestv = v; win = k; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(PARC_FULL_MASK, best, o);
-        const int ow = __shfl_xor_sync(PARC_FULL_MASK, win, o);
-        if (ov < best || (ov == best && ow < win)) { best = ov; win = ow; }
-      }
-      if (lane == 0) {
-        const float c = s_contact[j];
-        s_cterm[j] = best * c;                       // closest_distances * contacts[..., b]
-        s_winner[j] = win;
-        s_contact_w[j] = p.w_contact * c;
-      }
+      cterm = bestv * my_contact;                    // closest_distances * contacts[..., b]
+      s_bt[lane * 9 + 8] = __int_as_float(win);
     }
-    __syncthreads();
-    if (warp == 0 && lane == 0) {
-      float pen_f = 0.0f, contact_f = 0.0f;
-      for (int w = 0; w < LOSS_THREADS / 32; ++w) pen_f += s_warp_sum[w];
-      for (int j = 0; j < J; ++j) contact_f += s_cterm[j];   // body order, as the reference's python loop
-      if (p.pen_out) p.pen_out[q] = pen_f;
+    float contact_f = 0.0f;
+    for (int j = 0; j < J; ++j) contact_f += __shfl_sync(PARC_FULL_MASK, cterm, j);   // body order, as the reference
+    if (lane == 0) {
+      if (p.pen_out) p.pen_out[q] = pen_local;
       if (p.contact_out) p.contact_out[q] = contact_f;
     }
-    if (!p.want_grad) { __syncthreads(); continue; }
+    __syncwarp();
+    if (!p.want_grad) continue;
 
-    // ---- (4) chain d/d world-point through wp = rotate(body_rot, lp) + body_pos ----
-    for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    // ---- chain rule, lane = point: add the winner's contact gradient, VJP through the body transform ----
+    for (int k = lane; k < S; k += 32) {
       const int bj = s_body[k];
-      float* g7 = s_g + (size_t)k * 7;
+      const float* t = s_bt + bj * 9;
+      float* g7 = s_pt + (size_t)k * 7;
       float3 g = make_float3(g7[0], g7[1], g7[2]);
-      if (s_winner[bj] == k) {
-        const float cw = s_contact_w[bj];
+      if (__float_as_int(t[8]) == k) {               // this point won its body's contact min
+        const float cw = p.w_contact * t[7];
         g.x += cw * g7[3]; g.y += cw * g7[4]; g.z += cw * g7[5];
       }
-      const float3 lp = make_float3(__ldg(p.pts.points + k * 3), __ldg(p.pts.points + k * 3 + 1),
-                                    __ldg(p.pts.points + k * 3 + 2));
-      const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
-      const float4 gq = quat_rotate_vjp_q(br, lp, g);
+      const float3 lp = make_float3(s_lp[k * 3], s_lp[k * 3 + 1], s_lp[k * 3 + 2]);
+      const float4 gq = quat_rotate_vjp_q(make_float4(t[3], t[4], t[5], t[6]), lp, g);
       g7[0] = g.x; g7[1] = g.y; g7[2] = g.z;
       g7[3] = gq.x; g7[4] = gq.y; g7[5] = gq.z; g7[6] = gq.w;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- (5) per-body gradient sums (fixed-shape tree, deterministic), all warps; then the FK VJP by warp 0 ----
-    for (int j = warp; j < J; j += LOSS_THREADS / 32) {
-      const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
-      float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int k = s0 + lane; k < s1; k += 32) {
-        const float* g7 = s_g + (size_t)k * 7;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) acc[c] += g7[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 7; ++c) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(PARC_FULL_MASK, acc[c], o);
-      }
-      if (lane < 7) s_gbody[j][lane] = acc[lane];
+    // ---- body sums (fixed order), lane = body; then the FK VJP ----
+    float3 gp = make_float3(0.f, 0.f, 0.f);
+    float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = my_s0; k < my_s1; ++k) {
+      const float* g7 = s_pt + (size_t)k * 7;
+      gp.x += g7[0]; gp.y += g7[1]; gp.z += g7[2];
+      gr.x += g7[3]; gr.y += g7[4]; gr.z += g7[5]; gr.w += g7[6];
     }
-    __syncthreads();
-    if (warp == 0) {
-      float3 gp = make_float3(0.f, 0.f, 0.f);
-      float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < J) {
-        gp = make_float3(s_gbody[lane][0], s_gbody[lane][1], s_gbody[lane][2]);
-        gr = make_float4(s_gbody[lane][3], s_gbody[lane][4], s_gbody[lane][5], s_gbody[lane][6]);
-      }
-      float4 gj;
-      fk_warp_vjp(lb, J, lane, prot, local, gp, gr, gj);
-      if (lane == 0) {
-        if (p.g_root_pos) { p.g_root_pos[q * 3] = gp.x; p.g_root_pos[q * 3 + 1] = gp.y; p.g_root_pos[q * 3 + 2] = gp.z; }
-        if (p.g_root_rot) reinterpret_cast<float4*>(p.g_root_rot)[q] = gr;
-      } else if (lane < J) {
-        if (p.g_joint_rot) reinterpret_cast<float4*>(p.g_joint_rot)[q * (J - 1) + (lane - 1)] = gj;
-      }
+    float4 gj;
+    fk_warp_vjp(lb, J, lane, prot, local, gp, gr, gj);
+    if (lane == 0) {
+      if (p.g_root_pos) { p.g_root_pos[q * 3] = gp.x; p.g_root_pos[q * 3 + 1] = gp.y; p.g_root_pos[q * 3 + 2] = gp.z; }
+      if (p.g_root_rot) reinterpret_cast<float4*>(p.g_root_rot)[q] = gr;
+    } else if (lane < J) {
+      if (p.g_joint_rot) reinterpret_cast<float4*>(p.g_joint_rot)[q * (J - 1) + (lane - 1)] = gj;
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -502,17 +478,19 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
   p.g_root_pos = g_root_pos; p.g_root_rot = g_root_rot; p.g_joint_rot = g_joint_rot;
   p.want_grad = (g_root_pos || g_root_rot || g_joint_rot) ? 1 : 0;
 
-  const size_t smem = terrain_smem_bytes(terrain) + (size_t)pts->num_points * (1 + 7 + 1) * sizeof(float);
+  const size_t S = (size_t)pts->num_points;
+  const size_t smem = terrain_smem_bytes(terrain) + (S * (1 + 3) + LOSS_WARPS * (S * 7 + PARC_MAX_BODIES * 9)) * sizeof(float);
   if (smem > 200 * 1024) return PARC_E_SIZE;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(body_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  // enough CTAs to fill the GPU a few times over, but amortise the terrain staging when there is
-  // plenty of work
-  int64_t fpc = (batch * frames) / (148 * 8);
-  if (fpc < 1) fpc = 1;
-  if (fpc > 8) fpc = 8;
+  // one warp per frame, LOSS_WARPS frames in flight per CTA; amortise the terrain staging over several
+  // rounds when there is plenty of work, keep the grid wide when there is not
+  int64_t rounds = (batch * frames) / ((int64_t)148 * 16 * LOSS_WARPS);
+  if (rounds < 1) rounds = 1;
+  if (rounds > 8) rounds = 8;
+  const int64_t fpc = rounds * LOSS_WARPS;
   p.frames_per_cta = (int)fpc;
   dim3 grid((unsigned)((frames + fpc - 1) / fpc), (unsigned)batch);
   body_loss_kernel<<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
