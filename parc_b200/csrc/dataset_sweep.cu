@@ -9,6 +9,7 @@
 // frames laid out [root_pos(3) | root exp-map(3) | joint DoFs(D)].
 #include "parc_common.cuh"
 #include "parc_rotations.cuh"
+#include "parc_sdf.cuh"
 
 namespace parc {
 
@@ -68,8 +69,16 @@ frames_fk_kernel(const float* __restrict__ frames, int64_t n, int frame_stride,
   }
 }
 
-// ---- per-clip labelling ------------------------------------------------------------------------------
-#define LABEL_THREADS 320
+// ---- per-clip labelling: ONE WARP PER FRAME ----------------------------------------------------------
+// The warps of a CTA share one clip's terrain tile; inside the frame loop there is no block barrier.
+//   FK               lane = body; transforms parked in the warp's shared-memory slab
+//   body hf          lane = body: nearest-cell height under the body origin
+//   feet             lane = foot * 8 + corner (up to 4 feet): corner z vs the height of the cell it falls in
+//   hands            lane = hand: exact pruned min over cells of the solid rounded-box SDF at the body origin
+//   masks            lane = surface point (10 rounds for 304 points): cell -> bit in the warp's mask words,
+//                    float atomic-min into the per-cell minimum body height
+#define LABEL_WARPS 8
+#define LABEL_THREADS (LABEL_WARPS * 32)
 
 struct LabelParams {
   const float* frames;          // [B, F, frame_stride]
@@ -100,144 +109,122 @@ __global__ void __launch_bounds__(LABEL_THREADS)
 clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
   __shared__ ParcCharModel sm;
-  __shared__ float s_bpos[PARC_MAX_BODIES][3];
-  __shared__ float s_brot[PARC_MAX_BODIES][4];
-  __shared__ float s_foot_pen[PARC_MAX_KEY_BODIES];
+  __shared__ float s_minmax[2];
 
   const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
   const int S = p.pts.num_points;
+  const bool want_masks = (p.frame_mask || p.min_body_heights) && S > 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* s_hf = smem;
   float* s_cx = s_hf + X * Y;
   float* s_cy = s_cx + X;
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_cy + Y);         // [mask_words]
-  int* s_body = reinterpret_cast<int*>(s_mask + p.mask_words);      // [S]
+  int* s_body = reinterpret_cast<int*>(s_cy + Y);                              // [S]
+  float* s_lp = reinterpret_cast<float*>(s_body + S);                          // [S][3]
+  float* slab = s_lp + (size_t)S * 3 + (size_t)warp * (PARC_MAX_BODIES * 8 + p.mask_words);
+  float* s_bt = slab;                                                          // [J][8] pos(3) rot(4)
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(slab + PARC_MAX_BODIES * 8);  // [mask_words]
 
   const int64_t b = blockIdx.y;
   stage_model(&sm, model_param);
-  // terrain tile + absolute cell centres (node offset + min centre, fp32 add as the reference does)
-  {
-    const float* hf = p.terrain.hf + b * p.terrain.hf_batch_stride;
-    const float* mc = p.terrain.min_center + b * p.terrain.min_center_stride;
-    for (int i = threadIdx.x; i < X * Y; i += blockDim.x) s_hf[i] = __ldg(hf + i);
-    for (int i = threadIdx.x; i < X; i += blockDim.x) s_cx[i] = __ldg(p.terrain.x_nodes + i) + __ldg(mc);
-    for (int i = threadIdx.x; i < Y; i += blockDim.x) s_cy[i] = __ldg(p.terrain.y_nodes + i) + __ldg(mc + 1);
-  }
+  stage_terrain(p.terrain, b, s_hf, s_cx, s_cy, s_minmax);
   __syncthreads();
+  const float hf_min = s_minmax[0], hf_max = s_minmax[1];
   const int J = sm.num_bodies;
-  if (S > 0) {
+  if (want_masks) {
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
       const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
       for (int k = s0; k < s1; ++k) s_body[k] = j;
     }
+    for (int i = threadIdx.x; i < S * 3; i += blockDim.x) s_lp[i] = __ldg(p.pts.points + i);
   }
   const float* mc = p.terrain.min_center + b * p.terrain.min_center_stride;
   const float min_x = __ldg(mc), min_y = __ldg(mc + 1);
   const float dx = p.terrain.half_dx * 2.0f, dy = p.terrain.half_dy * 2.0f;   // exact: halves of fp32 values
-  const float base = p.terrain.base_z ? __ldg(p.terrain.base_z + b * p.terrain.base_z_stride) : p.terrain.base_z_value;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float base = sample_base_z(p.terrain, b);
   const LaneBody lb = load_lane_body(sm, lane, 0);
+  const int max_depth = sm.max_depth;
   __syncthreads();
 
   const int64_t f_begin = (int64_t)blockIdx.x * p.frames_per_cta;
   const int64_t f_end = min(f_begin + (int64_t)p.frames_per_cta, p.frames_per_clip);
-  for (int64_t f = f_begin; f < f_end; ++f) {
+  for (int64_t f = f_begin + warp; f < f_end; f += LABEL_WARPS) {
     const int64_t q = b * p.frames_per_clip + f;
-    for (int i = threadIdx.x; i < p.mask_words; i += blockDim.x) s_mask[i] = 0u;
-    // ---- FK by warp 0 (lane = body) ----
-    if (warp == 0) {
-      float3 pos;
-      float4 rot;
-      frame_to_lane_pose(sm, p.frames + q * p.frame_stride, lane, pos, rot);
-      fk_warp(lb, sm.max_depth, pos, rot);
-      if (lane < J) {
-        s_bpos[lane][0] = pos.x; s_bpos[lane][1] = pos.y; s_bpos[lane][2] = pos.z;
-        s_brot[lane][0] = rot.x; s_brot[lane][1] = rot.y; s_brot[lane][2] = rot.z; s_brot[lane][3] = rot.w;
-        if (p.body_pos) { float* o = p.body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
-        if (p.body_rot) reinterpret_cast<float4*>(p.body_rot)[q * J + lane] = rot;
-        // nearest-cell terrain height under the body origin
-        if (p.body_hf) {
-          const int ix = grid_index_1d(pos.x, min_x, dx, X), iy = grid_index_1d(pos.y, min_y, dy, Y);
-          p.body_hf[q * J + lane] = s_hf[ix * Y + iy];
-        }
-        if (p.contacts) p.contacts[q * J + lane] = 0.0f;
+    // ---- FK (lane = body) ----
+    float3 pos;
+    float4 rot;
+    frame_to_lane_pose(sm, p.frames + q * p.frame_stride, lane, pos, rot);
+    fk_warp(lb, max_depth, pos, rot);
+    if (lane < J) {
+      float* t = s_bt + lane * 8;
+      t[0] = pos.x; t[1] = pos.y; t[2] = pos.z; t[3] = rot.x; t[4] = rot.y; t[5] = rot.z; t[6] = rot.w;
+      if (p.body_pos) { float* o = p.body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
+      if (p.body_rot) reinterpret_cast<float4*>(p.body_rot)[q * J + lane] = rot;
+      if (p.body_hf) {
+        const int ix = grid_index_1d(pos.x, min_x, dx, X), iy = grid_index_1d(pos.y, min_y, dy, Y);
+        p.body_hf[q * J + lane] = s_hf[ix * Y + iy];
       }
     }
-    __syncthreads();
+    if (want_masks && p.frame_mask)
+      for (int i = lane; i < p.mask_words; i += 32) s_mask[i] = 0u;
+    __syncwarp();
 
-    // ---- every surface point: cell it falls in -> per-frame mask bit, per-cell min body height ----
-    if ((p.frame_mask || p.min_body_heights) && S > 0) {
-      for (int k = threadIdx.x; k < S; k += blockDim.x) {
-        const int bj = s_body[k];
-        const float3 lp = make_float3(__ldg(p.pts.points + k * 3), __ldg(p.pts.points + k * 3 + 1),
-                                      __ldg(p.pts.points + k * 3 + 2));
-        const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
-        const float3 r = quat_rotate(br, lp);
-        const float3 wp = make_float3(r.x + s_bpos[bj][0], r.y + s_bpos[bj][1], r.z + s_bpos[bj][2]);
-        const int cell = grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y);
-        if (p.frame_mask) atomicOr(&s_mask[cell >> 5], 1u << (cell & 31));
-        if (p.min_body_heights) atomic_min_float(p.min_body_heights + b * (int64_t)X * Y + cell, wp.z);
-      }
-    }
-
-    // ---- feet: 8 box corners vs the height of the cell each falls in (warp 1, lane = foot*8 + corner) ----
-    if (warp == 1 && p.contacts) {
+    if (p.contacts) {
+      // ---- feet: lane = foot * 8 + corner ----
       const int foot = lane >> 3, corner = lane & 7;
       bool touch = false;
       float pen = INFINITY;
       if (foot < p.keys.num_feet) {
-        const int bj = p.keys.foot_body[foot];
+        const float* t = s_bt + p.keys.foot_body[foot] * 8;
         const float hx = p.keys.foot_half[foot][0], hy = p.keys.foot_half[foot][1], hz = p.keys.foot_half[foot][2];
         float3 c = make_float3((corner & 1) ? hx : -hx, (corner & 2) ? hy : -hy, (corner & 4) ? hz : -hz);
         c.x += p.keys.foot_offset[foot][0]; c.y += p.keys.foot_offset[foot][1]; c.z += p.keys.foot_offset[foot][2];
-        const float4 br = make_float4(s_brot[bj][0], s_brot[bj][1], s_brot[bj][2], s_brot[bj][3]);
-        const float3 r = quat_rotate(br, c);
-        const float3 wp = make_float3(r.x + s_bpos[bj][0], r.y + s_bpos[bj][1], r.z + s_bpos[bj][2]);
+        const float3 r = quat_rotate(make_float4(t[3], t[4], t[5], t[6]), c);
+        const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
         const float h = s_hf[grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y)];
         touch = wp.z < add_rn(h, p.contact_eps);            // box_points_z < cell_heights + contact_eps
         pen = sub_rn(wp.z, h);
       }
-      // any / min over the 8 corners of each foot
-      unsigned any = __ballot_sync(PARC_FULL_MASK, touch);
+      const unsigned any = __ballot_sync(PARC_FULL_MASK, touch);
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) pen = fminf(pen, __shfl_xor_sync(PARC_FULL_MASK, pen, o));
-      if (corner == 0 && foot < p.keys.num_feet) {
-        p.contacts[q * J + p.keys.foot_body[foot]] = ((any >> (foot * 8)) & 0xffu) ? 1.0f : 0.0f;
-        s_foot_pen[foot] = pen;
+      for (int o = 4; o > 0; o >>= 1) pen = fminf(pen, __shfl_xor_sync(PARC_FULL_MASK, pen, o));   // min per foot
+      // pen_correction_z starts at zero (:683) and takes the min over feet
+      float corr = fminf(pen, 0.0f);
+      corr = fminf(corr, __shfl_xor_sync(PARC_FULL_MASK, corr, 8));
+      corr = fminf(corr, __shfl_xor_sync(PARC_FULL_MASK, corr, 16));
+      // ---- hands: lane = hand, exact min over cells of the solid rounded-box SDF at the body origin ----
+      float hand_sd = INFINITY;
+      if (lane < p.keys.num_hands) {
+        const float* t = s_bt + p.keys.hand_body[lane] * 8;
+        const SdfBest best = scan_cells<false, true>(s_hf, s_cx, s_cy, X, Y, p.terrain.half_dx, p.terrain.half_dy, base,
+                                                     hf_min, hf_max, make_float3(t[0], t[1], t[2]));
+        hand_sd = best.sol - p.keys.hand_radius[lane];      // sdRoundBox = sdBox - r (geom_util.py:113-120)
       }
+      // ---- contact row: zeros, then feet / hands ----
+      float* crow = p.contacts + q * J;
+      if (lane < J) crow[lane] = 0.0f;
       __syncwarp();
-      if (lane == 0 && p.pen_correction) {
-        float corr = 0.0f;                                   // pen_correction_z starts at zero (:683)
-        for (int i = 0; i < p.keys.num_feet; ++i) corr = fminf(corr, s_foot_pen[i]);
-        p.pen_correction[q] = corr;
-      }
+      if (corner == 0 && foot < p.keys.num_feet)
+        crow[p.keys.foot_body[foot]] = ((any >> (foot * 8)) & 0xffu) ? 1.0f : 0.0f;
+      if (lane < p.keys.num_hands) crow[p.keys.hand_body[lane]] = hand_sd < p.contact_eps ? 1.0f : 0.0f;
+      if (lane == 0 && p.pen_correction) p.pen_correction[q] = corr;
     }
 
-    // ---- hands: rounded-box SDF of the body origin to the SOLID heightfield, all cells (warp 2) ----
-    if (warp == 2 && p.contacts) {
-      for (int hnd = 0; hnd < p.keys.num_hands; ++hnd) {
-        const int bj = p.keys.hand_body[hnd];
-        const float3 pt = make_float3(s_bpos[bj][0], s_bpos[bj][1], s_bpos[bj][2]);
-        float best = INFINITY;
-        for (int c = lane; c < X * Y; c += 32) {
-          const int ix = c / Y, iy = c - ix * Y;
-          const float h = s_hf[c];
-          const float cz = (h + base) * 0.5f, hz = (h - base) * 0.5f;
-          const float qx = fabsf(pt.x - s_cx[ix]) - p.terrain.half_dx;
-          const float qy = fabsf(pt.y - s_cy[iy]) - p.terrain.half_dy;
-          const float qz = fabsf(pt.z - cz) - hz;
-          const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
-          const float sd = sqrtf(mx * mx + my * my + mz * mz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.0f);
-          best = fminf(best, sd - p.keys.hand_radius[hnd]);  // sdRoundBox = sdBox - r (geom_util.py:113-120)
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(PARC_FULL_MASK, best, o));
-        if (lane == 0) p.contacts[q * J + bj] = best < p.contact_eps ? 1.0f : 0.0f;
+    // ---- masks: lane = surface point ----
+    if (want_masks) {
+      for (int k = lane; k < S; k += 32) {
+        const float* t = s_bt + s_body[k] * 8;
+        const float3 lp = make_float3(s_lp[k * 3], s_lp[k * 3 + 1], s_lp[k * 3 + 2]);
+        const float3 r = quat_rotate(make_float4(t[3], t[4], t[5], t[6]), lp);
+        const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
+        const int cell = grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y);
+        if (p.frame_mask) atomicOr(&s_mask[cell >> 5], 1u << (cell & 31));
+        if (p.min_body_heights) atomic_min_float(p.min_body_heights + b * (int64_t)X * Y + cell, wp.z);
       }
+      __syncwarp();
+      if (p.frame_mask)
+        for (int i = lane; i < p.mask_words; i += 32) p.frame_mask[q * p.mask_words + i] = s_mask[i];
     }
-    __syncthreads();
-    if (p.frame_mask)
-      for (int i = threadIdx.x; i < p.mask_words; i += blockDim.x) p.frame_mask[q * p.mask_words + i] = s_mask[i];
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -304,15 +291,19 @@ extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frame
   p.frame_mask = frame_mask_out; p.min_body_heights = min_body_heights; p.body_pos = body_pos; p.body_rot = body_rot;
   const int cells = terrain->dim_x * terrain->dim_y;
   p.mask_words = (cells + 31) / 32;
-  const size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + p.mask_words + (size_t)pts->num_points) * 4;
+  const size_t S = (frame_mask_out || min_body_heights) ? (size_t)pts->num_points : 0;
+  p.pts.num_points = (int)S;
+  const size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + S * 4 +
+                       (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words)) * 4;
   if (smem > 200 * 1024) return PARC_E_SIZE;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(clip_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  int64_t fpc = (batch * frames_per_clip) / (148 * 8);
-  if (fpc < 1) fpc = 1;
-  if (fpc > 16) fpc = 16;
+  int64_t rounds = (batch * frames_per_clip) / ((int64_t)148 * 8 * LABEL_WARPS);
+  if (rounds < 1) rounds = 1;
+  if (rounds > 8) rounds = 8;
+  const int64_t fpc = rounds * LABEL_WARPS;
   p.frames_per_cta = (int)fpc;
   dim3 grid((unsigned)((frames_per_clip + fpc - 1) / fpc), (unsigned)batch);
   clip_label_kernel<<<grid, LABEL_THREADS, smem, (cudaStream_t)stream>>>(p, *model);

@@ -1,0 +1,192 @@
+// Exact point <-> heightfield box SDF (min over ALL cells, with result-preserving pruning), its sub-gradient,
+// and the terrain-tile staging shared by body_loss.cu and dataset_sweep.cu.
+// Reference: util/terrain_util.py:1835-1893 (points_hf_sdf), util/geom_util.py:122-143 (sdBox).
+#pragma once
+
+#include "parc_common.cuh"
+
+namespace parc {
+
+struct SdfBest {
+  float inv;   // min over cells of sdBox to the AIR column   (result of inverted=True is -inv)
+  float sol;   // min over cells of sdBox to the SOLID column
+  int arg_inv;
+  int arg_sol;
+};
+
+// Exact min over ALL cells of the box SDF, with pruning that cannot change the result.
+//
+// For a cell whose xy footprint does not contain the point (mx > 0 or my > 0, m = max(|p - c| - half, 0))
+// the SDF is sqrt(mx^2 + my^2 + mz^2) >= sqrt(mx^2 + my^2) =: bound.  A cell (or a whole row ix, bound mx)
+// whose bound is STRICTLY greater than the best value found so far can neither be the minimum nor tie
+// with it, so it is skipped; cells whose footprint contains the point are always evaluated (their SDF can
+// be negative).  The scan is seeded with the cell under the point.  Because evaluation order is no longer
+// index order, the first-index tie rule of torch.min is kept explicitly: a candidate replaces the best
+// iff it is smaller, or equal with a smaller flat index.  The bound test carries a 1e-6 relative margin
+// for the rounding of best^2 (evaluating too many cells is always safe).
+// hf/cx/cy are shared-memory arrays; a warp's threads are points of the same body, so their skip patterns
+// mostly coincide.
+template <bool WANT_INV, bool WANT_SOL>
+__device__ __forceinline__ void eval_cell(const float* __restrict__ hf, int cell, float mxy2, float qxy, float pz,
+                                          float base, float top, SdfBest& b) {
+  const float h = hf[cell];
+  if (WANT_INV) {
+    const float cz = (h + top) * 0.5f;
+    const float hz = (top - h) * 0.5f;
+    const float qz = fabsf(pz - cz) - hz;
+    const float mz = fmaxf(qz, 0.0f);
+    const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
+    if (sd < b.inv || (sd == b.inv && cell < b.arg_inv)) { b.inv = sd; b.arg_inv = cell; }
+  }
+  if (WANT_SOL) {
+    const float cz = (h + base) * 0.5f;
+    const float hz = (h - base) * 0.5f;
+    const float qz = fabsf(pz - cz) - hz;
+    const float mz = fmaxf(qz, 0.0f);
+    const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
+    if (sd < b.sol || (sd == b.sol && cell < b.arg_sol)) { b.sol = sd; b.arg_sol = cell; }
+  }
+}
+
+// squared pruning threshold for a current best value (negative best: every outside cell is > best)
+__device__ __forceinline__ float prune_thr(float best) {
+  return best < 0.0f ? 0.0f : best * best * 1.000001f;
+}
+
+// Effective squared xy-reach for the wanted modes.  Every solid column tops out at or below the tile's
+// maximum height H and every air column starts at or above the tile's minimum height L, so for a cell whose
+// footprint does not contain the point
+//     sdf_solid >= sqrt(mxy^2 + vz_sol^2),  vz_sol = max(pz - H, base - pz, 0)
+//     sdf_air   >= sqrt(mxy^2 + vz_inv^2),  vz_inv = max(L - pz, pz - top, 0)
+// and the cell can be skipped when mxy^2 > best^2 - vz^2 for every wanted mode.
+template <bool WANT_INV, bool WANT_SOL>
+__device__ __forceinline__ float prune_thr2(const SdfBest& b, float vz_inv2, float vz_sol2) {
+  return fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, WANT_SOL ? prune_thr(b.sol) - vz_sol2 : -1.0f);
+}
+
+// clamp-then-convert so that huge / NaN intermediate values cannot overflow the int conversion
+__device__ __forceinline__ int to_index(float v, int hi) {
+  return (int)fminf(fmaxf(v, 0.0f), (float)hi);
+}
+
+template <bool WANT_INV, bool WANT_SOL>
+__device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, const float* __restrict__ cx,
+                                              const float* __restrict__ cy, int X, int Y, float hx, float hy,
+                                              float base, float hf_min, float hf_max, float3 p) {
+  SdfBest b;
+  b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0x7fffffff; b.arg_sol = 0x7fffffff;
+  const float top = -base;
+  // vertical lower bounds, shrunk by a relative 1e-6 so rounding in the per-cell evaluation cannot beat them
+  const float vzs = fmaxf(fmaxf(p.z - hf_max, base - p.z), 0.0f) * 0.999999f;
+  const float vzi = fmaxf(fmaxf(hf_min - p.z, p.z - top), 0.0f) * 0.999999f;
+  const float vz_sol2 = vzs * vzs, vz_inv2 = vzi * vzi;
+  // cells are evenly spaced (torch.linspace nodes): spacing from the end points
+  const float sx = X > 1 ? (cx[X - 1] - cx[0]) / (float)(X - 1) : 1.0f;
+  const float sy = Y > 1 ? (cy[Y - 1] - cy[0]) / (float)(Y - 1) : 1.0f;
+  const float isx = 1.0f / sx, isy = 1.0f / sy;
+  // seed: the cell whose centre is nearest in xy
+  {
+    const int ix = to_index(rintf((p.x - cx[0]) * isx), X - 1);
+    const int iy = to_index(rintf((p.y - cy[0]) * isy), Y - 1);
+    const float qx = fabsf(p.x - cx[ix]) - hx, qy = fabsf(p.y - cy[iy]) - hy;
+    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b);
+  }
+  float thr = prune_thr2<WANT_INV, WANT_SOL>(b, vz_inv2, vz_sol2);
+  // Index window that is a SUPERSET of every cell that can still matter: a cell further than r = sqrt(thr)
+  // (+ its half width) from the point in x or in y is out of reach.  One extra cell of margin on each side
+  // absorbs the rounding of the spacing; cells inside the window are still bound-checked one by one.
+  const float r = sqrtf(fmaxf(thr, 0.0f));
+  const int ix_lo = to_index(floorf((p.x - r - hx - cx[0]) * isx) - 1.0f, X - 1);
+  const int ix_hi = to_index(ceilf((p.x + r + hx - cx[0]) * isx) + 1.0f, X - 1);
+  const int iy_lo = to_index(floorf((p.y - r - hy - cy[0]) * isy) - 1.0f, Y - 1);
+  const int iy_hi = to_index(ceilf((p.y + r + hy - cy[0]) * isy) + 1.0f, Y - 1);
+  for (int ix = ix_lo; ix <= ix_hi; ++ix) {
+    const float qx = fabsf(p.x - cx[ix]) - hx;
+    const float mx = fmaxf(qx, 0.0f);
+    const float mx2 = mx * mx;
+    if (mx2 > 0.0f && mx2 > thr) continue;         // whole row out of reach
+    for (int iy = iy_lo; iy <= iy_hi; ++iy) {
+      const float qy = fabsf(p.y - cy[iy]) - hy;
+      const float my = fmaxf(qy, 0.0f);
+      const float mxy2 = mx2 + my * my;
+      if (mxy2 > 0.0f && mxy2 > thr) continue;     // outside the footprint and strictly out of reach
+      const float old_inv = b.inv, old_sol = b.sol;
+      eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b);
+      if (b.inv < old_inv || b.sol < old_sol) thr = prune_thr2<WANT_INV, WANT_SOL>(b, vz_inv2, vz_sol2);
+    }
+  }
+  return b;
+}
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+// d sdBox(p - c, half) / d p for one cell, following autograd's sub-gradient conventions
+// (SURVEY A10): clamp passes the gradient at the bound, norm'(0) = 0, abs'(0) = 0, max -> first index.
+__device__ __forceinline__ float3 sd_box_grad(float3 d, float3 half) {
+  const float qx = fabsf(d.x) - half.x, qy = fabsf(d.y) - half.y, qz = fabsf(d.z) - half.z;
+  const float mq = fmaxf(qx, fmaxf(qy, qz));
+  float3 g = make_float3(0.f, 0.f, 0.f);
+  if (mq > 0.0f) {
+    const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
+    const float n = sqrtf(mx * mx + my * my + mz * mz);
+    if (n > 0.0f) {
+      g.x = mx / n * sgn(d.x);
+      g.y = my / n * sgn(d.y);
+      g.z = mz / n * sgn(d.z);
+    }
+  } else {
+    if (qx >= qy && qx >= qz) g.x = sgn(d.x);
+    else if (qy >= qz) g.y = sgn(d.y);
+    else g.z = sgn(d.z);
+  }
+  return g;
+}
+
+__device__ __forceinline__ float3 cell_grad(const float* hf, const float* cx, const float* cy, int Y, float hx,
+                                            float hy, float base, bool inverted, int cell, float3 p) {
+  const int ix = cell / Y, iy = cell - ix * Y;
+  const float h = hf[cell];
+  float cz, hz;
+  if (inverted) { const float top = -base; cz = (h + top) * 0.5f; hz = (top - h) * 0.5f; }
+  else { cz = (h + base) * 0.5f; hz = (h - base) * 0.5f; }
+  return sd_box_grad(make_float3(p.x - cx[ix], p.y - cy[iy], p.z - cz), make_float3(hx, hy, hz));
+}
+
+// Stage one sample's terrain: hf tile, absolute cell-centre coordinates (node offset + min centre, added
+// in fp32 as util/terrain_util.py:1859-1860 does), and the tile's min / max height for the pruning bounds
+// (s_minmax[0] = min, [1] = max; must be followed by __syncthreads()).
+__device__ __forceinline__ void stage_terrain(const ParcTerrainBatch& t, int64_t b, float* s_hf, float* s_cx,
+                                              float* s_cy, float* s_minmax) {
+  const int X = t.dim_x, Y = t.dim_y;
+  const float* hf = t.hf + b * t.hf_batch_stride;
+  const float* mc = t.min_center + b * t.min_center_stride;
+  if (threadIdx.x == 0) { s_minmax[0] = INFINITY; s_minmax[1] = -INFINITY; }
+  __syncthreads();
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < X * Y; i += blockDim.x) {
+    const float h = __ldg(hf + i);
+    s_hf[i] = h;
+    lo = fminf(lo, h); hi = fmaxf(hi, h);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(PARC_FULL_MASK, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(PARC_FULL_MASK, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // float min / max through the int-ordered trick (values may be negative)
+    if (lo >= 0.0f) atomicMin(reinterpret_cast<int*>(&s_minmax[0]), __float_as_int(lo));
+    else atomicMax(reinterpret_cast<unsigned int*>(&s_minmax[0]), __float_as_uint(lo));
+    if (hi >= 0.0f) atomicMax(reinterpret_cast<int*>(&s_minmax[1]), __float_as_int(hi));
+    else atomicMin(reinterpret_cast<unsigned int*>(&s_minmax[1]), __float_as_uint(hi));
+  }
+  for (int i = threadIdx.x; i < X; i += blockDim.x) s_cx[i] = __ldg(t.x_nodes + i) + __ldg(mc);
+  for (int i = threadIdx.x; i < Y; i += blockDim.x) s_cy[i] = __ldg(t.y_nodes + i) + __ldg(mc + 1);
+}
+
+__device__ __forceinline__ float sample_base_z(const ParcTerrainBatch& t, int64_t b) {
+  return t.base_z ? __ldg(t.base_z + b * t.base_z_stride) : t.base_z_value;
+}
+
+}  // namespace parc
