@@ -126,8 +126,22 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     if (BLEND) t_pre = __ldg(p.times + e0); else f_pre = __ldg(p.frame_idx + e0);
   }
   if (tmpl_in_smem) {
+    // all of a thread's template loads are issued before the first shared-memory store, so the cold misses
+    // overlap instead of queueing one round trip per element
     const float2* __restrict__ g = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
-    for (int i = threadIdx.x; i < P_pad; i += blockDim.x) s_tmpl[i] = __ldg(g + (i < P ? i : 0));
+    for (int i0 = threadIdx.x; i0 < P_pad; i0 += QUERY_CTA_THREADS * 8) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * QUERY_CTA_THREADS;
+        v[u] = __ldg(g + (i < P ? i : 0));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * QUERY_CTA_THREADS;
+        if (i < P_pad) s_tmpl[i] = v[u];
+      }
+    }
   }
   stage_tree(&sm, model_param);
   __syncthreads();
