@@ -90,3 +90,34 @@ def assert_close_normwise(actual, expected, rtol=1e-5, what=""):
     scale = max(e.abs().max().item(), 1e-30)
     err = (a - e).abs().max().item()
     assert err <= rtol * scale, f"{what}: max|err|={err:.3e} > {rtol:g} * max|expected|={scale:.3e}"
+
+
+def make_random_tree_model(num_bodies=21, seed=4):
+    """A synthetic character with more than 15 bodies (exercises the one-character-per-warp path): random
+    tree, mixed joint types, NON-identity local rotations.  Returns (oracle CharModel, dict of plain lists for
+    parc_b200.ops.make_char_model)."""
+    from oracle import parc_oracle as O
+    rng = np.random.default_rng(seed)
+    parents = [-1] + [int(rng.integers(max(0, b - 4), b)) for b in range(1, num_bodies)]
+    types = [O.ROOT] + [int(rng.choice([O.HINGE, O.SPHERICAL, O.SPHERICAL, O.FIXED])) for _ in range(1, num_bodies)]
+    lt = rng.uniform(-0.3, 0.3, size=(num_bodies, 3)).astype(np.float32)
+    lt[0] = 0
+    lr = rng.normal(size=(num_bodies, 4)).astype(np.float32)
+    lr /= np.linalg.norm(lr, axis=1, keepdims=True)
+    lr[0] = [0, 0, 0, 1]
+    axes = np.zeros((num_bodies, 3), np.float32)
+    dof_idx, dof_dim, d = [], [], 0
+    for b in range(num_bodies):
+        dim = 1 if types[b] == O.HINGE else (3 if types[b] == O.SPHERICAL else 0)
+        if types[b] == O.HINGE:
+            a = rng.normal(size=3)
+            axes[b] = (a / np.linalg.norm(a)).astype(np.float32)
+        dof_idx.append(d)
+        dof_dim.append(dim)
+        d += dim
+    om = O.CharModel(body_names=[f"b{i}" for i in range(num_bodies)], parents=parents, local_trans=torch.tensor(lt),
+                     local_rot=torch.tensor(lr), joint_type=types, joint_axis=torch.tensor(axes), dof_idx=dof_idx,
+                     dof_dim=dof_dim, body_points=[])
+    plain = dict(parents=parents, local_trans=lt.tolist(), local_rot=lr.tolist(), joint_types=types,
+                 joint_axes=axes.tolist(), dof_idx=dof_idx)
+    return om, plain

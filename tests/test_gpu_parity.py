@@ -562,3 +562,84 @@ def test_label_clips_batched_vs_oracle(gpu_model, O, oracle_model):
         assert (~same).sum() <= 2
     assert bad <= 3, f"{bad} contact labels differ"
     assert out["contacts"].sum() > 0
+
+
+# ----------------------------------------------------------------------------------------- generic character (J > 15)
+def test_generic_21_body_character_vs_oracle(O):
+    """Characters with more than 15 bodies take the one-character-per-warp (G = 32) instantiation of the fused
+    kernel; random tree, hinge/spherical/fixed mix, non-identity local rotations.  Query + FK + obs, the
+    stand-alone FK forward/backward and the DoF conversions, all against the oracle."""
+    from conftest import make_random_tree_model
+    from parc_b200 import ops
+    om, plain = make_random_tree_model(21)
+    m = ops.make_char_model(**plain)
+    J, D = 21, om.dof_size
+    rng = np.random.default_rng(12)
+    clips = []
+    for c in range(3):
+        F = [40, 17, 64][c]
+        fr = np.zeros((F, 6 + D), np.float32)
+        t = np.arange(F)[:, None] / 30.0
+        fr[:, 0:3] = np.cumsum(rng.normal(scale=0.02, size=(F, 3)), axis=0) + [3.0, 3.0, 1.0]
+        fr[:, 3:6] = 0.3 * np.sin(t * rng.uniform(0.5, 2, 3) + rng.uniform(0, 6, 3)) + 0.05
+        fr[:, 6:] = 0.8 * np.sin(t * rng.uniform(0.5, 3, D) + rng.uniform(0, 6, D)) + 0.01
+        ct = (rng.uniform(size=(F, J)) < 0.4).astype(np.float32)
+        clips.append(O.Clip(fr, ct, 30.0, O.WRAP if c == 1 else O.CLAMP, 1.0))
+    tb = O.build_tables(om, clips)
+    # pack the oracle's tables with the library and query through the C ABI
+    dv = lambda x: x.cuda()
+    rows, lay = ops.pack_frames(m, dv(tb.root_pos), dv(tb.root_rot), dv(tb.joint_rot), dv(tb.contacts), dv(tb.root_vel),
+                                dv(tb.root_ang_vel), dv(tb.dof_vel))
+    meta = ops.build_clip_meta(tb.num_frames, tb.loop_modes, tb.start_idx, tb.lengths, tb.root_pos_delta, "cuda:0")
+    packed = ops.PackedTables(rows=rows, clips=meta, total_frames=int(rows.shape[0]), num_clips=3, layout=lay)
+    gen = torch.Generator().manual_seed(9)
+    n = 777
+    ids = torch.randint(0, 3, (n,), generator=gen)
+    times = (torch.rand(n, generator=gen) * 2.5 - 0.5) * tb.lengths[ids]
+    hf = torch.tensor(np.random.default_rng(3).uniform(-0.3, 0.5, size=(24, 20)).astype(np.float32))
+    hfd = ops.HeightfieldDesc(hf=hf.cuda(), min_x=-1.0, min_y=0.5, dx=0.4, dy=0.3)
+    tmpl = O.cone_template(0.05, 2, 60, 3, 3, 0.26179938779)
+    r = ops.motion_query(packed, m, ids.cuda(), motion_times=times.cuda(), want_index=True, want_fk=True, hf=hfd,
+                         obs_tmpl=tmpl.cuda())
+    i0, i1, bl = O.frame_blend(tb, ids, times)
+    assert torch.equal(r["frame_idx0"].cpu(), i0) and torch.equal(r["frame_idx1"].cpu(), i1)
+    assert torch.equal(r["blend"].cpu(), bl)
+    ref = O.calc_motion_frame(tb, ids, times)
+    for k, t in zip(FRAME_KEYS, ref):
+        assert_close(r[k], t, what=f"generic.{k}")
+    assert torch.equal(r["dof_vel"].cpu(), ref[5]) and torch.equal(r["contacts"].cpu(), ref[6])
+    bp, br = O.forward_kinematics(om, ref[0], ref[1], ref[4])
+    assert_close(r["body_pos"], bp, what="generic.body_pos")
+    assert_close(r["body_rot"], br, what="generic.body_rot")
+    ot = O.Terrain(hf=hf, min_point=torch.tensor([-1.0, 0.5]), dxdy=torch.tensor([0.4, 0.3]))
+    heading = O.calc_heading(ref[1])
+    exp_obs = O.ray_obs(ot, ref[0], heading, tmpl)
+    mism = r["obs"].cpu() != exp_obs
+    border = _border_mask(O.grid_coord(ot, O.ray_obs_points(ref[0], heading, tmpl)), ulps=64).view(n, 441)
+    assert not (mism & ~border).any() and mism.float().mean() < 2e-3
+    # integer-frame lookup
+    fi = torch.randint(0, 17, (n,), generator=gen)
+    g = ops.motion_query(packed, m, ids.cuda(), frame_idxs=fi.cuda())
+    gref = O.get_motion_frame(tb, ids, fi)
+    assert torch.equal(g["joint_rot"].cpu(), gref[4]) and torch.equal(g["root_pos"].cpu(), gref[0])
+    # stand-alone FK forward + VJP and DoF conversions on the raw frames
+    fr = torch.tensor(clips[2].frames)
+    wp = torch.randn(64, J, 3, generator=gen)
+    wr = torch.randn(64, J, 4, generator=gen)
+
+    def run(fk, d2r, e2q, to):
+        a, b, c = (fr[:, 0:3].clone().to(to).requires_grad_(True), fr[:, 3:6].clone().to(to).requires_grad_(True),
+                   fr[:, 6:].clone().to(to).requires_grad_(True))
+        p_, r_ = fk(a, e2q(b), d2r(c))
+        ((p_ * wp.to(to)).sum() + (r_ * wr.to(to)).sum()).backward()
+        return p_.detach(), r_.detach(), a.grad, b.grad, c.grad
+
+    cpu = run(lambda p_, q_, j_: O.forward_kinematics(om, p_, q_, j_), lambda d: O.dof_to_rot(om, d), O.exp_map_to_quat, "cpu")
+    gpu = run(lambda p_, q_, j_: ops.forward_kinematics(m, p_, q_, j_), lambda d: ops.dof_to_rot(m, d), ops.exp_map_to_quat,
+              "cuda:0")
+    assert_close(gpu[0], cpu[0], what="generic fk pos")
+    assert_close(gpu[1], cpu[1], what="generic fk rot")
+    for nm, a, b in zip(("root_pos", "root_exp", "joint_dof"), gpu[2:], cpu[2:]):
+        assert_close_normwise(a, b, what=f"generic grad {nm}")
+    bp2, br2 = ops.frames_fk(m, fr.cuda())
+    assert_close(bp2, cpu[0], what="generic frames_fk pos")

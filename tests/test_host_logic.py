@@ -58,6 +58,21 @@ def test_row_layout_and_model_validation(cpu_model):
     assert _lib.load().parc_validate_model(C.byref(bad)) == -3
 
 
+def test_row_layout_of_a_large_model():
+    from conftest import make_random_tree_model
+    from parc_b200 import ops
+    om, plain = make_random_tree_model(21)
+    m = ops.make_char_model(**plain)
+    lay = ops.row_layout(m)
+    assert m.num_bodies == 21 and m.dof_size == om.dof_size and m.max_depth >= 2
+    assert lay.contact_slot == 22 and lay.pose_slots == 22 + 6 and lay.vel_slots == 2 + (om.dof_size + 3) // 4
+    assert lay.row_floats % 8 == 0 and lay.row_floats >= (lay.pose_slots + lay.vel_slots) * 4
+    _, plain25 = make_random_tree_model(25)
+    from parc_b200._lib import ParcLibraryError
+    with pytest.raises(ParcLibraryError):
+        ops.make_char_model(**plain25)
+
+
 def test_argument_errors_are_returned_not_thrown(cpu_model):
     """NULL / negative-size / misaligned arguments come back as negative codes; nothing is launched."""
     from parc_b200 import _lib
