@@ -54,6 +54,20 @@ def pin(name, ref, mine):
         raise SystemExit(f"oracle != reference for {name}: max abs diff {diff}")
 
 
+def pin_close(name, ref, mine, rtol):
+    """max|ref - mine| <= rtol * max|ref| -- for sums of many autograd branches, whose accumulation ORDER (and so
+    the last bits) depends on graph construction order rather than on the algorithm."""
+    ref = torch.as_tensor(ref).double()
+    mine = torch.as_tensor(mine).double()
+    scale = max(ref.abs().max().item(), 1e-30)
+    err = (ref - mine).abs().max().item() if ref.shape == mine.shape else float("inf")
+    ok = err <= rtol * scale
+    REPORT.append(f"{'OK~' if ok else 'FAIL'} {name} shape={tuple(ref.shape)} max|err|/max|ref|={err / scale:.2e} (bar {rtol:g})")
+    if not ok:
+        print("\n".join(REPORT))
+        raise SystemExit(f"oracle !~ reference for {name}")
+
+
 def npf(t):
     return t.detach().cpu().numpy()
 
@@ -371,6 +385,72 @@ def main():
         feet_body=np.array([lf, rf]), feet_half=np.array([f[1] for f in feet], np.float32),
         feet_offset=np.array([f[2] for f in feet], np.float32), hands_body=np.array([lh, rh]),
         hands_radius=np.array([h[1] for h in hands], np.float32))
+
+    # ------------------------------------------------------------------ 7. full objective incl. body constraints + Adam loop (8(f)-2)
+    W = dict(w_root_pos=1.0, w_root_rot=10.0, w_joint_rot=1.0, w_smoothness=10.0, w_penetration=1000.0,
+             w_contact=1000.0, w_sliding=10.0, w_body_constraints=1000.0, w_jerk=1000.0)      # PARC/kin_gen_default.yaml:28-37
+    bcs = [[] for _ in range(J)]
+
+    def mk_bc(s_, e_, pt):
+        c = ref_mopt.BodyConstraint()
+        c.start_frame_idx, c.end_frame_idx, c.constraint_point = s_, e_, torch.tensor(pt, dtype=torch.float32)
+        return c
+
+    with torch.no_grad():
+        tq = ref_tu.exp_map_to_quat(tgt_re)
+        tj = km.dof_to_rot(tgt_jd)
+        tbp, _ = km.forward_kinematics(tgt_rp, tq, tj)
+    bcs[lf] = [mk_bc(1, 4, (tbp[2, lf] + torch.tensor([0.02, -0.01, -0.06])).tolist())]
+    bcs[rh] = [mk_bc(2, 6, (tbp[4, rh] + torch.tensor([0.05, 0.03, -0.04])).tolist())]
+
+    def run_ref_bc():
+        a, b, c = (t.clone().requires_grad_(True) for t in (tgt_rp, tgt_re, tgt_jd))
+        loss, ld = ref_mopt.motion_terrain_contact_loss(
+            a, b, c, src_rp, src_rq, src_jr, src_bv, src_brv, cts, terr, body_points, km, body_constraints=bcs,
+            max_jerk=1000.0, **W)
+        loss.backward()
+        return loss.detach(), ld, a.grad, b.grad, c.grad
+
+    loss_bc, ld_bc, gb_rp, gb_re, gb_jd = run_ref_bc()
+    geom0 = [(km._geoms[b][0]._shape_type.value, npf(km._geoms[b][0]._offset).tolist(),
+              npf(km._geoms[b][0]._dims).reshape(-1).tolist() if km._geoms[b][0]._dims.dim() > 0 else float(km._geoms[b][0]._dims))
+             for b in range(J)]
+    o_bcs = [[(c.start_frame_idx, c.end_frame_idx, c.constraint_point.tolist()) for c in bcs[b]] for b in range(J)]
+    a, b, c = (t.clone().requires_grad_(True) for t in (tgt_rp, tgt_re, tgt_jd))
+    o_loss, o_terms = O.motion_terrain_contact_loss_full(model, a, b, c, src_rp, src_rq, src_jr, src_bv, src_brv, cts, terr.hf,
+                                                         terr.min_point, terr.dxdy, W, 1000.0, o_bcs, geom0)
+    o_loss.backward()
+    pin("motion_opt_full.loss", loss_bc, o_loss.detach())
+    pin("motion_opt_full.body_constraint_term", torch.tensor(float(ld_bc[ref_mopt.LossType.BODY_CONSTRAINT_LOSS])),
+        torch.tensor(float(o_terms["body_constraint"])))
+    pin_close("motion_opt_full.grad_root_pos", gb_rp, a.grad, 1e-6); pin_close("motion_opt_full.grad_root_rot", gb_re, b.grad, 1e-6)
+    pin_close("motion_opt_full.grad_joint_dof", gb_jd, c.grad, 1e-6)
+
+    # the Adam loop (motion_optimization.py:404-500) for 4 iterations, built from the reference's own loss function
+    src_fr = torch.cat([tgt_rp, tgt_re, tgt_jd], dim=-1)
+    s_rq = ref_tu.exp_map_to_quat(src_fr[:, 3:6]); s_jr = km.dof_to_rot(src_fr[:, 6:34])
+    s_bp, s_br = km.forward_kinematics(src_fr[:, 0:3], s_rq, s_jr)
+    s_bv = s_bp[1:] - s_bp[:-1]; s_brv = ref_tu.quat_diff_angle(s_br[1:], s_br[:-1])
+    leaves = [src_fr[:, 0:3].clone().requires_grad_(True), src_fr[:, 3:6].clone().requires_grad_(True),
+              src_fr[:, 6:34].clone().requires_grad_(True)]
+    opt = torch.optim.Adam(leaves, lr=0.001)
+    for _ in range(4):
+        opt.zero_grad()
+        l_, _d = ref_mopt.motion_terrain_contact_loss(leaves[0], leaves[1], leaves[2], src_fr[:, 0:3], s_rq, s_jr, s_bv, s_brv,
+                                                     cts, terr, body_points, km, body_constraints=bcs, max_jerk=1000.0, **W)
+        l_.backward()
+        opt.step()
+    ref_opt = torch.cat([t.detach() for t in leaves], dim=-1)
+    o_opt = O.motion_contact_optimization(model, src_fr, cts, terr.hf, terr.min_point, terr.dxdy, 4, 0.001, W, 1000.0, o_bcs, geom0)
+    pin_close("motion_opt_full.adam4_frames", ref_opt - src_fr, o_opt - src_fr, 1e-4)    # the 4-step UPDATE itself
+    np.savez_compressed(
+        os.path.join(GOLD, "motion_opt_golden.npz"), src_frames=npf(src_fr), contacts=npf(cts),
+        src_root_pos=npf(src_rp), src_root_quat=npf(src_rq), src_joint_rot=npf(src_jr), src_body_vels=npf(src_bv),
+        src_body_rot_vels=npf(src_brv), weights=np.array([W[k] for k in sorted(W)]), weight_names=np.array(sorted(W)),
+        bc_body=np.array([lf, rh]), bc_start=np.array([1, 2]), bc_end=np.array([4, 6]),
+        bc_point=np.stack([npf(bcs[lf][0].constraint_point), npf(bcs[rh][0].constraint_point)]),
+        loss=npf(loss_bc), body_constraint_term=np.array(float(ld_bc[ref_mopt.LossType.BODY_CONSTRAINT_LOSS])),
+        grad_root_pos=npf(gb_rp), grad_root_exp=npf(gb_re), grad_joint_dof=npf(gb_jd), adam4_frames=npf(ref_opt))
 
     with open(os.path.join(GOLD, "PIN_REPORT.txt"), "w") as f:
         f.write("oracle/parc_oracle.py vs the imported reference (torch %s, CPU, fp32) -- torch.equal on every line\n"

@@ -702,3 +702,90 @@ def hf_mask_inds(model: CharModel, frames, t: Terrain):
         min_h = min_h.view(-1).scatter_reduce(0, flat, pts[:, 2], reduce="amin", include_self=True).view(X, Y)
         inds.append(torch.unique(g, dim=0))
     return inds, min_h
+
+
+# --------------------------------------------------------------------------
+# the remaining motion_terrain_contact_loss terms
+# --------------------------------------------------------------------------
+def motion_terrain_contact_loss_full(model: CharModel, tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos,
+                                     src_root_rot_quat, src_joint_rot, src_body_vels, src_body_rot_vels, contacts, hf,
+                                     min_point, dxdy, w, max_jerk, body_constraints=None, geom0=None):
+    """tools/motion_opt/motion_optimization.py:183-395, every term.  `w`: dict of the nine weights;
+    body_constraints: per body a list of (start, end, point[3]); geom0: per body (type, offset[3], dims) of its
+    first geom (type 0 = BOX, 1 = SPHERE as anim/kin_char_model.py:102-107).  -> (loss, dict of term tensors)."""
+    root_pos_loss = torch.sum(torch.square(tgt_root_pos - src_root_pos))
+    rq = exp_map_to_quat(tgt_root_rot)
+    root_rot_loss = torch.sum(torch.square(quat_diff_angle(rq, src_root_rot_quat)))
+    jr = dof_to_rot(model, tgt_joint_dof)
+    joint_rot_loss = torch.sum(torch.square(quat_diff_angle(jr, src_joint_rot)))
+    bp, br = forward_kinematics(model, tgt_root_pos, rq, jr)
+    vels = bp[1:] - bp[:-1]
+    vel_err_sq = torch.square(vels - src_body_vels)
+    rot_vels = quat_diff_angle(br[1:], br[:-1])
+    rot_vel_err_sq = torch.square(rot_vels - src_body_rot_vels)
+    smoothness = torch.sum(vel_err_sq) + torch.sum(rot_vel_err_sq)
+    change = torch.clamp(torch.min(torch.cat([contacts[1:].unsqueeze(-1), contacts[:-1].unsqueeze(-1)], dim=-1), dim=-1)[0], min=0.0)
+    pen, con = pen_contact_terms(bp.unsqueeze(0), br.unsqueeze(0), contacts.unsqueeze(0), model.body_points, hf,
+                                 min_point, dxdy, -10.0)
+    pen, con = pen[0], con[0]
+    if w["w_contact"] == 0.0:
+        con = 0.0
+    bc_loss = 0.0
+    if body_constraints is not None:
+        for b in range(model.num_bodies):
+            for (s_, e_, point) in body_constraints[b]:
+                gtype, goff, gdims = geom0[b]
+                point = torch.as_tensor(point, dtype=F32)
+                if gtype == 1:      # SPHERE
+                    centre = quat_rotate(br[:, b], torch.as_tensor(goff, dtype=F32).unsqueeze(0)) + bp[:, b]
+                    diff = torch.norm(point.unsqueeze(0) - centre[s_:e_ + 1], dim=-1) - torch.as_tensor(gdims, dtype=F32)
+                    bc_loss = bc_loss + torch.sum(torch.abs(diff))
+                elif gtype == 0:    # BOX: the 18 sole points (first z slice of the box samples)
+                    radius = torch.norm(torch.as_tensor(gdims, dtype=F32)) * 1.25
+                    pts = quat_rotate(br[:, b].unsqueeze(1), model.body_points[b].unsqueeze(0)) + bp[:, b].unsqueeze(1)
+                    sole = pts[s_:e_ + 1, 0:18].reshape(-1, 3)
+                    diff = torch.norm(point.unsqueeze(0) - sole, dim=-1) - radius
+                    bc_loss = bc_loss + torch.sum(torch.clamp(diff, min=0.0))
+                else:
+                    continue
+                vel_err_sq = vel_err_sq.clone()
+                vel_err_sq[s_:e_ + 1, b] *= 0.0
+                rot_vel_err_sq = rot_vel_err_sq.clone()
+                rot_vel_err_sq[s_:e_ + 1, b] *= 0.0
+    if w["w_sliding"] != 0.0:
+        c, c2 = 0.03, 0.0009
+        sliding = torch.sum((torch.sqrt(torch.sum(vel_err_sq, dim=-1) + c2) - c) * change) \
+            + torch.sum((torch.sqrt(rot_vel_err_sq + c2) - c) * change)
+    else:
+        sliding = 0.0
+    acc = vels[1:] - vels[:-1]
+    jerk_mag = torch.norm(acc[1:] - acc[:-1], dim=-1)
+    jerk = torch.sum(torch.clamp(jerk_mag - max_jerk * ((1.0 / 30.0) ** 3), min=0.0))
+    loss = w["w_root_pos"] * root_pos_loss + w["w_root_rot"] * root_rot_loss + w["w_joint_rot"] * joint_rot_loss \
+        + w["w_smoothness"] * smoothness + w["w_penetration"] * pen + w["w_contact"] * con + w["w_sliding"] * sliding \
+        + w["w_body_constraints"] * bc_loss + w["w_jerk"] * jerk
+    return loss, dict(root_pos=root_pos_loss, root_rot=root_rot_loss, joint_rot=joint_rot_loss, smoothness=smoothness,
+                      penetration=pen, contact=con, sliding=sliding, body_constraint=bc_loss, jerk=jerk)
+
+
+def motion_contact_optimization(model: CharModel, src_frames, contacts, hf, min_point, dxdy, num_iters, step_size, w,
+                                max_jerk, body_constraints=None, geom0=None):
+    """The Adam loop of tools/motion_opt/motion_optimization.py:404-500 (logging omitted)."""
+    D = model.dof_size
+    src_root_pos, src_root_rot, src_joint_dof = src_frames[:, 0:3], src_frames[:, 3:6], src_frames[:, 6:6 + D]
+    src_rq = exp_map_to_quat(src_root_rot)
+    src_jr = dof_to_rot(model, src_joint_dof)
+    sbp, sbr = forward_kinematics(model, src_root_pos, src_rq, src_jr)
+    src_bv = sbp[1:] - sbp[:-1]
+    src_brv = quat_diff_angle(sbr[1:], sbr[:-1])
+    leaves = [src_root_pos.clone().requires_grad_(True), src_root_rot.clone().requires_grad_(True),
+              src_joint_dof.clone().requires_grad_(True)]
+    opt = torch.optim.Adam(leaves, lr=step_size)
+    for _ in range(num_iters):
+        opt.zero_grad()
+        loss, _t = motion_terrain_contact_loss_full(model, leaves[0], leaves[1], leaves[2], src_root_pos, src_rq, src_jr,
+                                                    src_bv, src_brv, contacts, hf, min_point, dxdy, w, max_jerk,
+                                                    body_constraints, geom0)
+        loss.backward()
+        opt.step()
+    return torch.cat([t.detach() for t in leaves], dim=-1)

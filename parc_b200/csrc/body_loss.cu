@@ -11,6 +11,8 @@
 //           penetration, solid column for contact), terrain tile staged in shared memory
 //   warp 0: per-body first-index min (contact), per-body gradient sums, FK VJP -> leaf gradients
 // The min is exact and tie-breaks on the first flat cell index, as torch.min does.
+#include <atomic>
+
 #include "parc_common.cuh"
 #include "parc_sdf.cuh"
 
@@ -261,8 +263,14 @@ extern "C" int parc_points_hf_sdf(const float* points, int64_t batch, int64_t n_
   const size_t smem = terrain_smem_bytes(terrain);
   if (smem > 200 * 1024) return PARC_E_SIZE;          // terrain tile must fit one SM's shared memory
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(points_hf_sdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    // opt in to > 48 KB dynamic shared memory; only when the requirement grows (a monotonic high-water mark --
+    // the one piece of process-wide state, benign: setting the attribute again is idempotent)
+    static std::atomic<size_t> high_water{0};
+    if (smem > high_water.load(std::memory_order_relaxed)) {
+      cudaError_t e = cudaFuncSetAttribute(points_hf_sdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      high_water.store(smem, std::memory_order_relaxed);
+    }
   }
   int64_t gx = (n_points + 255) / 256;
   if (gx > 4096) gx = 4096;
@@ -301,8 +309,14 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
   const size_t smem = terrain_smem_bytes(terrain) + (S * (1 + 3) + LOSS_WARPS * (S * 7 + PARC_MAX_BODIES * 9)) * sizeof(float);
   if (smem > 200 * 1024) return PARC_E_SIZE;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(body_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    // opt in to > 48 KB dynamic shared memory; only when the requirement grows (a monotonic high-water mark --
+    // the one piece of process-wide state, benign: setting the attribute again is idempotent)
+    static std::atomic<size_t> high_water{0};
+    if (smem > high_water.load(std::memory_order_relaxed)) {
+      cudaError_t e = cudaFuncSetAttribute(body_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      high_water.store(smem, std::memory_order_relaxed);
+    }
   }
   // one warp per frame, LOSS_WARPS frames in flight per CTA; amortise the terrain staging over several
   // rounds when there is plenty of work, keep the grid wide when there is not

@@ -7,6 +7,8 @@
 //   util/geom_util.py:80-111                          get_box_points_batch
 // and the front end every one of them repeats: exp_map_to_quat + dof_to_rot + forward_kinematics on
 // frames laid out [root_pos(3) | root exp-map(3) | joint DoFs(D)].
+#include <atomic>
+
 #include "parc_common.cuh"
 #include "parc_rotations.cuh"
 #include "parc_sdf.cuh"
@@ -297,8 +299,14 @@ extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frame
                        (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words)) * 4;
   if (smem > 200 * 1024) return PARC_E_SIZE;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(clip_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    // opt in to > 48 KB dynamic shared memory; only when the requirement grows (a monotonic high-water mark --
+    // the one piece of process-wide state, benign: setting the attribute again is idempotent)
+    static std::atomic<size_t> high_water{0};
+    if (smem > high_water.load(std::memory_order_relaxed)) {
+      cudaError_t e = cudaFuncSetAttribute(clip_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      high_water.store(smem, std::memory_order_relaxed);
+    }
   }
   int64_t rounds = (batch * frames_per_clip) / ((int64_t)148 * 8 * LABEL_WARPS);
   if (rounds < 1) rounds = 1;

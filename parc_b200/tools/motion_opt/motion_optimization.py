@@ -1,17 +1,22 @@
-"""motion_terrain_contact_loss: the per-clip objective of the kinematic motion optimiser.
+"""Kinematic motion optimisation against the terrain: the per-clip objective and its Adam loop.
 
-Drop-in for the reference's `tools/motion_opt/motion_optimization.py::motion_terrain_contact_loss`
-(:183-395): same arguments, returns (loss, losses-dict keyed by LossType).  The penetration and contact
-terms (:241-272) -- the part that dominates the reference's 21 s / iteration -- run forward AND backward
-in the fused kernel of csrc/body_loss.cu, entered through `ops.body_loss`; FK, DoF->quaternion and
-exp-map->quaternion are the CUDA operators of csrc/fk.cu with hand-written VJPs.  The remaining cheap
-regularisers (tracking, smoothness, sliding, jerk, body constraints) are elementwise torch expressions
-over the kernels' outputs (SURVEY.md section 8(f) row 2 lists fusing them as the next step).
+Drop-in for the reference's `tools/motion_opt/motion_optimization.py`: `motion_terrain_contact_loss`
+(:183-395) and `motion_contact_optimization` (:404-500), same arguments and returns.
+
+* The penetration and contact terms (:241-272) -- the part that dominates the reference's 21 s / iteration --
+  run forward AND backward in the fused kernel of csrc/body_loss.cu (`ops.body_loss`); FK, DoF->quaternion and
+  exp-map->quaternion are the CUDA operators of csrc/fk.cu with hand-written VJPs.
+* The remaining cheap regularisers (tracking, smoothness, sliding, jerk, body constraints) are elementwise torch
+  expressions over the kernels' outputs.
+* `motion_contact_optimization` captures ONE whole iteration (kernels + regularisers + backward + Adam step) in a
+  CUDA graph and replays it `num_iters` times; the host only synchronises on logging iterations.  The reference
+  calls `.item()` on seven loss terms every iteration.
 """
 from __future__ import annotations
 
 import enum
-from typing import List
+import time
+from typing import List, Optional
 
 import torch
 
@@ -40,24 +45,28 @@ class BodyConstraint:
     constraint_point = None
 
 
+def _terrain_desc(terrain, base_z=-10.0):
+    """Host-side preparation (one tiny D2H of dxdy): kept out of the captured iteration."""
+    return ops.make_terrain_batch(terrain.hf, terrain.min_point, terrain.dxdy.detach().cpu().tolist(), base_z=base_z)
+
+
 def pen_contact_loss(tgt_root_pos, tgt_root_rot_quat, tgt_joint_rot, contacts, terrain, body_points, char_model,
-                     w_penetration: float, w_contact: float, base_z: float = -10.0):
+                     w_penetration: float, w_contact: float, base_z: float = -10.0, _tb=None, _pts=None):
     """The two heightfield terms for one clip [F,...]: returns (weighted sum, pen, contact) with
     pen / contact detached (they are only logged by the reference, :366-373)."""
-    tb = ops.make_terrain_batch(terrain.hf, terrain.min_point, terrain.dxdy.detach().cpu().tolist(), base_z=base_z)
-    pts = body_points_desc(char_model, body_points)
+    tb = _tb if _tb is not None else _terrain_desc(terrain, base_z)
+    pts = _pts if _pts is not None else body_points_desc(char_model, body_points)
     total, pen, con = ops.body_loss(char_model.c_model(), pts, tb, tgt_root_pos.unsqueeze(0),
                                     tgt_root_rot_quat.unsqueeze(0), tgt_joint_rot.unsqueeze(0),
                                     contacts.unsqueeze(0), w_penetration, w_contact)
     return total[0], pen[0], con[0]
 
 
-def motion_terrain_contact_loss(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos, src_root_rot_quat,
-                                src_joint_rot, src_body_vels, src_body_rot_vels, contacts, terrain,
-                                body_points: List[torch.Tensor], char_model, w_root_pos: float, w_root_rot: float,
-                                w_joint_rot: float, w_smoothness: float, w_penetration: float, w_contact: float,
-                                w_sliding: float, w_body_constraints: float, w_jerk: float, body_constraints: list,
-                                max_jerk: float):
+def _loss_terms(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos, src_root_rot_quat, src_joint_rot,
+                src_body_vels, src_body_rot_vels, contacts, body_points, char_model, w, body_constraints, max_jerk,
+                tb, pts):
+    """All terms as tensors (no host synchronisation, graph-capturable).  `w` = dict of the nine weights.
+    Returns (weighted loss, dict LossType -> 0-dim tensor or python number)."""
     root_pos_loss = torch.sum(torch.square(tgt_root_pos - src_root_pos))
 
     tgt_root_rot_quat = ops.exp_map_to_quat(tgt_root_rot)
@@ -77,9 +86,10 @@ def motion_terrain_contact_loss(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_r
     frame_change_in_contact = torch.clamp(torch.minimum(contacts[1:], contacts[:-1]), min=0.0)
 
     # --- heightfield terms: fused CUDA forward + backward (:241-272) ---
+    w_contact = w["w_contact"]
     hf_total, penetration_loss, contact_loss = pen_contact_loss(
-        tgt_root_pos, tgt_root_rot_quat, tgt_joint_rot, contacts, terrain, body_points, char_model,
-        w_penetration, w_contact if w_contact != 0.0 else 0.0)
+        tgt_root_pos, tgt_root_rot_quat, tgt_joint_rot, contacts, None, body_points, char_model, w["w_penetration"],
+        w_contact, _tb=tb, _pts=pts)
     contact_logged = contact_loss if w_contact != 0.0 else 0.0
 
     # --- body constraints (:286-332) ---
@@ -105,13 +115,14 @@ def motion_terrain_contact_loss(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_r
                     body_constraint_loss = body_constraint_loss + torch.sum(torch.clamp(diff, min=0.0))
                 else:
                     continue
+                # a constrained body does not also pay for sliding / smoothness on those frames
                 body_vel_err_sq = body_vel_err_sq.clone()
                 body_vel_err_sq[s:e + 1, b] *= 0.0
                 body_rot_vel_err_sq = body_rot_vel_err_sq.clone()
                 body_rot_vel_err_sq[s:e + 1, b] *= 0.0
 
     # --- sliding: pseudo-Huber on contact bodies (:339-346) ---
-    if w_sliding != 0.0:
+    if w["w_sliding"] != 0.0:
         c, c2 = 0.03, 0.0009
         sliding_loss = torch.sum((torch.sqrt(torch.sum(body_vel_err_sq, dim=-1) + c2) - c) * frame_change_in_contact) \
             + torch.sum((torch.sqrt(body_rot_vel_err_sq + c2) - c) * frame_change_in_contact)
@@ -124,19 +135,139 @@ def motion_terrain_contact_loss(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_r
     dt = 1.0 / 30.0
     jerk_loss = torch.sum(torch.clamp(jerk_mag - max_jerk * (dt ** 3), min=0.0))
 
-    as_float = lambda v: v.item() if isinstance(v, torch.Tensor) else v
-    losses = {
-        LossType.ROOT_POS_LOSS: root_pos_loss.item(),
-        LossType.ROOT_ROT_LOSS: root_rot_loss.item(),
-        LossType.JOINT_ROT_LOSS: joint_rot_loss.item(),
-        LossType.SMOOTHNESS_LOSS: smoothness_loss.item(),
-        LossType.PENETRATION_LOSS: penetration_loss.item(),
-        LossType.CONTACT_LOSS: as_float(contact_logged),
-        LossType.SLIDING_LOSS: as_float(sliding_loss),
-        LossType.JERK_LOSS: jerk_loss.item(),
-        LossType.BODY_CONSTRAINT_LOSS: as_float(body_constraint_loss),
+    terms = {
+        LossType.ROOT_POS_LOSS: root_pos_loss, LossType.ROOT_ROT_LOSS: root_rot_loss,
+        LossType.JOINT_ROT_LOSS: joint_rot_loss, LossType.SMOOTHNESS_LOSS: smoothness_loss,
+        LossType.PENETRATION_LOSS: penetration_loss, LossType.CONTACT_LOSS: contact_logged,
+        LossType.SLIDING_LOSS: sliding_loss, LossType.JERK_LOSS: jerk_loss,
+        LossType.BODY_CONSTRAINT_LOSS: body_constraint_loss,
     }
-    loss = w_root_pos * root_pos_loss + w_root_rot * root_rot_loss + w_joint_rot * joint_rot_loss \
-        + w_smoothness * smoothness_loss + hf_total + w_sliding * sliding_loss \
-        + w_body_constraints * body_constraint_loss + w_jerk * jerk_loss
-    return loss, losses
+    loss = w["w_root_pos"] * root_pos_loss + w["w_root_rot"] * root_rot_loss + w["w_joint_rot"] * joint_rot_loss \
+        + w["w_smoothness"] * smoothness_loss + hf_total + w["w_sliding"] * sliding_loss \
+        + w["w_body_constraints"] * body_constraint_loss + w["w_jerk"] * jerk_loss
+    return loss, terms
+
+
+def _to_floats(terms):
+    return {k: (v.item() if isinstance(v, torch.Tensor) else v) for k, v in terms.items()}
+
+
+def motion_terrain_contact_loss(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos, src_root_rot_quat,
+                                src_joint_rot, src_body_vels, src_body_rot_vels, contacts, terrain,
+                                body_points: List[torch.Tensor], char_model, w_root_pos: float, w_root_rot: float,
+                                w_joint_rot: float, w_smoothness: float, w_penetration: float, w_contact: float,
+                                w_sliding: float, w_body_constraints: float, w_jerk: float, body_constraints: list,
+                                max_jerk: float):
+    """-> (loss tensor, dict LossType -> float).  Ref :183-395."""
+    w = dict(w_root_pos=w_root_pos, w_root_rot=w_root_rot, w_joint_rot=w_joint_rot, w_smoothness=w_smoothness,
+             w_penetration=w_penetration, w_contact=w_contact, w_sliding=w_sliding,
+             w_body_constraints=w_body_constraints, w_jerk=w_jerk)
+    loss, terms = _loss_terms(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos, src_root_rot_quat,
+                              src_joint_rot, src_body_vels, src_body_rot_vels, contacts, body_points, char_model, w,
+                              body_constraints, max_jerk, _terrain_desc(terrain), body_points_desc(char_model, body_points))
+    return loss, _to_floats(terms)
+
+
+class _TextLogger:
+    """Minimal stand-in for the reference's WandbLogger (wandb / tensorboard plumbing is out of scope): prints the
+    table and, if asked, appends it to `log_file`."""
+
+    def __init__(self, log_file: Optional[str]):
+        self._rows = []
+        self._file = open(log_file, "w") if log_file is not None else None
+
+    def log(self, key, val):
+        self._rows.append((key, val))
+
+    def flush(self, quiet=False):
+        line = "  ".join(f"{k}={v:.6g}" if isinstance(v, float) else f"{k}={v}" for k, v in self._rows)
+        if not quiet:
+            print(line)
+        if self._file is not None:
+            self._file.write(line + "\n")
+        self._rows = []
+
+    def close(self):
+        if self._file is not None:
+            self._file.close()
+
+
+def motion_contact_optimization(src_frames: torch.Tensor, contacts: torch.Tensor, body_points: list, terrain,
+                                char_model, num_iters: int, step_size: float, w_root_pos: float, w_root_rot: float,
+                                w_joint_rot: float, w_smoothness: float, w_penetration: float, w_contact: float,
+                                w_sliding: float, w_body_constraints: float, w_jerk: float, body_constraints: list,
+                                max_jerk: float, exp_name: str = "", use_wandb: bool = False, log_file: str = None,
+                                use_cuda_graph: bool = True, quiet: bool = False):
+    """Adam over (root_pos, root exp-map, joint DoFs) so that the clip stops penetrating / floating above the
+    terrain while staying close to `src_frames`.  -> optimised frames [F, 6+D].  Ref :404-500.
+    `use_wandb` is accepted and ignored (logging back ends are out of scope)."""
+    start_time = time.time()
+    D = char_model.get_dof_size()
+    src_root_pos = src_frames[:, 0:3]
+    src_root_rot = src_frames[:, 3:6]
+    src_joint_dof = src_frames[:, 6:6 + D]
+    with torch.no_grad():
+        src_root_rot_quat = ops.exp_map_to_quat(src_root_rot)
+        src_joint_rot = char_model.dof_to_rot(src_joint_dof)
+        src_body_pos, src_body_rot = char_model.forward_kinematics(src_root_pos, src_root_rot_quat, src_joint_rot)
+        src_body_vels = src_body_pos[1:] - src_body_pos[:-1]
+        src_body_rot_vels = torch_util.quat_diff_angle(src_body_rot[1:], src_body_rot[:-1])
+
+    leaves = [src_root_pos.clone().requires_grad_(True), src_root_rot.clone().requires_grad_(True),
+              src_joint_dof.clone().requires_grad_(True)]
+    w = dict(w_root_pos=w_root_pos, w_root_rot=w_root_rot, w_joint_rot=w_joint_rot, w_smoothness=w_smoothness,
+             w_penetration=w_penetration, w_contact=w_contact, w_sliding=w_sliding,
+             w_body_constraints=w_body_constraints, w_jerk=w_jerk)
+    tb = _terrain_desc(terrain)
+    pts = body_points_desc(char_model, body_points)
+    # capturable=True keeps Adam's step counter on the device so optimizer.step() can live inside a CUDA graph
+    optimizer = torch.optim.Adam(leaves, lr=step_size, capturable=use_cuda_graph)
+
+    def iteration():
+        optimizer.zero_grad(set_to_none=False)
+        loss, terms = _loss_terms(leaves[0], leaves[1], leaves[2], src_root_pos, src_root_rot_quat, src_joint_rot,
+                                  src_body_vels, src_body_rot_vels, contacts, body_points, char_model, w,
+                                  body_constraints, max_jerk, tb, pts)
+        loss.backward()
+        optimizer.step()
+        return loss, terms
+
+    logger = _TextLogger(log_file)
+    log_iter_stride = 25
+
+    def log(it, loss, terms):
+        logger.log("Iteration", it)
+        logger.log("Time (min)", (time.time() - start_time) / 60.0)
+        logger.log("TOTAL WEIGHTED LOSS", loss.item())
+        for key, val in _to_floats(terms).items():
+            logger.log(key.name, val)
+        logger.flush(quiet)
+
+    it = 0
+    if use_cuda_graph and num_iters > 3:
+        # two eager iterations on a side stream (allocator warm-up, Adam state creation), then capture one
+        side = torch.cuda.Stream(device=src_frames.device)
+        side.wait_stream(torch.cuda.current_stream(src_frames.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                loss, terms = iteration()
+                if it % log_iter_stride == 0:
+                    log(it, loss, terms)
+                it += 1
+        torch.cuda.current_stream(src_frames.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_loss, g_terms = iteration()
+        while it < num_iters:                     # capture records but does not execute: replay #1 is iteration 2
+            graph.replay()
+            if it % log_iter_stride == 0:
+                log(it, g_loss, g_terms)
+            it += 1
+    else:
+        while it < num_iters:
+            loss, terms = iteration()
+            if it % log_iter_stride == 0:
+                log(it, loss, terms)
+            it += 1
+    logger.close()
+    return torch.cat([t.detach() for t in leaves], dim=-1)

@@ -643,3 +643,74 @@ def test_generic_21_body_character_vs_oracle(O):
         assert_close_normwise(a, b, what=f"generic grad {nm}")
     bp2, br2 = ops.frames_fk(m, fr.cuda())
     assert_close(bp2, cpu[0], what="generic frames_fk pos")
+
+
+# ----------------------------------------------------------------------------------------- full objective + Adam loop (8(f)-2)
+def _motion_opt_case(gpu_model):
+    from parc_b200.tools.motion_opt.motion_optimization import BodyConstraint
+    g = golden("motion_opt_golden.npz")
+    W = {str(k): float(v) for k, v in zip(g["weight_names"], g["weights"])}
+    bcs = [[] for _ in range(15)]
+    for b, s_, e_, pt in zip(g["bc_body"], g["bc_start"], g["bc_end"], g["bc_point"]):
+        c = BodyConstraint()
+        c.start_frame_idx, c.end_frame_idx, c.constraint_point = int(s_), int(e_), dev(pt)
+        bcs[int(b)].append(c)
+    return g, W, bcs
+
+
+def test_full_objective_with_body_constraints_vs_golden(gpu_model):
+    from parc_b200.tools.motion_opt.motion_optimization import LossType, motion_terrain_contact_loss
+    from parc_b200.util import geom_util
+    g, W, bcs = _motion_opt_case(gpu_model)
+    pts = geom_util.get_char_point_samples(gpu_model)
+    fr = dev(g["src_frames"])
+    a, b, c = (fr[:, 0:3].clone().requires_grad_(True), fr[:, 3:6].clone().requires_grad_(True),
+               fr[:, 6:].clone().requires_grad_(True))
+    loss, ld = motion_terrain_contact_loss(a, b, c, dev(g["src_root_pos"]), dev(g["src_root_quat"]), dev(g["src_joint_rot"]),
+                                           dev(g["src_body_vels"]), dev(g["src_body_rot_vels"]), dev(g["contacts"]),
+                                           _civ_terrain(), pts, gpu_model, body_constraints=bcs, max_jerk=1000.0, **W)
+    loss.backward()
+    assert_close(loss, g["loss"], what="full objective")
+    assert_close(torch.tensor(ld[LossType.BODY_CONSTRAINT_LOSS]), g["body_constraint_term"], what="body constraint term")
+    assert ld[LossType.BODY_CONSTRAINT_LOSS] > 0
+    assert_close_normwise(a.grad, g["grad_root_pos"], what="full grad root_pos")
+    assert_close_normwise(b.grad, g["grad_root_exp"], what="full grad root_rot")
+    assert_close_normwise(c.grad, g["grad_joint_dof"], what="full grad joint_dof")
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_motion_contact_optimization_vs_golden(gpu_model, use_graph):
+    """4 Adam iterations of the reference's loop (tools/motion_opt/motion_optimization.py:404-500); the CUDA-graph
+    replay path and the eager path must both land on the reference's frames."""
+    from parc_b200.tools.motion_opt.motion_optimization import motion_contact_optimization
+    from parc_b200.util import geom_util
+    g, W, bcs = _motion_opt_case(gpu_model)
+    pts = geom_util.get_char_point_samples(gpu_model)
+    src = dev(g["src_frames"])
+    out = motion_contact_optimization(src.clone(), dev(g["contacts"]), pts, _civ_terrain(), gpu_model, num_iters=4,
+                                      step_size=0.001, body_constraints=bcs, max_jerk=1000.0, exp_name="t",
+                                      use_wandb=False, log_file=None, use_cuda_graph=use_graph, quiet=True, **W)
+    assert out.shape == (8, 34)
+    upd, exp_upd = (out - src).cpu(), torch.tensor(g["adam4_frames"] - g["src_frames"])
+    assert exp_upd.abs().max() > 1e-3                              # the loop actually moved the pose
+    # Adam normalises every gradient to ~+-lr per step.  Leaves whose gradient is decisive moved ~4 * lr and must
+    # match tightly; leaves whose true gradient cancels to rounding level (|g| ~ eps = 1e-8) get g / (|g| + eps),
+    # which turns last-bit differences into a fraction of one step -- in the reference just as much.
+    decisive = exp_upd.abs() >= 2e-3
+    assert decisive.float().mean() > 0.5
+    assert ((upd - exp_upd).abs()[decisive] <= 0.02 * exp_upd.abs()[decisive]).all(), "decisive leaves differ"
+    assert (upd - exp_upd).abs().max() <= 0.3e-3, "a noise-level leaf moved by more than 0.3 of one step"
+    assert torch.equal(src, dev(g["src_frames"]))                  # the input is not modified
+
+    # and the objective at our optimum equals the objective at the reference's optimum
+    from parc_b200.tools.motion_opt.motion_optimization import motion_terrain_contact_loss
+
+    def objective(fr):
+        with torch.no_grad():
+            return motion_terrain_contact_loss(fr[:, 0:3], fr[:, 3:6], fr[:, 6:], dev(g["src_root_pos"]), dev(g["src_root_quat"]),
+                                               dev(g["src_joint_rot"]), dev(g["src_body_vels"]), dev(g["src_body_rot_vels"]),
+                                               dev(g["contacts"]), _civ_terrain(), pts, gpu_model, body_constraints=bcs,
+                                               max_jerk=1000.0, **W)[0]
+    l_ours, l_ref, l_src = objective(out), objective(dev(g["adam4_frames"])), objective(src)
+    assert l_ref < l_src and l_ours < l_src
+    assert_close(l_ours, l_ref, rtol=2e-3, what="objective after 4 iterations")

@@ -20,7 +20,7 @@ def test_pin_report_is_all_ok():
     import os
     from conftest import GOLDEN
     lines = open(os.path.join(GOLDEN, "PIN_REPORT.txt")).read().splitlines()[1:]
-    assert len(lines) >= 50 and all(l.startswith("OK") for l in lines)
+    assert len(lines) >= 60 and all(l.startswith("OK") for l in lines)     # 'OK ' = torch.equal, 'OK~' = tolerance pin
 
 
 def test_tables(oracle_model):
