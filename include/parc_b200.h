@@ -190,6 +190,12 @@ int parc_dof_to_rot_fwd(const float* dof, int64_t n, const ParcCharModel* model,
 int parc_dof_to_rot_bwd(const float* dof, const float* g_joint_rot, int64_t n, const ParcCharModel* model,
                         float* g_dof, void* stream);
 
+/* KinCharModel.rot_to_dof (anim/kin_char_model.py:493-507; Joint.rot_to_dof :79-100): joint quaternions
+ * [n,J-1,4] -> DoFs [n,D] (hinge: signed angle about the joint axis; spherical: exp-map).  dof_out must be
+ * zero-initialised by the caller for joints without DoFs to read as 0 (all D columns belong to some joint, so
+ * in practice every element is written).  Forward only. */
+int parc_rot_to_dof(const float* joint_rot, int64_t n, const ParcCharModel* model, float* dof_out, void* stream);
+
 /* util/torch_util.py:414-419 exp_map_to_quat and its VJP (root rotation leaf of the optimiser). */
 int parc_exp_map_to_quat_fwd(const float* exp_map, int64_t n, float* quat, void* stream);
 int parc_exp_map_to_quat_bwd(const float* exp_map, const float* g_quat, int64_t n, float* g_exp_map,

@@ -117,6 +117,7 @@ SIGNATURES = {
     "parc_fk_bwd": (C.c_int, [_V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V, _V, _V]),
     "parc_dof_to_rot_fwd": (C.c_int, [_V, _I64, _P(ParcCharModel), _V, _V]),
     "parc_dof_to_rot_bwd": (C.c_int, [_V, _V, _I64, _P(ParcCharModel), _V, _V]),
+    "parc_rot_to_dof": (C.c_int, [_V, _I64, _P(ParcCharModel), _V, _V]),
     "parc_exp_map_to_quat_fwd": (C.c_int, [_V, _I64, _V, _V]),
     "parc_exp_map_to_quat_bwd": (C.c_int, [_V, _V, _I64, _V, _V]),
     "parc_hf_sample": (C.c_int, [_P(ParcHeightfield), _V, _I64, _V, _V, _V]),

@@ -361,8 +361,12 @@ class KinCharModel:
         return self._dof_index_cache
 
     def rot_to_dof(self, rot):
-        """joint_rot [...,J-1,4] -> dof [...,D] (ref :493-507), all joints converted in one pass of
-        torch ops on the tensor's device instead of a per-joint python loop."""
+        """joint_rot [...,J-1,4] -> dof [...,D] (ref :493-507).  CUDA tensors without autograd go through
+        `parc_rot_to_dof`; when gradients are needed (or at load time on the host) all joints are converted in
+        one pass of torch ops instead of the reference's per-joint python loop."""
+        if rot.is_cuda and not (rot.requires_grad and torch.is_grad_enabled()):
+            return ops.rot_to_dof(self.c_model(), rot)              # one kernel launch (csrc/fk.cu)
+        # differentiable / host-side use: the same arithmetic as torch ops on the tensor's device
         hj, hd, sj, scols, axes = self._dof_index(rot.device)
         dof = torch.zeros(list(rot.shape[:-2]) + [self._dof_size], device=rot.device, dtype=rot.dtype)
         axis, angle = torch_util.quat_to_axis_angle(rot)

@@ -77,6 +77,35 @@ dof_to_rot_bwd_kernel(const float* __restrict__ dof, const float* __restrict__ g
   }
 }
 
+// joint_rot [N,J-1,4] -> dof [N,D]: KinCharModel.rot_to_dof (anim/kin_char_model.py:493-507) with
+// Joint.rot_to_dof (:79-100) and quat_to_axis_angle / quat_to_exp_map (util/torch_util.py:68-88, :346-351).
+// One thread per (pose, joint); forward only.
+__global__ void __launch_bounds__(256)
+rot_to_dof_kernel(const float* __restrict__ jr, int64_t n, const __grid_constant__ ParcCharModel m,
+                  float* __restrict__ dof) {
+  const int Jm1 = m.num_bodies - 1;
+  const int64_t total = n * Jm1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / Jm1;
+    const int j = (int)(i - f * Jm1) + 1;
+    const int jt = m.joint_type[j];
+    if (jt != PARC_JOINT_HINGE && jt != PARC_JOINT_SPHERICAL) continue;
+    float4 q = reinterpret_cast<const float4*>(jr)[i];
+    if (q.w < 0.0f) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }        // quat_pos
+    const float len = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+    float angle = 2.0f * atan2f(len, q.w);
+    float3 axis = make_float3(q.x / len, q.y / len, q.z / len);
+    if (!(len > 1e-5f)) { angle = 0.0f; axis = make_float3(0.0f, 0.0f, 1.0f); }
+    float* o = dof + f * m.dof_size + m.dof_idx[j];
+    if (jt == PARC_JOINT_HINGE) {
+      const float d = m.joint_axis[j][0] * axis.x + m.joint_axis[j][1] * axis.y + m.joint_axis[j][2] * axis.z;
+      o[0] = d < 0.0f ? -angle : angle;
+    } else {
+      o[0] = angle * axis.x; o[1] = angle * axis.y; o[2] = angle * axis.z;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FK forward / VJP, one warp per character, lane b = body b
 // ------------------------------------------------------------------------------------------------
@@ -257,5 +286,19 @@ extern "C" int parc_exp_map_to_quat_bwd(const float* exp_map, const float* g_qua
   if (!aligned16(g_quat)) return PARC_E_ALIGN;
   if (n == 0) return PARC_OK;
   exp_map_bwd_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(exp_map, g_quat, n, g_exp_map);
+  return check_launch();
+}
+
+extern "C" int parc_rot_to_dof(const float* joint_rot, int64_t n, const ParcCharModel* model, float* dof_out,
+                               void* stream) {
+  if (!model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (n < 0) return PARC_E_SIZE;
+  if (n == 0 || model->num_bodies < 2 || model->dof_size == 0) return PARC_OK;
+  if (!joint_rot || !dof_out) return PARC_E_NULL;
+  if (!aligned16(joint_rot)) return PARC_E_ALIGN;
+  rot_to_dof_kernel<<<flat_grid(n * (model->num_bodies - 1)), 256, 0, (cudaStream_t)stream>>>(joint_rot, n, *model,
+                                                                                             dof_out);
   return check_launch();
 }

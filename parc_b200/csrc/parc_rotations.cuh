@@ -14,14 +14,16 @@ __device__ __forceinline__ float4 normalize4(const float4& u, float& nrm_out) {
   const float n = sqrtf(u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w);
   const float d = fmaxf(n, 1e-9f);                  // util/torch_util.py:12 clamp(min=eps)
   nrm_out = d;
-  return make_float4(u.x / d, u.y / d, u.z / d, u.w / d);
+  const float r = __frcp_rn(d);                     // value path: one reciprocal instead of four divisions
+  return make_float4(u.x * r, u.y * r, u.z * r, u.w * r);
 }
 
 __device__ __forceinline__ float3 normalize3(const float3& a, float& nrm_out) {
   const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
   const float d = fmaxf(n, 1e-9f);
   nrm_out = d;
-  return make_float3(a.x / d, a.y / d, a.z / d);
+  const float r = __frcp_rn(d);
+  return make_float3(a.x * r, a.y * r, a.z * r);
 }
 
 // util/torch_util.py:311-317
@@ -54,15 +56,29 @@ __device__ __forceinline__ void axis_angle_to_quat_vjp(const float3& axis, float
   g_axis = make_float3((gn.x - n.x * ngn) / an, (gn.y - n.y * ngn) / an, (gn.z - n.z * ngn) / an);
 }
 
-// util/torch_util.py:394-419
-__device__ __forceinline__ float4 exp_map_to_quat(const float3& e) {
+// normalize_angle(a) = atan2(sin a, cos a) for a >= 0 (util/torch_util.py:4-7): the identity on [0, pi] up to
+// an ulp, so the three transcendental calls are only paid for angles beyond pi.
+__device__ __forceinline__ float wrap_angle_nonneg(float a) {
+  return a <= 3.14159265f ? a : atan2f(sinf(a), cosf(a));
+}
+
+// util/torch_util.py:394-412: exp-map -> (axis, angle) with the reference's wrap and small-angle mask
+__device__ __forceinline__ void exp_map_to_axis_angle(const float3& e, float3& axis, float& ang) {
   const float a = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
-  float3 axis = make_float3(e.x / a, e.y / a, e.z / a);
-  float ang = atan2f(sinf(a), cosf(a));
+  const float r = 1.0f / a;                          // inf for a == 0: masked below, like the reference's NaN axis
+  axis = make_float3(e.x * r, e.y * r, e.z * r);
+  ang = wrap_angle_nonneg(a);
   if (!(fabsf(ang) > 1e-5f)) {
     ang = 0.0f;
     axis = make_float3(0.0f, 0.0f, 1.0f);
   }
+}
+
+// util/torch_util.py:414-419
+__device__ __forceinline__ float4 exp_map_to_quat(const float3& e) {
+  float3 axis;
+  float ang;
+  exp_map_to_axis_angle(e, axis, ang);
   return axis_angle_to_quat(axis, ang);
 }
 
@@ -70,27 +86,35 @@ __device__ __forceinline__ float4 exp_map_to_quat(const float3& e) {
 // SURVEY F8d); here the masked branch returns a zero gradient instead (documented divergence).
 __device__ __forceinline__ float3 exp_map_to_quat_vjp(const float3& e, const float4& g) {
   const float a = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
-  const float sa = sinf(a), ca = cosf(a);
-  const float ang = atan2f(sa, ca);
+  const float ang = wrap_angle_nonneg(a);
   if (!(fabsf(ang) > 1e-5f)) return make_float3(0.0f, 0.0f, 0.0f);
   const float3 axis = make_float3(e.x / a, e.y / a, e.z / a);
   float3 g_axis;
   float g_ang;
   axis_angle_to_quat_vjp(axis, ang, g, g_axis, g_ang);
-  // ang = atan2(sin a, cos a): d ang / d a = (ca*ca + sa*sa) / (sa*sa + ca*ca)
-  const float den = sa * sa + ca * ca;
-  float g_a = g_ang * (ca / den) * ca + g_ang * (sa / den) * sa;
+  // ang = atan2(sin a, cos a): d ang / d a = (cos^2 + sin^2) / (sin^2 + cos^2) = 1
+  float g_a = g_ang;
   // axis = e / a
   g_a -= (g_axis.x * e.x + g_axis.y * e.y + g_axis.z * e.z) / (a * a);
   return make_float3(g_axis.x / a + g_a * e.x / a, g_axis.y / a + g_a * e.y / a, g_axis.z / a + g_a * e.z / a);
 }
 
 
-// Joint j's quaternion from the pose's DoF vector (anim/kin_char_model.py:57-77).
+// Joint j's quaternion from the pose's DoF vector (anim/kin_char_model.py:57-77).  Hinge and spherical joints
+// (and the root's exp-map) share ONE axis_angle_to_quat call site so that lanes holding different joint types
+// do not serialise two copies of the transcendental chain.
 __device__ __forceinline__ float4 joint_dof_to_quat(int joint_type, const float* __restrict__ d, const float* axis) {
-  if (joint_type == PARC_JOINT_HINGE) return axis_angle_to_quat(make_float3(axis[0], axis[1], axis[2]), d[0]);
-  if (joint_type == PARC_JOINT_SPHERICAL) return exp_map_to_quat(make_float3(d[0], d[1], d[2]));
-  return make_float4(0.f, 0.f, 0.f, 1.f);
+  float3 ax = make_float3(0.0f, 0.0f, 1.0f);
+  float ang = 0.0f;
+  const bool rotates = joint_type == PARC_JOINT_HINGE || joint_type == PARC_JOINT_SPHERICAL;
+  if (joint_type == PARC_JOINT_HINGE) {
+    ax = make_float3(axis[0], axis[1], axis[2]);
+    ang = d[0];
+  } else if (joint_type == PARC_JOINT_SPHERICAL) {
+    exp_map_to_axis_angle(make_float3(d[0], d[1], d[2]), ax, ang);
+  }
+  const float4 q = axis_angle_to_quat(ax, ang);
+  return rotates ? q : make_float4(0.f, 0.f, 0.f, 1.f);
 }
 
 }  // namespace parc

@@ -190,8 +190,7 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
             if obs_tmpl is not None:
                 assert hf is not None
                 require_cuda(hf.hf, obs_tmpl)
-                tm = f32c(obs_tmpl)
-                res["_tmpl_keepalive"] = tm
+                tm = f32c(obs_tmpl)      # if this made a copy, the allocator's stream ordering keeps it valid
                 hfs, obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
                 obs_ptr = buf("obs", (N, int(tm.shape[0]))).data_ptr()
             rc = lib.parc_motion_query(C.byref(tb), ids.data_ptr(), times.data_ptr(), N, C.byref(model),
@@ -204,7 +203,6 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
             rc = lib.parc_get_motion_frame(C.byref(tb), ids.data_ptr(), fi.data_ptr(), N, C.byref(model),
                                            C.byref(fo), C.byref(fk) if want_fk else None, stream_ptr(dev))
             check(rc, "parc_get_motion_frame")
-    res.pop("_tmpl_keepalive", None)
     return res
 
 
@@ -366,6 +364,19 @@ class _DofToRot(torch.autograd.Function):
 
 def dof_to_rot(model: ParcCharModel, dof):
     return _DofToRot.apply(dof, model)
+
+
+def rot_to_dof(model: ParcCharModel, joint_rot: torch.Tensor) -> torch.Tensor:
+    """joint_rot [...,J-1,4] -> dof [...,D]; one launch, forward only (no autograd)."""
+    require_cuda(joint_rot)
+    lead = joint_rot.shape[:-2]
+    jr = f32c(joint_rot.detach()).reshape(-1, model.num_bodies - 1, 4)
+    n = jr.shape[0]
+    out = torch.zeros((n, model.dof_size), dtype=torch.float32, device=jr.device)
+    with torch.cuda.device(jr.device):
+        rc = _lib.load().parc_rot_to_dof(jr.data_ptr(), n, C.byref(model), out.data_ptr(), stream_ptr(jr.device))
+    check(rc, "parc_rot_to_dof")
+    return out.reshape(*lead, model.dof_size)
 
 
 class _ExpMapToQuat(torch.autograd.Function):

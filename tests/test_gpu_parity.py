@@ -209,7 +209,14 @@ def test_dof_to_rot_and_back(gpu_model):
     dof = dev(civ["frames"][:, 6:])
     jr = gpu_model.dof_to_rot(dof)
     assert_close(jr, g["joint_rot"], what="dof_to_rot")
-    assert_close(gpu_model.rot_to_dof(dev(g["joint_rot"])), g["dof_back"], atol=2e-6, what="rot_to_dof")
+    assert_close(gpu_model.rot_to_dof(dev(g["joint_rot"])), g["dof_back"], atol=2e-6, what="rot_to_dof (kernel)")
+    jr_g = dev(g["joint_rot"]).requires_grad_(True)
+    d_t = gpu_model.rot_to_dof(jr_g)                                        # autograd path (torch ops)
+    assert d_t.requires_grad
+    assert_close(d_t, g["dof_back"], atol=2e-6, what="rot_to_dof (torch path)")
+    assert gpu_model.rot_to_dof(dev(g["joint_rot"]).view(2, 127, 14, 4)).shape == (2, 127, 28)
+    ident = torch.zeros(3, 14, 4, device="cuda"); ident[..., 3] = 1.0          # identity -> zero DoFs, no NaN
+    assert (gpu_model.rot_to_dof(ident) == 0).all()
     from parc_b200 import ops
     assert_close(ops.exp_map_to_quat(dev(civ["frames"][:, 3:6])), g["root_quat"], what="exp_map_to_quat")
     z = gpu_model.dof_to_rot(torch.zeros(2, 28, device="cuda"))       # exact zeros: identity, no NaN
