@@ -721,3 +721,84 @@ def test_motion_contact_optimization_vs_golden(gpu_model, use_graph):
     l_ours, l_ref, l_src = objective(out), objective(dev(g["adam4_frames"])), objective(src)
     assert l_ref < l_src and l_ours < l_src
     assert_close(l_ours, l_ref, rtol=2e-3, what="objective after 4 iterations")
+
+
+# ----------------------------------------------------------------------------------------- edge cases with hand-built tables
+def _pack_oracle_tables(gpu_model, tb):
+    from parc_b200 import ops
+    m = gpu_model.c_model()
+    rows, lay = ops.pack_frames(m, tb.root_pos.cuda(), tb.root_rot.cuda(), tb.joint_rot.cuda(), tb.contacts.cuda(),
+                                tb.root_vel.cuda(), tb.root_ang_vel.cuda(), tb.dof_vel.cuda())
+    meta = ops.build_clip_meta(tb.num_frames, tb.loop_modes, tb.start_idx, tb.lengths, tb.root_pos_delta, "cuda:0")
+    return m, ops.PackedTables(rows=rows, clips=meta, total_frames=int(rows.shape[0]), num_clips=int(tb.num_frames.shape[0]),
+                               layout=lay)
+
+
+def test_slerp_edge_cases_through_the_abi(gpu_model, O, oracle_model):
+    """Key-frame pairs crafted to hit every slerp branch of util/torch_util.py:443-468: identical quaternions
+    (|cos| >= 1 -> q0), antipodal ones (cos < 0 -> sign flip, then q0), half-angles around the sin < 1e-3 midpoint
+    threshold, large rotations; plus 2-frame CLAMP and WRAP clips, negative / huge / exact-boundary times.  The tables are edited AFTER loading, so they need not be reachable from DoF frames."""
+    from parc_b200 import ops
+    civ = golden("clip_civilization.npz")
+    clips = [O.Clip(civ["frames"][:6], civ["contacts"][:6], 30.0, O.CLAMP, 1.0),
+             O.Clip(civ["frames"][10:12], civ["contacts"][10:12], 30.0, O.CLAMP, 1.0),        # 2 frames: the minimum the
+                                                                                              # reference can load
+             O.Clip(civ["frames"][20:22], civ["contacts"][20:22], 30.0, O.WRAP, 1.0)]
+    tb = O.build_tables(oracle_model, clips)
+    gen = torch.Generator().manual_seed(77)
+    q = torch.nn.functional.normalize(torch.randn(14, 4, generator=gen), dim=-1)
+    q = torch.where(q[:, 3:] < 0, -q, q)
+
+    def rotated(qb, half_angle):        # qb (x) small rotation about a random axis, half-angle given
+        ax = torch.nn.functional.normalize(torch.randn(qb.shape[0], 3, generator=gen), dim=-1)
+        d = torch.cat([ax * torch.sin(half_angle).unsqueeze(-1), torch.cos(half_angle).unsqueeze(-1)], dim=-1)
+        return O.quat_mul(qb, d)
+
+    tb.joint_rot[0] = q
+    tb.joint_rot[1] = q.clone()                                                   # identical -> q0
+    tb.joint_rot[2] = -q                                                          # antipodal -> flip -> q0
+    ha = torch.tensor([2e-4, 5e-4, 9e-4, 9.9e-4, 1.0e-3, 1.01e-3, 1.1e-3, 2e-3, 1e-2, 0.3, 1.0, 1.5, 1.57, 0.7])
+    tb.joint_rot[3] = rotated(tb.joint_rot[2], ha)                                # around the midpoint threshold
+    tb.joint_rot[4] = -rotated(tb.joint_rot[3], ha)                               # negative dot AND a real angle
+    tb.root_rot[1] = tb.root_rot[0].clone()
+    tb.root_rot[2] = -tb.root_rot[1]
+    m, packed = _pack_oracle_tables(gpu_model, tb)
+    L = tb.lengths
+    ids = torch.tensor([0] * 40 + [1] * 6 + [2] * 10)
+    times = torch.cat([torch.linspace(0.0, L[0].item(), 33), torch.tensor([-5.0, -0.0, 1e9, L[0].item() * 0.999999, 0.01, 0.05, 0.1]),
+                       torch.tensor([0.0, 1.0, -1.0, 1e-30, 3.4e38, 0.5]),
+                       torch.tensor([0.0, L[2].item(), L[2].item() * 3, -L[2].item() * 2.5, 0.02, 0.033, 0.0333, 10.0, -10.0, 1e6])])
+    r = ops.motion_query(packed, m, ids.cuda(), motion_times=times.cuda(), want_index=True, want_fk=True)
+    i0, i1, bl = O.frame_blend(tb, ids, times)
+    ref = O.calc_motion_frame(tb, ids, times)
+    finite = ~torch.isnan(times / L[ids])
+    assert torch.equal(r["frame_idx0"].cpu()[finite], i0[finite]) and torch.equal(r["frame_idx1"].cpu()[finite], i1[finite])
+    assert torch.equal(r["blend"].cpu()[finite], bl[finite])
+    ok = finite & ~torch.isnan(ref[4]).any(dim=-1).any(dim=-1)
+    assert ok.sum() >= 50
+    for k, t in zip(FRAME_KEYS, ref):
+        assert_close(r[k][ok.cuda()], t[ok], what=f"edge.{k}")
+    # branch-exact outputs: identical / antipodal key frames and sub-threshold angles are IEEE-only
+    q0, q1 = tb.joint_rot[i0], tb.joint_rot[i1]
+    c = torch.sum(q0 * q1, dim=-1).abs()
+    non_slerp = ((c >= 1) | (torch.sqrt(1.0 - c * c) < 0.001)) & ok.unsqueeze(-1)
+    assert non_slerp.sum() > 100
+    assert torch.equal(r["joint_rot"].cpu()[non_slerp], ref[4][non_slerp])
+    bp, br = O.forward_kinematics(oracle_model, ref[0], ref[1], ref[4])
+    assert_close(r["body_pos"][ok.cuda()], bp[ok], what="edge.body_pos")
+
+
+def test_heightfield_cell_borders_and_out_of_range(gpu_model):
+    """Points exactly on cell borders (round half to even), outside the grid, at +-inf and NaN."""
+    from parc_b200.util.terrain_util import SubTerrain
+    t = SubTerrain("b", x_dim=5, y_dim=4, dx=0.4, dy=0.25, min_x=-0.8, min_y=1.0, device="cuda:0")
+    t.hf = torch.arange(20, dtype=torch.float32, device="cuda").view(5, 4)
+    xs = torch.tensor([-0.8 + 0.4 * k + 0.2 for k in range(-2, 6)] + [float("inf"), -float("inf"), float("nan"), 1e30, -1e30])
+    ys = torch.tensor([1.0 + 0.25 * k + 0.125 for k in range(-2, 5)] + [float("inf"), -float("inf"), float("nan"), 0.0, 1e9, 1.3])
+    pts = torch.stack([xs, ys], dim=-1)
+    idx = t.get_grid_index(pts.cuda()).cpu()
+    exp = torch.round((pts - torch.tensor([-0.8, 1.0])) / torch.tensor([0.4, 0.25])).to(torch.int64)
+    exp = torch.clamp(exp, torch.zeros(2, dtype=torch.int64), torch.tensor([4, 3]))
+    assert torch.equal(idx, exp)
+    z = t.get_hf_val_from_points(pts.cuda()).cpu()
+    assert torch.equal(z, t.hf.cpu()[exp[:, 0], exp[:, 1]])
