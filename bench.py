@@ -223,8 +223,9 @@ def main():
     km = KinCharModel(dev)
     km.load_char_file(os.path.join(ROOT, "parc_b200", "assets", "humanoid.xml"))
     hf_np, frames, contacts = make_inputs(args, km, seed=1234)
-    mlib = MotionLib(torch.from_numpy(frames), km, dev, init_type="motion_frames", loop_mode=LoopMode.CLAMP, fps=30,
-                     contact_info=True, contacts=torch.from_numpy(contacts))
+    # CUDA frames -> the tables are built on the GPU (no host table building at start-up)
+    mlib = MotionLib(torch.from_numpy(frames).to(dev), km, dev, init_type="motion_frames", loop_mode=LoopMode.CLAMP,
+                     fps=30, contact_info=True, contacts=torch.from_numpy(contacts).to(dev))
     terrain = SubTerrain("global", x_dim=HF_DIM, y_dim=HF_DIM, dx=HF_DX, dy=HF_DX, min_x=0.0, min_y=0.0, device=dev)
     terrain.hf = torch.from_numpy(hf_np).to(dev)
     hfd = terrain.hf_desc()

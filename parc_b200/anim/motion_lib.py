@@ -6,8 +6,9 @@ is underneath: the eight per-frame tables are interleaved into one row of float4
 (include/parc_b200.h, ParcRowLayout) and a query is ONE launch of the fused sm_100a kernel in
 csrc/motion_query.cu (one warp per query) instead of ~180 eager torch ops.
 
-Loading (`_load_motions`, `_load_motion_frames`) is host-side: tables are built with torch ops on the
-CPU, in the reference's operation order, then uploaded and packed on the GPU.
+Loading: `_load_motions` (pickled clips) builds the tables with torch ops on the CPU, in the reference's
+operation order (bit-identical tables), then uploads and packs them on the GPU; `_load_motion_frames` does the
+same for host frames and builds directly on the GPU when handed CUDA frames.
 """
 from __future__ import annotations
 
@@ -241,13 +242,25 @@ class MotionLib:
         if frame_contacts is not None:
             assert motion_frames.dim() == frame_contacts.dim() == 3, frame_contacts.shape
         M, F = motion_frames.shape[0], motion_frames.shape[1]
-        root_pos, root_rot, joint_rot = self._extract_frame_data(motion_frames)
+        on_device = torch.is_tensor(motion_frames) and motion_frames.is_cuda
+        if on_device:
+            # CUDA frames (e.g. a batch the MDM just generated): build the tables where the data is, as the
+            # reference does on its device -- exp-map / DoF conversion through the CUDA operators, the
+            # finite differences as elementwise torch ops; nothing visits the host.
+            fr = motion_frames.detach().to(torch.float32)
+            model = self._kin_char_model
+            root_pos = fr[..., 0:3].clone()
+            root_rot = ops.exp_map_to_quat(fr[..., 3:6])
+            joint_rot = torch_util.quat_pos(model.dof_to_rot(fr[..., 6:6 + model.get_dof_size()]))
+        else:
+            model = self._host_model
+            root_pos, root_rot, joint_rot = self._extract_frame_data(motion_frames)
         delta = root_pos[:, -1] - root_pos[:, 0]
         delta[..., -1] = 0.0
         root_vel, root_ang_vel = self._finite_diff_vels(root_pos, root_rot, fps)
-        dof_vel = self._host_model.compute_frame_dof_vel(joint_rot, fps)
-        J = self._host_model.get_num_joints()
-
+        dof_vel = model.compute_frame_dof_vel(joint_rot, fps)
+        J = model.get_num_joints()
+        host = (lambda t: t) if on_device else (lambda t: torch.as_tensor(t, dtype=torch.float32).detach().cpu())
         dev = self._device
         self._motion_fps = fps * torch.ones(M, dtype=torch.float32, device=dev)
         self._motion_dt = 1.0 / fps * torch.ones(M, dtype=torch.float32, device=dev)
@@ -261,8 +274,8 @@ class MotionLib:
             joint_rot=joint_rot.reshape(-1, J - 1, 4), root_vel=root_vel.reshape(-1, 3),
             root_ang_vel=root_ang_vel.reshape(-1, 3), dof_vel=dof_vel.reshape(-1, dof_vel.shape[-1]),
             contacts=None if frame_contacts is None else
-            torch.as_tensor(frame_contacts, dtype=torch.float32).detach().cpu().reshape(-1, frame_contacts.shape[-1]),
-            frames=torch.as_tensor(motion_frames, dtype=torch.float32).detach().cpu().reshape(-1, motion_frames.shape[-1]))
+            host(frame_contacts.to(torch.float32)).reshape(-1, frame_contacts.shape[-1]),
+            frames=host(motion_frames.to(torch.float32)).reshape(-1, motion_frames.shape[-1]))
         self._finish_load()
 
     def _load_motions(self, motion_file):

@@ -191,16 +191,35 @@ def test_cpu_tensor_raises(golden_lib):
 
 
 def test_motion_frames_loader_quirk(gpu_model):
-    """init_type="motion_frames" reproduces the reference's fps-as-dt dof_vel (anim/motion_lib.py:178)."""
+    """init_type="motion_frames" reproduces the reference's fps-as-dt dof_vel (anim/motion_lib.py:178).  Host frames
+    are built on the CPU (bit-identical tables); CUDA frames are built on the GPU (ulp-level differences, as the
+    reference itself shows between devices) -- frame indices are exact either way."""
     from parc_b200.anim.motion_lib import LoopMode, MotionLib
     g = golden("tables_motion_frames_golden.npz")
+    host = MotionLib(torch.tensor(g["frames"]), gpu_model, "cuda:0", init_type="motion_frames", loop_mode=LoopMode.CLAMP,
+                     fps=30, contact_info=True, contacts=torch.tensor(g["contacts"]))
+    assert torch.equal(host._frame_dof_vel.cpu(), torch.tensor(g["dof_vel"]))
+    assert torch.equal(host._frame_root_ang_vel.cpu(), torch.tensor(g["root_ang_vel"]))
+    assert torch.equal(host._frame_joint_rot.cpu(), torch.tensor(g["joint_rot"]))
     lib = MotionLib(dev(g["frames"]), gpu_model, "cuda:0", init_type="motion_frames", loop_mode=LoopMode.CLAMP, fps=30,
                     contact_info=True, contacts=dev(g["contacts"]))
-    assert torch.equal(lib._frame_dof_vel.cpu(), torch.tensor(g["dof_vel"]))
-    assert torch.equal(lib._frame_root_ang_vel.cpu(), torch.tensor(g["root_ang_vel"]))
-    assert torch.equal(lib._frame_joint_rot.cpu(), torch.tensor(g["joint_rot"]))
-    out = lib.calc_motion_frame(torch.tensor([0, 1], device="cuda"), torch.tensor([0.5, 0.25], device="cuda"))
-    assert out[5].shape == (2, 28)
+    # finite differences multiply the ulp-level quaternion differences by fps (30): angular velocities get a
+    # correspondingly wider absolute bar
+    for k, a, atol in (("root_rot", lib._frame_root_rot, 2e-6), ("joint_rot", lib._frame_joint_rot, 2e-6),
+                       ("root_vel", lib._frame_root_vel, 1e-6), ("root_ang_vel", lib._frame_root_ang_vel, 1e-4),
+                       ("dof_vel", lib._frame_dof_vel, 2e-6)):
+        assert a.is_cuda
+        assert_close(a, g[k], atol=atol, what=f"device-built {k}")
+    assert torch.equal(lib._motion_lengths.cpu(), torch.tensor(g["lengths"]))
+    assert_close(lib._motion_root_pos_delta, g["root_pos_delta"], what="delta")
+    ids = torch.tensor([0, 1, 1, 0], device="cuda")
+    tms = torch.tensor([0.5, 0.25, 0.9, 0.0333], device="cuda")
+    a, b = lib._calc_frame_blend(ids, tms), host._calc_frame_blend(ids, tms)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    out, ref = lib.calc_motion_frame(ids, tms), host.calc_motion_frame(ids, tms)
+    assert out[5].shape == (4, 28)
+    for x, y in zip(out, ref):
+        assert_close(x, y, atol=1e-4, what="query on device-built tables")
 
 
 # ----------------------------------------------------------------------------------------- dof <-> rot
