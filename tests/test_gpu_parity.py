@@ -821,3 +821,95 @@ def test_heightfield_cell_borders_and_out_of_range(gpu_model):
     assert torch.equal(idx, exp)
     z = t.get_hf_val_from_points(pts.cuda()).cpu()
     assert torch.equal(z, t.hf.cpu()[exp[:, 0], exp[:, 1]])
+
+
+# ----------------------------------------------------------------------------------------- BASELINE full sizes: properties
+@pytest.fixture(scope="module")
+def big_lib(gpu_model):
+    """The bench's library: 2048 synthetic 265-frame clips (260 MB packed), built on the GPU."""
+    from parc_b200.anim.motion_lib import LoopMode, MotionLib
+    from parc_b200.util import synth
+    rng = np.random.default_rng(1234)
+    hf = synth.rolling_terrain(rng, 512, 512, num_boxes=800)
+    frames, contacts = synth.synth_clips(gpu_model, 2048, seed=1235, hf=hf)
+    lib = MotionLib(torch.from_numpy(frames).cuda(), gpu_model, "cuda:0", init_type="motion_frames",
+                    loop_mode=LoopMode.WRAP, fps=30, contact_info=True, contacts=torch.from_numpy(contacts).cuda())
+    return lib, torch.from_numpy(hf).cuda()
+
+
+def test_full_size_query_is_batch_order_and_split_invariant(big_lib, gpu_model):
+    """Config 4 size (65 536 envs): every query is independent, so permuting the batch permutes the outputs
+    bit-exactly, querying two halves equals querying the whole, and the fused FK equals the stand-alone FK."""
+    from parc_b200 import ops
+    from parc_b200.util import geom_util
+    lib, hf = big_lib
+    n = 65536
+    gen = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 2048, (n,), generator=gen).cuda()
+    times = ((torch.rand(n, generator=gen) * 3.0 - 1.0) * (264.0 / 30.0)).cuda()
+    hfd = ops.HeightfieldDesc(hf=hf, min_x=0.0, min_y=0.0, dx=0.4, dy=0.4)
+    tmpl = geom_util.get_xy_points_cone(torch.zeros(2, device="cuda"), 0.05, 2, 60, 3, 3, 0.26179938779)
+    keys = FRAME_KEYS + ("body_pos", "body_rot", "obs")
+    full = {k: v.clone() for k, v in lib.calc_motion_frame_fk_obs(ids, times, hf_desc=hfd, obs_tmpl=tmpl).items()}
+    perm = torch.randperm(n, generator=gen).cuda()
+    shuf = lib.calc_motion_frame_fk_obs(ids[perm], times[perm], hf_desc=hfd, obs_tmpl=tmpl)
+    for k in keys:
+        assert torch.equal(shuf[k], full[k][perm]), f"permutation changed {k}"
+    lo = lib.calc_motion_frame_fk_obs(ids[:30001].contiguous(), times[:30001].contiguous(), hf_desc=hfd, obs_tmpl=tmpl)
+    for k in keys:
+        assert torch.equal(lo[k], full[k][:30001]), f"split changed {k}"
+    bp, br = gpu_model.forward_kinematics(full["root_pos"], full["root_rot"], full["joint_rot"])
+    assert torch.equal(bp, full["body_pos"]) and torch.equal(br, full["body_rot"])
+    assert torch.isfinite(full["body_pos"]).all() and (full["obs"].abs() <= 3.0).all()
+    # unit quaternions stay (nearly) unit through slerp + FK for these smooth clips
+    assert (full["body_rot"].norm(dim=-1) - 1).abs().max() < 1e-3
+    i0, i1, bl = lib._calc_frame_blend(ids, times)
+    assert ((i1 - i0 == 1) | (i1 == i0)).all() and (bl >= 0).all() and (bl < 1).all()
+    assert (i0 // 265 == ids).all() and (i1 // 265 == ids).all()          # indices never leave their clip
+
+
+def test_full_size_loss_frames_are_independent(gpu_model):
+    """Config 3 size (1024 samples x 200 frames, one terrain per sample): per-frame terms and gradients do not
+    depend on which other frames / samples share the launch."""
+    from parc_b200 import ops
+    from parc_b200.tools.procgen.mdm_path import body_points_desc
+    from parc_b200.util import geom_util, synth
+    rng = np.random.default_rng(3)
+    B, F = 1024, 200
+    base = [synth.box_terrain(rng) if i % 2 == 0 else synth.stairs_terrain(rng) for i in range(16)]
+    hfs = torch.tensor(np.stack([base[i % 16] for i in range(B)])).cuda()
+    s = synth.synth_motion_samples(gpu_model, B, F, base[0], (0.0, 0.0), (0.4, 0.4), seed=11)
+    rp = torch.tensor(s["root_pos"]).cuda()
+    rq = ops.exp_map_to_quat(torch.tensor(s["root_exp"]).cuda())
+    jr = gpu_model.dof_to_rot(torch.tensor(s["joint_dof"]).cuda())
+    ct = torch.tensor(s["contacts"]).cuda()
+    pts = body_points_desc(gpu_model, geom_util.get_char_point_samples(gpu_model))
+    m = gpu_model.c_model()
+    tb = ops.make_terrain_batch(hfs, torch.zeros(B, 2).cuda(), (0.4, 0.4), base_z=-10.0)
+    full = ops._body_loss_launch(m, pts, tb, rp, rq, jr, ct, 0.1, 0.1, True)
+    sub = slice(100, 164)
+    fr = slice(37, 90)
+    tb2 = ops.make_terrain_batch(hfs[sub].contiguous(), torch.zeros(64, 2).cuda(), (0.4, 0.4), base_z=-10.0)
+    part = ops._body_loss_launch(m, pts, tb2, rp[sub, fr].contiguous(), rq[sub, fr].contiguous(), jr[sub, fr].contiguous(),
+                                 ct[sub, fr].contiguous(), 0.1, 0.1, True)
+    for a, b in zip(full, part):
+        assert torch.equal(a[sub, fr], b)
+    assert torch.isfinite(full[0]).all() and (full[0] >= 0).all() and full[0].sum() > 0
+
+
+def test_full_size_frames_fk_split_and_cross_kernel_consistency(gpu_model):
+    """Config 5 per-GPU shard (12 500 clips x 265 frames): the one-launch raw-frame FK equals the three-step path
+    (exp_map_to_quat, dof_to_rot, forward_kinematics) bit-exactly, and is split invariant."""
+    from parc_b200 import ops
+    from parc_b200.util import synth
+    fr_np, _ = synth.synth_clips(gpu_model, 250, seed=77)
+    fr = torch.tensor(fr_np).cuda().repeat(50, 1, 1).reshape(-1, 34)        # 3 312 500 frames
+    assert fr.shape[0] == 12500 * 265
+    bp, br = ops.frames_fk(gpu_model.c_model(), fr)
+    sel = torch.randint(0, fr.shape[0], (20000,), generator=torch.Generator().manual_seed(2)).cuda()
+    f2 = fr[sel]
+    bp2, br2 = gpu_model.forward_kinematics(f2[:, 0:3], ops.exp_map_to_quat(f2[:, 3:6]), gpu_model.dof_to_rot(f2[:, 6:]))
+    assert torch.equal(bp[sel], bp2) and torch.equal(br[sel], br2)
+    bp3, _ = ops.frames_fk(gpu_model.c_model(), fr[1000001:2000000])
+    assert torch.equal(bp3, bp[1000001:2000000])
+    assert torch.isfinite(bp).all()
