@@ -313,6 +313,81 @@ int parc_clip_label(const float* frames, int64_t batch, int64_t frames_per_clip,
                     float* body_hf_out, uint32_t* frame_mask_out, float* min_body_heights, float* body_pos,
                     float* body_rot, void* stream);
 
+/* ---- f3: tracker step assembly ------------------------------------------------
+ * What the tracking environment computes around the motion query every control step.  One launch each. */
+
+/* One character state, struct-of-arrays, all device float32: root_pos [n,3], root_rot [n,4] xyzw,
+ * root_vel [n,3], root_ang_vel [n,3], joint_rot [n,J-1,4], dof_vel [n,D], key_pos [n,K,3] (world-space
+ * positions of the key bodies; NULL iff K == 0).  root_rot / joint_rot 16-byte aligned. */
+typedef struct ParcCharState {
+  const float* root_pos;
+  const float* root_rot;
+  const float* root_vel;
+  const float* root_ang_vel;
+  const float* joint_rot;
+  const float* dof_vel;
+  const float* key_pos;
+} ParcCharState;
+
+/* envs/base_env.py:12-16 (DoneFlags) */
+#define PARC_DONE_NULL 0
+#define PARC_DONE_FAIL 1
+#define PARC_DONE_SUCC 2
+#define PARC_DONE_TIME 3
+
+/* Scalars of compute_done (envs/ig_parkour/mgdm_dm_util.py:399-460).  They are the reference's python
+ * floats, so they travel as doubles: each meets fp32 data as its fp32 rounding, and the squared root
+ * distance is formed in double first, as there.  contact_body_mask: bit b set = body b MAY touch the
+ * ground (the reference's contact_body_ids); has_contact_bodies = 0 skips the fall test entirely, as an
+ * empty id list does there.  pose_termination_dist: device [J-1] float32, per non-root body. */
+typedef struct ParcDoneSpec {
+  double episode_length;
+  double termination_height;
+  double root_pos_termination_dist;
+  double root_rot_termination_angle;
+  const float* pose_termination_dist;
+  uint32_t contact_body_mask;
+  int32_t has_contact_bodies;
+  int32_t pose_termination;
+  int32_t enable_early_termination;
+  int32_t track_root;
+} ParcDoneSpec;
+
+/* compute_char_obs (envs/ig_char_env.py:582-626): obs_out [n, W],
+ * W = (root_height_obs ? 1 : 0) + 6 + 3 + 3 + 6*num_joint_rots + dof_size + 3*num_keys, laid out as
+ * [root z] | tan-norm of the (heading-local unless global_obs) root rotation | root_vel | root_ang_vel |
+ * tan-norm of every joint rotation | dof_vel | key positions relative to the root (heading-local). */
+int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_joint_rots, int32_t dof_size,
+                  int32_t num_keys, int32_t global_obs, int32_t root_height_obs, float* obs_out, void* stream);
+
+/* compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): future targets [n,S,...] expressed against the
+ * character (ref_root_pos [n,3], ref_root_rot [n,4]); obs_out [n, S, 3 + 6 + 6*num_joint_rots + 3*num_keys] =
+ * root offset | root tan-norm | joint tan-norms | key positions.  tar_key_pos [n,S,K,3] world space. */
+int parc_tar_obs(const float* ref_root_pos, const float* ref_root_rot, const float* tar_root_pos,
+                 const float* tar_root_rot, const float* tar_joint_rot, const float* tar_key_pos, int64_t n,
+                 int32_t num_steps, int32_t num_joint_rots, int32_t num_keys, int32_t global_obs,
+                 int32_t global_tar_root_h_obs, float* obs_out, void* stream);
+
+/* compute_deepmimic_reward (envs/ig_parkour/mgdm_dm_util.py:328-397): reward_out [n,5] =
+ * exp(-0.25 pose), exp(-0.01 vel), exp(-5 (root_pos + 0.1 root_rot)), exp(-(root_vel + 0.1 root_ang_vel)),
+ * exp(-10 key_pos).  joint_rot_err_w [J-1], dof_err_w [D] device float32.  num_keys == 0 is PARC_E_SIZE
+ * (the reference raises on it too). */
+int parc_deepmimic_reward(const ParcCharState* sim, const ParcCharState* tar, int64_t n, int32_t num_joint_rots,
+                          int32_t dof_size, int32_t num_keys, const float* joint_rot_err_w,
+                          const float* dof_err_w, int32_t track_root_h, int32_t track_root, float* reward_out,
+                          void* stream);
+
+/* compute_done with the termination-height lookup of RefCharEnv.update_done fused in
+ * (envs/ig_parkour/mgdm_dm_util.py:205-230, :399-460).  time [n]; body_pos / tar_body_pos / contact_force
+ * [n,J,3]; root_rot / tar_root_rot [n,4].  Heights: pass term_heights [n,J] (compute_done's own argument),
+ * or NULL to sample hf at body xy + env_offsets[:, 0:2] (env_offsets [n, offset_stride], may be NULL) and
+ * add termination_height.  done_out [n] int32 (PARC_DONE_*); term_heights_out [n,J] optional. */
+int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
+              const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
+              const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
+              int32_t offset_stride, int64_t n, int32_t num_bodies, int32_t* done_out, float* term_heights_out,
+              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,8 @@ import util.motion_util as ref_mu  # noqa: E402
 import tools.procgen.mdm_path as ref_mdm_path  # noqa: E402
 import tools.motion_opt.motion_optimization as ref_mopt  # noqa: E402
 import zmotion_editing_tools.motion_edit_lib as ref_mel  # noqa: E402
+import envs.ig_char_env as ref_char_env  # noqa: E402
+import envs.ig_parkour.mgdm_dm_util as ref_dm_util  # noqa: E402
 
 from oracle import parc_oracle as O  # noqa: E402
 
@@ -451,6 +453,110 @@ def main():
         bc_point=np.stack([npf(bcs[lf][0].constraint_point), npf(bcs[rh][0].constraint_point)]),
         loss=npf(loss_bc), body_constraint_term=np.array(float(ld_bc[ref_mopt.LossType.BODY_CONSTRAINT_LOSS])),
         grad_root_pos=npf(gb_rp), grad_root_exp=npf(gb_re), grad_joint_dof=npf(gb_jd), adam4_frames=npf(ref_opt))
+
+    # ------------------------------------------------------------------ 9. tracker step assembly
+    g = torch.Generator().manual_seed(99)
+    NE, dt_ctrl = 96, 1.0 / 30.0
+    steps = torch.tensor([1, 2, 3, 10, 20, 30], dtype=torch.float32)         # dm_env_default.yaml:166-172
+    e_ids = torch.randint(0, 3, (NE,), generator=g)
+    e_t = torch.rand(NE, generator=g) * lens[e_ids] * 1.1
+    e_t[:4] = 0.0                                                            # first-step envs never fail
+    cur = mlib.calc_motion_frame(e_ids, e_t)
+    ref_bp, ref_br = km.forward_kinematics(cur[0], cur[1], cur[4])
+    # simulated character = reference pose + noise of mixed size so that every done / reward branch is exercised
+    amp = torch.where(torch.arange(NE) % 3 == 0, 0.6, 0.05).unsqueeze(-1)
+    sim_root_pos = cur[0] + amp * 0.5 * torch.randn(NE, 3, generator=g)
+    sim_root_rot = ref_tu.quat_mul(cur[1], ref_tu.exp_map_to_quat(amp * 1.5 * torch.randn(NE, 3, generator=g)))
+    sim_root_vel = cur[2] + 0.3 * torch.randn(NE, 3, generator=g)
+    sim_root_ang_vel = cur[3] + 0.3 * torch.randn(NE, 3, generator=g)
+    sim_dof = km.rot_to_dof(cur[4]) + amp * 0.4 * torch.randn(NE, km.get_dof_size(), generator=g)
+    sim_joint_rot = km.dof_to_rot(sim_dof)
+    sim_dof_vel = cur[5] + 0.5 * torch.randn(NE, km.get_dof_size(), generator=g)
+    sim_bp, _ = km.forward_kinematics(sim_root_pos, sim_root_rot, sim_joint_rot)
+    key_ids_t = torch.tensor([km.get_body_id(nm) for nm in ("right_hand", "left_hand", "right_foot", "left_foot")])
+    tar_rp, tar_rr, tar_jr, tar_ct = ref_dm_util.fetch_tar_obs_data(e_ids, e_t, mlib, dt_ctrl, steps)
+    tar_bp, _ = km.forward_kinematics(tar_rp.reshape(-1, 3), tar_rr.reshape(-1, 4), tar_jr.reshape(-1, J - 1, 4))
+    tar_key = tar_bp.reshape(NE, steps.shape[0], J, 3)[:, :, key_ids_t]
+    none = torch.zeros([0])
+    ts = {}
+    for gl in (False, True):
+        for rh in (False, True):
+            r = ref_char_env.compute_char_obs(sim_root_pos, sim_root_rot, sim_root_vel, sim_root_ang_vel, sim_joint_rot,
+                                              sim_dof_vel, sim_bp[:, key_ids_t], gl, rh)
+            o = O.compute_char_obs(sim_root_pos, sim_root_rot, sim_root_vel, sim_root_ang_vel, sim_joint_rot,
+                                   sim_dof_vel, sim_bp[:, key_ids_t], gl, rh)
+            pin(f"step.char_obs(global={gl},root_h={rh})", r, o)
+            ts[f"char_obs_g{int(gl)}_h{int(rh)}"] = npf(r)
+            r = ref_dm_util.compute_tar_obs(sim_root_pos, sim_root_rot, tar_rp.clone(), tar_rr.clone(), tar_jr, tar_key.clone(), gl, rh)
+            o = O.compute_tar_obs(sim_root_pos, sim_root_rot, tar_rp, tar_rr, tar_jr, tar_key, gl, rh)
+            pin(f"step.tar_obs(global={gl},tar_h={rh})", r, o)
+            ts[f"tar_obs_g{int(gl)}_h{int(rh)}"] = npf(r)
+    r = ref_char_env.compute_char_obs(sim_root_pos, sim_root_rot, sim_root_vel, sim_root_ang_vel, sim_joint_rot, sim_dof_vel, none, False, False)
+    pin("step.char_obs(no key bodies)", r, O.compute_char_obs(sim_root_pos, sim_root_rot, sim_root_vel, sim_root_ang_vel,
+                                                               sim_joint_rot, sim_dof_vel, none, False, False))
+    ts["char_obs_nokey"] = npf(r)
+    r = ref_dm_util.compute_tar_obs(sim_root_pos, sim_root_rot, tar_rp.clone(), tar_rr.clone(), tar_jr, none, False, False)
+    pin("step.tar_obs(no key bodies)", r, O.compute_tar_obs(sim_root_pos, sim_root_rot, tar_rp, tar_rr, tar_jr, none, False, False))
+    ts["tar_obs_nokey"] = npf(r)
+    jw = torch.tensor([1.0, 0.6, 0.6, 0.4, 0.0, 0.6, 0.4, 0.0, 1.0, 0.6, 0.4, 1.0, 0.6, 0.4])     # dm_env_default.yaml:99-113
+    dw = torch.zeros(km.get_dof_size())
+    for j in range(1, J):
+        if km.get_joint_dof_dim(j) > 0:
+            dw[km.get_joint_dof_idx(j):km.get_joint_dof_idx(j) + km.get_joint_dof_dim(j)] = jw[j - 1]
+    for tr in (True, False):
+        for th in (True, False):
+            args = (sim_root_pos, sim_root_rot, sim_root_vel, sim_root_ang_vel, sim_joint_rot, sim_dof_vel, sim_bp[:, key_ids_t],
+                    cur[0], cur[1], cur[2], cur[3], cur[4], cur[5], ref_bp[:, key_ids_t], jw, dw, th, tr)
+            r = ref_dm_util.compute_deepmimic_reward(*args)
+            pin(f"step.reward(track_root={tr},track_h={th})", r, O.compute_deepmimic_reward(*args))
+            ts[f"reward_r{int(tr)}_h{int(th)}"] = npf(r)
+    try:        # without key bodies the reference's torch.stack sees a [0] tensor next to [N] ones and raises
+        ref_dm_util.compute_deepmimic_reward(sim_root_pos, sim_root_rot, sim_root_vel, sim_root_ang_vel, sim_joint_rot, sim_dof_vel,
+                                             none, cur[0], cur[1], cur[2], cur[3], cur[4], cur[5], none, jw, dw, True, True)
+        raise SystemExit("reference reward unexpectedly accepts an empty key-body set")
+    except RuntimeError:
+        REPORT.append("OK  step.reward(no key bodies) raises in the reference")
+    # done flags, with the termination-height lookup of RefCharEnv.update_done (mgdm_dm_util.py:205-230)
+    terr_s = ref_terrain.SubTerrain("step", 40, 32, 0.4, 0.4, -3.0, -2.0, device="cpu")
+    # heights straddle the lowest bodies so that the fall test (height AND contact force) fires for some envs
+    terr_s.hf[...] = torch.rand(40, 32, generator=g) * 0.8 + (sim_bp[..., 2].min(dim=-1)[0].median() - 0.4)
+    env_off = torch.randn(NE, 3, generator=g) * 0.5
+    o_terr = O.Terrain(hf=terr_s.hf.clone(), min_point=terr_s.min_point.clone(), dxdy=terr_s.dxdy.clone())
+    ptd = torch.tensor([0.7, 1.0, 0.7, 0.7, 0.7, 0.7, 0.7, 0.7, 1.0, 1.2, 10.0, 1.0, 1.2, 10.0])   # dm_env_default.yaml:129-143
+    time_buf = torch.rand(NE, generator=g) * 12.0
+    time_buf[:4] = 0.0
+    forces = torch.randn(NE, J, 3, generator=g) * (torch.rand(NE, J, 1, generator=g) < 0.2)
+    feet = torch.tensor([km.get_body_id("right_foot"), km.get_body_id("left_foot")])
+    done_in = torch.zeros(NE, dtype=torch.int)
+    for tag, cids, pt, tr in (("default", torch.zeros([0], dtype=torch.long), True, True), ("feet", feet, True, True),
+                              ("feet_nopose", feet, False, True), ("noroot", feet, True, False)):
+        gpos = sim_bp[..., 0:2] + env_off[:, 0:2].unsqueeze(1)
+        gi = terr_s.get_grid_index(gpos)
+        th_ref = terr_s.hf[gi[..., 0], gi[..., 1]] + 0.15
+        th_o = O.termination_heights(o_terr, sim_bp, env_off, 0.15)
+        pin(f"step.termination_heights[{tag}]", th_ref, th_o)
+        r = ref_dm_util.compute_done(done_in, time_buf, 10.0, sim_root_rot, sim_bp, sim_root_pos, cur[1], ref_bp, forces, cids,
+                                     th_ref, pt, ptd, False, True, tr, 0.6, 1.309)
+        o = O.compute_done(done_in, time_buf, 10.0, sim_root_rot, sim_bp, cur[1], ref_bp, forces, cids, th_o, pt, ptd, True,
+                           tr, 0.6, 1.309)
+        pin(f"step.done[{tag}]", r, o)
+        ts[f"done_{tag}"] = npf(r)
+        ts["term_heights"] = npf(th_ref)
+    r = ref_dm_util.compute_done(done_in, time_buf, 10.0, sim_root_rot, sim_bp, sim_root_pos, cur[1], ref_bp, forces, feet,
+                                 th_ref, True, ptd, False, False, True, 0.6, 1.309)
+    pin("step.done[no early termination]", r, O.compute_done(done_in, time_buf, 10.0, sim_root_rot, sim_bp, cur[1], ref_bp, forces,
+                                                             feet, th_o, True, ptd, False, True, 0.6, 1.309))
+    ts["done_noearly"] = npf(r)
+    np.savez_compressed(
+        os.path.join(GOLD, "tracker_step_golden.npz"), ids=npf(e_ids), times=npf(e_t), steps=npf(steps), dt=np.float32(dt_ctrl),
+        key_ids=npf(key_ids_t), root_pos=npf(sim_root_pos), root_rot=npf(sim_root_rot), root_vel=npf(sim_root_vel),
+        root_ang_vel=npf(sim_root_ang_vel), joint_rot=npf(sim_joint_rot), dof_vel=npf(sim_dof_vel), body_pos=npf(sim_bp),
+        ref_root_pos=npf(cur[0]), ref_root_rot=npf(cur[1]), ref_root_vel=npf(cur[2]), ref_root_ang_vel=npf(cur[3]),
+        ref_joint_rot=npf(cur[4]), ref_dof_vel=npf(cur[5]), ref_body_pos=npf(ref_bp),
+        tar_root_pos=npf(tar_rp), tar_root_rot=npf(tar_rr), tar_joint_rot=npf(tar_jr), tar_key_pos=npf(tar_key),
+        tar_contacts=npf(tar_ct), joint_err_w=npf(jw), dof_err_w=npf(dw), hf=npf(terr_s.hf), hf_min=npf(terr_s.min_point),
+        hf_dxdy=npf(terr_s.dxdy), env_offsets=npf(env_off), pose_termination_dist=npf(ptd), time_buf=npf(time_buf),
+        contact_forces=npf(forces), feet=npf(feet), **ts)
 
     with open(os.path.join(GOLD, "PIN_REPORT.txt"), "w") as f:
         f.write("oracle/parc_oracle.py vs the imported reference (torch %s, CPU, fp32) -- torch.equal on every line\n"

@@ -789,3 +789,162 @@ def motion_contact_optimization(model: CharModel, src_frames, contacts, hf, min_
         loss.backward()
         opt.step()
     return torch.cat([t.detach() for t in leaves], dim=-1)
+
+
+# --------------------------------------------------------------------------
+# tracker step assembly: policy observation, reward, done
+# --------------------------------------------------------------------------
+DONE_NULL, DONE_FAIL, DONE_SUCC, DONE_TIME = 0, 1, 2, 3        # envs/base_env.py:12-16
+
+
+def heading_inverse_quat(q):
+    """Rotation about +z by -heading(q) -- util/torch_util.py:491-499."""
+    up = torch.zeros_like(q[..., 0:3])
+    up[..., 2] = 1
+    return axis_angle_to_quat(up, -calc_heading(q))
+
+
+def quat_to_tan_norm(q):
+    """Rotated x axis followed by rotated z axis, 6 numbers -- util/torch_util.py:361-373."""
+    ex = torch.zeros_like(q[..., 0:3])
+    ex[..., 0] = 1
+    ez = torch.zeros_like(q[..., 0:3])
+    ez[..., 2] = 1
+    return torch.cat([quat_rotate(q, ex), quat_rotate(q, ez)], dim=-1)
+
+
+def _rotate_rows(q, v):
+    """quat_rotate of v[..., k, 3] by q[..., 4] broadcast over k (the reference's repeat + flatten idiom)."""
+    return quat_rotate(q.unsqueeze(-2).expand(v.shape[:-1] + (4,)), v)
+
+
+def compute_char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos, global_obs,
+                     root_height_obs):
+    """Proprioceptive observation of the simulated character -- envs/ig_char_env.py:582-626.
+    joint_rot [N,J-1,4]; key_pos [N,K,3] or an empty tensor.  Layout:
+    [root_h (opt)] root tan-norm 6 | root_vel 3 | root_ang_vel 3 | joint tan-norm 6(J-1) | dof_vel D | key_pos 3K."""
+    hinv = heading_inverse_quat(root_rot)
+    if global_obs:
+        parts = [quat_to_tan_norm(root_rot), root_vel, root_ang_vel]
+    else:
+        parts = [quat_to_tan_norm(quat_mul(hinv, root_rot)), quat_rotate(hinv, root_vel), quat_rotate(hinv, root_ang_vel)]
+    parts.append(quat_to_tan_norm(joint_rot).reshape(joint_rot.shape[0], -1))
+    parts.append(dof_vel)
+    if key_pos.numel() > 0:
+        rel = key_pos - root_pos.unsqueeze(-2)
+        if not global_obs:
+            rel = _rotate_rows(hinv, rel)
+        parts.append(rel.reshape(rel.shape[0], -1))
+    if root_height_obs:
+        parts = [root_pos[:, 2:3]] + parts
+    return torch.cat(parts, dim=-1)
+
+
+def compute_tar_obs(ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, joint_rot, tar_key_pos, global_obs,
+                    global_tar_root_h_obs):
+    """Future-target observation -- envs/ig_parkour/mgdm_dm_util.py:462-518.  ref_* [N,.] is the character the
+    targets are expressed against; tar_root_pos [N,S,3], tar_root_rot [N,S,4], joint_rot [N,S,J-1,4],
+    tar_key_pos [N,S,K,3] or empty.  Returns [N,S, 3 + 6 + 6(J-1) + 3K]."""
+    pos_obs = tar_root_pos - ref_root_pos.unsqueeze(-2)
+    has_keys = tar_key_pos.numel() > 0
+    if has_keys:
+        tar_key_pos = tar_key_pos - tar_root_pos.unsqueeze(-2)
+    if not global_obs:
+        hinv = heading_inverse_quat(ref_root_rot)
+        pos_obs = _rotate_rows(hinv, pos_obs)
+        tar_root_rot = quat_mul(hinv.unsqueeze(-2).expand(tar_root_rot.shape), tar_root_rot)
+        if has_keys:
+            hk = hinv.unsqueeze(-2).unsqueeze(-2).expand(tar_key_pos.shape[:-1] + (4,))
+            tar_key_pos = quat_rotate(hk, tar_key_pos) + pos_obs.unsqueeze(2)
+    if global_tar_root_h_obs:
+        pos_obs = pos_obs.clone()
+        pos_obs[..., 2] = tar_root_pos[..., 2]
+    parts = [pos_obs, quat_to_tan_norm(tar_root_rot), quat_to_tan_norm(joint_rot).reshape(joint_rot.shape[:2] + (-1,))]
+    if has_keys:
+        parts.append(tar_key_pos.reshape(tar_key_pos.shape[:2] + (-1,)))
+    return torch.cat(parts, dim=-1)
+
+
+def _to_heading_frame(root_rot, root_vel, root_ang_vel, key_pos):
+    """envs/ig_parkour/mgdm_dm_util.py:304-326 (convert_to_local)"""
+    hinv = heading_inverse_quat(root_rot)
+    kp = _rotate_rows(hinv, key_pos) if key_pos.numel() > 0 else key_pos
+    return quat_mul(hinv, root_rot), quat_rotate(hinv, root_vel), quat_rotate(hinv, root_ang_vel), kp
+
+
+def compute_deepmimic_reward(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos,
+                             tar_root_pos, tar_root_rot, tar_root_vel, tar_root_ang_vel, tar_joint_rot, tar_dof_vel,
+                             tar_key_pos, joint_rot_err_w, dof_err_w, track_root_h, track_root):
+    """The five exponentiated tracking terms [N,5] = (pose, vel, root pose, root vel, key pos) --
+    envs/ig_parkour/mgdm_dm_util.py:328-397."""
+    ang = quat_diff_angle(joint_rot, tar_joint_rot)
+    pose_err = torch.sum(joint_rot_err_w * ang * ang, dim=-1)
+    dv = tar_dof_vel - dof_vel
+    vel_err = torch.sum(dof_err_w * dv * dv, dim=-1)
+    dp = (tar_root_pos - root_pos).clone()
+    if not track_root:
+        dp[..., 0:2] = 0
+    if not track_root_h:
+        dp[..., 2] = 0
+    root_pos_err = torch.sum(dp * dp, dim=-1)
+    has_keys = key_pos.numel() > 0
+    if has_keys:
+        key_pos = key_pos - root_pos.unsqueeze(-2)
+        tar_key_pos = tar_key_pos - tar_root_pos.unsqueeze(-2)
+    if not track_root:
+        root_rot, root_vel, root_ang_vel, key_pos = _to_heading_frame(root_rot, root_vel, root_ang_vel, key_pos)
+        tar_root_rot, tar_root_vel, tar_root_ang_vel, tar_key_pos = _to_heading_frame(tar_root_rot, tar_root_vel,
+                                                                                      tar_root_ang_vel, tar_key_pos)
+    rr = quat_diff_angle(root_rot, tar_root_rot)
+    root_rot_err = rr * rr
+    d = tar_root_vel - root_vel
+    root_vel_err = torch.sum(d * d, dim=-1)
+    d = tar_root_ang_vel - root_ang_vel
+    root_ang_vel_err = torch.sum(d * d, dim=-1)
+    if has_keys:
+        d = tar_key_pos - key_pos
+        key_pos_err = torch.sum(torch.sum(d * d, dim=-1), dim=-1)
+    else:
+        key_pos_err = torch.zeros([0])
+    return torch.stack([torch.exp(-0.25 * pose_err), torch.exp(-0.01 * vel_err),
+                        torch.exp(-5.0 * (root_pos_err + 0.1 * root_rot_err)),
+                        torch.exp(-1.0 * (root_vel_err + 0.1 * root_ang_vel_err)),
+                        torch.exp(-10.0 * key_pos_err)], dim=1)
+
+
+def termination_heights(t: Terrain, body_pos, env_offsets, termination_height):
+    """Terrain height under every body plus the margin -- envs/ig_parkour/mgdm_dm_util.py:208-210."""
+    xy = body_pos[..., 0:2] + env_offsets[:, 0:2].unsqueeze(1)
+    return hf_sample(t, xy) + termination_height
+
+
+def compute_done(done_buf, time, ep_len, root_rot, body_pos, tar_root_rot, tar_body_pos, contact_force,
+                 contact_body_ids, term_heights, pose_termination, pose_termination_dist, enable_early_termination,
+                 track_root, root_pos_termination_dist, root_rot_termination_angle):
+    """Episode flags -- envs/ig_parkour/mgdm_dm_util.py:399-460 (char_root_pos and global_obs are unused there).
+    contact_body_ids: bodies ALLOWED to touch the ground; pose_termination_dist [J-1]."""
+    done = torch.full_like(done_buf, DONE_NULL)
+    done[time >= ep_len] = DONE_TIME
+    if enable_early_termination:
+        failed = torch.zeros(done.shape, dtype=torch.bool)
+        if contact_body_ids.shape[0] > 0:
+            force = contact_force.detach().clone()
+            force[:, contact_body_ids, :] = 0
+            touched = torch.any(torch.any(torch.abs(force) > 0.1, dim=-1), dim=-1)
+            low = body_pos[..., 2] < term_heights
+            low[:, contact_body_ids] = False
+            failed = failed | (touched & torch.any(low, dim=-1))
+        if pose_termination:
+            rp = body_pos[..., 0:1, :]
+            trp = tar_body_pos[..., 0:1, :]
+            d = (tar_body_pos[..., 1:, :] - trp) - (body_pos[..., 1:, :] - rp)
+            pose_fail = torch.any(torch.sum(d * d, dim=-1) > pose_termination_dist * pose_termination_dist, dim=-1)
+            if track_root:
+                d = rp - trp
+                pose_fail = pose_fail | (torch.sum(d * d, dim=-1).squeeze(-1)
+                                         > root_pos_termination_dist * root_pos_termination_dist)
+                pose_fail = pose_fail | (torch.abs(quat_diff_angle(root_rot, tar_root_rot)) > root_rot_termination_angle)
+            failed = failed | pose_fail
+        failed = failed & (time > 1e-5)
+        done[failed] = DONE_FAIL
+    return done

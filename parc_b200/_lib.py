@@ -97,6 +97,22 @@ class ParcKeyBodies(C.Structure):
                 ("hand_radius", C.c_float * PARC_MAX_KEY_BODIES)]
 
 
+class ParcCharState(C.Structure):
+    _fields_ = [("root_pos", C.c_void_p), ("root_rot", C.c_void_p), ("root_vel", C.c_void_p),
+                ("root_ang_vel", C.c_void_p), ("joint_rot", C.c_void_p), ("dof_vel", C.c_void_p),
+                ("key_pos", C.c_void_p)]
+
+
+class ParcDoneSpec(C.Structure):
+    _fields_ = [("episode_length", C.c_double), ("termination_height", C.c_double),
+                ("root_pos_termination_dist", C.c_double), ("root_rot_termination_angle", C.c_double),
+                ("pose_termination_dist", C.c_void_p), ("contact_body_mask", C.c_uint32),
+                ("has_contact_bodies", C.c_int32), ("pose_termination", C.c_int32),
+                ("enable_early_termination", C.c_int32), ("track_root", C.c_int32)]
+
+
+PARC_DONE_NULL, PARC_DONE_FAIL, PARC_DONE_SUCC, PARC_DONE_TIME = 0, 1, 2, 3
+
 # name -> (restype, argtypes); every symbol include/parc_b200.h declares
 _V, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 _P = C.POINTER
@@ -129,6 +145,12 @@ SIGNATURES = {
                                   _P(ParcKeyBodies), _F, _V, _V, _V, _V, _V, _V, _V, _V]),
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
                                  _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
+    "parc_char_obs": (C.c_int, [_P(ParcCharState), _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
+    "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
+    "parc_deepmimic_reward": (C.c_int, [_P(ParcCharState), _P(ParcCharState), _I64, _I32, _I32, _I32, _V, _V, _I32,
+                                        _I32, _V, _V]),
+    "parc_done": (C.c_int, [_P(ParcDoneSpec), _V, _V, _V, _V, _V, _V, _V, _P(ParcHeightfield), _V, _I32, _I64, _I32,
+                            _V, _V, _V]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,0 +1,397 @@
+// Tracker step assembly: what the tracking environment computes around the motion
+// query every control step -- the policy observation of the simulated character, the future-target
+// observation, the five DeepMimic tracking rewards and the episode flags (with the terrain-height lookup
+// under every body fused in).  Each is ONE launch, one warp per env (per (env, step) for the targets),
+// lane = joint / body / DoF; the reference runs each as a chain of 40-120 eager torch ops.
+//
+// Reference: envs/ig_char_env.py:582-626 (compute_char_obs); envs/ig_parkour/mgdm_dm_util.py:462-518
+// (compute_tar_obs), :304-397 (convert_to_local, compute_deepmimic_reward), :205-230 + :399-460
+// (update_done, compute_done); util/torch_util.py:361-373 (quat_to_tan_norm), :422-431 (quat_diff_angle),
+// :491-499 (calc_heading_quat_inv).
+//
+// Arithmetic: every comparison that decides a flag (distances against thresholds, heights, forces, time)
+// is computed with the explicit *_rn intrinsics in the reference's operation order, so flags are
+// bit-identical unless a rotation ANGLE lands within an ulp of its threshold (atan2f vs the CPU libm).
+#include "parc_common.cuh"
+#include "parc_rotations.cuh"
+
+namespace parc {
+
+#define STEP_WARPS 4
+#define STEP_THREADS (STEP_WARPS * 32)
+
+__device__ __forceinline__ float3 ld3(const float* __restrict__ p) {
+  return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st3(float* __restrict__ p, const float3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// util/torch_util.py:491-499: rotation about +z by -heading(q)
+__device__ __forceinline__ float4 heading_inverse_quat(const float4& q) {
+  return axis_angle_to_quat(make_float3(0.0f, 0.0f, 1.0f), -calc_heading(q));
+}
+
+// util/torch_util.py:361-373: rotated x axis, then rotated z axis
+__device__ __forceinline__ void store_tan_norm(float* __restrict__ o, const float4& q) {
+  st3(o, quat_rotate(q, make_float3(1.0f, 0.0f, 0.0f)));
+  st3(o + 3, quat_rotate(q, make_float3(0.0f, 0.0f, 1.0f)));
+}
+
+// util/torch_util.py:422-431 with :68-88: angle of q1 * conj(q0), w made non-negative, 0 below 1e-5
+__device__ __forceinline__ float quat_diff_angle(const float4& q0, const float4& q1) {
+  float4 d = quat_mul(q1, quat_conj(q0));
+  if (d.w < 0.0f) { d.x = -d.x; d.y = -d.y; d.z = -d.z; d.w = -d.w; }
+  const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+  return len > 1e-5f ? 2.0f * atan2f(len, d.w) : 0.0f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PARC_FULL_MASK, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float3 sub3(const float3& a, const float3& b) {
+  return make_float3(a.x - b.x, a.y - b.y, a.z - b.z);
+}
+__device__ __forceinline__ float sq3(const float3& d) { return d.x * d.x + d.y * d.y + d.z * d.z; }
+
+// ------------------------------------------------------------------------------------------------
+// compute_char_obs: [root_h] | root tan-norm 6 | root_vel 3 | root_ang_vel 3 | joint tan-norm 6(J-1) | dof_vel D | key 3K
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS)
+char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int D, int K, int global_obs,
+                int root_height_obs, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int W = (root_height_obs ? 1 : 0) + 12 + 6 * Jm1 + D + 3 * K;
+  const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    float* __restrict__ o = out + e * W;
+    const float3 rp = ld3(s.root_pos + e * 3);
+    const float4 rr = ld4(s.root_rot + e * 4);
+    const float4 hinv = heading_inverse_quat(rr);
+    if (root_height_obs) {
+      if (lane == 0) o[0] = rp.z;
+      o += 1;
+    }
+    if (lane == 0) {
+      store_tan_norm(o, global_obs ? rr : quat_mul(hinv, rr));
+    } else if (lane == 1) {
+      const float3 v = ld3(s.root_vel + e * 3);
+      st3(o + 6, global_obs ? v : quat_rotate(hinv, v));
+    } else if (lane == 2) {
+      const float3 v = ld3(s.root_ang_vel + e * 3);
+      st3(o + 9, global_obs ? v : quat_rotate(hinv, v));
+    }
+    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 12 + 6 * j, ld4(s.joint_rot + (e * Jm1 + j) * 4));
+    float* __restrict__ ov = o + 12 + 6 * Jm1;
+    for (int d = lane; d < D; d += 32) ov[d] = __ldg(s.dof_vel + e * D + d);
+    float* __restrict__ ok = ov + D;
+    for (int k = lane; k < K; k += 32) {
+      float3 p = sub3(ld3(s.key_pos + (e * K + k) * 3), rp);
+      if (!global_obs) p = quat_rotate(hinv, p);
+      st3(ok + 3 * k, p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_tar_obs: per (env, step)  root_pos_obs 3 | root tan-norm 6 | joint tan-norm 6(J-1) | key 3K
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS)
+tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__ ref_root_rot,
+               const float* __restrict__ tar_root_pos, const float* __restrict__ tar_root_rot,
+               const float* __restrict__ tar_joint_rot, const float* __restrict__ tar_key_pos, int64_t n, int S,
+               int Jm1, int K, int global_obs, int global_tar_root_h, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int W = 9 + 6 * Jm1 + 3 * K;
+  const int64_t total = n * S;
+  const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
+  for (int64_t q = warp0; q < total; q += nwarps) {
+    const int64_t e = q / S;
+    float* __restrict__ o = out + q * W;
+    const float3 tp = ld3(tar_root_pos + q * 3);
+    float4 tr = ld4(tar_root_rot + q * 4);
+    float3 po = sub3(tp, ld3(ref_root_pos + e * 3));
+    float4 hinv = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (!global_obs) {
+      hinv = heading_inverse_quat(ld4(ref_root_rot + e * 4));
+      po = quat_rotate(hinv, po);
+      tr = quat_mul(hinv, tr);
+    }
+    if (lane == 0) {
+      st3(o, make_float3(po.x, po.y, global_tar_root_h ? tp.z : po.z));
+      store_tan_norm(o + 3, tr);
+    }
+    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 9 + 6 * j, ld4(tar_joint_rot + (q * Jm1 + j) * 4));
+    float* __restrict__ ok = o + 9 + 6 * Jm1;
+    for (int k = lane; k < K; k += 32) {
+      float3 p = sub3(ld3(tar_key_pos + (q * K + k) * 3), tp);
+      if (!global_obs) {
+        p = quat_rotate(hinv, p);
+        p.x += po.x; p.y += po.y; p.z += po.z;       // the rotated root offset, BEFORE the height override
+      }
+      st3(ok + 3 * k, p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_deepmimic_reward: [n,5] = exp(-scale * err) for pose, vel, root pose, root vel, key pos
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS)
+deepmimic_reward_kernel(const __grid_constant__ ParcCharState s, const __grid_constant__ ParcCharState t, int64_t n,
+                        int Jm1, int D, int K, const float* __restrict__ joint_w, const float* __restrict__ dof_w,
+                        int track_root_h, int track_root, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    float pose = 0.0f, vel = 0.0f, key = 0.0f;
+    for (int j = lane; j < Jm1; j += 32) {
+      const float a = quat_diff_angle(ld4(s.joint_rot + (e * Jm1 + j) * 4), ld4(t.joint_rot + (e * Jm1 + j) * 4));
+      pose += __ldg(joint_w + j) * a * a;
+    }
+    for (int d = lane; d < D; d += 32) {
+      const float dv = __ldg(t.dof_vel + e * D + d) - __ldg(s.dof_vel + e * D + d);
+      vel += __ldg(dof_w + d) * dv * dv;
+    }
+    const float3 rp = ld3(s.root_pos + e * 3), trp = ld3(t.root_pos + e * 3);
+    float4 rr = ld4(s.root_rot + e * 4), trr = ld4(t.root_rot + e * 4);
+    float3 rv = ld3(s.root_vel + e * 3), trv = ld3(t.root_vel + e * 3);
+    float3 rw = ld3(s.root_ang_vel + e * 3), trw = ld3(t.root_ang_vel + e * 3);
+    float3 dp = sub3(trp, rp);
+    if (!track_root) dp.x = dp.y = 0.0f;
+    if (!track_root_h) dp.z = 0.0f;
+    float4 hs = make_float4(0.f, 0.f, 0.f, 1.f), ht = hs;
+    if (!track_root) {                                 // convert_to_local: each side in its OWN heading frame
+      hs = heading_inverse_quat(rr);
+      ht = heading_inverse_quat(trr);
+      rv = quat_rotate(hs, rv); rw = quat_rotate(hs, rw); rr = quat_mul(hs, rr);
+      trv = quat_rotate(ht, trv); trw = quat_rotate(ht, trw); trr = quat_mul(ht, trr);
+    }
+    for (int k = lane; k < K; k += 32) {
+      float3 a = sub3(ld3(s.key_pos + (e * K + k) * 3), rp);
+      float3 b = sub3(ld3(t.key_pos + (e * K + k) * 3), trp);
+      if (!track_root) { a = quat_rotate(hs, a); b = quat_rotate(ht, b); }
+      key += sq3(sub3(b, a));
+    }
+    pose = warp_sum(pose);
+    vel = warp_sum(vel);
+    key = warp_sum(key);
+    if (lane == 0) {
+      const float ra = quat_diff_angle(rr, trr);
+      const float root_pose = sq3(dp) + 0.1f * (ra * ra);
+      const float root_vel = sq3(sub3(trv, rv)) + 0.1f * sq3(sub3(trw, rw));
+      float* __restrict__ o = out + e * 5;
+      o[0] = expf(-0.25f * pose);
+      o[1] = expf(-0.01f * vel);
+      o[2] = expf(-5.0f * root_pose);
+      o[3] = expf(-1.0f * root_vel);
+      o[4] = expf(-10.0f * key);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_done (+ the termination-height lookup of RefCharEnv.update_done): int32 flag per env
+// ------------------------------------------------------------------------------------------------
+struct DoneParams {
+  const float* time;
+  const float* root_rot;
+  const float* body_pos;
+  const float* tar_root_rot;
+  const float* tar_body_pos;
+  const float* contact_force;
+  const float* term_heights;      // [n,J] precomputed, or NULL -> sampled from hf at body xy + env_offsets
+  const float* env_offsets;       // [n, offset_stride] (first two columns used) or NULL
+  const float* pose_dist;         // [J-1]
+  ParcHeightfield hf;
+  int offset_stride;
+  float termination_height;
+  float ep_len, first_step_eps, force_eps, root_pos_dist_sq, root_rot_angle;
+  uint32_t contact_body_mask;
+  int has_contact_bodies, pose_termination, early_termination, track_root;
+  int J;
+};
+
+__global__ void __launch_bounds__(STEP_THREADS)
+done_kernel(const __grid_constant__ DoneParams p, int64_t n, int32_t* __restrict__ done,
+            float* __restrict__ term_heights_out) {
+  const int lane = threadIdx.x & 31;
+  const int J = p.J;
+  const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    const float tm = __ldg(p.time + e);
+    int flag = PARC_DONE_NULL;
+    if (tm >= p.ep_len) flag = PARC_DONE_TIME;
+    const bool body = lane < J;
+    float3 bp = make_float3(0.f, 0.f, 0.f);
+    if (body) bp = ld3(p.body_pos + (e * J + lane) * 3);
+    float th = 0.0f;
+    const bool need_heights = (p.early_termination && p.has_contact_bodies) || term_heights_out;
+    if (body && need_heights) {
+      if (p.term_heights) {
+        th = __ldg(p.term_heights + e * J + lane);
+      } else {
+        float gx = bp.x, gy = bp.y;
+        if (p.env_offsets) {
+          gx = add_rn(gx, __ldg(p.env_offsets + e * p.offset_stride));
+          gy = add_rn(gy, __ldg(p.env_offsets + e * p.offset_stride + 1));
+        }
+        th = add_rn(hf_lookup(p.hf, gx, gy), p.termination_height);
+      }
+      if (term_heights_out) term_heights_out[e * J + lane] = th;
+    }
+    if (p.early_termination) {
+      bool failed = false;
+      if (p.has_contact_bodies) {
+        const bool counted = body && !((p.contact_body_mask >> lane) & 1u);
+        bool touched = false;
+        if (counted) {
+          const float3 f = ld3(p.contact_force + (e * J + lane) * 3);
+          touched = fabsf(f.x) > p.force_eps || fabsf(f.y) > p.force_eps || fabsf(f.z) > p.force_eps;
+        }
+        const bool low = counted && bp.z < th;
+        const bool any_touch = __any_sync(PARC_FULL_MASK, touched);
+        const bool any_low = __any_sync(PARC_FULL_MASK, low);
+        failed = any_touch && any_low;
+      }
+      if (p.pose_termination) {
+        float3 tb = make_float3(0.f, 0.f, 0.f);
+        if (body) tb = ld3(p.tar_body_pos + (e * J + lane) * 3);
+        const float3 r0 = shfl3(bp, 0), t0 = shfl3(tb, 0);
+        bool bad = false;
+        if (body && lane > 0) {
+          const float dx = sub_rn(sub_rn(tb.x, t0.x), sub_rn(bp.x, r0.x));
+          const float dy = sub_rn(sub_rn(tb.y, t0.y), sub_rn(bp.y, r0.y));
+          const float dz = sub_rn(sub_rn(tb.z, t0.z), sub_rn(bp.z, r0.z));
+          const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+          const float lim = __ldg(p.pose_dist + lane - 1);
+          bad = d2 > mul_rn(lim, lim);
+        } else if (lane == 0 && p.track_root) {
+          const float dx = sub_rn(bp.x, tb.x), dy = sub_rn(bp.y, tb.y), dz = sub_rn(bp.z, tb.z);
+          const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+          const float ang = quat_diff_angle(ld4(p.root_rot + e * 4), ld4(p.tar_root_rot + e * 4));
+          bad = d2 > p.root_pos_dist_sq || fabsf(ang) > p.root_rot_angle;
+        }
+        failed = failed || __any_sync(PARC_FULL_MASK, bad);
+      }
+      if (failed && tm > p.first_step_eps) flag = PARC_DONE_FAIL;
+    }
+    if (lane == 0 && done) done[e] = flag;
+  }
+}
+
+static int warp_grid(int64_t warps) {
+  int64_t b = (warps + STEP_WARPS - 1) / STEP_WARPS;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)(b > 0 ? b : 1);
+}
+
+static int check_state(const ParcCharState* s, int D, int K, bool need_vel) {
+  if (!s) return PARC_E_NULL;
+  if (!s->root_pos || !s->root_rot || !s->joint_rot) return PARC_E_NULL;
+  if (need_vel && (!s->root_vel || !s->root_ang_vel || (D > 0 && !s->dof_vel))) return PARC_E_NULL;
+  if (K > 0 && !s->key_pos) return PARC_E_NULL;
+  if (!aligned16(s->root_rot) || !aligned16(s->joint_rot)) return PARC_E_ALIGN;
+  return PARC_OK;
+}
+
+}  // namespace parc
+
+using namespace parc;
+
+extern "C" int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_joint_rots, int32_t dof_size,
+                             int32_t num_keys, int32_t global_obs, int32_t root_height_obs, float* obs_out,
+                             void* stream) {
+  if (n < 0 || num_joint_rots < 0 || dof_size < 0 || num_keys < 0) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  int rc = check_state(state, dof_size, num_keys, true);
+  if (rc) return rc;
+  if (!obs_out) return PARC_E_NULL;
+  char_obs_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(*state, n, num_joint_rots, dof_size,
+                                                                         num_keys, global_obs, root_height_obs, obs_out);
+  return check_launch();
+}
+
+extern "C" int parc_tar_obs(const float* ref_root_pos, const float* ref_root_rot, const float* tar_root_pos,
+                            const float* tar_root_rot, const float* tar_joint_rot, const float* tar_key_pos,
+                            int64_t n, int32_t num_steps, int32_t num_joint_rots, int32_t num_keys,
+                            int32_t global_obs, int32_t global_tar_root_h_obs, float* obs_out, void* stream) {
+  if (n < 0 || num_steps < 0 || num_joint_rots < 0 || num_keys < 0) return PARC_E_SIZE;
+  if (n == 0 || num_steps == 0) return PARC_OK;
+  if (!ref_root_pos || !ref_root_rot || !tar_root_pos || !tar_root_rot || !obs_out) return PARC_E_NULL;
+  if ((num_joint_rots > 0 && !tar_joint_rot) || (num_keys > 0 && !tar_key_pos)) return PARC_E_NULL;
+  if (!aligned16(ref_root_rot) || !aligned16(tar_root_rot) || !aligned16(tar_joint_rot)) return PARC_E_ALIGN;
+  tar_obs_kernel<<<warp_grid(n * num_steps), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+      ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot, tar_key_pos, n, num_steps,
+      num_joint_rots, num_keys, global_obs, global_tar_root_h_obs, obs_out);
+  return check_launch();
+}
+
+extern "C" int parc_deepmimic_reward(const ParcCharState* sim, const ParcCharState* tar, int64_t n,
+                                     int32_t num_joint_rots, int32_t dof_size, int32_t num_keys,
+                                     const float* joint_rot_err_w, const float* dof_err_w, int32_t track_root_h,
+                                     int32_t track_root, float* reward_out, void* stream) {
+  if (n < 0 || num_joint_rots < 0 || dof_size < 0 || num_keys < 0) return PARC_E_SIZE;
+  if (num_keys == 0) return PARC_E_SIZE;      // the reference cannot stack an empty key term either (:395-397)
+  if (n == 0) return PARC_OK;
+  int rc = check_state(sim, dof_size, num_keys, true);
+  if (rc) return rc;
+  rc = check_state(tar, dof_size, num_keys, true);
+  if (rc) return rc;
+  if (!reward_out || (num_joint_rots > 0 && !joint_rot_err_w) || (dof_size > 0 && !dof_err_w)) return PARC_E_NULL;
+  deepmimic_reward_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+      *sim, *tar, n, num_joint_rots, dof_size, num_keys, joint_rot_err_w, dof_err_w, track_root_h, track_root,
+      reward_out);
+  return check_launch();
+}
+
+extern "C" int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
+                         const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
+                         const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
+                         int32_t offset_stride, int64_t n, int32_t num_bodies, int32_t* done_out,
+                         float* term_heights_out, void* stream) {
+  if (!spec) return PARC_E_NULL;
+  if (n < 0 || num_bodies < 1 || num_bodies > PARC_MAX_BODIES) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!time || !body_pos || (!done_out && !term_heights_out)) return PARC_E_NULL;
+  const bool early = spec->enable_early_termination != 0;
+  const bool fall = early && spec->has_contact_bodies;
+  if (fall && !contact_force) return PARC_E_NULL;
+  if ((fall || term_heights_out) && !term_heights) {
+    if (!hf || !hf->hf) return PARC_E_NULL;
+    if (hf->dim_x <= 0 || hf->dim_y <= 0) return PARC_E_SIZE;
+    if (env_offsets && offset_stride < 2) return PARC_E_SIZE;
+  }
+  if (early && spec->pose_termination) {
+    if (!tar_body_pos || !spec->pose_termination_dist) return PARC_E_NULL;
+    if (spec->track_root && (!root_rot || !tar_root_rot)) return PARC_E_NULL;
+    if (spec->track_root && (!aligned16(root_rot) || !aligned16(tar_root_rot))) return PARC_E_ALIGN;
+  }
+  DoneParams p{};
+  p.time = time; p.root_rot = root_rot; p.body_pos = body_pos; p.tar_root_rot = tar_root_rot;
+  p.tar_body_pos = tar_body_pos; p.contact_force = contact_force; p.term_heights = term_heights;
+  p.env_offsets = env_offsets; p.pose_dist = spec->pose_termination_dist;
+  if (hf) p.hf = *hf;
+  p.offset_stride = offset_stride;
+  // python-float scalars meet fp32 tensors as fp32 values; products of two scalars are formed in double first
+  p.termination_height = (float)spec->termination_height;
+  p.ep_len = (float)spec->episode_length;
+  p.first_step_eps = (float)1e-5;
+  p.force_eps = (float)0.1;
+  p.root_pos_dist_sq = (float)(spec->root_pos_termination_dist * spec->root_pos_termination_dist);
+  p.root_rot_angle = (float)spec->root_rot_termination_angle;
+  p.contact_body_mask = spec->contact_body_mask;
+  p.has_contact_bodies = spec->has_contact_bodies; p.pose_termination = spec->pose_termination;
+  p.early_termination = spec->enable_early_termination; p.track_root = spec->track_root;
+  p.J = num_bodies;
+  done_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, n, done_out, term_heights_out);
+  return check_launch();
+}

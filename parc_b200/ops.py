@@ -13,9 +13,9 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ParcBodyPoints, ParcCharModel, ParcKeyBodies, ParcClipMeta, ParcFkOut, ParcFrameOut, ParcHeightfield,
-                   ParcMotionTables, ParcObsSpec, ParcRowLayout, ParcTerrainBatch, check, f32c, ptr,
-                   require_cuda, stream_ptr)
+from ._lib import (ParcBodyPoints, ParcCharModel, ParcCharState, ParcDoneSpec, ParcKeyBodies, ParcClipMeta, ParcFkOut,
+                   ParcFrameOut, ParcHeightfield, ParcMotionTables, ParcObsSpec, ParcRowLayout, ParcTerrainBatch, check,
+                   f32c, ptr, require_cuda, stream_ptr)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -700,3 +700,133 @@ def unpack_frame_masks(bits: torch.Tensor, X: int, Y: int) -> torch.Tensor:
     shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
     b = ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
     return b.reshape(*bits.shape[:-1], -1)[..., :X * Y].reshape(*bits.shape[:-1], X, Y)
+
+
+# ----------------------------------------------------------------------------------------------
+# tracker step assembly: policy observation, reward, done -- one launch each
+# ----------------------------------------------------------------------------------------------
+def _has(t: Optional[torch.Tensor]) -> bool:
+    return t is not None and t.numel() > 0
+
+
+def _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos):
+    """-> (ParcCharState, tensors kept alive, n, J-1, D, K)"""
+    keep = [f32c(root_pos), f32c(root_rot), f32c(root_vel), f32c(root_ang_vel), f32c(joint_rot), f32c(dof_vel),
+            f32c(key_pos) if _has(key_pos) else None]
+    require_cuda(*keep)
+    n = keep[0].shape[0]
+    jm1, d = keep[4].shape[-2], keep[5].shape[-1]
+    k = keep[6].shape[-2] if keep[6] is not None else 0
+    assert keep[0].shape == (n, 3) and keep[1].shape == (n, 4) and keep[2].shape == (n, 3) and keep[3].shape == (n, 3)
+    assert keep[4].shape == (n, jm1, 4) and keep[5].shape == (n, d) and (k == 0 or keep[6].shape == (n, k, 3))
+    st = ParcCharState()
+    (st.root_pos, st.root_rot, st.root_vel, st.root_ang_vel, st.joint_rot, st.dof_vel,
+     st.key_pos) = [ptr(t) for t in keep]
+    return st, keep, n, jm1, d, k
+
+
+def char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos, global_obs: bool,
+             root_height_obs: bool) -> torch.Tensor:
+    """compute_char_obs (envs/ig_char_env.py:582-626) -> [n, W]; key_pos [n,K,3] or empty/None.  One launch."""
+    st, keep, n, jm1, d, k = _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos)
+    dev = keep[0].device
+    out = torch.empty((n, (1 if root_height_obs else 0) + 12 + 6 * jm1 + d + 3 * k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_char_obs(C.byref(st), n, jm1, d, k, int(bool(global_obs)), int(bool(root_height_obs)),
+                                       out.data_ptr(), stream_ptr(dev))
+    check(rc, "parc_char_obs")
+    return out
+
+
+def tar_obs(ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot, tar_key_pos, global_obs: bool,
+            global_tar_root_h_obs: bool) -> torch.Tensor:
+    """compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): targets [n,S,...] -> [n,S,W].  One launch."""
+    rp, rr, tp, tr, tj = (f32c(t) for t in (ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot))
+    tk = f32c(tar_key_pos) if _has(tar_key_pos) else None
+    require_cuda(rp, rr, tp, tr, tj, tk)
+    n, S, jm1 = tp.shape[0], tp.shape[1], tj.shape[-2]
+    k = tk.shape[-2] if tk is not None else 0
+    assert rp.shape == (n, 3) and rr.shape == (n, 4) and tp.shape == (n, S, 3) and tr.shape == (n, S, 4)
+    assert tj.shape == (n, S, jm1, 4) and (k == 0 or tk.shape == (n, S, k, 3))
+    out = torch.empty((n, S, 9 + 6 * jm1 + 3 * k), dtype=torch.float32, device=tp.device)
+    with torch.cuda.device(tp.device):
+        rc = _lib.load().parc_tar_obs(rp.data_ptr(), rr.data_ptr(), tp.data_ptr(), tr.data_ptr(), tj.data_ptr(), ptr(tk),
+                                      n, S, jm1, k, int(bool(global_obs)), int(bool(global_tar_root_h_obs)),
+                                      out.data_ptr(), stream_ptr(tp.device))
+    check(rc, "parc_tar_obs")
+    return out
+
+
+def deepmimic_reward(sim: tuple, tar: tuple, joint_rot_err_w, dof_err_w, track_root_h: bool, track_root: bool):
+    """compute_deepmimic_reward (envs/ig_parkour/mgdm_dm_util.py:328-397).  sim / tar are 7-tuples
+    (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos) -> [n,5].  One launch."""
+    if not _has(sim[6]) or not _has(tar[6]):
+        raise ValueError("compute_deepmimic_reward needs key bodies (the reference fails to stack its terms without)")
+    s, keep_s, n, jm1, d, k = _char_state(*sim)
+    t, keep_t, n2, jm2, d2, k2 = _char_state(*tar)
+    assert (n, jm1, d, k) == (n2, jm2, d2, k2)
+    jw, dw = f32c(joint_rot_err_w), f32c(dof_err_w)
+    require_cuda(jw, dw)
+    assert jw.shape == (jm1,) and dw.shape == (d,)
+    dev = keep_s[0].device
+    out = torch.empty((n, 5), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_deepmimic_reward(C.byref(s), C.byref(t), n, jm1, d, k, jw.data_ptr(), dw.data_ptr(),
+                                               int(bool(track_root_h)), int(bool(track_root)), out.data_ptr(),
+                                               stream_ptr(dev))
+    check(rc, "parc_deepmimic_reward")
+    return out
+
+
+def done_flags(time, ep_len: float, root_rot, body_pos, tar_root_rot, tar_body_pos, contact_force,
+               contact_body_ids, pose_termination: bool, pose_termination_dist, enable_early_termination: bool,
+               track_root: bool, root_pos_termination_dist: float, root_rot_termination_angle: float, *,
+               termination_heights: Optional[torch.Tensor] = None, hf: Optional[HeightfieldDesc] = None,
+               env_offsets: Optional[torch.Tensor] = None, termination_height: float = 0.0,
+               want_heights: bool = False):
+    """compute_done (envs/ig_parkour/mgdm_dm_util.py:399-460) -> int32 [n].  Heights under the bodies come
+    either from `termination_heights` [n,J] (the reference function's own argument) or are sampled in the same
+    launch from `hf` at body xy + env_offsets[:, 0:2] plus `termination_height` (RefCharEnv.update_done,
+    :205-210).  contact_body_ids: python sequence / tensor of body ids allowed to touch (host-side: it is
+    configuration, and becomes a bit mask).  One launch."""
+    tm, bp = f32c(time), f32c(body_pos)
+    require_cuda(tm, bp)
+    n, J = bp.shape[0], bp.shape[1]
+    dev = bp.device
+    ids = [int(i) for i in (contact_body_ids.tolist() if torch.is_tensor(contact_body_ids) else contact_body_ids)]
+    spec = ParcDoneSpec()
+    spec.episode_length = float(ep_len)
+    spec.termination_height = float(termination_height)
+    spec.root_pos_termination_dist = float(root_pos_termination_dist)
+    spec.root_rot_termination_angle = float(root_rot_termination_angle)
+    ptd = f32c(pose_termination_dist) if pose_termination_dist is not None else None
+    require_cuda(ptd)
+    spec.pose_termination_dist = ptr(ptd)
+    mask = 0
+    for i in ids:
+        assert 0 <= i < J
+        mask |= 1 << i
+    spec.contact_body_mask = mask
+    spec.has_contact_bodies = int(len(ids) > 0)
+    spec.pose_termination = int(bool(pose_termination))
+    spec.enable_early_termination = int(bool(enable_early_termination))
+    spec.track_root = int(bool(track_root))
+    rr = f32c(root_rot) if root_rot is not None else None
+    trr = f32c(tar_root_rot) if tar_root_rot is not None else None
+    tbp = f32c(tar_body_pos) if tar_body_pos is not None else None
+    cf = f32c(contact_force) if contact_force is not None else None
+    th = f32c(termination_heights) if termination_heights is not None else None
+    eo = f32c(env_offsets) if env_offsets is not None else None
+    require_cuda(rr, trr, tbp, cf, th, eo)
+    if ptd is not None:
+        assert ptd.shape == (J - 1,)
+    hfs = hf.c_struct() if hf is not None else ParcHeightfield()
+    out = torch.empty((n,), dtype=torch.int32, device=dev)
+    th_out = torch.empty((n, J), dtype=torch.float32, device=dev) if want_heights else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_done(C.byref(spec), tm.data_ptr(), ptr(rr), bp.data_ptr(), ptr(trr), ptr(tbp), ptr(cf),
+                                   ptr(th), C.byref(hfs) if hf is not None else None, ptr(eo),
+                                   int(eo.shape[-1]) if eo is not None else 0, n, J, out.data_ptr(), ptr(th_out),
+                                   stream_ptr(dev))
+    check(rc, "parc_done")
+    return (out, th_out) if want_heights else out

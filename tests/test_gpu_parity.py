@@ -913,3 +913,166 @@ def test_full_size_frames_fk_split_and_cross_kernel_consistency(gpu_model):
     bp3, _ = ops.frames_fk(gpu_model.c_model(), fr[1000001:2000000])
     assert torch.equal(bp3, bp[1000001:2000000])
     assert torch.isfinite(bp).all()
+
+
+# ----------------------------------------------------------------------------------------- f3: tracker step assembly
+def _cu(x):
+    return torch.as_tensor(np.asarray(x)).cuda()
+
+
+def _step_golden():
+    g = golden("tracker_step_golden.npz")
+    names = ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel")
+    sim = tuple(_cu(g[k]) for k in names)
+    ref = tuple(_cu(g["ref_" + k]) for k in names)
+    return g, sim, ref, _cu(g["key_ids"]).long()
+
+
+def test_step_char_and_tar_obs_match_reference():
+    from parc_b200.envs import ig_char_env
+    from parc_b200.envs.ig_parkour import mgdm_dm_util as dm
+    g, sim, ref, key_ids = _step_golden()
+    key = _cu(g["body_pos"])[:, key_ids]
+    none = torch.zeros([0], device="cuda")
+    tar = tuple(_cu(g["tar_" + k]) for k in ("root_pos", "root_rot", "joint_rot", "key_pos"))
+    for gl in (0, 1):
+        for h in (0, 1):
+            o = ig_char_env.compute_char_obs(*sim, key, bool(gl), bool(h))
+            assert_close(o, g[f"char_obs_g{gl}_h{h}"], what=f"char_obs g{gl} h{h}")
+            o = dm.compute_tar_obs(sim[0], sim[1], *tar, bool(gl), bool(h))
+            assert_close(o, g[f"tar_obs_g{gl}_h{h}"], what=f"tar_obs g{gl} h{h}")
+    assert_close(ig_char_env.compute_char_obs(*sim, none, False, False), g["char_obs_nokey"])
+    assert_close(dm.compute_tar_obs(sim[0], sim[1], tar[0], tar[1], tar[2], none, False, False), g["tar_obs_nokey"])
+    d = dm.compute_deepmimic_obs(*sim, key, False, False, True, *tar)
+    assert list(d) == ["char_obs", "tar_obs"]
+    assert_close(d["tar_obs"], g["tar_obs_g0_h0"])
+    # empty batch (an empty key tensor means "no key bodies", as in the reference)
+    e = ig_char_env.compute_char_obs(*(t[:0] for t in sim), key[:0], False, False)
+    assert e.shape == (0, g["char_obs_nokey"].shape[1])
+
+
+def test_step_reward_matches_reference():
+    from parc_b200.envs.ig_parkour import mgdm_dm_util as dm
+    g, sim, ref, key_ids = _step_golden()
+    key, ref_key = _cu(g["body_pos"])[:, key_ids], _cu(g["ref_body_pos"])[:, key_ids]
+    jw, dw = _cu(g["joint_err_w"]), _cu(g["dof_err_w"])
+    for tr in (1, 0):
+        for th in (1, 0):
+            r = dm.compute_deepmimic_reward(*sim, key, *ref, ref_key, jw, dw, bool(th), bool(tr))
+            assert_close(r, g[f"reward_r{tr}_h{th}"], what=f"reward track_root={tr} track_h={th}")
+    with pytest.raises(ValueError):
+        none = torch.zeros([0], device="cuda")
+        dm.compute_deepmimic_reward(*sim, none, *ref, none, jw, dw, True, True)
+    # identical states: every error is exactly zero -> all five rewards are exactly 1
+    r = dm.compute_deepmimic_reward(*ref, ref_key, *ref, ref_key, jw, dw, True, True)
+    assert torch.equal(r, torch.ones_like(r))
+
+
+def test_step_done_flags_bit_exact():
+    from parc_b200.envs.ig_parkour import mgdm_dm_util as dm
+    from parc_b200.util.terrain_util import SubTerrain
+    g, sim, ref, key_ids = _step_golden()
+    n = sim[0].shape[0]
+    feet = _cu(g["feet"]).long()
+    bp, rbp = _cu(g["body_pos"]), _cu(g["ref_body_pos"])
+    tm, cf, ptd = _cu(g["time_buf"]), _cu(g["contact_forces"]), _cu(g["pose_termination_dist"])
+    th = _cu(g["term_heights"])
+    done_in = torch.zeros(n, dtype=torch.int, device="cuda")
+    cases = {"default": (torch.zeros([0], dtype=torch.long, device="cuda"), True, True, True),
+             "feet": (feet, True, True, True), "feet_nopose": (feet, False, True, True),
+             "noroot": (feet, True, True, False), "noearly": (feet, True, False, True)}
+    terr = SubTerrain("step", g["hf"].shape[0], g["hf"].shape[1], float(g["hf_dxdy"][0]), float(g["hf_dxdy"][1]),
+                      float(g["hf_min"][0]), float(g["hf_min"][1]), device="cuda")
+    terr.hf[...] = _cu(g["hf"])
+    for tag, (cids, pose, early, track) in cases.items():
+        d = dm.compute_done(done_in, tm, 10.0, sim[1], bp, sim[0], ref[1], rbp, cf, cids, th, pose, ptd, False, early,
+                            track, 0.6, 1.309)
+        assert d.dtype == torch.int32 and torch.equal(d.cpu(), torch.as_tensor(g["done_" + tag])), tag
+        # the fused form: heights sampled in the same launch
+        buf = torch.full((n,), 7, dtype=torch.int, device="cuda")
+        dm.update_done(buf, tm, terr, _cu(g["env_offsets"]), 0.15, 10.0, cids, pose, ptd, False, early, track, 0.6, 1.309,
+                       sim[1], bp, ref[1], rbp, cf)
+        assert torch.equal(buf.cpu(), torch.as_tensor(g["done_" + tag])), tag + " (fused heights)"
+    from parc_b200 import ops
+    _, hts = ops.done_flags(tm, 10.0, sim[1], bp, ref[1], rbp, cf, [], True, ptd, True, True, 0.6, 1.309,
+                            hf=terr.hf_desc(), env_offsets=_cu(g["env_offsets"]), termination_height=0.15,
+                            want_heights=True)
+    assert torch.equal(hts.cpu(), torch.as_tensor(g["term_heights"]))
+    d64 = dm.compute_done(done_in.long(), tm, 10.0, sim[1], bp, sim[0], ref[1], rbp, cf, feet, th, True, ptd, False, True,
+                          True, 0.6, 1.309)
+    assert d64.dtype == torch.int64
+
+
+def test_step_assembly_matches_oracle_on_a_generic_tree():
+    """A 21-body random tree, 1000 envs, 3 key bodies, thresholds chosen from the data's own quantiles so that every
+    branch splits the batch: values to 1e-5, flags bit-exact."""
+    from parc_b200 import ops
+    from conftest import make_random_tree_model
+    from oracle import parc_oracle as O
+    model_o, _ = make_random_tree_model(21, seed=9)
+    J, D = 21, model_o.dof_size
+    gen = torch.Generator().manual_seed(5)
+    n, S = 1000, 4
+
+    def rq(*shape):
+        q = torch.randn(*shape, 4, generator=gen)
+        return q / q.norm(dim=-1, keepdim=True)
+
+    def state(noise_of=None, amp=0.3):
+        if noise_of is None:
+            return [torch.randn(n, 3, generator=gen), rq(n), torch.randn(n, 3, generator=gen),
+                    torch.randn(n, 3, generator=gen), rq(n, J - 1), torch.randn(n, D, generator=gen)]
+        out = []
+        for t in noise_of:
+            x = t + amp * torch.rand(n, *([1] * (t.dim() - 1)), generator=gen) * torch.randn(t.shape, generator=gen)
+            out.append(x / x.norm(dim=-1, keepdim=True) if t.shape[-1] == 4 else x)
+        return out
+
+    ref = state()
+    sim = state(ref)
+    rbp, _ = O.forward_kinematics(model_o, ref[0], ref[1], ref[4])
+    sbp, _ = O.forward_kinematics(model_o, sim[0], sim[1], sim[4])
+    key_ids = torch.tensor([4, 11, 20])
+    jw, dw = torch.rand(J - 1, generator=gen), torch.rand(D, generator=gen)
+    tar = [torch.randn(n, S, 3, generator=gen), rq(n, S), rq(n, S, J - 1), torch.randn(n, S, 3, 3, generator=gen)]
+    c = lambda ts: [t.cuda() for t in ts]
+    for gl in (False, True):
+        # randn positions reach |4|: components that cancel to ~0 carry the rounding of their O(4) terms -> atol 4e-6
+        assert_close(ops.char_obs(*c(sim), sbp[:, key_ids].cuda(), gl, True),
+                     O.compute_char_obs(*sim, sbp[:, key_ids], gl, True), atol=4e-6, what="char_obs")
+        assert_close(ops.tar_obs(sim[0].cuda(), sim[1].cuda(), *c(tar), gl, not gl),
+                     O.compute_tar_obs(sim[0], sim[1], *tar, gl, not gl), atol=4e-6, what="tar_obs")
+    for tr in (True, False):
+        r = ops.deepmimic_reward(tuple(c(sim)) + (sbp[:, key_ids].cuda(),), tuple(c(ref)) + (rbp[:, key_ids].cuda(),),
+                                 jw.cuda(), dw.cuda(), tr, tr)
+        assert_close(r, O.compute_deepmimic_reward(*sim, sbp[:, key_ids], *ref, rbp[:, key_ids], jw, dw, tr, tr),
+                     what="reward")
+    # done: thresholds at data quantiles
+    d = (rbp[:, 1:] - rbp[:, :1]) - (sbp[:, 1:] - sbp[:, :1])
+    ptd = (d * d).sum(-1).sqrt().quantile(0.97, dim=0)
+    root_d = float((sbp[:, 0] - rbp[:, 0]).norm(dim=-1).quantile(0.8))
+    ang = float(O.quat_diff_angle(sim[1], ref[1]).abs().quantile(0.8))
+    hf = torch.rand(24, 20, generator=gen) * 2 - 1
+    terr_o = O.Terrain(hf=hf, min_point=torch.tensor([-2.0, -2.0]), dxdy=torch.tensor([0.25, 0.25]))
+    off = torch.randn(n, 3, generator=gen)
+    th = O.termination_heights(terr_o, sbp, off, 0.2)
+    tm = torch.rand(n, generator=gen) * 6
+    tm[:10] = 0
+    cf = torch.randn(n, J, 3, generator=gen) * (torch.rand(n, J, 1, generator=gen) < 0.05)
+    allowed = torch.tensor([0, 7, 8, 19])
+    hfd = ops.HeightfieldDesc(hf=hf.cuda(), min_x=-2.0, min_y=-2.0, dx=0.25, dy=0.25)
+    seen = set()
+    for cids in (allowed, torch.zeros([0], dtype=torch.long)):
+        for pose in (True, False):
+            for track in (True, False):
+                want = O.compute_done(torch.zeros(n, dtype=torch.int), tm, 5.0, sim[1], sbp, ref[1], rbp, cf, cids, th,
+                                      pose, ptd, True, track, root_d, ang)
+                got = ops.done_flags(tm.cuda(), 5.0, sim[1].cuda(), sbp.cuda(), ref[1].cuda(), rbp.cuda(), cf.cuda(),
+                                     cids.tolist(), pose, ptd.cuda(), True, track, root_d, ang, hf=hfd,
+                                     env_offsets=off.cuda(), termination_height=0.2)
+                mism = (got.cpu() != want)
+                # a root angle within 1e-6 of its threshold may legitimately land on either side (libm atan2)
+                close = (O.quat_diff_angle(sim[1], ref[1]).abs() - ang).abs() < 1e-6
+                assert not (mism & ~close).any(), (int(mism.sum()), cids.tolist(), pose, track)
+                seen |= set(want.tolist())
+    assert seen == {0, 1, 3}

@@ -124,3 +124,48 @@ def test_contact_labelling_and_masks(oracle_model):
     assert [i.shape[0] for i in inds] == g["mask_counts"].tolist()
     assert torch.equal(torch.cat(inds), T(g["mask_inds"]))
     assert_close(minh, g["min_body_heights"], rtol=1e-6, atol=1e-6, what="min body heights")
+
+
+def _step_states(g):
+    sim = tuple(T(g[k]) for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel"))
+    ref = tuple(T(g["ref_" + k]) for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel"))
+    key_ids = T(g["key_ids"]).long()
+    return sim, ref, key_ids
+
+
+def test_tracker_step_obs_reward_done():
+    """§8(f)-3: compute_char_obs / compute_tar_obs / compute_deepmimic_reward / compute_done restatements against
+    the reference's outputs (flags bit-exact; values to 1e-6 across libm builds)."""
+    g = golden("tracker_step_golden.npz")
+    sim, ref, key_ids = _step_states(g)
+    key = T(g["body_pos"])[:, key_ids]
+    none = torch.zeros([0])
+    tar = tuple(T(g["tar_" + k]) for k in ("root_pos", "root_rot", "joint_rot", "key_pos"))
+    for gl in (0, 1):
+        for h in (0, 1):
+            assert_close(O.compute_char_obs(*sim, key, bool(gl), bool(h)), g[f"char_obs_g{gl}_h{h}"], what="char_obs")
+            assert_close(O.compute_tar_obs(sim[0], sim[1], *tar, bool(gl), bool(h)), g[f"tar_obs_g{gl}_h{h}"],
+                         what="tar_obs")
+    assert_close(O.compute_char_obs(*sim, none, False, False), g["char_obs_nokey"])
+    assert_close(O.compute_tar_obs(sim[0], sim[1], tar[0], tar[1], tar[2], none, False, False), g["tar_obs_nokey"])
+    jw, dw = T(g["joint_err_w"]), T(g["dof_err_w"])
+    ref_key = T(g["ref_body_pos"])[:, key_ids]
+    for tr in (1, 0):
+        for th in (1, 0):
+            r = O.compute_deepmimic_reward(*sim, key, *ref, ref_key, jw, dw, bool(th), bool(tr))
+            assert_close(r, g[f"reward_r{tr}_h{th}"], what="reward")
+    terr = O.Terrain(hf=T(g["hf"]), min_point=T(g["hf_min"]), dxdy=T(g["hf_dxdy"]))
+    th = O.termination_heights(terr, T(g["body_pos"]), T(g["env_offsets"]), 0.15)
+    assert torch.equal(th, T(g["term_heights"]))
+    feet = T(g["feet"]).long()
+    done_in = torch.zeros(sim[0].shape[0], dtype=torch.int)
+    common = (done_in, T(g["time_buf"]), 10.0, sim[1], T(g["body_pos"]), ref[1], T(g["ref_body_pos"]),
+              T(g["contact_forces"]))
+    ptd = T(g["pose_termination_dist"])
+    cases = {"default": (torch.zeros([0], dtype=torch.long), True, True, True), "feet": (feet, True, True, True),
+             "feet_nopose": (feet, False, True, True), "noroot": (feet, True, True, False),
+             "noearly": (feet, True, False, True)}
+    for tag, (cids, pose, early, track) in cases.items():
+        d = O.compute_done(*common, cids, th, pose, ptd, early, track, 0.6, 1.309)
+        assert d.dtype == torch.int32 and torch.equal(d, T(g["done_" + tag])), tag
+    assert set(np.unique(g["done_feet"])) == {0, 1, 3}                    # every flag value is exercised
