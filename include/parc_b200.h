@@ -161,12 +161,16 @@ int parc_motion_query(const ParcMotionTables* tables, const int64_t* motion_ids,
  * (query q = e * num_steps + k; outputs are [n, num_steps, ...], i.e. [n * num_steps, ...] rows) -- what the
  * tracker does every control step: the reference frame (dm_env.py:570-595) plus the future targets of
  * fetch_tar_obs_data (envs/ig_parkour/mgdm_dm_util.py:279-302: ids tiled, motion_times + timestep *
- * tar_obs_steps, one fp32 add as there).  Pass time_offsets[0] = 0 for the current frame.  The heightmap
- * observation, if requested, is produced for step 0 of each entry only: obs_out is [n, num_points]. */
+ * tar_obs_steps, one fp32 add as there).  Pass time_offsets[0] = 0 for the current frame (time_offsets may be
+ * NULL when num_steps == 1).  The heightmap observation, if requested, is produced for step 0 of each entry
+ * only: obs_out is [n, num_points].
+ * root_xy_offset (device [n,2] float32, 8-byte aligned, or NULL): where each entry's motion sits on the shared
+ * terrain -- added to root x,y of every step after the query and before FK / the observation, i.e.
+ * DMEnv._move_to_motion_terrain (envs/ig_parkour/dm_env.py:604-615, applied at :575 and :701). */
 int parc_motion_query_steps(const ParcMotionTables* tables, const int64_t* motion_ids, const float* motion_times,
-                            int64_t n, const float* time_offsets, int32_t num_steps, const ParcCharModel* model,
-                            const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
-                            const ParcObsSpec* obs, float* obs_out, void* stream);
+                            int64_t n, const float* time_offsets, int32_t num_steps, const float* root_xy_offset,
+                            const ParcCharModel* model, const ParcFrameOut* frame, const ParcFkOut* fk,
+                            const ParcHeightfield* hf, const ParcObsSpec* obs, float* obs_out, void* stream);
 
 /* a4: MotionLib.get_motion_frame (anim/motion_lib.py:114-131): integer frame lookup, no blending. */
 int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
@@ -217,9 +221,13 @@ int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint
 
 /* a10/a11: RefCharEnv._refresh_ray_obs_hfs (envs/ig_parkour/mgdm_dm_util.py:158-179) and
  * sample_hf_z_on_terrain (util/terrain_util.py:2049-2082) with caller-supplied root and heading.
- * root is [N,root_stride] floats (xy at 0,1 and z at 2 when obs->relative). */
+ * root is [N,root_stride] floats (xy at 0,1 and z at 2 when obs->relative).  heading [N], or NULL to take
+ * calc_heading(root_rot[N,4]) (util/torch_util.py:470-479) inside the launch, as the caller does at
+ * envs/ig_parkour/ig_parkour_env.py:641.  root_offset [N,offset_stride] (or NULL) is added to the root first:
+ * the env-local -> terrain shift of _get_global_xyz_pos (:640). */
 int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* root, int32_t root_stride,
-                const float* heading, int64_t n, float* obs_out, void* stream);
+                const float* heading, const float* root_rot, const float* root_offset, int32_t offset_stride,
+                int64_t n, float* obs_out, void* stream);
 
 /* One terrain per sample (hf_batch_stride = X*Y, min_center_stride = 2, base_z_stride = 1) or one
  * terrain shared by the whole batch (strides 0).  x_nodes[X] / y_nodes[Y] are the torch.linspace node
@@ -318,7 +326,10 @@ int parc_clip_label(const float* frames, int64_t batch, int64_t frames_per_clip,
 
 /* One character state, struct-of-arrays, all device float32: root_pos [n,3], root_rot [n,4] xyzw,
  * root_vel [n,3], root_ang_vel [n,3], joint_rot [n,J-1,4], dof_vel [n,D], key_pos [n,K,3] (world-space
- * positions of the key bodies; NULL iff K == 0).  root_rot / joint_rot 16-byte aligned. */
+ * positions of the key bodies; NULL iff K == 0).  root_rot / joint_rot 16-byte aligned.
+ * Zero-copy views: env e reads row e * env_stride of every array (1 = dense; S for step 0 of the [n,S,...]
+ * outputs of parc_motion_query_steps).  If key_body_ids (device int32 [K]) is non-NULL, key_pos is instead a
+ * body-position array [rows, num_bodies, 3] (row e * env_stride) and key k is body key_body_ids[k] of it. */
 typedef struct ParcCharState {
   const float* root_pos;
   const float* root_rot;
@@ -327,6 +338,9 @@ typedef struct ParcCharState {
   const float* joint_rot;
   const float* dof_vel;
   const float* key_pos;
+  const int32_t* key_body_ids;
+  int32_t num_bodies;
+  int32_t env_stride;
 } ParcCharState;
 
 /* envs/base_env.py:12-16 (DoneFlags) */
@@ -362,11 +376,16 @@ int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_joint_rots,
 
 /* compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): future targets [n,S,...] expressed against the
  * character (ref_root_pos [n,3], ref_root_rot [n,4]); obs_out [n, S, 3 + 6 + 6*num_joint_rots + 3*num_keys] =
- * root offset | root tan-norm | joint tan-norms | key positions.  tar_key_pos [n,S,K,3] world space. */
+ * root offset | root tan-norm | joint tan-norms | key positions.  tar_key_pos [n,S,K,3] world space.
+ * Zero-copy views: the target arrays hold tar_env_stride (>= S) step rows per env, of which the S starting at
+ * the given pointers are used (pass S for dense arrays; S+1 and pointers at step 1 for the outputs of
+ * parc_motion_query_steps); with key_body_ids (device int32 [K]) non-NULL, tar_key_pos is a body-position
+ * array [rows, num_bodies, 3] over the same rows. */
 int parc_tar_obs(const float* ref_root_pos, const float* ref_root_rot, const float* tar_root_pos,
                  const float* tar_root_rot, const float* tar_joint_rot, const float* tar_key_pos, int64_t n,
                  int32_t num_steps, int32_t num_joint_rots, int32_t num_keys, int32_t global_obs,
-                 int32_t global_tar_root_h_obs, float* obs_out, void* stream);
+                 int32_t global_tar_root_h_obs, int32_t tar_env_stride, const int32_t* key_body_ids,
+                 int32_t num_bodies, float* obs_out, void* stream);
 
 /* compute_deepmimic_reward (envs/ig_parkour/mgdm_dm_util.py:328-397): reward_out [n,5] =
  * exp(-0.25 pose), exp(-0.01 vel), exp(-5 (root_pos + 0.1 root_rot)), exp(-(root_vel + 0.1 root_ang_vel)),
@@ -381,12 +400,13 @@ int parc_deepmimic_reward(const ParcCharState* sim, const ParcCharState* tar, in
  * (envs/ig_parkour/mgdm_dm_util.py:205-230, :399-460).  time [n]; body_pos / tar_body_pos / contact_force
  * [n,J,3]; root_rot / tar_root_rot [n,4].  Heights: pass term_heights [n,J] (compute_done's own argument),
  * or NULL to sample hf at body xy + env_offsets[:, 0:2] (env_offsets [n, offset_stride], may be NULL) and
- * add termination_height.  done_out [n] int32 (PARC_DONE_*); term_heights_out [n,J] optional. */
+ * add termination_height.  tar_root_rot / tar_body_pos read row e * tar_env_stride (1 = dense).
+ * done_out [n] int32 (PARC_DONE_*); term_heights_out [n,J] optional. */
 int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
               const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
               const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
-              int32_t offset_stride, int64_t n, int32_t num_bodies, int32_t* done_out, float* term_heights_out,
-              void* stream);
+              int32_t offset_stride, int32_t tar_env_stride, int64_t n, int32_t num_bodies, int32_t* done_out,
+              float* term_heights_out, void* stream);
 
 #ifdef __cplusplus
 }

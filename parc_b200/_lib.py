@@ -100,7 +100,8 @@ class ParcKeyBodies(C.Structure):
 class ParcCharState(C.Structure):
     _fields_ = [("root_pos", C.c_void_p), ("root_rot", C.c_void_p), ("root_vel", C.c_void_p),
                 ("root_ang_vel", C.c_void_p), ("joint_rot", C.c_void_p), ("dof_vel", C.c_void_p),
-                ("key_pos", C.c_void_p)]
+                ("key_pos", C.c_void_p), ("key_body_ids", C.c_void_p), ("num_bodies", C.c_int32),
+                ("env_stride", C.c_int32)]
 
 
 class ParcDoneSpec(C.Structure):
@@ -124,7 +125,7 @@ SIGNATURES = {
     "parc_pack_frames": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V]),
     "parc_motion_query": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel), _P(ParcFrameOut),
                                     _P(ParcFkOut), _P(ParcHeightfield), _P(ParcObsSpec), _V, _V]),
-    "parc_motion_query_steps": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _V, _I32, _P(ParcCharModel),
+    "parc_motion_query_steps": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _V, _I32, _V, _P(ParcCharModel),
                                           _P(ParcFrameOut), _P(ParcFkOut), _P(ParcHeightfield), _P(ParcObsSpec),
                                           _V, _V]),
     "parc_get_motion_frame": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel),
@@ -138,7 +139,7 @@ SIGNATURES = {
     "parc_exp_map_to_quat_bwd": (C.c_int, [_V, _V, _I64, _V, _V]),
     "parc_hf_sample": (C.c_int, [_P(ParcHeightfield), _V, _I64, _V, _V, _V]),
     "parc_selftest_grid_index": (C.c_int, [_F, _F, _I32, _V, _V]),
-    "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _I64, _V, _V]),
+    "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _V, _V, _I32, _I64, _V, _V]),
     "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
     "parc_frames_fk": (C.c_int, [_V, _I64, _I32, _P(ParcCharModel), _V, _V, _V, _V, _V]),
     "parc_clip_label": (C.c_int, [_V, _I64, _I64, _I32, _P(ParcCharModel), _P(ParcBodyPoints), _P(ParcTerrainBatch),
@@ -146,11 +147,11 @@ SIGNATURES = {
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
                                  _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
     "parc_char_obs": (C.c_int, [_P(ParcCharState), _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
-    "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
+    "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _V, _I32, _V, _V]),
     "parc_deepmimic_reward": (C.c_int, [_P(ParcCharState), _P(ParcCharState), _I64, _I32, _I32, _I32, _V, _V, _I32,
                                         _I32, _V, _V]),
-    "parc_done": (C.c_int, [_P(ParcDoneSpec), _V, _V, _V, _V, _V, _V, _V, _P(ParcHeightfield), _V, _I32, _I64, _I32,
-                            _V, _V, _V]),
+    "parc_done": (C.c_int, [_P(ParcDoneSpec), _V, _V, _V, _V, _V, _V, _V, _P(ParcHeightfield), _V, _I32, _I32, _I64,
+                            _I32, _V, _V, _V]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -148,7 +148,7 @@ class MotionLib:
                                 obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out)
 
     def make_query_plan(self, motion_ids, motion_times, hf_desc=None, obs_tmpl=None, obs_relative=True,
-                        min_obs_h=-3.0, max_obs_h=3.0, want_fk=True, out=None, time_offsets=None):
+                        min_obs_h=-3.0, max_obs_h=3.0, want_fk=True, out=None, time_offsets=None, root_xy_offset=None):
         """Prebuilt launch of `calc_motion_frame_fk_obs` over fixed input/output buffers: returns an
         `ops.MotionQueryPlan` whose `.launch()` costs one C call.  Update `motion_ids` / `motion_times`
         in place between launches (as the tracker does with its time buffer).
@@ -156,11 +156,14 @@ class MotionLib:
         time_offsets [S] (fp32, offsets[0] = 0) turns it into the tracker-step form: every env is queried at
         t + offsets[k] -- the reference frame plus the future targets of fetch_tar_obs_data
         (`timestep * tar_obs_steps`) -- outputs are [N * S, ...] rows in env-major order (view as [N, S, ...]) and the
-        observation [N, P] is taken at the current frame only."""
+        observation [N, P] is taken at the current frame only.
+
+        root_xy_offset [N,2] (fp32): added to root x,y of every step before FK and the observation -- where each
+        env's motion sits on the shared terrain (DMEnv._move_to_motion_terrain, envs/ig_parkour/dm_env.py:604-615)."""
         return ops.MotionQueryPlan(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times,
                                    want_contacts=self._contact_info, want_fk=want_fk, hf=hf_desc, obs_tmpl=obs_tmpl,
                                    obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out,
-                                   time_offsets=time_offsets)
+                                   time_offsets=time_offsets, root_xy_offset=root_xy_offset)
 
     def joint_rot_to_dof(self, joint_rot):
         return self._kin_char_model.rot_to_dof(joint_rot)

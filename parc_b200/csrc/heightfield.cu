@@ -27,7 +27,8 @@ hf_sample_kernel(const __grid_constant__ ParcHeightfield t, const float* __restr
 // One thread per (env, template point): consecutive threads write consecutive outputs.
 __global__ void __launch_bounds__(256)
 hf_obs_kernel(const __grid_constant__ ParcHeightfield t, const __grid_constant__ ParcObsSpec obs,
-              const float* __restrict__ root, int root_stride, const float* __restrict__ heading, int64_t n,
+              const float* __restrict__ root, int root_stride, const float* __restrict__ heading,
+              const float* __restrict__ root_rot, const float* __restrict__ root_offset, int offset_stride, int64_t n,
               float* __restrict__ out) {
   const int P = obs.num_points;
   const int64_t total = n * P;
@@ -36,11 +37,21 @@ hf_obs_kernel(const __grid_constant__ ParcHeightfield t, const __grid_constant__
     const int64_t e = i / P;
     const int k = (int)(i - e * P);
     const float* r = root + e * root_stride;
-    const float h = __ldg(heading + e);
+    // heading given, or taken from the root rotation as the caller would (util/torch_util.py:470-479)
+    const float h = heading ? __ldg(heading + e) : calc_heading(__ldg(reinterpret_cast<const float4*>(root_rot) + e));
     const float sn = sinf(h), cs = cosf(h);
-    const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, __ldg(r), __ldg(r + 1));
+    float rx = __ldg(r), ry = __ldg(r + 1);
+    if (root_offset) {               // env-local -> terrain coordinates (ig_parkour_env.py:640), one add per component
+      rx = add_rn(rx, __ldg(root_offset + e * offset_stride));
+      ry = add_rn(ry, __ldg(root_offset + e * offset_stride + 1));
+    }
+    const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, rx, ry);
     float z = hf_lookup(t, w.x, w.y);
-    if (obs.relative) z = fminf(fmaxf(sub_rn(z, __ldg(r + 2)), obs.min_h), obs.max_h);
+    if (obs.relative) {
+      float rz = __ldg(r + 2);
+      if (root_offset) rz = add_rn(rz, __ldg(root_offset + e * offset_stride + 2));
+      z = fminf(fmaxf(sub_rn(z, rz), obs.min_h), obs.max_h);
+    }
     out[i] = z;
   }
 }
@@ -75,16 +86,19 @@ extern "C" int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_
 }
 
 extern "C" int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* root,
-                           int32_t root_stride, const float* heading, int64_t n, float* obs_out, void* stream) {
+                           int32_t root_stride, const float* heading, const float* root_rot,
+                           const float* root_offset, int32_t offset_stride, int64_t n, float* obs_out,
+                           void* stream) {
   int rc = check_hf(hf);
   if (rc) return rc;
   if (!obs) return PARC_E_NULL;
   if (n < 0 || obs->num_points < 0 || root_stride < (obs->relative ? 3 : 2)) return PARC_E_SIZE;
   if (n == 0 || obs->num_points == 0) return PARC_OK;
-  if (!obs->tmpl_xy || !root || !heading || !obs_out) return PARC_E_NULL;
+  if (!obs->tmpl_xy || !root || (!heading && !root_rot) || !obs_out) return PARC_E_NULL;
   if ((reinterpret_cast<uintptr_t>(obs->tmpl_xy) & 7u) != 0) return PARC_E_ALIGN;
-  if (n == 0 || obs->num_points == 0) return PARC_OK;
-  hf_obs_kernel<<<flat_grid(n * obs->num_points), 256, 0, (cudaStream_t)stream>>>(*hf, *obs, root, root_stride,
-                                                                                 heading, n, obs_out);
+  if (!heading && !aligned16(root_rot)) return PARC_E_ALIGN;
+  if (root_offset && offset_stride < (obs->relative ? 3 : 2)) return PARC_E_SIZE;
+  hf_obs_kernel<<<flat_grid(n * obs->num_points), 256, 0, (cudaStream_t)stream>>>(
+      *hf, *obs, root, root_stride, heading, root_rot, root_offset, offset_stride, n, obs_out);
   return check_launch();
 }

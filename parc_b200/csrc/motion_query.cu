@@ -19,6 +19,7 @@ struct QueryParams {
   const float* times;       // calc_motion_frame
   const int64_t* frame_idx; // get_motion_frame
   const float* offsets;     // [num_steps] time offsets (tracker step form) or nullptr
+  const float* xy_offset;   // [entries,2] added to root xy after the query (dm_env.py:604-615) or nullptr
   int num_steps;            // queries per (id, time) entry; query q = entry * num_steps + step
   int64_t n;                // total queries = entries * num_steps
   ParcRowLayout lay;
@@ -98,7 +99,7 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // sweep in flight) for launches that fit one wave and are latency-bound; 12 (<= 85 registers, half a
 // sweep in flight) for large launches, which are issue-bound and want more warps per scheduler.
 // (A middle point, whole sweep at <= 102 registers, spills and measured slower: profiles/README.md.)
-template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB>
+template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool XYOFF>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant__ ParcCharModel model_param) {
   __shared__ TreeSmem sm;
@@ -172,6 +173,9 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
     }
     // motion_times + timestep * tar_obs_steps (envs/ig_parkour/mgdm_dm_util.py:289-291): one fp32 add
     if (BLEND && p.offsets) t_q = add_rn(t_q, __ldg(p.offsets + step));
+    // where the env's motion sits on the shared terrain (_move_to_motion_terrain, dm_env.py:604-615): root lane only
+    float2 xy_off = make_float2(0.0f, 0.0f);
+    if (XYOFF && l == 0) xy_off = __ldg(reinterpret_cast<const float2*>(p.xy_offset) + entry);
     if (id < 0 || id >= p.tb.num_clips) id = 0;   // reference would raise an index error
     const int4* cmp = reinterpret_cast<const int4*>(p.tb.clips + id);
     const int4 c0 = __ldg(cmp);
@@ -221,6 +225,10 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
           R.z = add_rn(R.z, mul_rn(cycles, cm.root_pos_delta[2]));
         }
       }
+    }
+    if (XYOFF && l == 0) {                           // pos + offset: one fp32 add per component, as there
+      R.x = add_rn(R.x, xy_off.x);
+      R.y = add_rn(R.y, xy_off.y);
     }
     if (active) {
       if (l == 0) {
@@ -535,8 +543,8 @@ extern "C" int parc_pack_frames(const float* root_pos, const float* root_rot, co
 }
 
 static int launch_query(bool blend, const ParcMotionTables* tables, const int64_t* ids, const float* times,
-                        const int64_t* frame_idx, const float* offsets, int num_steps, int64_t n_entries,
-                        const ParcCharModel* model,
+                        const int64_t* frame_idx, const float* offsets, int num_steps, const float* xy_offset,
+                        int64_t n_entries, const ParcCharModel* model,
                         const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                         const ParcObsSpec* obs, float* obs_out, void* stream) {
   if (!tables || !model) return PARC_E_NULL;
@@ -553,6 +561,8 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   p.tb = *tables;
   p.ids = ids; p.times = times; p.frame_idx = frame_idx; p.n = n;
   p.offsets = offsets; p.num_steps = num_steps;
+  if ((reinterpret_cast<uintptr_t>(xy_offset) & 7u) != 0) return PARC_E_ALIGN;
+  p.xy_offset = xy_offset;
   ParcFrameOut none = {};
   p.out = frame ? *frame : none;
   if (!aligned16(p.out.root_rot) || !aligned16(p.out.joint_rot)) return PARC_E_ALIGN;
@@ -591,8 +601,13 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool rel = p.want_obs && p.obs.relative != 0;
-#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB) \
-  motion_query_kernel<B, GG, NF, RL, MB><<<grid, QUERY_CTA_THREADS, smem, st>>>(p, *model)
+  // XYOFF is a template flag: the two extra live registers of the offset would otherwise spill in the 80-register
+  // large-batch variant (measured: -4 % at 65 536 envs) for callers that never pass one.
+#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB)                                                        \
+  do {                                                                                              \
+    if (B && p.xy_offset) motion_query_kernel<B, GG, NF, RL, MB, B><<<grid, QUERY_CTA_THREADS, smem, st>>>(p, *model); \
+    else motion_query_kernel<B, GG, NF, RL, MB, false><<<grid, QUERY_CTA_THREADS, smem, st>>>(p, *model);              \
+  } while (0)
   if (blend) {
     if (half && one_wave) { if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); }
     else if (half) { if (rel) PARC_LAUNCH_QUERY(true, 16, 14, true, 12); else PARC_LAUNCH_QUERY(true, 16, 14, false, 12); }
@@ -608,24 +623,24 @@ extern "C" int parc_motion_query(const ParcMotionTables* tables, const int64_t* 
                                  const float* motion_times, int64_t n, const ParcCharModel* model,
                                  const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                                  const ParcObsSpec* obs, float* obs_out, void* stream) {
-  return launch_query(true, tables, motion_ids, motion_times, nullptr, nullptr, 1, n, model, frame, fk, hf, obs,
-                      obs_out, stream);
+  return launch_query(true, tables, motion_ids, motion_times, nullptr, nullptr, 1, nullptr, n, model, frame, fk, hf,
+                      obs, obs_out, stream);
 }
 
 extern "C" int parc_motion_query_steps(const ParcMotionTables* tables, const int64_t* motion_ids,
                                        const float* motion_times, int64_t n, const float* time_offsets,
-                                       int32_t num_steps, const ParcCharModel* model, const ParcFrameOut* frame,
-                                       const ParcFkOut* fk, const ParcHeightfield* hf, const ParcObsSpec* obs,
-                                       float* obs_out, void* stream) {
-  return launch_query(true, tables, motion_ids, motion_times, nullptr, time_offsets, num_steps, n, model, frame, fk,
-                      hf, obs, obs_out, stream);
+                                       int32_t num_steps, const float* root_xy_offset, const ParcCharModel* model,
+                                       const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
+                                       const ParcObsSpec* obs, float* obs_out, void* stream) {
+  return launch_query(true, tables, motion_ids, motion_times, nullptr, time_offsets, num_steps, root_xy_offset, n,
+                      model, frame, fk, hf, obs, obs_out, stream);
 }
 
 extern "C" int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
                                      const int64_t* frame_idxs, int64_t n, const ParcCharModel* model,
                                      const ParcFrameOut* frame, const ParcFkOut* fk, void* stream) {
-  return launch_query(false, tables, motion_ids, nullptr, frame_idxs, nullptr, 1, n, model, frame, fk, nullptr,
-                      nullptr, nullptr, stream);
+  return launch_query(false, tables, motion_ids, nullptr, frame_idxs, nullptr, 1, nullptr, n, model, frame, fk,
+                      nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint64_t* mismatches_dev,

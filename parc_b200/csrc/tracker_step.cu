@@ -53,6 +53,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Key body k of state row r: either the dense [n,K,3] array of the reference signature, or -- when key_body_ids
+// is set -- body key_body_ids[k] of a [rows, num_bodies, 3] body-position array (no gather copy needed).
+__device__ __forceinline__ float3 key_position(const float* __restrict__ key_pos, const int32_t* __restrict__ ids,
+                                               int num_bodies, int K, int64_t dense_row, int64_t body_row, int k) {
+  if (ids) return ld3(key_pos + (body_row * num_bodies + __ldg(ids + k)) * 3);
+  return ld3(key_pos + (dense_row * K + k) * 3);
+}
+
 __device__ __forceinline__ float3 sub3(const float3& a, const float3& b) {
   return make_float3(a.x - b.x, a.y - b.y, a.z - b.z);
 }
@@ -70,8 +78,9 @@ char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
     float* __restrict__ o = out + e * W;
-    const float3 rp = ld3(s.root_pos + e * 3);
-    const float4 rr = ld4(s.root_rot + e * 4);
+    const int64_t r = e * s.env_stride;
+    const float3 rp = ld3(s.root_pos + r * 3);
+    const float4 rr = ld4(s.root_rot + r * 4);
     const float4 hinv = heading_inverse_quat(rr);
     if (root_height_obs) {
       if (lane == 0) o[0] = rp.z;
@@ -80,18 +89,18 @@ char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int
     if (lane == 0) {
       store_tan_norm(o, global_obs ? rr : quat_mul(hinv, rr));
     } else if (lane == 1) {
-      const float3 v = ld3(s.root_vel + e * 3);
+      const float3 v = ld3(s.root_vel + r * 3);
       st3(o + 6, global_obs ? v : quat_rotate(hinv, v));
     } else if (lane == 2) {
-      const float3 v = ld3(s.root_ang_vel + e * 3);
+      const float3 v = ld3(s.root_ang_vel + r * 3);
       st3(o + 9, global_obs ? v : quat_rotate(hinv, v));
     }
-    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 12 + 6 * j, ld4(s.joint_rot + (e * Jm1 + j) * 4));
+    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 12 + 6 * j, ld4(s.joint_rot + (r * Jm1 + j) * 4));
     float* __restrict__ ov = o + 12 + 6 * Jm1;
-    for (int d = lane; d < D; d += 32) ov[d] = __ldg(s.dof_vel + e * D + d);
+    for (int d = lane; d < D; d += 32) ov[d] = __ldg(s.dof_vel + r * D + d);
     float* __restrict__ ok = ov + D;
     for (int k = lane; k < K; k += 32) {
-      float3 p = sub3(ld3(s.key_pos + (e * K + k) * 3), rp);
+      float3 p = sub3(key_position(s.key_pos, s.key_body_ids, s.num_bodies, K, e, r, k), rp);
       if (!global_obs) p = quat_rotate(hinv, p);
       st3(ok + 3 * k, p);
     }
@@ -105,7 +114,8 @@ __global__ void __launch_bounds__(STEP_THREADS)
 tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__ ref_root_rot,
                const float* __restrict__ tar_root_pos, const float* __restrict__ tar_root_rot,
                const float* __restrict__ tar_joint_rot, const float* __restrict__ tar_key_pos, int64_t n, int S,
-               int Jm1, int K, int global_obs, int global_tar_root_h, float* __restrict__ out) {
+               int Jm1, int K, int global_obs, int global_tar_root_h, int tar_env_stride,
+               const int32_t* __restrict__ key_body_ids, int num_bodies, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int W = 9 + 6 * Jm1 + 3 * K;
   const int64_t total = n * S;
@@ -113,9 +123,10 @@ tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t q = warp0; q < total; q += nwarps) {
     const int64_t e = q / S;
+    const int64_t r = e * tar_env_stride + (q - e * S);      // row of this (env, step) in the target arrays
     float* __restrict__ o = out + q * W;
-    const float3 tp = ld3(tar_root_pos + q * 3);
-    float4 tr = ld4(tar_root_rot + q * 4);
+    const float3 tp = ld3(tar_root_pos + r * 3);
+    float4 tr = ld4(tar_root_rot + r * 4);
     float3 po = sub3(tp, ld3(ref_root_pos + e * 3));
     float4 hinv = make_float4(0.f, 0.f, 0.f, 1.f);
     if (!global_obs) {
@@ -127,10 +138,10 @@ tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__
       st3(o, make_float3(po.x, po.y, global_tar_root_h ? tp.z : po.z));
       store_tan_norm(o + 3, tr);
     }
-    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 9 + 6 * j, ld4(tar_joint_rot + (q * Jm1 + j) * 4));
+    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 9 + 6 * j, ld4(tar_joint_rot + (r * Jm1 + j) * 4));
     float* __restrict__ ok = o + 9 + 6 * Jm1;
     for (int k = lane; k < K; k += 32) {
-      float3 p = sub3(ld3(tar_key_pos + (q * K + k) * 3), tp);
+      float3 p = sub3(key_position(tar_key_pos, key_body_ids, num_bodies, K, q, r, k), tp);
       if (!global_obs) {
         p = quat_rotate(hinv, p);
         p.x += po.x; p.y += po.y; p.z += po.z;       // the rotated root offset, BEFORE the height override
@@ -152,18 +163,19 @@ deepmimic_reward_kernel(const __grid_constant__ ParcCharState s, const __grid_co
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
     float pose = 0.0f, vel = 0.0f, key = 0.0f;
+    const int64_t rs = e * s.env_stride, rt = e * t.env_stride;
     for (int j = lane; j < Jm1; j += 32) {
-      const float a = quat_diff_angle(ld4(s.joint_rot + (e * Jm1 + j) * 4), ld4(t.joint_rot + (e * Jm1 + j) * 4));
+      const float a = quat_diff_angle(ld4(s.joint_rot + (rs * Jm1 + j) * 4), ld4(t.joint_rot + (rt * Jm1 + j) * 4));
       pose += __ldg(joint_w + j) * a * a;
     }
     for (int d = lane; d < D; d += 32) {
-      const float dv = __ldg(t.dof_vel + e * D + d) - __ldg(s.dof_vel + e * D + d);
+      const float dv = __ldg(t.dof_vel + rt * D + d) - __ldg(s.dof_vel + rs * D + d);
       vel += __ldg(dof_w + d) * dv * dv;
     }
-    const float3 rp = ld3(s.root_pos + e * 3), trp = ld3(t.root_pos + e * 3);
-    float4 rr = ld4(s.root_rot + e * 4), trr = ld4(t.root_rot + e * 4);
-    float3 rv = ld3(s.root_vel + e * 3), trv = ld3(t.root_vel + e * 3);
-    float3 rw = ld3(s.root_ang_vel + e * 3), trw = ld3(t.root_ang_vel + e * 3);
+    const float3 rp = ld3(s.root_pos + rs * 3), trp = ld3(t.root_pos + rt * 3);
+    float4 rr = ld4(s.root_rot + rs * 4), trr = ld4(t.root_rot + rt * 4);
+    float3 rv = ld3(s.root_vel + rs * 3), trv = ld3(t.root_vel + rt * 3);
+    float3 rw = ld3(s.root_ang_vel + rs * 3), trw = ld3(t.root_ang_vel + rt * 3);
     float3 dp = sub3(trp, rp);
     if (!track_root) dp.x = dp.y = 0.0f;
     if (!track_root_h) dp.z = 0.0f;
@@ -175,8 +187,8 @@ deepmimic_reward_kernel(const __grid_constant__ ParcCharState s, const __grid_co
       trv = quat_rotate(ht, trv); trw = quat_rotate(ht, trw); trr = quat_mul(ht, trr);
     }
     for (int k = lane; k < K; k += 32) {
-      float3 a = sub3(ld3(s.key_pos + (e * K + k) * 3), rp);
-      float3 b = sub3(ld3(t.key_pos + (e * K + k) * 3), trp);
+      float3 a = sub3(key_position(s.key_pos, s.key_body_ids, s.num_bodies, K, e, rs, k), rp);
+      float3 b = sub3(key_position(t.key_pos, t.key_body_ids, t.num_bodies, K, e, rt, k), trp);
       if (!track_root) { a = quat_rotate(hs, a); b = quat_rotate(ht, b); }
       key += sq3(sub3(b, a));
     }
@@ -217,6 +229,7 @@ struct DoneParams {
   uint32_t contact_body_mask;
   int has_contact_bodies, pose_termination, early_termination, track_root;
   int J;
+  int tar_env_stride;
 };
 
 __global__ void __launch_bounds__(STEP_THREADS)
@@ -264,7 +277,7 @@ done_kernel(const __grid_constant__ DoneParams p, int64_t n, int32_t* __restrict
       }
       if (p.pose_termination) {
         float3 tb = make_float3(0.f, 0.f, 0.f);
-        if (body) tb = ld3(p.tar_body_pos + (e * J + lane) * 3);
+        if (body) tb = ld3(p.tar_body_pos + (e * p.tar_env_stride * J + lane) * 3);
         const float3 r0 = shfl3(bp, 0), t0 = shfl3(tb, 0);
         bool bad = false;
         if (body && lane > 0) {
@@ -277,7 +290,7 @@ done_kernel(const __grid_constant__ DoneParams p, int64_t n, int32_t* __restrict
         } else if (lane == 0 && p.track_root) {
           const float dx = sub_rn(bp.x, tb.x), dy = sub_rn(bp.y, tb.y), dz = sub_rn(bp.z, tb.z);
           const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
-          const float ang = quat_diff_angle(ld4(p.root_rot + e * 4), ld4(p.tar_root_rot + e * 4));
+          const float ang = quat_diff_angle(ld4(p.root_rot + e * 4), ld4(p.tar_root_rot + e * p.tar_env_stride * 4));
           bad = d2 > p.root_pos_dist_sq || fabsf(ang) > p.root_rot_angle;
         }
         failed = failed || __any_sync(PARC_FULL_MASK, bad);
@@ -299,6 +312,7 @@ static int check_state(const ParcCharState* s, int D, int K, bool need_vel) {
   if (!s->root_pos || !s->root_rot || !s->joint_rot) return PARC_E_NULL;
   if (need_vel && (!s->root_vel || !s->root_ang_vel || (D > 0 && !s->dof_vel))) return PARC_E_NULL;
   if (K > 0 && !s->key_pos) return PARC_E_NULL;
+  if (s->env_stride < 1 || (s->key_body_ids && s->num_bodies < 1)) return PARC_E_SIZE;
   if (!aligned16(s->root_rot) || !aligned16(s->joint_rot)) return PARC_E_ALIGN;
   return PARC_OK;
 }
@@ -323,15 +337,17 @@ extern "C" int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_
 extern "C" int parc_tar_obs(const float* ref_root_pos, const float* ref_root_rot, const float* tar_root_pos,
                             const float* tar_root_rot, const float* tar_joint_rot, const float* tar_key_pos,
                             int64_t n, int32_t num_steps, int32_t num_joint_rots, int32_t num_keys,
-                            int32_t global_obs, int32_t global_tar_root_h_obs, float* obs_out, void* stream) {
+                            int32_t global_obs, int32_t global_tar_root_h_obs, int32_t tar_env_stride,
+                            const int32_t* key_body_ids, int32_t num_bodies, float* obs_out, void* stream) {
   if (n < 0 || num_steps < 0 || num_joint_rots < 0 || num_keys < 0) return PARC_E_SIZE;
+  if (tar_env_stride < num_steps || (key_body_ids && num_bodies < 1)) return PARC_E_SIZE;
   if (n == 0 || num_steps == 0) return PARC_OK;
   if (!ref_root_pos || !ref_root_rot || !tar_root_pos || !tar_root_rot || !obs_out) return PARC_E_NULL;
   if ((num_joint_rots > 0 && !tar_joint_rot) || (num_keys > 0 && !tar_key_pos)) return PARC_E_NULL;
   if (!aligned16(ref_root_rot) || !aligned16(tar_root_rot) || !aligned16(tar_joint_rot)) return PARC_E_ALIGN;
   tar_obs_kernel<<<warp_grid(n * num_steps), STEP_THREADS, 0, (cudaStream_t)stream>>>(
       ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot, tar_key_pos, n, num_steps,
-      num_joint_rots, num_keys, global_obs, global_tar_root_h_obs, obs_out);
+      num_joint_rots, num_keys, global_obs, global_tar_root_h_obs, tar_env_stride, key_body_ids, num_bodies, obs_out);
   return check_launch();
 }
 
@@ -356,10 +372,10 @@ extern "C" int parc_deepmimic_reward(const ParcCharState* sim, const ParcCharSta
 extern "C" int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
                          const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
                          const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
-                         int32_t offset_stride, int64_t n, int32_t num_bodies, int32_t* done_out,
-                         float* term_heights_out, void* stream) {
+                         int32_t offset_stride, int32_t tar_env_stride, int64_t n, int32_t num_bodies,
+                         int32_t* done_out, float* term_heights_out, void* stream) {
   if (!spec) return PARC_E_NULL;
-  if (n < 0 || num_bodies < 1 || num_bodies > PARC_MAX_BODIES) return PARC_E_SIZE;
+  if (n < 0 || num_bodies < 1 || num_bodies > PARC_MAX_BODIES || tar_env_stride < 1) return PARC_E_SIZE;
   if (n == 0) return PARC_OK;
   if (!time || !body_pos || (!done_out && !term_heights_out)) return PARC_E_NULL;
   const bool early = spec->enable_early_termination != 0;
@@ -392,6 +408,7 @@ extern "C" int parc_done(const ParcDoneSpec* spec, const float* time, const floa
   p.has_contact_bodies = spec->has_contact_bodies; p.pose_termination = spec->pose_termination;
   p.early_termination = spec->enable_early_termination; p.track_root = spec->track_root;
   p.J = num_bodies;
+  p.tar_env_stride = tar_env_stride;
   done_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, n, done_out, term_heights_out);
   return check_launch();
 }

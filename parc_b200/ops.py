@@ -215,10 +215,11 @@ class MotionQueryPlan:
     def __init__(self, tables: PackedTables, model: ParcCharModel, ids: torch.Tensor, times: torch.Tensor, *,
                  want_contacts: bool = True, want_fk: bool = True, hf: Optional[HeightfieldDesc] = None,
                  obs_tmpl: Optional[torch.Tensor] = None, obs_relative: bool = True, obs_min_h: float = -3.0,
-                 obs_max_h: float = 3.0, out: Optional[dict] = None, time_offsets: Optional[torch.Tensor] = None):
-        require_cuda(ids, times, tables.rows, time_offsets)
+                 obs_max_h: float = 3.0, out: Optional[dict] = None, time_offsets: Optional[torch.Tensor] = None,
+                 root_xy_offset: Optional[torch.Tensor] = None):
+        require_cuda(ids, times, tables.rows, time_offsets, root_xy_offset)
         assert ids.dtype == torch.int64 and times.dtype == torch.float32 and ids.is_contiguous() and times.is_contiguous()
-        self._keep = (tables, model, ids, times, hf, obs_tmpl, time_offsets)
+        self._keep = (tables, model, ids, times, hf, obs_tmpl, time_offsets, root_xy_offset)
         self.device = ids.device
         E = int(ids.shape[0])                    # entries (environments)
         S = 1 if time_offsets is None else int(time_offsets.shape[0])
@@ -259,13 +260,17 @@ class MotionQueryPlan:
         tail = (C.byref(model), C.byref(self._fo), C.byref(self._fk) if want_fk else None,
                 C.byref(self._hf) if self._hf is not None else None,
                 C.byref(self._obs) if self._obs is not None else None, self._obs_ptr)
-        if time_offsets is None:
+        if time_offsets is None and root_xy_offset is None:
             self._fn = lib.parc_motion_query
             self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E) + tail
         else:
-            assert time_offsets.dtype == torch.float32 and time_offsets.is_contiguous()
+            assert time_offsets is None or (time_offsets.dtype == torch.float32 and time_offsets.is_contiguous())
+            if root_xy_offset is not None:       # [E,2]: where each env's motion sits on the shared terrain
+                assert root_xy_offset.dtype == torch.float32 and root_xy_offset.is_contiguous()
+                assert tuple(root_xy_offset.shape) == (E, 2)
             self._fn = lib.parc_motion_query_steps
-            self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E, time_offsets.data_ptr(), S) + tail
+            self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E, ptr(time_offsets), S,
+                          ptr(root_xy_offset)) + tail
 
     def launch(self, stream: Optional[int] = None) -> dict:
         """Enqueue on `stream` (a raw cudaStream_t; default = torch's current stream of the plan's
@@ -442,21 +447,26 @@ def selftest_grid_index(min_coord: float, cell_size: float, dim: int, device="cu
     return int(cnt.item())
 
 
-def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, heading: torch.Tensor, *,
-           relative: bool, min_h: float = -3.0, max_h: float = 3.0, out: Optional[torch.Tensor] = None):
-    """root [N,>=2 (3 if relative)], heading [N], tmpl [P,2] -> [N,P]."""
-    require_cuda(hf.hf, tmpl_xy, root, heading)
+def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, heading: Optional[torch.Tensor], *,
+           relative: bool, min_h: float = -3.0, max_h: float = 3.0, out: Optional[torch.Tensor] = None,
+           root_rot: Optional[torch.Tensor] = None, root_offset: Optional[torch.Tensor] = None):
+    """root [N,>=2 (3 if relative)], heading [N], tmpl [P,2] -> [N,P].  With heading=None the heading is taken
+    from `root_rot` [N,4] inside the launch; `root_offset` [N,>=2 (3 if relative)] is added to the root first."""
+    require_cuda(hf.hf, tmpl_xy, root, heading, root_rot, root_offset)
     r = f32c(root)
     assert r.dim() == 2
-    hd = f32c(heading).reshape(-1)
+    hd = f32c(heading).reshape(-1) if heading is not None else None
+    rr = f32c(root_rot) if heading is None else None
+    assert hd is not None or (rr is not None and rr.shape == (r.shape[0], 4))
+    ro = f32c(root_offset) if root_offset is not None else None
     tm = f32c(tmpl_xy).reshape(-1, 2)
     n, P = r.shape[0], tm.shape[0]
     if out is None:
         out = torch.empty((n, P), dtype=torch.float32, device=r.device)
     h, o = hf.c_struct(), _obs_struct(tm, relative, min_h, max_h)
     with torch.cuda.device(r.device):
-        rc = _lib.load().parc_hf_obs(C.byref(h), C.byref(o), r.data_ptr(), int(r.shape[1]), hd.data_ptr(), n,
-                                     out.data_ptr(), stream_ptr(r.device))
+        rc = _lib.load().parc_hf_obs(C.byref(h), C.byref(o), r.data_ptr(), int(r.shape[1]), ptr(hd), ptr(rr), ptr(ro),
+                                     int(ro.shape[1]) if ro is not None else 0, n, out.data_ptr(), stream_ptr(r.device))
     check(rc, "parc_hf_obs")
     return out
 
@@ -709,26 +719,81 @@ def _has(t: Optional[torch.Tensor]) -> bool:
     return t is not None and t.numel() > 0
 
 
-def _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos):
-    """-> (ParcCharState, tensors kept alive, n, J-1, D, K)"""
-    keep = [f32c(root_pos), f32c(root_rot), f32c(root_vel), f32c(root_ang_vel), f32c(joint_rot), f32c(dof_vel),
-            f32c(key_pos) if _has(key_pos) else None]
+def _rows(t: torch.Tensor, lead: int = 1):
+    """(tensor, k): a zero-copy row-strided view if `t` is fp32 with contiguous inner dims and its leading stride
+    is k whole rows (rows = the first `lead` dims flattened; e.g. step 0 of [n,S,...] has k = S); otherwise a
+    contiguous fp32 copy with k = 1 (lead == 1) or k = shape[1] (lead == 2)."""
+    inner = 1
+    for d in t.shape[lead:]:
+        inner *= int(d)
+    ok = t.dtype == torch.float32 and t.shape[0] > 0 and inner > 0 and t.stride(0) % inner == 0
+    if ok:
+        probe = t[0] if lead == 1 else t[0, 0]
+        ok = probe.is_contiguous() if probe.dim() > 0 else True
+    if ok and lead == 2:
+        ok = t.shape[1] == 1 or t.stride(1) == inner
+    if ok:
+        k = t.stride(0) // inner
+        if k >= (1 if lead == 1 else int(t.shape[1])):
+            return t, int(k)
+    t = f32c(t)
+    return t, (1 if lead == 1 else int(t.shape[1]))
+
+
+def _key_ids(key_body_ids, device) -> Optional[torch.Tensor]:
+    if key_body_ids is None:
+        return None
+    ids = torch.as_tensor(key_body_ids, device=device).to(torch.int32).contiguous()
+    return ids
+
+
+def _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos, key_body_ids=None):
+    """-> (ParcCharState, tensors kept alive, n, J-1, D, K).  Row-strided fp32 views are passed without a copy when
+    all six arrays share the same row stride.  With `key_body_ids` (int tensor [K]), `key_pos` is the character's
+    body positions [n,J,3] and the key bodies are picked inside the kernel."""
+    views = [_rows(t) for t in (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel)]
+    body_view = _rows(key_pos) if (key_body_ids is not None and _has(key_pos)) else None
+    strides = {k for _, k in views} | ({body_view[1]} if body_view else set())
+    if len(strides) == 1:
+        keep = [t for t, _ in views]
+        stride = strides.pop()
+        kp = body_view[0] if body_view else None
+    else:
+        keep = [f32c(t) for t in (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel)]
+        stride = 1
+        kp = f32c(key_pos) if body_view else None
+    ids = None
+    if body_view:
+        ids = _key_ids(key_body_ids, keep[0].device)
+    elif _has(key_pos):
+        kp = f32c(key_pos)
+    keep += [kp, ids]
     require_cuda(*keep)
     n = keep[0].shape[0]
     jm1, d = keep[4].shape[-2], keep[5].shape[-1]
-    k = keep[6].shape[-2] if keep[6] is not None else 0
     assert keep[0].shape == (n, 3) and keep[1].shape == (n, 4) and keep[2].shape == (n, 3) and keep[3].shape == (n, 3)
-    assert keep[4].shape == (n, jm1, 4) and keep[5].shape == (n, d) and (k == 0 or keep[6].shape == (n, k, 3))
+    assert keep[4].shape == (n, jm1, 4) and keep[5].shape == (n, d)
     st = ParcCharState()
-    (st.root_pos, st.root_rot, st.root_vel, st.root_ang_vel, st.joint_rot, st.dof_vel,
-     st.key_pos) = [ptr(t) for t in keep]
+    (st.root_pos, st.root_rot, st.root_vel, st.root_ang_vel, st.joint_rot, st.dof_vel) = [ptr(t) for t in keep[:6]]
+    st.key_pos, st.key_body_ids = ptr(kp), ptr(ids)
+    st.env_stride = stride
+    if ids is not None:
+        k = int(ids.shape[0])
+        assert kp.shape[0] == n and kp.shape[-1] == 3
+        st.num_bodies = int(kp.shape[1])
+    else:
+        k = kp.shape[-2] if kp is not None else 0
+        assert k == 0 or kp.shape == (n, k, 3)
+        st.num_bodies = 0
     return st, keep, n, jm1, d, k
 
 
 def char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos, global_obs: bool,
-             root_height_obs: bool) -> torch.Tensor:
-    """compute_char_obs (envs/ig_char_env.py:582-626) -> [n, W]; key_pos [n,K,3] or empty/None.  One launch."""
-    st, keep, n, jm1, d, k = _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos)
+             root_height_obs: bool, key_body_ids=None) -> torch.Tensor:
+    """compute_char_obs (envs/ig_char_env.py:582-626) -> [n, W]; key_pos [n,K,3] or empty/None -- or, with
+    `key_body_ids`, the body positions [n,J,3] to pick the key bodies from.  One launch."""
+    st, keep, n, jm1, d, k = _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos,
+                                         key_body_ids)
     dev = keep[0].device
     out = torch.empty((n, (1 if root_height_obs else 0) + 12 + 6 * jm1 + d + 3 * k), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -739,31 +804,57 @@ def char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key
 
 
 def tar_obs(ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot, tar_key_pos, global_obs: bool,
-            global_tar_root_h_obs: bool) -> torch.Tensor:
-    """compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): targets [n,S,...] -> [n,S,W].  One launch."""
-    rp, rr, tp, tr, tj = (f32c(t) for t in (ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot))
-    tk = f32c(tar_key_pos) if _has(tar_key_pos) else None
+            global_tar_root_h_obs: bool, key_body_ids=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): targets [n,S,...] -> [n,S,W].  The target arrays
+    may be step slices of larger [n,S_total,...] buffers (no copy); with `key_body_ids`, `tar_key_pos` is the
+    targets' body positions [n,S,J,3].  One launch."""
+    rp, rr = f32c(ref_root_pos), f32c(ref_root_rot)
+    views = [_rows(t, lead=2) for t in (tar_root_pos, tar_root_rot, tar_joint_rot)]
+    use_ids = key_body_ids is not None and _has(tar_key_pos)
+    kview = _rows(tar_key_pos, lead=2) if use_ids else None
+    strides = {k for _, k in views} | ({kview[1]} if kview else set())
+    if len(strides) == 1:
+        tp, tr, tj = (t for t, _ in views)
+        stride = strides.pop()
+        tk = kview[0] if kview else None
+    else:
+        tp, tr, tj = (f32c(t) for t in (tar_root_pos, tar_root_rot, tar_joint_rot))
+        stride = int(tp.shape[1])
+        tk = f32c(tar_key_pos) if kview else None
+    ids = _key_ids(key_body_ids, tp.device) if use_ids else None
+    if not use_ids:
+        tk = f32c(tar_key_pos) if _has(tar_key_pos) else None
     require_cuda(rp, rr, tp, tr, tj, tk)
     n, S, jm1 = tp.shape[0], tp.shape[1], tj.shape[-2]
-    k = tk.shape[-2] if tk is not None else 0
     assert rp.shape == (n, 3) and rr.shape == (n, 4) and tp.shape == (n, S, 3) and tr.shape == (n, S, 4)
-    assert tj.shape == (n, S, jm1, 4) and (k == 0 or tk.shape == (n, S, k, 3))
-    out = torch.empty((n, S, 9 + 6 * jm1 + 3 * k), dtype=torch.float32, device=tp.device)
+    assert tj.shape == (n, S, jm1, 4)
+    if ids is not None:
+        k, nb = int(ids.shape[0]), int(tk.shape[2])
+        assert tk.shape == (n, S, nb, 3)
+    else:
+        k, nb = (tk.shape[-2] if tk is not None else 0), 0
+        assert k == 0 or tk.shape == (n, S, k, 3)
+    shape = (n, S, 9 + 6 * jm1 + 3 * k)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=tp.device)
+    assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.float32
     with torch.cuda.device(tp.device):
         rc = _lib.load().parc_tar_obs(rp.data_ptr(), rr.data_ptr(), tp.data_ptr(), tr.data_ptr(), tj.data_ptr(), ptr(tk),
-                                      n, S, jm1, k, int(bool(global_obs)), int(bool(global_tar_root_h_obs)),
-                                      out.data_ptr(), stream_ptr(tp.device))
+                                      n, S, jm1, k, int(bool(global_obs)), int(bool(global_tar_root_h_obs)), stride,
+                                      ptr(ids), nb, out.data_ptr(), stream_ptr(tp.device))
     check(rc, "parc_tar_obs")
     return out
 
 
-def deepmimic_reward(sim: tuple, tar: tuple, joint_rot_err_w, dof_err_w, track_root_h: bool, track_root: bool):
+def deepmimic_reward(sim: tuple, tar: tuple, joint_rot_err_w, dof_err_w, track_root_h: bool, track_root: bool,
+                     key_body_ids=None):
     """compute_deepmimic_reward (envs/ig_parkour/mgdm_dm_util.py:328-397).  sim / tar are 7-tuples
-    (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos) -> [n,5].  One launch."""
-    if not _has(sim[6]) or not _has(tar[6]):
+    (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos) -> [n,5]; with `key_body_ids` the
+    7th entries are body positions [n,J,3].  Row-strided views (step 0 of [n,S,...]) are read in place.  One launch."""
+    if not _has(sim[6]) or not _has(tar[6]) or (key_body_ids is not None and len(key_body_ids) == 0):
         raise ValueError("compute_deepmimic_reward needs key bodies (the reference fails to stack its terms without)")
-    s, keep_s, n, jm1, d, k = _char_state(*sim)
-    t, keep_t, n2, jm2, d2, k2 = _char_state(*tar)
+    s, keep_s, n, jm1, d, k = _char_state(*sim, key_body_ids=key_body_ids)
+    t, keep_t, n2, jm2, d2, k2 = _char_state(*tar, key_body_ids=key_body_ids)
     assert (n, jm1, d, k) == (n2, jm2, d2, k2)
     jw, dw = f32c(joint_rot_err_w), f32c(dof_err_w)
     require_cuda(jw, dw)
@@ -812,8 +903,16 @@ def done_flags(time, ep_len: float, root_rot, body_pos, tar_root_rot, tar_body_p
     spec.enable_early_termination = int(bool(enable_early_termination))
     spec.track_root = int(bool(track_root))
     rr = f32c(root_rot) if root_rot is not None else None
-    trr = f32c(tar_root_rot) if tar_root_rot is not None else None
-    tbp = f32c(tar_body_pos) if tar_body_pos is not None else None
+    tar_stride = 1
+    trr = tbp = None
+    if tar_root_rot is not None and tar_body_pos is not None:           # step 0 of [n,S,...] is read in place
+        (trr, k1), (tbp, k2) = _rows(tar_root_rot), _rows(tar_body_pos)
+        if k1 != k2:
+            trr, tbp, k1 = f32c(tar_root_rot), f32c(tar_body_pos), 1
+        tar_stride = k1
+    else:
+        trr = f32c(tar_root_rot) if tar_root_rot is not None else None
+        tbp = f32c(tar_body_pos) if tar_body_pos is not None else None
     cf = f32c(contact_force) if contact_force is not None else None
     th = f32c(termination_heights) if termination_heights is not None else None
     eo = f32c(env_offsets) if env_offsets is not None else None
@@ -826,7 +925,7 @@ def done_flags(time, ep_len: float, root_rot, body_pos, tar_root_rot, tar_body_p
     with torch.cuda.device(dev):
         rc = _lib.load().parc_done(C.byref(spec), tm.data_ptr(), ptr(rr), bp.data_ptr(), ptr(trr), ptr(tbp), ptr(cf),
                                    ptr(th), C.byref(hfs) if hf is not None else None, ptr(eo),
-                                   int(eo.shape[-1]) if eo is not None else 0, n, J, out.data_ptr(), ptr(th_out),
-                                   stream_ptr(dev))
+                                   int(eo.shape[-1]) if eo is not None else 0, tar_stride, n, J, out.data_ptr(),
+                                   ptr(th_out), stream_ptr(dev))
     check(rc, "parc_done")
     return (out, th_out) if want_heights else out

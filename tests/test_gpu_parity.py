@@ -1076,3 +1076,84 @@ def test_step_assembly_matches_oracle_on_a_generic_tree():
                 assert not (mism & ~close).any(), (int(mism.sum()), cids.tolist(), pose, track)
                 seen |= set(want.tolist())
     assert seen == {0, 1, 3}
+
+
+def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model, O, oracle_tables, oracle_model):
+    """The whole kinematic side of a control step (envs/ig_parkour/step_assembly.py): reference frame + 6 targets
+    with the per-env terrain placement, simulated character's observation, ray heightmap, reward terms and done
+    flags -- against the same sequence composed from the oracle; then the CUDA-graph replay against the eager run."""
+    from parc_b200.envs.ig_parkour.step_assembly import TrackerStep
+    from parc_b200.util import geom_util
+    from parc_b200.util.terrain_util import SubTerrain
+    g, sim, ref_g, key_ids = _step_golden()
+    n = sim[0].shape[0]
+    gen = torch.Generator().manual_seed(77)
+    terr = SubTerrain("step", g["hf"].shape[0], g["hf"].shape[1], float(g["hf_dxdy"][0]), float(g["hf_dxdy"][1]),
+                      float(g["hf_min"][0]), float(g["hf_min"][1]), device="cuda")
+    terr.hf[...] = _cu(g["hf"])
+    o_terr = O.Terrain(hf=torch.as_tensor(g["hf"]), min_point=torch.as_tensor(g["hf_min"]),
+                       dxdy=torch.as_tensor(g["hf_dxdy"]))
+    tmpl = geom_util.get_xy_points_cone(torch.zeros(2), 0.05, 2, 60, 3, 3, 0.26179938779)
+    jw, ptd = torch.as_tensor(g["joint_err_w"]), torch.as_tensor(g["pose_termination_dist"])
+    feet = [int(i) for i in g["feet"]]
+    ts = TrackerStep(golden_lib, terr, n, float(g["dt"]), g["steps"].tolist(), key_ids.tolist(), tmpl, joint_err_w=jw,
+                     pose_termination_dist=ptd, contact_body_ids=feet)
+    ids, times = torch.as_tensor(g["ids"]).long(), torch.as_tensor(g["times"])
+    xy_off = torch.randn(n, 2, generator=gen) * 0.3
+    env_off = torch.as_tensor(g["env_offsets"])
+    ts.motion_ids.copy_(ids); ts.motion_times.copy_(times); ts.motion_xy_offset.copy_(xy_off)
+    sim_c = [t.cpu() for t in sim]
+    dof_pos = O.rot_to_dof(oracle_model, sim_c[4])
+    body_pos = O.forward_kinematics(oracle_model, sim_c[0], sim_c[1], O.dof_to_rot(oracle_model, dof_pos))[0]
+    forces, tm = torch.as_tensor(g["contact_forces"]), torch.as_tensor(g["time_buf"])
+    char_contacts = (torch.rand(n, 15, generator=gen) < 0.3).float()
+    state = [t.cuda() for t in (sim_c[0], sim_c[1], sim_c[2], sim_c[3], dof_pos, sim_c[5], body_pos, forces, tm, env_off,
+                                char_contacts)]
+    res = ts.step(*state)
+
+    # ---- the same sequence from the oracle ----
+    S = len(g["steps"])
+    offs = torch.cat([torch.zeros(1), torch.as_tensor(g["dt"]) * torch.as_tensor(g["steps"])])
+    ids_t = ids.unsqueeze(-1).expand(n, S + 1).flatten()
+    times_t = (times.unsqueeze(-1) + offs).flatten()
+    fr = list(O.calc_motion_frame(oracle_tables, ids_t, times_t))
+    fr[0] = fr[0].clone()
+    fr[0][:, 0:2] += xy_off.repeat_interleave(S + 1, dim=0)
+    bp_all = O.forward_kinematics(oracle_model, fr[0], fr[1], fr[4])[0]
+    v = lambda t: t.view(n, S + 1, *t.shape[1:])
+    rp, rr, rv, rw, jr, dv, ct, bp = (v(t) for t in (fr[0], fr[1], fr[2], fr[3], fr[4], fr[5], fr[6], bp_all))
+    assert torch.equal(res["ref_root_pos"].cpu(), rp[:, 0])                       # placement is one exact fp32 add
+    sim_jr = O.dof_to_rot(oracle_model, dof_pos)
+    kid = key_ids.cpu()
+    o_char = O.compute_char_obs(sim_c[0], sim_c[1], sim_c[2], sim_c[3], sim_jr, sim_c[5], body_pos[:, kid], False, False)
+    o_tar = O.compute_tar_obs(sim_c[0], sim_c[1], rp[:, 1:], rr[:, 1:], jr[:, 1:], bp[:, 1:][:, :, kid], False, False)
+    o_ray = O.ray_obs(o_terr, sim_c[0] + env_off, O.calc_heading(sim_c[1]), tmpl)
+    o_obs = torch.cat([o_char, o_tar.reshape(n, -1), ct[:, 1:].reshape(n, -1), char_contacts, o_ray], dim=-1)
+    assert res["obs"].shape == o_obs.shape
+    # world coordinates reach ~20 m (ulp 1.9e-6); differences of them that land near 0 keep that granularity
+    assert_close(res["obs"], o_obs, atol=6e-6, what="policy observation")
+    dw = ts.dof_err_w.cpu()
+    assert torch.equal(dw, torch.as_tensor(g["dof_err_w"]))
+    o_rew = O.compute_deepmimic_reward(sim_c[0], sim_c[1], sim_c[2], sim_c[3], sim_jr, sim_c[5], body_pos[:, kid],
+                                       rp[:, 0], rr[:, 0], rv[:, 0], rw[:, 0], jr[:, 0], dv[:, 0], bp[:, 0][:, kid], jw, dw,
+                                       True, True)
+    assert_close(res["reward_terms"], o_rew, what="reward terms")
+    th = O.termination_heights(o_terr, body_pos, env_off, 0.15)
+    o_done = O.compute_done(torch.zeros(n, dtype=torch.int), tm, 10.0, sim_c[1], body_pos, rr[:, 0], bp[:, 0], forces,
+                            torch.tensor(feet), th, True, ptd, True, True, 0.6, 1.309)
+    assert torch.equal(res["done"].cpu(), o_done) and set(o_done.tolist()) == {0, 1, 3}
+
+    # ---- CUDA graph: one launch per step, same numbers; inputs are re-read from the same buffers ----
+    eager = {k: t.clone() for k, t in res.items() if k in ("obs", "reward_terms", "done")}
+    ts.capture(*state)
+    ts.motion_times.add_(0.25)
+    state[0].add_(0.01)
+    out2 = ts.replay()
+    assert not torch.equal(out2["obs"], eager["obs"])
+    ts.motion_times.sub_(0.25)
+    state[0].sub_(0.01)
+    out3 = ts.replay()
+    # (x + 0.01) - 0.01 is not always x in fp32: compare against a fresh eager run on the current buffers
+    again = ts.step(*state)
+    for k in ("obs", "reward_terms", "done"):
+        assert torch.equal(out3[k], again[k]), k
