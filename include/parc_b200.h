@@ -224,10 +224,11 @@ int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint
  * root is [N,root_stride] floats (xy at 0,1 and z at 2 when obs->relative).  heading [N], or NULL to take
  * calc_heading(root_rot[N,4]) (util/torch_util.py:470-479) inside the launch, as the caller does at
  * envs/ig_parkour/ig_parkour_env.py:641.  root_offset [N,offset_stride] (or NULL) is added to the root first:
- * the env-local -> terrain shift of _get_global_xyz_pos (:640). */
+ * the env-local -> terrain shift of _get_global_xyz_pos (:640).  obs_out rows are out_stride floats apart
+ * (0 = dense, num_points), so the heightmap can land directly inside a wider policy-observation row. */
 int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* root, int32_t root_stride,
                 const float* heading, const float* root_rot, const float* root_offset, int32_t offset_stride,
-                int64_t n, float* obs_out, void* stream);
+                int64_t n, float* obs_out, int64_t out_stride, void* stream);
 
 /* One terrain per sample (hf_batch_stride = X*Y, min_center_stride = 2, base_z_stride = 1) or one
  * terrain shared by the whole batch (strides 0).  x_nodes[X] / y_nodes[Y] are the torch.linspace node
@@ -370,9 +371,12 @@ typedef struct ParcDoneSpec {
 /* compute_char_obs (envs/ig_char_env.py:582-626): obs_out [n, W],
  * W = (root_height_obs ? 1 : 0) + 6 + 3 + 3 + 6*num_joint_rots + dof_size + 3*num_keys, laid out as
  * [root z] | tan-norm of the (heading-local unless global_obs) root rotation | root_vel | root_ang_vel |
- * tan-norm of every joint rotation | dof_vel | key positions relative to the root (heading-local). */
+ * tan-norm of every joint rotation | dof_vel | key positions relative to the root (heading-local).
+ * Rows of obs_out are out_stride floats apart (0 = dense, W): the block can be written straight into a
+ * wider policy-observation row. */
 int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_joint_rots, int32_t dof_size,
-                  int32_t num_keys, int32_t global_obs, int32_t root_height_obs, float* obs_out, void* stream);
+                  int32_t num_keys, int32_t global_obs, int32_t root_height_obs, float* obs_out,
+                  int64_t out_stride, void* stream);
 
 /* compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): future targets [n,S,...] expressed against the
  * character (ref_root_pos [n,3], ref_root_rot [n,4]); obs_out [n, S, 3 + 6 + 6*num_joint_rots + 3*num_keys] =
@@ -380,12 +384,13 @@ int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_joint_rots,
  * Zero-copy views: the target arrays hold tar_env_stride (>= S) step rows per env, of which the S starting at
  * the given pointers are used (pass S for dense arrays; S+1 and pointers at step 1 for the outputs of
  * parc_motion_query_steps); with key_body_ids (device int32 [K]) non-NULL, tar_key_pos is a body-position
- * array [rows, num_bodies, 3] over the same rows. */
+ * array [rows, num_bodies, 3] over the same rows.  Env e's S*W block starts at obs_out + e * out_env_stride
+ * (0 = dense, S*W). */
 int parc_tar_obs(const float* ref_root_pos, const float* ref_root_rot, const float* tar_root_pos,
                  const float* tar_root_rot, const float* tar_joint_rot, const float* tar_key_pos, int64_t n,
                  int32_t num_steps, int32_t num_joint_rots, int32_t num_keys, int32_t global_obs,
                  int32_t global_tar_root_h_obs, int32_t tar_env_stride, const int32_t* key_body_ids,
-                 int32_t num_bodies, float* obs_out, void* stream);
+                 int32_t num_bodies, float* obs_out, int64_t out_env_stride, void* stream);
 
 /* compute_deepmimic_reward (envs/ig_parkour/mgdm_dm_util.py:328-397): reward_out [n,5] =
  * exp(-0.25 pose), exp(-0.01 vel), exp(-5 (root_pos + 0.1 root_rot)), exp(-(root_vel + 0.1 root_ang_vel)),

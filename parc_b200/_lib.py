@@ -139,15 +139,16 @@ SIGNATURES = {
     "parc_exp_map_to_quat_bwd": (C.c_int, [_V, _V, _I64, _V, _V]),
     "parc_hf_sample": (C.c_int, [_P(ParcHeightfield), _V, _I64, _V, _V, _V]),
     "parc_selftest_grid_index": (C.c_int, [_F, _F, _I32, _V, _V]),
-    "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _V, _V, _I32, _I64, _V, _V]),
+    "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _V, _V, _I32, _I64, _V, _I64, _V]),
     "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
     "parc_frames_fk": (C.c_int, [_V, _I64, _I32, _P(ParcCharModel), _V, _V, _V, _V, _V]),
     "parc_clip_label": (C.c_int, [_V, _I64, _I64, _I32, _P(ParcCharModel), _P(ParcBodyPoints), _P(ParcTerrainBatch),
                                   _P(ParcKeyBodies), _F, _V, _V, _V, _V, _V, _V, _V, _V]),
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
                                  _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
-    "parc_char_obs": (C.c_int, [_P(ParcCharState), _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
-    "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _V, _I32, _V, _V]),
+    "parc_char_obs": (C.c_int, [_P(ParcCharState), _I64, _I32, _I32, _I32, _I32, _I32, _V, _I64, _V]),
+    "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _V, _I32, _V, _I64,
+                               _V]),
     "parc_deepmimic_reward": (C.c_int, [_P(ParcCharState), _P(ParcCharState), _I64, _I32, _I32, _I32, _V, _V, _I32,
                                         _I32, _V, _V]),
     "parc_done": (C.c_int, [_P(ParcDoneSpec), _V, _V, _V, _V, _V, _V, _V, _P(ParcHeightfield), _V, _I32, _I32, _I64,

@@ -24,35 +24,41 @@ hf_sample_kernel(const __grid_constant__ ParcHeightfield t, const float* __restr
   }
 }
 
-// One thread per (env, template point): consecutive threads write consecutive outputs.
-__global__ void __launch_bounds__(256)
+// One warp per env: heading / root are resolved once per env, lanes stride over the template points (consecutive
+// lanes write consecutive outputs); the cell index uses the hoisted-reciprocal form of parc_common.cuh, which
+// parc_selftest_grid_index proves index-identical to the reference's true division.
+__global__ void __launch_bounds__(128)
 hf_obs_kernel(const __grid_constant__ ParcHeightfield t, const __grid_constant__ ParcObsSpec obs,
               const float* __restrict__ root, int root_stride, const float* __restrict__ heading,
               const float* __restrict__ root_rot, const float* __restrict__ root_offset, int offset_stride, int64_t n,
-              float* __restrict__ out) {
+              float* __restrict__ out, int64_t out_stride) {
   const int P = obs.num_points;
-  const int64_t total = n * P;
+  const int lane = threadIdx.x & 31;
   const float2* __restrict__ tmpl = reinterpret_cast<const float2*>(obs.tmpl_xy);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i / P;
-    const int k = (int)(i - e * P);
+  const GridAxis gx = make_grid_axis(t.min_x, t.dx, t.dim_x);
+  const GridAxis gy = make_grid_axis(t.min_y, t.dy, t.dim_y);
+  const int64_t warp0 = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * 4;
+  for (int64_t e = warp0; e < n; e += nwarps) {
     const float* r = root + e * root_stride;
     // heading given, or taken from the root rotation as the caller would (util/torch_util.py:470-479)
     const float h = heading ? __ldg(heading + e) : calc_heading(__ldg(reinterpret_cast<const float4*>(root_rot) + e));
     const float sn = sinf(h), cs = cosf(h);
-    float rx = __ldg(r), ry = __ldg(r + 1);
+    float rx = __ldg(r), ry = __ldg(r + 1), rz = obs.relative ? __ldg(r + 2) : 0.0f;
     if (root_offset) {               // env-local -> terrain coordinates (ig_parkour_env.py:640), one add per component
       rx = add_rn(rx, __ldg(root_offset + e * offset_stride));
       ry = add_rn(ry, __ldg(root_offset + e * offset_stride + 1));
+      if (obs.relative) rz = add_rn(rz, __ldg(root_offset + e * offset_stride + 2));
     }
-    const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, rx, ry);
-    float z = hf_lookup(t, w.x, w.y);
-    if (obs.relative) {
-      float rz = __ldg(r + 2);
-      if (root_offset) rz = add_rn(rz, __ldg(root_offset + e * offset_stride + 2));
-      z = fminf(fmaxf(sub_rn(z, rz), obs.min_h), obs.max_h);
+    float* __restrict__ o = out + e * out_stride;
+#pragma unroll 4
+    for (int k = lane; k < P; k += 32) {
+      const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, rx, ry);
+      const int ix = grid_index_fast(w.x, gx), iy = grid_index_fast(w.y, gy);
+      float z = __ldg(t.hf + (size_t)ix * t.dim_y + iy);
+      if (obs.relative) z = fminf(fmaxf(sub_rn(z, rz), obs.min_h), obs.max_h);
+      o[k] = z;
     }
-    out[i] = z;
   }
 }
 
@@ -88,7 +94,7 @@ extern "C" int parc_hf_sample(const ParcHeightfield* hf, const float* xy, int64_
 extern "C" int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* root,
                            int32_t root_stride, const float* heading, const float* root_rot,
                            const float* root_offset, int32_t offset_stride, int64_t n, float* obs_out,
-                           void* stream) {
+                           int64_t out_stride, void* stream) {
   int rc = check_hf(hf);
   if (rc) return rc;
   if (!obs) return PARC_E_NULL;
@@ -98,7 +104,11 @@ extern "C" int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, co
   if ((reinterpret_cast<uintptr_t>(obs->tmpl_xy) & 7u) != 0) return PARC_E_ALIGN;
   if (!heading && !aligned16(root_rot)) return PARC_E_ALIGN;
   if (root_offset && offset_stride < (obs->relative ? 3 : 2)) return PARC_E_SIZE;
-  hf_obs_kernel<<<flat_grid(n * obs->num_points), 256, 0, (cudaStream_t)stream>>>(
-      *hf, *obs, root, root_stride, heading, root_rot, root_offset, offset_stride, n, obs_out);
+  if (out_stride == 0) out_stride = obs->num_points;
+  if (out_stride < obs->num_points) return PARC_E_SIZE;
+  int64_t ctas = (n + 3) / 4;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  hf_obs_kernel<<<(int)ctas, 128, 0, (cudaStream_t)stream>>>(*hf, *obs, root, root_stride, heading, root_rot,
+                                                            root_offset, offset_stride, n, obs_out, out_stride);
   return check_launch();
 }

@@ -71,9 +71,8 @@ __device__ __forceinline__ float sq3(const float3& d) { return d.x * d.x + d.y *
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS)
 char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int D, int K, int global_obs,
-                int root_height_obs, float* __restrict__ out) {
+                int root_height_obs, float* __restrict__ out, int64_t W) {
   const int lane = threadIdx.x & 31;
-  const int W = (root_height_obs ? 1 : 0) + 12 + 6 * Jm1 + D + 3 * K;
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
@@ -109,44 +108,53 @@ char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int
 
 // ------------------------------------------------------------------------------------------------
 // compute_tar_obs: per (env, step)  root_pos_obs 3 | root tan-norm 6 | joint tan-norm 6(J-1) | key 3K
+// One warp per env: the character's heading frame is resolved once, then the lanes stride over the env's
+// S * (1 + (J-1) + K) work items (root, joint, key body of each step), so all 32 lanes stay busy.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS)
 tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__ ref_root_rot,
                const float* __restrict__ tar_root_pos, const float* __restrict__ tar_root_rot,
                const float* __restrict__ tar_joint_rot, const float* __restrict__ tar_key_pos, int64_t n, int S,
                int Jm1, int K, int global_obs, int global_tar_root_h, int tar_env_stride,
-               const int32_t* __restrict__ key_body_ids, int num_bodies, float* __restrict__ out) {
+               const int32_t* __restrict__ key_body_ids, int num_bodies, float* __restrict__ out,
+               int64_t out_env_stride) {
   const int lane = threadIdx.x & 31;
   const int W = 9 + 6 * Jm1 + 3 * K;
-  const int64_t total = n * S;
+  const int per_step = 1 + Jm1 + K;
+  const int items = S * per_step;
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
-  for (int64_t q = warp0; q < total; q += nwarps) {
-    const int64_t e = q / S;
-    const int64_t r = e * tar_env_stride + (q - e * S);      // row of this (env, step) in the target arrays
-    float* __restrict__ o = out + q * W;
-    const float3 tp = ld3(tar_root_pos + r * 3);
-    float4 tr = ld4(tar_root_rot + r * 4);
-    float3 po = sub3(tp, ld3(ref_root_pos + e * 3));
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    const float3 cp = ld3(ref_root_pos + e * 3);
     float4 hinv = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (!global_obs) {
-      hinv = heading_inverse_quat(ld4(ref_root_rot + e * 4));
-      po = quat_rotate(hinv, po);
-      tr = quat_mul(hinv, tr);
-    }
-    if (lane == 0) {
-      st3(o, make_float3(po.x, po.y, global_tar_root_h ? tp.z : po.z));
-      store_tan_norm(o + 3, tr);
-    }
-    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 9 + 6 * j, ld4(tar_joint_rot + (r * Jm1 + j) * 4));
-    float* __restrict__ ok = o + 9 + 6 * Jm1;
-    for (int k = lane; k < K; k += 32) {
-      float3 p = sub3(key_position(tar_key_pos, key_body_ids, num_bodies, K, q, r, k), tp);
-      if (!global_obs) {
-        p = quat_rotate(hinv, p);
-        p.x += po.x; p.y += po.y; p.z += po.z;       // the rotated root offset, BEFORE the height override
+    if (!global_obs) hinv = heading_inverse_quat(ld4(ref_root_rot + e * 4));
+    float* __restrict__ oe = out + e * out_env_stride;
+    for (int it = lane; it < items; it += 32) {
+      const int st = it / per_step;
+      const int w = it - st * per_step;                      // 0 = root, 1..J-1 = joints, then key bodies
+      const int64_t r = e * tar_env_stride + st;             // row of this (env, step) in the target arrays
+      float* __restrict__ o = oe + (int64_t)st * W;
+      if (w >= 1 && w <= Jm1) {
+        store_tan_norm(o + 9 + 6 * (w - 1), ld4(tar_joint_rot + (r * Jm1 + (w - 1)) * 4));
+        continue;
       }
-      st3(ok + 3 * k, p);
+      const float3 tp = ld3(tar_root_pos + r * 3);
+      float3 po = sub3(tp, cp);
+      if (!global_obs) po = quat_rotate(hinv, po);
+      if (w == 0) {
+        float4 tr = ld4(tar_root_rot + r * 4);
+        if (!global_obs) tr = quat_mul(hinv, tr);
+        st3(o, make_float3(po.x, po.y, global_tar_root_h ? tp.z : po.z));
+        store_tan_norm(o + 3, tr);
+      } else {
+        const int k = w - 1 - Jm1;
+        float3 p = sub3(key_position(tar_key_pos, key_body_ids, num_bodies, K, e * S + st, r, k), tp);
+        if (!global_obs) {
+          p = quat_rotate(hinv, p);
+          p.x += po.x; p.y += po.y; p.z += po.z;     // the rotated root offset, BEFORE the height override
+        }
+        st3(o + 9 + 6 * Jm1 + 3 * k, p);
+      }
     }
   }
 }
@@ -323,14 +331,18 @@ using namespace parc;
 
 extern "C" int parc_char_obs(const ParcCharState* state, int64_t n, int32_t num_joint_rots, int32_t dof_size,
                              int32_t num_keys, int32_t global_obs, int32_t root_height_obs, float* obs_out,
-                             void* stream) {
+                             int64_t out_stride, void* stream) {
   if (n < 0 || num_joint_rots < 0 || dof_size < 0 || num_keys < 0) return PARC_E_SIZE;
+  const int64_t width = (root_height_obs ? 1 : 0) + 12 + 6 * (int64_t)num_joint_rots + dof_size + 3 * (int64_t)num_keys;
+  if (out_stride == 0) out_stride = width;
+  if (out_stride < width) return PARC_E_SIZE;
   if (n == 0) return PARC_OK;
   int rc = check_state(state, dof_size, num_keys, true);
   if (rc) return rc;
   if (!obs_out) return PARC_E_NULL;
   char_obs_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(*state, n, num_joint_rots, dof_size,
-                                                                         num_keys, global_obs, root_height_obs, obs_out);
+                                                                         num_keys, global_obs, root_height_obs, obs_out,
+                                                                         out_stride);
   return check_launch();
 }
 
@@ -338,16 +350,21 @@ extern "C" int parc_tar_obs(const float* ref_root_pos, const float* ref_root_rot
                             const float* tar_root_rot, const float* tar_joint_rot, const float* tar_key_pos,
                             int64_t n, int32_t num_steps, int32_t num_joint_rots, int32_t num_keys,
                             int32_t global_obs, int32_t global_tar_root_h_obs, int32_t tar_env_stride,
-                            const int32_t* key_body_ids, int32_t num_bodies, float* obs_out, void* stream) {
+                            const int32_t* key_body_ids, int32_t num_bodies, float* obs_out,
+                            int64_t out_env_stride, void* stream) {
   if (n < 0 || num_steps < 0 || num_joint_rots < 0 || num_keys < 0) return PARC_E_SIZE;
   if (tar_env_stride < num_steps || (key_body_ids && num_bodies < 1)) return PARC_E_SIZE;
+  const int64_t env_width = (int64_t)num_steps * (9 + 6 * (int64_t)num_joint_rots + 3 * (int64_t)num_keys);
+  if (out_env_stride == 0) out_env_stride = env_width;
+  if (out_env_stride < env_width) return PARC_E_SIZE;
   if (n == 0 || num_steps == 0) return PARC_OK;
   if (!ref_root_pos || !ref_root_rot || !tar_root_pos || !tar_root_rot || !obs_out) return PARC_E_NULL;
   if ((num_joint_rots > 0 && !tar_joint_rot) || (num_keys > 0 && !tar_key_pos)) return PARC_E_NULL;
   if (!aligned16(ref_root_rot) || !aligned16(tar_root_rot) || !aligned16(tar_joint_rot)) return PARC_E_ALIGN;
-  tar_obs_kernel<<<warp_grid(n * num_steps), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+  tar_obs_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
       ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot, tar_key_pos, n, num_steps,
-      num_joint_rots, num_keys, global_obs, global_tar_root_h_obs, tar_env_stride, key_body_ids, num_bodies, obs_out);
+      num_joint_rots, num_keys, global_obs, global_tar_root_h_obs, tar_env_stride, key_body_ids, num_bodies, obs_out,
+      out_env_stride);
   return check_launch();
 }
 

@@ -15,7 +15,8 @@ package, reading the simulator's state tensors in place:
   1          target observation, written straight into the policy observation   (parc_tar_obs)
   1          DeepMimic reward terms                                             (parc_deepmimic_reward)
   1          episode flags incl. termination heights                            (parc_done)
-  + 1 torch.cat for the final observation row.
+  + 2 small copies (target / character contact flags).  The observation operators write their blocks of the
+  policy-observation row in place (row-strided outputs), so there is no concatenation pass.
 
 Every output buffer is allocated once, so the sequence can be captured in a CUDA graph (`capture()`), after
 which a step is one graph launch.  The Isaac Gym classes themselves (simulation, resets, actors) are out of
@@ -74,8 +75,25 @@ class TrackerStep:
         K = int(self.key_body_ids.shape[0])
         self.char_w = (1 if root_height_obs else 0) + 12 + 6 * (J - 1) + D + 3 * K
         self.tar_w = 9 + 6 * (J - 1) + 3 * K
-        self._tar_obs = torch.empty(self.n, self.S, self.tar_w, dtype=torch.float32, device=self.device)
+        # the policy-observation row, written in place by the operators (no concatenation pass):
+        # char_obs | tar_obs | tar_contacts | [char_contacts] | ray heightmap   (ig_parkour_env.py:1178-1215)
+        self.P = int(self.ray_xy_points.shape[0])
+        self._contacts = bool(getattr(mlib, "_contact_info", False))
+        self._obs_bufs = {}
         self._graph = None
+
+    def _obs_layout(self, with_char_contacts: bool):
+        J = self.kcm.get_num_joints()
+        cols, c = {}, 0
+        for name, w in (("char", self.char_w), ("tar", self.S * self.tar_w),
+                        ("tar_contacts", self.S * J if self._contacts else 0),
+                        ("char_contacts", J if (self._contacts and with_char_contacts) else 0), ("ray", self.P)):
+            cols[name] = (c, c + w)
+            c += w
+        key = bool(with_char_contacts)
+        if key not in self._obs_bufs:
+            self._obs_bufs[key] = torch.empty(self.n, c, dtype=torch.float32, device=self.device)
+        return self._obs_bufs[key], cols
 
     # ---- views of the query output: [n, S+1, ...] rows, step 0 = reference frame, 1.. = targets -------------
     def _views(self, out):
@@ -94,22 +112,23 @@ class TrackerStep:
         ref_contacts)."""
         c = self.cfg
         ref, tar = self._views(self._plan.launch())
+        obs, col = self._obs_layout(char_contacts is not None)
+        blk = lambda name: obs[:, col[name][0]:col[name][1]]
         joint_rot = self.kcm.dof_to_rot(dof_pos)
         # ray heightmap around the SIMULATED character (ig_parkour_env.py:636-646, mgdm_dm_util.py:158-179)
         # heading = calc_heading(root_rot) and the env-local -> terrain shift are taken inside the launch
         ray_hfs = ops.hf_obs(self.terrain.hf_desc(), self.ray_xy_points, root_pos, None, relative=True,
-                             min_h=c["min_obs_h"], max_h=c["max_obs_h"], root_rot=root_rot, root_offset=env_offsets)
+                             min_h=c["min_obs_h"], max_h=c["max_obs_h"], root_rot=root_rot, root_offset=env_offsets,
+                             out=blk("ray"))
         char_obs = ops.char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, body_pos,
-                                c["global_obs"], c["root_height_obs"], key_body_ids=self.key_body_ids)
-        ops.tar_obs(root_pos, root_rot, tar["root_pos"], tar["root_rot"], tar["joint_rot"], tar["body_pos"],
-                    c["global_obs"], False, key_body_ids=self.key_body_ids, out=self._tar_obs)
-        parts = [char_obs, self._tar_obs.view(self.n, -1)]
-        if "contacts" in tar:
-            parts.append(tar["contacts"].reshape(self.n, -1))
+                                c["global_obs"], c["root_height_obs"], key_body_ids=self.key_body_ids, out=blk("char"))
+        tar_obs = ops.tar_obs(root_pos, root_rot, tar["root_pos"], tar["root_rot"], tar["joint_rot"], tar["body_pos"],
+                              c["global_obs"], False, key_body_ids=self.key_body_ids, out=blk("tar"))
+        if self._contacts:
+            J = self.kcm.get_num_joints()
+            blk("tar_contacts").view(self.n, self.S, J).copy_(tar["contacts"])
             if char_contacts is not None:
-                parts.append(char_contacts)
-        parts.append(ray_hfs)
-        obs = torch.cat(parts, dim=-1)
+                blk("char_contacts").copy_(char_contacts)
         reward_terms = ops.deepmimic_reward(
             (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, body_pos),
             (ref["root_pos"], ref["root_rot"], ref["root_vel"], ref["root_ang_vel"], ref["joint_rot"], ref["dof_vel"],
@@ -120,7 +139,8 @@ class TrackerStep:
                               c["enable_early_termination"], c["track_root"], c["root_pos_termination_dist"],
                               c["root_rot_termination_angle"], hf=self.terrain.hf_desc(), env_offsets=env_offsets,
                               termination_height=c["termination_height"])
-        res = dict(obs=obs, reward_terms=reward_terms, done=done, char_obs=char_obs, tar_obs=self._tar_obs, ray_hfs=ray_hfs)
+        res = dict(obs=obs, reward_terms=reward_terms, done=done, char_obs=char_obs,
+                   tar_obs=tar_obs.view(self.n, self.S, self.tar_w), ray_hfs=ray_hfs)
         res.update({"ref_" + k: t for k, t in ref.items()})
         return res
 

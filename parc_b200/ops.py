@@ -461,12 +461,12 @@ def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, headi
     ro = f32c(root_offset) if root_offset is not None else None
     tm = f32c(tmpl_xy).reshape(-1, 2)
     n, P = r.shape[0], tm.shape[0]
-    if out is None:
-        out = torch.empty((n, P), dtype=torch.float32, device=r.device)
+    out, out_stride = _out_rows(out, n, P, r.device)
     h, o = hf.c_struct(), _obs_struct(tm, relative, min_h, max_h)
     with torch.cuda.device(r.device):
         rc = _lib.load().parc_hf_obs(C.byref(h), C.byref(o), r.data_ptr(), int(r.shape[1]), ptr(hd), ptr(rr), ptr(ro),
-                                     int(ro.shape[1]) if ro is not None else 0, n, out.data_ptr(), stream_ptr(r.device))
+                                     int(ro.shape[1]) if ro is not None else 0, n, out.data_ptr(), out_stride,
+                                     stream_ptr(r.device))
     check(rc, "parc_hf_obs")
     return out
 
@@ -715,6 +715,18 @@ def unpack_frame_masks(bits: torch.Tensor, X: int, Y: int) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # tracker step assembly: policy observation, reward, done -- one launch each
 # ----------------------------------------------------------------------------------------------
+def _out_rows(out: Optional[torch.Tensor], n: int, width: int, device) -> Tuple[torch.Tensor, int]:
+    """(out, row stride in floats): a fresh dense [n,width] buffer, or the caller's -- which may be a column slice
+    of a wider row-major buffer (e.g. a block of the policy-observation row): unit inner stride required."""
+    if out is None:
+        return torch.empty((n, width), dtype=torch.float32, device=device), width
+    assert out.dtype == torch.float32 and tuple(out.shape) == (n, width) and out.is_cuda
+    assert width <= 1 or out.stride(1) == 1
+    stride = int(out.stride(0)) if n > 1 else max(int(out.stride(0)), width)
+    assert stride >= width
+    return out, stride
+
+
 def _has(t: Optional[torch.Tensor]) -> bool:
     return t is not None and t.numel() > 0
 
@@ -789,16 +801,17 @@ def _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, 
 
 
 def char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos, global_obs: bool,
-             root_height_obs: bool, key_body_ids=None) -> torch.Tensor:
+             root_height_obs: bool, key_body_ids=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """compute_char_obs (envs/ig_char_env.py:582-626) -> [n, W]; key_pos [n,K,3] or empty/None -- or, with
-    `key_body_ids`, the body positions [n,J,3] to pick the key bodies from.  One launch."""
+    `key_body_ids`, the body positions [n,J,3] to pick the key bodies from.  `out` may be a column block of a
+    wider observation buffer.  One launch."""
     st, keep, n, jm1, d, k = _char_state(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key_pos,
                                          key_body_ids)
     dev = keep[0].device
-    out = torch.empty((n, (1 if root_height_obs else 0) + 12 + 6 * jm1 + d + 3 * k), dtype=torch.float32, device=dev)
+    out, out_stride = _out_rows(out, n, (1 if root_height_obs else 0) + 12 + 6 * jm1 + d + 3 * k, dev)
     with torch.cuda.device(dev):
         rc = _lib.load().parc_char_obs(C.byref(st), n, jm1, d, k, int(bool(global_obs)), int(bool(root_height_obs)),
-                                       out.data_ptr(), stream_ptr(dev))
+                                       out.data_ptr(), out_stride, stream_ptr(dev))
     check(rc, "parc_char_obs")
     return out
 
@@ -834,16 +847,17 @@ def tar_obs(ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_ro
     else:
         k, nb = (tk.shape[-2] if tk is not None else 0), 0
         assert k == 0 or tk.shape == (n, S, k, 3)
-    shape = (n, S, 9 + 6 * jm1 + 3 * k)
+    W = 9 + 6 * jm1 + 3 * k
     if out is None:
-        out = torch.empty(shape, dtype=torch.float32, device=tp.device)
-    assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.float32
+        flat, out_stride = torch.empty((n, S * W), dtype=torch.float32, device=tp.device), S * W
+    else:                                     # [n, S*W] (possibly a column block of a wider buffer) or [n, S, W]
+        flat, out_stride = _out_rows(out.view(n, S * W) if out.dim() == 3 else out, n, S * W, tp.device)
     with torch.cuda.device(tp.device):
         rc = _lib.load().parc_tar_obs(rp.data_ptr(), rr.data_ptr(), tp.data_ptr(), tr.data_ptr(), tj.data_ptr(), ptr(tk),
                                       n, S, jm1, k, int(bool(global_obs)), int(bool(global_tar_root_h_obs)), stride,
-                                      ptr(ids), nb, out.data_ptr(), stream_ptr(tp.device))
+                                      ptr(ids), nb, flat.data_ptr(), out_stride, stream_ptr(tp.device))
     check(rc, "parc_tar_obs")
-    return out
+    return flat.view(n, S, W) if out is None else out
 
 
 def deepmimic_reward(sim: tuple, tar: tuple, joint_rot_err_w, dof_err_w, track_root_h: bool, track_root: bool,

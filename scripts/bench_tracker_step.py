@@ -33,10 +33,10 @@ def bytes_per_env_step(J, D, K, S, P):
     char = (13 + 4 * (J - 1) + D + 3 * K) * 4 + char_w * 4
     tar = S * (7 + 4 * (J - 1) + 3 * K) * 4 + 28 + S * tar_w * 4
     W = char_w + S * tar_w + S * J + J + P
-    cat = 2 * W * 4
+    cat = 2 * (S * J + J) * 4            # the two contact-flag copies; every other block is written in place
     rew = 2 * (13 + 4 * (J - 1) + D + 3 * K) * 4 + 20
     done = 4 + 2 * J * 12 + 32 + J * 12 + 12 + J * 4 + 4
-    return dict(query=q, dof_to_rot=d2r, ray_obs=ray, char_obs=char, tar_obs=tar, concat=cat, reward=rew, done=done,
+    return dict(query=q, dof_to_rot=d2r, ray_obs=ray, char_obs=char, tar_obs=tar, contact_copies=cat, reward=rew, done=done,
                 total=q + d2r + ray + char + tar + cat + rew + done, obs_width=W)
 
 
@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--clips", type=int, default=2048)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
     import __graft_entry__ as entry
     entry.ensure_built()
@@ -166,7 +167,7 @@ def main():
         return obs, rew, done
 
     cpu = None
-    if True:
+    if not args.no_cpu:
         o_obs, o_rew, o_done = cpu_step()
         best = 1e9
         for _ in range(args.cpu_reps):

@@ -14,6 +14,10 @@ CMD2="python bench.py --steps 6 --warmup 3 --envs 65536 --no-cpu-baseline --no-s
 $CMD2 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:motion_query -s 4 -c 2 -f -o gpurun_out/prof_${TAG}_query65k $CMD2 > gpurun_out/ncu_full65k.log 2>&1
 python scripts/bench_loss.py > gpurun_out/bench_loss.log 2>&1; tail -1 gpurun_out/bench_loss.log
 python scripts/bench_sweep.py > gpurun_out/bench_sweep.log 2>&1; tail -1 gpurun_out/bench_sweep.log
+python scripts/bench_motion_opt.py > gpurun_out/bench_motion_opt.log 2>&1; tail -1 gpurun_out/bench_motion_opt.log
+python scripts/bench_tracker_step.py > gpurun_out/bench_tracker_step.log 2>&1; tail -1 gpurun_out/bench_tracker_step.log
+CMD3="python scripts/bench_tracker_step.py --steps 3 --no-cpu"
+$CMD3 > gpurun_out/plain4.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}_step.csv $CMD3 > gpurun_out/ncu_list_step.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log
 python - <<'PY'
 import json
