@@ -413,6 +413,20 @@ int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot
               int32_t offset_stride, int32_t tar_env_stride, int64_t n, int32_t num_bodies, int32_t* done_out,
               float* term_heights_out, void* stream);
 
+/* ---- f4: GPU loader -----------------------------------------------------------------
+ * Raw clip frames -> packed frame rows, every frame of every clip in one launch: what MotionLib._load_motions /
+ * _load_motion_frames do per clip on the host (anim/motion_lib.py:137-202, :204-380 -- extract_frame_data with
+ * quat_pos on the joints :405-423, forward-difference root velocities with the last frame repeated :281-288,
+ * KinCharModel.compute_frame_dof_vel anim/kin_char_model.py:543-581) plus parc_pack_frames.
+ * frames [total, frame_stride >= 6 + D] (root_pos | root exp-map | DoFs), contacts [total, J] or NULL,
+ * frame_clip [total] int32 = clip of each frame, per-clip start / num_frames (int64), fps and the divisor of the
+ * DoF velocities (1/fps -- or fps itself to reproduce the motion_frames quirk of :178).  rows_out
+ * [total, row_floats], 16-byte aligned.  Clips of a single frame get zero velocities. */
+int parc_build_tables(const float* frames, int64_t total_frames, int32_t frame_stride, const float* contacts,
+                      const int32_t* frame_clip, const int64_t* clip_start, const int64_t* clip_num_frames,
+                      const float* clip_fps, const float* clip_dof_vel_dt, int64_t num_clips,
+                      const ParcCharModel* model, float* rows_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,7 @@ SIGNATURES = {
                                   _P(ParcKeyBodies), _F, _V, _V, _V, _V, _V, _V, _V, _V]),
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
                                  _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
+    "parc_build_tables": (C.c_int, [_V, _I64, _I32, _V, _V, _V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V]),
     "parc_char_obs": (C.c_int, [_P(ParcCharState), _I64, _I32, _I32, _I32, _I32, _I32, _V, _I64, _V]),
     "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _V, _I32, _V, _I64,
                                _V]),

@@ -54,7 +54,12 @@ def load_clip_file(path):
 
 class MotionLib:
     def __init__(self, motion_input, kin_char_model: KinCharModel, device, init_type="motion_file",
-                 loop_mode=None, fps=None, contact_info=False, contacts=None):
+                 loop_mode=None, fps=None, contact_info=False, contacts=None, build_on_device=False):
+        """Reference signature (:22-40) plus `build_on_device`: False (default) builds the frame tables with host
+        torch ops in the reference's operation order (bit-identical tables); True hands the raw frames to the GPU
+        loader (one launch for all clips, csrc/table_build.cu) -- what a 100k-clip library wants.  CUDA frames
+        passed to init_type="motion_frames" always use the GPU loader.  init_type="packed_file" opens a file
+        written by `save_packed` (no per-clip work at all)."""
         self._device = device
         self._kin_char_model = kin_char_model
         self._contact_info = contact_info
@@ -64,13 +69,23 @@ class MotionLib:
         self._host_model = kin_char_model if torch.device(kin_char_model._device).type == "cpu" \
             else kin_char_model.get_copy("cpu")
 
+        self._build_on_device = bool(build_on_device)
         if init_type == "motion_file":
             self._load_motions(motion_input)
+        elif init_type == "packed_file":
+            from . import packed_format
+            packed_format.load_into(self, motion_input)
         elif init_type == "motion_frames":   # (num motions, num_frames, dofs)
             self._load_motion_frames(motion_input, loop_mode, fps, frame_contacts=contacts if contact_info else None)
         else:
             # the reference's "diffusion_file" branch calls a method that does not exist (:30-31)
             raise ValueError(f"unsupported init_type {init_type!r}")
+
+    def save_packed(self, path):
+        """Write the library as one packed binary file (anim/packed_format.py); reopen it with
+        `MotionLib(path, kin_char_model, device, init_type="packed_file", contact_info=...)`."""
+        from . import packed_format
+        packed_format.save(self, path)
 
     # ------------------------------------------------------------------ simple accessors
     def num_motions(self):
@@ -246,24 +261,28 @@ class MotionLib:
             assert motion_frames.dim() == frame_contacts.dim() == 3, frame_contacts.shape
         M, F = motion_frames.shape[0], motion_frames.shape[1]
         on_device = torch.is_tensor(motion_frames) and motion_frames.is_cuda
-        if on_device:
-            # CUDA frames (e.g. a batch the MDM just generated): build the tables where the data is, as the
-            # reference does on its device -- exp-map / DoF conversion through the CUDA operators, the
-            # finite differences as elementwise torch ops; nothing visits the host.
-            fr = motion_frames.detach().to(torch.float32)
-            model = self._kin_char_model
-            root_pos = fr[..., 0:3].clone()
-            root_rot = ops.exp_map_to_quat(fr[..., 3:6])
-            joint_rot = torch_util.quat_pos(model.dof_to_rot(fr[..., 6:6 + model.get_dof_size()]))
-        else:
-            model = self._host_model
-            root_pos, root_rot, joint_rot = self._extract_frame_data(motion_frames)
+        if (on_device or self._build_on_device) and torch.device(self._device).type == "cuda":
+            # CUDA frames (e.g. a batch the MDM just generated) or an explicit request: the GPU loader builds the
+            # packed rows of all clips in one launch; nothing visits the host.
+            dev = self._device
+            fr = torch.as_tensor(motion_frames).detach().to(device=dev, dtype=torch.float32)
+            ct = None if frame_contacts is None else torch.as_tensor(frame_contacts).detach().to(device=dev,
+                                                                                                 dtype=torch.float32)
+            ones = torch.ones(M, dtype=torch.float32, device=dev)
+            self._adopt_device_build(fr.reshape(M * F, -1), None if ct is None else ct.reshape(M * F, -1),
+                                     num_frames=F * torch.ones(M, dtype=torch.long, device=dev), fps=fps * ones,
+                                     dof_vel_dt=fps * ones,                 # the reference's quirk (:178), kept
+                                     loop_modes=loop_mode.value * torch.ones(M, dtype=torch.int, device=dev),
+                                     weights=ones.clone())
+            return
+        model = self._host_model
+        root_pos, root_rot, joint_rot = self._extract_frame_data(motion_frames)
         delta = root_pos[:, -1] - root_pos[:, 0]
         delta[..., -1] = 0.0
         root_vel, root_ang_vel = self._finite_diff_vels(root_pos, root_rot, fps)
         dof_vel = model.compute_frame_dof_vel(joint_rot, fps)
         J = model.get_num_joints()
-        host = (lambda t: t) if on_device else (lambda t: torch.as_tensor(t, dtype=torch.float32).detach().cpu())
+        host = lambda t: torch.as_tensor(t, dtype=torch.float32).detach().cpu()
         dev = self._device
         self._motion_fps = fps * torch.ones(M, dtype=torch.float32, device=dev)
         self._motion_dt = 1.0 / fps * torch.ones(M, dtype=torch.float32, device=dev)
@@ -281,6 +300,44 @@ class MotionLib:
             frames=host(motion_frames.to(torch.float32)).reshape(-1, motion_frames.shape[-1]))
         self._finish_load()
 
+    def _adopt_device_build(self, frames, contacts, num_frames, fps, dof_vel_dt, loop_modes, weights, lengths=None):
+        """GPU loader: `frames` [total, 6+D] / `contacts` [total, J] of the concatenated clips and the
+        per-clip meta tensors, all on the device -> packed rows (one launch); the reference's per-frame tables become
+        zero-copy strided views of those rows."""
+        dev = self._device
+        model = self._kin_char_model.c_model()
+        rows, lay, start = ops.build_tables(model, frames, contacts if self._contact_info else None, num_frames, fps,
+                                            dof_vel_dt)
+        self._adopt_rows(rows, lay, frames, num_frames, start, fps, loop_modes, weights, lengths=lengths)
+
+    def _adopt_rows(self, rows, lay, frames, num_frames, start, fps, loop_modes, weights, lengths=None, delta=None):
+        dev = self._device
+        M = int(num_frames.shape[0])
+        J, D = self._kin_char_model.get_num_joints(), self._kin_char_model.get_dof_size()
+        v = ops.unpack_row_views(rows, lay, J, D)
+        self._frame_root_pos, self._frame_root_rot, self._frame_joint_rot = v["root_pos"], v["root_rot"], v["joint_rot"]
+        self._frame_root_vel, self._frame_root_ang_vel, self._frame_dof_vel = v["root_vel"], v["root_ang_vel"], v["dof_vel"]
+        if self._contact_info:
+            self._frame_contacts = v["contacts"]
+        self._motion_frames = frames
+        self._motion_fps = fps.to(torch.float32)
+        self._motion_dt = 1.0 / self._motion_fps
+        self._motion_num_frames = num_frames.to(torch.long)
+        # length = 1/fps * (n-1), formed in double and rounded once, as the reference's python floats are (:275,:355)
+        self._motion_lengths = lengths if lengths is not None else \
+            (1.0 / fps.double() * (num_frames.double() - 1.0)).to(torch.float32)
+        self._motion_loop_modes = loop_modes.to(torch.int)
+        self._motion_weights = weights
+        self._motion_ids = torch.arange(M, dtype=torch.long, device=dev)
+        self._motion_start_idx = start
+        if delta is None:
+            delta = v["root_pos"][start + self._motion_num_frames - 1] - v["root_pos"][start]
+            delta[..., -1] = 0.0
+        self._motion_root_pos_delta = delta
+        clips = ops.build_clip_meta(self._motion_num_frames, self._motion_loop_modes, self._motion_start_idx,
+                                    self._motion_lengths, self._motion_root_pos_delta, dev)
+        self._packed = ops.PackedTables(rows=rows, clips=clips, total_frames=int(rows.shape[0]), num_clips=M, layout=lay)
+
     def _load_motions(self, motion_file):
         """yaml list of clip pickles (or a single pickle).  Ref :204-380."""
         files, weights = self._fetch_motion_files(motion_file)
@@ -291,6 +348,8 @@ class MotionLib:
         self._terrains, self._hf_mask_inds = [], []
         D = self._host_model.get_dof_size()
         J = self._host_model.get_num_joints()
+        # GPU loader: the host only unpickles and concatenates; every conversion happens in one launch afterwards
+        on_device = self._build_on_device and torch.device(self._device).type == "cuda"
         for f, path in enumerate(files):
             if len(files) < 1000 or f % 500 == 0:
                 print("Loading {:d}/{:d} motion files: {:s}".format(f + 1, len(files), path))
@@ -307,17 +366,18 @@ class MotionLib:
             assert name not in self._motion_names
             self._motion_names.append(name)
             n = frames.shape[0]
-            root_pos, root_rot, joint_rot = self._extract_frame_data(frames)
-            delta = root_pos[-1] - root_pos[0]
-            delta[..., -1] = 0.0
-            root_vel, root_ang_vel = self._finite_diff_vels(root_pos, root_rot, fps)
-            acc["root_pos"].append(root_pos)
-            acc["root_rot"].append(root_rot)
-            acc["joint_rot"].append(joint_rot)
-            acc["root_vel"].append(root_vel)
-            acc["root_ang_vel"].append(root_ang_vel)
-            acc["dof_vel"].append(self._host_model.compute_frame_dof_vel(joint_rot, 1.0 / fps))
-            acc["delta"].append(delta)
+            if not on_device:
+                root_pos, root_rot, joint_rot = self._extract_frame_data(frames)
+                delta = root_pos[-1] - root_pos[0]
+                delta[..., -1] = 0.0
+                root_vel, root_ang_vel = self._finite_diff_vels(root_pos, root_rot, fps)
+                acc["root_pos"].append(root_pos)
+                acc["root_rot"].append(root_rot)
+                acc["joint_rot"].append(joint_rot)
+                acc["root_vel"].append(root_vel)
+                acc["root_ang_vel"].append(root_ang_vel)
+                acc["dof_vel"].append(self._host_model.compute_frame_dof_vel(joint_rot, 1.0 / fps))
+                acc["delta"].append(delta)
             acc["frames"].append(torch.as_tensor(np.asarray(frames), dtype=torch.float32))
             if self._contact_info:
                 if "contacts" in clip:
@@ -346,6 +406,17 @@ class MotionLib:
 
         dev = self._device
         w = torch.tensor(weights, dtype=torch.float32, device=dev)
+        if on_device:
+            fps_t = torch.tensor(meta["fps"], dtype=torch.float32, device=dev)
+            self._adopt_device_build(
+                torch.cat(acc["frames"], dim=0).to(dev), torch.cat(acc["contacts"], dim=0).to(dev) if self._contact_info else None,
+                num_frames=torch.tensor(meta["n"], dtype=torch.long, device=dev), fps=fps_t,
+                dof_vel_dt=torch.tensor(meta["dt"], dtype=torch.float32, device=dev),
+                loop_modes=torch.tensor(meta["loop"], dtype=torch.int, device=dev), weights=w / w.sum(),
+                lengths=torch.tensor(meta["len"], dtype=torch.float32, device=dev))
+            self._motion_dt = torch.tensor(meta["dt"], dtype=torch.float32, device=dev)
+            print("Loaded {:d} motions with a total length of {:.3f}s.".format(self.num_motions(), self.get_total_length()))
+            return
         self._motion_weights = w / w.sum()
         self._motion_fps = torch.tensor(meta["fps"], dtype=torch.float32, device=dev)
         self._motion_dt = torch.tensor(meta["dt"], dtype=torch.float32, device=dev)

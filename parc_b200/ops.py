@@ -110,6 +110,43 @@ def pack_frames(model: ParcCharModel, root_pos, root_rot, joint_rot, contacts, r
 # ----------------------------------------------------------------------------------------------
 # heightfield descriptors
 # ----------------------------------------------------------------------------------------------
+def build_tables(model: ParcCharModel, frames: torch.Tensor, contacts: Optional[torch.Tensor],
+                 num_frames: torch.Tensor, fps: torch.Tensor, dof_vel_dt: torch.Tensor):
+    """GPU loader: raw frames [total, >= 6+D] of M concatenated clips (`num_frames` [M] int64, `fps` /
+    `dof_vel_dt` [M] fp32, all CUDA) -> (packed rows [total, row_floats], layout, start_idx [M]).  One launch
+    (csrc/table_build.cu); see include/parc_b200.h::parc_build_tables."""
+    fr = f32c(frames)
+    ct = f32c(contacts) if contacts is not None else None
+    require_cuda(fr, ct, num_frames, fps, dof_vel_dt)
+    assert fr.dim() == 2
+    total, M = int(fr.shape[0]), int(num_frames.shape[0])
+    dev = fr.device
+    nf = num_frames.to(torch.int64).contiguous()
+    start = torch.cumsum(nf, 0) - nf
+    frame_clip = torch.repeat_interleave(torch.arange(M, dtype=torch.int32, device=dev), nf, output_size=total)
+    lay = row_layout(model)
+    rows = torch.empty((total, lay.row_floats), dtype=torch.float32, device=dev)
+    fps_c, dt_c = f32c(fps), f32c(dof_vel_dt)
+    if ct is not None:
+        assert tuple(ct.shape) == (total, model.num_bodies)
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_build_tables(fr.data_ptr(), total, int(fr.shape[1]), ptr(ct), frame_clip.data_ptr(),
+                                           start.data_ptr(), nf.data_ptr(), fps_c.data_ptr(), dt_c.data_ptr(), M,
+                                           C.byref(model), rows.data_ptr(), stream_ptr(dev))
+    check(rc, "parc_build_tables")
+    return rows, lay, start
+
+
+def unpack_row_views(rows: torch.Tensor, lay: ParcRowLayout, num_bodies: int, dof_size: int) -> dict:
+    """The reference's per-frame tables as zero-copy strided views of the packed rows."""
+    J, D = num_bodies, dof_size
+    cf, pf = lay.contact_slot * 4, lay.pose_slots * 4
+    total = rows.shape[0]
+    return dict(root_pos=rows[:, 0:3], root_rot=rows[:, 4:8], joint_rot=rows[:, 8:8 + 4 * (J - 1)].view(total, J - 1, 4),
+                contacts=rows[:, cf:cf + J], root_vel=rows[:, pf:pf + 3], root_ang_vel=rows[:, pf + 4:pf + 7],
+                dof_vel=rows[:, pf + 8:pf + 8 + D])
+
+
 @dataclass
 class HeightfieldDesc:
     """Host copy of SubTerrain's scalars + the device hf tensor, so launches never sync."""

@@ -5,6 +5,8 @@ Tolerances (north_star): frame indices / grid indices bit-exact; fp32 values wit
 Heightmap observations are exact except where the sample lands within a few ulps of a cell border,
 where sin/cos of the GPU and of the host may legitimately round the coordinate to the other cell.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -1157,3 +1159,89 @@ def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model,
     again = ts.step(*state)
     for k in ("obs", "reward_terms", "done"):
         assert torch.equal(out3[k], again[k]), k
+
+
+# ----------------------------------------------------------------------------------------- f4: GPU loader + packed file
+def test_gpu_loader_matches_host_built_tables(golden_lib, gpu_model, tmp_path):
+    """MotionLib(..., build_on_device=True): every clip's conversions and finite differences in one launch
+    (csrc/table_build.cu) against the host-built tables (which are bit-identical to the reference's).  Mixed
+    lengths (254 / 58 / 40 frames), mixed fps (30 / 60), CLAMP and WRAP."""
+    from parc_b200.anim.motion_lib import MotionLib
+    y = write_clip_library(tmp_path, lib_clips_from_golden())
+    lib = MotionLib(y, gpu_model, "cuda:0", init_type="motion_file", contact_info=True, build_on_device=True)
+    h = golden_lib
+    for k in ("_motion_num_frames", "_motion_start_idx", "_motion_lengths", "_motion_loop_modes", "_motion_weights",
+              "_motion_fps", "_motion_dt", "_frame_root_pos", "_frame_contacts", "_motion_frames", "_frame_root_vel"):
+        assert torch.equal(getattr(lib, k), getattr(h, k)), k          # IEEE-only arithmetic: exact
+    assert torch.equal(lib._motion_root_pos_delta, h._motion_root_pos_delta)
+    for k, atol in (("_frame_root_rot", 2e-6), ("_frame_joint_rot", 2e-6), ("_frame_root_ang_vel", 2e-4),
+                    ("_frame_dof_vel", 2e-4)):
+        # velocities = ulp-level quaternion differences x fps (up to 60)
+        assert_close(getattr(lib, k), getattr(h, k), atol=atol, what=k)
+    assert (lib._frame_joint_rot[..., 3] >= 0).all()                    # quat_pos applied
+    # last frame of every clip repeats the previous velocity
+    last = (lib._motion_start_idx + lib._motion_num_frames - 1)
+    assert torch.equal(lib._frame_dof_vel[last], lib._frame_dof_vel[last - 1])
+    assert torch.equal(lib._frame_root_ang_vel[last], lib._frame_root_ang_vel[last - 1])
+    # the rows the kernel wrote are what packing the unpacked views would give
+    from parc_b200 import ops
+    rows2, _ = ops.pack_frames(gpu_model.c_model(), lib._frame_root_pos, lib._frame_root_rot, lib._frame_joint_rot,
+                               lib._frame_contacts, lib._frame_root_vel, lib._frame_root_ang_vel, lib._frame_dof_vel)
+    assert torch.equal(rows2, lib._packed.rows)
+    gen = torch.Generator().manual_seed(8)
+    ids = torch.randint(0, 3, (2000,), generator=gen).cuda()
+    times = (torch.rand(2000, generator=gen) * 9.0 - 0.5).cuda()
+    a, b = lib._calc_frame_blend(ids, times), h._calc_frame_blend(ids, times)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # Query values: the reference's slerp is DISCONTINUOUS at sin(half angle) = 1e-3 (midpoint vs true slerp,
+    # util/torch_util.py:460-466), a jump of up to |t - 0.5| * |q1 - q0| ~ 5e-4; key frames that differ in the last
+    # bit can sit on either side.  So: everything within that jump, and all but a sliver within the normal bar.
+    for name, x, y in zip(FRAME_KEYS, lib.calc_motion_frame(ids, times), h.calc_motion_frame(ids, times)):
+        err = (x.double() - y.double()).abs()
+        assert float(err.max()) < 1e-3, name
+        assert float((err > 2e-4).double().mean()) < 1e-3, name
+
+
+def test_packed_file_round_trip(golden_lib, gpu_model, tmp_path):
+    """save_packed -> init_type="packed_file": identical rows, clip records, terrains and query results; a file
+    packed for another character is refused."""
+    from parc_b200.anim.motion_lib import MotionLib
+    from parc_b200.util.terrain_util import SubTerrain
+    lib = golden_lib
+    t = SubTerrain("t0", 8, 6, 0.4, 0.4, -1.0, 2.0, device="cuda:0")
+    t.hf[...] = torch.rand(8, 6, device="cuda")
+    old_terrains = lib._terrains
+    lib._terrains = [t, None, None]
+    path = str(tmp_path / "lib.parcpack")
+    try:
+        lib.save_packed(path)
+    finally:
+        lib._terrains = old_terrains
+    assert os.path.getsize(path) > lib._packed.rows.numel() * 4
+    back = MotionLib(path, gpu_model, "cuda:0", init_type="packed_file", contact_info=True)
+    assert torch.equal(back._packed.rows, lib._packed.rows) and torch.equal(back._packed.clips, lib._packed.clips)
+    for k in ("_motion_num_frames", "_motion_start_idx", "_motion_lengths", "_motion_loop_modes", "_motion_weights",
+              "_motion_fps", "_motion_dt", "_motion_root_pos_delta", "_frame_root_pos", "_frame_root_rot",
+              "_frame_joint_rot", "_frame_root_vel", "_frame_root_ang_vel", "_frame_dof_vel", "_frame_contacts",
+              "_motion_frames"):
+        assert torch.equal(getattr(back, k), getattr(lib, k)), k
+    assert back._motion_names == lib._motion_names and back.num_motions() == 3
+    assert back._terrains[1] is None and torch.equal(back._terrains[0].hf, t.hf)
+    assert torch.equal(back._terrains[0].min_point, t.min_point) and torch.equal(back._terrains[0].dxdy, t.dxdy)
+    gen = torch.Generator().manual_seed(9)
+    ids = torch.randint(0, 3, (777,), generator=gen).cuda()
+    times = (torch.rand(777, generator=gen) * 9.0).cuda()
+    for x, y in zip(back.calc_motion_frame(ids, times), lib.calc_motion_frame(ids, times)):
+        assert torch.equal(x, y)
+    assert back.sample_motions(5).shape == (5,)
+    # another character model -> refused
+    other = gpu_model.get_copy("cuda:0")
+    other._local_translation[3, 0] += 0.01                       # a limb of different length
+    with pytest.raises(ValueError):
+        MotionLib(path, other, "cuda:0", init_type="packed_file", contact_info=True)
+    # truncated file -> refused
+    data = open(path, "rb").read()
+    bad = str(tmp_path / "short.parcpack")
+    open(bad, "wb").write(data[:len(data) // 2])
+    with pytest.raises(ValueError):
+        MotionLib(bad, gpu_model, "cuda:0", init_type="packed_file", contact_info=True)

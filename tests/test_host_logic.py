@@ -275,3 +275,29 @@ def test_synthetic_generators_are_seeded_and_in_spec(cpu_model):
     s = synth.synth_motion_samples(cpu_model, 2, 10, hf, (0.0, 0.0), (0.4, 0.4))
     assert s["contacts"].min() < 0 or s["contacts"].min() == 0
     assert s["root_pos"].shape == (2, 10, 3) and s["joint_dof"].shape == (2, 10, 28)
+
+
+def test_packed_container_round_trip_and_rejections(tmp_path):
+    """anim/packed_format.py: the .parcpack container (header + 64-byte-aligned raw arrays) without a GPU."""
+    from parc_b200.anim import packed_format as pf
+    rng = np.random.default_rng(0)
+    arrays = {"rows": rng.normal(size=(37, 120)).astype(np.float32), "num_frames": np.array([30, 7], np.int64),
+              "loop_modes": np.array([0, 1], np.int32), "mask": (rng.uniform(size=(5, 3)) < 0.5).astype(np.uint8),
+              "empty": np.zeros((0, 4), np.float32)}
+    meta = {"num_clips": 2, "names": ["a", "b"], "terrains": [None, {"name": "t", "dxdy": [0.4, 0.4]}]}
+    path = str(tmp_path / "x.parcpack")
+    pf.write_container(path, meta, arrays)
+    raw = open(path, "rb").read()
+    assert raw[:8] == pf.MAGIC and not os.path.exists(path + ".tmp")
+    m2, a2 = pf.read_container(path)
+    assert m2 == meta and set(a2) == set(arrays)
+    head = __import__("json").loads(raw[16:16 + int(np.frombuffer(raw[12:16], "<u4")[0])])
+    for k, v in arrays.items():
+        assert a2[k].dtype == v.dtype and a2[k].shape == v.shape and np.array_equal(a2[k], v), k
+        assert head["arrays"][k]["offset"] % 64 == 0
+    for bad, why in ((b"NOTAPACK" + raw[8:], "magic"), (raw[:8] + np.array([99], "<u4").tobytes() + raw[12:], "version"),
+                     (raw[:len(raw) // 2], "truncated"), (raw[:10], "short")):
+        p = str(tmp_path / f"bad_{why}.parcpack")
+        open(p, "wb").write(bad)
+        with pytest.raises(ValueError):
+            pf.read_container(p)
