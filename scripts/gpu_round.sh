@@ -16,6 +16,7 @@ python scripts/bench_loss.py > gpurun_out/bench_loss.log 2>&1; tail -1 gpurun_ou
 python scripts/bench_sweep.py > gpurun_out/bench_sweep.log 2>&1; tail -1 gpurun_out/bench_sweep.log
 python scripts/bench_motion_opt.py > gpurun_out/bench_motion_opt.log 2>&1; tail -1 gpurun_out/bench_motion_opt.log
 python scripts/bench_tracker_step.py > gpurun_out/bench_tracker_step.log 2>&1; tail -1 gpurun_out/bench_tracker_step.log
+python scripts/bench_loader.py > gpurun_out/bench_loader.log 2>&1; tail -1 gpurun_out/bench_loader.log
 CMD3="python scripts/bench_tracker_step.py --steps 3 --no-cpu"
 $CMD3 > gpurun_out/plain4.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}_step.csv $CMD3 > gpurun_out/ncu_list_step.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log
