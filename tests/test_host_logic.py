@@ -301,3 +301,51 @@ def test_packed_container_round_trip_and_rejections(tmp_path):
         open(p, "wb").write(bad)
         with pytest.raises(ValueError):
             pf.read_container(p)
+
+
+def test_step_and_loader_entry_points_reject_bad_arguments(cpu_model):
+    """Argument validation of the §8(f)-3 / §8(f)-4 entry points (no launch happens on any of these paths)."""
+    from parc_b200 import _lib
+    lib = _lib.load()
+    m = cpu_model.c_model()
+    st = _lib.ParcCharState()
+    st.env_stride = 1
+    # empty batches are no-ops even with NULL pointers
+    assert lib.parc_char_obs(C.byref(st), 0, 14, 28, 4, 0, 0, None, 0, None) == 0
+    assert lib.parc_tar_obs(None, None, None, None, None, None, 0, 6, 14, 4, 0, 0, 6, None, 0, None, 0, None) == 0
+    assert lib.parc_char_obs(C.byref(st), 8, 14, 28, 4, 0, 0, None, 0, None) == -1          # NULL state arrays
+    assert lib.parc_char_obs(None, 8, 14, 28, 4, 0, 0, 64, 0, None) == -1
+    assert lib.parc_char_obs(C.byref(st), -1, 14, 28, 4, 0, 0, 64, 0, None) == -2
+    for f in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "key_pos"):
+        setattr(st, f, 4096)
+    assert lib.parc_char_obs(C.byref(st), 8, 14, 28, 4, 0, 0, 4096, 100, None) == -2        # out_stride < row width
+    st.root_rot = 4100
+    assert lib.parc_char_obs(C.byref(st), 8, 14, 28, 4, 0, 0, 4096, 0, None) == -4          # misaligned quaternions
+    st.root_rot, st.env_stride = 4096, 0
+    assert lib.parc_char_obs(C.byref(st), 8, 14, 28, 4, 0, 0, 4096, 0, None) == -2          # env_stride < 1
+    st.env_stride = 1
+    # the reference cannot form the key-body reward term without key bodies; neither can we
+    assert lib.parc_deepmimic_reward(C.byref(st), C.byref(st), 8, 14, 28, 0, 4096, 4096, 1, 1, 4096, None) == -2
+    # targets: the env stride must cover the steps
+    assert lib.parc_tar_obs(4096, 4096, 4096, 4096, 4096, 4096, 8, 6, 14, 4, 0, 0, 5, None, 0, 4096, 0, None) == -2
+    spec = _lib.ParcDoneSpec()
+    assert lib.parc_done(None, 4096, None, 4096, None, None, None, None, None, None, 0, 1, 8, 15, 4096, None, None) == -1
+    assert lib.parc_done(C.byref(spec), 4096, None, 4096, None, None, None, None, None, None, 0, 1, 8, 40, 4096, None, None) == -2
+    spec.enable_early_termination, spec.has_contact_bodies = 1, 1
+    # fall test requested without contact forces / without any height source
+    assert lib.parc_done(C.byref(spec), 4096, None, 4096, None, None, None, None, None, None, 0, 1, 8, 15, 4096, None, None) == -1
+    assert lib.parc_done(C.byref(spec), 4096, None, 4096, None, None, 4096, None, None, None, 0, 1, 8, 15, 4096, None, None) == -1
+    # loader
+    assert lib.parc_build_tables(None, 0, 34, None, None, None, None, None, None, 0, C.byref(m), None, None) == 0
+    assert lib.parc_build_tables(4096, 10, 20, None, 4096, 4096, 4096, 4096, 4096, 1, C.byref(m), 4096, None) == -2   # stride < 6+D
+    assert lib.parc_build_tables(4096, 10, 34, None, 4096, 4096, 4096, 4096, 4096, 1, C.byref(m), None, None) == -1
+    assert lib.parc_build_tables(4096, 10, 34, None, 4096, 4096, 4096, 4096, 4096, 1, C.byref(m), 4100, None) == -4
+    assert lib.parc_build_tables(4096, 10, 34, None, 4096, 4096, 4096, 4096, 4096, 0, C.byref(m), 4096, None) == -2
+    # heightmap observation needs a heading or a root rotation
+    hf = _lib.ParcHeightfield()
+    hf.hf, hf.dim_x, hf.dim_y, hf.dx, hf.dy = 4096, 4, 4, 0.4, 0.4
+    ob = _lib.ParcObsSpec()
+    ob.tmpl_xy, ob.num_points, ob.relative = 4096, 8, 1
+    assert lib.parc_hf_obs(C.byref(hf), C.byref(ob), 4096, 3, None, None, None, 0, 4, 4096, 0, None) == -1
+    assert lib.parc_hf_obs(C.byref(hf), C.byref(ob), 4096, 3, 4096, None, 4096, 2, 4, 4096, 0, None) == -2   # offset needs z
+    assert lib.parc_hf_obs(C.byref(hf), C.byref(ob), 4096, 3, 4096, None, None, 0, 4, 4096, 4, None) == -2    # out_stride < P
