@@ -1245,3 +1245,52 @@ def test_packed_file_round_trip(golden_lib, gpu_model, tmp_path):
     open(bad, "wb").write(data[:len(data) // 2])
     with pytest.raises(ValueError):
         MotionLib(bad, gpu_model, "cuda:0", init_type="packed_file", contact_info=True)
+
+
+def test_frame_index_path_is_bit_exact_over_random_clip_shapes(gpu_model, O, oracle_model, tmp_path):
+    """Indices, blend, lerped root position / contacts and the un-blended velocities are IEEE-only arithmetic and
+    must be bit-identical to the reference's for ANY clip shape: 160 clips with 2..400 frames at 24 / 29.97 / 30 /
+    60 / 120 fps, CLAMP and WRAP, queried at adversarial times (exact key-frame times, clip ends and their float
+    neighbours, negative and multi-cycle times, huge times)."""
+    from parc_b200.anim.motion_lib import MotionLib
+    rng = np.random.default_rng(2024)
+    D = oracle_model.dof_size
+    clips = []
+    for c in range(160):
+        n = int(rng.choice([2, 3, 5, 17, 64, 100, 265, 400])) if c < 40 else int(rng.integers(2, 401))
+        fps = float(rng.choice([24.0, 29.97, 30.0, 60.0, 120.0]))
+        fr = np.zeros((n, 6 + D), np.float32)
+        t = np.arange(n)[:, None] / fps
+        fr[:, 0:3] = np.cumsum(rng.normal(scale=0.03, size=(n, 3)), axis=0) + rng.uniform(-50, 50, 3)
+        fr[:, 3:6] = 0.4 * np.sin(t * rng.uniform(0.5, 2, 3) + rng.uniform(0, 6, 3)) + 0.05
+        fr[:, 6:] = 0.7 * np.sin(t * rng.uniform(0.5, 3, D) + rng.uniform(0, 6, D)) + 0.01
+        ct = (rng.uniform(size=(n, 15)) < 0.4).astype(np.float32)
+        clips.append(O.Clip(fr, ct, fps, O.WRAP if c % 3 == 1 else O.CLAMP, float(rng.uniform(0.1, 2.0))))
+    tb = O.build_tables(oracle_model, clips)
+    lib = MotionLib(write_clip_library(tmp_path, clips), gpu_model, "cuda:0", init_type="motion_file", contact_info=True)
+    assert torch.equal(lib._motion_lengths.cpu(), tb.lengths) and torch.equal(lib._motion_start_idx.cpu(), tb.start_idx)
+    M = len(clips)
+    ids, times = [], []
+    f32 = lambda x: np.float32(x)
+    for c in range(M):
+        n, fps, L = int(tb.num_frames[c]), float(tb.fps[c]), float(tb.lengths[c])
+        ks = rng.integers(0, n, 6)
+        cand = [0.0, L, np.nextafter(f32(L), f32(0)), np.nextafter(f32(L), f32(1e9)), -L, -0.5 * L, 2.0 * L, 7.25 * L,
+                -3.5 * L, 1e6, -1e6, 1e-30, L * 0.5]
+        cand += [k / fps for k in ks] + [float(np.nextafter(f32(k / fps), f32(1e9))) for k in ks]
+        cand += [float(f32(k) * f32(1.0 / fps)) for k in ks] + list(rng.uniform(-2 * L, 3 * L, 20))
+        ids += [c] * len(cand)
+        times += [float(x) for x in cand]
+    ids_t, times_t = torch.tensor(ids, dtype=torch.long), torch.tensor(times, dtype=torch.float32)
+    i0, i1, bl = O.frame_blend(tb, ids_t, times_t)
+    ref = O.calc_motion_frame(tb, ids_t, times_t)
+    g0, g1, gb = lib._calc_frame_blend(ids_t.cuda(), times_t.cuda())
+    assert torch.equal(g0.cpu(), i0) and torch.equal(g1.cpu(), i1) and torch.equal(gb.cpu(), bl)
+    out = lib.calc_motion_frame(ids_t.cuda(), times_t.cuda())
+    for k in (0, 2, 3, 5, 6):                          # root_pos, root_vel, root_ang_vel, dof_vel, contacts
+        assert torch.equal(out[k].cpu(), ref[k]), FRAME_KEYS[k]
+    assert torch.equal(lib.calc_motion_phase(ids_t.cuda(), times_t.cuda()).cpu(), O.motion_phase(tb, ids_t, times_t))
+    assert (bl == 0).any() and (i0 == i1).any() and len(times) > 8000
+    # rotations: slerp value path, 1e-5 (away from the reference's own branch discontinuity, see the loader test)
+    err = (out[4].cpu().double() - ref[4].double()).abs()
+    assert float((err > 2e-5).double().mean()) < 2e-3 and float(err.max()) < 1e-3
