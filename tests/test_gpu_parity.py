@@ -1294,3 +1294,62 @@ def test_frame_index_path_is_bit_exact_over_random_clip_shapes(gpu_model, O, ora
     # rotations: slerp value path, 1e-5 (away from the reference's own branch discontinuity, see the loader test)
     err = (out[4].cpu().double() - ref[4].double()).abs()
     assert float((err > 2e-5).double().mean()) < 2e-3 and float(err.max()) < 1e-3
+
+
+def test_strided_outputs_stay_inside_their_blocks(gpu_model):
+    """Canary test for the row-strided outputs (char_obs / tar_obs / hf_obs write a column block of a wider buffer)
+    and for the loader's row buffer: sentinels around the blocks must survive, the blocks must equal the dense
+    results bit for bit."""
+    import ctypes as C
+    from parc_b200 import _lib, ops
+    g, sim, ref, key_ids = _step_golden()
+    n = sim[0].shape[0]
+    key = _cu(g["body_pos"])[:, key_ids]
+    tar = tuple(_cu(g["tar_" + k]) for k in ("root_pos", "root_rot", "joint_rot", "key_pos"))
+    S = tar[0].shape[1]
+    SENT = 12345.0
+    dense_c = ops.char_obs(*sim, key, False, True)
+    dense_t = ops.tar_obs(sim[0], sim[1], *tar, False, False)
+    hf = torch.rand(30, 20, device="cuda")
+    hfd = ops.HeightfieldDesc(hf=hf, min_x=-3.0, min_y=-2.0, dx=0.4, dy=0.4)
+    tmpl = torch.randn(77, 2, device="cuda")
+    dense_h = ops.hf_obs(hfd, tmpl, sim[0], None, relative=True, root_rot=sim[1])
+    wc, wt, wh = dense_c.shape[1], S * dense_t.shape[2], 77
+    buf = torch.full((n, 5 + wc + 3 + wt + 2 + wh + 4), SENT, device="cuda")
+    c0, t0, h0 = 5, 5 + wc + 3, 5 + wc + 3 + wt + 2
+    ops.char_obs(*sim, key, False, True, out=buf[:, c0:c0 + wc])
+    ops.tar_obs(sim[0], sim[1], *tar, False, False, out=buf[:, t0:t0 + wt])
+    ops.hf_obs(hfd, tmpl, sim[0], None, relative=True, root_rot=sim[1], out=buf[:, h0:h0 + wh])
+    assert torch.equal(buf[:, c0:c0 + wc], dense_c)
+    assert torch.equal(buf[:, t0:t0 + wt], dense_t.view(n, -1))
+    assert torch.equal(buf[:, h0:h0 + wh], dense_h)
+    gaps = torch.cat([buf[:, :c0], buf[:, c0 + wc:t0], buf[:, t0 + wt:h0], buf[:, h0 + wh:]], dim=1)
+    assert (gaps == SENT).all()
+    # zero-copy input views: step 0 / steps 1.. of an [n, S+1, ...] buffer give the same results as dense copies
+    big = {k: torch.cat([torch.full_like(t[:, :1], SENT), t], dim=1) for k, t in
+           zip(("root_pos", "root_rot", "joint_rot"), tar[:3])}
+    body = torch.full((n, S + 1, 15, 3), SENT, device="cuda")
+    body[:, 1:, key_ids] = tar[3]
+    v = ops.tar_obs(sim[0], sim[1], big["root_pos"][:, 1:], big["root_rot"][:, 1:], big["joint_rot"][:, 1:], body[:, 1:],
+                    False, False, key_body_ids=key_ids)
+    assert torch.equal(v, dense_t)
+    # loader: rows_out followed by a canary
+    m = gpu_model.c_model()
+    lay = ops.row_layout(m)
+    civ = golden("clip_civilization.npz")
+    fr = dev(civ["frames"])
+    total = fr.shape[0]
+    raw = torch.full((total * lay.row_floats + 64,), SENT, device="cuda")
+    nf = torch.tensor([total], dtype=torch.long, device="cuda")
+    clip = torch.zeros(total, dtype=torch.int32, device="cuda")
+    start = torch.zeros(1, dtype=torch.long, device="cuda")
+    fps = torch.tensor([30.0], device="cuda")
+    dt = torch.tensor([1.0 / 30.0], device="cuda")
+    rc = _lib.load().parc_build_tables(fr.data_ptr(), total, fr.shape[1], None, clip.data_ptr(), start.data_ptr(),
+                                       nf.data_ptr(), fps.data_ptr(), dt.data_ptr(), 1, C.byref(m), raw.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert (raw[total * lay.row_floats:] == SENT).all() and not (raw[:total * lay.row_floats] == SENT).any()
+    rows, _, _ = ops.build_tables(m, fr, None, nf, fps, dt)
+    assert torch.equal(raw[:total * lay.row_floats].view(total, -1), rows)
