@@ -439,7 +439,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "parc::motion_query_kernel<true>",
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "median_launch_us": statistics.median(per_step_ms) * 1e3}
+                "median_launch_us": statistics.median(per_step_ms) * 1e3,
+                "frac_of_nominal_8TBps": achieved / 8000.0}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

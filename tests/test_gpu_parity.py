@@ -1353,3 +1353,44 @@ def test_strided_outputs_stay_inside_their_blocks(gpu_model):
     assert (raw[total * lay.row_floats:] == SENT).all() and not (raw[:total * lay.row_floats] == SENT).any()
     rows, _, _ = ops.build_tables(m, fr, None, nf, fps, dt)
     assert torch.equal(raw[:total * lay.row_floats].view(total, -1), rows)
+
+
+@pytest.mark.parametrize("loop", ["CLAMP", "WRAP"])
+def test_config0_single_265_frame_clip(gpu_model, O, oracle_model, tmp_path, loop):
+    """BASELINE.json configs[0]: frame query + FK on ONE synthetic 265-frame 34-DoF humanoid clip (SURVEY §8(d)
+    cfg 1): every integer frame through get_motion_frame and 4240 random times through calc_motion_frame, FK on
+    all of them, against the oracle."""
+    from parc_b200.anim.motion_lib import MotionLib
+    from parc_b200.util import synth
+    frames, contacts = synth.synth_clips(gpu_model, 1, seed=1234)
+    assert frames.shape == (1, 265, 34)
+    mode = O.WRAP if loop == "WRAP" else O.CLAMP
+    clips = [O.Clip(frames[0], contacts[0], 30.0, mode, 1.0)]
+    tb = O.build_tables(oracle_model, clips)
+    lib = MotionLib(write_clip_library(tmp_path, clips), gpu_model, "cuda:0", init_type="motion_file", contact_info=True)
+    zeros = torch.zeros(265, dtype=torch.long)
+    fidx = torch.arange(265)
+    got = lib.get_motion_frame(zeros.cuda(), fidx.cuda())
+    want = O.get_motion_frame(tb, zeros, fidx)
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a.cpu(), b), ("get_motion_frame", FRAME_KEYS[k])        # pure gathers
+    gen = torch.Generator().manual_seed(1234)
+    ids = torch.zeros(4240, dtype=torch.long)
+    times = (torch.rand(4240, generator=gen) * 1.4 - 0.2) * tb.lengths[0]
+    out = lib.calc_motion_frame_fk_obs(ids.cuda(), times.cuda())
+    i0, i1, bl = O.frame_blend(tb, ids, times)
+    g0, g1, gb = lib._calc_frame_blend(ids.cuda(), times.cuda())
+    assert torch.equal(g0.cpu(), i0) and torch.equal(g1.cpu(), i1) and torch.equal(gb.cpu(), bl)
+    ref = O.calc_motion_frame(tb, ids, times)
+    for k in (0, 2, 3, 5, 6):
+        assert torch.equal(out[FRAME_KEYS[k]].cpu(), ref[k]), FRAME_KEYS[k]
+    assert_close(out["root_rot"], ref[1], what="root_rot")
+    assert_close(out["joint_rot"], ref[4], what="joint_rot")
+    bp, br = O.forward_kinematics(oracle_model, ref[0], ref[1], ref[4])
+    assert_close(out["body_pos"], bp, atol=2e-6, what="body_pos")
+    assert_close(out["body_rot"], br, what="body_rot")
+    # FK of the integer frames through the stand-alone operator
+    bp2, br2 = gpu_model.forward_kinematics(got[0], got[1], got[4])
+    wp, wr = O.forward_kinematics(oracle_model, want[0], want[1], want[4])
+    assert_close(bp2, wp, atol=2e-6, what="fk body_pos")
+    assert_close(br2, wr, what="fk body_rot")
