@@ -195,6 +195,27 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so the pinned staging buffers of
+    the end-to-end leg are first-touched on the GPU's own NUMA node (one process per GPU: each rank's PCIe traffic
+    then stays on its socket).  Returns a short description for the JSON line; a no-op when NVML or the cpuset
+    does not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 8)
+        local = {w * 64 + b for w, v in enumerate(words) for b in range(64) if (v >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = local & allowed
+        if not use or use == allowed:
+            return f"unchanged ({len(allowed)} cpus allowed, {len(local)} local to the GPU)"
+        os.sched_setaffinity(0, use)
+        return f"{len(use)} of {len(allowed)} cpus (local to GPU {local_rank})"
+    except Exception as e:          # NVML missing, permission, ...
+        return f"unchanged ({type(e).__name__})"
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -206,6 +227,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "unchanged (single process)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -463,7 +485,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "envs_per_gpu": args.envs, "clips": args.clips,
                    "frames_per_clip": 265, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write); "
-                   "frame table 260 MB > L2", "timing": "CUDA events per step on the launch stream, max over ranks"},
+                   "frame table 260 MB > L2", "timing": "CUDA events per step on the launch stream, max over ranks",
+                   "host_cpu_affinity": affinity},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "tracker_step": tracker_step, "l2_warm": l2_warm,
