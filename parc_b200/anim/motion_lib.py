@@ -180,6 +180,14 @@ class MotionLib:
                                    obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out,
                                    time_offsets=time_offsets, root_xy_offset=root_xy_offset)
 
+    def _calc_loop_offset(self, motion_ids, times):
+        """floor(t / len) * root_pos_delta for WRAP clips, zero otherwise (ref :458-475).  Kept for callers that
+        reach for it; `calc_motion_frame` applies the same offset inside its kernel."""
+        wrap = self._motion_loop_modes[motion_ids] == LoopMode.WRAP.value
+        cycles = torch.floor(times / self._motion_lengths[motion_ids]).unsqueeze(-1)
+        off = cycles * self._motion_root_pos_delta[motion_ids]
+        return torch.where(wrap.unsqueeze(-1), off, torch.zeros_like(off))
+
     def joint_rot_to_dof(self, joint_rot):
         return self._kin_char_model.rot_to_dof(joint_rot)
 

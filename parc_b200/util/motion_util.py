@@ -44,3 +44,27 @@ class MotionFrames:
 
     def get_copy(self, new_device=None):
         return self._map(lambda t: t.clone() if new_device is None else t.clone().to(new_device))
+
+
+def cat_motion_frames(motion_frames_list):
+    """Concatenate [B, F_i, ...] MotionFrames along time; a field is kept iff the first element has it.
+    Ref util/motion_util.py:145-193."""
+    first = motion_frames_list[0]
+    assert first.root_pos.dim() == 3
+    return MotionFrames(**{k: (None if getattr(first, k) is None else
+                               torch.cat([getattr(m, k) for m in motion_frames_list], dim=1)) for k in _FIELDS})
+
+
+def motion_frames_from_mlib_format(mlib_motion_frames, char_model, contacts=None):
+    """[..., 6+D] raw frames -> MotionFrames with FK filled in (one launch on CUDA frames: exp-map / DoF
+    conversion + FK fused, csrc/dataset_sweep.cu).  Ref util/motion_util.py:195-222."""
+    root_pos = mlib_motion_frames[..., 0:3]
+    if mlib_motion_frames.is_cuda and not mlib_motion_frames.requires_grad:
+        from .. import ops
+        bp, br, rr, jr = ops.frames_fk(char_model.c_model(), mlib_motion_frames, want_rot=True)
+        return MotionFrames(root_pos=root_pos, root_rot=rr, joint_rot=jr, body_pos=bp, body_rot=br, contacts=contacts)
+    root_rot = torch_util.exp_map_to_quat(mlib_motion_frames[..., 3:6])
+    joint_rot = char_model.dof_to_rot(mlib_motion_frames[..., 6:])
+    body_pos, body_rot = char_model.forward_kinematics(root_pos, root_rot, joint_rot)
+    return MotionFrames(root_pos=root_pos, root_rot=root_rot, joint_rot=joint_rot, body_pos=body_pos, body_rot=body_rot,
+                        contacts=contacts)

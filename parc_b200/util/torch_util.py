@@ -168,3 +168,37 @@ def rotate_2d_vec(vec, angle):
     x, y = vec[..., 0], vec[..., 1]
     c, s = torch.cos(angle), torch.sin(angle)
     return torch.stack([x * c - y * s, x * s + y * c], dim=-1)
+
+
+def quat_to_tan_norm(q):
+    """The 6-number rotation encoding of the policy observations: rotated x axis, then rotated z axis.
+    Ref util/torch_util.py:361-373.  (The step kernels of csrc/tracker_step.cu compute this in place.)"""
+    ex = torch.zeros_like(q[..., 0:3])
+    ex[..., 0] = 1
+    return torch.cat([quat_rotate(q, ex), quat_rotate(q, _z_axis_like(q[..., 0:3]))], dim=-1)
+
+
+def quat_abs(x):
+    """Ref util/torch_util.py:433-436."""
+    return x.norm(p=2, dim=-1)
+
+
+def quat_inv(q):
+    """Conjugate as the inverse of a unit quaternion.  Ref util/torch_util.py:597-607."""
+    return torch.cat([-q[..., 0:3], q[..., 3:4]], dim=-1)
+
+
+def quat_multiply(q1, q2):
+    """Plain 16-multiply Hamilton product q1 * q2 (the reference keeps it beside the 8-multiply `quat_mul`).
+    Ref util/torch_util.py:577-595."""
+    x1, y1, z1, w1 = q1.unbind(-1)
+    x2, y2, z2, w2 = q2.unbind(-1)
+    return torch.stack((w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                        w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2), dim=-1)
+
+
+def heading_to_quat(heading):
+    """Rotation about +z by `heading`.  Ref util/torch_util.py:319-326."""
+    axis = torch.zeros(list(heading.shape) + [3], dtype=torch.float32, device=heading.device)
+    axis[..., 2] = 1
+    return axis_angle_to_quat(axis, heading)

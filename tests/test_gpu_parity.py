@@ -1394,3 +1394,26 @@ def test_config0_single_265_frame_clip(gpu_model, O, oracle_model, tmp_path, loo
     wp, wr = O.forward_kinematics(oracle_model, want[0], want[1], want[4])
     assert_close(bp2, wp, atol=2e-6, what="fk body_pos")
     assert_close(br2, wr, what="fk body_rot")
+
+
+def test_small_api_helpers(golden_lib, gpu_model, O, oracle_model, oracle_tables):
+    """motion_util.motion_frames_from_mlib_format / cat_motion_frames and MotionLib._calc_loop_offset."""
+    from parc_b200.util import motion_util
+    civ = golden("clip_civilization.npz")
+    fr = dev(civ["frames"]).view(2, 127, 34)
+    mf = motion_util.motion_frames_from_mlib_format(fr, gpu_model, contacts=dev(civ["contacts"]).view(2, 127, 15))
+    f_cpu = torch.as_tensor(civ["frames"])
+    rq, jr = O.exp_map_to_quat(f_cpu[:, 3:6]), O.dof_to_rot(oracle_model, f_cpu[:, 6:])
+    bp, br = O.forward_kinematics(oracle_model, f_cpu[:, 0:3], rq, jr)
+    assert mf.root_pos.shape == (2, 127, 3) and mf.joint_rot.shape == (2, 127, 14, 4)
+    assert_close(mf.root_rot.reshape(-1, 4), rq, what="root_rot")
+    assert_close(mf.joint_rot.reshape(-1, 14, 4), jr, what="joint_rot")
+    assert_close(mf.body_pos.reshape(-1, 15, 3), bp, atol=2e-6, what="body_pos")
+    assert_close(mf.body_rot.reshape(-1, 15, 4), br, what="body_rot")
+    both = motion_util.cat_motion_frames([mf.get_slice(slice(0, 100)), mf.get_slice(slice(100, 127))])
+    for k in ("root_pos", "root_rot", "joint_rot", "body_pos", "body_rot", "contacts"):
+        assert torch.equal(getattr(both, k), getattr(mf, k)), k
+    gen = torch.Generator().manual_seed(4)
+    ids = torch.randint(0, 3, (500,), generator=gen)
+    times = (torch.rand(500, generator=gen) * 6 - 2) * oracle_tables.lengths[ids]
+    assert torch.equal(golden_lib._calc_loop_offset(ids.cuda(), times.cuda()).cpu(), O.loop_offset(oracle_tables, ids, times))

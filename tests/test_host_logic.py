@@ -176,6 +176,17 @@ def test_host_quaternion_helpers_match_reference(cpu_model):
     assert torch.equal(cpu_model.rot_to_dof(T(g["joint_rot"])), T(g["dof_back"]))
     og = golden("obs_golden.npz")
     assert torch.equal(torch_util.calc_heading(T(og["root_quat"])), T(og["heading"]))
+    # the encoding the policy observations use, against the reference's compute_char_obs output (global frame:
+    # columns 0:6 are quat_to_tan_norm(root_rot), 12:96 the joints')
+    ts = golden("tracker_step_golden.npz")
+    assert torch.equal(torch_util.quat_to_tan_norm(T(ts["root_rot"])), T(ts["char_obs_g1_h0"])[:, 0:6])
+    assert torch.equal(torch_util.quat_to_tan_norm(T(ts["joint_rot"])).reshape(-1, 84), T(ts["char_obs_g1_h0"])[:, 12:96])
+    q = torch_util.quat_unit(T(ts["root_rot"]))
+    ident = torch_util.quat_multiply(q, torch_util.quat_inv(q))
+    assert torch.allclose(ident, torch.tensor([0.0, 0.0, 0.0, 1.0]).expand_as(ident), atol=1e-6)
+    assert torch.allclose(torch_util.quat_abs(q), torch.ones(q.shape[0]), atol=1e-6)
+    hq = torch_util.heading_to_quat(torch_util.calc_heading(q))
+    assert torch.equal(hq, torch_util.calc_heading_quat(q))
 
 
 # ------------------------------------------------------------------ MotionLib loading
