@@ -49,7 +49,10 @@ class ParcClipMeta(C.Structure):
 
 class ParcMotionTables(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("clips", C.c_void_p), ("total_frames", C.c_int64),
-                ("num_clips", C.c_int64), ("row_floats", C.c_int32), ("reserved", C.c_int32)]
+                ("num_clips", C.c_int64), ("row_floats", C.c_int32), ("reserved", C.c_int32), ("tree", C.c_void_p)]
+
+
+PARC_TREE_BYTES = 880
 
 
 class ParcFrameOut(C.Structure):
@@ -122,6 +125,7 @@ SIGNATURES = {
     "parc_error_string": (C.c_char_p, [C.c_int]),
     "parc_row_layout": (C.c_int, [_P(ParcCharModel), _P(ParcRowLayout)]),
     "parc_validate_model": (C.c_int, [_P(ParcCharModel)]),
+    "parc_tree_from_model": (C.c_int, [_P(ParcCharModel), _V]),
     "parc_pack_frames": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V]),
     "parc_motion_query": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel), _P(ParcFrameOut),
                                     _P(ParcFkOut), _P(ParcHeightfield), _P(ParcObsSpec), _V, _V]),
@@ -183,7 +187,7 @@ def load() -> C.CDLL:
 
 # number of kernel-launching C-ABI calls made by this process (bench.py reports it as gpu_launches)
 LAUNCHES = [0]
-_HOST_ONLY = {"parc_validate_model", "parc_row_layout"}
+_HOST_ONLY = {"parc_validate_model", "parc_row_layout", "parc_tree_from_model"}
 
 
 def check(rc: int, what: str):

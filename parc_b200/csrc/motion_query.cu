@@ -9,6 +9,7 @@
 //
 // Reference semantics: anim/motion_lib.py:80-131, :443-475, :527-538; anim/kin_char_model.py:509-541;
 // envs/ig_parkour/mgdm_dm_util.py:158-179; util/terrain_util.py:113-130.
+#include <cstring>
 #include "parc_common.cuh"
 
 namespace parc {
@@ -101,7 +102,7 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // (A middle point, whole sweep at <= 102 registers, spills and measured slower: profiles/README.md.)
 template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool XYOFF>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
-motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant__ ParcCharModel model_param) {
+motion_query_kernel(const __grid_constant__ QueryParams p) {
   __shared__ TreeSmem sm;
   extern __shared__ float2 s_tmpl[];
   constexpr int GROUPS = 32 / G;
@@ -144,7 +145,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p, const __grid_constant
       }
     }
   }
-  stage_tree(&sm, model_param);
+  stage_tree_global(&sm, p.tb.tree);
   __syncthreads();
 
   const int J = sm.num_bodies;
@@ -503,6 +504,23 @@ extern "C" int parc_validate_model(const ParcCharModel* m) {
   return PARC_OK;
 }
 
+extern "C" int parc_tree_from_model(const ParcCharModel* m, void* tree_host_out) {
+  if (!m || !tree_host_out) return PARC_E_NULL;
+  const int rc = parc_validate_model(m);
+  if (rc) return rc;
+  TreeSmem t;
+  memset(&t, 0, sizeof(t));
+  t.num_bodies = m->num_bodies; t.dof_size = m->dof_size; t.max_depth = m->max_depth;
+  for (int b = 0; b < m->num_bodies; ++b) {
+    t.parent[b] = m->parent[b];
+    t.depth[b] = m->depth[b];
+    for (int k = 0; k < 3; ++k) t.lt[b][k] = m->local_trans[b][k];
+    for (int k = 0; k < 4; ++k) t.lr[b][k] = m->local_rot[b][k];
+  }
+  memcpy(tree_host_out, &t, sizeof(t));
+  return PARC_OK;
+}
+
 extern "C" int parc_row_layout(const ParcCharModel* m, ParcRowLayout* out) {
   if (!m || !out) return PARC_E_NULL;
   const int rc = parc_validate_model(m);
@@ -558,6 +576,8 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   if (rc) return rc;
   if (tables->row_floats != p.lay.row_floats) return PARC_E_LAYOUT;
   if (!aligned16(tables->rows) || !aligned16(tables->clips)) return PARC_E_ALIGN;
+  if (!tables->tree) return PARC_E_NULL;
+  if (!aligned16(tables->tree)) return PARC_E_ALIGN;
   p.tb = *tables;
   p.ids = ids; p.times = times; p.frame_idx = frame_idx; p.n = n;
   p.offsets = offsets; p.num_steps = num_steps;
@@ -605,8 +625,8 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   // large-batch variant (measured: -4 % at 65 536 envs) for callers that never pass one.
 #define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB)                                                        \
   do {                                                                                              \
-    if (B && p.xy_offset) motion_query_kernel<B, GG, NF, RL, MB, B><<<grid, QUERY_CTA_THREADS, smem, st>>>(p, *model); \
-    else motion_query_kernel<B, GG, NF, RL, MB, false><<<grid, QUERY_CTA_THREADS, smem, st>>>(p, *model);              \
+    if (B && p.xy_offset) motion_query_kernel<B, GG, NF, RL, MB, B><<<grid, QUERY_CTA_THREADS, smem, st>>>(p); \
+    else motion_query_kernel<B, GG, NF, RL, MB, false><<<grid, QUERY_CTA_THREADS, smem, st>>>(p);              \
   } while (0)
   if (blend) {
     if (half && one_wave) { if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); }

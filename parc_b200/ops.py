@@ -56,6 +56,14 @@ def row_layout(model: ParcCharModel) -> ParcRowLayout:
     return lay
 
 
+def make_tree(model: ParcCharModel, device) -> torch.Tensor:
+    """The compact kinematic tree the query kernel stages into shared memory, as a device byte tensor
+    (include/parc_b200.h: PARC_TREE_BYTES).  Keeps the 1.4 KB model out of the kernel's parameter block."""
+    host = (C.c_uint8 * _lib.PARC_TREE_BYTES)()
+    check(_lib.load().parc_tree_from_model(C.byref(model), host), "parc_tree_from_model")
+    return torch.frombuffer(bytearray(host), dtype=torch.uint8).to(device)
+
+
 @dataclass
 class PackedTables:
     """Device-resident packed frame rows + clip metadata (include/parc_b200.h: ParcMotionTables)."""
@@ -64,14 +72,18 @@ class PackedTables:
     total_frames: int
     num_clips: int
     layout: ParcRowLayout
+    tree: Optional[torch.Tensor] = None     # uint8 [PARC_TREE_BYTES], made on first use from the model
 
-    def c_struct(self) -> ParcMotionTables:
+    def c_struct(self, model: Optional[ParcCharModel] = None) -> ParcMotionTables:
+        if self.tree is None and model is not None:
+            self.tree = make_tree(model, self.rows.device)
         t = ParcMotionTables()
         t.rows = self.rows.data_ptr()
         t.clips = self.clips.data_ptr()
         t.total_frames = self.total_frames
         t.num_clips = self.num_clips
         t.row_floats = self.layout.row_floats
+        t.tree = ptr(self.tree)
         return t
 
 
@@ -217,7 +229,7 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
     if want_fk:
         fk.body_pos = buf("body_pos", (N, J, 3)).data_ptr()
         fk.body_rot = buf("body_rot", (N, J, 4)).data_ptr()
-    tb = tables.c_struct()
+    tb = tables.c_struct(model)
     lib = _lib.load()
     with torch.cuda.device(dev):
         if motion_times is not None:
@@ -284,7 +296,7 @@ class MotionQueryPlan:
         if want_fk:
             self._fk.body_pos = buf("body_pos", (N, J, 3)).data_ptr()
             self._fk.body_rot = buf("body_rot", (N, J, 4)).data_ptr()
-        self._tb = tables.c_struct()
+        self._tb = tables.c_struct(model)
         self._hf = self._obs = None
         self._obs_ptr = None
         if obs_tmpl is not None:

@@ -40,7 +40,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.ParcClipMeta) == 32
     assert C.sizeof(_lib.ParcRowLayout) == 32
     assert C.sizeof(_lib.ParcCharModel) == 16 + 4 * 24 * 4 + 24 * (3 + 4 + 3) * 4
-    assert C.sizeof(_lib.ParcMotionTables) == 40 and C.sizeof(_lib.ParcFrameOut) == 80
+    assert C.sizeof(_lib.ParcMotionTables) == 48 and C.sizeof(_lib.ParcFrameOut) == 80
     assert C.sizeof(_lib.ParcHeightfield) == 32 and C.sizeof(_lib.ParcTerrainBatch) == 80
 
 
@@ -80,7 +80,7 @@ def test_argument_errors_are_returned_not_thrown(cpu_model):
     m = cpu_model.c_model()
     assert lib.parc_motion_query(None, None, None, 0, C.byref(m), None, None, None, None, None, None) == -1
     tb = _lib.ParcMotionTables()
-    tb.rows, tb.clips, tb.total_frames, tb.num_clips, tb.row_floats = 256, 512, 10, 1, 120
+    tb.rows, tb.clips, tb.total_frames, tb.num_clips, tb.row_floats, tb.tree = 256, 512, 10, 1, 120, 1024
     fo = _lib.ParcFrameOut()
     assert lib.parc_motion_query(C.byref(tb), 64, 64, -5, C.byref(m), C.byref(fo), None, None, None, None, None) == -2
     tb.row_floats = 116
@@ -91,8 +91,17 @@ def test_argument_errors_are_returned_not_thrown(cpu_model):
     assert lib.parc_hf_sample(None, None, 4, None, None, None) == -1
     assert lib.parc_points_hf_sdf(None, 1, 1, None, 1, None, None, None) == -1
     assert lib.parc_exp_map_to_quat_fwd(64, -1, 64, None) == -2
+    tb.rows, tb.tree = 256, None                     # the device-resident tree is required
+    assert lib.parc_motion_query(C.byref(tb), 64, 64, 0, C.byref(m), C.byref(fo), None, None, None, None, None) == -1
+    tb.tree = 1028
+    assert lib.parc_motion_query(C.byref(tb), 64, 64, 0, C.byref(m), C.byref(fo), None, None, None, None, None) == -4
+    host_tree = (C.c_uint8 * _lib.PARC_TREE_BYTES)()
+    assert lib.parc_tree_from_model(C.byref(m), host_tree) == 0 and lib.parc_tree_from_model(C.byref(m), None) == -1
+    words = np.frombuffer(bytes(host_tree), np.int32)
+    assert words[0] == m.num_bodies and words[1] == m.dof_size and words[2] == m.max_depth
+    assert list(words[4:4 + m.num_bodies]) == list(m.parent)[:m.num_bodies]
     # n == 0 is a valid no-op
-    tb.rows = 256
+    tb.rows, tb.tree = 256, 1024
     assert lib.parc_motion_query(C.byref(tb), 64, 64, 0, C.byref(m), C.byref(fo), None, None, None, None, None) == 0
 
 
