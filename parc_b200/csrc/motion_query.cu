@@ -613,7 +613,11 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   const int64_t warps = half ? (n + 1) / 2 : n;
   const bool one_wave = warps <= (int64_t)sms * 16;           // 8 CTAs x 2 warps resident per SM
   const int grid = query_grid(warps, sms);
-  const int inflight = half ? (one_wave ? 28 : 14) : 14;
+  // Regimes (measured on B200): one resident wave -> the whole 28-deep sweep in flight at <= 128 registers;
+  // beyond it occupancy wins: 7 gathers in flight at 64 registers / 16 CTAs per SM beat 14 in flight at 80
+  // registers / 12 CTAs (65 536 envs: 87.3 -> 85.2 us; the 7-step tracker form: 396 -> 337 us), while 4 in
+  // flight (88.5 us) and 48 registers / 20 CTAs (97.7 us, spills) lose again.
+  const int inflight = half ? (one_wave ? 28 : 7) : 14;
   size_t smem = 0;
   if (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) {
     const int sweep = (half ? 16 : 32) * inflight;
@@ -630,7 +634,7 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   } while (0)
   if (blend) {
     if (half && one_wave) { if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); }
-    else if (half) { if (rel) PARC_LAUNCH_QUERY(true, 16, 14, true, 12); else PARC_LAUNCH_QUERY(true, 16, 14, false, 12); }
+    else if (half) { if (rel) PARC_LAUNCH_QUERY(true, 16, 7, true, 16); else PARC_LAUNCH_QUERY(true, 16, 7, false, 16); }
     else { if (rel) PARC_LAUNCH_QUERY(true, 32, 14, true, 8); else PARC_LAUNCH_QUERY(true, 32, 14, false, 8); }
   } else {
     if (half) PARC_LAUNCH_QUERY(false, 16, 14, false, 12); else PARC_LAUNCH_QUERY(false, 32, 14, false, 8);
