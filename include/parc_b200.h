@@ -423,6 +423,48 @@ int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot
               int32_t offset_stride, int32_t tar_env_stride, int64_t n, int32_t num_bodies, int32_t* done_out,
               float* term_heights_out, void* stream);
 
+/* The simulated character's whole share of a control step in ONE launch: DoF -> joint rotations (never leaving
+ * registers), compute_char_obs, compute_deepmimic_reward, compute_done with the termination-height lookup, and
+ * the two contact-flag blocks of the policy-observation row.  Same device code as parc_dof_to_rot_fwd +
+ * parc_char_obs + parc_deepmimic_reward + parc_done; flags identical, values to fp32 rounding.
+ * sim.joint_rot is ignored (dof_pos is converted); sim.key_pos / ref.key_pos follow ParcCharState's rules.
+ * ref is the reference frame the character tracks (typically step 0 of parc_motion_query_steps' output:
+ * env_stride = number of steps); ref_body_pos [rows, J, 3] over the same rows feeds the pose-termination test.
+ * Heights for the fall test are sampled from hf at body xy + env_offsets[:, 0:2].
+ * tar_contacts (step 1 of a [n, tar_env_stride, J] array) / char_contacts [n,J] are copied into
+ * tar_contacts_out / char_contacts_out when those are non-NULL; all three observation outputs share obs_stride
+ * (floats between consecutive envs), i.e. they are column blocks of one policy-observation buffer. */
+typedef struct ParcSimStep {
+  ParcCharState sim;
+  ParcCharState ref;
+  const float* dof_pos;            /* [n, D] */
+  const float* body_pos;           /* [n, J, 3] simulated body positions */
+  const float* ref_body_pos;       /* [rows, J, 3], row e * ref.env_stride */
+  const float* contact_force;      /* [n, J, 3] (NULL unless the fall test is enabled) */
+  const float* time;               /* [n] */
+  const float* env_offsets;        /* [n, offset_stride] or NULL */
+  const float* joint_rot_err_w;    /* [J-1] */
+  const float* dof_err_w;          /* [D] */
+  const float* tar_contacts;
+  const float* char_contacts;
+  ParcDoneSpec done;
+  ParcHeightfield hf;
+  int32_t offset_stride;
+  int32_t tar_env_stride;
+  int32_t num_tar_steps;
+  int32_t num_keys;
+  int32_t global_obs, root_height_obs, track_root_h, track_root;
+  float* joint_rot_out;            /* [n, J-1, 4] or NULL */
+  float* char_obs_out;
+  float* tar_contacts_out;         /* or NULL */
+  float* char_contacts_out;        /* or NULL */
+  float* reward_out;               /* [n, 5] */
+  int32_t* done_out;               /* [n] */
+  int64_t obs_stride;
+} ParcSimStep;
+
+int parc_sim_step(const ParcSimStep* args, int64_t n, const ParcCharModel* model, void* stream);
+
 /* ---- f4: GPU loader -----------------------------------------------------------------
  * Raw clip frames -> packed frame rows, every frame of every clip in one launch: what MotionLib._load_motions /
  * _load_motion_frames do per clip on the host (anim/motion_lib.py:137-202, :204-380 -- extract_frame_data with

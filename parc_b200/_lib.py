@@ -115,6 +115,19 @@ class ParcDoneSpec(C.Structure):
                 ("enable_early_termination", C.c_int32), ("track_root", C.c_int32)]
 
 
+class ParcSimStep(C.Structure):
+    _fields_ = [("sim", ParcCharState), ("ref", ParcCharState), ("dof_pos", C.c_void_p), ("body_pos", C.c_void_p),
+                ("ref_body_pos", C.c_void_p), ("contact_force", C.c_void_p), ("time", C.c_void_p),
+                ("env_offsets", C.c_void_p), ("joint_rot_err_w", C.c_void_p), ("dof_err_w", C.c_void_p),
+                ("tar_contacts", C.c_void_p), ("char_contacts", C.c_void_p), ("done", ParcDoneSpec),
+                ("hf", ParcHeightfield), ("offset_stride", C.c_int32), ("tar_env_stride", C.c_int32),
+                ("num_tar_steps", C.c_int32), ("num_keys", C.c_int32), ("global_obs", C.c_int32),
+                ("root_height_obs", C.c_int32), ("track_root_h", C.c_int32), ("track_root", C.c_int32),
+                ("joint_rot_out", C.c_void_p), ("char_obs_out", C.c_void_p), ("tar_contacts_out", C.c_void_p),
+                ("char_contacts_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p),
+                ("obs_stride", C.c_int64)]
+
+
 PARC_DONE_NULL, PARC_DONE_FAIL, PARC_DONE_SUCC, PARC_DONE_TIME = 0, 1, 2, 3
 
 # name -> (restype, argtypes); every symbol include/parc_b200.h declares
@@ -156,6 +169,7 @@ SIGNATURES = {
                                _V]),
     "parc_deepmimic_reward": (C.c_int, [_P(ParcCharState), _P(ParcCharState), _I64, _I32, _I32, _I32, _V, _V, _I32,
                                         _I32, _V, _V]),
+    "parc_sim_step": (C.c_int, [_P(ParcSimStep), _I64, _P(ParcCharModel), _V]),
     "parc_done": (C.c_int, [_P(ParcDoneSpec), _V, _V, _V, _V, _V, _V, _V, _P(ParcHeightfield), _V, _I32, _I32, _I64,
                             _I32, _V, _V, _V]),
 }

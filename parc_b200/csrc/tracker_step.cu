@@ -69,41 +69,52 @@ __device__ __forceinline__ float sq3(const float3& d) { return d.x * d.x + d.y *
 // ------------------------------------------------------------------------------------------------
 // compute_char_obs: [root_h] | root tan-norm 6 | root_vel 3 | root_ang_vel 3 | joint tan-norm 6(J-1) | dof_vel D | key 3K
 // ------------------------------------------------------------------------------------------------
+// One env's observation row; the calling warp's lanes cooperate.  JR_IN_LANE: lane j already holds joint j's
+// rotation in `my_jr` (the fused step kernel converts the DoFs in registers); otherwise it is read from s.joint_rot.
+template <bool JR_IN_LANE>
+__device__ __forceinline__ void char_obs_env(const ParcCharState& s, int64_t e, int Jm1, int D, int K, int global_obs,
+                                             int root_height_obs, float* __restrict__ o, int lane, const float4& my_jr) {
+  const int64_t r = e * s.env_stride;
+  const float3 rp = ld3(s.root_pos + r * 3);
+  const float4 rr = ld4(s.root_rot + r * 4);
+  const float4 hinv = heading_inverse_quat(rr);
+  if (root_height_obs) {
+    if (lane == 0) o[0] = rp.z;
+    o += 1;
+  }
+  if (lane == 0) {
+    store_tan_norm(o, global_obs ? rr : quat_mul(hinv, rr));
+  } else if (lane == 1) {
+    const float3 v = ld3(s.root_vel + r * 3);
+    st3(o + 6, global_obs ? v : quat_rotate(hinv, v));
+  } else if (lane == 2) {
+    const float3 v = ld3(s.root_ang_vel + r * 3);
+    st3(o + 9, global_obs ? v : quat_rotate(hinv, v));
+  }
+  if (JR_IN_LANE) {
+    if (lane < Jm1) store_tan_norm(o + 12 + 6 * lane, my_jr);
+  } else {
+    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 12 + 6 * j, ld4(s.joint_rot + (r * Jm1 + j) * 4));
+  }
+  float* __restrict__ ov = o + 12 + 6 * Jm1;
+  for (int d = lane; d < D; d += 32) ov[d] = __ldg(s.dof_vel + r * D + d);
+  float* __restrict__ ok = ov + D;
+  for (int k = lane; k < K; k += 32) {
+    float3 p = sub3(key_position(s.key_pos, s.key_body_ids, s.num_bodies, K, e, r, k), rp);
+    if (!global_obs) p = quat_rotate(hinv, p);
+    st3(ok + 3 * k, p);
+  }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS)
 char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int D, int K, int global_obs,
                 int root_height_obs, float* __restrict__ out, int64_t W) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
-  for (int64_t e = warp0; e < n; e += nwarps) {
-    float* __restrict__ o = out + e * W;
-    const int64_t r = e * s.env_stride;
-    const float3 rp = ld3(s.root_pos + r * 3);
-    const float4 rr = ld4(s.root_rot + r * 4);
-    const float4 hinv = heading_inverse_quat(rr);
-    if (root_height_obs) {
-      if (lane == 0) o[0] = rp.z;
-      o += 1;
-    }
-    if (lane == 0) {
-      store_tan_norm(o, global_obs ? rr : quat_mul(hinv, rr));
-    } else if (lane == 1) {
-      const float3 v = ld3(s.root_vel + r * 3);
-      st3(o + 6, global_obs ? v : quat_rotate(hinv, v));
-    } else if (lane == 2) {
-      const float3 v = ld3(s.root_ang_vel + r * 3);
-      st3(o + 9, global_obs ? v : quat_rotate(hinv, v));
-    }
-    for (int j = lane; j < Jm1; j += 32) store_tan_norm(o + 12 + 6 * j, ld4(s.joint_rot + (r * Jm1 + j) * 4));
-    float* __restrict__ ov = o + 12 + 6 * Jm1;
-    for (int d = lane; d < D; d += 32) ov[d] = __ldg(s.dof_vel + r * D + d);
-    float* __restrict__ ok = ov + D;
-    for (int k = lane; k < K; k += 32) {
-      float3 p = sub3(key_position(s.key_pos, s.key_body_ids, s.num_bodies, K, e, r, k), rp);
-      if (!global_obs) p = quat_rotate(hinv, p);
-      st3(ok + 3 * k, p);
-    }
-  }
+  const float4 none = make_float4(0.f, 0.f, 0.f, 1.f);
+  for (int64_t e = warp0; e < n; e += nwarps)
+    char_obs_env<false>(s, e, Jm1, D, K, global_obs, root_height_obs, out + e * W, lane, none);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,6 +173,63 @@ tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // compute_deepmimic_reward: [n,5] = exp(-scale * err) for pose, vel, root pose, root vel, key pos
 // ------------------------------------------------------------------------------------------------
+template <bool JR_IN_LANE>
+__device__ __forceinline__ void reward_env(const ParcCharState& s, const ParcCharState& t, int64_t e, int Jm1, int D, int K,
+                                           const float* __restrict__ joint_w, const float* __restrict__ dof_w,
+                                           int track_root_h, int track_root, float* __restrict__ o, int lane,
+                                           const float4& my_jr) {
+  float pose = 0.0f, vel = 0.0f, key = 0.0f;
+  const int64_t rs = e * s.env_stride, rt = e * t.env_stride;
+  if (JR_IN_LANE) {
+    if (lane < Jm1) {
+      const float a = quat_diff_angle(my_jr, ld4(t.joint_rot + (rt * Jm1 + lane) * 4));
+      pose = __ldg(joint_w + lane) * a * a;
+    }
+  } else {
+    for (int j = lane; j < Jm1; j += 32) {
+      const float a = quat_diff_angle(ld4(s.joint_rot + (rs * Jm1 + j) * 4), ld4(t.joint_rot + (rt * Jm1 + j) * 4));
+      pose += __ldg(joint_w + j) * a * a;
+    }
+  }
+  for (int d = lane; d < D; d += 32) {
+    const float dv = __ldg(t.dof_vel + rt * D + d) - __ldg(s.dof_vel + rs * D + d);
+    vel += __ldg(dof_w + d) * dv * dv;
+  }
+  const float3 rp = ld3(s.root_pos + rs * 3), trp = ld3(t.root_pos + rt * 3);
+  float4 rr = ld4(s.root_rot + rs * 4), trr = ld4(t.root_rot + rt * 4);
+  float3 rv = ld3(s.root_vel + rs * 3), trv = ld3(t.root_vel + rt * 3);
+  float3 rw = ld3(s.root_ang_vel + rs * 3), trw = ld3(t.root_ang_vel + rt * 3);
+  float3 dp = sub3(trp, rp);
+  if (!track_root) dp.x = dp.y = 0.0f;
+  if (!track_root_h) dp.z = 0.0f;
+  float4 hs = make_float4(0.f, 0.f, 0.f, 1.f), ht = hs;
+  if (!track_root) {                                 // convert_to_local: each side in its OWN heading frame
+    hs = heading_inverse_quat(rr);
+    ht = heading_inverse_quat(trr);
+    rv = quat_rotate(hs, rv); rw = quat_rotate(hs, rw); rr = quat_mul(hs, rr);
+    trv = quat_rotate(ht, trv); trw = quat_rotate(ht, trw); trr = quat_mul(ht, trr);
+  }
+  for (int k = lane; k < K; k += 32) {
+    float3 a = sub3(key_position(s.key_pos, s.key_body_ids, s.num_bodies, K, e, rs, k), rp);
+    float3 b = sub3(key_position(t.key_pos, t.key_body_ids, t.num_bodies, K, e, rt, k), trp);
+    if (!track_root) { a = quat_rotate(hs, a); b = quat_rotate(ht, b); }
+    key += sq3(sub3(b, a));
+  }
+  pose = warp_sum(pose);
+  vel = warp_sum(vel);
+  key = warp_sum(key);
+  if (lane == 0) {
+    const float ra = quat_diff_angle(rr, trr);
+    const float root_pose = sq3(dp) + 0.1f * (ra * ra);
+    const float root_vel = sq3(sub3(trv, rv)) + 0.1f * sq3(sub3(trw, rw));
+    o[0] = expf(-0.25f * pose);
+    o[1] = expf(-0.01f * vel);
+    o[2] = expf(-5.0f * root_pose);
+    o[3] = expf(-1.0f * root_vel);
+    o[4] = expf(-10.0f * key);
+  }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS)
 deepmimic_reward_kernel(const __grid_constant__ ParcCharState s, const __grid_constant__ ParcCharState t, int64_t n,
                         int Jm1, int D, int K, const float* __restrict__ joint_w, const float* __restrict__ dof_w,
@@ -169,52 +237,9 @@ deepmimic_reward_kernel(const __grid_constant__ ParcCharState s, const __grid_co
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
-  for (int64_t e = warp0; e < n; e += nwarps) {
-    float pose = 0.0f, vel = 0.0f, key = 0.0f;
-    const int64_t rs = e * s.env_stride, rt = e * t.env_stride;
-    for (int j = lane; j < Jm1; j += 32) {
-      const float a = quat_diff_angle(ld4(s.joint_rot + (rs * Jm1 + j) * 4), ld4(t.joint_rot + (rt * Jm1 + j) * 4));
-      pose += __ldg(joint_w + j) * a * a;
-    }
-    for (int d = lane; d < D; d += 32) {
-      const float dv = __ldg(t.dof_vel + rt * D + d) - __ldg(s.dof_vel + rs * D + d);
-      vel += __ldg(dof_w + d) * dv * dv;
-    }
-    const float3 rp = ld3(s.root_pos + rs * 3), trp = ld3(t.root_pos + rt * 3);
-    float4 rr = ld4(s.root_rot + rs * 4), trr = ld4(t.root_rot + rt * 4);
-    float3 rv = ld3(s.root_vel + rs * 3), trv = ld3(t.root_vel + rt * 3);
-    float3 rw = ld3(s.root_ang_vel + rs * 3), trw = ld3(t.root_ang_vel + rt * 3);
-    float3 dp = sub3(trp, rp);
-    if (!track_root) dp.x = dp.y = 0.0f;
-    if (!track_root_h) dp.z = 0.0f;
-    float4 hs = make_float4(0.f, 0.f, 0.f, 1.f), ht = hs;
-    if (!track_root) {                                 // convert_to_local: each side in its OWN heading frame
-      hs = heading_inverse_quat(rr);
-      ht = heading_inverse_quat(trr);
-      rv = quat_rotate(hs, rv); rw = quat_rotate(hs, rw); rr = quat_mul(hs, rr);
-      trv = quat_rotate(ht, trv); trw = quat_rotate(ht, trw); trr = quat_mul(ht, trr);
-    }
-    for (int k = lane; k < K; k += 32) {
-      float3 a = sub3(key_position(s.key_pos, s.key_body_ids, s.num_bodies, K, e, rs, k), rp);
-      float3 b = sub3(key_position(t.key_pos, t.key_body_ids, t.num_bodies, K, e, rt, k), trp);
-      if (!track_root) { a = quat_rotate(hs, a); b = quat_rotate(ht, b); }
-      key += sq3(sub3(b, a));
-    }
-    pose = warp_sum(pose);
-    vel = warp_sum(vel);
-    key = warp_sum(key);
-    if (lane == 0) {
-      const float ra = quat_diff_angle(rr, trr);
-      const float root_pose = sq3(dp) + 0.1f * (ra * ra);
-      const float root_vel = sq3(sub3(trv, rv)) + 0.1f * sq3(sub3(trw, rw));
-      float* __restrict__ o = out + e * 5;
-      o[0] = expf(-0.25f * pose);
-      o[1] = expf(-0.01f * vel);
-      o[2] = expf(-5.0f * root_pose);
-      o[3] = expf(-1.0f * root_vel);
-      o[4] = expf(-10.0f * key);
-    }
-  }
+  const float4 none = make_float4(0.f, 0.f, 0.f, 1.f);
+  for (int64_t e = warp0; e < n; e += nwarps)
+    reward_env<false>(s, t, e, Jm1, D, K, joint_w, dof_w, track_root_h, track_root, out + e * 5, lane, none);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -240,72 +265,133 @@ struct DoneParams {
   int tar_env_stride;
 };
 
+__device__ __forceinline__ void done_env(const DoneParams& p, int64_t e, int32_t* __restrict__ done,
+                                         float* __restrict__ term_heights_out, int lane) {
+  const int J = p.J;
+  const float tm = __ldg(p.time + e);
+  int flag = PARC_DONE_NULL;
+  if (tm >= p.ep_len) flag = PARC_DONE_TIME;
+  const bool body = lane < J;
+  float3 bp = make_float3(0.f, 0.f, 0.f);
+  if (body) bp = ld3(p.body_pos + (e * J + lane) * 3);
+  float th = 0.0f;
+  const bool need_heights = (p.early_termination && p.has_contact_bodies) || term_heights_out;
+  if (body && need_heights) {
+    if (p.term_heights) {
+      th = __ldg(p.term_heights + e * J + lane);
+    } else {
+      float gx = bp.x, gy = bp.y;
+      if (p.env_offsets) {
+        gx = add_rn(gx, __ldg(p.env_offsets + e * p.offset_stride));
+        gy = add_rn(gy, __ldg(p.env_offsets + e * p.offset_stride + 1));
+      }
+      th = add_rn(hf_lookup(p.hf, gx, gy), p.termination_height);
+    }
+    if (term_heights_out) term_heights_out[e * J + lane] = th;
+  }
+  if (p.early_termination) {
+    bool failed = false;
+    if (p.has_contact_bodies) {
+      const bool counted = body && !((p.contact_body_mask >> lane) & 1u);
+      bool touched = false;
+      if (counted) {
+        const float3 f = ld3(p.contact_force + (e * J + lane) * 3);
+        touched = fabsf(f.x) > p.force_eps || fabsf(f.y) > p.force_eps || fabsf(f.z) > p.force_eps;
+      }
+      const bool low = counted && bp.z < th;
+      const bool any_touch = __any_sync(PARC_FULL_MASK, touched);
+      const bool any_low = __any_sync(PARC_FULL_MASK, low);
+      failed = any_touch && any_low;
+    }
+    if (p.pose_termination) {
+      float3 tb = make_float3(0.f, 0.f, 0.f);
+      if (body) tb = ld3(p.tar_body_pos + (e * p.tar_env_stride * J + lane) * 3);
+      const float3 r0 = shfl3(bp, 0), t0 = shfl3(tb, 0);
+      bool bad = false;
+      if (body && lane > 0) {
+        const float dx = sub_rn(sub_rn(tb.x, t0.x), sub_rn(bp.x, r0.x));
+        const float dy = sub_rn(sub_rn(tb.y, t0.y), sub_rn(bp.y, r0.y));
+        const float dz = sub_rn(sub_rn(tb.z, t0.z), sub_rn(bp.z, r0.z));
+        const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+        const float lim = __ldg(p.pose_dist + lane - 1);
+        bad = d2 > mul_rn(lim, lim);
+      } else if (lane == 0 && p.track_root) {
+        const float dx = sub_rn(bp.x, tb.x), dy = sub_rn(bp.y, tb.y), dz = sub_rn(bp.z, tb.z);
+        const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+        const float ang = quat_diff_angle(ld4(p.root_rot + e * 4), ld4(p.tar_root_rot + e * p.tar_env_stride * 4));
+        bad = d2 > p.root_pos_dist_sq || fabsf(ang) > p.root_rot_angle;
+      }
+      failed = failed || __any_sync(PARC_FULL_MASK, bad);
+    }
+    if (failed && tm > p.first_step_eps) flag = PARC_DONE_FAIL;
+  }
+  if (lane == 0 && done) done[e] = flag;
+}
+
 __global__ void __launch_bounds__(STEP_THREADS)
 done_kernel(const __grid_constant__ DoneParams p, int64_t n, int32_t* __restrict__ done,
             float* __restrict__ term_heights_out) {
   const int lane = threadIdx.x & 31;
-  const int J = p.J;
+  const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
+  for (int64_t e = warp0; e < n; e += nwarps) done_env(p, e, done, term_heights_out, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The simulated character's whole step in ONE launch: DoF -> joint rotations (kept in registers, lane = joint),
+// the character observation block, the reward terms, the episode flag and the two contact-flag blocks of the
+// policy-observation row.  Same device code as the stand-alone kernels above.
+// ------------------------------------------------------------------------------------------------
+struct SimStepParams {
+  ParcCharState sim;              // joint_rot unused (converted from dof_pos); key_pos = body positions if key ids set
+  ParcCharState ref;              // reference frame (step 0 of the query output, env_stride = S + 1)
+  const float* dof_pos;           // [n, D]
+  const float* joint_w;
+  const float* dof_w;
+  const float* tar_contacts;      // [n, tar_env_stride, J] at step 1, or nullptr
+  const float* char_contacts;     // [n, J] or nullptr
+  float* joint_rot_out;           // [n, J-1, 4] or nullptr
+  float* char_obs_out;            // row stride obs_stride
+  float* tar_contacts_out;        // row stride obs_stride, S*J floats per env, or nullptr
+  float* char_contacts_out;       // row stride obs_stride, J floats per env, or nullptr
+  float* reward_out;              // [n, 5]
+  int32_t* done_out;              // [n]
+  int64_t obs_stride;
+  int tar_env_stride, num_tar_steps;
+  int K, global_obs, root_height_obs, track_root_h, track_root;
+  DoneParams done;
+};
+
+__global__ void __launch_bounds__(STEP_THREADS)
+sim_step_kernel(const __grid_constant__ SimStepParams p, const __grid_constant__ ParcCharModel model_param, int64_t n) {
+  __shared__ ParcCharModel sm;
+  stage_model(&sm, model_param);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int J = sm.num_bodies, Jm1 = J - 1, D = sm.dof_size;
+  // lane j (< J-1) owns joint j + 1
+  int jt = PARC_JOINT_FIXED, didx = 0;
+  const float* axis = sm.joint_axis[0];
+  if (lane < Jm1) { jt = sm.joint_type[lane + 1]; didx = sm.dof_idx[lane + 1]; axis = sm.joint_axis[lane + 1]; }
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
-    const float tm = __ldg(p.time + e);
-    int flag = PARC_DONE_NULL;
-    if (tm >= p.ep_len) flag = PARC_DONE_TIME;
-    const bool body = lane < J;
-    float3 bp = make_float3(0.f, 0.f, 0.f);
-    if (body) bp = ld3(p.body_pos + (e * J + lane) * 3);
-    float th = 0.0f;
-    const bool need_heights = (p.early_termination && p.has_contact_bodies) || term_heights_out;
-    if (body && need_heights) {
-      if (p.term_heights) {
-        th = __ldg(p.term_heights + e * J + lane);
-      } else {
-        float gx = bp.x, gy = bp.y;
-        if (p.env_offsets) {
-          gx = add_rn(gx, __ldg(p.env_offsets + e * p.offset_stride));
-          gy = add_rn(gy, __ldg(p.env_offsets + e * p.offset_stride + 1));
-        }
-        th = add_rn(hf_lookup(p.hf, gx, gy), p.termination_height);
-      }
-      if (term_heights_out) term_heights_out[e * J + lane] = th;
+    float dd[3] = {0.f, 0.f, 0.f};
+    const float* d = p.dof_pos + e * D + didx;
+    if (jt == PARC_JOINT_HINGE) dd[0] = __ldg(d);
+    else if (jt == PARC_JOINT_SPHERICAL) { dd[0] = __ldg(d); dd[1] = __ldg(d + 1); dd[2] = __ldg(d + 2); }
+    const float4 jr = joint_dof_to_quat(jt, dd, axis);
+    if (p.joint_rot_out && lane < Jm1) reinterpret_cast<float4*>(p.joint_rot_out)[e * Jm1 + lane] = jr;
+    char_obs_env<true>(p.sim, e, Jm1, D, p.K, p.global_obs, p.root_height_obs, p.char_obs_out + e * p.obs_stride, lane, jr);
+    if (p.tar_contacts_out) {
+      const float* __restrict__ src = p.tar_contacts + e * p.tar_env_stride * J;
+      float* __restrict__ dst = p.tar_contacts_out + e * p.obs_stride;
+      for (int i = lane; i < p.num_tar_steps * J; i += 32) dst[i] = __ldg(src + i);
     }
-    if (p.early_termination) {
-      bool failed = false;
-      if (p.has_contact_bodies) {
-        const bool counted = body && !((p.contact_body_mask >> lane) & 1u);
-        bool touched = false;
-        if (counted) {
-          const float3 f = ld3(p.contact_force + (e * J + lane) * 3);
-          touched = fabsf(f.x) > p.force_eps || fabsf(f.y) > p.force_eps || fabsf(f.z) > p.force_eps;
-        }
-        const bool low = counted && bp.z < th;
-        const bool any_touch = __any_sync(PARC_FULL_MASK, touched);
-        const bool any_low = __any_sync(PARC_FULL_MASK, low);
-        failed = any_touch && any_low;
-      }
-      if (p.pose_termination) {
-        float3 tb = make_float3(0.f, 0.f, 0.f);
-        if (body) tb = ld3(p.tar_body_pos + (e * p.tar_env_stride * J + lane) * 3);
-        const float3 r0 = shfl3(bp, 0), t0 = shfl3(tb, 0);
-        bool bad = false;
-        if (body && lane > 0) {
-          const float dx = sub_rn(sub_rn(tb.x, t0.x), sub_rn(bp.x, r0.x));
-          const float dy = sub_rn(sub_rn(tb.y, t0.y), sub_rn(bp.y, r0.y));
-          const float dz = sub_rn(sub_rn(tb.z, t0.z), sub_rn(bp.z, r0.z));
-          const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
-          const float lim = __ldg(p.pose_dist + lane - 1);
-          bad = d2 > mul_rn(lim, lim);
-        } else if (lane == 0 && p.track_root) {
-          const float dx = sub_rn(bp.x, tb.x), dy = sub_rn(bp.y, tb.y), dz = sub_rn(bp.z, tb.z);
-          const float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
-          const float ang = quat_diff_angle(ld4(p.root_rot + e * 4), ld4(p.tar_root_rot + e * p.tar_env_stride * 4));
-          bad = d2 > p.root_pos_dist_sq || fabsf(ang) > p.root_rot_angle;
-        }
-        failed = failed || __any_sync(PARC_FULL_MASK, bad);
-      }
-      if (failed && tm > p.first_step_eps) flag = PARC_DONE_FAIL;
-    }
-    if (lane == 0 && done) done[e] = flag;
+    if (p.char_contacts_out && lane < J) p.char_contacts_out[e * p.obs_stride + lane] = __ldg(p.char_contacts + e * J + lane);
+    reward_env<true>(p.sim, p.ref, e, Jm1, D, p.K, p.joint_w, p.dof_w, p.track_root_h, p.track_root,
+                     p.reward_out + e * 5, lane, jr);
+    done_env(p.done, e, p.done_out, nullptr, lane);
   }
 }
 
@@ -386,19 +472,19 @@ extern "C" int parc_deepmimic_reward(const ParcCharState* sim, const ParcCharSta
   return check_launch();
 }
 
-extern "C" int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
-                         const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
-                         const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
-                         int32_t offset_stride, int32_t tar_env_stride, int64_t n, int32_t num_bodies,
-                         int32_t* done_out, float* term_heights_out, void* stream) {
+// Validation + parameter block shared by parc_done and parc_sim_step.
+static int build_done_params(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
+                             const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
+                             const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
+                             int32_t offset_stride, int32_t tar_env_stride, int32_t num_bodies, bool want_heights_out,
+                             DoneParams* out) {
   if (!spec) return PARC_E_NULL;
-  if (n < 0 || num_bodies < 1 || num_bodies > PARC_MAX_BODIES || tar_env_stride < 1) return PARC_E_SIZE;
-  if (n == 0) return PARC_OK;
-  if (!time || !body_pos || (!done_out && !term_heights_out)) return PARC_E_NULL;
+  if (num_bodies < 1 || num_bodies > PARC_MAX_BODIES || tar_env_stride < 1) return PARC_E_SIZE;
+  if (!time || !body_pos) return PARC_E_NULL;
   const bool early = spec->enable_early_termination != 0;
   const bool fall = early && spec->has_contact_bodies;
   if (fall && !contact_force) return PARC_E_NULL;
-  if ((fall || term_heights_out) && !term_heights) {
+  if ((fall || want_heights_out) && !term_heights) {
     if (!hf || !hf->hf) return PARC_E_NULL;
     if (hf->dim_x <= 0 || hf->dim_y <= 0) return PARC_E_SIZE;
     if (env_offsets && offset_stride < 2) return PARC_E_SIZE;
@@ -426,6 +512,59 @@ extern "C" int parc_done(const ParcDoneSpec* spec, const float* time, const floa
   p.early_termination = spec->enable_early_termination; p.track_root = spec->track_root;
   p.J = num_bodies;
   p.tar_env_stride = tar_env_stride;
+  *out = p;
+  return PARC_OK;
+}
+
+extern "C" int parc_done(const ParcDoneSpec* spec, const float* time, const float* root_rot, const float* body_pos,
+                         const float* tar_root_rot, const float* tar_body_pos, const float* contact_force,
+                         const float* term_heights, const ParcHeightfield* hf, const float* env_offsets,
+                         int32_t offset_stride, int32_t tar_env_stride, int64_t n, int32_t num_bodies,
+                         int32_t* done_out, float* term_heights_out, void* stream) {
+  if (!spec) return PARC_E_NULL;
+  if (n < 0 || num_bodies < 1 || num_bodies > PARC_MAX_BODIES || tar_env_stride < 1) return PARC_E_SIZE;
+  if (n == 0) return PARC_OK;
+  if (!done_out && !term_heights_out) return PARC_E_NULL;
+  DoneParams p;
+  const int rc = build_done_params(spec, time, root_rot, body_pos, tar_root_rot, tar_body_pos, contact_force, term_heights,
+                                   hf, env_offsets, offset_stride, tar_env_stride, num_bodies, term_heights_out != nullptr,
+                                   &p);
+  if (rc) return rc;
   done_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, n, done_out, term_heights_out);
+  return check_launch();
+}
+
+extern "C" int parc_sim_step(const ParcSimStep* a, int64_t n, const ParcCharModel* model, void* stream) {
+  if (!a || !model) return PARC_E_NULL;
+  int rc = parc_validate_model(model);
+  if (rc) return rc;
+  if (n < 0 || a->num_keys < 1 || a->num_tar_steps < 0) return PARC_E_SIZE;   // the reward needs key bodies
+  if (n == 0) return PARC_OK;
+  const int J = model->num_bodies, D = model->dof_size;
+  ParcCharState sim = a->sim;
+  sim.joint_rot = a->sim.root_rot;          // never read (the DoFs are converted in registers); keeps the checker happy
+  rc = check_state(&sim, D, a->num_keys, true);
+  if (rc) return rc;
+  rc = check_state(&a->ref, D, a->num_keys, true);
+  if (rc) return rc;
+  if (!a->dof_pos || !a->char_obs_out || !a->reward_out || !a->done_out || !a->joint_rot_err_w || (D > 0 && !a->dof_err_w))
+    return PARC_E_NULL;
+  if (a->joint_rot_out && !aligned16(a->joint_rot_out)) return PARC_E_ALIGN;
+  if ((a->tar_contacts_out && !a->tar_contacts) || (a->char_contacts_out && !a->char_contacts)) return PARC_E_NULL;
+  if (a->tar_contacts_out && a->tar_env_stride < a->num_tar_steps) return PARC_E_SIZE;
+  const int64_t width = (a->root_height_obs ? 1 : 0) + 12 + 6 * (int64_t)(J - 1) + D + 3 * (int64_t)a->num_keys;
+  if (a->obs_stride < width) return PARC_E_SIZE;
+  SimStepParams p{};
+  rc = build_done_params(&a->done, a->time, a->sim.root_rot, a->body_pos, a->ref.root_rot, a->ref_body_pos, a->contact_force,
+                         nullptr, &a->hf, a->env_offsets, a->offset_stride, a->ref.env_stride, J, false, &p.done);
+  if (rc) return rc;
+  p.sim = sim; p.ref = a->ref; p.dof_pos = a->dof_pos; p.joint_w = a->joint_rot_err_w; p.dof_w = a->dof_err_w;
+  p.tar_contacts = a->tar_contacts; p.char_contacts = a->char_contacts; p.joint_rot_out = a->joint_rot_out;
+  p.char_obs_out = a->char_obs_out; p.tar_contacts_out = a->tar_contacts_out; p.char_contacts_out = a->char_contacts_out;
+  p.reward_out = a->reward_out; p.done_out = a->done_out; p.obs_stride = a->obs_stride;
+  p.tar_env_stride = a->tar_env_stride; p.num_tar_steps = a->num_tar_steps;
+  p.K = a->num_keys; p.global_obs = a->global_obs; p.root_height_obs = a->root_height_obs;
+  p.track_root_h = a->track_root_h; p.track_root = a->track_root;
+  sim_step_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, *model, n);
   return check_launch();
 }

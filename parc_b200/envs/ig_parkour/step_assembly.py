@@ -18,6 +18,10 @@ package, reading the simulator's state tensors in place:
   + 2 small copies (target / character contact flags).  The observation operators write their blocks of the
   policy-observation row in place (row-strided outputs), so there is no concatenation pass.
 
+With `fused=True` (default) the simulated character's share -- DoF conversion, proprioceptive observation, reward
+terms, episode flags and both contact-flag blocks -- is ONE launch (`parc_sim_step`, same device code as the
+stand-alone kernels, joint rotations never leave registers): 4 launches per step in total.
+
 Every output buffer is allocated once, so the sequence can be captured in a CUDA graph (`capture()`), after
 which a step is one graph launch.  The Isaac Gym classes themselves (simulation, resets, actors) are out of
 scope; this is the piece of them that sits on the kinematic-query path.
@@ -39,7 +43,7 @@ class TrackerStep:
                  pose_termination: bool = True, enable_early_termination: bool = True,
                  termination_height: float = 0.15, episode_length: float = 10.0,
                  root_pos_termination_dist: float = 0.6, root_rot_termination_angle: float = 1.309,
-                 min_obs_h: float = -3.0, max_obs_h: float = 3.0):
+                 min_obs_h: float = -3.0, max_obs_h: float = 3.0, fused: bool = True):
         dev = mlib._device if hasattr(mlib, "_device") else ray_xy_points.device
         self.device = torch.device(dev)
         self.mlib, self.kcm, self.terrain = mlib, mlib._kin_char_model, terrain
@@ -81,6 +85,14 @@ class TrackerStep:
         self._contacts = bool(getattr(mlib, "_contact_info", False))
         self._obs_bufs = {}
         self._graph = None
+        # fused=True: the simulated character's share of the step (DoF conversion, observation block, reward, done,
+        # contact blocks) is ONE launch (parc_sim_step) instead of four launches and two copies
+        self.fused = bool(fused)
+        self._sim_plan, self._sim_key = None, None
+        D = self.kcm.get_dof_size()
+        self._reward = torch.empty(self.n, 5, dtype=torch.float32, device=self.device)
+        self._done = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        self._joint_rot = torch.empty(self.n, J - 1, 4, dtype=torch.float32, device=self.device)
 
     def _obs_layout(self, with_char_contacts: bool):
         J = self.kcm.get_num_joints()
@@ -114,6 +126,9 @@ class TrackerStep:
         ref, tar = self._views(self._plan.launch())
         obs, col = self._obs_layout(char_contacts is not None)
         blk = lambda name: obs[:, col[name][0]:col[name][1]]
+        if self.fused:
+            return self._step_fused(ref, tar, obs, blk, root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel,
+                                    body_pos, contact_forces, time_buf, env_offsets, char_contacts)
         joint_rot = self.kcm.dof_to_rot(dof_pos)
         # ray heightmap around the SIMULATED character (ig_parkour_env.py:636-646, mgdm_dm_util.py:158-179)
         # heading = calc_heading(root_rot) and the env-local -> terrain shift are taken inside the launch
@@ -143,6 +158,44 @@ class TrackerStep:
                    tar_obs=tar_obs.view(self.n, self.S, self.tar_w), ray_hfs=ray_hfs)
         res.update({"ref_" + k: t for k, t in ref.items()})
         return res
+
+    def _step_fused(self, ref, tar, obs, blk, root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, body_pos,
+                    contact_forces, time_buf, env_offsets, char_contacts):
+        """4 launches: query (already done by the caller), ray heightmap, target observation, parc_sim_step -- each a
+        prebuilt argument list over the caller's (persistent) state tensors, rebuilt only if a tensor is replaced."""
+        c = self.cfg
+        state = (root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, body_pos, contact_forces, time_buf,
+                 env_offsets, char_contacts)
+        key = tuple(None if t is None else (t.data_ptr(), tuple(t.shape), tuple(t.stride())) for t in state) \
+            + (obs.data_ptr(),)
+        if self._sim_plan is None or key != self._sim_key:
+            ray = ops.hf_obs(self.terrain.hf_desc(), self.ray_xy_points, root_pos, None, relative=True,
+                             min_h=c["min_obs_h"], max_h=c["max_obs_h"], root_rot=root_rot, root_offset=env_offsets,
+                             out=blk("ray"), plan=True)
+            tarp = ops.tar_obs(root_pos, root_rot, tar["root_pos"], tar["root_rot"], tar["joint_rot"], tar["body_pos"],
+                               c["global_obs"], False, key_body_ids=self.key_body_ids, out=blk("tar"), plan=True)
+            sim = dict(root_pos=root_pos, root_rot=root_rot, root_vel=root_vel, root_ang_vel=root_ang_vel,
+                       dof_pos=dof_pos, dof_vel=dof_vel, body_pos=body_pos, contact_force=contact_forces, time=time_buf,
+                       env_offsets=env_offsets, char_contacts=char_contacts)
+            refd = dict(ref)
+            out = dict(char_obs=blk("char"), reward=self._reward, done=self._done, joint_rot=self._joint_rot)
+            if self._contacts:
+                refd["tar_contacts"] = tar["contacts"]
+                out["tar_contacts"] = blk("tar_contacts")
+                if char_contacts is not None:
+                    out["char_contacts"] = blk("char_contacts")
+            cfg = dict(c, pose_termination_dist=self.pose_termination_dist)
+            simp = ops.SimStepPlan(self.kcm.c_model(), sim, refd, self.key_body_ids, self.joint_err_w, self.dof_err_w,
+                                   self.terrain.hf_desc(), out, cfg=cfg, contact_body_ids=self.contact_body_ids)
+            self._sim_plan, self._sim_key = (ray, tarp, simp), key
+            res = dict(obs=obs, reward_terms=self._reward, done=self._done, char_obs=blk("char"),
+                       tar_obs=blk("tar").view(self.n, self.S, self.tar_w), ray_hfs=blk("ray"), joint_rot=self._joint_rot)
+            res.update({"ref_" + k: t for k, t in ref.items()})
+            self._fused_result = res
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for p in self._sim_plan:
+            p.launch(stream)
+        return self._fused_result
 
     def capture(self, *state) -> "torch.cuda.CUDAGraph":
         """Capture `step(*state)` over the given (persistent) simulator tensors into a CUDA graph; afterwards

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ParcBodyPoints, ParcCharModel, ParcCharState, ParcDoneSpec, ParcKeyBodies, ParcClipMeta, ParcFkOut,
+from ._lib import (ParcBodyPoints, ParcCharModel, ParcCharState, ParcDoneSpec, ParcSimStep, ParcKeyBodies, ParcClipMeta, ParcFkOut,
                    ParcFrameOut, ParcHeightfield, ParcMotionTables, ParcObsSpec, ParcRowLayout, ParcTerrainBatch, check,
                    f32c, ptr, require_cuda, stream_ptr)
 
@@ -498,9 +498,10 @@ def selftest_grid_index(min_coord: float, cell_size: float, dim: int, device="cu
 
 def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, heading: Optional[torch.Tensor], *,
            relative: bool, min_h: float = -3.0, max_h: float = 3.0, out: Optional[torch.Tensor] = None,
-           root_rot: Optional[torch.Tensor] = None, root_offset: Optional[torch.Tensor] = None):
+           root_rot: Optional[torch.Tensor] = None, root_offset: Optional[torch.Tensor] = None, plan: bool = False):
     """root [N,>=2 (3 if relative)], heading [N], tmpl [P,2] -> [N,P].  With heading=None the heading is taken
-    from `root_rot` [N,4] inside the launch; `root_offset` [N,>=2 (3 if relative)] is added to the root first."""
+    from `root_rot` [N,4] inside the launch; `root_offset` [N,>=2 (3 if relative)] is added to the root first.
+    plan=True returns a CallPlan over these buffers instead of launching."""
     require_cuda(hf.hf, tmpl_xy, root, heading, root_rot, root_offset)
     r = f32c(root)
     assert r.dim() == 2
@@ -512,10 +513,12 @@ def hf_obs(hf: HeightfieldDesc, tmpl_xy: torch.Tensor, root: torch.Tensor, headi
     n, P = r.shape[0], tm.shape[0]
     out, out_stride = _out_rows(out, n, P, r.device)
     h, o = hf.c_struct(), _obs_struct(tm, relative, min_h, max_h)
+    args = (C.byref(h), C.byref(o), r.data_ptr(), int(r.shape[1]), ptr(hd), ptr(rr), ptr(ro),
+            int(ro.shape[1]) if ro is not None else 0, n, out.data_ptr(), out_stride)
+    if plan:
+        return CallPlan("parc_hf_obs", args, r.device, (h, o, r, hd, rr, ro, tm, hf, out), out)
     with torch.cuda.device(r.device):
-        rc = _lib.load().parc_hf_obs(C.byref(h), C.byref(o), r.data_ptr(), int(r.shape[1]), ptr(hd), ptr(rr), ptr(ro),
-                                     int(ro.shape[1]) if ro is not None else 0, n, out.data_ptr(), out_stride,
-                                     stream_ptr(r.device))
+        rc = _lib.load().parc_hf_obs(*args, stream_ptr(r.device))
     check(rc, "parc_hf_obs")
     return out
 
@@ -764,6 +767,24 @@ def unpack_frame_masks(bits: torch.Tensor, X: int, Y: int) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # tracker step assembly: policy observation, reward, done -- one launch each
 # ----------------------------------------------------------------------------------------------
+class CallPlan:
+    """One C entry point with its argument list prebuilt over fixed buffers: `launch()` is a single ctypes call.
+    Returned by the operators that accept `plan=True`; `result` is what the eager call would have returned."""
+
+    def __init__(self, name: str, args: tuple, device, keep, result):
+        self._fn, self._name, self._args = getattr(_lib.load(), name), name, args
+        self.device, self._keep, self.result = device, keep, result
+
+    def launch(self, stream: Optional[int] = None):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._fn(*self._args, stream)
+        _lib.LAUNCHES[0] += 1
+        if rc != 0:
+            check(rc, self._name)
+        return self.result
+
+
 def _out_rows(out: Optional[torch.Tensor], n: int, width: int, device) -> Tuple[torch.Tensor, int]:
     """(out, row stride in floats): a fresh dense [n,width] buffer, or the caller's -- which may be a column slice
     of a wider row-major buffer (e.g. a block of the policy-observation row): unit inner stride required."""
@@ -866,7 +887,7 @@ def char_obs(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel, key
 
 
 def tar_obs(ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_rot, tar_key_pos, global_obs: bool,
-            global_tar_root_h_obs: bool, key_body_ids=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            global_tar_root_h_obs: bool, key_body_ids=None, out: Optional[torch.Tensor] = None, plan: bool = False):
     """compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518): targets [n,S,...] -> [n,S,W].  The target arrays
     may be step slices of larger [n,S_total,...] buffers (no copy); with `key_body_ids`, `tar_key_pos` is the
     targets' body positions [n,S,J,3].  One launch."""
@@ -901,12 +922,15 @@ def tar_obs(ref_root_pos, ref_root_rot, tar_root_pos, tar_root_rot, tar_joint_ro
         flat, out_stride = torch.empty((n, S * W), dtype=torch.float32, device=tp.device), S * W
     else:                                     # [n, S*W] (possibly a column block of a wider buffer) or [n, S, W]
         flat, out_stride = _out_rows(out.view(n, S * W) if out.dim() == 3 else out, n, S * W, tp.device)
+    args = (rp.data_ptr(), rr.data_ptr(), tp.data_ptr(), tr.data_ptr(), tj.data_ptr(), ptr(tk), n, S, jm1, k,
+            int(bool(global_obs)), int(bool(global_tar_root_h_obs)), stride, ptr(ids), nb, flat.data_ptr(), out_stride)
+    result = flat.view(n, S, W) if out is None else out
+    if plan:
+        return CallPlan("parc_tar_obs", args, tp.device, (rp, rr, tp, tr, tj, tk, ids, flat), result)
     with torch.cuda.device(tp.device):
-        rc = _lib.load().parc_tar_obs(rp.data_ptr(), rr.data_ptr(), tp.data_ptr(), tr.data_ptr(), tj.data_ptr(), ptr(tk),
-                                      n, S, jm1, k, int(bool(global_obs)), int(bool(global_tar_root_h_obs)), stride,
-                                      ptr(ids), nb, flat.data_ptr(), out_stride, stream_ptr(tp.device))
+        rc = _lib.load().parc_tar_obs(*args, stream_ptr(tp.device))
     check(rc, "parc_tar_obs")
-    return flat.view(n, S, W) if out is None else out
+    return result
 
 
 def deepmimic_reward(sim: tuple, tar: tuple, joint_rot_err_w, dof_err_w, track_root_h: bool, track_root: bool,
@@ -992,3 +1016,119 @@ def done_flags(time, ep_len: float, root_rot, body_pos, tar_root_rot, tar_body_p
                                    ptr(th_out), stream_ptr(dev))
     check(rc, "parc_done")
     return (out, th_out) if want_heights else out
+
+
+def _done_spec(ep_len, termination_height, root_pos_termination_dist, root_rot_termination_angle, pose_termination_dist,
+               contact_body_ids, num_bodies, pose_termination, enable_early_termination, track_root):
+    spec = ParcDoneSpec()
+    spec.episode_length = float(ep_len)
+    spec.termination_height = float(termination_height)
+    spec.root_pos_termination_dist = float(root_pos_termination_dist)
+    spec.root_rot_termination_angle = float(root_rot_termination_angle)
+    spec.pose_termination_dist = ptr(pose_termination_dist)
+    mask = 0
+    for i in contact_body_ids:
+        assert 0 <= int(i) < num_bodies
+        mask |= 1 << int(i)
+    spec.contact_body_mask = mask
+    spec.has_contact_bodies = int(len(contact_body_ids) > 0)
+    spec.pose_termination = int(bool(pose_termination))
+    spec.enable_early_termination = int(bool(enable_early_termination))
+    spec.track_root = int(bool(track_root))
+    return spec
+
+
+class SimStepPlan:
+    """parc_sim_step over fixed buffers with every argument prebuilt (one ctypes call per step): the simulated
+    character's DoF conversion, observation block, reward terms, episode flag and contact-flag blocks in ONE launch.
+    `sim` = dict(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, body_pos, contact_force, time,
+    env_offsets[, char_contacts]); `ref` = dict of the reference frame as row-strided views (root_pos, root_rot,
+    root_vel, root_ang_vel, joint_rot, dof_vel, body_pos[, and `tar_contacts` = contacts of steps 1..S]).
+    Outputs: column blocks `char_obs` / `tar_contacts` / `char_contacts` of one observation buffer, `reward` [n,5],
+    `done` [n] int32, optional `joint_rot` [n,J-1,4]."""
+
+    def __init__(self, model: ParcCharModel, sim: dict, ref: dict, key_body_ids: torch.Tensor, joint_rot_err_w,
+                 dof_err_w, hf: HeightfieldDesc, out: dict, *, cfg: dict, contact_body_ids=()):
+        J, D = model.num_bodies, model.dof_size
+        self.model, self.device = model, sim["root_pos"].device
+        n = int(sim["root_pos"].shape[0])
+        self.n = n
+        keep = []
+
+        def dense(t, shape):
+            assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(shape), (t.shape, shape)
+            require_cuda(t)
+            keep.append(t)
+            return t.data_ptr()
+
+        a = ParcSimStep()
+        ids = key_body_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        keep.append(ids)
+        K = int(ids.shape[0])
+        a.sim.root_pos, a.sim.root_rot = dense(sim["root_pos"], (n, 3)), dense(sim["root_rot"], (n, 4))
+        a.sim.root_vel, a.sim.root_ang_vel = dense(sim["root_vel"], (n, 3)), dense(sim["root_ang_vel"], (n, 3))
+        a.sim.dof_vel = dense(sim["dof_vel"], (n, D))
+        a.sim.key_pos = dense(sim["body_pos"], (n, J, 3))
+        a.sim.key_body_ids, a.sim.num_bodies, a.sim.env_stride = ids.data_ptr(), J, 1
+        views = {k: _rows(ref[k]) for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel",
+                                            "body_pos")}
+        strides = {k for _, k in views.values()}
+        assert len(strides) == 1, "the reference-frame views must share one row stride"
+        stride = strides.pop()
+        keep += [t for t, _ in views.values()]
+        rv = {k: t.data_ptr() for k, (t, _) in views.items()}
+        a.ref.root_pos, a.ref.root_rot, a.ref.root_vel = rv["root_pos"], rv["root_rot"], rv["root_vel"]
+        a.ref.root_ang_vel, a.ref.joint_rot, a.ref.dof_vel = rv["root_ang_vel"], rv["joint_rot"], rv["dof_vel"]
+        a.ref.key_pos, a.ref.key_body_ids, a.ref.num_bodies, a.ref.env_stride = rv["body_pos"], ids.data_ptr(), J, stride
+        a.ref_body_pos = rv["body_pos"]
+        a.dof_pos, a.body_pos = dense(sim["dof_pos"], (n, D)), a.sim.key_pos
+        a.contact_force = dense(sim["contact_force"], (n, J, 3)) if sim.get("contact_force") is not None else None
+        a.time = dense(sim["time"], (n,))
+        eo = sim.get("env_offsets")
+        if eo is not None:
+            a.env_offsets, a.offset_stride = dense(eo, (n, eo.shape[1])), int(eo.shape[1])
+        jw, dw = f32c(joint_rot_err_w), f32c(dof_err_w)
+        ptd = f32c(cfg["pose_termination_dist"])
+        keep += [jw, dw, ptd]
+        assert jw.shape == (J - 1,) and dw.shape == (D,) and ptd.shape == (J - 1,)
+        a.joint_rot_err_w, a.dof_err_w = jw.data_ptr(), dw.data_ptr()
+        a.done = _done_spec(cfg["episode_length"], cfg["termination_height"], cfg["root_pos_termination_dist"],
+                            cfg["root_rot_termination_angle"], ptd, contact_body_ids, J, cfg["pose_termination"],
+                            cfg["enable_early_termination"], cfg["track_root"])
+        a.hf = hf.c_struct()
+        keep.append(hf.hf)
+        a.num_keys = K
+        a.global_obs, a.root_height_obs = int(bool(cfg["global_obs"])), int(bool(cfg["root_height_obs"]))
+        a.track_root_h, a.track_root = int(bool(cfg["track_root_h"])), int(bool(cfg["track_root"]))
+        # outputs: column blocks of one observation buffer share its row stride
+        width = (1 if cfg["root_height_obs"] else 0) + 12 + 6 * (J - 1) + D + 3 * K
+        blk, stride_obs = _out_rows(out["char_obs"], n, width, self.device)
+        a.char_obs_out, a.obs_stride = blk.data_ptr(), stride_obs
+        if out.get("tar_contacts") is not None:
+            tc, k2 = _rows(ref["tar_contacts"], lead=2)
+            S = int(tc.shape[1])
+            assert tc.shape == (n, S, J)
+            b2, s2 = _out_rows(out["tar_contacts"], n, S * J, self.device)
+            assert s2 == stride_obs
+            keep += [tc, b2]
+            a.tar_contacts, a.tar_env_stride, a.num_tar_steps, a.tar_contacts_out = tc.data_ptr(), k2, S, b2.data_ptr()
+        if out.get("char_contacts") is not None:
+            b3, s3 = _out_rows(out["char_contacts"], n, J, self.device)
+            assert s3 == stride_obs
+            keep.append(b3)
+            a.char_contacts, a.char_contacts_out = dense(sim["char_contacts"], (n, J)), b3.data_ptr()
+        assert out["reward"].shape == (n, 5) and out["reward"].is_contiguous() and out["done"].dtype == torch.int32
+        a.reward_out, a.done_out = out["reward"].data_ptr(), out["done"].data_ptr()
+        if out.get("joint_rot") is not None:
+            a.joint_rot_out = dense(out["joint_rot"], (n, J - 1, 4))
+        keep += [blk, out["reward"], out["done"]]
+        self._args, self._keep = a, keep
+        self._fn = _lib.load().parc_sim_step
+
+    def launch(self, stream: Optional[int] = None):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._fn(C.byref(self._args), self.n, C.byref(self.model), stream)
+        _lib.LAUNCHES[0] += 1
+        if rc != 0:
+            check(rc, "parc_sim_step")

@@ -1080,7 +1080,8 @@ def test_step_assembly_matches_oracle_on_a_generic_tree():
     assert seen == {0, 1, 3}
 
 
-def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model, O, oracle_tables, oracle_model):
+@pytest.mark.parametrize("fused", [False, True])
+def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model, O, oracle_tables, oracle_model, fused):
     """The whole kinematic side of a control step (envs/ig_parkour/step_assembly.py): reference frame + 6 targets
     with the per-env terrain placement, simulated character's observation, ray heightmap, reward terms and done
     flags -- against the same sequence composed from the oracle; then the CUDA-graph replay against the eager run."""
@@ -1099,7 +1100,7 @@ def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model,
     jw, ptd = torch.as_tensor(g["joint_err_w"]), torch.as_tensor(g["pose_termination_dist"])
     feet = [int(i) for i in g["feet"]]
     ts = TrackerStep(golden_lib, terr, n, float(g["dt"]), g["steps"].tolist(), key_ids.tolist(), tmpl, joint_err_w=jw,
-                     pose_termination_dist=ptd, contact_body_ids=feet)
+                     pose_termination_dist=ptd, contact_body_ids=feet, fused=fused)
     ids, times = torch.as_tensor(g["ids"]).long(), torch.as_tensor(g["times"])
     xy_off = torch.randn(n, 2, generator=gen) * 0.3
     env_off = torch.as_tensor(g["env_offsets"])
