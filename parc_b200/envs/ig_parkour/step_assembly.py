@@ -89,6 +89,8 @@ class TrackerStep:
         # contact blocks) is ONE launch (parc_sim_step) instead of four launches and two copies
         self.fused = bool(fused)
         self._sim_plan, self._sim_key = None, None
+        self._side = torch.cuda.Stream(self.device)
+        self._query_done = torch.cuda.Event()
         D = self.kcm.get_dof_size()
         self._reward = torch.empty(self.n, 5, dtype=torch.float32, device=self.device)
         self._done = torch.empty(self.n, dtype=torch.int32, device=self.device)
@@ -123,12 +125,13 @@ class TrackerStep:
         (ref_root_pos, ref_root_rot, ref_root_vel, ref_root_ang_vel, ref_joint_rot, ref_dof_vel, ref_body_pos,
         ref_contacts)."""
         c = self.cfg
-        ref, tar = self._views(self._plan.launch())
         obs, col = self._obs_layout(char_contacts is not None)
         blk = lambda name: obs[:, col[name][0]:col[name][1]]
         if self.fused:
+            ref, tar = self._views(self._plan.out)           # buffers are fixed; the query is launched inside
             return self._step_fused(ref, tar, obs, blk, root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel,
                                     body_pos, contact_forces, time_buf, env_offsets, char_contacts)
+        ref, tar = self._views(self._plan.launch())
         joint_rot = self.kcm.dof_to_rot(dof_pos)
         # ray heightmap around the SIMULATED character (ig_parkour_env.py:636-646, mgdm_dm_util.py:158-179)
         # heading = calc_heading(root_rot) and the env-local -> terrain shift are taken inside the launch
@@ -192,9 +195,19 @@ class TrackerStep:
                        tar_obs=blk("tar").view(self.n, self.S, self.tar_w), ray_hfs=blk("ray"), joint_rot=self._joint_rot)
             res.update({"ref_" + k: t for k, t in ref.items()})
             self._fused_result = res
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        for p in self._sim_plan:
-            p.launch(stream)
+        # Two branches: the ray heightmap needs only the simulator state, and once the query has finished the target
+        # observation and the character's step are independent of each other.  (Under CUDA-graph capture the side
+        # stream becomes a parallel branch of the graph.)
+        ray, tarp, simp = self._sim_plan
+        cur, side = torch.cuda.current_stream(self.device), self._side
+        side.wait_stream(cur)
+        ray.launch(side.cuda_stream)
+        self._plan.launch(cur.cuda_stream)
+        self._query_done.record(cur)
+        side.wait_event(self._query_done)
+        simp.launch(side.cuda_stream)
+        tarp.launch(cur.cuda_stream)
+        cur.wait_stream(side)
         return self._fused_result
 
     def capture(self, *state) -> "torch.cuda.CUDAGraph":
