@@ -1418,3 +1418,60 @@ def test_small_api_helpers(golden_lib, gpu_model, O, oracle_model, oracle_tables
     ids = torch.randint(0, 3, (500,), generator=gen)
     times = (torch.rand(500, generator=gen) * 6 - 2) * oracle_tables.lengths[ids]
     assert torch.equal(golden_lib._calc_loop_offset(ids.cuda(), times.cuda()).cpu(), O.loop_offset(oracle_tables, ids, times))
+
+
+@pytest.mark.parametrize("global_obs,root_h,track_root,track_h,feet_only,pose", [
+    (False, False, True, True, True, True), (True, True, False, False, False, True),
+    (False, True, False, True, True, False), (True, False, True, False, False, False)])
+def test_sim_step_equals_the_standalone_operators(gpu_model, global_obs, root_h, track_root, track_h, feet_only, pose):
+    """parc_sim_step (one launch) against dof_to_rot + char_obs + deepmimic_reward + done_flags + the two contact
+    copies, over the flag combinations; reference frame read in place as step 0 of an [n, 3, ...] buffer."""
+    from parc_b200 import ops
+    g, sim, ref, key_ids = _step_golden()
+    n, J, D = sim[0].shape[0], 15, 28
+    kid = key_ids.to(torch.int32)
+    dof_pos = gpu_model.rot_to_dof(sim[4])
+    body_pos = gpu_model.forward_kinematics(sim[0], sim[1], gpu_model.dof_to_rot(dof_pos))[0].contiguous()
+    SENT = 777.0
+    names = ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel")
+    big = {k: torch.full((n, 3) + tuple(t.shape[1:]), SENT, device="cuda") for k, t in zip(names, ref)}
+    for k, t in zip(names, ref):
+        big[k][:, 0] = t
+    big["body_pos"] = torch.full((n, 3, J, 3), SENT, device="cuda")
+    big["body_pos"][:, 0] = _cu(g["ref_body_pos"])
+    big["contacts"] = torch.rand(n, 3, J, device="cuda")
+    refv = {k: v[:, 0] for k, v in big.items()}
+    forces, tm, off = _cu(g["contact_forces"]), _cu(g["time_buf"]), _cu(g["env_offsets"])
+    char_contacts = (torch.rand(n, J, device="cuda") < 0.5).float()
+    hfd = ops.HeightfieldDesc(hf=_cu(g["hf"]), min_x=float(g["hf_min"][0]), min_y=float(g["hf_min"][1]),
+                              dx=float(g["hf_dxdy"][0]), dy=float(g["hf_dxdy"][1]))
+    jw, dw, ptd = _cu(g["joint_err_w"]), _cu(g["dof_err_w"]), _cu(g["pose_termination_dist"])
+    allowed = [int(i) for i in g["feet"]] if feet_only else []
+    cfg = dict(global_obs=global_obs, root_height_obs=root_h, track_root=track_root, track_root_h=track_h,
+               pose_termination=pose, enable_early_termination=True, termination_height=0.15, episode_length=10.0,
+               root_pos_termination_dist=0.6, root_rot_termination_angle=1.309, pose_termination_dist=ptd)
+    wc = (1 if root_h else 0) + 12 + 6 * (J - 1) + D + 3 * 4
+    obs = torch.full((n, 3 + wc + 2 * J + J + 5), SENT, device="cuda")
+    out = dict(char_obs=obs[:, 3:3 + wc], tar_contacts=obs[:, 3 + wc:3 + wc + 2 * J],
+               char_contacts=obs[:, 3 + wc + 2 * J:3 + wc + 3 * J], reward=torch.empty(n, 5, device="cuda"),
+               done=torch.empty(n, dtype=torch.int32, device="cuda"), joint_rot=torch.empty(n, J - 1, 4, device="cuda"))
+    simd = dict(root_pos=sim[0], root_rot=sim[1], root_vel=sim[2], root_ang_vel=sim[3], dof_pos=dof_pos, dof_vel=sim[5],
+                body_pos=body_pos, contact_force=forces, time=tm, env_offsets=off, char_contacts=char_contacts)
+    refd = dict(refv, tar_contacts=big["contacts"][:, 1:])
+    plan = ops.SimStepPlan(gpu_model.c_model(), simd, refd, kid, jw, dw, hfd, out, cfg=cfg, contact_body_ids=allowed)
+    plan.launch()
+    # stand-alone operators
+    jr = gpu_model.dof_to_rot(dof_pos)
+    want_obs = ops.char_obs(sim[0], sim[1], sim[2], sim[3], jr, sim[5], body_pos, global_obs, root_h, key_body_ids=kid)
+    want_rew = ops.deepmimic_reward((sim[0], sim[1], sim[2], sim[3], jr, sim[5], body_pos),
+                                    tuple(refv[k] for k in names) + (refv["body_pos"],), jw, dw, track_h, track_root,
+                                    key_body_ids=kid)
+    want_done = ops.done_flags(tm, 10.0, sim[1], body_pos, refv["root_rot"], refv["body_pos"], forces, allowed, pose, ptd,
+                               True, track_root, 0.6, 1.309, hf=hfd, env_offsets=off, termination_height=0.15)
+    assert_close(out["joint_rot"], jr, what="joint_rot")
+    assert_close(out["char_obs"], want_obs, atol=2e-6, what="char_obs")
+    assert_close(out["reward"], want_rew, atol=2e-6, what="reward")
+    assert torch.equal(out["done"], want_done)
+    assert torch.equal(out["tar_contacts"], big["contacts"][:, 1:].reshape(n, -1))
+    assert torch.equal(out["char_contacts"], char_contacts)
+    assert (obs[:, :3] == SENT).all() and (obs[:, -5:] == SENT).all()
