@@ -285,7 +285,10 @@ __device__ __forceinline__ void done_env(const DoneParams& p, int64_t e, int32_t
         gx = add_rn(gx, __ldg(p.env_offsets + e * p.offset_stride));
         gy = add_rn(gy, __ldg(p.env_offsets + e * p.offset_stride + 1));
       }
-      th = add_rn(hf_lookup(p.hf, gx, gy), p.termination_height);
+      // hoisted-reciprocal cell index: index-identical to the reference's true division (parc_selftest_grid_index)
+      const int ix = grid_index_fast(gx, make_grid_axis(p.hf.min_x, p.hf.dx, p.hf.dim_x));
+      const int iy = grid_index_fast(gy, make_grid_axis(p.hf.min_y, p.hf.dy, p.hf.dim_y));
+      th = add_rn(__ldg(p.hf.hf + (size_t)ix * p.hf.dim_y + iy), p.termination_height);
     }
     if (term_heights_out) term_heights_out[e * J + lane] = th;
   }
