@@ -199,6 +199,17 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
     Returns a dict of output tensors; `out` may carry preallocated tensors to reuse."""
     require_cuda(motion_ids, motion_times, frame_idxs)
     dev = motion_ids.device
+    # ids may carry any leading shape (the reference gathers with whatever it is handed): flatten here, restore below
+    lead = tuple(motion_ids.shape)
+    if len(lead) != 1:
+        other = motion_times if motion_times is not None else frame_idxs
+        motion_ids, other = torch.broadcast_tensors(motion_ids, other)
+        lead = tuple(motion_ids.shape)
+        motion_ids = motion_ids.reshape(-1)
+        if motion_times is not None:
+            motion_times = other.reshape(-1)
+        else:
+            frame_idxs = other.reshape(-1)
     N = int(motion_ids.shape[0])
     J, D = model.num_bodies, model.dof_size
     ids = motion_ids.to(torch.int64).contiguous()
@@ -252,6 +263,8 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
             rc = lib.parc_get_motion_frame(C.byref(tb), ids.data_ptr(), fi.data_ptr(), N, C.byref(model),
                                            C.byref(fo), C.byref(fk) if want_fk else None, stream_ptr(dev))
             check(rc, "parc_get_motion_frame")
+    if len(lead) != 1:
+        return {k: v.reshape(*lead, *v.shape[1:]) for k, v in res.items()}
     return res
 
 

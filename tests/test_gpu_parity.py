@@ -1475,3 +1475,23 @@ def test_sim_step_equals_the_standalone_operators(gpu_model, global_obs, root_h,
     assert torch.equal(out["tar_contacts"], big["contacts"][:, 1:].reshape(n, -1))
     assert torch.equal(out["char_contacts"], char_contacts)
     assert (obs[:, :3] == SENT).all() and (obs[:, -5:] == SENT).all()
+
+
+def test_query_accepts_any_leading_shape_and_int32_ids(golden_lib):
+    """The reference indexes its tables with whatever shape / integer dtype the ids have; so does the mirror."""
+    gen = torch.Generator().manual_seed(6)
+    ids = torch.randint(0, 3, (4, 5), generator=gen).cuda()
+    times = (torch.rand(4, 5, generator=gen) * 3.0).cuda()
+    flat = golden_lib.calc_motion_frame(ids.reshape(-1), times.reshape(-1))
+    shaped = golden_lib.calc_motion_frame(ids.to(torch.int32), times)
+    assert shaped[0].shape == (4, 5, 3) and shaped[4].shape == (4, 5, 14, 4) and shaped[6].shape == (4, 5, 15)
+    for a, b in zip(shaped, flat):
+        assert torch.equal(a.reshape(b.shape), b)
+    scalar = golden_lib.calc_motion_frame(torch.tensor(1, device="cuda"), torch.tensor(0.7, device="cuda"))
+    assert scalar[0].shape == (3,) and scalar[4].shape == (14, 4)
+    one = golden_lib.calc_motion_frame(torch.tensor([1], device="cuda"), torch.tensor([0.7], device="cuda"))
+    assert torch.equal(scalar[1], one[1][0])
+    g = golden_lib.get_motion_frame(ids, torch.randint(0, 30, (4, 5), generator=gen).cuda())
+    assert g[5].shape == (4, 5, 28)
+    i0, i1, bl = golden_lib._calc_frame_blend(ids, times)
+    assert i0.shape == (4, 5) and i0.dtype == torch.int64 and bl.shape == (4, 5)
