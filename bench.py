@@ -193,6 +193,117 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# CPU legs of the secondary workloads (scripts/bench_*.py call these).  Together with cpu_reference_step_fn above
+# this file is the only place outside tests/ and smoke() that executes oracle/ -- always as the timed CPU
+# baseline beside a GPU measurement, never as part of a product path.
+# ------------------------------------------------------------------------------------------------
+def _oracle_and_model():
+    from oracle import parc_oracle as O
+    om = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    return O, om, cores
+
+
+def cpu_leg_loss(smp, hfs, num_samples, num_frames, full_frames):
+    """Config 3: pen/contact loss fwd+bwd of `num_samples` samples x `num_frames` frames -> samples/s scaled linearly
+    to `full_frames` frames."""
+    O, om, cores = _oracle_and_model()
+    t0 = time.perf_counter()
+    for i in range(num_samples):
+        a = torch.tensor(smp["root_pos"][i, :num_frames]).requires_grad_(True)
+        b = torch.tensor(smp["root_exp"][i, :num_frames]).requires_grad_(True)
+        c = torch.tensor(smp["joint_dof"][i, :num_frames]).requires_grad_(True)
+        loss, _, _ = O.motion_opt_pen_contact(om, a, b, c, torch.tensor(smp["contacts"][i, :num_frames]),
+                                              torch.tensor(hfs[i]), torch.zeros(2), torch.tensor([0.4, 0.4]), 0.1, 0.1)
+        loss.backward()
+    cpu_s = time.perf_counter() - t0
+    return {"samples_per_s": num_samples * (num_frames / full_frames) / cpu_s, "cores": cores,
+            "sample": f"{num_samples} sample(s) x {num_frames} frames fwd+bwd, scaled linearly to {full_frames} frames"}
+
+
+def cpu_leg_motion_opt(frames, contacts, hf, weights):
+    """One Adam iteration of the restated motion_contact_optimization on the host cores -> seconds."""
+    O, om, cores = _oracle_and_model()
+    t0 = time.perf_counter()
+    O.motion_contact_optimization(om, frames, contacts, hf, torch.zeros(2), torch.tensor([0.4, 0.4]), 1, 0.001, weights,
+                                  1000.0)
+    return time.perf_counter() - t0, cores
+
+
+def cpu_leg_sweep(fr_np, base_hf, num_clips, frames_per_clip):
+    """Config 5: FK + foot / hand labels on `num_clips` clips, heightfield masks on one clip."""
+    O, om, cores = _oracle_and_model()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "label_golden.npz"))
+    feet = [(int(b), h.tolist(), o.tolist()) for b, h, o in zip(g["feet_body"], g["feet_half"], g["feet_offset"])]
+    hands = [(int(b), float(r)) for b, r in zip(g["hands_body"], g["hands_radius"])]
+    terr = lambda i: O.Terrain(hf=torch.tensor(base_hf[(i // 4) % 64]), min_point=torch.zeros(2),
+                               dxdy=torch.tensor([0.4, 0.4]))
+    t0 = time.perf_counter()
+    for i in range(num_clips):
+        f_i = torch.tensor(fr_np[i])
+        O.frames_fk(om, f_i)
+        O.foot_contacts_and_pen(om, f_i, terr(i), feet)
+        O.hand_contacts(om, f_i, terr(i), hands)
+    label_s = (time.perf_counter() - t0) / num_clips
+    t0 = time.perf_counter()
+    O.hf_mask_inds(om, torch.tensor(fr_np[0]), terr(0))
+    mask_s = time.perf_counter() - t0
+    return {"cores": cores, "label_s_per_clip": label_s, "mask_s_per_clip": mask_s,
+            "body_frames_per_s_label": frames_per_clip * 15 / label_s,
+            "sample": f"{num_clips} clips (FK + foot + hand labels), 1 clip (masks; vectorised restatement "
+                      "-- the reference's python triple loop is ~14 ms/frame, SURVEY section 6)"}
+
+
+def cpu_leg_tracker_step(mlib, hf_np, hf_dx, state, ids, times, xy_offset, time_offsets, key_ids, feet, joint_w,
+                         dof_w, pose_dist, tmpl, reps):
+    """The kinematic side of one tracker control step composed from the oracle on all host cores.
+    -> (best seconds, cores, (obs, reward_terms, done) of one evaluation)."""
+    O, om, cores = _oracle_and_model()
+    cpu_t = lambda name: getattr(mlib, name).detach().cpu().contiguous()
+    tb = O.FrameTables(root_pos=cpu_t("_frame_root_pos"), root_rot=cpu_t("_frame_root_rot"),
+                       joint_rot=cpu_t("_frame_joint_rot"), root_vel=cpu_t("_frame_root_vel"),
+                       root_ang_vel=cpu_t("_frame_root_ang_vel"), dof_vel=cpu_t("_frame_dof_vel"),
+                       contacts=cpu_t("_frame_contacts"), frames=torch.zeros(0), num_frames=cpu_t("_motion_num_frames"),
+                       start_idx=cpu_t("_motion_start_idx"), lengths=cpu_t("_motion_lengths"),
+                       loop_modes=cpu_t("_motion_loop_modes"), root_pos_delta=cpu_t("_motion_root_pos_delta"),
+                       weights=cpu_t("_motion_weights"), fps=cpu_t("_motion_fps"), dt=1.0 / cpu_t("_motion_fps"))
+    o_terr = O.Terrain(hf=torch.from_numpy(hf_np), min_point=torch.zeros(2), dxdy=torch.tensor([hf_dx, hf_dx]))
+    c = [None if t is None else t.detach().cpu() for t in state]
+    n, S = int(ids.shape[0]), int(time_offsets.shape[0]) - 1
+    kid = torch.tensor(key_ids)
+
+    def step():
+        ids_t = ids.unsqueeze(-1).expand(n, S + 1).flatten()
+        times_t = (times.unsqueeze(-1) + time_offsets).flatten()
+        f = list(O.calc_motion_frame(tb, ids_t, times_t))
+        f[0] = f[0].clone()
+        f[0][:, 0:2] += xy_offset.repeat_interleave(S + 1, dim=0)
+        bp = O.forward_kinematics(om, f[0], f[1], f[4])[0]
+        v = lambda t: t.view(n, S + 1, *t.shape[1:])
+        rp, rr, rv, rw, jr, dv, ct, bpv = (v(t) for t in (f[0], f[1], f[2], f[3], f[4], f[5], f[6], bp))
+        sjr = O.dof_to_rot(om, c[4])
+        char = O.compute_char_obs(c[0], c[1], c[2], c[3], sjr, c[5], c[6][:, kid], False, False)
+        tar = O.compute_tar_obs(c[0], c[1], rp[:, 1:], rr[:, 1:], jr[:, 1:], bpv[:, 1:][:, :, kid], False, False)
+        ray = O.ray_obs(o_terr, c[0] + c[9], O.calc_heading(c[1]), tmpl)
+        obs = torch.cat([char, tar.reshape(n, -1), ct[:, 1:].reshape(n, -1), c[10], ray], dim=-1)
+        rew = O.compute_deepmimic_reward(c[0], c[1], c[2], c[3], sjr, c[5], c[6][:, kid], rp[:, 0], rr[:, 0], rv[:, 0],
+                                         rw[:, 0], jr[:, 0], dv[:, 0], bpv[:, 0][:, kid], joint_w, dof_w, True, True)
+        th = O.termination_heights(o_terr, c[6], c[9], 0.15)
+        done = O.compute_done(torch.zeros(n, dtype=torch.int), c[8], 10.0, c[1], c[6], rr[:, 0], bpv[:, 0], c[7],
+                              torch.tensor(feet), th, True, pose_dist, True, True, 0.6, 1.309)
+        return obs, rew, done
+
+    first = step()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        best = min(best, time.perf_counter() - t0)
+    return best, cores, first
+
+
+# ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
 def bind_to_gpu_numa_node(local_rank):

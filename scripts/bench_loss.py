@@ -80,28 +80,15 @@ def main():
         torch.cuda.synchronize()
     ms_fwd = e0.elapsed_time(e1) / args.steps
 
-    # CPU oracle on a sub-sample
-    from oracle import parc_oracle as O
-    om = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cb, cf = args.cpu_samples, args.cpu_frames
-    t0 = time.perf_counter()
-    for i in range(cb):
-        a = torch.tensor(smp["root_pos"][i, :cf]).requires_grad_(True)
-        b = torch.tensor(smp["root_exp"][i, :cf]).requires_grad_(True)
-        c = torch.tensor(smp["joint_dof"][i, :cf]).requires_grad_(True)
-        loss, _, _ = O.motion_opt_pen_contact(om, a, b, c, torch.tensor(smp["contacts"][i, :cf]), torch.tensor(hfs[i]),
-                                              torch.zeros(2), torch.tensor([0.4, 0.4]), 0.1, 0.1)
-        loss.backward()
-    cpu_s = time.perf_counter() - t0
-    cpu_samples_per_s = cb * (cf / F) / cpu_s          # linear in frames
+    # CPU leg (oracle port) on a sub-sample: lives in bench.py, the one place that may execute oracle/
+    import bench
+    cpu = bench.cpu_leg_loss(smp, hfs, args.cpu_samples, args.cpu_frames, F)
+    cpu_samples_per_s = cpu["samples_per_s"]
     print(json.dumps({
         "workload": f"cfg3: pen/contact loss fwd+bwd, B={B} samples x F={F} frames, 304 body points, 16x16 terrain/sample",
         "gpu_ms_fwd_bwd": ms, "gpu_ms_fwd": ms_fwd, "samples_per_s_fwd_bwd": B / (ms * 1e-3),
         "point_cell_evals_per_s": evals / (ms * 1e-3),
-        "cpu_oracle": {"samples_per_s": cpu_samples_per_s, "cores": cores,
-                       "sample": f"{cb} sample(s) x {cf} frames fwd+bwd, scaled linearly to {F} frames"},
+        "cpu_oracle": cpu,
         "speedup_vs_cpu": (B / (ms * 1e-3)) / cpu_samples_per_s}))
 
 

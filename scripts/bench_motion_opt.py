@@ -53,15 +53,8 @@ def main():
     s_graph, out_g = run(True, args.iters)
     s_eager, out_e = run(False, args.iters)
 
-    from oracle import parc_oracle as O
-    om = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    fr_c, ct_c = frames.cpu(), contacts.cpu()
-    t0 = time.perf_counter()
-    O.motion_contact_optimization(om, fr_c, ct_c, torch.tensor(civ["hf"]), torch.zeros(2), torch.tensor([0.4, 0.4]), 1, 0.001,
-                                  W, 1000.0)
-    cpu_iter_s = time.perf_counter() - t0
+    import bench          # the CPU leg (oracle port) lives in bench.py, the one place that may execute oracle/
+    cpu_iter_s, cores = bench.cpu_leg_motion_opt(frames.cpu(), contacts.cpu(), torch.tensor(civ["hf"]), W)
     print(json.dumps({
         "workload": f"motion_contact_optimization: 254-frame clip, 50x50 terrain, {args.iters} Adam iterations, all loss terms",
         "gpu_ms_per_iter_cuda_graph": s_graph / args.iters * 1e3, "gpu_ms_per_iter_eager": s_eager / args.iters * 1e3,

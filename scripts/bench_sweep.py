@@ -64,36 +64,16 @@ def main():
     ms_full = timed(lambda: label_clips(frames, tb, km, body_points=pts, want_masks=True, want_body_hf=True, want_fk=True),
                     args.steps)
     n_frames = B * F
-    # CPU oracle
-    from oracle import parc_oracle as O
-    om = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
-    g = np.load(os.path.join(ROOT, "tests", "golden", "label_golden.npz"))
-    feet = [(int(b), h.tolist(), o.tolist()) for b, h, o in zip(g["feet_body"], g["feet_half"], g["feet_offset"])]
-    hands = [(int(b), float(r)) for b, r in zip(g["hands_body"], g["hands_radius"])]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    t0 = time.perf_counter()
-    for i in range(args.cpu_clips):
-        f_i = torch.tensor(fr_np[i])
-        t = O.Terrain(hf=torch.tensor(base_hf[(i // 4) % 64]), min_point=torch.zeros(2), dxdy=torch.tensor([0.4, 0.4]))
-        O.frames_fk(om, f_i)
-        O.foot_contacts_and_pen(om, f_i, t, feet)
-        O.hand_contacts(om, f_i, t, hands)
-    cpu_label_s = (time.perf_counter() - t0) / args.cpu_clips
-    t0 = time.perf_counter()
-    O.hf_mask_inds(om, torch.tensor(fr_np[0]), O.Terrain(hf=torch.tensor(base_hf[0]), min_point=torch.zeros(2),
-                                                       dxdy=torch.tensor([0.4, 0.4])))
-    cpu_mask_s = time.perf_counter() - t0
+    # CPU leg (oracle port): lives in bench.py, the one place that may execute oracle/
+    import bench
+    cpu = bench.cpu_leg_sweep(fr_np, base_hf, args.cpu_clips, F)
     out = {
         "workload": f"cfg5 shard: {B} clips x {F} frames ({n_frames} character-frames), one 16x16 terrain per clip",
         "fk_only": {"ms": ms_fk, "body_frames_per_s": n_frames * 15 / (ms_fk * 1e-3),
                     "achieved_GBps": n_frames * 556 / (ms_fk * 1e-3) / 1e9, "algorithmic_bytes_per_char_frame": 556},
         "fk_contacts_bodyhf": {"ms": ms_label, "body_frames_per_s": n_frames * 15 / (ms_label * 1e-3)},
         "fk_contacts_bodyhf_masks": {"ms": ms_full, "body_frames_per_s": n_frames * 15 / (ms_full * 1e-3)},
-        "cpu_oracle": {"cores": cores, "label_s_per_clip": cpu_label_s, "mask_s_per_clip": cpu_mask_s,
-                       "body_frames_per_s_label": F * 15 / cpu_label_s,
-                       "sample": f"{args.cpu_clips} clips (FK + foot + hand labels), 1 clip (masks; vectorised restatement "
-                                 "-- the reference's python triple loop is ~14 ms/frame, SURVEY section 6)"},
+        "cpu_oracle": cpu,
     }
     out["speedup_label_vs_cpu"] = out["fk_contacts_bodyhf"]["body_frames_per_s"] / out["cpu_oracle"]["body_frames_per_s_label"]
     print(json.dumps(out))

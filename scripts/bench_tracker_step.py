@@ -124,56 +124,14 @@ def main():
     b = bytes_per_env_step(J, D, K, S, P)
     assert res["obs"].shape[1] == b["obs_width"]
 
-    # ---- CPU: the same sequence from the oracle, all host cores ----
-    from oracle import parc_oracle as O
-    om = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cpu_t = lambda name: getattr(mlib, name).cpu()
-    tb = O.FrameTables(root_pos=cpu_t("_frame_root_pos"), root_rot=cpu_t("_frame_root_rot"),
-                       joint_rot=cpu_t("_frame_joint_rot"), root_vel=cpu_t("_frame_root_vel"),
-                       root_ang_vel=cpu_t("_frame_root_ang_vel"), dof_vel=cpu_t("_frame_dof_vel"),
-                       contacts=cpu_t("_frame_contacts"), frames=torch.zeros(0), num_frames=cpu_t("_motion_num_frames"),
-                       start_idx=cpu_t("_motion_start_idx"), lengths=cpu_t("_motion_lengths"),
-                       loop_modes=cpu_t("_motion_loop_modes"), root_pos_delta=cpu_t("_motion_root_pos_delta"),
-                       weights=cpu_t("_motion_weights"), fps=cpu_t("_motion_fps"), dt=1.0 / cpu_t("_motion_fps"))
-    o_terr = O.Terrain(hf=torch.from_numpy(hf_np), min_point=torch.zeros(2), dxdy=torch.tensor([HF_DX, HF_DX]))
-    c = [t.cpu() for t in state]
-    xy = ts.motion_xy_offset.cpu()
-    offs = ts.time_offsets.cpu()
-    kid = torch.tensor(key_ids)
-    dw = ts.dof_err_w.cpu()
-    tm_cpu = tmpl.cpu()
-
-    def cpu_step():
-        ids_t = ids.unsqueeze(-1).expand(n, S + 1).flatten()
-        times_t = (times.unsqueeze(-1) + offs).flatten()
-        f = list(O.calc_motion_frame(tb, ids_t, times_t))
-        f[0] = f[0].clone()
-        f[0][:, 0:2] += xy.repeat_interleave(S + 1, dim=0)
-        bp = O.forward_kinematics(om, f[0], f[1], f[4])[0]
-        v = lambda t: t.view(n, S + 1, *t.shape[1:])
-        rp, rr, rv, rw, jr, dv, ct, bpv = (v(t) for t in (f[0], f[1], f[2], f[3], f[4], f[5], f[6], bp))
-        sjr = O.dof_to_rot(om, c[4])
-        char = O.compute_char_obs(c[0], c[1], c[2], c[3], sjr, c[5], c[6][:, kid], False, False)
-        tar = O.compute_tar_obs(c[0], c[1], rp[:, 1:], rr[:, 1:], jr[:, 1:], bpv[:, 1:][:, :, kid], False, False)
-        ray = O.ray_obs(o_terr, c[0] + c[9], O.calc_heading(c[1]), tm_cpu)
-        obs = torch.cat([char, tar.reshape(n, -1), ct[:, 1:].reshape(n, -1), c[10], ray], dim=-1)
-        rew = O.compute_deepmimic_reward(c[0], c[1], c[2], c[3], sjr, c[5], c[6][:, kid], rp[:, 0], rr[:, 0], rv[:, 0],
-                                         rw[:, 0], jr[:, 0], dv[:, 0], bpv[:, 0][:, kid], jw, dw, True, True)
-        th = O.termination_heights(o_terr, c[6], c[9], 0.15)
-        done = O.compute_done(torch.zeros(n, dtype=torch.int), c[8], 10.0, c[1], c[6], rr[:, 0], bpv[:, 0], c[7],
-                              torch.tensor(feet), th, True, ptd, True, True, 0.6, 1.309)
-        return obs, rew, done
-
+    # ---- CPU: the same sequence composed from the oracle on all host cores (the leg lives in bench.py, the one
+    #      place that may execute oracle/) ----
     cpu = None
     if not args.no_cpu:
-        o_obs, o_rew, o_done = cpu_step()
-        best = 1e9
-        for _ in range(args.cpu_reps):
-            t0 = time.perf_counter()
-            cpu_step()
-            best = min(best, time.perf_counter() - t0)
+        import bench
+        best, cores, (o_obs, o_rew, o_done) = bench.cpu_leg_tracker_step(
+            mlib, hf_np, HF_DX, state, ids, times, ts.motion_xy_offset.cpu(), ts.time_offsets.cpu(), key_ids, feet, jw,
+            ts.dof_err_w.cpu(), ptd, tmpl.cpu(), args.cpu_reps)
         cpu = dict(cores=cores, ms_per_step=best * 1e3, env_steps_per_s=n / best,
                    sample=f"the full {n}-env step, best of {args.cpu_reps}, oracle composition (torch CPU fp32)",
                    obs_max_abs_diff=float((res["obs"].cpu() - o_obs).abs().max()),

@@ -120,9 +120,23 @@ def test_product_never_imports_the_oracle():
     import subprocess
     import sys
     code = ("import sys; sys.path.insert(0, %r); import parc_b200.anim.motion_lib, parc_b200.tools.procgen.mdm_path, "
-            "parc_b200.tools.motion_opt.motion_optimization, parc_b200.envs.ig_parkour.mgdm_dm_util, parc_b200.sharding; "
+            "parc_b200.tools.motion_opt.motion_optimization, parc_b200.envs.ig_parkour.mgdm_dm_util, parc_b200.sharding, "
+            "parc_b200.envs.ig_parkour.step_assembly, parc_b200.envs.ig_char_env, parc_b200.anim.packed_format, "
+            "parc_b200.zmotion_editing_tools.motion_edit_lib; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True)
+    # statically: outside tests/, oracle/ itself, smoke() in __graft_entry__.py and the CPU legs of bench.py, no
+    # python file of the repository names the oracle package in an import
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for dirpath, dirnames, files in os.walk(ROOT):
+        dirnames[:] = [d for d in dirnames if d not in (".git", "tests", "oracle", "gpurun_out", "__pycache__", "baseline")]
+        for f in files:
+            if f.endswith(".py") and os.path.join(dirpath, f) not in (os.path.join(ROOT, "bench.py"),
+                                                                       os.path.join(ROOT, "__graft_entry__.py")):
+                if pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert not offenders, offenders
     for dirpath, _, files in os.walk(os.path.join(ROOT, "parc_b200")):
         for f in files:
             if f.endswith(".py"):
