@@ -345,6 +345,28 @@ class MotionQueryPlan:
             check(rc, "parc_motion_query")
         return self.out
 
+    def capture(self) -> "torch.cuda.CUDAGraph":
+        """Record the launch in a CUDA graph (one kernel node).  `replay()` then costs a graph launch, which on
+        B200 reaches the SMs ~1.8 us sooner than a stream launch of the same kernel (measured: 5.6 vs 7.5 us event
+        to event for an empty kernel of this grid) -- a tenth of the whole 4096-env query.  The buffers the plan was
+        built over stay the inputs / outputs of every replay."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self.launch()                                   # warm-up outside the capture
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.launch()
+        return self._graph
+
+    def replay(self) -> dict:
+        """Re-run the captured launch on torch's current stream (call `capture()` once first)."""
+        self._graph.replay()
+        _lib.LAUNCHES[0] += 1
+        return self.out
+
 
 # ----------------------------------------------------------------------------------------------
 # a6: forward kinematics (differentiable)
