@@ -119,8 +119,9 @@ char_obs_kernel(const __grid_constant__ ParcCharState s, int64_t n, int Jm1, int
 
 // ------------------------------------------------------------------------------------------------
 // compute_tar_obs: per (env, step)  root_pos_obs 3 | root tan-norm 6 | joint tan-norm 6(J-1) | key 3K
-// One warp per env: the character's heading frame is resolved once, then the lanes stride over the env's
-// S * (1 + (J-1) + K) work items (root, joint, key body of each step), so all 32 lanes stay busy.
+// One warp per env; the lanes stride over the env's work items so all 32 stay busy: first the S * (J-1) joint
+// encodings (they do not depend on the character, so they cover the latency of its root load and of the
+// atan2 / sincos chain of the heading frame), then the S * (1 + K) root / key-body items in that frame.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS)
 tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__ ref_root_rot,
@@ -131,24 +132,29 @@ tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__
                int64_t out_env_stride) {
   const int lane = threadIdx.x & 31;
   const int W = 9 + 6 * Jm1 + 3 * K;
-  const int per_step = 1 + Jm1 + K;
-  const int items = S * per_step;
+  const int joint_items = S * Jm1;            // independent of the character's frame: done first
+  const int frame_items = S * (1 + K);        // root + key bodies of each step: need the heading frame
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
+    // the character's root is requested first and consumed last: the joint encodings below hide its latency
     const float3 cp = ld3(ref_root_pos + e * 3);
-    float4 hinv = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (!global_obs) hinv = heading_inverse_quat(ld4(ref_root_rot + e * 4));
+    float4 cq = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (!global_obs) cq = ld4(ref_root_rot + e * 4);
     float* __restrict__ oe = out + e * out_env_stride;
-    for (int it = lane; it < items; it += 32) {
-      const int st = it / per_step;
-      const int w = it - st * per_step;                      // 0 = root, 1..J-1 = joints, then key bodies
+    for (int it = lane; it < joint_items; it += 32) {
+      const int st = it / Jm1;
+      const int j = it - st * Jm1;
       const int64_t r = e * tar_env_stride + st;             // row of this (env, step) in the target arrays
+      store_tan_norm(oe + (int64_t)st * W + 9 + 6 * j, ld4(tar_joint_rot + (r * Jm1 + j) * 4));
+    }
+    float4 hinv = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (!global_obs) hinv = heading_inverse_quat(cq);
+    for (int it = lane; it < frame_items; it += 32) {
+      const int st = it / (1 + K);
+      const int w = it - st * (1 + K);                       // 0 = root, 1.. = key bodies
+      const int64_t r = e * tar_env_stride + st;
       float* __restrict__ o = oe + (int64_t)st * W;
-      if (w >= 1 && w <= Jm1) {
-        store_tan_norm(o + 9 + 6 * (w - 1), ld4(tar_joint_rot + (r * Jm1 + (w - 1)) * 4));
-        continue;
-      }
       const float3 tp = ld3(tar_root_pos + r * 3);
       float3 po = sub3(tp, cp);
       if (!global_obs) po = quat_rotate(hinv, po);
@@ -158,7 +164,7 @@ tar_obs_kernel(const float* __restrict__ ref_root_pos, const float* __restrict__
         st3(o, make_float3(po.x, po.y, global_tar_root_h ? tp.z : po.z));
         store_tan_norm(o + 3, tr);
       } else {
-        const int k = w - 1 - Jm1;
+        const int k = w - 1;
         float3 p = sub3(key_position(tar_key_pos, key_body_ids, num_bodies, K, e * S + st, r, k), tp);
         if (!global_obs) {
           p = quat_rotate(hinv, p);
