@@ -19,6 +19,9 @@ python scripts/bench_tracker_step.py > gpurun_out/bench_tracker_step.log 2>&1; t
 python scripts/bench_loader.py > gpurun_out/bench_loader.log 2>&1; tail -1 gpurun_out/bench_loader.log
 CMD3="python scripts/bench_tracker_step.py --steps 3 --no-cpu"
 $CMD3 > gpurun_out/plain4.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}_step.csv $CMD3 > gpurun_out/ncu_list_step.log 2>&1
+$CMD3 > gpurun_out/plain5.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"sim_step|tar_obs|hf_obs" -s 12 -c 6 -f -o gpurun_out/prof_${TAG}_step $CMD3 > gpurun_out/ncu_full_step.log 2>&1
+CMD5="python scripts/bench_loader.py --clips 1024 --host-clips 16"
+$CMD5 > gpurun_out/plain6.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:build_tables -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_loader $CMD5 > gpurun_out/ncu_full_loader.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log
 python - <<'PY'
 import json
