@@ -347,7 +347,6 @@ def main():
         dist.init_process_group(backend="nccl", device_id=dev)
 
     import __graft_entry__ as entry
-    from parc_b200 import ops
     from parc_b200.anim.kin_char_model import KinCharModel
     from parc_b200.anim.motion_lib import LoopMode, MotionLib
     from parc_b200.util import geom_util

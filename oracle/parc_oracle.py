@@ -22,7 +22,6 @@ Conventions: quaternions are xyzw, z is up, `hf[ix, iy]` is x-major and cell
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 

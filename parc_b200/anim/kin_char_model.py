@@ -10,7 +10,7 @@ from __future__ import annotations
 import copy
 import enum
 import xml.etree.ElementTree as ET
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 import torch

@@ -7,7 +7,7 @@ and the CUDA path are fed bit-identical inputs; nothing here is on the hot path.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

@@ -11,7 +11,6 @@ import sys
 import tempfile
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ASSET, ROOT, golden, lib_clips_from_golden, write_clip_library
+from conftest import ROOT, golden, lib_clips_from_golden, write_clip_library
 
 
 def T(x):
