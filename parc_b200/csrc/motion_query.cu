@@ -23,6 +23,7 @@ struct QueryParams {
   const float* xy_offset;   // [entries,2] added to root xy after the query (dm_env.py:604-615) or nullptr
   int num_steps;            // queries per (id, time) entry; query q = entry * num_steps + step
   int64_t n;                // total queries = entries * num_steps
+  int64_t entries;
   ParcRowLayout lay;
   ParcFrameOut out;
   ParcFkOut fk;
@@ -32,6 +33,19 @@ struct QueryParams {
   int want_fk;
   int want_obs;
 };
+
+// Work item -> (entry, step).  In the tracker-step form the items are ordered so that all step-0 queries -- the only
+// ones that sweep the observation template -- come first and share warps with each other: a warp then either sweeps
+// for both of its characters or for neither, instead of idling one half-warp through the other's sweep.
+__device__ __forceinline__ void decode_item(int64_t idx, int64_t entries, int S, int64_t& entry, int& step) {
+  entry = idx;
+  step = 0;
+  if (S > 1 && idx >= entries) {
+    const int64_t r = idx - entries;
+    entry = r / (S - 1);
+    step = 1 + (int)(r - entry * (S - 1));
+  }
+}
 
 // anim/motion_lib.py:527-538 + :443-456.  All ops individually rounded; indices are exact.
 __device__ __forceinline__ void frame_blend(const ParcClipMeta& cm, float t, int64_t& i0, int64_t& i1,
@@ -100,7 +114,7 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // sweep in flight) for launches that fit one wave and are latency-bound; 12 (<= 85 registers, half a
 // sweep in flight) for large launches, which are issue-bound and want more warps per scheduler.
 // (A middle point, whole sweep at <= 102 registers, spills and measured slower: profiles/README.md.)
-template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool XYOFF>
+template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p) {
   __shared__ TreeSmem sm;
@@ -123,7 +137,9 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
   int64_t f_pre = 0;
   {
     const int64_t q0 = first + grp < p.n ? first + grp : p.n - 1;
-    const int64_t e0 = p.num_steps > 1 ? q0 / p.num_steps : q0;
+    int64_t e0 = p.num_steps > 1 ? q0 / p.num_steps : q0;
+    int s0 = 0;
+    if (STEPFORM) decode_item(q0, p.entries, p.num_steps, e0, s0);
     id_pre = __ldg(p.ids + e0);
     if (BLEND) t_pre = __ldg(p.times + e0); else f_pre = __ldg(p.frame_idx + e0);
   }
@@ -160,11 +176,14 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
   for (int64_t base = first; base < p.n; base += stride) {
     const int64_t qq = base + grp;
     const bool active = qq < p.n;
-    const int64_t q = active ? qq : p.n - 1;
     // ---- clip metadata + frame indices (uniform within the group) ----
-    // entry (env) and step of this query: q = entry * num_steps + step
-    const int64_t entry = p.num_steps > 1 ? q / p.num_steps : q;
-    const int step = (int)(q - entry * p.num_steps);
+    // entry (env) and step of this work item; its output row is q = entry * num_steps + step
+    // (the plain instantiation keeps the natural order q = item: its register allocation is the tuned one)
+    const int64_t item = active ? qq : p.n - 1;
+    int64_t entry = p.num_steps > 1 ? item / p.num_steps : item;
+    int step = (int)(item - entry * p.num_steps);
+    if (STEPFORM) decode_item(item, p.entries, p.num_steps, entry, step);
+    const int64_t q = STEPFORM ? entry * p.num_steps + step : item;
     int64_t id = id_pre;
     float t_q = t_pre;
     int64_t f_q = f_pre;
@@ -176,7 +195,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     if (BLEND && p.offsets) t_q = add_rn(t_q, __ldg(p.offsets + step));
     // where the env's motion sits on the shared terrain (_move_to_motion_terrain, dm_env.py:604-615): root lane only
     float2 xy_off = make_float2(0.0f, 0.0f);
-    if (XYOFF && l == 0) xy_off = __ldg(reinterpret_cast<const float2*>(p.xy_offset) + entry);
+    if (STEPFORM && p.xy_offset && l == 0) xy_off = __ldg(reinterpret_cast<const float2*>(p.xy_offset) + entry);
     if (id < 0 || id >= p.tb.num_clips) id = 0;   // reference would raise an index error
     const int4* cmp = reinterpret_cast<const int4*>(p.tb.clips + id);
     const int4 c0 = __ldg(cmp);
@@ -227,7 +246,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
         }
       }
     }
-    if (XYOFF && l == 0) {                           // pos + offset: one fp32 add per component, as there
+    if (STEPFORM && p.xy_offset && l == 0) {         // pos + offset: one fp32 add per component, as there
       R.x = add_rn(R.x, xy_off.x);
       R.y = add_rn(R.y, xy_off.y);
     }
@@ -580,7 +599,7 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   if (!aligned16(tables->tree)) return PARC_E_ALIGN;
   p.tb = *tables;
   p.ids = ids; p.times = times; p.frame_idx = frame_idx; p.n = n;
-  p.offsets = offsets; p.num_steps = num_steps;
+  p.offsets = offsets; p.num_steps = num_steps; p.entries = n_entries;
   if ((reinterpret_cast<uintptr_t>(xy_offset) & 7u) != 0) return PARC_E_ALIGN;
   p.xy_offset = xy_offset;
   ParcFrameOut none = {};
@@ -625,11 +644,14 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool rel = p.want_obs && p.obs.relative != 0;
-  // XYOFF is a template flag: the two extra live registers of the offset would otherwise spill in the 80-register
-  // large-batch variant (measured: -4 % at 65 536 envs) for callers that never pass one.
+  // STEPFORM is a template flag: the per-entry xy offset and the step-0-first item order cost live registers that
+  // spill in the 64-register large-batch variant (measured: -2..4 % at 65 536 envs when they were run-time
+  // branches), so the plain one-query-per-entry call runs an instantiation without them -- whose code must stay
+  // exactly the tuned one: making `step` a compile-time 0 there changed the schedule and cost 13 %.
+  const bool step_form = blend && (p.num_steps > 1 || p.xy_offset);
 #define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB)                                                        \
   do {                                                                                              \
-    if (B && p.xy_offset) motion_query_kernel<B, GG, NF, RL, MB, B><<<grid, QUERY_CTA_THREADS, smem, st>>>(p); \
+    if (B && step_form) motion_query_kernel<B, GG, NF, RL, MB, B><<<grid, QUERY_CTA_THREADS, smem, st>>>(p);   \
     else motion_query_kernel<B, GG, NF, RL, MB, false><<<grid, QUERY_CTA_THREADS, smem, st>>>(p);              \
   } while (0)
   if (blend) {
