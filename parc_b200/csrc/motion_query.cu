@@ -412,11 +412,22 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
             z[u] = __ldg(hfp + obs_cell(oc, tmpl[k < P ? k : l]));
           }
         }
+        float* __restrict__ ok = o + k0;        // one pointer per pass: the stores below use immediate offsets
+        if (k0 + G * INFLIGHT <= P) {           // a full pass: no bounds checks
 #pragma unroll
-        for (int u = 0; u < INFLIGHT; ++u) {
-          float v = z[u];
-          if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
-          if (k0 + l + G * u < P) o[k0 + G * u] = v;
+          for (int u = 0; u < INFLIGHT; ++u) {
+            float v = z[u];
+            if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+            ok[G * u] = v;
+          }
+        } else {
+          const int left = P - k0 - l;          // this lane's valid samples are those with G * u < left
+#pragma unroll
+          for (int u = 0; u < INFLIGHT; ++u) {
+            float v = z[u];
+            if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+            if (G * u < left) ok[G * u] = v;
+          }
         }
       }
     }
