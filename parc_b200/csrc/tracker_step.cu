@@ -33,10 +33,20 @@ __device__ __forceinline__ float4 heading_inverse_quat(const float4& q) {
   return axis_angle_to_quat(make_float3(0.0f, 0.0f, 1.0f), -calc_heading(q));
 }
 
-// util/torch_util.py:361-373: rotated x axis, then rotated z axis
+// util/torch_util.py:361-373: rotated x axis, then rotated z axis.  quat_rotate (v + w t + q_v x t, t = 2 q_v x v)
+// written out for v = e_x and v = e_z: the terms the general form multiplies by an exact 0 are dropped -- they
+// contribute exact zeros for finite q -- which is a third of the instructions.
 __device__ __forceinline__ void store_tan_norm(float* __restrict__ o, const float4& q) {
-  st3(o, quat_rotate(q, make_float3(1.0f, 0.0f, 0.0f)));
-  st3(o + 3, quat_rotate(q, make_float3(0.0f, 0.0f, 1.0f)));
+  // v = e_x: q_v x v = (0, z, -y), t = (0, 2z, -2y), q_v x t = (y ty... ) = (-2y^2 - 2z^2, 2xy, 2xz)
+  {
+    const float ty = 2.0f * q.z, tz = -2.0f * q.y;
+    st3(o, make_float3(1.0f + (q.y * tz - q.z * ty), q.w * ty + (-q.x * tz), q.w * tz + (q.x * ty)));
+  }
+  // v = e_z: q_v x v = (y, -x, 0), t = (2y, -2x, 0), q_v x t = (-z ty.. ) = (2xz, 2yz, -2x^2 - 2y^2)
+  {
+    const float tx = 2.0f * q.y, ty = -2.0f * q.x;
+    st3(o + 3, make_float3(q.w * tx + (-q.z * ty), q.w * ty + (q.z * tx), 1.0f + (q.x * ty - q.y * tx)));
+  }
 }
 
 // util/torch_util.py:422-431 with :68-88: angle of q1 * conj(q0), w made non-negative, 0 below 1e-5
@@ -371,17 +381,23 @@ struct SimStepParams {
   DoneParams done;
 };
 
-__global__ void __launch_bounds__(STEP_THREADS)
+// 7 CTAs x 4 warps per SM = 28 resident warps: exactly one wave for 4096 envs on 148 SMs (27.7 warps per SM); at 80
+// registers only 6 CTAs fit and the kernel needs a second wave (+8 us measured).
+__global__ void __launch_bounds__(STEP_THREADS, 7)
 sim_step_kernel(const __grid_constant__ SimStepParams p, const __grid_constant__ ParcCharModel model_param, int64_t n) {
-  __shared__ ParcCharModel sm;
-  stage_model(&sm, model_param);
-  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int J = sm.num_bodies, Jm1 = J - 1, D = sm.dof_size;
-  // lane j (< J-1) owns joint j + 1
+  const int J = model_param.num_bodies, Jm1 = J - 1, D = model_param.dof_size;
+  // lane j (< J-1) owns joint j + 1: its five constants are read once, straight from the kernel parameter (staging
+  // the whole 1.4 KB model through shared memory held 21 % of this kernel's stall samples)
   int jt = PARC_JOINT_FIXED, didx = 0;
-  const float* axis = sm.joint_axis[0];
-  if (lane < Jm1) { jt = sm.joint_type[lane + 1]; didx = sm.dof_idx[lane + 1]; axis = sm.joint_axis[lane + 1]; }
+  float axis[3] = {0.0f, 0.0f, 1.0f};
+  if (lane < Jm1) {
+    jt = model_param.joint_type[lane + 1];
+    didx = model_param.dof_idx[lane + 1];
+    axis[0] = model_param.joint_axis[lane + 1][0];
+    axis[1] = model_param.joint_axis[lane + 1][1];
+    axis[2] = model_param.joint_axis[lane + 1][2];
+  }
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
