@@ -420,6 +420,17 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
             if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
             ok[G * u] = v;
           }
+        } else if (P - k0 >= G * (INFLIGHT - 1)) {
+          // only the last sample of the pass can be out of range (the 441-point fan: 105 samples left, 7 * 16 slots)
+#pragma unroll
+          for (int u = 0; u < INFLIGHT - 1; ++u) {
+            float v = z[u];
+            if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+            ok[G * u] = v;
+          }
+          float v = z[INFLIGHT - 1];
+          if (RELATIVE) v = fminf(fmaxf(sub_rn(v, root_z), lo), hi);
+          if (k0 + l + G * (INFLIGHT - 1) < P) ok[G * (INFLIGHT - 1)] = v;
         } else {
           const int left = P - k0 - l;          // this lane's valid samples are those with G * u < left
 #pragma unroll
