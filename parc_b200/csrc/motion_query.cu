@@ -111,9 +111,9 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 #define QUERY_CTA_THREADS (QUERY_WARPS_PER_CTA * 32)
 
 // MINB = resident CTAs per SM the register allocation must allow: 8 (<= 128 registers, whole template
-// sweep in flight) for launches that fit one wave and are latency-bound; 12 (<= 85 registers, half a
-// sweep in flight) for large launches, which are issue-bound and want more warps per scheduler.
-// (A middle point, whole sweep at <= 102 registers, spills and measured slower: profiles/README.md.)
+// sweep in flight) for launches that fit one wave and are latency-bound; 16 (64 registers, a quarter of the
+// sweep = 7 gathers in flight) for large launches, which are issue-bound and want more warps per scheduler.
+// (Middle points -- whole sweep at <= 102 registers, half a sweep at <= 85 -- measured slower: profiles/README.md.)
 template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p) {
