@@ -1495,3 +1495,28 @@ def test_query_accepts_any_leading_shape_and_int32_ids(golden_lib):
     assert g[5].shape == (4, 5, 28)
     i0, i1, bl = golden_lib._calc_frame_blend(ids, times)
     assert i0.shape == (4, 5) and i0.dtype == torch.int64 and bl.shape == (4, 5)
+
+
+@pytest.mark.parametrize("n", [500, 6000])
+def test_fused_obs_any_template_size(golden_lib, O, oracle_tables, n):
+    """The fused sweep's pass structure (whole passes without bounds checks, a partial last pass, templates shorter
+    than one pass or longer than the shared-memory staging) for template sizes around every boundary, in the
+    one-wave instantiation (n = 500: 448-sample passes) and the large-batch one (n = 6000: 112-sample passes)."""
+    from parc_b200 import ops
+    t = _civ_terrain()
+    gen = torch.Generator().manual_seed(77 + n)
+    ids = torch.randint(0, 3, (n,), generator=gen)
+    times = torch.rand(n, generator=gen) * oracle_tables.lengths[ids]
+    ref = O.calc_motion_frame(oracle_tables, ids, times)
+    ot = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
+    heading = O.calc_heading(ref[1])
+    for P in (1, 15, 16, 100, 112, 113, 200, 224, 441, 448, 449, 500, 900, 1100):
+        tmpl = (torch.rand(P, 2, generator=gen) * 2 - 1) * 3.0
+        out = golden_lib.calc_motion_frame_fk_obs(ids.cuda(), times.cuda(), hf_desc=t.hf_desc(), obs_tmpl=tmpl.cuda())
+        want = O.ray_obs(ot, ref[0], heading, tmpl)
+        got = out["obs"].cpu()
+        assert got.shape == (n, P)
+        mism = got != want
+        # a mismatch is legitimate only where sin/cos rounding moved a sample across a cell border
+        assert float(mism.float().mean()) < 2e-3, (P, float(mism.float().mean()))
+        assert torch.isfinite(got).all() and (got.abs() <= 3.0).all()
