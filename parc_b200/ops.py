@@ -1007,23 +1007,10 @@ def done_flags(time, ep_len: float, root_rot, body_pos, tar_root_rot, tar_body_p
     n, J = bp.shape[0], bp.shape[1]
     dev = bp.device
     ids = [int(i) for i in (contact_body_ids.tolist() if torch.is_tensor(contact_body_ids) else contact_body_ids)]
-    spec = ParcDoneSpec()
-    spec.episode_length = float(ep_len)
-    spec.termination_height = float(termination_height)
-    spec.root_pos_termination_dist = float(root_pos_termination_dist)
-    spec.root_rot_termination_angle = float(root_rot_termination_angle)
     ptd = f32c(pose_termination_dist) if pose_termination_dist is not None else None
     require_cuda(ptd)
-    spec.pose_termination_dist = ptr(ptd)
-    mask = 0
-    for i in ids:
-        assert 0 <= i < J
-        mask |= 1 << i
-    spec.contact_body_mask = mask
-    spec.has_contact_bodies = int(len(ids) > 0)
-    spec.pose_termination = int(bool(pose_termination))
-    spec.enable_early_termination = int(bool(enable_early_termination))
-    spec.track_root = int(bool(track_root))
+    spec = _done_spec(ep_len, termination_height, root_pos_termination_dist, root_rot_termination_angle, ptd, ids, J,
+                      pose_termination, enable_early_termination, track_root)
     rr = f32c(root_rot) if root_rot is not None else None
     tar_stride = 1
     trr = tbp = None
