@@ -383,3 +383,28 @@ def test_step_and_loader_entry_points_reject_bad_arguments(cpu_model):
     assert lib.parc_hf_obs(C.byref(hf), C.byref(ob), 4096, 3, None, None, None, 0, 4, 4096, 0, None) == -1
     assert lib.parc_hf_obs(C.byref(hf), C.byref(ob), 4096, 3, 4096, None, 4096, 2, 4, 4096, 0, None) == -2   # offset needs z
     assert lib.parc_hf_obs(C.byref(hf), C.byref(ob), 4096, 3, 4096, None, None, 0, 4, 4096, 4, None) == -2    # out_stride < P
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/parc_b200.h must compile as C99 (no C++-isms) and a plain C program
+    must link against the shared library and call a host-only entry point."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from parc_b200 import _lib
+    _lib.load()
+    src = tmp_path / "abi.c"
+    src.write_text('#include "parc_b200.h"\n'
+                   "int main(void) {\n"
+                   "  ParcCharModel m; ParcRowLayout lay; ParcSimStep s; ParcMotionTables t;\n"
+                   "  (void)s; (void)t; m.num_bodies = 0;\n"
+                   "  if (parc_abi_version() != PARC_ABI_VERSION) return 1;\n"
+                   "  if (parc_row_layout(&m, &lay) != PARC_E_MODEL) return 2;   /* 0 bodies: rejected, nothing launched */\n"
+                   "  if (sizeof(ParcClipMeta) != 32 || PARC_TREE_BYTES != 880) return 3;\n"
+                   "  return 0;\n}\n")
+    libdir = os.path.join(ROOT, "parc_b200")
+    exe = str(tmp_path / "abi")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", libdir, "-lparc_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    assert subprocess.run([exe]).returncode == 0
