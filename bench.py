@@ -6,9 +6,18 @@ each ask for one (clip id, time) frame of a library of CLIPS (default 2048) synt
 humanoid clips (packed table 2048*265*480 B = 260 MB > the 126 MB L2), get the 15-body forward
 kinematics of the blended pose and the 441-point ray heightmap observation on a 1536x1536-cell global
 heightfield.  1 character-frame = 15 body-frames.  One "step" = one pass over the batch = ONE launch of
-`motion_query_kernel` (csrc/motion_query.cu).  N > 1: every rank runs the same per-GPU workload on its
-own GPU (weak scaling, no data-path collective); NCCL only carries the barrier and the max-reduce of the
-elapsed time.
+`motion_query_kernel` (csrc/motion_query.cu); the K timed steps are one CUDA graph of K kernel nodes, each over its
+own input batch.  N > 1: every rank runs the same per-GPU workload on its own GPU (weak scaling, no data-path
+collective); NCCL only carries the barrier and the max-reduce of the elapsed time.
+
+Extra keys of the same JSON line (each a leg of this script, see DESIGN.md "Measurement"):
+  cfg4         BASELINE configs[3]: 65 536 envs -- one GPU at N = 1, split contiguously over the ranks at N > 1 with the
+               NCCL all-gather of body_pos + obs timed alone and inside a per-step figure, and the strong-scaling
+               efficiency against the same batch on one GPU measured in the same run
+  cfg5         BASELINE configs[4]: 100 000 clips x 265 frames sharded over the ranks: GPU table build + FK + contact
+               labels + heightfield samples / masks, label statistics reduced over the ranks at the end
+  tracker_step the tracker's real per-step shape (current frame + 6 look-ahead targets per env in one launch)
+  selfcheck    (N > 1) the sharded + NCCL-gathered query equals the single-GPU query bit for bit
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--clips M] [--impl reference]
 
@@ -40,19 +49,24 @@ BYTES_PER_CHAR_FRAME = 12 + 36 + 624 + 136 + 448 + 420 + 1764 + 1764   # = 5204
 HF_DIM = 1536
 HF_DX = 0.4
 L2_FLUSH_BYTES = 256 << 20
+CFG5_CLIPS_DEFAULT = 100000
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--clips", type=int, default=2048)
     ap.add_argument("--impl", default="parc_b200", choices=["parc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-soak", action="store_true", help="skip the clock-sampling soak loop (profiler runs)")
-    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of one-kernel graph replays")
+    ap.add_argument("--no-pdl", action="store_true", help="no programmatic dependent launch between the steps")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the 65 536-env (sharded) leg")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the dataset-sweep leg")
+    ap.add_argument("--cfg5-clips", type=int, default=CFG5_CLIPS_DEFAULT, help="clips of the dataset sweep (whole job)")
+    ap.add_argument("--selfcheck", action="store_true", help="run the sharded == single-GPU check also at N = 1")
     return ap.parse_args()
 
 
@@ -137,27 +151,37 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference / CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(args, frames, contacts, hf, sample_clips=64):
-    """Returns (fn(ids, times) -> None, description).  The oracle (oracle/parc_oracle.py) is the CPU
-    restatement of the reference's torch op chain: calc_motion_frame -> forward_kinematics ->
-    _refresh_ray_obs_hfs, fp32 torch CPU tensors, all host threads."""
+def cpu_reference_step_fn(frames, contacts, hf):
+    """Returns (fn(ids, times) -> (body_pos, body_rot, obs), description).  The oracle (oracle/parc_oracle.py) is the
+    CPU restatement of the reference's torch op chain: calc_motion_frame -> forward_kinematics ->
+    _refresh_ray_obs_hfs, fp32 torch CPU tensors, all host threads, over the FULL clip table of the workload."""
     from oracle import parc_oracle as O
     model = O.CharModel.from_npz(os.path.join(ROOT, "tests", "golden", "humanoid_model.npz"))
-    m = min(sample_clips, frames.shape[0])
+    m = frames.shape[0]
     tb = O.build_tables(model, [O.Clip(frames[i], contacts[i], 30.0, O.CLAMP, 1.0) for i in range(m)])
     terr = O.Terrain(hf=torch.from_numpy(hf), min_point=torch.zeros(2), dxdy=torch.tensor([HF_DX, HF_DX]))
     tmpl = O.cone_template(0.05, 2, 60, 3, 3, 0.26179938779)
 
     def step(ids, times):
-        fr = O.calc_motion_frame(tb, ids % m, times)
+        fr = O.calc_motion_frame(tb, ids, times)
         bp, br = O.forward_kinematics(model, fr[0], fr[1], fr[4])
         obs = O.ray_obs(terr, fr[0], O.calc_heading(fr[1]), tmpl)
         return bp, br, obs
 
-    return step, f"oracle port, clip ids folded onto the first {m} clips (tables are gather-only)"
+    return step, f"oracle port (torch CPU op chain of the reference) over the full {m}-clip table"
+
+
+def config_dict(args, **extra):
+    """The `config` object of the JSON line; both arms emit the same workload keys."""
+    c = {"workload": workload_name(args), "envs_per_gpu": args.envs, "clips": args.clips, "frames_per_clip": 265}
+    c.update(extra)
+    return c
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port: the reference is pure
+    Python / torch and /root/reference does not travel to the GPU box) on all host cores, same workload, metric and
+    unit; every step is one full ENVS-env pass.  Rank 0 only; other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,26 +190,24 @@ def run_reference_arm(args):
     from parc_b200.anim.kin_char_model import KinCharModel
     km = KinCharModel("cpu")
     km.load_char_file(os.path.join(ROOT, "parc_b200", "assets", "humanoid.xml"))
-    small = argparse.Namespace(**vars(args))
-    small.clips = min(args.clips, 64)
-    hf, frames, contacts = make_inputs(small, km, seed=1234)
-    step, desc = cpu_reference_step_fn(small, frames, contacts, hf)
-    ids, times = query_batches(8, args.envs, small.clips, 264.0 / 30.0, seed=77)
-    steps = min(args.steps, 40)          # bounded: each step is a full ENVS-env pass (~0.1 s on 8 cores)
-    for w in range(min(args.warmup, 3)):
-        step(ids[w % 8], times[w % 8])
+    hf, frames, contacts = make_inputs(args, km, seed=1234)
+    step, desc = cpu_reference_step_fn(frames, contacts, hf)
+    NB = 8
+    ids, times = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77)
+    steps, warmup = args.steps, args.warmup
+    for w in range(warmup):
+        step(ids[w % NB], times[w % NB])
     t0 = time.perf_counter()
     for s in range(steps):
-        step(ids[s % 8], times[s % 8])
+        step(ids[s % NB], times[s % NB])
     dt = time.perf_counter() - t0
     value = args.envs * BODIES * steps / dt
-    sample = f"{steps} steps of {args.envs} envs (full per-GPU batch) on CPU; {desc}"
+    sample = f"{steps} steps of {args.envs} envs (the full per-GPU batch) after {warmup} warm-up steps; {desc}"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "arm": "reference CPU path (oracle port; the reference is "
-                   "pure Python/torch and /root/reference is absent on the GPU box)"},
+        "config": config_dict(args, arm="reference CPU path on the host cores (rank 0 only)"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -328,23 +350,84 @@ def bind_to_gpu_numa_node(local_rank):
         return f"unchanged ({type(e).__name__})"
 
 
-def main():
-    args = parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
+class Ctx:
+    """Everything the measurement legs share: process layout, library objects, synthetic inputs."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+def dist_max(ctx, x):
+    t = torch.tensor([x], dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return t.item()
+
+
+def barrier(ctx):
+    torch.cuda.synchronize(ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.barrier()
+    torch.cuda.synchronize(ctx.dev)
+
+
+def timed_graph_steps(ctx, plans, K, warm_steps):
+    """K back-to-back steps as ONE CUDA graph of K kernel nodes (step s = plans[s % len(plans)], each over its own input
+    batch), one event pair around the replay, barrier + synchronize on both sides.  -> milliseconds for the K steps
+    (max over ranks).  Warm-up replays the same graph until at least `warm_steps` steps (and ~2 ms of work) ran."""
+    from parc_b200 import ops
+    seq = [plans[s % len(plans)] for s in range(K)]
+    graph = ops.capture_launches(seq)
+    reps = max(1, (warm_steps + K - 1) // K, 3)
+    for _ in range(reps):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream(ctx.dev)
+    barrier(ctx)
+    e0.record(stream)
+    graph.replay()
+    e1.record(stream)
+    barrier(ctx)
+    ctx.launches += K
+    return dist_max(ctx, e0.elapsed_time(e1))
+
+
+def timed_flushed_steps(ctx, plans, K, warm_steps):
+    """The conservative form: every step timed by its own event pair with a 256 MiB L2-evicting write (untimed) before
+    it; each step a one-kernel graph replay.  -> (mean ms per step max over ranks, median ms on this rank)."""
+    stream = torch.cuda.current_stream(ctx.dev)
+    for pl in plans:
+        if not hasattr(pl, "_graph"):
+            pl.capture()
+    for w in range(warm_steps):
+        ctx.flush.zero_()
+        plans[w % len(plans)].replay()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier(ctx)
+    for s in range(K):
+        ctx.flush.zero_()
+        starts[s].record(stream)
+        plans[s % len(plans)].replay()
+        stops[s].record(stream)
+    barrier(ctx)
+    per = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    return dist_max(ctx, sum(per) / K), statistics.median(per)
+
+
+def setup(args):
+    ctx = Ctx()
+    ctx.args = args
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "unchanged (single process)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
+    ctx.affinity = bind_to_gpu_numa_node(ctx.local_rank) if ctx.world > 1 else "unchanged (single process)"
+    torch.cuda.set_device(ctx.local_rank)
+    ctx.dev = dev = torch.device("cuda", ctx.local_rank)
+    ctx.dist = None
+    if ctx.world > 1:
         import torch.distributed as dist
         dist.init_process_group(backend="nccl", device_id=dev)
+        ctx.dist = dist
 
     import __graft_entry__ as entry
     from parc_b200.anim.kin_char_model import KinCharModel
@@ -353,144 +436,82 @@ def main():
     from parc_b200.util.terrain_util import SubTerrain
     entry.ensure_built()
 
-    km = KinCharModel(dev)
+    ctx.km = km = KinCharModel(dev)
     km.load_char_file(os.path.join(ROOT, "parc_b200", "assets", "humanoid.xml"))
-    hf_np, frames, contacts = make_inputs(args, km, seed=1234)
+    ctx.hf_np, ctx.frames, ctx.contacts = make_inputs(args, km, seed=1234)
     # CUDA frames -> the tables are built on the GPU (no host table building at start-up)
-    mlib = MotionLib(torch.from_numpy(frames).to(dev), km, dev, init_type="motion_frames", loop_mode=LoopMode.CLAMP,
-                     fps=30, contact_info=True, contacts=torch.from_numpy(contacts).to(dev))
+    ctx.mlib = MotionLib(torch.from_numpy(ctx.frames).to(dev), km, dev, init_type="motion_frames",
+                         loop_mode=LoopMode.CLAMP, fps=30, contact_info=True,
+                         contacts=torch.from_numpy(ctx.contacts).to(dev))
     terrain = SubTerrain("global", x_dim=HF_DIM, y_dim=HF_DIM, dx=HF_DX, dy=HF_DX, min_x=0.0, min_y=0.0, device=dev)
-    terrain.hf = torch.from_numpy(hf_np).to(dev)
-    hfd = terrain.hf_desc()
-    tmpl = geom_util.get_xy_points_cone(center=torch.zeros(2, device=dev), dx=0.05, num_neg=2, num_pos=60,
-                                        num_rays_neg=3, num_rays_pos=3, angle_between_rays=0.26179938779)
-    assert tmpl.shape[0] == RAY_POINTS
+    terrain.hf = torch.from_numpy(ctx.hf_np).to(dev)
+    ctx.hfd = terrain.hf_desc()
+    ctx.tmpl = geom_util.get_xy_points_cone(center=torch.zeros(2, device=dev), dx=0.05, num_neg=2, num_pos=60,
+                                            num_rays_neg=3, num_rays_pos=3, angle_between_rays=0.26179938779)
+    assert ctx.tmpl.shape[0] == RAY_POINTS
+    ctx.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    ctx.launches = 0
+    return ctx
 
-    NB = 16                                           # distinct query batches, resident in HBM
-    ids_h, times_h = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77 + rank)
-    ids_d, times_d = ids_h.to(dev), times_h.to(dev)
+
+def make_plans(ctx, ids_d, times_d, out, **kw):
+    return [ctx.mlib.make_query_plan(ids_d[b], times_d[b], hf_desc=ctx.hfd, obs_tmpl=ctx.tmpl, out=out, **kw)
+            for b in range(ids_d.shape[0])]
+
+
+# ---- cfg2: the headline ------------------------------------------------------------------------------------------
+def leg_cfg2(ctx):
+    args, dev = ctx.args, ctx.dev
+    K, W = args.steps, max(args.warmup, 3)
+    NB = 64        # distinct resident input batches: a batch's rows come round again after 64 steps = ~1.3 GB of L2 traffic
+    ctx.ids_h, ctx.times_h = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77 + ctx.rank)
+    ids_d, times_d = ctx.ids_h.to(dev), ctx.times_h.to(dev)
     out = {}
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    pdl = not args.no_pdl
+    plans = make_plans(ctx, ids_d, times_d, out, pdl=pdl, pdl_early_inputs=pdl)
+    ms = timed_graph_steps(ctx, plans, K, W)
+    res = {"ms_total": ms, "ms_per_step": ms / K}
+    # the same K steps without programmatic dependent launch (each kernel starts only after the previous one ended)
+    plain = make_plans(ctx, ids_d, times_d, out) if pdl else plans
+    res["serial_ms_per_step"] = (timed_graph_steps(ctx, plain, K, W) / K) if pdl else res["ms_per_step"]
+    # and the conservative isolated-launch figure of round 1: L2 flushed before every step, one event pair per step
+    KF = min(K, 100)
+    mean_f, med_f = timed_flushed_steps(ctx, plain[:16], KF, W)
+    ctx.launches += KF
+    res["flushed_ms_per_step"], res["flushed_median_ms"] = mean_f, med_f
+    ctx.plain_plans, ctx.ids_d, ctx.times_d = plain, ids_d, times_d
+    return res
 
-    # one prebuilt launch per resident input batch, all writing the same output buffers
-    plans = [mlib.make_query_plan(ids_d[b], times_d[b], hf_desc=hfd, obs_tmpl=tmpl, out=out) for b in range(NB)]
-    raw_stream = stream.cuda_stream
 
-    # each step is ONE kernel; replaying it as a one-node CUDA graph reaches the SMs ~1.8 us sooner than a stream
-    # launch (the tracker would hold the same captured plan); --no-graph times plain stream launches
-    use_graph = not args.no_graph
-    if use_graph:
-        for pl in plans:
-            pl.capture()
-
-    def step(i):
-        if use_graph:
-            plans[i % NB].replay()
-        else:
-            plans[i % NB].launch(raw_stream)
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-
-    for w in range(max(args.warmup, 3)):
-        flush.zero_()
-        step(w)
-
-    # ---- kernel-resident timing: inputs in HBM, L2 flushed between steps, CUDA events per step ----
-    K = args.steps
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    barrier()
-    launches0 = ops_launch_count()
-    for s in range(K):
-        flush.zero_()                                  # evict L2 (not timed)
-        starts[s].record(stream)
-        step(s)
-        stops[s].record(stream)
-    launches = ops_launch_count() - launches0
-    barrier()
-    per_step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
-    elapsed_ms = sum(per_step_ms)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms_max = t.item()
-    total_envs = args.envs * world
-    value = total_envs * BODIES * K / (elapsed_ms_max * 1e-3)
-
-    # ---- extra: the same launches WITHOUT the L2 flush (inputs are still larger than L2: the 260 MB frame table is
-    #      gathered at random, 16 distinct batches rotate).  This is the steady state of a running tracker, where the
-    #      clip records, the heightfield and the ray template stay L2-resident from step to step; it shows how much
-    #      of the headline's time is cold-miss latency.  Reported beside the headline, never instead of it. ----
-    KW = min(K, 100)
-    w_start, w_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for w in range(3):
-        step(w)
-    barrier()
-    w_start.record(stream)
-    for s in range(KW):
-        step(s + 5)
-    w_stop.record(stream)
-    barrier()
-    warm_ms = w_start.elapsed_time(w_stop) / KW              # ONE event pair around KW back-to-back launches
-    t = torch.tensor([warm_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    warm_ms = t.item()
-    l2_warm = {"what": "same launches back to back without the L2 flush, one event pair around all of them (frame table "
-                       "260 MB > L2; clip records, heightfield and template stay L2-resident as in a running tracker)",
-               "value": total_envs * BODIES / (warm_ms * 1e-3), "unit": UNIT, "ms_per_step": warm_ms}
-
-    # ---- extra: the tracker's real per-step shape (reference frame + 6 tar_obs_steps look-aheads per env in ONE
-    #      launch, observation at the current frame) -- reported beside the headline, not instead of it ----
+# ---- the tracker's real per-step shape ---------------------------------------------------------------------------
+def leg_tracker_step(ctx):
+    args, dev = ctx.args, ctx.dev
     tar_steps = torch.tensor([0, 1, 2, 3, 10, 20, 30], dtype=torch.float32)
     offsets = ((1.0 / 30.0) * tar_steps).to(dev)
     step_out = {}
-    step_plans = [mlib.make_query_plan(ids_d[b], times_d[b], hf_desc=hfd, obs_tmpl=tmpl, out=step_out,
-                                       time_offsets=offsets) for b in range(NB)]
-    if use_graph:
-        for pl in step_plans:
-            pl.capture()
-    step_launch = (lambda pl: pl.replay()) if use_graph else (lambda pl: pl.launch(raw_stream))
-    for w in range(3):
-        flush.zero_()
-        step_launch(step_plans[w])
-    KS = min(K, 100)
-    s_starts = [torch.cuda.Event(enable_timing=True) for _ in range(KS)]
-    s_stops = [torch.cuda.Event(enable_timing=True) for _ in range(KS)]
-    barrier()
-    for s in range(KS):
-        flush.zero_()
-        s_starts[s].record(stream)
-        step_launch(step_plans[s % NB])
-        s_stops[s].record(stream)
-    barrier()
-    step_ms = sum(a.elapsed_time(b) for a, b in zip(s_starts, s_stops)) / KS
-    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms = t.item()
+    pdl = not args.no_pdl
+    plans = make_plans(ctx, ctx.ids_d[:16], ctx.times_d[:16], step_out, time_offsets=offsets, pdl=pdl,
+                       pdl_early_inputs=pdl)
+    KS = min(args.steps, 100)
+    ms = timed_graph_steps(ctx, plans, KS, 3) / KS
     S = int(tar_steps.shape[0])
     step_bytes = args.envs * (12 + S * (36 + 624 + 136 + 448 + 420) + 1764 + 1764)
-    tracker_step = {"what": f"{args.envs} envs x {S} frame queries + FK (current + tar_obs_steps 1,2,3,10,20,30) + "
-                            f"{RAY_POINTS}-pt obs at the current frame, one launch",
-                    "value": total_envs * S * BODIES / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms,
-                    "algorithmic_bytes_per_launch": step_bytes}
+    return {"what": f"{args.envs} envs x {S} frame queries + FK (current + tar_obs_steps 1,2,3,10,20,30) + "
+                    f"{RAY_POINTS}-pt obs at the current frame, one launch per step, {KS} steps back to back",
+            "value": args.envs * ctx.world * S * BODIES / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "algorithmic_bytes_per_launch": step_bytes}
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the region ----
-    # Every step: H2D of that step's ids/times from pinned memory, one launch, D2H of EVERY output into pinned
-    # memory, and the host waits for the result.  The plan's outputs are views of one contiguous device buffer
-    # so the read-back is a single copy; two buffer sets on two streams let step i's read-back overlap step
-    # i+1's upload + launch (a result is only counted once its copy has completed).
-    ids_p, times_p = ids_h.pin_memory(), times_h.pin_memory()
+
+# ---- end to end through the public API with HOST buffers ------------------------------------------------------------
+def leg_e2e(ctx):
+    """Every step: H2D of that step's ids/times from pinned memory, one launch, D2H of EVERY output into pinned
+    memory, and the host waits for the result.  The plan's outputs are views of one contiguous device buffer so the
+    read-back is a single copy; two buffer sets on two streams let step i's read-back overlap step i+1's upload +
+    launch (a result is only counted once its copy has completed)."""
+    args, dev = ctx.args, ctx.dev
+    K = args.steps
+    NB = ctx.ids_h.shape[0]
+    ids_p, times_p = ctx.ids_h.pin_memory(), ctx.times_h.pin_memory()
     J, D = 15, 28
     fields = (("root_pos", (args.envs, 3)), ("root_rot", (args.envs, 4)), ("root_vel", (args.envs, 3)),
               ("root_ang_vel", (args.envs, 3)), ("joint_rot", (args.envs, J - 1, 4)), ("dof_vel", (args.envs, D)),
@@ -503,7 +524,7 @@ def main():
             n = int(np.prod(shape))
             views[name] = flat[off:off + n].view(*shape)
             off += (n + 3) // 4 * 4                      # keep every view 16-byte aligned
-        return views, off
+        return views
 
     total = sum((int(np.prod(sh)) + 3) // 4 * 4 for _, sh in fields)
     NSET = 2
@@ -514,12 +535,12 @@ def main():
         times_in = torch.empty(args.envs, dtype=torch.float32, device=dev)
         flat_d = torch.empty(total, dtype=torch.float32, device=dev)
         flat_h = torch.empty(total, dtype=torch.float32).pin_memory()
-        views, _ = carve(flat_d)
-        plan = mlib.make_query_plan(ids_in, times_in, hf_desc=hfd, obs_tmpl=tmpl, out=views)
+        views = carve(flat_d)
+        plan = ctx.mlib.make_query_plan(ids_in, times_in, hf_desc=ctx.hfd, obs_tmpl=ctx.tmpl, out=views)
         assert all(plan.out[k].data_ptr() == views[k].data_ptr() for k, _ in fields), "plan must write into the views"
         sets.append((st, ids_in, times_in, flat_d, flat_h, plan, torch.cuda.Event()))
 
-    def e2e_issue(i):
+    def issue(i):
         st, ids_in, times_in, flat_d, flat_h, plan, done = sets[i % NSET]
         with torch.cuda.stream(st):
             ids_in.copy_(ids_p[i % NB], non_blocking=True)
@@ -528,98 +549,296 @@ def main():
             flat_h.copy_(flat_d, non_blocking=True)
             done.record(st)
 
-    def e2e_wait(i):
+    def wait(i):
         sets[i % NSET][6].synchronize()                  # the caller reads step i's result on the host here
 
     for w in range(4):
-        e2e_issue(w)
-        e2e_wait(w)
-    barrier()
+        issue(w)
+        wait(w)
+    barrier(ctx)
     t0 = time.perf_counter()
-    e2e_issue(0)
+    issue(0)
     for s in range(K):
         if s + 1 < K:
-            e2e_issue(s + 1)                            # buffer set (s+1) % 2 was consumed at step s-1
-        e2e_wait(s)
+            issue(s + 1)                                # buffer set (s+1) % 2 was consumed at step s-1
+        wait(s)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_envs * BODIES * K / t.item()
-    h2d = args.envs * (8 + 4)
-    d2h = total * 4
-    e2e_launches = K
+    e2e_s = dist_max(ctx, time.perf_counter() - t0)
+    ctx.launches += K
+    return {"value": args.envs * ctx.world * BODIES * K / e2e_s, "unit": UNIT,
+            "h2d_bytes_per_step": args.envs * (8 + 4), "d2h_bytes_per_step": total * 4}
+
+
+# ---- cfg4: 65 536 envs, one GPU at N = 1, sharded contiguously over the ranks at N > 1 -------------------------------
+CFG4_ENVS = 65536
+
+
+def leg_cfg4(ctx):
+    """BASELINE configs[3].  N = 1: the whole batch on one GPU.  N > 1: env ranges split contiguously
+    (sharding.shard_bounds), every rank queries its slice, then the slices of body_pos and obs are all-gathered over
+    NCCL so that every rank holds the full batch.  Reported: kernel-only step time (max over ranks), the
+    gather alone, kernel + gather per step, and the strong-scaling efficiency against the same 65 536 envs run on ONE
+    GPU in the same process (rank 0, untimed ranks idle)."""
+    from parc_b200 import sharding
+    args, dev = ctx.args, ctx.dev
+    K4 = max(4, min(args.steps, 50))
+    NB = 8
+    ids_h, times_h = query_batches(NB, CFG4_ENVS, args.clips, 264.0 / 30.0, seed=4077)     # same on every rank
+    lo, hi = sharding.shard_bounds(CFG4_ENVS, ctx.rank, ctx.world)
+    ids_d, times_d = ids_h[:, lo:hi].contiguous().to(dev), times_h[:, lo:hi].contiguous().to(dev)
+    pdl = not args.no_pdl
+    out = {}
+    plans = make_plans(ctx, ids_d, times_d, out, pdl=pdl, pdl_early_inputs=pdl)
+    shard_ms = timed_graph_steps(ctx, plans, K4, 3) / K4
+    res = {"envs_total": CFG4_ENVS, "envs_per_gpu": hi - lo, "steps": K4, "shard_ms_per_step": shard_ms,
+           "value": CFG4_ENVS * BODIES / (shard_ms * 1e-3), "unit": UNIT,
+           "roofline_frac": (hi - lo) * BYTES_PER_CHAR_FRAME / (shard_ms * 1e-3) / 1e9 / ctx.peak}
+    if ctx.world == 1:
+        res["n1_ms_per_step"] = shard_ms
+        return res
+    # the same batch on one GPU, in this run (all ranks execute it so the clocks / thermal state match; rank 0's counts)
+    full_out = {}
+    full_plans = make_plans(ctx, ids_h.to(dev), times_h.to(dev), full_out, pdl=pdl, pdl_early_inputs=pdl)
+    n1_ms = timed_graph_steps(ctx, full_plans, K4, 3) / K4
+    del full_plans, full_out
+    # gather of body_pos + obs: one all_gather_into_tensor each, straight into the preallocated global tensors
+    plain = make_plans(ctx, ids_d, times_d, out)
+    g_bp = sharding.AllGatherPlan(out["body_pos"], CFG4_ENVS)
+    g_obs = sharding.AllGatherPlan(out["obs"], CFG4_ENVS)
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        plain[0].launch(); g_bp.run(); g_obs.run()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * K4)]
+    barrier(ctx)
+    for s in range(K4):
+        ev[3 * s].record(stream)
+        plain[s % NB].launch()
+        ev[3 * s + 1].record(stream)
+        g_bp.run(); g_obs.run()
+        ev[3 * s + 2].record(stream)
+    barrier(ctx)
+    ctx.launches += K4 + 3
+    kern = sum(ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(K4)) / K4
+    gath = sum(ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(K4)) / K4
+    both = ev[0].elapsed_time(ev[3 * K4 - 1]) / K4
+    gather_bytes = CFG4_ENVS * (BODIES * 3 + RAY_POINTS) * 4
+    kern, gath, both = dist_max(ctx, kern), dist_max(ctx, gath), dist_max(ctx, both)
+    res.update({"n1_ms_per_step": n1_ms, "efficiency": n1_ms / (ctx.world * shard_ms),
+                "speedup_vs_1gpu": n1_ms / shard_ms,
+                "gather": {"what": "all_gather_into_tensor of body_pos + obs shards (NCCL), every rank receives the full batch",
+                           "bytes_total": gather_bytes, "ms": gath, "algbw_GBps": gather_bytes / (gath * 1e-3) / 1e9},
+                "kernel_ms_stream_launch": kern, "kernel_plus_gather_ms_per_step": both,
+                "value_with_gather": CFG4_ENVS * BODIES / (both * 1e-3),
+                "efficiency_with_gather": n1_ms / (ctx.world * both)})
+    return res
+
+
+# ---- cfg5: dataset sweep, clips sharded over the ranks ---------------------------------------------------------------
+CFG5_CHUNK = 12500
+
+
+def leg_cfg5(ctx):
+    """BASELINE configs[4]: 100 000 synthetic 265-frame clips split contiguously over the ranks.  Per rank and chunk of
+    <= 12 500 clips: the GPU loader builds the packed MotionLib rows of the chunk (parc_build_tables), then one
+    parc_clip_label launch does FK + foot / hand contact labels + nearest-cell height under every body + per-frame cell
+    masks + per-cell min body height on the clip's own 16x16 terrain.  At the end the label statistics are reduced over
+    the ranks (sharding.reduce_loss_stats, 3 collectives).  256 distinct synthetic clips / 64 terrains are tiled to the
+    shard size (content does not change the cost)."""
+    from parc_b200 import ops, sharding
+    from parc_b200.util import geom_util, synth
+    from parc_b200.zmotion_editing_tools.motion_edit_lib import label_clips
+    args, dev, km = ctx.args, ctx.dev, ctx.km
+    total = args.cfg5_clips
+    F = 265
+    lo, hi = sharding.shard_bounds(total, ctx.rank, ctx.world)
+    mine = hi - lo
+    rng = np.random.default_rng(5)
+    base_hf = [synth.box_terrain(rng, h_range=(-0.4, 0.7)) if i % 2 else synth.stairs_terrain(rng) for i in range(64)]
+    nb = 256
+    fr_np = np.concatenate([synth.synth_clips(km, 4, seed=100 + i, num_frames=F, hf=base_hf[i % 64])[0]
+                            for i in range(nb // 4)])
+    chunk = min(CFG5_CHUNK, mine)
+    reps = (chunk + nb - 1) // nb
+    frames = torch.tensor(fr_np).to(dev).repeat(reps, 1, 1)[:chunk].contiguous()
+    hfs = torch.tensor(np.stack([base_hf[(i // 4) % 64] for i in range(nb)])).to(dev).repeat(reps, 1, 1)[:chunk].contiguous()
+    contacts0 = torch.zeros(chunk * F, 15, device=dev)
+    pts = geom_util.get_char_point_samples(km)
+    model = km.c_model()
+    nf = torch.full((chunk,), F, dtype=torch.long, device=dev)
+    fps = torch.full((chunk,), 30.0, device=dev)
+    dtv = 1.0 / fps
+    chunks = []
+    c0 = 0
+    while c0 < mine:
+        chunks.append(min(chunk, mine - c0))
+        c0 += chunk
+
+    def one_pass():
+        stats = None
+        for n in chunks:
+            fr, hf = frames[:n], hfs[:n]
+            rows, _, _ = ops.build_tables(model, fr.reshape(n * F, -1), contacts0[:n * F], nf[:n], fps[:n], dtv[:n])
+            tb = ops.make_terrain_batch(hf, torch.zeros(n, 2, device=dev), (0.4, 0.4), base_z=hf.amin(dim=(1, 2)) - 10.0)
+            lab = label_clips(fr, tb, km, body_points=pts, want_masks=True, want_body_hf=True)
+            s = torch.stack([lab["contacts"].sum(dim=(1, 2)), lab["pen_correction"].amin(dim=1)], dim=0)   # [2, n]
+            stats = s if stats is None else torch.cat([stats, s], dim=1)
+            del rows, lab
+        return stats
+
+    one_pass()
+    K5 = max(1, min(args.steps, 3))
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    stream = torch.cuda.current_stream(dev)
+    barrier(ctx)
+    e0.record(stream)
+    for _ in range(K5):
+        stats = one_pass()
+    e1.record(stream)
+    red = sharding.reduce_loss_stats({"contact_frames_per_clip": stats[0], "pen_correction_min": stats[1]})
+    e2.record(stream)
+    barrier(ctx)
+    ms = dist_max(ctx, e0.elapsed_time(e1)) / K5
+    ctx.launches += K5 * 2 * len(chunks)
+    lay_bytes = 676            # loader: algorithmic bytes per frame (DESIGN 4.10)
+    return {"clips_total": total, "clips_per_gpu": mine, "frames_per_clip": F, "chunks_per_gpu": len(chunks),
+            "passes": K5, "ms_per_pass": ms, "value": total * F * BODIES / (ms * 1e-3), "unit": UNIT,
+            "what": "per chunk: GPU table build (parc_build_tables) + FK + foot/hand contact labels + body heightfield "
+                    "samples + per-frame cell masks + per-cell min body height (parc_clip_label); clips sharded over ranks",
+            "reduce_stats_ms": dist_max(ctx, e1.elapsed_time(e2)),
+            "stats": {k: {kk: v[kk] for kk in ("count", "mean", "min", "max")} for k, v in red.items()},
+            "loader_bytes_per_frame": lay_bytes}
+
+
+# ---- N > 1 self check: the sharded + gathered query equals the single-GPU query bit for bit -------------------------
+def leg_selfcheck(ctx):
+    from parc_b200 import sharding
+    dev = ctx.dev
+    n = 8191                                             # odd: ragged shards
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, ctx.args.clips, (n,), generator=g).to(dev)
+    times = (torch.rand(n, generator=g) * 12.0 - 1.5).to(dev)
+    full = ctx.mlib.calc_motion_frame_fk_obs(ids, times, hf_desc=ctx.hfd, obs_tmpl=ctx.tmpl)
+    full = {k: v.clone() for k, v in full.items()}
+    sq = sharding.ShardedMotionQuery(ctx.mlib, hf_desc=ctx.hfd, obs_tmpl=ctx.tmpl)
+    got = sq.query_gathered(ids, times, keys=("root_pos", "body_pos", "body_rot", "obs", "contacts"))
+    same = all(torch.equal(got[k], full[k]) for k in got)
+    lo, hi = sharding.shard_bounds(n, ctx.rank, ctx.world)
+    plan = sharding.AllGatherPlan(sq._out["obs"], n)
+    same = same and torch.equal(plan.run(), full["obs"])
+    st = sharding.reduce_loss_stats({"z": full["root_pos"][lo:hi, 2]})
+    ref = full["root_pos"][:, 2].double()
+    ok_stats = (st["z"]["count"] == n and abs(st["z"]["sum"] - ref.sum().item()) <= 1e-9 * n
+                and st["z"]["min"] == ref.min().item() and st["z"]["max"] == ref.max().item())
+    flag = torch.tensor([1.0 if (same and ok_stats) else 0.0], dtype=torch.float64, device=dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+    return {"sharded_gather_equals_single_gpu": bool(flag.item() == 1.0), "ranks": ctx.world, "queries": n,
+            "collectives": "all_gather_into_tensor (ragged + fixed-buffer forms), all_reduce sum/min/max"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    ctx = setup(args)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        ctx.peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth, burst)"
+    else:
+        ctx.peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    sampler = ClockSampler(ctx.local_rank)
+    if ctx.rank == 0:
+        sampler.start()
+
+    K = args.steps
+    c2 = leg_cfg2(ctx)
+    launches_cfg2 = K
+    tracker_step = leg_tracker_step(ctx)
+    e2e = leg_e2e(ctx)
+    cfg4 = leg_cfg4(ctx) if not args.no_cfg4 else None
+    cfg5 = leg_cfg5(ctx) if not args.no_cfg5 else None
+    selfcheck = leg_selfcheck(ctx) if (ctx.world > 1 or args.selfcheck) else None
 
     # ---- soak: keep the kernel running ~1.5 s so the clock sampler sees the GPU under this load ----
     t_end = time.perf_counter() + (0.0 if args.no_soak else 1.5)
     i = 0
     while time.perf_counter() < t_end:
         for _ in range(200):
-            step(i)
+            ctx.plain_plans[i % 16].replay()
             i += 1
-        torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if rank == 0 else None
+        torch.cuda.synchronize(ctx.dev)
+    clocks = sampler.stop() if ctx.rank == 0 else None
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    if ctx.rank != 0:
+        if ctx.world > 1:
+            ctx.dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant (only) kernel ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = json.load(open(peaks_path))["hbm_gbs"]
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth, burst)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    avg_launch_s = (sum(per_step_ms) / K) * 1e-3
+    total_envs = args.envs * ctx.world
+    value = total_envs * BODIES * K / (c2["ms_total"] * 1e-3)
     alg_bytes = args.envs * BYTES_PER_CHAR_FRAME
-    achieved = alg_bytes / avg_launch_s / 1e9
+    step_s = c2["ms_per_step"] * 1e-3
+    achieved = alg_bytes / step_s / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("envs") == args.envs:
             traffic = tj.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
                 "traffic": traffic, "kernel": "parc::motion_query_kernel<true>",
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "median_launch_us": statistics.median(per_step_ms) * 1e3,
+                "launch_us": c2["ms_per_step"] * 1e3,
+                "how": "algorithmic bytes of one launch / (event time of the K-launch timed region / K)",
+                "serial_launch_us": c2["serial_ms_per_step"] * 1e3,
+                "frac_serial": alg_bytes / (c2["serial_ms_per_step"] * 1e-3) / 1e9 / ctx.peak,
+                "isolated_flushed_launch_us": c2["flushed_ms_per_step"] * 1e3,
+                "frac_isolated_flushed": alg_bytes / (c2["flushed_ms_per_step"] * 1e-3) / 1e9 / ctx.peak,
                 "frac_of_nominal_8TBps": achieved / 8000.0}
+    tracker_step["roofline_frac"] = (tracker_step["algorithmic_bytes_per_launch"] / (tracker_step["ms_per_step"] * 1e-3)
+                                     / 1e9 / ctx.peak)
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if ctx.world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        fn, desc = cpu_reference_step_fn(args, frames, contacts, hf_np)
-        fn(ids_h[0], times_h[0])
-        best = float("inf")
+        fn, desc = cpu_reference_step_fn(ctx.frames, ctx.contacts, ctx.hf_np)
+        fn(ctx.ids_h[0], ctx.times_h[0])
         reps = 5
+        t0 = time.perf_counter()
         for r in range(reps):
-            t0 = time.perf_counter()
-            fn(ids_h[r % NB], times_h[r % NB])
-            best = min(best, time.perf_counter() - t0)
-        cpu_baseline = {"value": args.envs * BODIES / best, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"best of {reps} full {args.envs}-env steps after 1 warm-up; {desc}"}
+            fn(ctx.ids_h[r], ctx.times_h[r])
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": args.envs * BODIES / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"mean of {reps} full {args.envs}-env steps after 1 warm-up; {desc}"}
 
+    pdl = not args.no_pdl
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-        "ms_per_step": elapsed_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": c2["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "envs_per_gpu": args.envs, "clips": args.clips,
-                   "frames_per_clip": 265, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write); "
-                   "frame table 260 MB > L2", "timing": "CUDA events per step on the launch stream, max over ranks",
-                   "launch": "one-kernel CUDA graph replay per step" if use_graph else "stream launch per step",
-                   "host_cpu_affinity": affinity},
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clocks, "tracker_step": tracker_step, "l2_warm": l2_warm,
+        "config": config_dict(
+            args, l2="inputs larger than L2, no flush: every step reads its own (ids, times) batch -- 64 distinct "
+                     "batches rotate, a batch's frame rows come round again after ~1.3 GB of L2 traffic -- and gathers "
+                     "its rows at random from the 260 MB frame table; clip records, heightfield and template stay "
+                     "L2-resident as in a running tracker (the L2-flushed isolated-launch time is roofline."
+                     "isolated_flushed_launch_us)",
+            timing="one CUDA-event pair on the launch stream around the K steps, barrier + synchronize on both sides, "
+                   "max over ranks",
+            launch=("the K steps are ONE CUDA graph of K kernel nodes" +
+                    (" chained by programmatic dependent launch (a step's read side overlaps the previous step's tail; "
+                     "its stores wait for it)" if pdl else "")),
+            heading="reference chain (atan2 -> cos/sin)", host_cpu_affinity=ctx.affinity),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": launches_cfg2, "gpu_launches_all_legs": ctx.launches, "clocks": clocks,
+        "tracker_step": tracker_step, "cfg4": cfg4, "cfg5": cfg5, "selfcheck": selfcheck,
     }
-    tracker_step["roofline_frac"] = step_bytes / (step_ms * 1e-3) / 1e9 / peak
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def ops_launch_count():

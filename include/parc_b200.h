@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PARC_ABI_VERSION 1
+#define PARC_ABI_VERSION 2
 #define PARC_MAX_BODIES 24   /* position + rotation slots of a packed row must fit one warp: J + 1 <= 32 */
 #define PARC_MAX_DOF 96
 
@@ -186,6 +186,59 @@ int parc_motion_query_steps(const ParcMotionTables* tables, const int64_t* motio
 int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
                           const int64_t* frame_idxs, int64_t n, const ParcCharModel* model,
                           const ParcFrameOut* frame, const ParcFkOut* fk, void* stream);
+
+/* The general form of the three queries above: one argument block, plus what a stepping caller needs.
+ *   motion_times (blended query, calc_motion_frame) XOR frame_idxs (integer frames, get_motion_frame);
+ *   num_steps / time_offsets / root_xy_offset as in parc_motion_query_steps (num_steps 0 or 1 = plain query).
+ *   error_flags  device int32[1] (caller-zeroed, 4-byte aligned) or NULL.  The reference raises an IndexError (CPU)
+ *                or a device assert (CUDA) on a clip id outside [0, num_clips) / a frame outside the table; the kernel
+ *                never reads out of bounds: it ORs PARC_QUERY_ERR_CLIP_ID / PARC_QUERY_ERR_FRAME_IDX into
+ *                *error_flags and answers with clip 0 / the clip's nearest valid frame.  The Python mirror turns a
+ *                non-zero word into IndexError.
+ *   flags        PARC_QUERY_FAST_HEADING   observation heading cos/sin straight from the rotated x axis instead of
+ *                                          the reference's atan2 -> cos/sin chain (util/torch_util.py:470-479,
+ *                                          :619-631); default is the reference chain.
+ *                PARC_QUERY_PDL            launch with programmatic stream serialisation (sm_90+): the kernel's
+ *                                          prologue (kinematic tree / template staging) overlaps the tail of the
+ *                                          previous kernel of `stream`; it waits for that kernel before reading
+ *                                          the inputs or writing anything.
+ *                PARC_QUERY_PDL_EARLY_INPUTS  with PARC_QUERY_PDL: the caller guarantees that motion_ids, motion_times
+ *                                          / frame_idxs, time_offsets and root_xy_offset were NOT written by the
+ *                                          previous kernel of `stream` (e.g. they were uploaded, or produced two
+ *                                          kernels earlier); the whole read side -- ids, clip records, frame rows,
+ *                                          slerp -- then runs before the wait and only the stores are ordered
+ *                                          behind the previous kernel.
+ *   variant      0 = chosen by batch size; 1..4 force one instantiation (tuning / tests): 1 = two characters per warp,
+ *                whole template sweep in flight (<= 128 registers); 2 = quarter sweep in flight, 64 registers;
+ *                3 = half sweep, 80 registers; 4 = one character per warp. */
+#define PARC_QUERY_FAST_HEADING 1u
+#define PARC_QUERY_PDL 2u
+#define PARC_QUERY_PDL_EARLY_INPUTS 4u
+#define PARC_QUERY_ERR_CLIP_ID 1
+#define PARC_QUERY_ERR_FRAME_IDX 2
+
+typedef struct ParcQueryArgs {
+  const ParcMotionTables* tables;
+  const int64_t* motion_ids;      /* device [n] */
+  const float* motion_times;      /* device [n] or NULL */
+  const int64_t* frame_idxs;      /* device [n] or NULL */
+  int64_t n;                      /* entries */
+  const float* time_offsets;      /* device [num_steps] or NULL */
+  const float* root_xy_offset;    /* device [n,2] or NULL */
+  const ParcCharModel* model;
+  const ParcFrameOut* frame;      /* may be NULL */
+  const ParcFkOut* fk;            /* may be NULL */
+  const ParcHeightfield* hf;      /* required iff obs_out */
+  const ParcObsSpec* obs;         /* required iff obs_out */
+  float* obs_out;                 /* [n, num_points] or NULL */
+  int32_t* error_flags;
+  int32_t num_steps;
+  uint32_t flags;
+  int32_t variant;
+  int32_t reserved;
+} ParcQueryArgs;
+
+int parc_motion_query_ex(const ParcQueryArgs* args, void* stream);
 
 /* a6: KinCharModel.forward_kinematics (anim/kin_char_model.py:509-541) on caller-supplied poses. */
 int parc_fk_fwd(const float* root_pos, const float* root_rot, const float* joint_rot, int64_t n,

@@ -76,6 +76,18 @@ class ParcObsSpec(C.Structure):
                 ("min_h", C.c_float), ("max_h", C.c_float)]
 
 
+class ParcQueryArgs(C.Structure):
+    _fields_ = [("tables", C.c_void_p), ("motion_ids", C.c_void_p), ("motion_times", C.c_void_p),
+                ("frame_idxs", C.c_void_p), ("n", C.c_int64), ("time_offsets", C.c_void_p),
+                ("root_xy_offset", C.c_void_p), ("model", C.c_void_p), ("frame", C.c_void_p), ("fk", C.c_void_p),
+                ("hf", C.c_void_p), ("obs", C.c_void_p), ("obs_out", C.c_void_p), ("error_flags", C.c_void_p),
+                ("num_steps", C.c_int32), ("flags", C.c_uint32), ("variant", C.c_int32), ("reserved", C.c_int32)]
+
+
+PARC_QUERY_FAST_HEADING, PARC_QUERY_PDL, PARC_QUERY_PDL_EARLY_INPUTS = 1, 2, 4
+PARC_QUERY_ERR_CLIP_ID, PARC_QUERY_ERR_FRAME_IDX = 1, 2
+
+
 class ParcTerrainBatch(C.Structure):
     _fields_ = [("hf", C.c_void_p), ("hf_batch_stride", C.c_int64), ("min_center", C.c_void_p),
                 ("x_nodes", C.c_void_p), ("y_nodes", C.c_void_p), ("base_z", C.c_void_p),
@@ -147,6 +159,7 @@ SIGNATURES = {
                                           _V, _V]),
     "parc_get_motion_frame": (C.c_int, [_P(ParcMotionTables), _V, _V, _I64, _P(ParcCharModel),
                                         _P(ParcFrameOut), _P(ParcFkOut), _V]),
+    "parc_motion_query_ex": (C.c_int, [_P(ParcQueryArgs), _V]),
     "parc_fk_fwd": (C.c_int, [_V, _V, _V, _I64, _P(ParcCharModel), _V, _V, _V]),
     "parc_fk_bwd": (C.c_int, [_V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V, _V, _V]),
     "parc_dof_to_rot_fwd": (C.c_int, [_V, _I64, _P(ParcCharModel), _V, _V]),

@@ -129,16 +129,49 @@ class MotionLib:
         return torch.clip(phase, 0.0, 1.0)
 
     # ------------------------------------------------------------------ the hot path
+    def _error_word(self, device):
+        """Device int32[1] the query kernels OR their PARC_QUERY_ERR_* bits into (one per device used)."""
+        words = self.__dict__.setdefault("_query_error_words", {})
+        w = words.get(device)
+        if w is None:
+            w = words[device] = torch.zeros(1, dtype=torch.int32, device=device)
+        return w
+
+    def check_query_errors(self):
+        """Raise IndexError if any query since the last check was handed a clip id / frame index outside the tables
+        (the reference's gathers raise there: IndexError on CPU, a device assert on CUDA).  Synchronises.  Queries
+        never read out of bounds either way: the offending entry is answered with clip 0 / the nearest valid frame.
+        Set `validate_ids = True` (or PARC_B200_VALIDATE=1) to check after every call."""
+        for w in self.__dict__.get("_query_error_words", {}).values():
+            ops.raise_query_errors(w, "MotionLib query")
+
+    @property
+    def validate_ids(self):
+        v = self.__dict__.get("_validate_ids")
+        if v is None:
+            import os
+            v = self.__dict__["_validate_ids"] = os.environ.get("PARC_B200_VALIDATE", "0") not in ("", "0")
+        return v
+
+    @validate_ids.setter
+    def validate_ids(self, value):
+        self.__dict__["_validate_ids"] = bool(value)
+
+    def _query(self, motion_ids, **kw):
+        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids,
+                             error_flags=self._error_word(motion_ids.device), **kw)
+        if self.validate_ids:
+            self.check_query_errors()
+        return r
+
     def calc_motion_frame(self, motion_ids, motion_times):
         """(root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_vel[, contacts]).  Ref :80-112."""
-        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times=motion_times,
-                             want_contacts=self._contact_info)
+        r = self._query(motion_ids, motion_times=motion_times, want_contacts=self._contact_info)
         return self._as_tuple(r)
 
     def get_motion_frame(self, motion_ids, frame_idxs):
         """Integer-frame lookup, no blending.  Ref :114-131."""
-        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, frame_idxs=frame_idxs,
-                             want_contacts=self._contact_info)
+        r = self._query(motion_ids, frame_idxs=frame_idxs, want_contacts=self._contact_info)
         return self._as_tuple(r)
 
     def _as_tuple(self, r):
@@ -149,21 +182,23 @@ class MotionLib:
 
     def _calc_frame_blend(self, motion_ids, times):
         """(frame_idx0, frame_idx1, blend), absolute table rows.  Ref :443-456."""
-        r = ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times=times,
-                             want_frame=False, want_index=True)
+        r = self._query(motion_ids, motion_times=times, want_frame=False, want_index=True)
         return r["frame_idx0"], r["frame_idx1"], r["blend"]
 
     def calc_motion_frame_fk_obs(self, motion_ids, motion_times, hf_desc=None, obs_tmpl=None, obs_relative=True,
-                                 min_obs_h=-3.0, max_obs_h=3.0, out=None):
+                                 min_obs_h=-3.0, max_obs_h=3.0, out=None, fast_heading=False):
         """Fused extension (no reference counterpart as ONE call): the frame query, the forward
         kinematics of the blended pose and the heightmap observation around it in a single launch --
-        what dm_env.py:570-595 + ig_parkour_env.py:636-656 do in ~1500 eager ops.  Returns a dict."""
-        return ops.motion_query(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times=motion_times,
-                                want_contacts=self._contact_info, want_fk=True, hf=hf_desc, obs_tmpl=obs_tmpl,
-                                obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out)
+        what dm_env.py:570-595 + ig_parkour_env.py:636-656 do in ~1500 eager ops.  Returns a dict.
+        The observation's heading follows the reference chain (atan2 -> cos / sin); fast_heading=True takes cos / sin
+        straight from the rotated x axis instead (a few instructions cheaper, ~2 ulp apart)."""
+        return self._query(motion_ids, motion_times=motion_times, want_contacts=self._contact_info, want_fk=True,
+                           hf=hf_desc, obs_tmpl=obs_tmpl, obs_relative=obs_relative, obs_min_h=min_obs_h,
+                           obs_max_h=max_obs_h, out=out, fast_heading=fast_heading)
 
     def make_query_plan(self, motion_ids, motion_times, hf_desc=None, obs_tmpl=None, obs_relative=True,
-                        min_obs_h=-3.0, max_obs_h=3.0, want_fk=True, out=None, time_offsets=None, root_xy_offset=None):
+                        min_obs_h=-3.0, max_obs_h=3.0, want_fk=True, out=None, time_offsets=None, root_xy_offset=None,
+                        outputs=None, fast_heading=False, pdl=False, pdl_early_inputs=False, variant=0):
         """Prebuilt launch of `calc_motion_frame_fk_obs` over fixed input/output buffers: returns an
         `ops.MotionQueryPlan` whose `.launch()` costs one C call.  Update `motion_ids` / `motion_times`
         in place between launches (as the tracker does with its time buffer).
@@ -174,11 +209,15 @@ class MotionLib:
         observation [N, P] is taken at the current frame only.
 
         root_xy_offset [N,2] (fp32): added to root x,y of every step before FK and the observation -- where each
-        env's motion sits on the shared terrain (DMEnv._move_to_motion_terrain, envs/ig_parkour/dm_env.py:604-615)."""
+        env's motion sits on the shared terrain (DMEnv._move_to_motion_terrain, envs/ig_parkour/dm_env.py:604-615).
+
+        outputs / fast_heading / pdl / pdl_early_inputs / variant: see `ops.MotionQueryPlan`."""
         return ops.MotionQueryPlan(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times,
                                    want_contacts=self._contact_info, want_fk=want_fk, hf=hf_desc, obs_tmpl=obs_tmpl,
                                    obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out,
-                                   time_offsets=time_offsets, root_xy_offset=root_xy_offset)
+                                   time_offsets=time_offsets, root_xy_offset=root_xy_offset, outputs=outputs,
+                                   fast_heading=fast_heading, pdl=pdl, pdl_early_inputs=pdl_early_inputs,
+                                   variant=variant, error_flags=self._error_word(motion_ids.device))
 
     def _calc_loop_offset(self, motion_ids, times):
         """floor(t / len) * root_pos_delta for WRAP clips, zero otherwise (ref :458-475).  Kept for callers that

@@ -32,7 +32,16 @@ struct QueryParams {
   float* obs_out;
   int want_fk;
   int want_obs;
+  int32_t* err;             // device error bits (PARC_QUERY_ERR_*) or nullptr
+  int fast_heading;         // 0: heading -> atan2f -> sincosf as the reference; 1: cos/sin straight from the rotated x axis
+  int pdl_early;            // 1: ids / times are safe to read before the previous kernel of the stream has finished
 };
+
+// Programmatic dependent launch (sm_90+): `launch_dependents` lets the next kernel of the stream start its prologue
+// on SMs this grid no longer fills; `wait` blocks until the previous kernel has completed and flushed.  Both are
+// no-ops for a launch without the programmatic-serialisation attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Work item -> (entry, step).  In the tracker-step form the items are ordered so that all step-0 queries -- the only
 // ones that sweep the observation template -- come first and share warps with each other: a warp then either sweeps
@@ -135,6 +144,8 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
   int64_t id_pre = 0;
   float t_pre = 0.0f;
   int64_t f_pre = 0;
+  griddep_launch_dependents();
+  if (!p.pdl_early) griddep_wait();     // the inputs may come from the previous kernel of the stream
   {
     const int64_t q0 = first + grp < p.n ? first + grp : p.n - 1;
     int64_t e0 = p.num_steps > 1 ? q0 / p.num_steps : q0;
@@ -196,7 +207,10 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     // where the env's motion sits on the shared terrain (_move_to_motion_terrain, dm_env.py:604-615): root lane only
     float2 xy_off = make_float2(0.0f, 0.0f);
     if (STEPFORM && p.xy_offset && l == 0) xy_off = __ldg(reinterpret_cast<const float2*>(p.xy_offset) + entry);
-    if (id < 0 || id >= p.tb.num_clips) id = 0;   // reference would raise an index error
+    if (id < 0 || id >= p.tb.num_clips) {         // the reference raises an IndexError / device assert here
+      id = 0;
+      if (p.err && l == 0) atomicOr(p.err, PARC_QUERY_ERR_CLIP_ID);
+    }
     const int4* cmp = reinterpret_cast<const int4*>(p.tb.clips + id);
     const int4 c0 = __ldg(cmp);
     const int4 c1 = __ldg(cmp + 1);
@@ -214,6 +228,10 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     if (BLEND) {
       frame_blend(cm, t_q, i0, i1, blend, cycles);
     } else {
+      if (f_q < 0 || f_q >= cm.num_frames) {      // never read outside the clip's rows
+        f_q = f_q < 0 ? 0 : cm.num_frames - 1;
+        if (p.err && l == 0) atomicOr(p.err, PARC_QUERY_ERR_FRAME_IDX);
+      }
       i0 = i1 = cm.start_idx + f_q;
     }
     const float4* r0 = rows + i0 * row_f4;
@@ -250,6 +268,9 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
       R.x = add_rn(R.x, xy_off.x);
       R.y = add_rn(R.y, xy_off.y);
     }
+    // early-input PDL launches ran everything above -- immutable tables and caller-guaranteed inputs only -- while the
+    // previous kernel of the stream was still draining; nothing may be written before it has finished
+    if (p.pdl_early && base == first) griddep_wait();
     if (active) {
       if (l == 0) {
         if (p.out.root_pos) {
@@ -314,16 +335,21 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     float4 rr = make_float4(0.f, 0.f, 0.f, 1.f);
     if (p.want_obs) rr = make_float4(shfl_g(R.x, 1, G), shfl_g(R.y, 1, G), shfl_g(R.z, 1, G), shfl_g(R.w, 1, G));
     if (grp_obs) {
-      // cos / sin of heading = atan2(d.y, d.x) taken directly from the rotated x axis d (the reference goes
-      // through atan2 -> cos/sin; both are within ~2 ulp of the true value, far below the fp32 granularity
-      // of the world coordinate they are added to).
       const float3 dir = quat_rotate(rr, make_float3(1.0f, 0.0f, 0.0f));
-      const float n2 = dir.x * dir.x + dir.y * dir.y;
-      float sn = 0.0f, cs = (dir.x < 0.0f) ? -1.0f : 1.0f;       // atan2(0, +-0)
-      if (n2 > 0.0f) {
-        const float rn = rsqrtf(n2);
-        cs = dir.x * rn;
-        sn = dir.y * rn;
+      float sn, cs;
+      if (!p.fast_heading) {
+        // the reference's chain: heading = atan2(d.y, d.x) (util/torch_util.py:470-479), then cos / sin of it
+        // (rotate_2d_vec, :619-631)
+        sincos_reduced(atan2f(dir.y, dir.x), sn, cs);
+      } else {
+        // PARC_QUERY_FAST_HEADING: cos / sin taken directly from the rotated x axis d; within ~2 ulp of the chain
+        const float n2 = dir.x * dir.x + dir.y * dir.y;
+        sn = 0.0f; cs = (dir.x < 0.0f) ? -1.0f : 1.0f;           // atan2(0, +-0)
+        if (n2 > 0.0f) {
+          const float rn = rsqrtf(n2);
+          cs = dir.x * rn;
+          sn = dir.y * rn;
+        }
       }
       const GridAxis gx = make_grid_axis(p.hf.min_x, p.hf.dx, p.hf.dim_x);
       const GridAxis gy = make_grid_axis(p.hf.min_y, p.hf.dy, p.hf.dim_y);
@@ -601,17 +627,43 @@ extern "C" int parc_pack_frames(const float* root_pos, const float* root_rot, co
   return check_launch();
 }
 
-static int launch_query(bool blend, const ParcMotionTables* tables, const int64_t* ids, const float* times,
-                        const int64_t* frame_idx, const float* offsets, int num_steps, const float* xy_offset,
-                        int64_t n_entries, const ParcCharModel* model,
-                        const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
-                        const ParcObsSpec* obs, float* obs_out, void* stream) {
+// Launch helper: plain <<<>>> or, for PARC_QUERY_PDL, cudaLaunchKernelEx with programmatic stream serialisation (the
+// kernel may begin while the previous kernel of the stream drains; it orders itself with griddepcontrol.wait).
+template <typename K>
+static void launch_maybe_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, bool pdl, const QueryParams& p) {
+  if (!pdl) {
+    kernel<<<grid, block, smem, st>>>(p);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
+extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
+  if (!a) return PARC_E_NULL;
+  const ParcMotionTables* tables = a->tables;
+  const ParcCharModel* model = a->model;
   if (!tables || !model) return PARC_E_NULL;
   if (!tables->rows || !tables->clips) return PARC_E_NULL;
-  if (n_entries < 0 || num_steps < 1 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
-  if (num_steps > 1 && !offsets) return PARC_E_NULL;
+  const bool blend = a->frame_idxs == nullptr;
+  if (!blend && a->motion_times) return PARC_E_SIZE;            // exactly one of times / frame indices
+  const int num_steps = a->num_steps < 1 ? 1 : a->num_steps;
+  const int64_t n_entries = a->n;
+  if (n_entries < 0 || a->num_steps < 0 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
+  if (num_steps > 1 && (!a->time_offsets || !blend)) return PARC_E_NULL;
+  if (!blend && a->root_xy_offset) return PARC_E_SIZE;
+  if (a->variant < 0 || a->variant > 4) return PARC_E_SIZE;
   const int64_t n = n_entries * num_steps;
-  if (n > 0 && (!ids || (blend ? !times : !frame_idx))) return PARC_E_NULL;
+  if (n > 0 && (!a->motion_ids || (blend && !a->motion_times))) return PARC_E_NULL;
   QueryParams p;
   int rc = parc_row_layout(model, &p.lay);
   if (rc) return rc;
@@ -620,23 +672,32 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   if (!tables->tree) return PARC_E_NULL;
   if (!aligned16(tables->tree)) return PARC_E_ALIGN;
   p.tb = *tables;
-  p.ids = ids; p.times = times; p.frame_idx = frame_idx; p.n = n;
-  p.offsets = offsets; p.num_steps = num_steps; p.entries = n_entries;
-  if ((reinterpret_cast<uintptr_t>(xy_offset) & 7u) != 0) return PARC_E_ALIGN;
-  p.xy_offset = xy_offset;
+  p.ids = a->motion_ids; p.times = a->motion_times; p.frame_idx = a->frame_idxs; p.n = n;
+  p.offsets = a->time_offsets; p.num_steps = num_steps; p.entries = n_entries;
+  if ((reinterpret_cast<uintptr_t>(a->root_xy_offset) & 7u) != 0) return PARC_E_ALIGN;
+  p.xy_offset = a->root_xy_offset;
+  if ((reinterpret_cast<uintptr_t>(a->error_flags) & 3u) != 0) return PARC_E_ALIGN;
+  p.err = a->error_flags;
+  p.fast_heading = (a->flags & PARC_QUERY_FAST_HEADING) ? 1 : 0;
+  const bool pdl = (a->flags & PARC_QUERY_PDL) != 0;
+  p.pdl_early = (pdl && (a->flags & PARC_QUERY_PDL_EARLY_INPUTS)) ? 1 : 0;
   ParcFrameOut none = {};
-  p.out = frame ? *frame : none;
+  p.out = a->frame ? *a->frame : none;
   if (!aligned16(p.out.root_rot) || !aligned16(p.out.joint_rot)) return PARC_E_ALIGN;
+  const ParcFkOut* fk = a->fk;
   p.want_fk = (fk && (fk->body_pos || fk->body_rot)) ? 1 : 0;
   p.fk.body_pos = p.want_fk ? fk->body_pos : nullptr;
   p.fk.body_rot = p.want_fk ? fk->body_rot : nullptr;
   if (!aligned16(p.fk.body_rot)) return PARC_E_ALIGN;
-  p.want_obs = obs_out ? 1 : 0;
-  p.obs_out = obs_out;
+  // an empty observation template asks for nothing: the sweep would otherwise read an unstaged template
+  p.want_obs = (blend && a->obs_out && !(a->obs && a->obs->num_points == 0)) ? 1 : 0;
+  p.obs_out = p.want_obs ? a->obs_out : nullptr;
   ParcHeightfield hf0 = {};
   ParcObsSpec obs0 = {};
   p.hf = hf0; p.obs = obs0;
   if (p.want_obs) {
+    const ParcHeightfield* hf = a->hf;
+    const ParcObsSpec* obs = a->obs;
     if (!hf || !obs || !hf->hf || !obs->tmpl_xy) return PARC_E_NULL;
     if (hf->dim_x <= 0 || hf->dim_y <= 0 || obs->num_points < 0) return PARC_E_SIZE;
     if ((reinterpret_cast<uintptr_t>(obs->tmpl_xy) & 7u) != 0) return PARC_E_ALIGN;
@@ -650,15 +711,23 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const bool half = model->num_bodies + 1 <= 16;
-  const int64_t warps = half ? (n + 1) / 2 : n;
-  const bool one_wave = warps <= (int64_t)sms * 16;           // 8 CTAs x 2 warps resident per SM
-  const int grid = query_grid(warps, sms);
+  const bool fits16 = model->num_bodies + 1 <= 16;
   // Regimes (measured on B200): one resident wave -> the whole 28-deep sweep in flight at <= 128 registers;
   // beyond it occupancy wins: 7 gathers in flight at 64 registers / 16 CTAs per SM beat 14 in flight at 80
   // registers / 12 CTAs (65 536 envs: 87.3 -> 85.2 us; the 7-step tracker form: 396 -> 337 us), while 4 in
   // flight (88.5 us) and 48 registers / 20 CTAs (97.7 us, spills) lose again.
-  const int inflight = half ? (one_wave ? 28 : 7) : 14;
+  // variant: 0 = by regime; 1 = G16 / 28 in flight / 8 CTAs per SM; 2 = G16 / 7 / 16; 3 = G16 / 14 / 12; 4 = G32 / 14 / 8
+  int variant = a->variant;
+  if (!fits16) variant = 4;
+  if (variant == 0) {
+    const int64_t warps16 = (n + 1) / 2;
+    variant = blend ? (warps16 <= (int64_t)sms * 16 ? 1 : 2) : 3;
+  }
+  if (!blend && variant != 4) variant = 3;
+  const bool half = variant != 4;
+  const int64_t warps = half ? (n + 1) / 2 : n;
+  const int grid = query_grid(warps, sms);
+  const int inflight = variant == 1 ? 28 : (variant == 2 ? 7 : 14);
   size_t smem = 0;
   if (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) {
     const int sweep = (half ? 16 : 32) * inflight;
@@ -671,15 +740,20 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   // branches), so the plain one-query-per-entry call runs an instantiation without them -- whose code must stay
   // exactly the tuned one: making `step` a compile-time 0 there changed the schedule and cost 13 %.
   const bool step_form = blend && (p.num_steps > 1 || p.xy_offset);
-#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB)                                                        \
-  do {                                                                                              \
-    if (B && step_form) motion_query_kernel<B, GG, NF, RL, MB, B><<<grid, QUERY_CTA_THREADS, smem, st>>>(p);   \
-    else motion_query_kernel<B, GG, NF, RL, MB, false><<<grid, QUERY_CTA_THREADS, smem, st>>>(p);              \
+#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB)                                                                         \
+  do {                                                                                                               \
+    if (B && step_form)                                                                                              \
+      launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, B>, grid, QUERY_CTA_THREADS, smem, st, pdl, p);        \
+    else                                                                                                             \
+      launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, false>, grid, QUERY_CTA_THREADS, smem, st, pdl, p);    \
   } while (0)
   if (blend) {
-    if (half && one_wave) { if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); }
-    else if (half) { if (rel) PARC_LAUNCH_QUERY(true, 16, 7, true, 16); else PARC_LAUNCH_QUERY(true, 16, 7, false, 16); }
-    else { if (rel) PARC_LAUNCH_QUERY(true, 32, 14, true, 8); else PARC_LAUNCH_QUERY(true, 32, 14, false, 8); }
+    switch (variant) {
+      case 1: if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); break;
+      case 2: if (rel) PARC_LAUNCH_QUERY(true, 16, 7, true, 16); else PARC_LAUNCH_QUERY(true, 16, 7, false, 16); break;
+      case 3: if (rel) PARC_LAUNCH_QUERY(true, 16, 14, true, 12); else PARC_LAUNCH_QUERY(true, 16, 14, false, 12); break;
+      default: if (rel) PARC_LAUNCH_QUERY(true, 32, 14, true, 8); else PARC_LAUNCH_QUERY(true, 32, 14, false, 8); break;
+    }
   } else {
     if (half) PARC_LAUNCH_QUERY(false, 16, 14, false, 12); else PARC_LAUNCH_QUERY(false, 32, 14, false, 8);
   }
@@ -687,12 +761,24 @@ static int launch_query(bool blend, const ParcMotionTables* tables, const int64_
   return check_launch();
 }
 
+static int query_basic(const ParcMotionTables* tables, const int64_t* ids, const float* times,
+                       const int64_t* frame_idx, const float* offsets, int num_steps, const float* xy_offset,
+                       int64_t n_entries, const ParcCharModel* model, const ParcFrameOut* frame, const ParcFkOut* fk,
+                       const ParcHeightfield* hf, const ParcObsSpec* obs, float* obs_out, void* stream) {
+  ParcQueryArgs a = {};
+  a.tables = tables; a.motion_ids = ids; a.motion_times = times; a.frame_idxs = frame_idx; a.n = n_entries;
+  a.time_offsets = offsets; a.num_steps = num_steps; a.root_xy_offset = xy_offset; a.model = model;
+  a.frame = frame; a.fk = fk; a.hf = hf; a.obs = obs; a.obs_out = obs_out;
+  return parc_motion_query_ex(&a, stream);
+}
+
 extern "C" int parc_motion_query(const ParcMotionTables* tables, const int64_t* motion_ids,
                                  const float* motion_times, int64_t n, const ParcCharModel* model,
                                  const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                                  const ParcObsSpec* obs, float* obs_out, void* stream) {
-  return launch_query(true, tables, motion_ids, motion_times, nullptr, nullptr, 1, nullptr, n, model, frame, fk, hf,
-                      obs, obs_out, stream);
+  if (n > 0 && !motion_times) return PARC_E_NULL;
+  return query_basic(tables, motion_ids, motion_times, nullptr, nullptr, 1, nullptr, n, model, frame, fk, hf, obs,
+                     obs_out, stream);
 }
 
 extern "C" int parc_motion_query_steps(const ParcMotionTables* tables, const int64_t* motion_ids,
@@ -700,15 +786,22 @@ extern "C" int parc_motion_query_steps(const ParcMotionTables* tables, const int
                                        int32_t num_steps, const float* root_xy_offset, const ParcCharModel* model,
                                        const ParcFrameOut* frame, const ParcFkOut* fk, const ParcHeightfield* hf,
                                        const ParcObsSpec* obs, float* obs_out, void* stream) {
-  return launch_query(true, tables, motion_ids, motion_times, nullptr, time_offsets, num_steps, root_xy_offset, n,
-                      model, frame, fk, hf, obs, obs_out, stream);
+  if (num_steps < 1) return PARC_E_SIZE;
+  if (n > 0 && !motion_times) return PARC_E_NULL;
+  return query_basic(tables, motion_ids, motion_times, nullptr, time_offsets, num_steps, root_xy_offset, n, model,
+                     frame, fk, hf, obs, obs_out, stream);
 }
 
 extern "C" int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_ids,
                                      const int64_t* frame_idxs, int64_t n, const ParcCharModel* model,
                                      const ParcFrameOut* frame, const ParcFkOut* fk, void* stream) {
-  return launch_query(false, tables, motion_ids, nullptr, frame_idxs, nullptr, 1, nullptr, n, model, frame, fk,
-                      nullptr, nullptr, nullptr, stream);
+  if (n > 0 && !frame_idxs) return PARC_E_NULL;
+  if (!frame_idxs) {                        // n == 0: still validate the remaining arguments as a blended query of 0
+    static const int64_t dummy = 0;
+    frame_idxs = &dummy;
+  }
+  return query_basic(tables, motion_ids, nullptr, frame_idxs, nullptr, 1, nullptr, n, model, frame, fk, nullptr,
+                     nullptr, nullptr, stream);
 }
 
 extern "C" int parc_selftest_grid_index(float min_coord, float cell_size, int32_t dim, uint64_t* mismatches_dev,

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ParcBodyPoints, ParcCharModel, ParcCharState, ParcDoneSpec, ParcSimStep, ParcKeyBodies, ParcClipMeta, ParcFkOut,
+from ._lib import (ParcQueryArgs, ParcBodyPoints, ParcCharModel, ParcCharState, ParcDoneSpec, ParcSimStep, ParcKeyBodies, ParcClipMeta, ParcFkOut,
                    ParcFrameOut, ParcHeightfield, ParcMotionTables, ParcObsSpec, ParcRowLayout, ParcTerrainBatch, check,
                    f32c, ptr, require_cuda, stream_ptr)
 
@@ -193,10 +193,13 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
                  want_frame: bool = True, want_contacts: bool = True, want_index: bool = False,
                  want_fk: bool = False, hf: Optional[HeightfieldDesc] = None,
                  obs_tmpl: Optional[torch.Tensor] = None, obs_relative: bool = True, obs_min_h: float = -3.0,
-                 obs_max_h: float = 3.0, out: Optional[dict] = None) -> dict:
+                 obs_max_h: float = 3.0, out: Optional[dict] = None, fast_heading: bool = False,
+                 error_flags: Optional[torch.Tensor] = None) -> dict:
     """One launch of the fused kernel.  Exactly one of motion_times (blended query,
     MotionLib.calc_motion_frame) or frame_idxs (MotionLib.get_motion_frame) must be given.
-    Returns a dict of output tensors; `out` may carry preallocated tensors to reuse."""
+    Returns a dict of output tensors; `out` may carry preallocated tensors to reuse.
+    `error_flags` (int32 [1] on the ids' device): the kernel ORs PARC_QUERY_ERR_* bits into it when a clip id / frame
+    index is out of range (see `raise_query_errors`)."""
     require_cuda(motion_ids, motion_times, frame_idxs)
     dev = motion_ids.device
     # ids may carry any leading shape (the reference gathers with whatever it is handed): flatten here, restore below
@@ -217,7 +220,8 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
 
     def buf(name, shape, dtype=torch.float32):
         t = res.get(name)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+        if (t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev
+                or not t.is_contiguous()):
             t = torch.empty(shape, dtype=dtype, device=dev)
             res[name] = t
         return t
@@ -241,98 +245,146 @@ def motion_query(tables: PackedTables, model: ParcCharModel, motion_ids: torch.T
         fk.body_pos = buf("body_pos", (N, J, 3)).data_ptr()
         fk.body_rot = buf("body_rot", (N, J, 4)).data_ptr()
     tb = tables.c_struct(model)
-    lib = _lib.load()
+    qa = ParcQueryArgs()
+    qa.tables, qa.model, qa.frame = C.addressof(tb), C.addressof(model), C.addressof(fo)
+    qa.motion_ids, qa.n = ids.data_ptr(), N
+    if want_fk:
+        qa.fk = C.addressof(fk)
+    qa.flags = _lib.PARC_QUERY_FAST_HEADING if fast_heading else 0
+    if error_flags is not None:
+        assert error_flags.dtype == torch.int32 and error_flags.device == dev
+        qa.error_flags = error_flags.data_ptr()
+    keep = [tb, fo, fk, ids]
+    if motion_times is not None:
+        assert frame_idxs is None
+        times = f32c(motion_times)
+        qa.motion_times = times.data_ptr()
+        keep.append(times)
+        if obs_tmpl is not None:
+            assert hf is not None
+            require_cuda(hf.hf, obs_tmpl)
+            tm = f32c(obs_tmpl)      # if this made a copy, the allocator's stream ordering keeps it valid
+            hfs, obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
+            qa.hf, qa.obs = C.addressof(hfs), C.addressof(obs)
+            qa.obs_out = buf("obs", (N, int(tm.shape[0]))).data_ptr()
+            keep += [tm, hfs, obs]
+    else:
+        fi = frame_idxs.to(torch.int64).contiguous()
+        qa.frame_idxs = fi.data_ptr()
+        keep.append(fi)
     with torch.cuda.device(dev):
-        if motion_times is not None:
-            assert frame_idxs is None
-            times = f32c(motion_times)
-            obs_ptr, hfs, obs = None, None, None
-            if obs_tmpl is not None:
-                assert hf is not None
-                require_cuda(hf.hf, obs_tmpl)
-                tm = f32c(obs_tmpl)      # if this made a copy, the allocator's stream ordering keeps it valid
-                hfs, obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
-                obs_ptr = buf("obs", (N, int(tm.shape[0]))).data_ptr()
-            rc = lib.parc_motion_query(C.byref(tb), ids.data_ptr(), times.data_ptr(), N, C.byref(model),
-                                       C.byref(fo), C.byref(fk) if want_fk else None,
-                                       C.byref(hfs) if hfs is not None else None,
-                                       C.byref(obs) if obs is not None else None, obs_ptr, stream_ptr(dev))
-            check(rc, "parc_motion_query")
-        else:
-            fi = frame_idxs.to(torch.int64).contiguous()
-            rc = lib.parc_get_motion_frame(C.byref(tb), ids.data_ptr(), fi.data_ptr(), N, C.byref(model),
-                                           C.byref(fo), C.byref(fk) if want_fk else None, stream_ptr(dev))
-            check(rc, "parc_get_motion_frame")
+        rc = _lib.load().parc_motion_query_ex(C.byref(qa), stream_ptr(dev))
+    check(rc, "parc_motion_query_ex")
+    del keep
     if len(lead) != 1:
         return {k: v.reshape(*lead, *v.shape[1:]) for k, v in res.items()}
     return res
+
+
+QUERY_OUTPUTS = ("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_vel", "contacts", "body_pos",
+                 "body_rot", "obs")
+
+
+def raise_query_errors(error_flags: torch.Tensor, what: str = "motion query"):
+    """Host check of the device error word a query ORs its PARC_QUERY_ERR_* bits into (synchronises).  Mirrors the
+    reference, whose gathers raise IndexError on a clip id / frame index outside the tables."""
+    bits = int(error_flags.item())
+    if bits:
+        error_flags.zero_()
+        msgs = []
+        if bits & _lib.PARC_QUERY_ERR_CLIP_ID:
+            msgs.append("motion id out of range")
+        if bits & _lib.PARC_QUERY_ERR_FRAME_IDX:
+            msgs.append("frame index out of range for its clip")
+        raise IndexError(f"{what}: " + "; ".join(msgs))
 
 
 class MotionQueryPlan:
     """A fused query(+FK)(+obs) launch with every argument struct prebuilt: `launch()` is one ctypes call
     (~2 us of host time instead of ~40 us of Python), for callers that step the same buffers every control
     tick -- the tracker's per-step query is exactly that.  Inputs are read from `ids` / `times` (write new
-    values into them in place, or build one plan per input buffer); outputs land in `self.out`."""
+    values into them in place, or build one plan per input buffer); outputs land in `self.out`.
+
+    outputs: names out of QUERY_OUTPUTS to produce (default: all the plan's options allow) -- a caller that only
+        consumes e.g. ("body_pos", "obs") saves the other stores and, end to end, their read-back.
+    pdl: launch with programmatic stream serialisation (include/parc_b200.h: PARC_QUERY_PDL); with
+        pdl_early_inputs=True the caller guarantees ids / times / offsets are not written by the previous kernel of
+        the launch stream, and the whole read side overlaps that kernel's tail.
+    variant: 0 = by batch size, 1..4 force an instantiation (tuning)."""
 
     def __init__(self, tables: PackedTables, model: ParcCharModel, ids: torch.Tensor, times: torch.Tensor, *,
                  want_contacts: bool = True, want_fk: bool = True, hf: Optional[HeightfieldDesc] = None,
                  obs_tmpl: Optional[torch.Tensor] = None, obs_relative: bool = True, obs_min_h: float = -3.0,
                  obs_max_h: float = 3.0, out: Optional[dict] = None, time_offsets: Optional[torch.Tensor] = None,
-                 root_xy_offset: Optional[torch.Tensor] = None):
-        require_cuda(ids, times, tables.rows, time_offsets, root_xy_offset)
+                 root_xy_offset: Optional[torch.Tensor] = None, outputs: Optional[Tuple[str, ...]] = None,
+                 fast_heading: bool = False, pdl: bool = False, pdl_early_inputs: bool = False, variant: int = 0,
+                 error_flags: Optional[torch.Tensor] = None):
+        require_cuda(ids, times, tables.rows, time_offsets, root_xy_offset, error_flags)
         assert ids.dtype == torch.int64 and times.dtype == torch.float32 and ids.is_contiguous() and times.is_contiguous()
-        self._keep = (tables, model, ids, times, hf, obs_tmpl, time_offsets, root_xy_offset)
+        assert ids.shape == times.shape and ids.dim() == 1
+        self._keep = (tables, model, ids, times, hf, obs_tmpl, time_offsets, root_xy_offset, error_flags)
         self.device = ids.device
         E = int(ids.shape[0])                    # entries (environments)
         S = 1 if time_offsets is None else int(time_offsets.shape[0])
         N, J, D = E * S, model.num_bodies, model.dof_size
         self.n = N
         self.out = {} if out is None else out
+        if outputs is not None:
+            unknown = set(outputs) - set(QUERY_OUTPUTS)
+            assert not unknown, f"unknown outputs {sorted(unknown)}"
+        want = (lambda name: True) if outputs is None else (lambda name: name in outputs)
 
         def buf(name, shape):
             t = self.out.get(name)
-            if t is None or tuple(t.shape) != tuple(shape) or t.device != self.device:
+            if (t is None or tuple(t.shape) != tuple(shape) or t.device != self.device or t.dtype != torch.float32
+                    or not t.is_contiguous()):
                 t = torch.empty(shape, dtype=torch.float32, device=self.device)
                 self.out[name] = t
             return t
 
         self._fo = ParcFrameOut()
-        self._fo.root_pos = buf("root_pos", (N, 3)).data_ptr()
-        self._fo.root_rot = buf("root_rot", (N, 4)).data_ptr()
-        self._fo.root_vel = buf("root_vel", (N, 3)).data_ptr()
-        self._fo.root_ang_vel = buf("root_ang_vel", (N, 3)).data_ptr()
-        self._fo.joint_rot = buf("joint_rot", (N, J - 1, 4)).data_ptr()
-        self._fo.dof_vel = buf("dof_vel", (N, D)).data_ptr()
-        if want_contacts:
+        for name, shape in (("root_pos", (N, 3)), ("root_rot", (N, 4)), ("root_vel", (N, 3)), ("root_ang_vel", (N, 3)),
+                            ("joint_rot", (N, J - 1, 4)), ("dof_vel", (N, D))):
+            if want(name):
+                setattr(self._fo, name, buf(name, shape).data_ptr())
+        if want_contacts and want("contacts"):
             self._fo.contacts = buf("contacts", (N, J)).data_ptr()
         self._fk = ParcFkOut()
-        if want_fk:
+        if want_fk and want("body_pos"):
             self._fk.body_pos = buf("body_pos", (N, J, 3)).data_ptr()
+        if want_fk and want("body_rot"):
             self._fk.body_rot = buf("body_rot", (N, J, 4)).data_ptr()
         self._tb = tables.c_struct(model)
         self._hf = self._obs = None
-        self._obs_ptr = None
-        if obs_tmpl is not None:
+        qa = ParcQueryArgs()
+        qa.tables, qa.model, qa.frame, qa.fk = (C.addressof(self._tb), C.addressof(model), C.addressof(self._fo),
+                                               C.addressof(self._fk))
+        qa.motion_ids, qa.motion_times, qa.n = ids.data_ptr(), times.data_ptr(), E
+        if obs_tmpl is not None and want("obs"):
             assert hf is not None
+            require_cuda(hf.hf, obs_tmpl)
             tm = f32c(obs_tmpl)
             self._keep += (tm,)
             self._hf, self._obs = hf.c_struct(), _obs_struct(tm, obs_relative, obs_min_h, obs_max_h)
-            self._obs_ptr = buf("obs", (E, int(tm.shape[0]))).data_ptr()
-        lib = _lib.load()
-        tail = (C.byref(model), C.byref(self._fo), C.byref(self._fk) if want_fk else None,
-                C.byref(self._hf) if self._hf is not None else None,
-                C.byref(self._obs) if self._obs is not None else None, self._obs_ptr)
-        if time_offsets is None and root_xy_offset is None:
-            self._fn = lib.parc_motion_query
-            self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E) + tail
-        else:
-            assert time_offsets is None or (time_offsets.dtype == torch.float32 and time_offsets.is_contiguous())
-            if root_xy_offset is not None:       # [E,2]: where each env's motion sits on the shared terrain
-                assert root_xy_offset.dtype == torch.float32 and root_xy_offset.is_contiguous()
-                assert tuple(root_xy_offset.shape) == (E, 2)
-            self._fn = lib.parc_motion_query_steps
-            self._args = (C.byref(self._tb), ids.data_ptr(), times.data_ptr(), E, ptr(time_offsets), S,
-                          ptr(root_xy_offset)) + tail
+            qa.hf, qa.obs = C.addressof(self._hf), C.addressof(self._obs)
+            qa.obs_out = buf("obs", (E, int(tm.shape[0]))).data_ptr()
+        if time_offsets is not None:
+            assert time_offsets.dtype == torch.float32 and time_offsets.is_contiguous()
+            qa.time_offsets, qa.num_steps = time_offsets.data_ptr(), S
+        if root_xy_offset is not None:           # [E,2]: where each env's motion sits on the shared terrain
+            assert root_xy_offset.dtype == torch.float32 and root_xy_offset.is_contiguous()
+            assert tuple(root_xy_offset.shape) == (E, 2)
+            qa.root_xy_offset = root_xy_offset.data_ptr()
+        if error_flags is not None:
+            assert error_flags.dtype == torch.int32 and error_flags.device == self.device
+            qa.error_flags = error_flags.data_ptr()
+        self.error_flags = error_flags
+        qa.flags = ((_lib.PARC_QUERY_FAST_HEADING if fast_heading else 0) | (_lib.PARC_QUERY_PDL if pdl else 0)
+                    | (_lib.PARC_QUERY_PDL_EARLY_INPUTS if (pdl and pdl_early_inputs) else 0))
+        qa.variant = int(variant)
+        self._qa = qa
+        self._fn = _lib.load().parc_motion_query_ex
+        self._args = (C.byref(qa),)
 
     def launch(self, stream: Optional[int] = None) -> dict:
         """Enqueue on `stream` (a raw cudaStream_t; default = torch's current stream of the plan's
@@ -342,23 +394,20 @@ class MotionQueryPlan:
         rc = self._fn(*self._args, stream)
         _lib.LAUNCHES[0] += 1
         if rc != 0:
-            check(rc, "parc_motion_query")
+            check(rc, "parc_motion_query_ex")
         return self.out
+
+    def check_errors(self):
+        """Raise IndexError if any launch since the last check saw an out-of-range clip id (synchronises)."""
+        if self.error_flags is not None:
+            raise_query_errors(self.error_flags)
 
     def capture(self) -> "torch.cuda.CUDAGraph":
         """Record the launch in a CUDA graph (one kernel node).  `replay()` then costs a graph launch, which on
         B200 reaches the SMs ~1.8 us sooner than a stream launch of the same kernel (measured: 5.6 vs 7.5 us event
         to event for an empty kernel of this grid) -- a tenth of the whole 4096-env query.  The buffers the plan was
         built over stay the inputs / outputs of every replay."""
-        with torch.cuda.device(self.device):
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                self.launch()                                   # warm-up outside the capture
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self.launch()
+        self._graph = capture_launches([self])
         return self._graph
 
     def replay(self) -> dict:
@@ -366,6 +415,24 @@ class MotionQueryPlan:
         self._graph.replay()
         _lib.LAUNCHES[0] += 1
         return self.out
+
+
+def capture_launches(plans) -> "torch.cuda.CUDAGraph":
+    """Record `plan.launch()` of every plan, in order, into ONE CUDA graph on the plans' device (kernel nodes only;
+    PDL launches become programmatic-dependency edges).  Replaying it enqueues the whole sequence with one host call --
+    the tracker holds such a graph per control step, a sweep holds one per chunk."""
+    dev = plans[0].device
+    with torch.cuda.device(dev):
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            plans[0].launch()                                   # warm-up outside the capture (module load)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for pl in plans:
+                pl.launch()
+    return graph
 
 
 # ----------------------------------------------------------------------------------------------

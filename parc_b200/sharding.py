@@ -60,6 +60,46 @@ def all_gather_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Te
     return torch.cat(pieces, dim=0)
 
 
+class AllGatherPlan:
+    """`all_gather_shards` over FIXED buffers, for callers that gather every step (config 4: each rank's slice of
+    `body_pos` / `obs` -> the full batch on every rank).  The global tensor is allocated once; with equal shards the
+    collective writes straight into it (one `all_gather_into_tensor`, no staging copy, no concatenation); ragged
+    shards go through one padded staging buffer.  `local` must be the same tensor on every call (e.g. a
+    `MotionQueryPlan` output)."""
+
+    def __init__(self, local: torch.Tensor, n_total: int, group=None):
+        self.rank, self.world = world()
+        self.local, self.n_total, self.group = local, int(n_total), group
+        rest = tuple(local.shape[1:])
+        lo, hi = shard_bounds(self.n_total, self.rank, self.world)
+        assert local.shape[0] == hi - lo and local.is_contiguous()
+        self.equal = self.n_total % self.world == 0
+        if self.world == 1:
+            self.out = local
+        elif self.equal:
+            self.out = local.new_empty((self.n_total,) + rest)
+        else:
+            per = (self.n_total + self.world - 1) // self.world
+            self._padded = local.new_zeros((per,) + rest)
+            self._stage = local.new_empty((self.world * per,) + rest)
+            self.out = local.new_empty((self.n_total,) + rest)
+            self._per = per
+
+    def run(self) -> torch.Tensor:
+        """Enqueue the gather behind the work already queued on the current stream; returns the global tensor."""
+        if self.world == 1:
+            return self.out
+        if self.equal:
+            dist.all_gather_into_tensor(self.out, self.local, group=self.group)
+            return self.out
+        self._padded[:self.local.shape[0]].copy_(self.local)
+        dist.all_gather_into_tensor(self._stage, self._padded, group=self.group)
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.n_total, r, self.world)
+            self.out[lo:hi].copy_(self._stage[r * self._per:r * self._per + (hi - lo)])
+        return self.out
+
+
 def gather_shards_to(local: torch.Tensor, n_total: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
     """Like all_gather_shards but only `dst` receives the result (others get None)."""
     rank, w = world()

@@ -321,37 +321,147 @@ def test_ray_obs_vs_golden():
     assert mism.float().mean() < 1e-3
 
 
-def test_grid_obs_vs_golden():
+def test_grid_obs_vs_golden(O):
     from parc_b200.util.terrain_util import sample_hf_z_on_terrain
     g = golden("obs_golden.npz")
     t = _civ_terrain()
     z = sample_hf_z_on_terrain(t, dev(g["root_pos"][:16, 0:2]), dev(g["heading"][:16]), 0.2, 0.2, 15, 15, 15, 15).cpu()
     exp = torch.tensor(g["grid_obs"])
     assert z.shape == (16, 31, 31)
-    assert (z != exp).float().mean() < 2e-3      # only cell-border samples may differ
+    # every differing sample must sit within 8 ulp of a cell border (GPU vs host sin / cos of the heading)
+    ot = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
+    tmpl = O.grid_template(0.2, 0.2, 15, 15, 15, 15)
+    pts = O.rotate_2d(tmpl, torch.tensor(g["heading"][:16]).view(16, 1, 1)) + torch.tensor(g["root_pos"][:16, 0:2]).view(16, 1, 1, 2)
+    assert torch.equal(O.hf_sample(ot, pts), exp), "oracle restatement of the golden grid observation"
+    border = _border_mask(O.grid_coord(ot, pts)).view(16, 31, 31)
+    mism = z != exp
+    assert not (mism & ~border).any(), f"{int((mism & ~border).sum())} mismatches away from cell borders"
+    assert mism.float().mean() < 2e-3
 
 
-def test_fused_obs_vs_oracle(golden_lib, O, oracle_tables):
+@pytest.mark.parametrize("fast_heading", [False, True])
+def test_fused_obs_vs_oracle(golden_lib, O, oracle_tables, fast_heading):
+    """The fused observation against the oracle, two ways.  (1) Against the oracle evaluated on the kernel's OWN
+    root position / rotation outputs (which are checked to 1e-5 elsewhere): the only differences left are the last
+    bits of atan2 / sin / cos, so every mismatching sample must lie within 8 ulp of a cell border -- the bar of the
+    stand-alone observation kernel.  (2) Against the all-oracle chain (CPU slerp -> heading -> samples), where the
+    heading additionally inherits the few-ulp difference of the slerped rotation: 64-ulp mask."""
     g = golden("obs_golden.npz")
     t = _civ_terrain()
     gen = torch.Generator().manual_seed(11)
     n = 2048
     ids = torch.zeros(n, dtype=torch.long)
     times = torch.rand(n, generator=gen) * oracle_tables.lengths[0]
-    r = golden_lib.calc_motion_frame_fk_obs(ids.cuda(), times.cuda(), hf_desc=t.hf_desc(), obs_tmpl=dev(g["tmpl"]))
-    ref = O.calc_motion_frame(oracle_tables, ids, times)
+    r = golden_lib.calc_motion_frame_fk_obs(ids.cuda(), times.cuda(), hf_desc=t.hf_desc(), obs_tmpl=dev(g["tmpl"]),
+                                            fast_heading=fast_heading)
     ot = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
-    heading = O.calc_heading(ref[1])
     tmpl = torch.tensor(g["tmpl"])
+    obs = r["obs"].cpu()
+    # (1) oracle on the kernel's own frame outputs
+    rp, rr = r["root_pos"].cpu(), r["root_rot"].cpu()
+    heading = O.calc_heading(rr)
+    exp = O.ray_obs(ot, rp, heading, tmpl)
+    coord = O.grid_coord(ot, O.ray_obs_points(rp, heading, tmpl))
+    mism = obs != exp
+    border = _border_mask(coord, ulps=8 if not fast_heading else 16).view(n, 441)
+    assert not (mism & ~border).any(), f"{int((mism & ~border).sum())} mismatches away from cell borders (own frame)"
+    assert mism.float().mean() < 5e-4
+    # (2) all-oracle chain
+    ref = O.calc_motion_frame(oracle_tables, ids, times)
+    heading = O.calc_heading(ref[1])
     exp = O.ray_obs(ot, ref[0], heading, tmpl)
     coord = O.grid_coord(ot, O.ray_obs_points(ref[0], heading, tmpl))
-    obs = r["obs"].cpu()
     mism = obs != exp
-    border = _border_mask(coord, ulps=64).view(n, 441)   # heading itself is an atan2 of GPU-vs-host values
+    border = _border_mask(coord, ulps=64).view(n, 441)
     assert not (mism & ~border).any(), f"{int((mism & ~border).sum())} mismatches away from cell borders"
     assert mism.float().mean() < 1e-3
     assert_close(r["body_pos"], O.forward_kinematics(O.CharModel.from_npz(__import__("os").path.join(
         __import__("conftest").GOLDEN, "humanoid_model.npz")), ref[0], ref[1], ref[4])[0], what="fused body_pos")
+
+
+def test_out_of_range_ids_are_flagged_not_read(golden_lib):
+    """The reference raises IndexError (CPU) / a device assert (CUDA) on a clip id or frame outside the tables.
+    Here the kernel answers the entry with clip 0 / the nearest valid frame, never reads out of bounds, and sets an
+    error bit the mirror turns into IndexError."""
+    M = golden_lib.num_motions()
+    ids = torch.tensor([0, 1, M, -1, 2], device="cuda:0")
+    times = torch.zeros(5, device="cuda:0")
+    r = golden_lib.calc_motion_frame(ids, times)           # lazily checked: no exception yet
+    with pytest.raises(IndexError, match="motion id out of range"):
+        golden_lib.check_query_errors()
+    golden_lib.check_query_errors()                        # the word is cleared by the raise
+    ok = golden_lib.calc_motion_frame(torch.tensor([0, 1, 0, 0, 2], device="cuda:0"), times)
+    for a, b in zip(r, ok):
+        assert torch.equal(a, b)                           # bad ids answered as clip 0
+    nf = int(golden_lib._motion_num_frames[1].item())
+    fr = golden_lib.get_motion_frame(torch.tensor([1, 1, 1], device="cuda:0"),
+                                     torch.tensor([nf, -3, nf - 1], device="cuda:0"))
+    with pytest.raises(IndexError, match="frame index out of range"):
+        golden_lib.check_query_errors()
+    ok = golden_lib.get_motion_frame(torch.tensor([1, 1, 1], device="cuda:0"),
+                                     torch.tensor([nf - 1, 0, nf - 1], device="cuda:0"))
+    for a, b in zip(fr, ok):
+        assert torch.equal(a, b)
+    golden_lib.check_query_errors()
+    golden_lib.validate_ids = True
+    try:
+        with pytest.raises(IndexError):
+            golden_lib.calc_motion_frame(ids, times)
+        golden_lib.calc_motion_frame(ids.clamp(0, M - 1), times)
+    finally:
+        golden_lib.validate_ids = False
+
+
+def test_empty_observation_template_is_a_no_op(golden_lib):
+    """P == 0: the sweep must not read an unstaged template; the frame / FK outputs are unaffected."""
+    t = _civ_terrain()
+    ids = torch.zeros(33, dtype=torch.long, device="cuda:0")
+    times = torch.linspace(0, 3, 33, device="cuda:0")
+    a = golden_lib.calc_motion_frame_fk_obs(ids, times, hf_desc=t.hf_desc(), obs_tmpl=torch.zeros(0, 2, device="cuda:0"))
+    b = golden_lib.calc_motion_frame_fk_obs(ids, times)
+    assert a["obs"].shape == (33, 0)
+    for k in ("root_pos", "joint_rot", "body_pos", "body_rot"):
+        assert torch.equal(a[k], b[k])
+
+
+def test_query_variants_pdl_and_output_selection_are_bit_identical(golden_lib):
+    """Every instantiation (sweep depth / characters per warp), the programmatic-dependent-launch forms and a plan
+    restricted to some outputs must produce the same bits as the default launch."""
+    g = golden("obs_golden.npz")
+    t = _civ_terrain()
+    gen = torch.Generator().manual_seed(5)
+    n = 3001
+    ids = torch.randint(0, golden_lib.num_motions(), (n,), generator=gen).cuda()
+    times = (torch.rand(n, generator=gen) * 9.0 - 0.5).cuda()
+    tmpl = dev(g["tmpl"])
+    base = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl).launch()
+    torch.cuda.synchronize()
+    base = {k: v.clone() for k, v in base.items()}
+    for variant in (1, 2, 3, 4):
+        got = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, variant=variant).launch()
+        for k, v in base.items():
+            assert torch.equal(got[k], v), f"variant {variant}: {k}"
+    for early in (False, True):
+        pl = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, pdl=True, pdl_early_inputs=early)
+        for _ in range(3):                         # back to back: each launch overlaps the previous one's tail
+            got = pl.launch()
+        for k, v in base.items():
+            assert torch.equal(got[k], v), f"pdl early={early}: {k}"
+    from parc_b200 import ops
+    plans = [golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, pdl=True, pdl_early_inputs=True,
+                                        out={}) for _ in range(4)]
+    graph = ops.capture_launches(plans)
+    for pl in plans:
+        for v in pl.out.values():
+            v.zero_()
+    graph.replay()
+    for pl in plans:
+        for k, v in base.items():
+            assert torch.equal(pl.out[k], v), f"graph of pdl launches: {k}"
+    sel = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, outputs=("body_pos", "obs"), out={})
+    got = sel.launch()
+    assert set(got) == {"body_pos", "obs"}
+    assert torch.equal(got["body_pos"], base["body_pos"]) and torch.equal(got["obs"], base["obs"])
 
 
 # ----------------------------------------------------------------------------------------- SDF + losses

@@ -48,6 +48,10 @@ def _worker(rank, world_size, port, n, q):
         assert mine.shape[0] == hi - lo and torch.equal(mine, full[lo:hi])
         back = sharding.all_gather_shards(mine * 2.0, n)
         assert torch.equal(back, full * 2.0)
+        plan = sharding.AllGatherPlan((mine * 3.0).contiguous(), n)       # fixed-buffer form (config 4's per-step gather)
+        assert plan.equal == (n % world_size == 0)
+        for _ in range(2):
+            assert torch.equal(plan.run(), full * 3.0)
         on0 = sharding.gather_shards_to(mine + 1.0, n, dst=0)
         assert (on0 is None) == (rank != 0)
         if rank == 0:
