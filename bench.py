@@ -555,6 +555,15 @@ def leg_e2e(ctx):
     for w in range(4):
         issue(w)
         wait(w)
+    # probe: the read-back alone (pinned, one copy of the whole result buffer), so the line explains its own e2e figure
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(sets[0][0]):
+        pe0.record()
+        for _ in range(8):
+            sets[0][4].copy_(sets[0][3], non_blocking=True)
+        pe1.record()
+    pe1.synchronize()
+    d2h_gbps = total * 4 * 8 / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
     barrier(ctx)
     t0 = time.perf_counter()
     issue(0)
@@ -566,7 +575,9 @@ def leg_e2e(ctx):
     e2e_s = dist_max(ctx, time.perf_counter() - t0)
     ctx.launches += K
     return {"value": args.envs * ctx.world * BODIES * K / e2e_s, "unit": UNIT,
-            "h2d_bytes_per_step": args.envs * (8 + 4), "d2h_bytes_per_step": total * 4}
+            "h2d_bytes_per_step": args.envs * (8 + 4), "d2h_bytes_per_step": total * 4,
+            "d2h_probe_GBps": d2h_gbps, "ms_per_step": e2e_s / K * 1e3,
+            "bound": "host link: the read-back of every output (pinned, one copy per step, double-buffered)"}
 
 
 # ---- cfg4: 65 536 envs, one GPU at N = 1, sharded contiguously over the ranks at N > 1 -------------------------------

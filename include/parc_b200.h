@@ -210,7 +210,9 @@ int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_
  *                                          behind the previous kernel.
  *   variant      0 = chosen by batch size; 1..4 force one instantiation (tuning / tests): 1 = two characters per warp,
  *                whole template sweep in flight (<= 128 registers); 2 = quarter sweep in flight, 64 registers;
- *                3 = half sweep, 80 registers; 4 = one character per warp. */
+ *                3 = half sweep, 80 registers; 4 = one character per warp; 5 = as 1 with every store of a warp's first
+ *                work item deferred behind its forward kinematics (for PARC_QUERY_PDL_EARLY_INPUTS: read AND compute
+ *                side overlap the previous kernel, only the stores are ordered behind it). */
 #define PARC_QUERY_FAST_HEADING 1u
 #define PARC_QUERY_PDL 2u
 #define PARC_QUERY_PDL_EARLY_INPUTS 4u
@@ -317,9 +319,21 @@ typedef struct ParcTerrainBatch {
 /* a13: terrain_util.points_hf_sdf (util/terrain_util.py:1835-1893): exact min over ALL cells of the
  * box SDF (util/geom_util.py:122-143); solid columns [base_z, hf] or, if inverted, air columns
  * [hf, -base_z] with the result negated.  points [B,N,3] -> sdf_out [B,N]; arg_out (int32 [B,N], flat
- * cell index ix*Y+iy of the minimum, first index on ties) may be NULL. */
+ * cell index ix*Y+iy of the minimum, first index on ties) may be NULL.  Any batch size (launches are chunked to the
+ * grid limit) and any terrain size: tiles up to ~200 KB are staged in shared memory, larger ones are scanned from
+ * global memory with the same exact result. */
 int parc_points_hf_sdf(const float* points, int64_t batch, int64_t n_points, const ParcTerrainBatch* terrain,
                        int32_t inverted, float* sdf_out, int32_t* arg_out, void* stream);
+
+/* Gradient of parc_points_hf_sdf with respect to the points -- what autograd yields through
+ * util/terrain_util.py:1835-1893 (the MDM's heightfield-collision loss and guidance back-propagate through it:
+ * diffusion/mdm.py:729-737, :1484-1496; util/terrain_util.py:1895-1949).  arg = arg_out of the forward call with
+ * the same points / terrain / inverted; g_sdf [B,N] upstream gradient; g_points_out [B,N,3] (overwritten).
+ * torch.min routes the gradient to the first arg-min cell; sdBox's sub-gradients follow autograd (clamp passes at
+ * the bound, norm'(0) = 0, abs'(0) = 0, max -> first index).  No gradient is produced for the heightfield. */
+int parc_points_hf_sdf_bwd(const float* points, int64_t batch, int64_t n_points, const ParcTerrainBatch* terrain,
+                           int32_t inverted, const int32_t* arg, const float* g_sdf, float* g_points_out,
+                           void* stream);
 
 /* Body surface samples: concatenated local points [S,3] (body-major) and per-body offsets
  * point_start[J+1] -- util/geom_util.py:788-870 produces the per-body lists. */
@@ -329,6 +343,18 @@ typedef struct ParcBodyPoints {
   int32_t num_points;           /* S */
   int32_t reserved;
 } ParcBodyPoints;
+
+/* Body surface points in world space, in the layout the reference's callers build with their per-body loop
+ * (util/terrain_util.py:1918-1936 motion_frames_hf_sdf_loss, diffusion/mdm.py:1006-1020 compute_point_hf_sdf):
+ * body_pos [B,F,J,3], body_rot [B,F,J,4] -> points_out [B, F*S, 3] where, inside a batch entry, body b's block
+ * starts at F * point_start[b] and holds [F, P_b] points frame-major:
+ *   points_out[i, F*start_b + f*P_b + k] = quat_rotate(body_rot[i,f,b], points[start_b + k]) + body_pos[i,f,b].
+ * _bwd is its VJP: g_points [B, F*S, 3] -> g_body_pos [B,F,J,3], g_body_rot [B,F,J,4] (either may be NULL). */
+int parc_body_points_fwd(const float* body_pos, const float* body_rot, int64_t batch, int64_t frames,
+                         int32_t num_bodies, const ParcBodyPoints* pts, float* points_out, void* stream);
+int parc_body_points_bwd(const float* body_rot, const float* g_points, int64_t batch, int64_t frames,
+                         int32_t num_bodies, const ParcBodyPoints* pts, float* g_body_pos, float* g_body_rot,
+                         void* stream);
 
 /* a14/a15: the body-point penetration and contact terms, forward AND gradient in one launch.
  * Per (sample b, frame f), with FK of (root_pos, root_rot, joint_rot)[b,f] done in-kernel:

@@ -638,6 +638,41 @@ def motion_opt_pen_contact(model: CharModel, tgt_root_pos, tgt_root_rot_expmap, 
     return w_penetration * pen + w_contact * con, pen, con
 
 
+def world_body_points(body_pos, body_rot, body_points):
+    """All bodies' surface points in world space, concatenated body-major exactly as the reference's callers do:
+    util/terrain_util.py:1918-1936 (motion_frames_hf_sdf_loss), diffusion/mdm.py:1006-1020 (compute_point_hf_sdf).
+    body_pos [B,F,J,3], body_rot [B,F,J,4] -> [B, sum_b F*P_b, 3]."""
+    B = body_pos.shape[0]
+    out = []
+    for b in range(body_pos.shape[2]):
+        cur = body_points[b].unsqueeze(0).unsqueeze(0)
+        out.append((quat_rotate(body_rot[..., b, :].unsqueeze(2), cur) + body_pos[..., b, :].unsqueeze(2)).view(B, -1, 3))
+    return torch.cat(out, dim=1)
+
+
+def hf_collision_loss(sdf):
+    """0.5 * sum(clamp(sdf, max=0)^2) -- diffusion/mdm.py:735 (training loss), :1493 (guidance)."""
+    return 0.5 * torch.sum(torch.square(torch.clamp(sdf, max=0.0)), dim=-1)
+
+
+def motion_frames_hf_sdf_loss(model: CharModel, motion_frames, body_points, hf, min_center, dxdy,
+                              interior_distance=True):
+    """util/terrain_util.py:1895-1949.  motion_frames [B,S,6+D] (root pos | root exp-map | DoFs), hf [B,X,Y],
+    min_center [B,2] -> (loss [B], world points [B,N,3], sdf [B,N]); base_z = -10."""
+    D = model.dof_size
+    root_pos = motion_frames[..., 0:3]
+    rq = exp_map_to_quat(motion_frames[..., 3:6])
+    jr = quat_w_positive(dof_to_rot(model, motion_frames[..., 6:6 + D]))
+    body_pos, body_rot = forward_kinematics(model, root_pos, rq, jr)
+    pts = world_body_points(body_pos, body_rot, body_points)
+    sdf = points_hf_sdf(pts, hf, min_center, dxdy, base_z=-10.0, inverted=interior_distance)
+    if interior_distance:
+        loss = 0.5 * torch.sum(torch.square(torch.clamp(sdf, max=0.0)), dim=-1)
+    else:
+        loss = 0.5 * torch.sum(torch.square(torch.clamp(sdf, min=0.0)), dim=-1)
+    return loss, pts, sdf
+
+
 # --------------------------------------------------------------------------
 # SURVEY section 8(f) row 1: contact labelling + heightfield masks
 # --------------------------------------------------------------------------

@@ -171,6 +171,9 @@ SIGNATURES = {
     "parc_selftest_grid_index": (C.c_int, [_F, _F, _I32, _V, _V]),
     "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _V, _V, _I32, _I64, _V, _I64, _V]),
     "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
+    "parc_points_hf_sdf_bwd": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V, _V]),
+    "parc_body_points_fwd": (C.c_int, [_V, _V, _I64, _I64, _I32, _P(ParcBodyPoints), _V, _V]),
+    "parc_body_points_bwd": (C.c_int, [_V, _V, _I64, _I64, _I32, _P(ParcBodyPoints), _V, _V, _V]),
     "parc_frames_fk": (C.c_int, [_V, _I64, _I32, _P(ParcCharModel), _V, _V, _V, _V, _V]),
     "parc_clip_label": (C.c_int, [_V, _I64, _I64, _I32, _P(ParcCharModel), _P(ParcBodyPoints), _P(ParcTerrainBatch),
                                   _P(ParcKeyBodies), _F, _V, _V, _V, _V, _V, _V, _V, _V]),

@@ -11,8 +11,6 @@
 //           penetration, solid column for contact), terrain tile staged in shared memory
 //   warp 0: per-body first-index min (contact), per-body gradient sums, FK VJP -> leaf gradients
 // The min is exact and tie-breaks on the first flat cell index, as torch.min does.
-#include <atomic>
-
 #include "parc_common.cuh"
 #include "parc_sdf.cuh"
 
@@ -21,17 +19,27 @@ namespace parc {
 // ------------------------------------------------------------------------------------------------
 // a13 stand-alone: points [B,N,3] -> sdf [B,N]
 // ------------------------------------------------------------------------------------------------
+// SMEM_TILE: the sample's heightfield tile is staged in shared memory; otherwise (tiles beyond PARC_SMEM_LIMIT) it is
+// read from global memory and only the cell-centre coordinates are staged.
+template <bool SMEM_TILE>
 __global__ void __launch_bounds__(256)
 points_hf_sdf_kernel(const float* __restrict__ points, int64_t n_points, const __grid_constant__ ParcTerrainBatch t,
                      int inverted, float* __restrict__ sdf, int32_t* __restrict__ arg) {
   extern __shared__ float smem[];
   const int X = t.dim_x, Y = t.dim_y;
-  float* s_hf = smem;
-  float* s_cx = s_hf + X * Y;
+  float* s_cx = smem;
   float* s_cy = s_cx + X;
+  float* s_hf = s_cy + Y;
   __shared__ float s_minmax[2];
   const int64_t b = blockIdx.y;
-  stage_terrain(t, b, s_hf, s_cx, s_cy, s_minmax);
+  const float* __restrict__ hfp;
+  if (SMEM_TILE) {
+    stage_terrain(t, b, s_hf, s_cx, s_cy, s_minmax);
+    hfp = s_hf;
+  } else {
+    stage_terrain_global(t, b, s_cx, s_cy, s_minmax);
+    hfp = t.hf + b * t.hf_batch_stride;
+  }
   __syncthreads();
   const float base = sample_base_z(t, b);
   const float hf_min = s_minmax[0], hf_max = s_minmax[1];
@@ -41,14 +49,41 @@ points_hf_sdf_kernel(const float* __restrict__ points, int64_t n_points, const _
     float v;
     int a;
     if (inverted) {
-      const SdfBest r = scan_cells<true, false>(s_hf, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
+      const SdfBest r = scan_cells<true, false>(hfp, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
       v = -1.0f * r.inv; a = r.arg_inv;
     } else {
-      const SdfBest r = scan_cells<false, true>(s_hf, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
+      const SdfBest r = scan_cells<false, true>(hfp, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
       v = r.sol; a = r.arg_sol;
     }
     sdf[b * n_points + i] = v;
     if (arg) arg[b * n_points + i] = a;
+  }
+}
+
+// VJP of the above with respect to the points: the min routes the gradient to the arg-min cell (first index on
+// ties, recorded by the forward launch), whose box SDF has the sub-gradient of sd_box_grad; inverted negates.
+// One thread per point; the cell's height / centre are read straight from global memory.
+__global__ void __launch_bounds__(256)
+points_hf_sdf_bwd_kernel(const float* __restrict__ points, int64_t batch, int64_t n_points,
+                         const __grid_constant__ ParcTerrainBatch t, int inverted, const int32_t* __restrict__ arg,
+                         const float* __restrict__ g_sdf, float* __restrict__ g_points) {
+  const int64_t total = batch * n_points;
+  const int Y = t.dim_y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / n_points;
+    const int cell = __ldg(arg + i);
+    const int ix = cell / Y, iy = cell - ix * Y;
+    const float* mc = t.min_center + b * t.min_center_stride;
+    const float cx = __ldg(t.x_nodes + ix) + __ldg(mc), cy = __ldg(t.y_nodes + iy) + __ldg(mc + 1);
+    const float h = __ldg(t.hf + b * t.hf_batch_stride + cell);
+    const float base = sample_base_z(t, b);
+    float cz, hz;
+    if (inverted) { const float top = -base; cz = (h + top) * 0.5f; hz = (top - h) * 0.5f; }
+    else { cz = (h + base) * 0.5f; hz = (h - base) * 0.5f; }
+    const float3 p = make_float3(__ldg(points + i * 3), __ldg(points + i * 3 + 1), __ldg(points + i * 3 + 2));
+    const float3 g = sd_box_grad(make_float3(p.x - cx, p.y - cy, p.z - cz), make_float3(t.half_dx, t.half_dy, hz));
+    const float s = inverted ? -__ldg(g_sdf + i) : __ldg(g_sdf + i);
+    g_points[i * 3] = s * g.x; g_points[i * 3 + 1] = s * g.y; g_points[i * 3 + 2] = s * g.z;
   }
 }
 
@@ -79,6 +114,7 @@ struct BodyLossParams {
   int want_grad;
 };
 
+template <bool SMEM_TILE>
 __global__ void __launch_bounds__(LOSS_THREADS)
 body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
@@ -88,18 +124,25 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
   const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
   const int S = p.pts.num_points;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* s_hf = smem;
-  float* s_cx = s_hf + X * Y;
+  float* s_cx = smem;
   float* s_cy = s_cx + X;
   int* s_body = reinterpret_cast<int*>(s_cy + Y);                    // [S] body of point
   float* s_lp = reinterpret_cast<float*>(s_body + S);                // [S][3] local points
   float* slab = s_lp + (size_t)S * 3 + (size_t)warp * ((size_t)S * 7 + PARC_MAX_BODIES * 9);
   float* s_bt = slab;                                                // [J][9] pos(3) rot(4) contact(1) winner(1)
   float* s_pt = slab + PARC_MAX_BODIES * 9;                          // [S][7]
+  float* s_tile = s_lp + (size_t)S * 3 + (size_t)LOSS_WARPS * ((size_t)S * 7 + PARC_MAX_BODIES * 9);   // [X*Y] last
 
   const int64_t b = blockIdx.y;
   stage_model(&sm, model_param);
-  stage_terrain(p.terrain, b, s_hf, s_cx, s_cy, s_minmax);
+  const float* __restrict__ s_hf;       // the sample's tile: shared memory, or global for tiles beyond PARC_SMEM_LIMIT
+  if (SMEM_TILE) {
+    stage_terrain(p.terrain, b, s_tile, s_cx, s_cy, s_minmax);
+    s_hf = s_tile;
+  } else {
+    stage_terrain_global(p.terrain, b, s_cx, s_cy, s_minmax);
+    s_hf = p.terrain.hf + b * p.terrain.hf_batch_stride;
+  }
   __syncthreads();
   const float hf_min = s_minmax[0], hf_max = s_minmax[1];
   const int J = sm.num_bodies;
@@ -238,14 +281,23 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
   }
 }
 
-static size_t terrain_smem_bytes(const ParcTerrainBatch* t) {
-  return ((size_t)t->dim_x * t->dim_y + t->dim_x + t->dim_y) * sizeof(float);
-}
+static size_t nodes_smem_bytes(const ParcTerrainBatch* t) { return ((size_t)t->dim_x + t->dim_y) * sizeof(float); }
+static size_t tile_smem_bytes(const ParcTerrainBatch* t) { return (size_t)t->dim_x * t->dim_y * sizeof(float); }
 
 static int check_terrain(const ParcTerrainBatch* t) {
   if (!t || !t->hf || !t->min_center || !t->x_nodes || !t->y_nodes) return PARC_E_NULL;
   if (t->dim_x <= 0 || t->dim_y <= 0 || t->hf_batch_stride < 0) return PARC_E_SIZE;
+  if ((int64_t)t->dim_x * t->dim_y >= (1ll << 31)) return PARC_E_SIZE;
   return PARC_OK;
+}
+
+// the terrain descriptor of samples [b0, ...) of a batch (launches are chunked to the grid's y limit)
+static ParcTerrainBatch terrain_from(const ParcTerrainBatch& t, int64_t b0) {
+  ParcTerrainBatch r = t;
+  r.hf += b0 * t.hf_batch_stride;
+  r.min_center += b0 * t.min_center_stride;
+  if (r.base_z) r.base_z += b0 * t.base_z_stride;
+  return r;
 }
 
 }  // namespace parc
@@ -255,28 +307,47 @@ using namespace parc;
 extern "C" int parc_points_hf_sdf(const float* points, int64_t batch, int64_t n_points,
                                   const ParcTerrainBatch* terrain, int32_t inverted, float* sdf_out,
                                   int32_t* arg_out, void* stream) {
-  if (batch < 0 || n_points < 0 || batch > 65535) return PARC_E_SIZE;
+  if (batch < 0 || n_points < 0) return PARC_E_SIZE;
   if (batch == 0 || n_points == 0) return PARC_OK;
   if (!points || !sdf_out) return PARC_E_NULL;
   int rc = check_terrain(terrain);
   if (rc) return rc;
-  const size_t smem = terrain_smem_bytes(terrain);
-  if (smem > 200 * 1024) return PARC_E_SIZE;          // terrain tile must fit one SM's shared memory
-  if (smem > 48 * 1024) {
-    // opt in to > 48 KB dynamic shared memory; only when the requirement grows (a monotonic high-water mark --
-    // the one piece of process-wide state, benign: setting the attribute again is idempotent)
-    static std::atomic<size_t> high_water{0};
-    if (smem > high_water.load(std::memory_order_relaxed)) {
-      cudaError_t e = cudaFuncSetAttribute(points_hf_sdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      high_water.store(smem, std::memory_order_relaxed);
-    }
-  }
+  // the tile goes to shared memory when it fits; larger terrains are scanned from global memory
+  const bool smem_tile = nodes_smem_bytes(terrain) + tile_smem_bytes(terrain) <= PARC_SMEM_LIMIT;
+  const size_t smem = nodes_smem_bytes(terrain) + (smem_tile ? tile_smem_bytes(terrain) : 0);
+  if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;     // only the cell-centre coordinates of a > 25 600-cell-wide grid
+  static SmemOptIn opt_tile, opt_global;
+  rc = smem_tile ? ensure_dynamic_smem(points_hf_sdf_kernel<true>, opt_tile, smem)
+                 : ensure_dynamic_smem(points_hf_sdf_kernel<false>, opt_global, smem);
+  if (rc) return rc;
   int64_t gx = (n_points + 255) / 256;
   if (gx > 4096) gx = 4096;
-  dim3 grid((unsigned)gx, (unsigned)batch);
-  points_hf_sdf_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, n_points, *terrain, inverted, sdf_out,
-                                                                  arg_out);
+  for (int64_t b0 = 0; b0 < batch; b0 += PARC_GRID_Y_MAX) {       // grid.y is limited to 65 535 samples per launch
+    const int64_t nb = batch - b0 < PARC_GRID_Y_MAX ? batch - b0 : PARC_GRID_Y_MAX;
+    const ParcTerrainBatch t = terrain_from(*terrain, b0);
+    dim3 grid((unsigned)gx, (unsigned)nb);
+    const float* pp = points + b0 * n_points * 3;
+    float* so = sdf_out + b0 * n_points;
+    int32_t* ao = arg_out ? arg_out + b0 * n_points : nullptr;
+    if (smem_tile) points_hf_sdf_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(pp, n_points, t, inverted, so, ao);
+    else points_hf_sdf_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(pp, n_points, t, inverted, so, ao);
+  }
+  return check_launch();
+}
+
+extern "C" int parc_points_hf_sdf_bwd(const float* points, int64_t batch, int64_t n_points,
+                                      const ParcTerrainBatch* terrain, int32_t inverted, const int32_t* arg,
+                                      const float* g_sdf, float* g_points_out, void* stream) {
+  if (batch < 0 || n_points < 0) return PARC_E_SIZE;
+  if (batch == 0 || n_points == 0) return PARC_OK;
+  if (!points || !arg || !g_sdf || !g_points_out) return PARC_E_NULL;
+  int rc = check_terrain(terrain);
+  if (rc) return rc;
+  const int64_t total = batch * n_points;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  points_hf_sdf_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(points, batch, n_points, *terrain, inverted,
+                                                                          arg, g_sdf, g_points_out);
   return check_launch();
 }
 
@@ -288,7 +359,7 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
   if (!model || !pts) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
-  if (batch < 0 || frames < 0 || batch > 65535 || pts->num_points <= 0) return PARC_E_SIZE;
+  if (batch < 0 || frames < 0 || pts->num_points <= 0) return PARC_E_SIZE;
   if (batch == 0 || frames == 0) return PARC_OK;
   if (!root_pos || !root_rot || !contacts || !pts->points || !pts->point_start) return PARC_E_NULL;
   if (model->num_bodies > 1 && !joint_rot) return PARC_E_NULL;
@@ -296,28 +367,21 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
   if (rc) return rc;
   if (!aligned16(root_rot) || !aligned16(joint_rot) || !aligned16(g_root_rot) || !aligned16(g_joint_rot))
     return PARC_E_ALIGN;
-  if (batch == 0 || frames == 0) return PARC_OK;
 
   BodyLossParams p;
-  p.root_pos = root_pos; p.root_rot = root_rot; p.joint_rot = joint_rot; p.contacts = contacts;
-  p.batch = batch; p.frames = frames; p.pts = *pts; p.terrain = *terrain;
-  p.w_pen = w_pen; p.w_contact = w_contact; p.pen_out = pen_out; p.contact_out = contact_out;
-  p.g_root_pos = g_root_pos; p.g_root_rot = g_root_rot; p.g_joint_rot = g_joint_rot;
+  p.frames = frames; p.pts = *pts;
+  p.w_pen = w_pen; p.w_contact = w_contact;
   p.want_grad = (g_root_pos || g_root_rot || g_joint_rot) ? 1 : 0;
 
   const size_t S = (size_t)pts->num_points;
-  const size_t smem = terrain_smem_bytes(terrain) + (S * (1 + 3) + LOSS_WARPS * (S * 7 + PARC_MAX_BODIES * 9)) * sizeof(float);
-  if (smem > 200 * 1024) return PARC_E_SIZE;
-  if (smem > 48 * 1024) {
-    // opt in to > 48 KB dynamic shared memory; only when the requirement grows (a monotonic high-water mark --
-    // the one piece of process-wide state, benign: setting the attribute again is idempotent)
-    static std::atomic<size_t> high_water{0};
-    if (smem > high_water.load(std::memory_order_relaxed)) {
-      cudaError_t e = cudaFuncSetAttribute(body_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      high_water.store(smem, std::memory_order_relaxed);
-    }
-  }
+  const size_t fixed = nodes_smem_bytes(terrain) + (S * (1 + 3) + LOSS_WARPS * (S * 7 + PARC_MAX_BODIES * 9)) * sizeof(float);
+  const bool smem_tile = fixed + tile_smem_bytes(terrain) <= PARC_SMEM_LIMIT;
+  const size_t smem = fixed + (smem_tile ? tile_smem_bytes(terrain) : 0);
+  if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;      // too many surface points for one CTA's slabs
+  static SmemOptIn opt_tile, opt_global;
+  rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true>, opt_tile, smem)
+                 : ensure_dynamic_smem(body_loss_kernel<false>, opt_global, smem);
+  if (rc) return rc;
   // one warp per frame, LOSS_WARPS frames in flight per CTA; amortise the terrain staging over several
   // rounds when there is plenty of work, keep the grid wide when there is not
   int64_t rounds = (batch * frames) / ((int64_t)148 * 16 * LOSS_WARPS);
@@ -325,7 +389,22 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
   if (rounds > 8) rounds = 8;
   const int64_t fpc = rounds * LOSS_WARPS;
   p.frames_per_cta = (int)fpc;
-  dim3 grid((unsigned)((frames + fpc - 1) / fpc), (unsigned)batch);
-  body_loss_kernel<<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+  const int J = model->num_bodies;
+  for (int64_t b0 = 0; b0 < batch; b0 += PARC_GRID_Y_MAX) {       // grid.y is limited to 65 535 samples per launch
+    const int64_t nb = batch - b0 < PARC_GRID_Y_MAX ? batch - b0 : PARC_GRID_Y_MAX;
+    const int64_t q0 = b0 * frames;
+    p.batch = nb;
+    p.terrain = terrain_from(*terrain, b0);
+    p.root_pos = root_pos + q0 * 3; p.root_rot = root_rot + q0 * 4;
+    p.joint_rot = joint_rot ? joint_rot + q0 * (J - 1) * 4 : nullptr;
+    p.contacts = contacts + q0 * J;
+    p.pen_out = pen_out ? pen_out + q0 : nullptr; p.contact_out = contact_out ? contact_out + q0 : nullptr;
+    p.g_root_pos = g_root_pos ? g_root_pos + q0 * 3 : nullptr;
+    p.g_root_rot = g_root_rot ? g_root_rot + q0 * 4 : nullptr;
+    p.g_joint_rot = g_joint_rot ? g_joint_rot + q0 * (J - 1) * 4 : nullptr;
+    dim3 grid((unsigned)((frames + fpc - 1) / fpc), (unsigned)nb);
+    if (smem_tile) body_loss_kernel<true><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+    else body_loss_kernel<false><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+  }
   return check_launch();
 }

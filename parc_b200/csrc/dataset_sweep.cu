@@ -7,7 +7,6 @@
 //   util/geom_util.py:80-111                          get_box_points_batch
 // and the front end every one of them repeats: exp_map_to_quat + dof_to_rot + forward_kinematics on
 // frames laid out [root_pos(3) | root exp-map(3) | joint DoFs(D)].
-#include <atomic>
 
 #include "parc_common.cuh"
 #include "parc_rotations.cuh"
@@ -104,12 +103,6 @@ struct LabelParams {
   int frames_per_cta;
   int mask_words;
 };
-
-// float atomic-min on a location that starts positive: int compare for v >= 0, unsigned for v < 0
-__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
-  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
-  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
-}
 
 __global__ void __launch_bounds__(LABEL_THREADS)
 clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__ ParcCharModel model_param) {
@@ -275,7 +268,7 @@ extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frame
   if (!model || !pts || !terrain || !keys) return PARC_E_NULL;
   int rc = parc_validate_model(model);
   if (rc) return rc;
-  if (batch < 0 || frames_per_clip < 0 || batch > 65535 || frame_stride < 6 + model->dof_size) return PARC_E_SIZE;
+  if (batch < 0 || frames_per_clip < 0 || frame_stride < 6 + model->dof_size) return PARC_E_SIZE;
   if (keys->num_feet < 0 || keys->num_feet > PARC_MAX_KEY_BODIES || keys->num_hands < 0 ||
       keys->num_hands > PARC_MAX_KEY_BODIES)
     return PARC_E_SIZE;
@@ -301,23 +294,35 @@ extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frame
   p.pts.num_points = (int)S;
   const size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + S * 4 +
                        (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words)) * 4;
-  if (smem > 200 * 1024) return PARC_E_SIZE;
-  if (smem > 48 * 1024) {
-    // opt in to > 48 KB dynamic shared memory; only when the requirement grows (a monotonic high-water mark --
-    // the one piece of process-wide state, benign: setting the attribute again is idempotent)
-    static std::atomic<size_t> high_water{0};
-    if (smem > high_water.load(std::memory_order_relaxed)) {
-      cudaError_t e = cudaFuncSetAttribute(clip_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      high_water.store(smem, std::memory_order_relaxed);
-    }
-  }
+  if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;       // per-clip labelling terrains are small tiles (<= ~190 x 190)
+  static SmemOptIn opt;
+  rc = ensure_dynamic_smem(clip_label_kernel, opt, smem);
+  if (rc) return rc;
   int64_t rounds = (batch * frames_per_clip) / ((int64_t)148 * 8 * LABEL_WARPS);
   if (rounds < 1) rounds = 1;
   if (rounds > 8) rounds = 8;
   const int64_t fpc = rounds * LABEL_WARPS;
   p.frames_per_cta = (int)fpc;
-  dim3 grid((unsigned)((frames_per_clip + fpc - 1) / fpc), (unsigned)batch);
-  clip_label_kernel<<<grid, LABEL_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+  const int J = model->num_bodies;
+  const int64_t cells64 = cells;
+  for (int64_t b0 = 0; b0 < batch; b0 += PARC_GRID_Y_MAX) {       // grid.y is limited to 65 535 clips per launch
+    const int64_t nb = batch - b0 < PARC_GRID_Y_MAX ? batch - b0 : PARC_GRID_Y_MAX;
+    const int64_t q0 = b0 * frames_per_clip;
+    p.batch = nb;
+    p.frames = frames + q0 * frame_stride;
+    p.terrain = *terrain;
+    p.terrain.hf += b0 * terrain->hf_batch_stride;
+    p.terrain.min_center += b0 * terrain->min_center_stride;
+    if (p.terrain.base_z) p.terrain.base_z += b0 * terrain->base_z_stride;
+    p.contacts = contacts_out ? contacts_out + q0 * J : nullptr;
+    p.pen_correction = pen_correction_out ? pen_correction_out + q0 : nullptr;
+    p.body_hf = body_hf_out ? body_hf_out + q0 * J : nullptr;
+    p.frame_mask = frame_mask_out ? frame_mask_out + q0 * p.mask_words : nullptr;
+    p.min_body_heights = min_body_heights ? min_body_heights + b0 * cells64 : nullptr;
+    p.body_pos = body_pos ? body_pos + q0 * J * 3 : nullptr;
+    p.body_rot = body_rot ? body_rot + q0 * J * 4 : nullptr;
+    dim3 grid((unsigned)((frames_per_clip + fpc - 1) / fpc), (unsigned)nb);
+    clip_label_kernel<<<grid, LABEL_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+  }
   return check_launch();
 }

@@ -184,6 +184,63 @@ fk_bwd_kernel(const float* __restrict__ root_rot, const float* __restrict__ join
   }
 }
 
+// Body surface points in world space, in the layout the reference's callers build with their per-body loop
+// (util/terrain_util.py:1918-1936, diffusion/mdm.py:1006-1020): for batch entry i, body b, frame f, point k of the
+// body's P_b points:  out[i, F * start_b + f * P_b + k] = rotate(body_rot[i,f,b], local_k) + body_pos[i,f,b].
+// One thread per output point.
+__global__ void __launch_bounds__(256)
+body_points_fwd_kernel(const float* __restrict__ body_pos, const float* __restrict__ body_rot, int64_t batch,
+                       int64_t frames, int J, const __grid_constant__ ParcBodyPoints pts, float* __restrict__ out) {
+  const int S = pts.num_points;
+  const int64_t per = frames * S, total = batch * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bi = i / per;
+    const int64_t r = i - bi * per;                 // position inside the batch entry's [F * S] block
+    // body of this slot: the last b with F * start_b <= r (J <= 24: a short linear search)
+    int b = 0;
+    while (b + 1 < J && (int64_t)__ldg(pts.point_start + b + 1) * frames <= r) ++b;
+    const int s0 = __ldg(pts.point_start + b), pb = __ldg(pts.point_start + b + 1) - s0;
+    const int64_t rr = r - (int64_t)s0 * frames;
+    const int64_t f = rr / pb;
+    const int k = (int)(rr - f * pb);
+    const int64_t q = (bi * frames + f) * J + b;
+    const float4 rot = __ldg(reinterpret_cast<const float4*>(body_rot) + q);
+    const float* lp = pts.points + (size_t)(s0 + k) * 3;
+    const float3 w = quat_rotate(rot, make_float3(__ldg(lp), __ldg(lp + 1), __ldg(lp + 2)));
+    out[i * 3] = w.x + __ldg(body_pos + q * 3);
+    out[i * 3 + 1] = w.y + __ldg(body_pos + q * 3 + 1);
+    out[i * 3 + 2] = w.z + __ldg(body_pos + q * 3 + 2);
+  }
+}
+
+// VJP: one thread per (batch entry, frame, body) sums its points' upstream gradients in point order (deterministic).
+__global__ void __launch_bounds__(256)
+body_points_bwd_kernel(const float* __restrict__ body_rot, const float* __restrict__ g_out, int64_t batch,
+                       int64_t frames, int J, const __grid_constant__ ParcBodyPoints pts,
+                       float* __restrict__ g_body_pos, float* __restrict__ g_body_rot) {
+  const int S = pts.num_points;
+  const int64_t total = batch * frames * J;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(q % J);
+    const int64_t bf = q / J;
+    const int64_t bi = bf / frames, f = bf - bi * frames;
+    const int s0 = __ldg(pts.point_start + b), pb = __ldg(pts.point_start + b + 1) - s0;
+    const float4 rot = __ldg(reinterpret_cast<const float4*>(body_rot) + q);
+    const float* g = g_out + (bi * frames * S + (int64_t)s0 * frames + f * pb) * 3;
+    float3 gp = make_float3(0.f, 0.f, 0.f);
+    float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < pb; ++k) {
+      const float3 gk = make_float3(__ldg(g + k * 3), __ldg(g + k * 3 + 1), __ldg(g + k * 3 + 2));
+      const float* lp = pts.points + (size_t)(s0 + k) * 3;
+      const float4 c = quat_rotate_vjp_q(rot, make_float3(__ldg(lp), __ldg(lp + 1), __ldg(lp + 2)), gk);
+      gp.x += gk.x; gp.y += gk.y; gp.z += gk.z;
+      gr.x += c.x; gr.y += c.y; gr.z += c.z; gr.w += c.w;
+    }
+    if (g_body_pos) { g_body_pos[q * 3] = gp.x; g_body_pos[q * 3 + 1] = gp.y; g_body_pos[q * 3 + 2] = gp.z; }
+    if (g_body_rot) reinterpret_cast<float4*>(g_body_rot)[q] = gr;
+  }
+}
+
 static int warp_grid(int64_t n) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -300,5 +357,39 @@ extern "C" int parc_rot_to_dof(const float* joint_rot, int64_t n, const ParcChar
   if (!aligned16(joint_rot)) return PARC_E_ALIGN;
   rot_to_dof_kernel<<<flat_grid(n * (model->num_bodies - 1)), 256, 0, (cudaStream_t)stream>>>(joint_rot, n, *model,
                                                                                              dof_out);
+  return check_launch();
+}
+
+static int check_body_points(const ParcBodyPoints* pts, int64_t batch, int64_t frames, int32_t num_bodies) {
+  if (!pts) return PARC_E_NULL;
+  if (batch < 0 || frames < 0 || num_bodies < 1 || num_bodies > PARC_MAX_BODIES || pts->num_points < 0) return PARC_E_SIZE;
+  if (pts->num_points > 0 && (!pts->points || !pts->point_start)) return PARC_E_NULL;
+  return PARC_OK;
+}
+
+extern "C" int parc_body_points_fwd(const float* body_pos, const float* body_rot, int64_t batch, int64_t frames,
+                                    int32_t num_bodies, const ParcBodyPoints* pts, float* points_out, void* stream) {
+  int rc = check_body_points(pts, batch, frames, num_bodies);
+  if (rc) return rc;
+  const int64_t total = batch * frames * pts->num_points;
+  if (total == 0) return PARC_OK;
+  if (!body_pos || !body_rot || !points_out) return PARC_E_NULL;
+  if (!aligned16(body_rot)) return PARC_E_ALIGN;
+  body_points_fwd_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(body_pos, body_rot, batch, frames,
+                                                                           num_bodies, *pts, points_out);
+  return check_launch();
+}
+
+extern "C" int parc_body_points_bwd(const float* body_rot, const float* g_points, int64_t batch, int64_t frames,
+                                    int32_t num_bodies, const ParcBodyPoints* pts, float* g_body_pos,
+                                    float* g_body_rot, void* stream) {
+  int rc = check_body_points(pts, batch, frames, num_bodies);
+  if (rc) return rc;
+  const int64_t total = batch * frames * num_bodies;
+  if (total == 0) return PARC_OK;
+  if (!body_rot || !g_points) return PARC_E_NULL;
+  if (!aligned16(body_rot) || !aligned16(g_body_rot)) return PARC_E_ALIGN;
+  body_points_bwd_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(body_rot, g_points, batch, frames,
+                                                                           num_bodies, *pts, g_body_pos, g_body_rot);
   return check_launch();
 }

@@ -123,7 +123,11 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // sweep in flight) for launches that fit one wave and are latency-bound; 16 (64 registers, a quarter of the
 // sweep = 7 gathers in flight) for large launches, which are issue-bound and want more warps per scheduler.
 // (Middle points -- whole sweep at <= 102 registers, half a sweep at <= 85 -- measured slower: profiles/README.md.)
-template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM>
+// DEFER: every store of the first work item waits until the forward kinematics are computed and the observation
+// gathers are in flight -- with an early-input PDL launch the whole read AND compute side then overlaps the previous
+// kernel of the stream, and only the stores are ordered behind it (the deferred values stay in registers, so this is
+// for the <= 128-register one-wave variant).
+template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM, bool DEFER = false>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p) {
   __shared__ TreeSmem sm;
@@ -268,60 +272,71 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
       R.x = add_rn(R.x, xy_off.x);
       R.y = add_rn(R.y, xy_off.y);
     }
-    // early-input PDL launches ran everything above -- immutable tables and caller-guaranteed inputs only -- while the
-    // previous kernel of the stream was still draining; nothing may be written before it has finished
-    if (p.pdl_early && base == first) griddep_wait();
-    if (active) {
-      if (l == 0) {
-        if (p.out.root_pos) {
-          float* o = p.out.root_pos + q * 3;
-          o[0] = R.x; o[1] = R.y; o[2] = R.z;
-        }
-        if (p.out.frame_idx0) p.out.frame_idx0[q] = i0;
-        if (p.out.frame_idx1) p.out.frame_idx1[q] = i1;
-        if (p.out.blend) p.out.blend[q] = blend;
-      } else if (l == 1) {
-        if (p.out.root_rot) reinterpret_cast<float4*>(p.out.root_rot)[q] = R;
-      } else if (own) {
-        if (p.out.joint_rot) reinterpret_cast<float4*>(p.out.joint_rot)[q * (J - 1) + (l - 2)] = R;
-      }
-      // contacts, lerped (anim/motion_lib.py:109)
-      if (has_c) {
-        float4 c = CA;
-        if (BLEND) {
-          c.x = lerp_rn(CA.x, CB.x, blend); c.y = lerp_rn(CA.y, CB.y, blend);
-          c.z = lerp_rn(CA.z, CB.z, blend); c.w = lerp_rn(CA.w, CB.w, blend);
-        }
-        const int ck = l * 4;
-        float* o = p.out.contacts + q * J + ck;
-        o[0] = c.x;
-        if (ck + 1 < J) o[1] = c.y;
-        if (ck + 2 < J) o[2] = c.z;
-        if (ck + 3 < J) o[3] = c.w;
-      }
-      // velocities of key frame 0, un-blended (anim/motion_lib.py:89-95):
-      // vel slot 0 = root_vel.xyz, 1 = root_ang_vel.xyz, 2.. = dof_vel in groups of 4
-      if (has_v) {
+    auto store_frame = [&]() {
+      if (active) {
         if (l == 0) {
-          if (p.out.root_vel) { float* o = p.out.root_vel + q * 3; o[0] = V.x; o[1] = V.y; o[2] = V.z; }
+          if (p.out.root_pos) {
+            float* o = p.out.root_pos + q * 3;
+            o[0] = R.x; o[1] = R.y; o[2] = R.z;
+          }
+          if (p.out.frame_idx0) p.out.frame_idx0[q] = i0;
+          if (p.out.frame_idx1) p.out.frame_idx1[q] = i1;
+          if (p.out.blend) p.out.blend[q] = blend;
         } else if (l == 1) {
-          if (p.out.root_ang_vel) { float* o = p.out.root_ang_vel + q * 3; o[0] = V.x; o[1] = V.y; o[2] = V.z; }
-        } else if (p.out.dof_vel) {
-          const int k = (l - 2) * 4;
-          float* o = p.out.dof_vel + q * D + k;
-          if ((D & 3) == 0) {
-            *reinterpret_cast<float4*>(o) = V;
-          } else {
-            o[0] = V.x;
-            if (k + 1 < D) o[1] = V.y;
-            if (k + 2 < D) o[2] = V.z;
-            if (k + 3 < D) o[3] = V.w;
+          if (p.out.root_rot) reinterpret_cast<float4*>(p.out.root_rot)[q] = R;
+        } else if (own) {
+          if (p.out.joint_rot) reinterpret_cast<float4*>(p.out.joint_rot)[q * (J - 1) + (l - 2)] = R;
+        }
+        // contacts, lerped (anim/motion_lib.py:109)
+        if (has_c) {
+          float4 c = CA;
+          if (BLEND) {
+            c.x = lerp_rn(CA.x, CB.x, blend); c.y = lerp_rn(CA.y, CB.y, blend);
+            c.z = lerp_rn(CA.z, CB.z, blend); c.w = lerp_rn(CA.w, CB.w, blend);
+          }
+          const int ck = l * 4;
+          float* o = p.out.contacts + q * J + ck;
+          o[0] = c.x;
+          if (ck + 1 < J) o[1] = c.y;
+          if (ck + 2 < J) o[2] = c.z;
+          if (ck + 3 < J) o[3] = c.w;
+        }
+        // velocities of key frame 0, un-blended (anim/motion_lib.py:89-95):
+        // vel slot 0 = root_vel.xyz, 1 = root_ang_vel.xyz, 2.. = dof_vel in groups of 4
+        if (has_v) {
+          if (l == 0) {
+            if (p.out.root_vel) { float* o = p.out.root_vel + q * 3; o[0] = V.x; o[1] = V.y; o[2] = V.z; }
+          } else if (l == 1) {
+            if (p.out.root_ang_vel) { float* o = p.out.root_ang_vel + q * 3; o[0] = V.x; o[1] = V.y; o[2] = V.z; }
+          } else if (p.out.dof_vel) {
+            const int k = (l - 2) * 4;
+            float* o = p.out.dof_vel + q * D + k;
+            if ((D & 3) == 0) {
+              *reinterpret_cast<float4*>(o) = V;
+            } else {
+              o[0] = V.x;
+              if (k + 1 < D) o[1] = V.y;
+              if (k + 2 < D) o[2] = V.z;
+              if (k + 3 < D) o[3] = V.w;
+            }
           }
         }
       }
+    };
+    // early-input PDL launches ran everything above -- immutable tables and caller-guaranteed inputs only -- while the
+    // previous kernel of the stream was still draining; nothing may be written before it has finished
+    if (!DEFER) {
+      if (p.pdl_early && base == first) griddep_wait();
+      store_frame();
     }
 
-    if (!p.want_fk && !p.want_obs) continue;
+    if (!p.want_fk && !p.want_obs) {
+      if (DEFER) {
+        if (p.pdl_early && base == first) griddep_wait();
+        store_frame();
+      }
+      continue;
+    }
 
     // root position lives in group lane 0, root rotation in group lane 1 (= body 0's lane)
     const float3 rp = make_float3(shfl_g(R.x, 0, G), shfl_g(R.y, 0, G), shfl_g(R.z, 0, G));
@@ -370,9 +385,9 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     }
 
     // ---- forward kinematics down the tree (shuffles stay inside the group) ----
+    float3 pos = rp;
+    float4 rot = R;
     if (p.want_fk) {
-      float3 pos = rp;
-      float4 rot = R;
       float4 local = rot;
       if (lb.body > 0) local = quat_mul_plain(lb.lr, rot);
 #pragma unroll 1
@@ -387,13 +402,17 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
           rot = quat_mul_plain(pr, local);
         }
       }
-      if (active && lb.body >= 0) {
-        if (p.fk.body_pos) {
-          float* o = p.fk.body_pos + (q * J + lb.body) * 3;
-          o[0] = pos.x; o[1] = pos.y; o[2] = pos.z;
-        }
-        if (p.fk.body_rot) reinterpret_cast<float4*>(p.fk.body_rot)[q * J + lb.body] = rot;
+    }
+    if (DEFER) {
+      if (p.pdl_early && base == first) griddep_wait();
+      store_frame();
+    }
+    if (p.want_fk && active && lb.body >= 0) {
+      if (p.fk.body_pos) {
+        float* o = p.fk.body_pos + (q * J + lb.body) * 3;
+        o[0] = pos.x; o[1] = pos.y; o[2] = pos.z;
       }
+      if (p.fk.body_rot) reinterpret_cast<float4*>(p.fk.body_rot)[q * J + lb.body] = rot;
     }
 
     // ---- heightmap observation, part 2: consume the gathers; then any further points ----
@@ -661,7 +680,7 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
   if (n_entries < 0 || a->num_steps < 0 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
   if (num_steps > 1 && (!a->time_offsets || !blend)) return PARC_E_NULL;
   if (!blend && a->root_xy_offset) return PARC_E_SIZE;
-  if (a->variant < 0 || a->variant > 4) return PARC_E_SIZE;
+  if (a->variant < 0 || a->variant > 5) return PARC_E_SIZE;
   const int64_t n = n_entries * num_steps;
   if (n > 0 && (!a->motion_ids || (blend && !a->motion_times))) return PARC_E_NULL;
   QueryParams p;
@@ -716,18 +735,23 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
   // beyond it occupancy wins: 7 gathers in flight at 64 registers / 16 CTAs per SM beat 14 in flight at 80
   // registers / 12 CTAs (65 536 envs: 87.3 -> 85.2 us; the 7-step tracker form: 396 -> 337 us), while 4 in
   // flight (88.5 us) and 48 registers / 20 CTAs (97.7 us, spills) lose again.
-  // variant: 0 = by regime; 1 = G16 / 28 in flight / 8 CTAs per SM; 2 = G16 / 7 / 16; 3 = G16 / 14 / 12; 4 = G32 / 14 / 8
+  // variant: 0 = by regime; 1 = G16 / 28 in flight / 8 CTAs per SM; 2 = G16 / 7 / 16; 3 = G16 / 14 / 12; 4 = G32 / 14 / 8;
+  // 5 = 1 with deferred stores -- the one-wave choice: same speed as 1 launched alone (7.9 vs 8.0 us at 4096 envs),
+  // 5.4 vs 5.9 us per step in a chain of early-input PDL launches (profiles/r2_variants.json)
   int variant = a->variant;
   if (!fits16) variant = 4;
   if (variant == 0) {
     const int64_t warps16 = (n + 1) / 2;
-    variant = blend ? (warps16 <= (int64_t)sms * 16 ? 1 : 2) : 3;
+    variant = blend ? (warps16 <= (int64_t)sms * 16 ? 5 : 2) : 3;
+    // a launch so small that one character per warp still fits a single resident wave: the observation sweep is
+    // then spread over twice the lanes (2048 envs: 4.9 us against 5.4 us per step)
+    if (blend && p.want_obs && n <= (int64_t)sms * 16) variant = 4;
   }
   if (!blend && variant != 4) variant = 3;
   const bool half = variant != 4;
   const int64_t warps = half ? (n + 1) / 2 : n;
   const int grid = query_grid(warps, sms);
-  const int inflight = variant == 1 ? 28 : (variant == 2 ? 7 : 14);
+  const int inflight = (variant == 1 || variant == 5) ? 28 : (variant == 2 ? 7 : 14);
   size_t smem = 0;
   if (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) {
     const int sweep = (half ? 16 : 32) * inflight;
@@ -740,24 +764,27 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
   // branches), so the plain one-query-per-entry call runs an instantiation without them -- whose code must stay
   // exactly the tuned one: making `step` a compile-time 0 there changed the schedule and cost 13 %.
   const bool step_form = blend && (p.num_steps > 1 || p.xy_offset);
-#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB)                                                                         \
+#define PARC_LAUNCH_QUERY_D(B, GG, NF, RL, MB, DF)                                                                   \
   do {                                                                                                               \
     if (B && step_form)                                                                                              \
-      launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, B>, grid, QUERY_CTA_THREADS, smem, st, pdl, p);        \
+      launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, B, DF>, grid, QUERY_CTA_THREADS, smem, st, pdl, p);    \
     else                                                                                                             \
-      launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, false>, grid, QUERY_CTA_THREADS, smem, st, pdl, p);    \
+      launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, false, DF>, grid, QUERY_CTA_THREADS, smem, st, pdl, p); \
   } while (0)
+#define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB) PARC_LAUNCH_QUERY_D(B, GG, NF, RL, MB, false)
   if (blend) {
     switch (variant) {
       case 1: if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); break;
       case 2: if (rel) PARC_LAUNCH_QUERY(true, 16, 7, true, 16); else PARC_LAUNCH_QUERY(true, 16, 7, false, 16); break;
       case 3: if (rel) PARC_LAUNCH_QUERY(true, 16, 14, true, 12); else PARC_LAUNCH_QUERY(true, 16, 14, false, 12); break;
+      case 5: if (rel) PARC_LAUNCH_QUERY_D(true, 16, 28, true, 8, true); else PARC_LAUNCH_QUERY_D(true, 16, 28, false, 8, true); break;
       default: if (rel) PARC_LAUNCH_QUERY(true, 32, 14, true, 8); else PARC_LAUNCH_QUERY(true, 32, 14, false, 8); break;
     }
   } else {
     if (half) PARC_LAUNCH_QUERY(false, 16, 14, false, 12); else PARC_LAUNCH_QUERY(false, 32, 14, false, 8);
   }
 #undef PARC_LAUNCH_QUERY
+#undef PARC_LAUNCH_QUERY_D
   return check_launch();
 }
 

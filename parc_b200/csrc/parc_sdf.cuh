@@ -153,14 +153,31 @@ __device__ __forceinline__ float3 cell_grad(const float* hf, const float* cx, co
   return sd_box_grad(make_float3(p.x - cx[ix], p.y - cy[iy], p.z - cz), make_float3(hx, hy, hz));
 }
 
-// Stage one sample's terrain: hf tile, absolute cell-centre coordinates (node offset + min centre, added
-// in fp32 as util/terrain_util.py:1859-1860 does), and the tile's min / max height for the pruning bounds
-// (s_minmax[0] = min, [1] = max; must be followed by __syncthreads()).
+// float atomic min / max through the int-ordering trick.  The branch is on the SIGN BIT, not on v >= 0: -0.0f has
+// the bit pattern 0x80000000 = INT_MIN, which the signed compare would treat as the smallest value of all.
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (__float_as_int(v) >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (__float_as_int(v) >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// Absolute cell-centre coordinates of one sample's terrain (node offset + min centre, added in fp32 as
+// util/terrain_util.py:1859-1860 does) -> shared memory.
+__device__ __forceinline__ void stage_terrain_nodes(const ParcTerrainBatch& t, int64_t b, float* s_cx, float* s_cy) {
+  const float* mc = t.min_center + b * t.min_center_stride;
+  for (int i = threadIdx.x; i < t.dim_x; i += blockDim.x) s_cx[i] = __ldg(t.x_nodes + i) + __ldg(mc);
+  for (int i = threadIdx.x; i < t.dim_y; i += blockDim.x) s_cy[i] = __ldg(t.y_nodes + i) + __ldg(mc + 1);
+}
+
+// Stage one sample's terrain: hf tile, cell-centre coordinates, and the tile's min / max height for the pruning
+// bounds (s_minmax[0] = min, [1] = max; must be followed by __syncthreads()).
 __device__ __forceinline__ void stage_terrain(const ParcTerrainBatch& t, int64_t b, float* s_hf, float* s_cx,
                                               float* s_cy, float* s_minmax) {
   const int X = t.dim_x, Y = t.dim_y;
   const float* hf = t.hf + b * t.hf_batch_stride;
-  const float* mc = t.min_center + b * t.min_center_stride;
   if (threadIdx.x == 0) { s_minmax[0] = INFINITY; s_minmax[1] = -INFINITY; }
   __syncthreads();
   float lo = INFINITY, hi = -INFINITY;
@@ -175,14 +192,19 @@ __device__ __forceinline__ void stage_terrain(const ParcTerrainBatch& t, int64_t
     hi = fmaxf(hi, __shfl_xor_sync(PARC_FULL_MASK, hi, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    // float min / max through the int-ordered trick (values may be negative)
-    if (lo >= 0.0f) atomicMin(reinterpret_cast<int*>(&s_minmax[0]), __float_as_int(lo));
-    else atomicMax(reinterpret_cast<unsigned int*>(&s_minmax[0]), __float_as_uint(lo));
-    if (hi >= 0.0f) atomicMax(reinterpret_cast<int*>(&s_minmax[1]), __float_as_int(hi));
-    else atomicMin(reinterpret_cast<unsigned int*>(&s_minmax[1]), __float_as_uint(hi));
+    atomic_min_float(&s_minmax[0], lo);
+    atomic_max_float(&s_minmax[1], hi);
   }
-  for (int i = threadIdx.x; i < X; i += blockDim.x) s_cx[i] = __ldg(t.x_nodes + i) + __ldg(mc);
-  for (int i = threadIdx.x; i < Y; i += blockDim.x) s_cy[i] = __ldg(t.y_nodes + i) + __ldg(mc + 1);
+  stage_terrain_nodes(t, b, s_cx, s_cy);
+}
+
+// A terrain too large for shared memory stays in global memory (read through L1 / L2): only the cell-centre
+// coordinates are staged, and the pruning runs without the tile's height range (min = -inf, max = +inf: the vertical
+// bound degenerates to 0, which only makes the scan visit more cells -- never fewer than the exact result needs).
+__device__ __forceinline__ void stage_terrain_global(const ParcTerrainBatch& t, int64_t b, float* s_cx, float* s_cy,
+                                                     float* s_minmax) {
+  if (threadIdx.x == 0) { s_minmax[0] = -INFINITY; s_minmax[1] = INFINITY; }
+  stage_terrain_nodes(t, b, s_cx, s_cy);
 }
 
 __device__ __forceinline__ float sample_base_z(const ParcTerrainBatch& t, int64_t b) {

@@ -169,6 +169,8 @@ class HeightfieldDesc:
     dy: float
 
     def c_struct(self) -> ParcHeightfield:
+        assert self.hf.is_cuda and self.hf.dtype == torch.float32 and self.hf.dim() == 2 and self.hf.is_contiguous(), \
+            "heightfield must be a contiguous fp32 CUDA tensor [X, Y]"
         h = ParcHeightfield()
         h.hf = self.hf.data_ptr()
         h.dim_x, h.dim_y = int(self.hf.shape[0]), int(self.hf.shape[1])
@@ -644,6 +646,10 @@ class TerrainBatchDesc:
         hb = int(self.hf.shape[0])
         X, Y = int(self.hf.shape[1]), int(self.hf.shape[2])
         assert hb in (1, batch) and self.min_center.shape[0] in (1, batch)
+        for name in ("hf", "min_center", "x_nodes", "y_nodes", "base_z"):
+            v = getattr(self, name)
+            assert v is None or (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous() and
+                                 v.device == self.hf.device), f"terrain batch field {name}: contiguous fp32 CUDA expected"
         t.hf = self.hf.data_ptr()
         t.hf_batch_stride = X * Y if hb > 1 else 0
         t.min_center = self.min_center.data_ptr()
@@ -690,11 +696,7 @@ def make_terrain_batch(hf: torch.Tensor, min_center: torch.Tensor, dxdy_host: Tu
     return desc
 
 
-def points_hf_sdf(points: torch.Tensor, terrain: TerrainBatchDesc, inverted: bool, want_arg: bool = False):
-    """points [B,N,3] -> sdf [B,N] (exact min over all cells)."""
-    require_cuda(points)
-    p = f32c(points)
-    assert p.dim() == 3
+def _points_hf_sdf_launch(p: torch.Tensor, terrain: "TerrainBatchDesc", inverted: bool, want_arg: bool):
     B, N = p.shape[0], p.shape[1]
     out = torch.empty((B, N), dtype=torch.float32, device=p.device)
     arg = torch.empty((B, N), dtype=torch.int32, device=p.device) if want_arg else None
@@ -703,7 +705,45 @@ def points_hf_sdf(points: torch.Tensor, terrain: TerrainBatchDesc, inverted: boo
         rc = _lib.load().parc_points_hf_sdf(p.data_ptr(), B, N, C.byref(t), 1 if inverted else 0, out.data_ptr(),
                                             ptr(arg), stream_ptr(p.device))
     check(rc, "parc_points_hf_sdf")
-    return (out, arg) if want_arg else out
+    return out, arg
+
+
+class _PointsHfSdf(torch.autograd.Function):
+    """sdf [B,N] of points [B,N,3]; backward routes the upstream gradient through the arg-min cell's box SDF
+    (parc_points_hf_sdf_bwd).  No gradient for the heightfield (the reference's callers never ask for one)."""
+
+    @staticmethod
+    def forward(ctx, points, terrain, inverted):
+        p = f32c(points)
+        need = ctx.needs_input_grad[0]
+        out, arg = _points_hf_sdf_launch(p, terrain, inverted, need)
+        if need:
+            ctx.terrain, ctx.inverted = terrain, inverted
+            ctx.save_for_backward(p, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, arg = ctx.saved_tensors
+        B, N = p.shape[0], p.shape[1]
+        gs = f32c(g)
+        gp = torch.empty_like(p)
+        t = ctx.terrain.c_struct(B)
+        with torch.cuda.device(p.device):
+            rc = _lib.load().parc_points_hf_sdf_bwd(p.data_ptr(), B, N, C.byref(t), 1 if ctx.inverted else 0,
+                                                    arg.data_ptr(), gs.data_ptr(), gp.data_ptr(), stream_ptr(p.device))
+        check(rc, "parc_points_hf_sdf_bwd")
+        return gp, None, None
+
+
+def points_hf_sdf(points: torch.Tensor, terrain: TerrainBatchDesc, inverted: bool, want_arg: bool = False):
+    """points [B,N,3] -> sdf [B,N] (exact min over all cells).  Differentiable with respect to the points; with
+    want_arg=True returns (sdf, flat arg-min cell index int32 [B,N]) detached."""
+    require_cuda(points)
+    assert points.dim() == 3 and points.shape[-1] == 3
+    if want_arg:
+        return _points_hf_sdf_launch(f32c(points.detach()), terrain, inverted, True)
+    return _PointsHfSdf.apply(points, terrain, inverted)
 
 
 @dataclass
@@ -712,6 +752,9 @@ class BodyPointsDesc:
     point_start: torch.Tensor   # int32 [J+1] device
 
     def c_struct(self) -> ParcBodyPoints:
+        assert self.points.is_cuda and self.points.dtype == torch.float32 and self.points.is_contiguous()
+        assert self.point_start.dtype == torch.int32 and self.point_start.is_contiguous()
+        assert self.point_start.device == self.points.device
         b = ParcBodyPoints()
         b.points = self.points.data_ptr()
         b.point_start = self.point_start.data_ptr()
@@ -727,6 +770,45 @@ def make_body_points(body_points, device) -> BodyPointsDesc:
     pts = torch.cat([f32c(p.detach()).reshape(-1, 3) for p in body_points], dim=0).to(device)
     return BodyPointsDesc(points=pts.contiguous(),
                           point_start=torch.tensor(starts, dtype=torch.int32, device=device))
+
+
+class _BodyPointsWorld(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, body_pos, body_rot, pts):
+        require_cuda(body_pos, body_rot)
+        bp, br = f32c(body_pos), f32c(body_rot)
+        assert bp.dim() == 4 and br.dim() == 4 and bp.shape[:3] == br.shape[:3] and bp.shape[3] == 3 and br.shape[3] == 4
+        B, F, J = bp.shape[0], bp.shape[1], bp.shape[2]
+        S = int(pts.points.shape[0])
+        out = torch.empty((B, F * S, 3), dtype=torch.float32, device=bp.device)
+        c = pts.c_struct()
+        with torch.cuda.device(bp.device):
+            rc = _lib.load().parc_body_points_fwd(bp.data_ptr(), br.data_ptr(), B, F, J, C.byref(c), out.data_ptr(),
+                                                  stream_ptr(bp.device))
+        check(rc, "parc_body_points_fwd")
+        ctx.pts, ctx.dims = pts, (B, F, J)
+        ctx.save_for_backward(br)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (br,) = ctx.saved_tensors
+        B, F, J = ctx.dims
+        gg = f32c(g)
+        gp = torch.empty((B, F, J, 3), dtype=torch.float32, device=br.device)
+        gr = torch.empty((B, F, J, 4), dtype=torch.float32, device=br.device)
+        c = ctx.pts.c_struct()
+        with torch.cuda.device(br.device):
+            rc = _lib.load().parc_body_points_bwd(br.data_ptr(), gg.data_ptr(), B, F, J, C.byref(c), gp.data_ptr(),
+                                                  gr.data_ptr(), stream_ptr(br.device))
+        check(rc, "parc_body_points_bwd")
+        return gp, gr, None
+
+
+def body_points_world(body_pos: torch.Tensor, body_rot: torch.Tensor, pts: BodyPointsDesc) -> torch.Tensor:
+    """body_pos [B,F,J,3], body_rot [B,F,J,4] -> world surface points [B, F*S, 3] in the reference's body-major
+    layout (body b's block = [F, P_b] points starting at F * point_start[b]); differentiable."""
+    return _BodyPointsWorld.apply(body_pos, body_rot, pts)
 
 
 def _body_loss_launch(model, pts, terrain, root_pos, root_rot, joint_rot, contacts, w_pen, w_contact, want_grad):

@@ -30,11 +30,13 @@ class MDMPathSettings:
 def body_points_desc(char_model, body_points):
     """Cache the concatenated device copy of the per-body point lists on the model."""
     cache = char_model.__dict__.setdefault("_body_points_cache", {})
-    key = tuple((p.data_ptr(), tuple(p.shape)) for p in body_points)
+    key = tuple((id(p), p.data_ptr(), tuple(p.shape), p._version) for p in body_points)
     if key not in cache:
         cache.clear()
-        cache[key] = ops.make_body_points(body_points, body_points[0].device)
-    return cache[key]
+        # the keyed tensors are kept alive next to the descriptor, so a recycled allocator address / object id can
+        # never alias a stale entry
+        cache[key] = (ops.make_body_points(body_points, body_points[0].device), list(body_points))
+    return cache[key][0]
 
 
 def compute_motion_loss(motion_frames: MotionFrames, path_nodes, terrain, char_model, body_points: list,

@@ -127,9 +127,10 @@ class SubTerrain:
     def hf_desc(self) -> "ops.HeightfieldDesc":
         """Host copies of min_point / dxdy next to the device hf, so launches never sync.  The cache is
         keyed on the tensors' identity and in-place version counters, so edits (pad(), flips, a new
-        min_point) are picked up automatically."""
-        key = (self.hf.data_ptr(), tuple(self.hf.shape), id(self.min_point), self.min_point._version,
-               id(self.dxdy), self.dxdy._version)
+        min_point, in-place height edits -- which matter when a non-contiguous hf is served from a contiguous
+        copy) are picked up automatically."""
+        key = (self.hf.data_ptr(), tuple(self.hf.shape), self.hf._version, self.hf.is_contiguous(),
+               id(self.min_point), self.min_point._version, id(self.dxdy), self.dxdy._version)
         cached = self.__dict__.get("_desc")
         if cached is None or cached[0] != key:
             mp = self.min_point.detach().cpu().tolist()
@@ -178,6 +179,8 @@ def points_hf_sdf(points: torch.Tensor, hf: torch.Tensor, hf_min_box_center: tor
                   base_z=-10.0, inverted=True, radius: Optional[float] = None):
     """Exact signed distance from each point to the union-of-boxes heightfield: min over ALL cells of
     the box SDF.  points [B,N,3], hf [B,X,Y], hf_min_box_center [B,2], hf_dxdy [2] -> [B,N].
+    Differentiable with respect to `points` (the MDM's collision loss / guidance back-propagate through it,
+    diffusion/mdm.py:729-737, :1484-1496); any batch size, any terrain size.
     Ref util/terrain_util.py:1835-1893."""
     assert points.dim() == 3 and hf.dim() == 3 and hf_min_box_center.dim() == 2 and hf_dxdy.dim() == 1
     terrain = ops.make_terrain_batch(hf, hf_min_box_center, hf_dxdy.detach().cpu().tolist(), base_z=base_z)
@@ -187,6 +190,33 @@ def points_hf_sdf(points: torch.Tensor, hf: torch.Tensor, hf_min_box_center: tor
         assert isinstance(radius, float) and radius > 0.0
         sdf = sdf + radius if inverted else sdf - radius
     return sdf
+
+
+def motion_frames_hf_sdf_loss(motion_frames, char_point_samples, hf, hf_min_box_center, hf_dxdy, char_model,
+                              ret_vis_info=False, interior_distance=True):
+    """Heightfield-collision loss of a batch of motions: 0.5 * sum over all body points and frames of
+    clamp(sdf, max=0)^2 (interior distance; clamp(min=0) otherwise).  motion_frames [B,S,6+D] in the heightfield's
+    frame, char_point_samples: list of [P_b,3] per body, hf [B,X,Y], hf_min_box_center [B,2], hf_dxdy [2] -> loss [B]
+    (+ world points [B,N,3], sdf [B,N] with ret_vis_info).  Differentiable with respect to motion_frames: every stage
+    -- exp-map / DoF conversion, FK, point transform, SDF -- is a CUDA operator with a hand-written VJP.
+    Ref util/terrain_util.py:1895-1949."""
+    from .. import ops as _ops
+    from ..tools.procgen.mdm_path import body_points_desc
+    from . import torch_util
+    D = char_model.get_dof_size()
+    root_pos = motion_frames[..., 0:3]
+    root_rot_quat = _ops.exp_map_to_quat(motion_frames[..., 3:6])
+    joint_rot = torch_util.quat_pos(char_model.dof_to_rot(motion_frames[..., 6:6 + D]))
+    body_pos, body_rot = char_model.forward_kinematics(root_pos, root_rot_quat, joint_rot)
+    pts = _ops.body_points_world(body_pos, body_rot, body_points_desc(char_model, char_point_samples))
+    sdf = points_hf_sdf(pts, hf, hf_min_box_center, hf_dxdy, base_z=-10.0, inverted=interior_distance)
+    if interior_distance:
+        loss = 0.5 * torch.sum(torch.square(torch.clamp(sdf, max=0.0)), dim=-1)
+    else:
+        loss = 0.5 * torch.sum(torch.square(torch.clamp(sdf, min=0.0)), dim=-1)
+    if ret_vis_info:
+        return loss, pts, sdf
+    return loss
 
 
 # ---- heightfield masks of a motion (SURVEY.md section 8(f) row 1) ---------------------------------------

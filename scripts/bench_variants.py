@@ -32,7 +32,7 @@ def main():
     for envs in [int(x) for x in a.envs.split(",")]:
         ids_h, times_h = bench.query_batches(NB, envs, a.clips, 264.0 / 30.0, seed=7)
         ids_d, times_d = ids_h.to(ctx.dev), times_h.to(ctx.dev)
-        for variant in (0, 1, 2, 3, 4):
+        for variant in (0, 1, 2, 3, 4, 5):
             for mode in ("serial", "pdl", "pdl_early", "pdl_early_fast_heading"):
                 kw = dict(variant=variant, pdl=mode != "serial", pdl_early_inputs=mode.startswith("pdl_early"),
                           fast_heading=mode.endswith("fast_heading"))

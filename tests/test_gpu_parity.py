@@ -437,16 +437,17 @@ def test_query_variants_pdl_and_output_selection_are_bit_identical(golden_lib):
     base = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl).launch()
     torch.cuda.synchronize()
     base = {k: v.clone() for k, v in base.items()}
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 3, 4, 5):
         got = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, variant=variant).launch()
         for k, v in base.items():
             assert torch.equal(got[k], v), f"variant {variant}: {k}"
-    for early in (False, True):
-        pl = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, pdl=True, pdl_early_inputs=early)
+    for early, variant in ((False, 0), (True, 0), (True, 5), (True, 2)):
+        pl = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, pdl=True, pdl_early_inputs=early,
+                                        variant=variant)
         for _ in range(3):                         # back to back: each launch overlaps the previous one's tail
             got = pl.launch()
         for k, v in base.items():
-            assert torch.equal(got[k], v), f"pdl early={early}: {k}"
+            assert torch.equal(got[k], v), f"pdl early={early} variant={variant}: {k}"
     from parc_b200 import ops
     plans = [golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, pdl=True, pdl_early_inputs=True,
                                         out={}) for _ in range(4)]
@@ -478,6 +479,121 @@ def test_points_hf_sdf_vs_golden():
         sd = points_hf_sdf(dev(g["clip_points"]), t.hf.unsqueeze(0), t.min_point.unsqueeze(0), t.dxdy, base_z=-10.0,
                            inverted=inv)
         assert_close(sd, g[key], what=key)
+
+
+def _a16_points(g):
+    pts, s0 = [], 0
+    for n in g["minimal_point_count"].tolist():
+        pts.append(dev(g["minimal_points"][s0:s0 + n]))
+        s0 += n
+    return pts
+
+
+def test_points_hf_sdf_gradient_vs_golden():
+    """Row a16: the MDM back-propagates 0.5 * sum(clamp(sdf, max=0)^2) through points_hf_sdf (diffusion/mdm.py:729-737,
+    :1484-1496); golden = the reference's own autograd gradients on its 31 x 31 @ 0.2 m local grid."""
+    from parc_b200.util.terrain_util import points_hf_sdf
+    g = golden("a16_golden.npz")
+    hf, mc, dxdy = dev(g["hf"]), dev(g["min_center"]), dev(g["dxdy"])
+    for tag in ("guidance", "train"):
+        p = dev(g["world_points"]).clone().requires_grad_(True)
+        sdf = points_hf_sdf(p, hf, mc, dxdy, base_z=float(g[f"base_z_{tag}"]))
+        loss = 0.5 * torch.sum(torch.square(torch.clamp(sdf, max=0.0)))
+        loss.backward()
+        assert_close(sdf, g[f"psdf_{tag}"], rtol=1e-5, atol=2e-6, what=f"sdf {tag}")
+        assert_close_normwise(p.grad, g[f"pgrad_{tag}"], 1e-5, what=f"d loss / d points {tag}")
+        assert (torch.tensor(g[f"pgrad_{tag}"]).abs().sum(-1) > 0).sum() > 20       # the fixture really penetrates
+    p = dev(g["world_points"]).clone().requires_grad_(True)
+    sdf = points_hf_sdf(p, hf, mc, dxdy, base_z=-10.0, inverted=False)
+    (sdf * dev(g["upstream_solid"])).sum().backward()
+    assert_close(sdf, g["psdf_solid"], rtol=1e-5, atol=2e-6, what="solid sdf")
+    assert_close_normwise(p.grad, g["pgrad_solid"], 1e-5, what="solid d/d points")
+    # no graph when nothing requires grad; want_arg still served
+    from parc_b200 import ops
+    tb = ops.make_terrain_batch(hf, mc, (0.2, 0.2), base_z=-10.0)
+    v, a = ops.points_hf_sdf(dev(g["world_points"]), tb, True, want_arg=True)
+    assert not v.requires_grad and a.dtype == torch.int32 and int(a.max()) < 31 * 31
+
+
+def test_motion_frames_hf_sdf_loss_vs_golden(gpu_model):
+    """util/terrain_util.py:1895-1949 with get_minimal_char_point_samples: value, per-point sdf, world points and
+    the gradient with respect to the motion frames, against the reference's own outputs."""
+    from parc_b200.util.terrain_util import motion_frames_hf_sdf_loss
+    g = golden("a16_golden.npz")
+    hf, mc, dxdy = dev(g["hf"]), dev(g["min_center"]), dev(g["dxdy"])
+    pts = _a16_points(g)
+    for interior, tag in ((True, "int"), (False, "ext")):
+        mf = dev(g["frames"]).clone().requires_grad_(True)
+        loss, wp, sdf = motion_frames_hf_sdf_loss(mf, pts, hf, mc, dxdy, gpu_model, ret_vis_info=True,
+                                                  interior_distance=interior)
+        loss.sum().backward()
+        assert_close(loss, g[f"loss_{tag}"], rtol=1e-5, atol=1e-7, what=f"loss {tag}")
+        assert_close(sdf, g[f"sdf_{tag}"], rtol=1e-5, atol=2e-6, what=f"sdf {tag}")
+        if interior:
+            assert_close(wp, g["world_points"], rtol=1e-5, atol=1e-6, what="world points")
+        assert_close_normwise(mf.grad, g[f"grad_frames_{tag}"], 1e-5, what=f"d loss / d motion_frames {tag}")
+    only = motion_frames_hf_sdf_loss(dev(g["frames"]), pts, hf, mc, dxdy, gpu_model)
+    assert_close(only, g["loss_int"], rtol=1e-5, atol=1e-7, what="loss (no vis info)")
+
+
+def test_body_points_world_layout_and_gradient_vs_oracle(gpu_model, O, oracle_model):
+    from parc_b200 import ops
+    from parc_b200.tools.procgen.mdm_path import body_points_desc
+    from parc_b200.util import geom_util
+    gen = torch.Generator().manual_seed(4)
+    B, F = 3, 5
+    bp = torch.randn(B, F, 15, 3, generator=gen)
+    br = torch.nn.functional.normalize(torch.randn(B, F, 15, 4, generator=gen), dim=-1)
+    up = torch.randn(B, F * 304, 3, generator=gen)
+    a, b = bp.clone().requires_grad_(True), br.clone().requires_grad_(True)
+    want = O.world_body_points(a, b, oracle_model.body_points)
+    (want * up).sum().backward()
+    pts = body_points_desc(gpu_model, geom_util.get_char_point_samples(gpu_model))
+    c, d = bp.cuda().requires_grad_(True), br.cuda().requires_grad_(True)
+    got = ops.body_points_world(c, d, pts)
+    (got * up.cuda()).sum().backward()
+    assert_close(got, want, rtol=1e-5, atol=1e-6, what="world body points")
+    assert_close_normwise(c.grad, a.grad, 1e-5, what="d/d body_pos")
+    assert_close_normwise(d.grad, b.grad, 1e-5, what="d/d body_rot")
+
+
+def test_sdf_on_terrains_beyond_shared_memory_and_huge_batches(O):
+    """No size limits: a 300 x 260 tile (312 KB > one SM's shared memory) is scanned from global memory
+    with the same exact result as the oracle's brute-force min over all cells -- values, arg-min and gradient; a batch
+    beyond the grid's 65 535-sample y limit is chunked."""
+    from parc_b200 import ops
+    gen = torch.Generator().manual_seed(8)
+    X, Y = 300, 260
+    hf = torch.zeros(1, X, Y)
+    for _ in range(400):
+        x0, y0 = int(torch.randint(0, X - 12, (1,), generator=gen)), int(torch.randint(0, Y - 12, (1,), generator=gen))
+        hf[0, x0:x0 + int(torch.randint(2, 12, (1,), generator=gen)), y0:y0 + int(torch.randint(2, 12, (1,), generator=gen))] = \
+            float(torch.rand(1, generator=gen) * 2.0 - 0.7)
+    mc = torch.tensor([[-3.0, 1.5]])
+    dxdy = torch.tensor([0.4, 0.4])
+    n = 600
+    p = torch.rand(1, n, 3, generator=gen) * torch.tensor([X * 0.4 + 4.0, Y * 0.4 + 4.0, 2.4]) + torch.tensor([-5.0, -0.5, -0.9])
+    tb = ops.make_terrain_batch(hf.cuda(), mc.cuda(), (0.4, 0.4), base_z=-10.0)
+    for inverted in (True, False):
+        want = O.points_hf_sdf(p, hf, mc, dxdy, base_z=-10.0, inverted=inverted, chunk=64)
+        got, arg = ops.points_hf_sdf(p.cuda(), tb, inverted, want_arg=True)
+        assert_close(got, want, rtol=1e-5, atol=2e-6, what=f"large-terrain sdf inverted={inverted}")
+        pg = p.clone().requires_grad_(True)
+        O.points_hf_sdf(pg, hf, mc, dxdy, base_z=-10.0, inverted=inverted, chunk=64).sum().backward()
+        pc = p.cuda().requires_grad_(True)
+        ops.points_hf_sdf(pc, tb, inverted).sum().backward()
+        assert_close_normwise(pc.grad, pg.grad, 1e-5, what=f"large-terrain gradient inverted={inverted}")
+    # batch > 65 535: chunked launches
+    Bn = 70001
+    small = torch.rand(Bn, 4, 4, generator=gen).cuda()
+    pts = (torch.rand(Bn, 3, 3, generator=gen) * 1.6 - 0.2).cuda()
+    tbs = ops.make_terrain_batch(small, torch.zeros(Bn, 2).cuda(), (0.4, 0.4), base_z=-10.0)
+    full = ops.points_hf_sdf(pts, tbs, True)
+    for lo in (0, 65535, 70000):
+        one = ops.points_hf_sdf(pts[lo:lo + 1].contiguous(),
+                                ops.make_terrain_batch(small[lo:lo + 1].contiguous(), torch.zeros(1, 2).cuda(), (0.4, 0.4),
+                                                       base_z=-10.0), True)
+        assert torch.equal(full[lo:lo + 1], one)
 
 
 def test_compute_motion_loss_vs_golden(gpu_model):

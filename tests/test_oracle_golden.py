@@ -169,3 +169,41 @@ def test_tracker_step_obs_reward_done():
         d = O.compute_done(*common, cids, th, pose, ptd, early, track, 0.6, 1.309)
         assert d.dtype == torch.int32 and torch.equal(d, T(g["done_" + tag])), tag
     assert set(np.unique(g["done_feet"])) == {0, 1, 3}                    # every flag value is exercised
+
+
+def _a16_points(g):
+    cnt = g["minimal_point_count"].tolist()
+    pts, s0 = [], 0
+    for n in cnt:
+        pts.append(T(g["minimal_points"][s0:s0 + n]))
+        s0 += n
+    return pts
+
+
+def test_a16_pin_report_is_all_ok():
+    import os
+    from conftest import GOLDEN
+    lines = open(os.path.join(GOLDEN, "PIN_REPORT_a16.txt")).read().splitlines()
+    assert len(lines) == 12 and all(l.startswith("OK") for l in lines)
+
+
+def test_mdm_hf_collision_loss_and_gradients(oracle_model):
+    """util/terrain_util.py:1895-1949 and the MDM's 0.5 * sum(clamp(sdf, max=0)^2) through
+    points_hf_sdf (diffusion/mdm.py:729-737, :1484-1496), values and autograd gradients of the reference."""
+    g = golden("a16_golden.npz")
+    hf, mc, dxdy = T(g["hf"]), T(g["min_center"]), T(g["dxdy"])
+    pts = _a16_points(g)
+    assert sum(p.shape[0] for p in pts) == 42
+    for interior, tag in ((True, "int"), (False, "ext")):
+        mf = T(g["frames"]).clone().requires_grad_(True)
+        loss, wp, sdf = O.motion_frames_hf_sdf_loss(oracle_model, mf, pts, hf, mc, dxdy, interior_distance=interior)
+        loss.sum().backward()
+        assert_close(loss, g[f"loss_{tag}"], rtol=1e-5, atol=1e-7, what=f"loss {tag}")
+        assert_close(sdf, g[f"sdf_{tag}"], rtol=1e-5, atol=2e-6, what=f"sdf {tag}")
+        gr = T(g[f"grad_frames_{tag}"])
+        assert (mf.grad - gr).abs().max() <= 2e-5 * gr.abs().max()
+    for tag in ("guidance", "train"):
+        p = T(g["world_points"]).clone().requires_grad_(True)
+        sdf = O.points_hf_sdf(p, hf, mc, dxdy, base_z=float(g[f"base_z_{tag}"]), inverted=True)
+        O.hf_collision_loss(sdf).sum().backward()
+        assert torch.equal(sdf, T(g[f"psdf_{tag}"])) and torch.equal(p.grad, T(g[f"pgrad_{tag}"]))
