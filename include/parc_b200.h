@@ -295,6 +295,59 @@ int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, const float* 
                 const float* heading, const float* root_rot, const float* root_offset, int32_t offset_stride,
                 int64_t n, float* obs_out, int64_t out_stride, void* stream);
 
+/* ---- per-clip terrains, packed (the MDM sampler's terrain gather) ------------------
+ * MotionLib keeps one SubTerrain per clip (anim/motion_lib.py:303-321 `_terrains`) and, from the dataset-prep step,
+ * per-frame lists of the cells the character's body covers (`_hf_mask_inds`, util/terrain_util.py:1951-1997).  For
+ * the device they are concatenated: every clip's heightfield (row-major) and (max, min) band back to back, the
+ * per-frame cell lists as bit words (bit ix*Y+iy of frame t of clip c at mask_words[mask_offset + t*W + word],
+ * W = ceil(dim_x*dim_y/32) -- the frame_mask_out layout of parc_clip_label). */
+typedef struct ParcClipTerrain {
+  int64_t cell_offset;       /* first cell of this clip in hf / hf_maxmin */
+  int64_t mask_offset;       /* first mask word of this clip, or -1 if the clip carries no masks */
+  int32_t dim_x, dim_y;
+  int32_t num_frames;        /* frames the mask covers */
+  int32_t reserved;
+  float min_x, min_y, dx, dy;
+} ParcClipTerrain;
+
+typedef struct ParcClipTerrains {
+  const ParcClipTerrain* clips;   /* device [num_clips] */
+  const float* hf;                /* device [total_cells] */
+  const float* hf_maxmin;         /* device [total_cells, 2] (max, min) as SubTerrain.hf_maxmin, or NULL */
+  const uint32_t* mask_words;     /* device, or NULL */
+  int64_t num_clips;
+  int32_t max_mask_words;         /* max over clips of W */
+  int32_t reserved;
+} ParcClipTerrains;
+
+/* MDMHeightfieldContactMotionSampler.get_hfs_from_data (diffusion/mdm_heightfield_contact_motion_sampler.py:449-474,
+ * helper :414-447) without the random augmentation: for sample i of clip motion_ids[i], a grid_x x grid_y template
+ * (util/geom_util.py:210-221) is rotated by calc_heading(root_rot[i]) and moved to root_pos[i].xy, the clip's
+ * terrain is sampled nearest-cell, and
+ *   hf_out[i, gx, gy]        = hf(cell) - ref_z
+ *   maxmin_out[i, gx, gy, :] = (band(cell) - ref_z), band = the cell's hf_maxmin where any frame of
+ *                              [frame_lo[i], frame_hi[i]] marks the cell, else (free_max, free_min) = (2 max_h, 2 min_h)
+ *   centre_h_out[i]          = hf at the template's centre point (centre_x, centre_y)
+ * ref_z = canon_root_z[i] (RelativeZStyle.RELATIVE_TO_ROOT) or, with canon_root_z == NULL, the centre height
+ * (RELATIVE_TO_ROOT_FLOOR).  maxmin_out / centre_h_out may be NULL. */
+typedef struct ParcClipHfQuery {
+  const int64_t* motion_ids;   /* [n] */
+  const float* root_pos;       /* [n,3] */
+  const float* root_rot;       /* [n,4] */
+  const float* canon_root_z;   /* [n] or NULL */
+  const int32_t* frame_lo;     /* [n] first frame of the sample's window (motion_time_indices[i][0]) */
+  const int32_t* frame_hi;     /* [n] last frame, inclusive */
+  const float* tmpl_xy;        /* [grid_x*grid_y, 2] */
+  int64_t n;
+  int32_t grid_x, grid_y, centre_x, centre_y;
+  float free_max, free_min;
+  float* hf_out;               /* [n, grid_x, grid_y] */
+  float* maxmin_out;           /* [n, grid_x, grid_y, 2] or NULL */
+  float* centre_h_out;         /* [n] or NULL */
+} ParcClipHfQuery;
+
+int parc_clip_hf_gather(const ParcClipTerrains* terrains, const ParcClipHfQuery* query, void* stream);
+
 /* One terrain per sample (hf_batch_stride = X*Y, min_center_stride = 2, base_z_stride = 1) or one
  * terrain shared by the whole batch (strides 0).  x_nodes[X] / y_nodes[Y] are the torch.linspace node
  * offsets the reference adds to min_center (util/terrain_util.py:1855-1860); they are passed in rather
@@ -410,6 +463,84 @@ int parc_clip_label(const float* frames, int64_t batch, int64_t frames_per_clip,
                     const ParcKeyBodies* keys, float contact_eps, float* contacts_out, float* pen_correction_out,
                     float* body_hf_out, uint32_t* frame_mask_out, float* min_body_heights, float* body_pos,
                     float* body_rot, void* stream);
+
+/* ---- f2: kinematic motion optimisation ------------------------------------------
+ * tools/motion_opt/motion_optimization.py:183-395 (motion_terrain_contact_loss) and :404-500
+ * (motion_contact_optimization).  One clip; the optimised leaves are the rows of `frames` [F, 6+D] =
+ * root position | root exp-map | joint DoFs. */
+
+#define PARC_CONSTRAINT_SPHERE 0
+#define PARC_CONSTRAINT_BOX 1
+/* One BodyConstraint (motion_optimization.py:29-32) of a body whose first geom is a sphere or a box (:299-327):
+ * frames start_frame..end_frame (inclusive) pull the body's surface onto `point`.  Sphere: |sdSphere(point, rotate(
+ * body_rot, offset) + body_pos, radius)|.  Box: sum over the body's first 18 surface points (the sole, :320) of
+ * clamp(sdSphere(point, p, radius), min=0) with radius = 1.25 |half extents|.  A constrained (body, frame) pays no
+ * sliding term (:329-332). */
+typedef struct ParcBodyConstraint {
+  int32_t body;
+  int32_t start_frame;
+  int32_t end_frame;
+  int32_t shape;            /* PARC_CONSTRAINT_* */
+  float point[3];
+  float radius;
+  float offset[3];
+  float reserved;
+} ParcBodyConstraint;
+
+typedef struct ParcMotionOptArgs {
+  float* frames;                      /* device [F, 6+D]: the leaves; updated in place by the Adam step */
+  int64_t num_frames;                 /* F */
+  const float* src_root_pos;          /* [F,3]      source clip (constants of the objective) */
+  const float* src_root_rot;          /* [F,4]      quaternion */
+  const float* src_joint_rot;         /* [F,J-1,4] */
+  const float* src_body_vels;         /* [F-1,J,3]  body_pos[1:] - body_pos[:-1] of the source */
+  const float* src_body_rot_vels;     /* [F-1,J]    quat_diff_angle(body_rot[1:], body_rot[:-1]) of the source */
+  const float* contacts;              /* [F,J] */
+  const ParcTerrainBatch* terrain;    /* host pointer: one terrain (strides 0), base_z = -10 in the reference */
+  ParcBodyPoints pts;
+  const ParcBodyConstraint* constraints;   /* device [num_constraints] or NULL */
+  int32_t num_constraints;
+  int32_t reserved;
+  float w_root_pos, w_root_rot, w_joint_rot, w_smoothness, w_penetration, w_contact, w_sliding,
+        w_body_constraints, w_jerk;
+  float reserved2;
+  double max_jerk_dt3;                /* max_jerk * dt^3 (dt = 1/30, :355-356), formed in double as there */
+  double lr, beta1, beta2, eps;       /* torch.optim.Adam: lr = step_size, (0.9, 0.999), 1e-8 */
+  float* exp_avg;                     /* [F, 6+D] Adam state, caller-zeroed */
+  float* exp_avg_sq;                  /* [F, 6+D] */
+  int32_t* step;                      /* device int32[1], caller-zeroed: incremented once per loss_grad launch
+                                         (NULL for a loss / gradient evaluation outside an optimisation) */
+  /* caller-allocated scratch / outputs */
+  float* root_rot;                    /* [F,4]      quaternions of the current leaves */
+  float* joint_rot;                   /* [F,J-1,4] */
+  float* body_pos;                    /* [F,J,3] */
+  float* body_rot;                    /* [F,J,4] */
+  float* g_root_pos;                  /* [F,3]      gradient of the weighted penetration + contact terms */
+  float* g_root_rot;                  /* [F,4] */
+  float* g_joint_rot;                 /* [F,J-1,4] */
+  float* pen;                         /* [F] unweighted per-frame penetration term (may be NULL) */
+  float* con;                         /* [F] unweighted per-frame contact term (may be NULL) */
+  float* grad;                        /* [F, 6+D]   d (weighted objective) / d frames */
+  float* terms;                       /* [F, 8] per-frame partial sums, unweighted: root_pos, root_rot, joint_rot,
+                                         smoothness, sliding, jerk, body_constraint, 0 (may be NULL) */
+} ParcMotionOptArgs;
+
+/* The source-clip constants of the objective (motion_optimization.py:428-436) from the source frames [F, 6+D], with
+ * the SAME device code the objective uses on the leaves -- so a target equal to the source has velocity / tracking
+ * errors of exactly 0, as in the reference (where both sides are the same torch ops); Adam would otherwise turn
+ * last-bit noise into full +-lr steps.  src_root_rot [F,4], src_joint_rot [F,J-1,4], src_body_pos [F,J,3],
+ * src_body_rot [F,J,4], src_body_vels [F-1,J,3], src_body_rot_vels [F-1,J].  2 launches. */
+int parc_motion_opt_source(const float* src_frames, int64_t num_frames, const ParcCharModel* model,
+                           float* src_root_rot, float* src_joint_rot, float* src_body_pos, float* src_body_rot,
+                           float* src_body_vels, float* src_body_rot_vels, void* stream);
+
+/* Objective and gradient at the current leaves: 3 launches (frames -> FK; penetration / contact terms + gradient;
+ * every other term + the whole backward pass).  Same sub-gradient conventions as autograd on the reference. */
+int parc_motion_opt_loss_grad(const ParcMotionOptArgs* args, const ParcCharModel* model, void* stream);
+/* torch.optim.Adam's update of `frames` from `grad` (1 launch); bias correction from *step. */
+int parc_motion_opt_adam_step(const ParcMotionOptArgs* args, const ParcCharModel* model, void* stream);
+/* loss_grad + adam_step: one optimiser iteration, 4 launches, no host synchronisation -- capturable in a CUDA graph. */
+int parc_motion_opt_iteration(const ParcMotionOptArgs* args, const ParcCharModel* model, void* stream);
 
 /* ---- f3: tracker step assembly ------------------------------------------------
  * What the tracking environment computes around the motion query every control step.  One launch each. */

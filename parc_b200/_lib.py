@@ -96,9 +96,52 @@ class ParcTerrainBatch(C.Structure):
                 ("base_z_value", C.c_float), ("reserved", C.c_int32)]
 
 
+class ParcClipTerrain(C.Structure):
+    _fields_ = [("cell_offset", C.c_int64), ("mask_offset", C.c_int64), ("dim_x", C.c_int32), ("dim_y", C.c_int32),
+                ("num_frames", C.c_int32), ("reserved", C.c_int32), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("dx", C.c_float), ("dy", C.c_float)]
+
+
+class ParcClipTerrains(C.Structure):
+    _fields_ = [("clips", C.c_void_p), ("hf", C.c_void_p), ("hf_maxmin", C.c_void_p), ("mask_words", C.c_void_p),
+                ("num_clips", C.c_int64), ("max_mask_words", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ParcClipHfQuery(C.Structure):
+    _fields_ = [("motion_ids", C.c_void_p), ("root_pos", C.c_void_p), ("root_rot", C.c_void_p),
+                ("canon_root_z", C.c_void_p), ("frame_lo", C.c_void_p), ("frame_hi", C.c_void_p),
+                ("tmpl_xy", C.c_void_p), ("n", C.c_int64), ("grid_x", C.c_int32), ("grid_y", C.c_int32),
+                ("centre_x", C.c_int32), ("centre_y", C.c_int32), ("free_max", C.c_float), ("free_min", C.c_float),
+                ("hf_out", C.c_void_p), ("maxmin_out", C.c_void_p), ("centre_h_out", C.c_void_p)]
+
+
 class ParcBodyPoints(C.Structure):
     _fields_ = [("points", C.c_void_p), ("point_start", C.c_void_p), ("num_points", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+class ParcBodyConstraint(C.Structure):
+    _fields_ = [("body", C.c_int32), ("start_frame", C.c_int32), ("end_frame", C.c_int32), ("shape", C.c_int32),
+                ("point", C.c_float * 3), ("radius", C.c_float), ("offset", C.c_float * 3), ("reserved", C.c_float)]
+
+
+PARC_CONSTRAINT_SPHERE, PARC_CONSTRAINT_BOX = 0, 1
+
+
+class ParcMotionOptArgs(C.Structure):
+    _fields_ = [("frames", C.c_void_p), ("num_frames", C.c_int64), ("src_root_pos", C.c_void_p),
+                ("src_root_rot", C.c_void_p), ("src_joint_rot", C.c_void_p), ("src_body_vels", C.c_void_p),
+                ("src_body_rot_vels", C.c_void_p), ("contacts", C.c_void_p), ("terrain", C.c_void_p),
+                ("pts", ParcBodyPoints), ("constraints", C.c_void_p), ("num_constraints", C.c_int32),
+                ("reserved", C.c_int32), ("w_root_pos", C.c_float), ("w_root_rot", C.c_float),
+                ("w_joint_rot", C.c_float), ("w_smoothness", C.c_float), ("w_penetration", C.c_float),
+                ("w_contact", C.c_float), ("w_sliding", C.c_float), ("w_body_constraints", C.c_float),
+                ("w_jerk", C.c_float), ("reserved2", C.c_float), ("max_jerk_dt3", C.c_double), ("lr", C.c_double),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("step", C.c_void_p), ("root_rot", C.c_void_p), ("joint_rot", C.c_void_p),
+                ("body_pos", C.c_void_p), ("body_rot", C.c_void_p), ("g_root_pos", C.c_void_p),
+                ("g_root_rot", C.c_void_p), ("g_joint_rot", C.c_void_p), ("pen", C.c_void_p), ("con", C.c_void_p),
+                ("grad", C.c_void_p), ("terms", C.c_void_p)]
 
 
 PARC_MAX_KEY_BODIES = 4
@@ -170,6 +213,7 @@ SIGNATURES = {
     "parc_hf_sample": (C.c_int, [_P(ParcHeightfield), _V, _I64, _V, _V, _V]),
     "parc_selftest_grid_index": (C.c_int, [_F, _F, _I32, _V, _V]),
     "parc_hf_obs": (C.c_int, [_P(ParcHeightfield), _P(ParcObsSpec), _V, _I32, _V, _V, _V, _I32, _I64, _V, _I64, _V]),
+    "parc_clip_hf_gather": (C.c_int, [_P(ParcClipTerrains), _P(ParcClipHfQuery), _V]),
     "parc_points_hf_sdf": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V]),
     "parc_points_hf_sdf_bwd": (C.c_int, [_V, _I64, _I64, _P(ParcTerrainBatch), _I32, _V, _V, _V, _V]),
     "parc_body_points_fwd": (C.c_int, [_V, _V, _I64, _I64, _I32, _P(ParcBodyPoints), _V, _V]),
@@ -180,6 +224,10 @@ SIGNATURES = {
     "parc_body_loss": (C.c_int, [_V, _V, _V, _V, _I64, _I64, _P(ParcCharModel), _P(ParcBodyPoints),
                                  _P(ParcTerrainBatch), _F, _F, _V, _V, _V, _V, _V, _V]),
     "parc_build_tables": (C.c_int, [_V, _I64, _I32, _V, _V, _V, _V, _V, _V, _I64, _P(ParcCharModel), _V, _V]),
+    "parc_motion_opt_source": (C.c_int, [_V, _I64, _P(ParcCharModel), _V, _V, _V, _V, _V, _V, _V]),
+    "parc_motion_opt_loss_grad": (C.c_int, [_P(ParcMotionOptArgs), _P(ParcCharModel), _V]),
+    "parc_motion_opt_adam_step": (C.c_int, [_P(ParcMotionOptArgs), _P(ParcCharModel), _V]),
+    "parc_motion_opt_iteration": (C.c_int, [_P(ParcMotionOptArgs), _P(ParcCharModel), _V]),
     "parc_char_obs": (C.c_int, [_P(ParcCharState), _I64, _I32, _I32, _I32, _I32, _I32, _V, _I64, _V]),
     "parc_tar_obs": (C.c_int, [_V, _V, _V, _V, _V, _V, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _V, _I32, _V, _I64,
                                _V]),

@@ -12,6 +12,7 @@
 //   warp 0: per-body first-index min (contact), per-body gradient sums, FK VJP -> leaf gradients
 // The min is exact and tie-breaks on the first flat cell index, as torch.min does.
 #include "parc_common.cuh"
+#include "parc_internal.h"
 #include "parc_sdf.cuh"
 
 namespace parc {
@@ -104,6 +105,7 @@ points_hf_sdf_bwd_kernel(const float* __restrict__ points, int64_t batch, int64_
 
 struct BodyLossParams {
   const float *root_pos, *root_rot, *joint_rot, *contacts;
+  int64_t root_pos_stride;      // floats between consecutive frames' root positions (3 = dense [B,F,3])
   int64_t batch, frames;
   ParcBodyPoints pts;
   ParcTerrainBatch terrain;
@@ -167,7 +169,8 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
     float4 prot, local, rot = make_float4(0.f, 0.f, 0.f, 1.f);
     float3 pos = make_float3(0.f, 0.f, 0.f);
     if (lane == 0) {
-      pos = make_float3(__ldg(p.root_pos + q * 3), __ldg(p.root_pos + q * 3 + 1), __ldg(p.root_pos + q * 3 + 2));
+      const float* rp = p.root_pos + q * p.root_pos_stride;
+      pos = make_float3(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2));
       rot = __ldg(reinterpret_cast<const float4*>(p.root_rot) + q);
     } else if (lane < J) {
       rot = __ldg(reinterpret_cast<const float4*>(p.joint_rot) + q * (J - 1) + (lane - 1));
@@ -356,7 +359,19 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
                               const ParcBodyPoints* pts, const ParcTerrainBatch* terrain, float w_pen,
                               float w_contact, float* pen_out, float* contact_out, float* g_root_pos,
                               float* g_root_rot, float* g_joint_rot, void* stream) {
+  return parc::body_loss_launch(root_pos, 3, root_rot, joint_rot, contacts, batch, frames, model, pts, terrain, w_pen,
+                                w_contact, pen_out, contact_out, g_root_pos, g_root_rot, g_joint_rot, stream);
+}
+
+// The launch behind parc_body_loss; root positions may be rows of a wider array (root_pos_stride floats apart), which
+// lets the motion optimiser (motion_opt.cu) read them straight out of its [F, 6+D] leaf buffer.
+int parc::body_loss_launch(const float* root_pos, int64_t root_pos_stride, const float* root_rot, const float* joint_rot,
+                           const float* contacts, int64_t batch, int64_t frames, const ParcCharModel* model,
+                           const ParcBodyPoints* pts, const ParcTerrainBatch* terrain, float w_pen, float w_contact,
+                           float* pen_out, float* contact_out, float* g_root_pos, float* g_root_rot,
+                           float* g_joint_rot, void* stream) {
   if (!model || !pts) return PARC_E_NULL;
+  if (root_pos_stride < 3) return PARC_E_SIZE;
   int rc = parc_validate_model(model);
   if (rc) return rc;
   if (batch < 0 || frames < 0 || pts->num_points <= 0) return PARC_E_SIZE;
@@ -395,7 +410,7 @@ extern "C" int parc_body_loss(const float* root_pos, const float* root_rot, cons
     const int64_t q0 = b0 * frames;
     p.batch = nb;
     p.terrain = terrain_from(*terrain, b0);
-    p.root_pos = root_pos + q0 * 3; p.root_rot = root_rot + q0 * 4;
+    p.root_pos = root_pos + q0 * root_pos_stride; p.root_pos_stride = root_pos_stride; p.root_rot = root_rot + q0 * 4;
     p.joint_rot = joint_rot ? joint_rot + q0 * (J - 1) * 4 : nullptr;
     p.contacts = contacts + q0 * J;
     p.pen_out = pen_out ? pen_out + q0 : nullptr; p.contact_out = contact_out ? contact_out + q0 : nullptr;

@@ -62,6 +62,74 @@ hf_obs_kernel(const __grid_constant__ ParcHeightfield t, const __grid_constant__
   }
 }
 
+// The MDM training sampler's per-sample terrain gather (diffusion/mdm_heightfield_contact_motion_sampler.py:414-447
+// get_hfs_from_data_helper + :449-474 the sampling grid and the relative-z shift of get_hfs_from_data): sample i
+// looks at ITS clip's own terrain through a heading-rotated grid around its root.  The reference loops over the
+// samples in Python (one get_grid_index + 3 advanced-index gathers + a mask rebuild from per-frame index lists each);
+// here: one warp per sample.
+//   1  OR the clip's per-frame cell bitmasks over the sample's frame window -> the warp's shared-memory words
+//      (= compute_hf_mask_from_inds of the window, util/terrain_util.py:1999-2007)
+//   2  lanes stride over the grid points: rotate + translate (rotate_2d_vec, then + root xy), nearest-cell index on
+//      the clip's terrain, gather the height and -- where the window's mask is set -- the cell's (max, min) band,
+//      elsewhere the "free" band (2 max_h, 2 min_h); subtract the relative-z reference (centre cell's height or the
+//      caller's canon root z).
+#define CLIPHF_WARPS 4
+__global__ void __launch_bounds__(CLIPHF_WARPS * 32)
+clip_hf_gather_kernel(const __grid_constant__ ParcClipTerrains ct, const __grid_constant__ ParcClipHfQuery q) {
+  extern __shared__ uint32_t s_words[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* mask = s_words + (size_t)warp * ct.max_mask_words;
+  const float2* __restrict__ tmpl = reinterpret_cast<const float2*>(q.tmpl_xy);
+  const int P = q.grid_x * q.grid_y;
+  const int centre = q.centre_x * q.grid_y + q.centre_y;
+  for (int64_t i = (int64_t)blockIdx.x * CLIPHF_WARPS + warp; i < q.n; i += (int64_t)gridDim.x * CLIPHF_WARPS) {
+    int64_t id = __ldg(q.motion_ids + i);
+    if (id < 0 || id >= ct.num_clips) id = 0;                    // validated on the host side of the mirror
+    const ParcClipTerrain rec = ct.clips[id];
+    const int cells = rec.dim_x * rec.dim_y;
+    const int W = (cells + 31) >> 5;
+    // ---- 1: mask of the frame window ----
+    int t0 = __ldg(q.frame_lo + i), t1 = __ldg(q.frame_hi + i);
+    t0 = max(t0, 0); t1 = min(t1, rec.num_frames - 1);
+    const bool want_band = q.maxmin_out != nullptr && ct.mask_words != nullptr && rec.mask_offset >= 0;
+    if (want_band) {
+      for (int w = lane; w < W; w += 32) {
+        uint32_t acc = 0u;
+        for (int t = t0; t <= t1; ++t) acc |= __ldg(ct.mask_words + rec.mask_offset + (int64_t)t * W + w);
+        mask[w] = acc;
+      }
+    }
+    __syncwarp();
+    // ---- 2: the rotated grid ----
+    const float4 rr = __ldg(reinterpret_cast<const float4*>(q.root_rot) + i);
+    const float h = calc_heading(rr);
+    const float sn = sinf(h), cs = cosf(h);
+    const float rx = __ldg(q.root_pos + i * 3), ry = __ldg(q.root_pos + i * 3 + 1);
+    const float* __restrict__ hf = ct.hf + rec.cell_offset;
+    // relative-z reference: the centre cell's height (RELATIVE_TO_ROOT_FLOOR) or the caller's root z
+    const float2 wc = rotate_offset_2d(__ldg(tmpl + centre), cs, sn, rx, ry);
+    const float centre_h = __ldg(hf + (size_t)grid_index_1d(wc.x, rec.min_x, rec.dx, rec.dim_x) * rec.dim_y +
+                                 grid_index_1d(wc.y, rec.min_y, rec.dy, rec.dim_y));
+    const float ref_z = q.canon_root_z ? __ldg(q.canon_root_z + i) : centre_h;
+    if (lane == 0 && q.centre_h_out) q.centre_h_out[i] = centre_h;
+    for (int k = lane; k < P; k += 32) {
+      const float2 w = rotate_offset_2d(__ldg(tmpl + k), cs, sn, rx, ry);
+      const int cell = grid_index_1d(w.x, rec.min_x, rec.dx, rec.dim_x) * rec.dim_y +
+                       grid_index_1d(w.y, rec.min_y, rec.dy, rec.dim_y);
+      q.hf_out[i * P + k] = sub_rn(__ldg(hf + cell), ref_z);
+      if (q.maxmin_out) {
+        float hi = q.free_max, lo = q.free_min;
+        if (want_band && ((mask[cell >> 5] >> (cell & 31)) & 1u)) {
+          const float2 mm = __ldg(reinterpret_cast<const float2*>(ct.hf_maxmin) + rec.cell_offset + cell);
+          hi = mm.x; lo = mm.y;
+        }
+        reinterpret_cast<float2*>(q.maxmin_out)[i * P + k] = make_float2(sub_rn(hi, ref_z), sub_rn(lo, ref_z));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 static int flat_grid(int64_t total) {
   int64_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
@@ -110,5 +178,33 @@ extern "C" int parc_hf_obs(const ParcHeightfield* hf, const ParcObsSpec* obs, co
   if (ctas > 148 * 16) ctas = 148 * 16;
   hf_obs_kernel<<<(int)ctas, 128, 0, (cudaStream_t)stream>>>(*hf, *obs, root, root_stride, heading, root_rot,
                                                             root_offset, offset_stride, n, obs_out, out_stride);
+  return check_launch();
+}
+
+
+extern "C" int parc_clip_hf_gather(const ParcClipTerrains* terrains, const ParcClipHfQuery* query, void* stream) {
+  if (!terrains || !query) return PARC_E_NULL;
+  if (query->n < 0 || terrains->num_clips <= 0 || query->grid_x <= 0 || query->grid_y <= 0 ||
+      terrains->max_mask_words < 0)
+    return PARC_E_SIZE;
+  if (query->centre_x < 0 || query->centre_x >= query->grid_x || query->centre_y < 0 || query->centre_y >= query->grid_y)
+    return PARC_E_SIZE;
+  if (query->n == 0) return PARC_OK;
+  if (!terrains->clips || !terrains->hf || !query->motion_ids || !query->root_pos || !query->root_rot ||
+      !query->tmpl_xy || !query->hf_out || !query->frame_lo || !query->frame_hi)
+    return PARC_E_NULL;
+  if (query->maxmin_out && !terrains->hf_maxmin) return PARC_E_NULL;
+  if (!aligned16(query->root_rot)) return PARC_E_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(query->tmpl_xy) & 7u) != 0 || (reinterpret_cast<uintptr_t>(query->maxmin_out) & 7u) != 0 ||
+      (reinterpret_cast<uintptr_t>(terrains->hf_maxmin) & 7u) != 0)
+    return PARC_E_ALIGN;
+  const size_t smem = (size_t)CLIPHF_WARPS * terrains->max_mask_words * sizeof(uint32_t);
+  if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;
+  static SmemOptIn opt;
+  int rc = ensure_dynamic_smem(clip_hf_gather_kernel, opt, smem);
+  if (rc) return rc;
+  int64_t ctas = (query->n + CLIPHF_WARPS - 1) / CLIPHF_WARPS;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  clip_hf_gather_kernel<<<(int)ctas, CLIPHF_WARPS * 32, smem, (cudaStream_t)stream>>>(*terrains, *query);
   return check_launch();
 }

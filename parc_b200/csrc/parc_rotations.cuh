@@ -117,4 +117,27 @@ __device__ __forceinline__ float4 joint_dof_to_quat(int joint_type, const float*
   return rotates ? q : make_float4(0.f, 0.f, 0.f, 1.f);
 }
 
+// Lane b (0..J-1) of a warp turns its slice of one raw frame into (pos, rot) inputs of fk_warp:
+// lane 0 -> root position + exp_map_to_quat(root exp-map); lane j >= 1 -> joint j's quaternion.
+__device__ __forceinline__ void frame_to_lane_pose(const ParcCharModel& m, const float* __restrict__ fr, int lane,
+                                                   float3& pos, float4& rot) {
+  pos = make_float3(0.f, 0.f, 0.f);
+  // every lane funnels into the same joint_dof_to_quat call: the root's exp-map is a "spherical joint"
+  int jt = PARC_JOINT_FIXED;
+  float dd[3] = {0.f, 0.f, 0.f};
+  const float* axis = m.joint_axis[0];
+  if (lane == 0) {
+    pos = make_float3(__ldg(fr), __ldg(fr + 1), __ldg(fr + 2));
+    jt = PARC_JOINT_SPHERICAL;
+    dd[0] = __ldg(fr + 3); dd[1] = __ldg(fr + 4); dd[2] = __ldg(fr + 5);
+  } else if (lane < m.num_bodies) {
+    jt = m.joint_type[lane];
+    axis = m.joint_axis[lane];
+    const float* d = fr + 6 + m.dof_idx[lane];
+    if (jt == PARC_JOINT_HINGE) dd[0] = __ldg(d);
+    else if (jt == PARC_JOINT_SPHERICAL) { dd[0] = __ldg(d); dd[1] = __ldg(d + 1); dd[2] = __ldg(d + 2); }
+  }
+  rot = joint_dof_to_quat(jt, dd, axis);
+}
+
 }  // namespace parc

@@ -20,7 +20,7 @@ from typing import List, Optional
 
 import torch
 
-from ... import ops
+from ... import _lib, ops
 from ...anim import kin_char_model
 from ...util import geom_util, torch_util
 from ..procgen.mdm_path import body_points_desc
@@ -62,90 +62,185 @@ def pen_contact_loss(tgt_root_pos, tgt_root_rot_quat, tgt_joint_rot, contacts, t
     return total[0], pen[0], con[0]
 
 
-def _loss_terms(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos, src_root_rot_quat, src_joint_rot,
-                src_body_vels, src_body_rot_vels, contacts, body_points, char_model, w, body_constraints, max_jerk,
-                tb, pts):
-    """All terms as tensors (no host synchronisation, graph-capturable).  `w` = dict of the nine weights.
-    Returns (weighted loss, dict LossType -> 0-dim tensor or python number)."""
-    root_pos_loss = torch.sum(torch.square(tgt_root_pos - src_root_pos))
+WEIGHT_KEYS = ("w_root_pos", "w_root_rot", "w_joint_rot", "w_smoothness", "w_penetration", "w_contact", "w_sliding",
+               "w_body_constraints", "w_jerk")
+_DT = 1.0 / 30.0          # the reference hard-codes the frame time of the jerk term (:355)
 
-    tgt_root_rot_quat = ops.exp_map_to_quat(tgt_root_rot)
-    root_rot_loss = torch.sum(torch.square(torch_util.quat_diff_angle(tgt_root_rot_quat, src_root_rot_quat)))
 
-    tgt_joint_rot = char_model.dof_to_rot(tgt_joint_dof)
-    joint_rot_loss = torch.sum(torch.square(torch_util.quat_diff_angle(tgt_joint_rot, src_joint_rot)))
+def _constraint_records(body_constraints, char_model, body_points):
+    """python BodyConstraint lists (one list per body) -> ParcBodyConstraint records, as :286-332 reads them: only
+    bodies whose first geom is a sphere or a box take part; a box body uses its first 18 surface points (the sole)."""
+    recs = []
+    if body_constraints is None:
+        return recs
+    for b in range(char_model.get_num_joints()):
+        if len(body_constraints[b]) == 0:
+            continue
+        geom0 = char_model.get_geoms(b)[0]
+        if geom0._shape_type == kin_char_model.GeomType.SPHERE:
+            shape, radius = _lib.PARC_CONSTRAINT_SPHERE, float(geom0._dims.reshape(-1)[0].item())
+            offset = geom0._offset.detach().cpu().tolist()
+        elif geom0._shape_type == kin_char_model.GeomType.BOX:
+            shape, radius = _lib.PARC_CONSTRAINT_BOX, float((torch.norm(geom0._dims) * 1.25).item())
+            offset = [0.0, 0.0, 0.0]
+            assert body_points[b].shape[0] >= 18, "a box-constrained body needs its 18 sole points first (:320)"
+        else:
+            continue
+        for c in body_constraints[b]:
+            r = _lib.ParcBodyConstraint()
+            r.body, r.start_frame, r.end_frame, r.shape = b, int(c.start_frame_idx), int(c.end_frame_idx), shape
+            pt = c.constraint_point.detach().cpu().tolist()
+            for k in range(3):
+                r.point[k] = float(pt[k])
+                r.offset[k] = float(offset[k])
+            r.radius = radius
+            recs.append(r)
+    return recs
 
-    tgt_body_pos, tgt_body_rot = char_model.forward_kinematics(tgt_root_pos, tgt_root_rot_quat, tgt_joint_rot)
 
-    tgt_body_vels = tgt_body_pos[1:] - tgt_body_pos[:-1]
-    body_vel_err_sq = torch.square(tgt_body_vels - src_body_vels)
-    tgt_body_rot_vels = torch_util.quat_diff_angle(tgt_body_rot[1:], tgt_body_rot[:-1])
-    body_rot_vel_err_sq = torch.square(tgt_body_rot_vels - src_body_rot_vels)
-    smoothness_loss = torch.sum(body_vel_err_sq) + torch.sum(body_rot_vel_err_sq)
+def source_constants(src_frames, char_model):
+    """(src_root_rot_quat [F,4], src_joint_rot [F,J-1,4], src_body_vels [F-1,J,3], src_body_rot_vels [F-1,J]) of a
+    source clip [F, 6+D] -- motion_optimization.py:428-436 -- computed by the same device code the objective runs on
+    the leaves (include/parc_b200.h: parc_motion_opt_source), so "target == source" has errors of exactly 0."""
+    import ctypes as C
+    model = char_model.c_model()
+    J, D = model.num_bodies, model.dof_size
+    src = _lib.f32c(src_frames.detach()[:, 0:6 + D])
+    _lib.require_cuda(src)
+    F, dev = int(src.shape[0]), src.device
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+    rq, jr, bp, br = z(F, 4), z(F, J - 1, 4), z(F, J, 3), z(F, J, 4)
+    bv, brv = z(max(F - 1, 0), J, 3), z(max(F - 1, 0), J)
+    with torch.cuda.device(dev):
+        rc = _lib.load().parc_motion_opt_source(src.data_ptr(), F, C.byref(model), rq.data_ptr(), jr.data_ptr(),
+                                                bp.data_ptr(), br.data_ptr(), bv.data_ptr(), brv.data_ptr(),
+                                                _lib.stream_ptr(dev))
+    _lib.LAUNCHES[0] += 1
+    _lib.check(rc, "parc_motion_opt_source")
+    return rq, jr, bv, brv
 
-    frame_change_in_contact = torch.clamp(torch.minimum(contacts[1:], contacts[:-1]), min=0.0)
 
-    # --- heightfield terms: fused CUDA forward + backward (:241-272) ---
-    w_contact = w["w_contact"]
-    hf_total, penetration_loss, contact_loss = pen_contact_loss(
-        tgt_root_pos, tgt_root_rot_quat, tgt_joint_rot, contacts, None, body_points, char_model, w["w_penetration"],
-        w_contact, _tb=tb, _pts=pts)
-    contact_logged = contact_loss if w_contact != 0.0 else 0.0
+class MotionOptPlan:
+    """Everything one clip's objective needs, resident on the device, with the argument block of the C entry points
+    (include/parc_b200.h: ParcMotionOptArgs) prebuilt: `loss_grad()` is three launches, `iteration()` four, each ONE
+    ctypes call with no host synchronisation -- so a whole iteration can be captured in a CUDA graph.
 
-    # --- body constraints (:286-332) ---
-    body_constraint_loss = 0.0
-    if body_constraints is not None:
-        for b in range(char_model.get_num_joints()):
-            if len(body_constraints[b]) == 0:
-                continue
-            geom0 = char_model.get_geoms(b)[0]
-            curr_rot = tgt_body_rot[:, b]
-            curr_pos = tgt_body_pos[:, b]
-            for c in body_constraints[b]:
-                s, e = c.start_frame_idx, c.end_frame_idx
-                if geom0._shape_type == kin_char_model.GeomType.SPHERE:
-                    centre = torch_util.quat_rotate(curr_rot, geom0._offset.unsqueeze(0)) + curr_pos
-                    diff = geom_util.sdSphere(c.constraint_point.unsqueeze(0), centre[s:e + 1], geom0._dims)
-                    body_constraint_loss = body_constraint_loss + torch.sum(torch.abs(diff))
-                elif geom0._shape_type == kin_char_model.GeomType.BOX:
-                    radius = torch.norm(geom0._dims) * 1.25
-                    sole = torch_util.quat_rotate(curr_rot[s:e + 1].unsqueeze(1), body_points[b][0:18].unsqueeze(0)) \
-                        + curr_pos[s:e + 1].unsqueeze(1)
-                    diff = geom_util.sdSphere(c.constraint_point.unsqueeze(0), sole.reshape(-1, 3), radius)
-                    body_constraint_loss = body_constraint_loss + torch.sum(torch.clamp(diff, min=0.0))
-                else:
-                    continue
-                # a constrained body does not also pay for sliding / smoothness on those frames
-                body_vel_err_sq = body_vel_err_sq.clone()
-                body_vel_err_sq[s:e + 1, b] *= 0.0
-                body_rot_vel_err_sq = body_rot_vel_err_sq.clone()
-                body_rot_vel_err_sq[s:e + 1, b] *= 0.0
+    frames [F, 6+D] holds the leaves (root position | root exp-map | joint DoFs) and is updated in place."""
 
-    # --- sliding: pseudo-Huber on contact bodies (:339-346) ---
-    if w["w_sliding"] != 0.0:
-        c, c2 = 0.03, 0.0009
-        sliding_loss = torch.sum((torch.sqrt(torch.sum(body_vel_err_sq, dim=-1) + c2) - c) * frame_change_in_contact) \
-            + torch.sum((torch.sqrt(body_rot_vel_err_sq + c2) - c) * frame_change_in_contact)
-    else:
-        sliding_loss = 0.0
+    def __init__(self, frames, src_root_pos, src_root_rot_quat, src_joint_rot, src_body_vels, src_body_rot_vels,
+                 contacts, terrain, body_points, char_model, w: dict, body_constraints, max_jerk: float,
+                 step_size: float = 0.0, with_adam: bool = False, terrain_desc=None):
+        dev = frames.device
+        _lib.require_cuda(frames, src_root_pos, src_root_rot_quat, src_joint_rot, contacts)
+        self.model = char_model.c_model()
+        J, D = self.model.num_bodies, self.model.dof_size
+        F = int(frames.shape[0])
+        assert frames.shape == (F, 6 + D) and frames.dtype == torch.float32 and frames.is_contiguous()
+        f32 = lambda t, shape: _lib.f32c(t.detach()).reshape(shape)
+        self.frames = frames
+        self.w = {k: float(w[k]) for k in WEIGHT_KEYS}
+        self._src = (f32(src_root_pos, (F, 3)), f32(src_root_rot_quat, (F, 4)), f32(src_joint_rot, (F, J - 1, 4)),
+                     f32(src_body_vels, (max(F - 1, 0), J, 3)), f32(src_body_rot_vels, (max(F - 1, 0), J)),
+                     f32(contacts, (F, J)))
+        self._tb = terrain_desc if terrain_desc is not None else _terrain_desc(terrain)
+        self._tbs = self._tb.c_struct(1)
+        self._pts = body_points_desc(char_model, body_points)
+        recs = _constraint_records(body_constraints, char_model, body_points)
+        self._recs = None
+        if recs:
+            import ctypes as C
+            arr = (_lib.ParcBodyConstraint * len(recs))(*recs)
+            self._recs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        self.root_rot, self.joint_rot = z(F, 4), z(F, J - 1, 4)
+        self.body_pos, self.body_rot = z(F, J, 3), z(F, J, 4)
+        self._g = (z(F, 3), z(F, 4), z(F, J - 1, 4))
+        self.pen, self.con = z(F), z(F)
+        self.grad, self.terms = z(F, 6 + D), z(F, 8)
+        self.exp_avg = self.exp_avg_sq = self.step = None
+        if with_adam:
+            self.exp_avg, self.exp_avg_sq = z(F, 6 + D), z(F, 6 + D)
+            self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        a = _lib.ParcMotionOptArgs()
+        a.frames, a.num_frames = frames.data_ptr(), F
+        (a.src_root_pos, a.src_root_rot, a.src_joint_rot, a.src_body_vels, a.src_body_rot_vels,
+         a.contacts) = [t.data_ptr() for t in self._src]
+        import ctypes as C
+        a.terrain = C.addressof(self._tbs)
+        a.pts = self._pts.c_struct()
+        a.constraints, a.num_constraints = _lib.ptr(self._recs), len(recs)
+        for k in WEIGHT_KEYS:
+            setattr(a, k, self.w[k])
+        a.max_jerk_dt3 = float(max_jerk) * (_DT ** 3)
+        a.lr, a.beta1, a.beta2, a.eps = float(step_size), 0.9, 0.999, 1e-8
+        a.exp_avg, a.exp_avg_sq, a.step = _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.step)
+        a.root_rot, a.joint_rot, a.body_pos, a.body_rot = (self.root_rot.data_ptr(), self.joint_rot.data_ptr(),
+                                                           self.body_pos.data_ptr(), self.body_rot.data_ptr())
+        a.g_root_pos, a.g_root_rot, a.g_joint_rot = [t.data_ptr() for t in self._g]
+        a.pen, a.con, a.grad, a.terms = (self.pen.data_ptr(), self.con.data_ptr(), self.grad.data_ptr(),
+                                         self.terms.data_ptr())
+        self._args = a
+        self._lib = _lib.load()
+        self._has_constraints = bool(recs)
+        self.device = dev
 
-    # --- jerk (:348-354) ---
-    acc = tgt_body_vels[1:] - tgt_body_vels[:-1]
-    jerk_mag = torch.norm(acc[1:] - acc[:-1], dim=-1)
-    dt = 1.0 / 30.0
-    jerk_loss = torch.sum(torch.clamp(jerk_mag - max_jerk * (dt ** 3), min=0.0))
+    def _call(self, fn, name, launches):
+        import ctypes as C
+        with torch.cuda.device(self.device):
+            rc = fn(C.byref(self._args), C.byref(self.model), _lib.stream_ptr(self.device))
+        _lib.LAUNCHES[0] += launches - 1
+        _lib.check(rc, name)
 
-    terms = {
-        LossType.ROOT_POS_LOSS: root_pos_loss, LossType.ROOT_ROT_LOSS: root_rot_loss,
-        LossType.JOINT_ROT_LOSS: joint_rot_loss, LossType.SMOOTHNESS_LOSS: smoothness_loss,
-        LossType.PENETRATION_LOSS: penetration_loss, LossType.CONTACT_LOSS: contact_logged,
-        LossType.SLIDING_LOSS: sliding_loss, LossType.JERK_LOSS: jerk_loss,
-        LossType.BODY_CONSTRAINT_LOSS: body_constraint_loss,
-    }
-    loss = w["w_root_pos"] * root_pos_loss + w["w_root_rot"] * root_rot_loss + w["w_joint_rot"] * joint_rot_loss \
-        + w["w_smoothness"] * smoothness_loss + hf_total + w["w_sliding"] * sliding_loss \
-        + w["w_body_constraints"] * body_constraint_loss + w["w_jerk"] * jerk_loss
-    return loss, terms
+    def loss_grad(self):
+        """Objective + gradient at the current `frames`: fills grad / terms / pen / con.  3 launches."""
+        self._call(self._lib.parc_motion_opt_loss_grad, "parc_motion_opt_loss_grad", 3)
+
+    def adam_step(self):
+        self._call(self._lib.parc_motion_opt_adam_step, "parc_motion_opt_adam_step", 1)
+
+    def iteration(self):
+        """loss_grad + Adam update of `frames`: 4 launches, one C call, no host synchronisation."""
+        self._call(self._lib.parc_motion_opt_iteration, "parc_motion_opt_iteration", 4)
+
+    def term_tensors(self):
+        """(weighted loss, dict LossType -> 0-dim tensor or python number) of the LAST loss_grad / iteration --
+        a few reductions over [F] vectors, only run when somebody looks (logging iterations)."""
+        t = self.terms.sum(dim=0)
+        pen, con = self.pen.sum(), self.con.sum()
+        w = self.w
+        terms = {
+            LossType.ROOT_POS_LOSS: t[0], LossType.ROOT_ROT_LOSS: t[1], LossType.JOINT_ROT_LOSS: t[2],
+            LossType.SMOOTHNESS_LOSS: t[3], LossType.PENETRATION_LOSS: pen,
+            LossType.CONTACT_LOSS: con if w["w_contact"] != 0.0 else 0.0,
+            LossType.SLIDING_LOSS: t[4] if w["w_sliding"] != 0.0 else 0.0, LossType.JERK_LOSS: t[5],
+            LossType.BODY_CONSTRAINT_LOSS: t[6] if self._has_constraints else 0.0,
+        }
+        loss = (w["w_root_pos"] * t[0] + w["w_root_rot"] * t[1] + w["w_joint_rot"] * t[2] + w["w_smoothness"] * t[3]
+                + w["w_penetration"] * pen + w["w_contact"] * con + w["w_sliding"] * t[4]
+                + w["w_body_constraints"] * t[6] + w["w_jerk"] * t[5])
+        return loss, terms
+
+
+class _MotionOptLoss(torch.autograd.Function):
+    """The nine-term objective as ONE differentiable operator: forward runs MotionOptPlan.loss_grad (value and
+    gradient come out of the same three launches), backward scales the stored gradient."""
+
+    @staticmethod
+    def forward(ctx, tgt_root_pos, tgt_root_rot, tgt_joint_dof, plan_args):
+        frames = torch.cat([tgt_root_pos, tgt_root_rot, tgt_joint_dof], dim=-1).detach().to(torch.float32).contiguous()
+        plan = MotionOptPlan(frames, *plan_args)
+        plan.loss_grad()
+        loss, terms = plan.term_tensors()
+        ctx.save_for_backward(plan.grad)
+        ctx.D = tgt_joint_dof.shape[-1]
+        ctx.mark_non_differentiable(plan.terms, plan.pen, plan.con)
+        return loss, plan.terms, plan.pen, plan.con
+
+    @staticmethod
+    def backward(ctx, g, _gt, _gp, _gc):
+        (grad,) = ctx.saved_tensors
+        gg = grad * g
+        return gg[:, 0:3], gg[:, 3:6], gg[:, 6:6 + ctx.D], None
 
 
 def _to_floats(terms):
@@ -158,13 +253,23 @@ def motion_terrain_contact_loss(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_r
                                 w_joint_rot: float, w_smoothness: float, w_penetration: float, w_contact: float,
                                 w_sliding: float, w_body_constraints: float, w_jerk: float, body_constraints: list,
                                 max_jerk: float):
-    """-> (loss tensor, dict LossType -> float).  Ref :183-395."""
+    """-> (loss tensor, dict LossType -> float); `loss.backward()` reaches tgt_root_pos / tgt_root_rot / tgt_joint_dof
+    exactly as autograd does in the reference.  Three launches forward + backward together.  Ref :183-395."""
     w = dict(w_root_pos=w_root_pos, w_root_rot=w_root_rot, w_joint_rot=w_joint_rot, w_smoothness=w_smoothness,
              w_penetration=w_penetration, w_contact=w_contact, w_sliding=w_sliding,
              w_body_constraints=w_body_constraints, w_jerk=w_jerk)
-    loss, terms = _loss_terms(tgt_root_pos, tgt_root_rot, tgt_joint_dof, src_root_pos, src_root_rot_quat,
-                              src_joint_rot, src_body_vels, src_body_rot_vels, contacts, body_points, char_model, w,
-                              body_constraints, max_jerk, _terrain_desc(terrain), body_points_desc(char_model, body_points))
+    plan_args = (src_root_pos, src_root_rot_quat, src_joint_rot, src_body_vels, src_body_rot_vels, contacts, terrain,
+                 body_points, char_model, w, body_constraints, max_jerk)
+    loss, terms_f, pen, con = _MotionOptLoss.apply(tgt_root_pos, tgt_root_rot, tgt_joint_dof, plan_args)
+    t = terms_f.detach().sum(dim=0)
+    has_bc = body_constraints is not None and any(len(c) > 0 for c in body_constraints)
+    terms = {
+        LossType.ROOT_POS_LOSS: t[0], LossType.ROOT_ROT_LOSS: t[1], LossType.JOINT_ROT_LOSS: t[2],
+        LossType.SMOOTHNESS_LOSS: t[3], LossType.PENETRATION_LOSS: pen.detach().sum(),
+        LossType.CONTACT_LOSS: con.detach().sum() if w_contact != 0.0 else 0.0,
+        LossType.SLIDING_LOSS: t[4] if w_sliding != 0.0 else 0.0, LossType.JERK_LOSS: t[5],
+        LossType.BODY_CONSTRAINT_LOSS: t[6] if has_bc else 0.0,
+    }
     return loss, _to_floats(terms)
 
 
@@ -200,42 +305,28 @@ def motion_contact_optimization(src_frames: torch.Tensor, contacts: torch.Tensor
                                 use_cuda_graph: bool = True, quiet: bool = False):
     """Adam over (root_pos, root exp-map, joint DoFs) so that the clip stops penetrating / floating above the
     terrain while staying close to `src_frames`.  -> optimised frames [F, 6+D].  Ref :404-500.
+
+    One iteration = MotionOptPlan.iteration(): four launches (FK of the leaves; penetration / contact terms + gradient;
+    every other term + the whole backward pass; the Adam update), replayed as a CUDA graph; the host synchronises
+    only on logging iterations (every 25th), where the reference calls `.item()` on seven terms every iteration.
+    `use_cuda_graph=False` enqueues the same four launches from Python -- results are bit-identical.
     `use_wandb` is accepted and ignored (logging back ends are out of scope)."""
     start_time = time.time()
     D = char_model.get_dof_size()
-    src_root_pos = src_frames[:, 0:3]
-    src_root_rot = src_frames[:, 3:6]
-    src_joint_dof = src_frames[:, 6:6 + D]
-    with torch.no_grad():
-        src_root_rot_quat = ops.exp_map_to_quat(src_root_rot)
-        src_joint_rot = char_model.dof_to_rot(src_joint_dof)
-        src_body_pos, src_body_rot = char_model.forward_kinematics(src_root_pos, src_root_rot_quat, src_joint_rot)
-        src_body_vels = src_body_pos[1:] - src_body_pos[:-1]
-        src_body_rot_vels = torch_util.quat_diff_angle(src_body_rot[1:], src_body_rot[:-1])
-
-    leaves = [src_root_pos.clone().requires_grad_(True), src_root_rot.clone().requires_grad_(True),
-              src_joint_dof.clone().requires_grad_(True)]
+    src = src_frames[:, 0:6 + D].detach().to(torch.float32).contiguous()
+    src_root_rot_quat, src_joint_rot, src_body_vels, src_body_rot_vels = source_constants(src, char_model)
     w = dict(w_root_pos=w_root_pos, w_root_rot=w_root_rot, w_joint_rot=w_joint_rot, w_smoothness=w_smoothness,
              w_penetration=w_penetration, w_contact=w_contact, w_sliding=w_sliding,
              w_body_constraints=w_body_constraints, w_jerk=w_jerk)
-    tb = _terrain_desc(terrain)
-    pts = body_points_desc(char_model, body_points)
-    # capturable=True keeps Adam's step counter on the device so optimizer.step() can live inside a CUDA graph
-    optimizer = torch.optim.Adam(leaves, lr=step_size, capturable=use_cuda_graph)
-
-    def iteration():
-        optimizer.zero_grad(set_to_none=False)
-        loss, terms = _loss_terms(leaves[0], leaves[1], leaves[2], src_root_pos, src_root_rot_quat, src_joint_rot,
-                                  src_body_vels, src_body_rot_vels, contacts, body_points, char_model, w,
-                                  body_constraints, max_jerk, tb, pts)
-        loss.backward()
-        optimizer.step()
-        return loss, terms
-
+    frames = src.clone()
+    plan = MotionOptPlan(frames, src[:, 0:3], src_root_rot_quat, src_joint_rot, src_body_vels, src_body_rot_vels,
+                         contacts, terrain, body_points, char_model, w, body_constraints, max_jerk, step_size=step_size,
+                         with_adam=True)
     logger = _TextLogger(log_file)
     log_iter_stride = 25
 
-    def log(it, loss, terms):
+    def log(it):
+        loss, terms = plan.term_tensors()
         logger.log("Iteration", it)
         logger.log("Time (min)", (time.time() - start_time) / 60.0)
         logger.log("TOTAL WEIGHTED LOSS", loss.item())
@@ -244,30 +335,29 @@ def motion_contact_optimization(src_frames: torch.Tensor, contacts: torch.Tensor
         logger.flush(quiet)
 
     it = 0
+    dev = frames.device
     if use_cuda_graph and num_iters > 3:
-        # two eager iterations on a side stream (allocator warm-up, Adam state creation), then capture one
-        side = torch.cuda.Stream(device=src_frames.device)
-        side.wait_stream(torch.cuda.current_stream(src_frames.device))
+        # one eager iteration on a side stream (module load, first-use work), then capture the next
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(2):
-                loss, terms = iteration()
-                if it % log_iter_stride == 0:
-                    log(it, loss, terms)
-                it += 1
-        torch.cuda.current_stream(src_frames.device).wait_stream(side)
+            plan.iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        log(it)
+        it += 1
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            g_loss, g_terms = iteration()
-        while it < num_iters:                     # capture records but does not execute: replay #1 is iteration 2
+            plan.iteration()
+        while it < num_iters:                     # capture records but does not execute: replay #1 is iteration 1
             graph.replay()
             if it % log_iter_stride == 0:
-                log(it, g_loss, g_terms)
+                log(it)
             it += 1
     else:
         while it < num_iters:
-            loss, terms = iteration()
+            plan.iteration()
             if it % log_iter_stride == 0:
-                log(it, loss, terms)
+                log(it)
             it += 1
     logger.close()
-    return torch.cat([t.detach() for t in leaves], dim=-1)
+    return frames
