@@ -826,6 +826,42 @@ def motion_contact_optimization(model: CharModel, src_frames, contacts, hf, min_
 
 
 # --------------------------------------------------------------------------
+# MDM sampler terrain gather (SURVEY.md §8(f)-4 clause)
+# --------------------------------------------------------------------------
+def clip_hfs_from_data(terrains, hf_maxmins, hf_mask_inds, motion_ids, root_pos, root_rot, canon_root_z,
+                       motion_time_indices, tmpl, num_x_neg, num_y_neg, max_h, relative_to_root):
+    """diffusion/mdm_heightfield_contact_motion_sampler.py:449-474 (get_hfs_from_data, augmentation off) with its helper
+    :414-447.  terrains: list of Terrain; hf_maxmins: list of [X,Y,2]; hf_mask_inds: per clip a list (frames) of int64
+    [n,2] index tensors; tmpl [GX,GY,2].  -> (hfs [B,GX,GY], center_h [B], hf_maxmins [B,GX,GY,2])."""
+    B = root_pos.shape[0]
+    GX, GY = tmpl.shape[0], tmpl.shape[1]
+    heading = calc_heading(root_rot).unsqueeze(-1).unsqueeze(-1).expand(-1, GX, GY)
+    xy = rotate_2d(tmpl.unsqueeze(0).expand(B, -1, -1, -1), heading) + root_pos[:, 0:2].unsqueeze(1).unsqueeze(1)
+    min_h = -max_h
+    hfs, mms = [], []
+    for i in range(B):
+        t = terrains[int(motion_ids[i])]
+        inds = grid_index(t, xy[i])
+        hfs.append(t.hf[inds[..., 0], inds[..., 1]])
+        sl = slice(int(motion_time_indices[i][0]), int(motion_time_indices[i][-1]) + 1)
+        mask = torch.zeros(t.hf.shape, dtype=torch.bool)
+        for fr in hf_mask_inds[int(motion_ids[i])][sl]:
+            mask[fr[..., 0], fr[..., 1]] = True
+        mask = mask.unsqueeze(-1).expand(-1, -1, 2)
+        band = torch.zeros_like(hf_maxmins[int(motion_ids[i])])
+        band[..., 0] = max_h * 2.0
+        band[..., -1] = min_h * 2.0
+        band[mask] = hf_maxmins[int(motion_ids[i])][mask]
+        mms.append(band[inds[..., 0], inds[..., 1], :])
+    hfs, mms = torch.stack(hfs, dim=0), torch.stack(mms, dim=0)
+    center_h = hfs[:, num_x_neg, num_y_neg].clone()
+    ref = canon_root_z if relative_to_root else center_h
+    hfs = hfs - ref.unsqueeze(-1).unsqueeze(-1)
+    mms = mms - ref.unsqueeze(-1).unsqueeze(-1).unsqueeze(-1)
+    return hfs, center_h, mms
+
+
+# --------------------------------------------------------------------------
 # tracker step assembly (SURVEY.md §8(f)-3): policy observation, reward, done
 # --------------------------------------------------------------------------
 DONE_NULL, DONE_FAIL, DONE_SUCC, DONE_TIME = 0, 1, 2, 3        # envs/base_env.py:12-16

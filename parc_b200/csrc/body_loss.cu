@@ -116,24 +116,36 @@ struct BodyLossParams {
   int want_grad;
 };
 
-template <bool SMEM_TILE>
+// WPF = warps per frame.  1: one warp per frame, LOSS_WARPS frames in flight per CTA, no block barrier in the frame
+// loop -- the throughput form for big batches.  LOSS_WARPS: the whole CTA works on ONE frame (surface points spread
+// over 128 threads, the lane = body steps on warp 0 between block barriers) -- the latency form for a single clip
+// (the motion optimiser's 254 frames would otherwise occupy 254 warps of the 9 472 the GPU holds).  Both forms add
+// in the same order and give identical bits.
+#define LOSS_PT 8            // floats per surface point in the slab: 7 gradient slots + its penetration term
+template <bool SMEM_TILE, int WPF>
 __global__ void __launch_bounds__(LOSS_THREADS)
 body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
   __shared__ ParcCharModel sm;
   __shared__ float s_minmax[2];
+  constexpr int TEAMS = LOSS_WARPS / WPF;          // frames in flight per CTA
 
   const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
   const int S = p.pts.num_points;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / WPF, twarp = warp % WPF;      // this warp's team and its index inside it
+  const int tlane = twarp * 32 + lane;                  // thread index inside the team
   float* s_cx = smem;
   float* s_cy = s_cx + X;
   int* s_body = reinterpret_cast<int*>(s_cy + Y);                    // [S] body of point
   float* s_lp = reinterpret_cast<float*>(s_body + S);                // [S][3] local points
-  float* slab = s_lp + (size_t)S * 3 + (size_t)warp * ((size_t)S * 7 + PARC_MAX_BODIES * 9);
+  float* slab = s_lp + (size_t)S * 3 + (size_t)team * ((size_t)S * LOSS_PT + PARC_MAX_BODIES * 9);
   float* s_bt = slab;                                                // [J][9] pos(3) rot(4) contact(1) winner(1)
-  float* s_pt = slab + PARC_MAX_BODIES * 9;                          // [S][7]
-  float* s_tile = s_lp + (size_t)S * 3 + (size_t)LOSS_WARPS * ((size_t)S * 7 + PARC_MAX_BODIES * 9);   // [X*Y] last
+  float* s_pt = slab + PARC_MAX_BODIES * 9;                          // [S][LOSS_PT]
+  float* s_tile = s_lp + (size_t)S * 3 + (size_t)TEAMS * ((size_t)S * LOSS_PT + PARC_MAX_BODIES * 9);   // [X*Y] last
+  auto team_sync = [&]() {
+    if (WPF == 1) __syncwarp(); else __syncthreads();              // WPF == LOSS_WARPS: the team is the CTA
+  };
 
   const int64_t b = blockIdx.y;
   stage_model(&sm, model_param);
@@ -163,31 +175,32 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
 
   const int64_t f_begin = (int64_t)blockIdx.x * p.frames_per_cta;
   const int64_t f_end = min(f_begin + (int64_t)p.frames_per_cta, p.frames);
-  for (int64_t f = f_begin + warp; f < f_end; f += LOSS_WARPS) {
+  for (int64_t f = f_begin + team; f < f_end; f += TEAMS) {
     const int64_t q = b * p.frames + f;
-    // ---- FK, lane = body ----
-    float4 prot, local, rot = make_float4(0.f, 0.f, 0.f, 1.f);
+    // ---- FK, lane = body (the team's first warp) ----
+    float4 prot = make_float4(0.f, 0.f, 0.f, 1.f), local = prot, rot = prot;
     float3 pos = make_float3(0.f, 0.f, 0.f);
-    if (lane == 0) {
-      const float* rp = p.root_pos + q * p.root_pos_stride;
-      pos = make_float3(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2));
-      rot = __ldg(reinterpret_cast<const float4*>(p.root_rot) + q);
-    } else if (lane < J) {
-      rot = __ldg(reinterpret_cast<const float4*>(p.joint_rot) + q * (J - 1) + (lane - 1));
-    }
-    fk_warp_keep(lb, max_depth, pos, rot, prot, local);
     float my_contact = 0.0f;
-    if (lane < J) {
-      my_contact = __ldg(p.contacts + q * J + lane);
-      float* t = s_bt + lane * 9;
-      t[0] = pos.x; t[1] = pos.y; t[2] = pos.z; t[3] = rot.x; t[4] = rot.y; t[5] = rot.z; t[6] = rot.w;
-      t[7] = my_contact;
+    if (twarp == 0) {
+      if (lane == 0) {
+        const float* rp = p.root_pos + q * p.root_pos_stride;
+        pos = make_float3(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2));
+        rot = __ldg(reinterpret_cast<const float4*>(p.root_rot) + q);
+      } else if (lane < J) {
+        rot = __ldg(reinterpret_cast<const float4*>(p.joint_rot) + q * (J - 1) + (lane - 1));
+      }
+      fk_warp_keep(lb, max_depth, pos, rot, prot, local);
+      if (lane < J) {
+        my_contact = __ldg(p.contacts + q * J + lane);
+        float* t = s_bt + lane * 9;
+        t[0] = pos.x; t[1] = pos.y; t[2] = pos.z; t[3] = rot.x; t[4] = rot.y; t[5] = rot.z; t[6] = rot.w;
+        t[7] = my_contact;
+      }
     }
-    __syncwarp();
+    team_sync();
 
-    // ---- sweep, lane = surface point ----
-    float pen_local = 0.0f;
-    for (int k = lane; k < S; k += 32) {
+    // ---- sweep, team thread = surface point ----
+    for (int k = tlane; k < S; k += 32 * WPF) {
       const int bj = s_body[k];
       const float* t = s_bt + bj * 9;
       const float3 lp = make_float3(s_lp[k * 3], s_lp[k * 3 + 1], s_lp[k * 3 + 2]);
@@ -205,8 +218,8 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
       }
       // penetration: sdf = -best.inv ; neg = min(sdf, 0) ; pen += -neg
       const float sdf_inv = -1.0f * best.inv;
-      pen_local += -fminf(sdf_inv, 0.0f);
-      float* g7 = s_pt + (size_t)k * 7;
+      float* g7 = s_pt + (size_t)k * LOSS_PT;
+      g7[7] = -fminf(sdf_inv, 0.0f);
       g7[6] = fmaxf(best.sol, 0.0f);                 // clamp(sdf_solid, min=0)
       if (p.want_grad) {
         // d pen / d wp = [sdf_inv <= 0] * grad sdBox(air cell), already weighted
@@ -222,36 +235,41 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
         g7[3] = gs.x; g7[4] = gs.y; g7[5] = gs.z;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pen_local += __shfl_xor_sync(PARC_FULL_MASK, pen_local, o);
-    __syncwarp();
+    team_sync();
 
-    // ---- contact term, lane = body: first-index min over the body's points ----
-    float cterm = 0.0f;
-    int win = -1;
-    if (lane < J) {
-      float bestv = INFINITY;
-      for (int k = my_s0; k < my_s1; ++k) {
-        const float v = s_pt[(size_t)k * 7 + 6];
-        if (v < bestv) { bestv = v; win = k; }
+    // ---- penetration sum + contact term on the team's first warp: lane-strided partial sums in point order, then
+    //      the xor tree (the same order for every WPF); first-index min over each body's points ----
+    if (twarp == 0) {
+      float pen_local = 0.0f;
+      for (int k = lane; k < S; k += 32) pen_local += s_pt[(size_t)k * LOSS_PT + 7];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pen_local += __shfl_xor_sync(PARC_FULL_MASK, pen_local, o);
+      float cterm = 0.0f;
+      int win = -1;
+      if (lane < J) {
+        float bestv = INFINITY;
+        for (int k = my_s0; k < my_s1; ++k) {
+          const float v = s_pt[(size_t)k * LOSS_PT + 6];
+          if (v < bestv) { bestv = v; win = k; }
+        }
+        cterm = bestv * my_contact;                    // closest_distances * contacts[..., b]
+        s_bt[lane * 9 + 8] = __int_as_float(win);
       }
-      cterm = bestv * my_contact;                    // closest_distances * contacts[..., b]
-      s_bt[lane * 9 + 8] = __int_as_float(win);
+      float contact_f = 0.0f;
+      for (int j = 0; j < J; ++j) contact_f += __shfl_sync(PARC_FULL_MASK, cterm, j);   // body order, as the reference
+      if (lane == 0) {
+        if (p.pen_out) p.pen_out[q] = pen_local;
+        if (p.contact_out) p.contact_out[q] = contact_f;
+      }
     }
-    float contact_f = 0.0f;
-    for (int j = 0; j < J; ++j) contact_f += __shfl_sync(PARC_FULL_MASK, cterm, j);   // body order, as the reference
-    if (lane == 0) {
-      if (p.pen_out) p.pen_out[q] = pen_local;
-      if (p.contact_out) p.contact_out[q] = contact_f;
-    }
-    __syncwarp();
+    team_sync();
     if (!p.want_grad) continue;
 
-    // ---- chain rule, lane = point: add the winner's contact gradient, VJP through the body transform ----
-    for (int k = lane; k < S; k += 32) {
+    // ---- chain rule, team thread = point: add the winner's contact gradient, VJP through the body transform ----
+    for (int k = tlane; k < S; k += 32 * WPF) {
       const int bj = s_body[k];
       const float* t = s_bt + bj * 9;
-      float* g7 = s_pt + (size_t)k * 7;
+      float* g7 = s_pt + (size_t)k * LOSS_PT;
       float3 g = make_float3(g7[0], g7[1], g7[2]);
       if (__float_as_int(t[8]) == k) {               // this point won its body's contact min
         const float cw = p.w_contact * t[7];
@@ -262,25 +280,27 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
       g7[0] = g.x; g7[1] = g.y; g7[2] = g.z;
       g7[3] = gq.x; g7[4] = gq.y; g7[5] = gq.z; g7[6] = gq.w;
     }
-    __syncwarp();
+    team_sync();
 
     // ---- body sums (fixed order), lane = body; then the FK VJP ----
-    float3 gp = make_float3(0.f, 0.f, 0.f);
-    float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = my_s0; k < my_s1; ++k) {
-      const float* g7 = s_pt + (size_t)k * 7;
-      gp.x += g7[0]; gp.y += g7[1]; gp.z += g7[2];
-      gr.x += g7[3]; gr.y += g7[4]; gr.z += g7[5]; gr.w += g7[6];
+    if (twarp == 0) {
+      float3 gp = make_float3(0.f, 0.f, 0.f);
+      float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = my_s0; k < my_s1; ++k) {
+        const float* g7 = s_pt + (size_t)k * LOSS_PT;
+        gp.x += g7[0]; gp.y += g7[1]; gp.z += g7[2];
+        gr.x += g7[3]; gr.y += g7[4]; gr.z += g7[5]; gr.w += g7[6];
+      }
+      float4 gj;
+      fk_warp_vjp(lb, J, lane, prot, local, gp, gr, gj);
+      if (lane == 0) {
+        if (p.g_root_pos) { p.g_root_pos[q * 3] = gp.x; p.g_root_pos[q * 3 + 1] = gp.y; p.g_root_pos[q * 3 + 2] = gp.z; }
+        if (p.g_root_rot) reinterpret_cast<float4*>(p.g_root_rot)[q] = gr;
+      } else if (lane < J) {
+        if (p.g_joint_rot) reinterpret_cast<float4*>(p.g_joint_rot)[q * (J - 1) + (lane - 1)] = gj;
+      }
     }
-    float4 gj;
-    fk_warp_vjp(lb, J, lane, prot, local, gp, gr, gj);
-    if (lane == 0) {
-      if (p.g_root_pos) { p.g_root_pos[q * 3] = gp.x; p.g_root_pos[q * 3 + 1] = gp.y; p.g_root_pos[q * 3 + 2] = gp.z; }
-      if (p.g_root_rot) reinterpret_cast<float4*>(p.g_root_rot)[q] = gr;
-    } else if (lane < J) {
-      if (p.g_joint_rot) reinterpret_cast<float4*>(p.g_joint_rot)[q * (J - 1) + (lane - 1)] = gj;
-    }
-    __syncwarp();
+    team_sync();
   }
 }
 
@@ -389,20 +409,25 @@ int parc::body_loss_launch(const float* root_pos, int64_t root_pos_stride, const
   p.want_grad = (g_root_pos || g_root_rot || g_joint_rot) ? 1 : 0;
 
   const size_t S = (size_t)pts->num_points;
-  const size_t fixed = nodes_smem_bytes(terrain) + (S * (1 + 3) + LOSS_WARPS * (S * 7 + PARC_MAX_BODIES * 9)) * sizeof(float);
+  // Few frames in total (a single clip being optimised): the whole CTA works on one frame, one frame per CTA.
+  // Otherwise one warp per frame, LOSS_WARPS frames in flight per CTA, the terrain staging amortised over several
+  // rounds when there is plenty of work.
+  const bool team = batch * frames <= (int64_t)148 * 16;
+  const int teams = team ? 1 : LOSS_WARPS;
+  const size_t fixed = nodes_smem_bytes(terrain) + (S * (1 + 3) + teams * (S * LOSS_PT + PARC_MAX_BODIES * 9)) * sizeof(float);
   const bool smem_tile = fixed + tile_smem_bytes(terrain) <= PARC_SMEM_LIMIT;
   const size_t smem = fixed + (smem_tile ? tile_smem_bytes(terrain) : 0);
   if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;      // too many surface points for one CTA's slabs
-  static SmemOptIn opt_tile, opt_global;
-  rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true>, opt_tile, smem)
-                 : ensure_dynamic_smem(body_loss_kernel<false>, opt_global, smem);
+  static SmemOptIn opt[4];
+  if (team) rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true, LOSS_WARPS>, opt[0], smem)
+                           : ensure_dynamic_smem(body_loss_kernel<false, LOSS_WARPS>, opt[1], smem);
+  else rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true, 1>, opt[2], smem)
+                      : ensure_dynamic_smem(body_loss_kernel<false, 1>, opt[3], smem);
   if (rc) return rc;
-  // one warp per frame, LOSS_WARPS frames in flight per CTA; amortise the terrain staging over several
-  // rounds when there is plenty of work, keep the grid wide when there is not
   int64_t rounds = (batch * frames) / ((int64_t)148 * 16 * LOSS_WARPS);
   if (rounds < 1) rounds = 1;
   if (rounds > 8) rounds = 8;
-  const int64_t fpc = rounds * LOSS_WARPS;
+  const int64_t fpc = team ? 1 : rounds * LOSS_WARPS;
   p.frames_per_cta = (int)fpc;
   const int J = model->num_bodies;
   for (int64_t b0 = 0; b0 < batch; b0 += PARC_GRID_Y_MAX) {       // grid.y is limited to 65 535 samples per launch
@@ -418,8 +443,13 @@ int parc::body_loss_launch(const float* root_pos, int64_t root_pos_stride, const
     p.g_root_rot = g_root_rot ? g_root_rot + q0 * 4 : nullptr;
     p.g_joint_rot = g_joint_rot ? g_joint_rot + q0 * (J - 1) * 4 : nullptr;
     dim3 grid((unsigned)((frames + fpc - 1) / fpc), (unsigned)nb);
-    if (smem_tile) body_loss_kernel<true><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
-    else body_loss_kernel<false><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+    if (team) {
+      if (smem_tile) body_loss_kernel<true, LOSS_WARPS><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+      else body_loss_kernel<false, LOSS_WARPS><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+    } else {
+      if (smem_tile) body_loss_kernel<true, 1><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+      else body_loss_kernel<false, 1><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+    }
   }
   return check_launch();
 }

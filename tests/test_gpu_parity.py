@@ -465,6 +465,58 @@ def test_query_variants_pdl_and_output_selection_are_bit_identical(golden_lib):
     assert torch.equal(got["body_pos"], base["body_pos"]) and torch.equal(got["obs"], base["obs"])
 
 
+def test_mdm_sampler_terrain_gather_vs_golden():
+    """diffusion/mdm_heightfield_contact_motion_sampler.py:414-474 (get_hfs_from_data, augmentation off) in one
+    launch over packed per-clip terrains: heights, centre heights and the augmenter's (max, min) bands under the
+    frame-window body masks, both relative-z styles, against the reference's outputs.  Samples within 8 ulp of a cell
+    border may land in the neighbouring cell (GPU vs host sin / cos of the heading); everything else is exact."""
+    from parc_b200.diffusion.mdm_heightfield_contact_motion_sampler import (ClipHeightfieldSampler, ClipTerrainPack,
+                                                                             RelativeZStyle, mask_inds_to_bits)
+    from parc_b200.util.terrain_util import SubTerrain
+    g = golden("sampler_golden.npz")
+    terrains, bits = [], []
+    for c in range(3):
+        hf = g[f"hf{c}"]
+        t = SubTerrain(f"c{c}", x_dim=hf.shape[0], y_dim=hf.shape[1], dx=float(g[f"dxdy{c}"][0]), dy=float(g[f"dxdy{c}"][1]),
+                       min_x=float(g[f"min_point{c}"][0]), min_y=float(g[f"min_point{c}"][1]), device="cuda:0")
+        t.hf, t.hf_maxmin = dev(hf), dev(g[f"maxmin{c}"])
+        terrains.append(t)
+        flat, cnt = torch.tensor(g[f"mask_inds{c}"]), g[f"mask_count{c}"].tolist()
+        per, s0 = [], 0
+        for n in cnt:
+            per.append(flat[s0:s0 + n])
+            s0 += n
+        W = (hf.shape[0] * hf.shape[1] + 31) // 32
+        bits.append(torch.from_numpy(mask_inds_to_bits(per, hf.shape[1], W).view(np.int32)))
+    pack = ClipTerrainPack(terrains, bits, "cuda:0")
+    coord = torch.as_tensor(g["grid_coord"]).double()
+    border = ((coord - torch.floor(coord) - 0.5).abs() <= 8 * 1.2e-7 * coord.abs().clamp(min=1.0)).any(dim=-1)
+    n = int(g["num_neg"])
+    for style, tag in ((RelativeZStyle.RELATIVE_TO_ROOT_FLOOR, "relative_to_root_floor"),
+                       (RelativeZStyle.RELATIVE_TO_ROOT, "relative_to_root")):
+        smp = ClipHeightfieldSampler(pack, float(g["dx"]), n, n, n, n, float(g["max_h"]), style)
+        assert torch.equal(smp._generic_heightmap.cpu(), torch.tensor(g["grid"]))
+        hfs, ch, mm = smp.get_hfs_from_data(dev(g["ids"]), dev(g["root_pos"]), dev(g["root_rot"]), dev(g["canon_z"]),
+                                            dev(g["mti"]))
+        e_hfs, e_ch, e_mm = torch.tensor(g[f"hfs_{tag}"]), torch.tensor(g[f"center_h_{tag}"]), torch.tensor(g[f"mm_{tag}"])
+        centre_ok = ch.cpu() == e_ch
+        assert (~centre_ok).sum() <= 1
+        if style == RelativeZStyle.RELATIVE_TO_ROOT_FLOOR:          # a flipped centre cell shifts its whole sample
+            border = border | (~centre_ok).view(-1, 1, 1)
+        bad_h = (hfs.cpu() != e_hfs) & ~border
+        bad_m = (mm.cpu() != e_mm).any(dim=-1) & ~border
+        assert not bad_h.any() and not bad_m.any(), f"{int(bad_h.sum())} heights / {int(bad_m.sum())} bands differ off-border"
+        assert (hfs.cpu() != e_hfs).float().mean() < 2e-3
+        assert (e_mm[..., 0] + (e_ch if style == RelativeZStyle.RELATIVE_TO_ROOT_FLOOR else torch.tensor(g["canon_z"])).view(-1, 1, 1)
+                < 2.0 * float(g["max_h"]) - 1e-3).float().mean() > 0.02           # the masks really select bands
+    two = smp.get_hfs_from_data(dev(g["ids"]), dev(g["root_pos"]), dev(g["root_rot"]), dev(g["canon_z"]), dev(g["mti"]),
+                                want_maxmin=False)
+    assert len(two) == 2 and torch.equal(two[0], hfs)
+    with pytest.raises(IndexError):
+        smp.get_hfs_from_data(torch.tensor([3], device="cuda:0"), dev(g["root_pos"][:1]), dev(g["root_rot"][:1]),
+                              dev(g["canon_z"][:1]), dev(g["mti"][:1]))
+
+
 # ----------------------------------------------------------------------------------------- SDF + losses
 def test_points_hf_sdf_vs_golden():
     from parc_b200.util.terrain_util import points_hf_sdf
@@ -684,6 +736,40 @@ def test_body_loss_vs_oracle_synthetic(gpu_model, O, oracle_model):
     assert float(torch.stack(pens).sum()) > 0 and float(torch.stack(cons).abs().sum()) > 0
     for nm, a, b in zip(("root_pos", "root_exp", "joint_dof"), g_leaves, leaves):
         assert_close_normwise(a.grad, b.grad, what=f"body_loss grad {nm}")
+
+
+@pytest.mark.parametrize("kind", ["box", "stairs"])
+def test_cfg3_shape_loss_and_gradients_vs_oracle(gpu_model, O, oracle_model, kind):
+    """BASELINE configs[2] at its own shape, subsampled in the batch only: B = 8 MDM-style samples x F = 150 frames,
+    each on its own 16 x 16 procedural terrain (boxes / stairs as kin_gen_default.yaml:98-121), contacts in
+    [-0.05, 1], ranking weights 0.1 / 0.1 -- forward values and the gradients of all three leaves against autograd
+    through the oracle (the a15 formulation batched over samples)."""
+    from parc_b200 import ops
+    from parc_b200.tools.procgen.mdm_path import body_points_desc
+    from parc_b200.util import geom_util, synth
+    rng = np.random.default_rng(31 if kind == "box" else 32)
+    B, F = 8, 150
+    hfs = np.stack([synth.box_terrain(rng) if kind == "box" else synth.stairs_terrain(rng) for _ in range(B)])
+    smp = synth.synth_motion_samples(gpu_model, B, F, hfs[0], (0.0, 0.0), (0.4, 0.4), seed=77)
+    pts = body_points_desc(gpu_model, geom_util.get_char_point_samples(gpu_model))
+    tb = ops.make_terrain_batch(torch.tensor(hfs).cuda(), torch.zeros(B, 2).cuda(), (0.4, 0.4), base_z=-10.0)
+    leaves = [torch.tensor(smp[k]).cuda().requires_grad_(True) for k in ("root_pos", "root_exp", "joint_dof")]
+    total, pen, con = ops.body_loss(gpu_model.c_model(), pts, tb, leaves[0], ops.exp_map_to_quat(leaves[1]),
+                                    gpu_model.dof_to_rot(leaves[2]), torch.tensor(smp["contacts"]).cuda(), 0.1, 0.1)
+    total.sum().backward()
+    pens, cons = [], []
+    for i in range(B):
+        cpu = [torch.tensor(smp[k][i]).requires_grad_(True) for k in ("root_pos", "root_exp", "joint_dof")]
+        loss, p_i, c_i = O.motion_opt_pen_contact(oracle_model, cpu[0], cpu[1], cpu[2], torch.tensor(smp["contacts"][i]),
+                                                  torch.tensor(hfs[i]), torch.zeros(2), torch.tensor([0.4, 0.4]), 0.1, 0.1)
+        loss.backward()
+        pens.append(p_i.detach())
+        cons.append(c_i.detach())
+        for a, c, nm in zip(leaves, cpu, ("root_pos", "root exp-map", "joint dofs")):
+            assert_close_normwise(a.grad[i], c.grad, 1e-5, what=f"{kind} sample {i} d/d {nm}")
+    assert_close(pen, torch.stack(pens), rtol=1e-5, atol=1e-6, what=f"{kind} pen")
+    assert_close(con, torch.stack(cons), rtol=1e-5, atol=2e-6, what=f"{kind} contact")
+    assert float(torch.stack(pens).sum()) > 0 and float(torch.stack(cons).abs().sum()) > 0
 
 
 def test_body_loss_linearity_full_size(gpu_model):
@@ -1240,6 +1326,13 @@ def test_full_size_loss_frames_are_independent(gpu_model):
     for a, b in zip(full, part):
         assert torch.equal(a[sub, fr], b)
     assert torch.isfinite(full[0]).all() and (full[0] >= 0).all() and full[0].sum() > 0
+    # a launch of few frames runs the CTA-per-frame form of the kernel (the motion optimiser's regime): same bits
+    sub, fr = slice(700, 704), slice(0, 200)
+    tb3 = ops.make_terrain_batch(hfs[sub].contiguous(), torch.zeros(4, 2).cuda(), (0.4, 0.4), base_z=-10.0)
+    few = ops._body_loss_launch(m, pts, tb3, rp[sub, fr].contiguous(), rq[sub, fr].contiguous(), jr[sub, fr].contiguous(),
+                                ct[sub, fr].contiguous(), 0.1, 0.1, True)
+    for a, b in zip(full, few):
+        assert torch.equal(a[sub, fr], b)
 
 
 def test_full_size_frames_fk_split_and_cross_kernel_consistency(gpu_model):

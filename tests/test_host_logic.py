@@ -408,3 +408,15 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                     str(src), "-L", libdir, "-lparc_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_mask_index_lists_to_bit_rows():
+    """The reference keeps per-frame [n,2] cell lists (util/terrain_util.py:1951-1997); the device wants bit rows."""
+    from parc_b200.diffusion.mdm_heightfield_contact_motion_sampler import mask_inds_to_bits
+    inds = [torch.tensor([[0, 0], [1, 2], [3, 9], [3, 9]]), torch.zeros(0, 2, dtype=torch.long), torch.tensor([[4, 1]])]
+    bits = mask_inds_to_bits(inds, dim_y=10, words=2)
+    assert bits.shape == (3, 2) and bits.dtype == np.uint32
+    want0 = np.zeros(64, dtype=bool)
+    want0[[0, 12, 39]] = True
+    got0 = ((bits[0][:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(-1)
+    assert np.array_equal(got0, want0) and bits[1].sum() == 0 and bits[2][1] == (1 << (41 - 32))

@@ -207,3 +207,36 @@ def test_mdm_hf_collision_loss_and_gradients(oracle_model):
         sdf = O.points_hf_sdf(p, hf, mc, dxdy, base_z=float(g[f"base_z_{tag}"]), inverted=True)
         O.hf_collision_loss(sdf).sum().backward()
         assert torch.equal(sdf, T(g[f"psdf_{tag}"])) and torch.equal(p.grad, T(g[f"pgrad_{tag}"]))
+
+
+def _sampler_case(g):
+    terr, mms, inds = [], [], []
+    for c in range(3):
+        terr.append(O.Terrain(hf=T(g[f"hf{c}"]), min_point=T(g[f"min_point{c}"]), dxdy=T(g[f"dxdy{c}"])))
+        mms.append(T(g[f"maxmin{c}"]))
+        flat, cnt = T(g[f"mask_inds{c}"]), g[f"mask_count{c}"].tolist()
+        per, s0 = [], 0
+        for n in cnt:
+            per.append(flat[s0:s0 + n])
+            s0 += n
+        inds.append(per)
+    return terr, mms, inds
+
+
+def test_mdm_sampler_terrain_gather():
+    """SURVEY 8(f)-4 clause: diffusion/mdm_heightfield_contact_motion_sampler.py:414-474 on three clips with their own
+    terrains (50x50, 102x102, 16x16) and body-cover masks, both relative-z styles."""
+    g = golden("sampler_golden.npz")
+    terr, mms, inds = _sampler_case(g)
+    n = int(g["num_neg"])
+    for tag, rel_root in (("relative_to_root_floor", False), ("relative_to_root", True)):
+        hfs, ch, mm = O.clip_hfs_from_data(terr, mms, inds, T(g["ids"]), T(g["root_pos"]), T(g["root_rot"]), T(g["canon_z"]),
+                                           T(g["mti"]), T(g["grid"]), n, n, float(g["max_h"]), rel_root)
+        # host libm may round the heading's sin / cos differently from the authoring container: compare off-border
+        coord = torch.as_tensor(g["grid_coord"]).double()
+        border = ((coord - torch.floor(coord) - 0.5).abs() <= 8 * 1.2e-7 * coord.abs().clamp(min=1.0)).any(dim=-1)
+        assert torch.equal(hfs[~border], T(g[f"hfs_{tag}"])[~border])
+        assert torch.equal(mm[~border], T(g[f"mm_{tag}"])[~border])
+        assert (ch != T(g[f"center_h_{tag}"])).sum() <= 1
+    lines = open(__import__("os").path.join(__import__("conftest").GOLDEN, "PIN_REPORT_sampler.txt")).read().splitlines()
+    assert len(lines) == 6 and all(l.startswith("OK") for l in lines)
