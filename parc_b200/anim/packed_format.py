@@ -130,7 +130,29 @@ def save(mlib, path: str) -> None:
         arrays[f"terrain{i}.hf_maxmin"] = cpu(t.hf_maxmin)
         t_meta.append({"name": t.terrain_name, "min_point": [float(v) for v in t.min_point.tolist()],
                        "dxdy": [float(v) for v in t.dxdy.tolist()]})
+    # per-clip, per-frame body-cover cell lists (`_hf_mask_inds`, consumed by the MDM sampler,
+    # diffusion/mdm_heightfield_contact_motion_sampler.py:433): ragged -> one [n,2] index array + per-frame counts
+    mask_inds = getattr(mlib, "_hf_mask_inds", None) or []
+    has_masks = []
+    for i, inds in enumerate(mask_inds):
+        if inds is None:
+            has_masks.append(False)
+            continue
+        per = [np.asarray(t.detach().cpu() if isinstance(t, torch.Tensor) else t, dtype=np.int64).reshape(-1, 2) for t in inds]
+        arrays[f"mask{i}.count"] = np.array([p.shape[0] for p in per], dtype=np.int64)
+        arrays[f"mask{i}.inds"] = np.concatenate(per, axis=0) if per else np.zeros((0, 2), np.int64)
+        has_masks.append(True)
+    extras = []
+    for e in (getattr(mlib, "_motion_extras", None) or []):
+        try:
+            json.dumps(e)
+            extras.append(e)
+        except (TypeError, ValueError):
+            import warnings
+            warnings.warn("save_packed: a clip's `extra` field is not JSON-serialisable and is dropped")
+            extras.append(None)
     meta = {
+        "hf_mask_inds": has_masks, "motion_extras": extras,
         "num_clips": int(mlib.num_motions()), "total_frames": int(mlib._packed.total_frames),
         "row_floats": int(lay.row_floats), "num_bodies": int(kcm.get_num_joints()), "dof_size": int(kcm.get_dof_size()),
         "contact_info": bool(mlib._contact_info), "model_fingerprint": model_fingerprint(kcm),
@@ -160,8 +182,16 @@ def load_into(mlib, path: str) -> None:
     rows = up("rows")
     mlib._motion_names = list(meta["motion_names"])
     mlib._motion_files = list(meta["motion_files"])
-    mlib._motion_extras = [None] * meta["num_clips"]
-    mlib._hf_mask_inds = [None] * meta["num_clips"]
+    mlib._motion_extras = list(meta.get("motion_extras") or [None] * meta["num_clips"])
+    mlib._motion_extras += [None] * (meta["num_clips"] - len(mlib._motion_extras))
+    mlib._hf_mask_inds = []
+    has_masks = meta.get("hf_mask_inds") or []
+    for i in range(meta["num_clips"]):
+        if i < len(has_masks) and has_masks[i]:
+            flat = torch.from_numpy(np.array(a[f"mask{i}.inds"])).to(dev)
+            mlib._hf_mask_inds.append(list(torch.split(flat, np.array(a[f"mask{i}.count"]).tolist(), dim=0)))
+        else:
+            mlib._hf_mask_inds.append(None)
     mlib._terrains = []
     for i, tm in enumerate(meta["terrains"]):
         if tm is None:

@@ -1647,13 +1647,18 @@ def test_packed_file_round_trip(golden_lib, gpu_model, tmp_path):
     lib = golden_lib
     t = SubTerrain("t0", 8, 6, 0.4, 0.4, -1.0, 2.0, device="cuda:0")
     t.hf[...] = torch.rand(8, 6, device="cuda")
-    old_terrains = lib._terrains
+    old_terrains, old_masks, old_extras = lib._terrains, lib._hf_mask_inds, lib._motion_extras
     lib._terrains = [t, None, None]
+    # per-frame body-cover cell lists (ragged) and a JSON-able extra travel too
+    masks0 = [torch.tensor([[0, 1], [3, 2]], device="cuda"), torch.zeros(0, 2, dtype=torch.long, device="cuda"),
+              torch.tensor([[7, 5]], device="cuda")]
+    lib._hf_mask_inds = [masks0, None, None]
+    lib._motion_extras = [{"tag": "a", "k": [1, 2]}, None, None]
     path = str(tmp_path / "lib.parcpack")
     try:
         lib.save_packed(path)
     finally:
-        lib._terrains = old_terrains
+        lib._terrains, lib._hf_mask_inds, lib._motion_extras = old_terrains, old_masks, old_extras
     assert os.path.getsize(path) > lib._packed.rows.numel() * 4
     back = MotionLib(path, gpu_model, "cuda:0", init_type="packed_file", contact_info=True)
     assert torch.equal(back._packed.rows, lib._packed.rows) and torch.equal(back._packed.clips, lib._packed.clips)
@@ -1664,6 +1669,9 @@ def test_packed_file_round_trip(golden_lib, gpu_model, tmp_path):
         assert torch.equal(getattr(back, k), getattr(lib, k)), k
     assert back._motion_names == lib._motion_names and back.num_motions() == 3
     assert back._terrains[1] is None and torch.equal(back._terrains[0].hf, t.hf)
+    assert back._hf_mask_inds[1] is None and len(back._hf_mask_inds[0]) == 3
+    assert all(torch.equal(x, y) for x, y in zip(back._hf_mask_inds[0], masks0))
+    assert back._motion_extras == [{"tag": "a", "k": [1, 2]}, None, None]
     assert torch.equal(back._terrains[0].min_point, t.min_point) and torch.equal(back._terrains[0].dxdy, t.dxdy)
     gen = torch.Generator().manual_seed(9)
     ids = torch.randint(0, 3, (777,), generator=gen).cuda()
