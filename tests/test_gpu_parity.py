@@ -815,61 +815,149 @@ def test_frames_fk_matches_three_step_path(gpu_model):
     assert bp3.shape == (2, 127, 15, 3) and torch.equal(bp3.view(254, 15, 3), bp)
 
 
-def test_contact_labelling_vs_golden(gpu_model):
+# Thresholded outputs (contact labels, cell membership) can legitimately differ from the CPU reference only where the
+# decision is numerically borderline.  These helpers compute, with the oracle, how far every decision is from its
+# threshold, so the tests can PROVE each tolerated mismatch is such a case.
+LABEL_TOL = 1e-5        # metres: GPU vs host FK / SDF differ by a few 1e-7
+
+
+def _foot_decision(O, om, frames, terr, feet, eps=0.04):
+    """-> {body: (worst margin [F] = min over the 8 box corners of z - (h + eps); on_border [F])}: the label is
+    `worst margin < 0`; a corner whose xy sits within a few ulp of a cell border may read a neighbouring height."""
+    bp, br = O.frames_fk(om, frames)
+    out = {}
+    for b, half, off in feet:
+        pts = O.box_corners(bp[:, b], br[:, b], torch.tensor(half, dtype=torch.float32), torch.tensor(off, dtype=torch.float32))
+        h = O.hf_sample(terr, pts[..., 0:2])
+        coord = O.grid_coord(terr, pts[..., 0:2])
+        out[b] = ((pts[..., 2] - (h + eps)).min(dim=-1)[0], _border_mask(coord.reshape(-1, 2), ulps=16).view(-1, 8).any(dim=-1))
+    return out
+
+
+def _hand_decision(O, om, frames, terr, hands, eps=0.04):
+    bp, _ = O.frames_fk(om, frames)
+    base_z = torch.min(terr.hf).item() - 10.0
+    out = {}
+    for b, radius in hands:
+        sd = O.points_hf_sdf(bp[:, b].unsqueeze(0), terr.hf.unsqueeze(0), terr.min_point.unsqueeze(0), terr.dxdy, base_z, False)
+        out[b] = sd[0] - radius - eps              # label = margin < 0
+    return out
+
+
+def _assert_label_mismatches_are_borderline(got, exp, foot_dec, hand_dec, what):
+    """Every (frame, body) where the labels differ must have its decision within LABEL_TOL of the threshold (or a foot
+    corner on a cell border); returns the number of such justified mismatches."""
+    diff = (got != exp).nonzero().tolist()
+    for f, b in diff:
+        if b in foot_dec:
+            margin, border = foot_dec[b]
+            assert abs(float(margin[f])) <= LABEL_TOL or bool(border[f]), \
+                f"{what}: foot label of frame {f} body {b} differs although its margin is {float(margin[f]):.3e}"
+        elif b in hand_dec:
+            assert abs(float(hand_dec[b][f])) <= LABEL_TOL, \
+                f"{what}: hand label of frame {f} body {b} differs although its margin is {float(hand_dec[b][f]):.3e}"
+        else:
+            raise AssertionError(f"{what}: label of a body that is neither foot nor hand differs (frame {f} body {b})")
+    return len(diff)
+
+
+def _uncertain_cells(O, om, frames, terr):
+    """bool [F, X, Y]: cells a surface point within 16 ulp of a cell border could be attributed to (the 3 x 3 block
+    around the cell the oracle put it in)."""
+    bp, br = O.frames_fk(om, frames)
+    X, Y = terr.hf.shape
+    out = torch.zeros(frames.shape[0], X, Y, dtype=torch.bool)
+    for f in range(frames.shape[0]):
+        pts = torch.cat([O.quat_rotate(br[f, b].unsqueeze(0), om.body_points[b]) + bp[f, b] for b in range(om.num_bodies)], dim=0)
+        near = _border_mask(O.grid_coord(terr, pts[:, 0:2]), ulps=16)
+        g = O.grid_index(terr, pts[near][:, 0:2])
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                out[f, (g[:, 0] + dx).clamp(0, X - 1), (g[:, 1] + dy).clamp(0, Y - 1)] = True
+    return out
+
+
+def _golden_feet_hands(g):
+    feet = [(int(b), h.tolist(), o.tolist()) for b, h, o in zip(g["feet_body"], g["feet_half"], g["feet_offset"])]
+    hands = [(int(b), float(r)) for b, r in zip(g["hands_body"], g["hands_radius"])]
+    return feet, hands
+
+
+def test_contact_labelling_vs_golden(gpu_model, O, oracle_model):
     from parc_b200.zmotion_editing_tools.motion_edit_lib import (compute_hf_foot_contacts_and_correct_pen,
                                                                  compute_motion_terrain_hand_contacts)
     g = golden("label_golden.npz")
     t = _civ_terrain()
+    ot = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
+    feet, hands = _golden_feet_hands(g)
     frames = dev(g["frames"])
     upd, fc = compute_hf_foot_contacts_and_correct_pen(frames, t, gpu_model)
     assert fc.shape == (64, 15)
-    assert (fc.cpu() != torch.tensor(g["foot_contacts"])).sum() <= 1        # thresholded; 1 borderline frame allowed
+    # labels are exact except where the thresholded quantity sits on its threshold -- proven per mismatch
+    foot_dec = _foot_decision(O, oracle_model, torch.tensor(g["frames"]), ot, feet)
+    n = _assert_label_mismatches_are_borderline(fc.cpu(), torch.tensor(g["foot_contacts"]), foot_dec, {}, "feet")
+    assert n <= 2
     assert fc[:, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13]].abs().sum() == 0
     assert_close(upd[:, 2], g["updated_z"], atol=2e-6, what="penetration-corrected root z")
     assert torch.equal(upd[:, :2], frames[:, :2]) and torch.equal(upd[:, 3:], frames[:, 3:])
     hc = compute_motion_terrain_hand_contacts(frames, t, gpu_model)
-    assert (hc.cpu() != torch.tensor(g["hand_contacts"])).sum() <= 1
+    hand_dec = _hand_decision(O, oracle_model, torch.tensor(g["frames"]), ot, hands)
+    assert _assert_label_mismatches_are_borderline(hc.cpu(), torch.tensor(g["hand_contacts"]), {}, hand_dec, "hands") <= 2
     t.hf = t.hf + float(g["raised_by"])
+    ot2 = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
     hc2 = compute_motion_terrain_hand_contacts(frames, t, gpu_model)
-    assert (hc2.cpu() != torch.tensor(g["hand_contacts_raised"])).sum() <= 1
+    hand_dec2 = _hand_decision(O, oracle_model, torch.tensor(g["frames"]), ot2, hands)
+    assert _assert_label_mismatches_are_borderline(hc2.cpu(), torch.tensor(g["hand_contacts_raised"]), {}, hand_dec2,
+                                                   "hands, raised terrain") <= 2
     assert hc2.sum() > 10
 
 
-def test_hf_mask_inds_vs_golden(gpu_model):
+def test_hf_mask_inds_vs_golden(gpu_model, O, oracle_model):
     from parc_b200.util import geom_util
     from parc_b200.util.terrain_util import compute_hf_extra_vals, compute_hf_mask_from_inds, compute_hf_mask_inds
     g = golden("label_golden.npz")
     t = _civ_terrain()
+    ot = O.Terrain(hf=t.hf.cpu(), min_point=t.min_point.cpu(), dxdy=t.dxdy.cpu())
     frames = dev(g["frames"][:24])
     pts = geom_util.get_char_point_samples(gpu_model)
     inds, minh = compute_hf_mask_inds(frames, t, gpu_model, pts)
     assert len(inds) == 24 and all(i.dtype == torch.int64 and i.shape[1] == 2 for i in inds)
-    # cell membership is exact except for surface points within an ulp of a cell border
+    # cell membership is exact except for surface points within a few ulp of a cell border: every differing cell of
+    # every frame must be one such a point could be attributed to
+    unc = _uncertain_cells(O, oracle_model, torch.tensor(g["frames"][:24]), ot)
     exp_counts = g["mask_counts"].tolist()
-    got = torch.cat(inds).cpu()
-    if [i.shape[0] for i in inds] == exp_counts:
-        assert (got != torch.tensor(g["mask_inds"])).any(dim=1).float().mean() < 0.01
-    else:
-        assert sum(abs(a.shape[0] - b) for a, b in zip(inds, exp_counts)) <= 3
+    exp_flat, s0 = torch.tensor(g["mask_inds"]), 0
+    for f, n in enumerate(exp_counts):
+        exp_m = torch.zeros(50, 50, dtype=torch.bool)
+        e = exp_flat[s0:s0 + n]
+        exp_m[e[:, 0], e[:, 1]] = True
+        got_m = torch.zeros(50, 50, dtype=torch.bool)
+        got_m[inds[f][:, 0].cpu(), inds[f][:, 1].cpu()] = True
+        assert not ((got_m != exp_m) & ~unc[f]).any(), f"frame {f}: a cell differs that no border point explains"
+        s0 += n
+    assert sum(abs(a.shape[0] - b) for a, b in zip(inds, exp_counts)) <= 3
     mask = compute_hf_mask_from_inds(t, inds).cpu()
-    assert (mask != torch.tensor(g["hf_mask"])).sum() <= 2
+    anyf = unc.any(dim=0)
+    assert not ((mask != torch.tensor(g["hf_mask"])) & ~anyf).any() and (mask != torch.tensor(g["hf_mask"])).sum() <= 2
     exp_minh = torch.tensor(g["min_body_heights"])
     same = (minh.cpu() - exp_minh).abs() <= 1e-5 * exp_minh.abs().clamp(min=1.0)
-    assert (~same).sum() <= 2
+    assert not (~same & ~anyf).any() and (~same).sum() <= 2
     compute_hf_extra_vals(frames, t, gpu_model, pts)
-    assert (t.hf_mask.cpu() != torch.tensor(g["extra_hf_mask"])).sum() <= 2
-    mm = (t.hf_maxmin.cpu() - torch.tensor(g["extra_hf_maxmin"])).abs() > 1e-4
-    assert mm.sum() <= 4
+    assert not ((t.hf_mask.cpu() != torch.tensor(g["extra_hf_mask"])) & ~anyf).any()
+    mm = ((t.hf_maxmin.cpu() - torch.tensor(g["extra_hf_maxmin"])).abs() > 1e-4).any(dim=-1)
+    assert not (mm & ~anyf).any() and mm.sum() <= 4
 
 
-def test_label_clips_batched_vs_oracle(gpu_model, O, oracle_model):
-    """Config-5-shaped: a batch of clips, one 16x16 terrain per clip, feet + hands + body hf in one launch."""
+@pytest.mark.parametrize("B,F", [(5, 40), (32, 265)])
+def test_label_clips_batched_vs_oracle(gpu_model, O, oracle_model, B, F):
+    """Config-5-shaped: a batch of clips, one 16x16 terrain per clip, feet + hands + body hf + masks in one launch;
+    (32, 265) is a subsample of BASELINE configs[4] at its own clip length.  Labels / cell memberships are exact
+    except where the oracle's decision margin shows the case is borderline."""
     from parc_b200 import ops
     from parc_b200.util import geom_util, synth
     from parc_b200.zmotion_editing_tools.motion_edit_lib import label_clips
     g = golden("label_golden.npz")
     rng = np.random.default_rng(8)
-    B, F = 5, 40
     hfs = np.stack([synth.box_terrain(rng, h_range=(-0.4, 0.7)) if i % 2 else synth.stairs_terrain(rng) for i in range(B)])
     fr = np.concatenate([synth.synth_clips(gpu_model, 1, seed=50 + i, num_frames=F, hf=hfs[i])[0] for i in range(B)])
     fr[..., 2] -= 0.02
@@ -877,30 +965,39 @@ def test_label_clips_batched_vs_oracle(gpu_model, O, oracle_model):
                                 base_z=(torch.tensor(hfs).amin(dim=(1, 2)) - 10.0).cuda())
     pts = geom_util.get_char_point_samples(gpu_model)
     out = label_clips(torch.tensor(fr).cuda(), tb, gpu_model, body_points=pts, want_masks=True, want_fk=True)
-    feet = [(int(b), h.tolist(), o.tolist()) for b, h, o in zip(g["feet_body"], g["feet_half"], g["feet_offset"])]
-    hands = [(int(b), float(r)) for b, r in zip(g["hands_body"], g["hands_radius"])]
+    feet, hands = _golden_feet_hands(g)
     bad = 0
+    mask_clips = range(B) if B <= 8 else range(0, B, 8)            # the oracle's mask restatement loops over frames
     for i in range(B):
         t = O.Terrain(hf=torch.tensor(hfs[i]), min_point=torch.zeros(2), dxdy=torch.tensor([0.4, 0.4]))
         f_i = torch.tensor(fr[i])
         _, fc, corr = O.foot_contacts_and_pen(oracle_model, f_i, t, feet)
         hc = O.hand_contacts(oracle_model, f_i, t, hands)
-        exp = fc + hc
-        bad += int((out["contacts"][i].cpu() != exp).sum())
-        assert_close(out["pen_correction"][i], corr, atol=2e-6, what=f"pen_correction clip {i}")
+        got = out["contacts"][i].cpu()
+        if (got != fc + hc).any():
+            bad += _assert_label_mismatches_are_borderline(got, fc + hc, _foot_decision(O, oracle_model, f_i, t, feet),
+                                                           _hand_decision(O, oracle_model, f_i, t, hands), f"clip {i}")
+        # the correction is a min over corners of z - h: a corner on a cell border may read the neighbouring height
+        dec = _foot_decision(O, oracle_model, f_i, t, feet)
+        on_border = torch.stack([d[1] for d in dec.values()]).any(dim=0)
+        pc = out["pen_correction"][i].cpu()
+        assert ((pc - corr).abs() <= 2e-6)[~on_border].all(), f"pen_correction clip {i}"
         bp, _ = O.frames_fk(oracle_model, f_i)
         assert_close(out["body_pos"][i], bp, what="label body_pos")
         bhf = O.hf_sample(t, bp[..., 0:2])
-        assert (out["body_hf"][i].cpu() != bhf).float().mean() < 0.01
-        inds, minh = O.hf_mask_inds(oracle_model, f_i, t)
-        masks = ops.unpack_frame_masks(out["frame_mask_bits"][i], 16, 16).cpu()
-        exp_m = torch.zeros(F, 16, 16, dtype=torch.bool)
-        for f, ind in enumerate(inds):
-            exp_m[f, ind[:, 0], ind[:, 1]] = True
-        assert (masks != exp_m).float().mean() < 1e-3
-        same = (out["min_body_heights"][i].cpu() - minh).abs() <= 1e-5 * minh.abs().clamp(min=1.0)
-        assert (~same).sum() <= 2
-    assert bad <= 3, f"{bad} contact labels differ"
+        origin_border = _border_mask(O.grid_coord(t, bp[..., 0:2]).reshape(-1, 2), ulps=16).view(F, -1)
+        assert not ((out["body_hf"][i].cpu() != bhf) & ~origin_border).any()
+        if i in mask_clips:
+            inds, minh = O.hf_mask_inds(oracle_model, f_i, t)
+            unc = _uncertain_cells(O, oracle_model, f_i, t)
+            masks = ops.unpack_frame_masks(out["frame_mask_bits"][i], 16, 16).cpu()
+            exp_m = torch.zeros(F, 16, 16, dtype=torch.bool)
+            for f, ind in enumerate(inds):
+                exp_m[f, ind[:, 0], ind[:, 1]] = True
+            assert not ((masks != exp_m) & ~unc).any(), f"clip {i}: a mask cell differs that no border point explains"
+            same = (out["min_body_heights"][i].cpu() - minh).abs() <= 1e-5 * minh.abs().clamp(min=1.0)
+            assert not (~same & ~unc.any(dim=0)).any()
+    assert bad <= max(3, B * F // 1000), f"{bad} borderline contact labels"
     assert out["contacts"].sum() > 0
 
 
