@@ -667,6 +667,7 @@ def leg_cfg4(ctx):
     piped = dist_max(ctx, p0.elapsed_time(p1) / K4)
     gather_bytes = CFG4_ENVS * (BODIES * 3 + RAY_POINTS) * 4
     kern, gath, both = dist_max(ctx, kern), dist_max(ctx, gath), dist_max(ctx, both)
+    peer = leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms)
     res.update({"n1_ms_per_step": n1_ms, "efficiency": n1_ms / (ctx.world * shard_ms),
                 "speedup_vs_1gpu": n1_ms / shard_ms,
                 "gather": {"what": "all_gather_into_tensor of body_pos + obs shards (NCCL), every rank receives the full batch",
@@ -675,7 +676,107 @@ def leg_cfg4(ctx):
                 "value_with_gather": CFG4_ENVS * BODIES / (both * 1e-3),
                 "efficiency_with_gather": n1_ms / (ctx.world * both),
                 "pipelined_ms_per_step": piped, "value_pipelined": CFG4_ENVS * BODIES / (piped * 1e-3),
-                "pipelined": "two output sets: step s's gather (NCCL stream) overlaps step s+1's kernel"})
+                "pipelined": "two output sets: step s's gather (NCCL stream) overlaps step s+1's kernel",
+                "peer_gather": peer})
+    return res
+
+
+def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms):
+    """The same exchange with the library's own kernels over NVLink peer memory (csrc/peer_gather.cu) instead of NCCL.
+    push: query -> parc_peer_push (16-byte multicast stores of the L2-resident shard + in-kernel hand-shake).
+    direct: the query kernel's body_pos / obs stores go straight to the multicast address, then parc_peer_barrier.
+    Two symmetric buffer sets alternate, as a consumer of step s may still read while step s + 1 arrives."""
+    from parc_b200 import sharding
+    dev = ctx.dev
+    stream = torch.cuda.current_stream(dev)
+    try:
+        pgs = [sharding.PeerGather({"body_pos": (BODIES, 3), "obs": (RAY_POINTS,)}, CFG4_ENVS, dev) for _ in range(2)]
+    except Exception as e:
+        return {"unavailable": repr(e)[:300]}
+    res = {"multicast": bool(pgs[0].multicast), "bytes_total": gather_bytes}
+    outs = [{}, {}]
+    plans = [make_plans(ctx, ids_d, times_d, outs[i]) for i in range(2)]
+
+    def timed(step_fn, label, finish=None):
+        for s in range(4):
+            step_fn(s)
+        if finish:
+            finish()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(ctx)
+        e0.record(stream)
+        for s in range(K4):
+            step_fn(s)
+        if finish:
+            finish()
+        e1.record(stream)
+        barrier(ctx)
+        ctx.launches += 2 * (K4 + 4)
+        ms = dist_max(ctx, e0.elapsed_time(e1) / K4)
+        res[label + "_ms_per_step"] = ms
+        res[label + "_value"] = CFG4_ENVS * BODIES / (ms * 1e-3)
+        res[label + "_algbw_GBps"] = gather_bytes / (ms * 1e-3) / 1e9
+        res[label + "_efficiency"] = n1_ms / (ctx.world * ms)
+
+    def push_step(s):
+        i = s % 2
+        plans[i][s % NB].launch()
+        pgs[i].push({"body_pos": outs[i]["body_pos"], "obs": outs[i]["obs"]})
+
+    timed(push_step, "push")
+    # the push alone (shards already computed)
+    def push_only(s):
+        pgs[s % 2].push({"body_pos": outs[s % 2]["body_pos"], "obs": outs[s % 2]["obs"]})
+    timed(push_only, "push_only")
+
+    # pipelined: the push of step s runs on a side stream next to the query of step s + 1; a set's shard buffers are
+    # rewritten only after the push that read them (two steps earlier) has finished
+    side = torch.cuda.Stream(dev)
+    q_done = [torch.cuda.Event(), torch.cuda.Event()]
+    p_done = [torch.cuda.Event(), torch.cuda.Event()]
+    started = [False, False]
+
+    def piped_step(s):
+        i = s % 2
+        if started[i]:
+            stream.wait_event(p_done[i])
+        plans[i][s % NB].launch()
+        q_done[i].record(stream)
+        side.wait_event(q_done[i])
+        pgs[i].push({"body_pos": outs[i]["body_pos"], "obs": outs[i]["obs"]}, stream=side.cuda_stream)
+        p_done[i].record(side)
+        started[i] = True
+
+    timed(piped_step, "push_pipelined", finish=lambda: stream.wait_stream(side))
+    # the same push through plain peer pointers (one store per peer, no switch replication, no loop-back of own rows)
+    try:
+        pgu = [sharding.PeerGather({"body_pos": (BODIES, 3), "obs": (RAY_POINTS,)}, CFG4_ENVS, dev, use_multicast=False)
+               for _ in range(2)]
+
+        def push_p2p(s):
+            pgu[s % 2].push({"body_pos": outs[s % 2]["body_pos"], "obs": outs[s % 2]["obs"]})
+        timed(push_p2p, "push_only_peer_pointers")
+        del pgu
+    except Exception as e:
+        res["push_only_peer_pointers"] = repr(e)[:200]
+    ok = torch.equal(pgs[0].out["obs"][pgs[0].lo:pgs[0].hi], outs[0]["obs"])
+    if pgs[0].multicast:
+        dplans = [make_plans(ctx, ids_d, times_d, {}) for _ in range(2)]
+        for i in range(2):
+            for pl in dplans[i]:
+                pl.redirect_output("body_pos", pgs[i].direct_ptr("body_pos"))
+                pl.redirect_output("obs", pgs[i].direct_ptr("obs"))
+
+        def direct_step(s):
+            i = s % 2
+            dplans[i][s % NB].launch()
+            pgs[i].barrier()
+
+        timed(direct_step, "direct")
+    res["local_rows_intact"] = bool(ok)
+    res["what"] = ("query + gather of body_pos / obs over NVLink peer memory with the library's own kernels; "
+                   "push = 16-byte stores of the shard to the NVSwitch multicast address (or to each peer) + in-kernel "
+                   "release/acquire hand-shake; direct = the query kernel itself stores to the multicast address")
     return res
 
 
@@ -771,6 +872,19 @@ def leg_selfcheck(ctx):
     lo, hi = sharding.shard_bounds(n, ctx.rank, ctx.world)
     plan = sharding.AllGatherPlan(sq._out["obs"], n)
     same = same and torch.equal(plan.run(), full["obs"])
+    peer = None
+    if ctx.world > 1:
+        # the library's own NVLink gather (csrc/peer_gather.cu) must produce the same bits as NCCL and one GPU
+        try:
+            J, P = int(full["body_pos"].shape[1]), int(full["obs"].shape[1])
+            pg = sharding.PeerGather({"body_pos": (J, 3), "obs": (P,)}, n, dev)
+            pg.push({"body_pos": sq._out["body_pos"], "obs": sq._out["obs"]})
+            torch.cuda.synchronize(dev)
+            ok = torch.equal(pg.out["body_pos"], full["body_pos"]) and torch.equal(pg.out["obs"], full["obs"])
+            peer = {"equal": bool(ok), "multicast": bool(pg.multicast)}
+            same = same and ok
+        except Exception as e:                           # no symmetric memory on this box: reported, not hidden
+            peer = {"unavailable": repr(e)[:200]}
     st = sharding.reduce_loss_stats({"z": full["root_pos"][lo:hi, 2]})
     ref = full["root_pos"][:, 2].double()
     ok_stats = (st["z"]["count"] == n and abs(st["z"]["sum"] - ref.sum().item()) <= 1e-9 * n
@@ -779,7 +893,8 @@ def leg_selfcheck(ctx):
     if ctx.world > 1:
         ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
     return {"sharded_gather_equals_single_gpu": bool(flag.item() == 1.0), "ranks": ctx.world, "queries": n,
-            "collectives": "all_gather_into_tensor (ragged + fixed-buffer forms), all_reduce sum/min/max"}
+            "collectives": "all_gather_into_tensor (ragged + fixed-buffer forms), all_reduce sum/min/max",
+            "peer_gather": peer}
 
 
 def main():

@@ -689,6 +689,46 @@ int parc_build_tables(const float* frames, int64_t total_frames, int32_t frame_s
                       const float* clip_fps, const float* clip_dof_vel_dt, int64_t num_clips,
                       const ParcCharModel* model, float* rows_out, void* stream);
 
+/* ---- multi-GPU: gathering the shards of a sharded query over NVLink / NVSwitch peer memory ------------
+ * The reference is single-GPU; this has no counterpart in it.  BASELINE config 4 splits 65 536 envs contiguously over
+ * the GPUs of a box; when a consumer wants the full `body_pos` / `obs` batch on every GPU, the shards are exchanged
+ * through SYMMETRIC memory (the same allocation on every GPU, peer-mapped into every process, optionally behind an
+ * NVSwitch multicast address).  The library does not allocate or map that memory: the caller does (the Python side
+ * uses torch.distributed._symmetric_memory) and passes plain addresses.
+ *
+ * Signals: `num_slots` uint64 counters at the same offset of every rank's symmetric buffer, zero-initialised, plus a
+ * rank-private `epoch[num_slots]` (ordinary device memory, zero-initialised).  A hand-shake on slot s adds 1 to slot s
+ * on every rank (release) and waits until the local copy reaches world * (epoch[s] + 1) (acquire), then bumps
+ * epoch[s]; the launch is therefore replayable from a CUDA graph. */
+#define PARC_MAX_PEERS 16
+#define PARC_MAX_PUSH_SEGMENTS 4
+
+typedef struct ParcPeerSignals {
+  uint64_t* multicast_signal;              /* multicast address of the slots, or NULL (then peer_signal is used) */
+  uint64_t* peer_signal[PARC_MAX_PEERS];   /* rank r's slots as mapped into THIS process (r < world; incl. own) */
+  uint64_t* local_signal;                  /* this rank's slots */
+  uint64_t* epoch;                         /* [num_slots] rank-private launch counters */
+  int32_t world;
+  int32_t num_slots;
+} ParcPeerSignals;
+
+typedef struct ParcPeerSegment {
+  const void* src;                         /* this rank's shard (local memory) */
+  void* dst_multicast;                     /* multicast address of the shard's place in the gathered tensor, or NULL */
+  void* dst_peer[PARC_MAX_PEERS];          /* the same place in rank r's buffer (used when dst_multicast is NULL) */
+  int64_t bytes;                           /* multiple of 4; 16-byte vectors are used when everything is 16-aligned */
+} ParcPeerSegment;
+
+/* All ranks call it on their stream after the kernels that stored into peer / multicast addresses: returns (on the
+ * stream) once every rank has arrived, with the ranks' earlier stores visible.  One 32-thread block. */
+int parc_peer_barrier(const ParcPeerSignals* signals, int32_t slot, void* stream);
+
+/* Copies up to PARC_MAX_PUSH_SEGMENTS local shards into every rank's gathered tensors (one multicast store per 16
+ * bytes, or one store per peer without multicast) and performs the hand-shake per block (slots 0..num_blocks-1;
+ * num_blocks <= 0 selects 64): when the kernel has finished on a rank, every rank's shards have arrived there. */
+int parc_peer_push(const ParcPeerSegment* segments, int32_t num_segments, const ParcPeerSignals* signals,
+                   int32_t num_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

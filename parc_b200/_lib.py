@@ -183,6 +183,19 @@ class ParcSimStep(C.Structure):
                 ("obs_stride", C.c_int64)]
 
 
+PARC_MAX_PEERS, PARC_MAX_PUSH_SEGMENTS = 16, 4
+
+
+class ParcPeerSignals(C.Structure):
+    _fields_ = [("multicast_signal", C.c_void_p), ("peer_signal", C.c_void_p * PARC_MAX_PEERS),
+                ("local_signal", C.c_void_p), ("epoch", C.c_void_p), ("world", C.c_int32), ("num_slots", C.c_int32)]
+
+
+class ParcPeerSegment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_multicast", C.c_void_p), ("dst_peer", C.c_void_p * PARC_MAX_PEERS),
+                ("bytes", C.c_int64)]
+
+
 PARC_DONE_NULL, PARC_DONE_FAIL, PARC_DONE_SUCC, PARC_DONE_TIME = 0, 1, 2, 3
 
 # name -> (restype, argtypes); every symbol include/parc_b200.h declares
@@ -234,6 +247,8 @@ SIGNATURES = {
     "parc_deepmimic_reward": (C.c_int, [_P(ParcCharState), _P(ParcCharState), _I64, _I32, _I32, _I32, _V, _V, _I32,
                                         _I32, _V, _V]),
     "parc_sim_step": (C.c_int, [_P(ParcSimStep), _I64, _P(ParcCharModel), _V]),
+    "parc_peer_barrier": (C.c_int, [_P(ParcPeerSignals), _I32, _V]),
+    "parc_peer_push": (C.c_int, [_P(ParcPeerSegment), _I32, _P(ParcPeerSignals), _I32, _V]),
     "parc_done": (C.c_int, [_P(ParcDoneSpec), _V, _V, _V, _V, _V, _V, _V, _P(ParcHeightfield), _V, _I32, _I32, _I64,
                             _I32, _V, _V, _V]),
 }

@@ -79,6 +79,7 @@ struct LabelParams {
   float* body_rot;              // [B,F,J,4]
   int frames_per_cta;
   int mask_words;
+  int minh_in_smem;             // 1: per-cell minimum body heights are combined in shared memory, flushed once per CTA
 };
 
 __global__ void __launch_bounds__(LABEL_THREADS)
@@ -99,12 +100,15 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
   float* slab = s_lp + (size_t)S * 3 + (size_t)warp * (PARC_MAX_BODIES * 8 + p.mask_words);
   float* s_bt = slab;                                                          // [J][8] pos(3) rot(4)
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(slab + PARC_MAX_BODIES * 8);  // [mask_words]
+  // [X*Y] per-cell minimum of the surface-point heights over this CTA's frames (after the warps' slabs)
+  float* s_minh = s_lp + (size_t)S * 3 + (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words);
+  const bool minh_smem = p.min_body_heights && p.minh_in_smem;
 
   const int64_t b = blockIdx.y;
   stage_model(&sm, model_param);
   stage_terrain(p.terrain, b, s_hf, s_cx, s_cy, s_minmax);
   __syncthreads();
-  const float hf_min = s_minmax[0], hf_max = s_minmax[1];
+  const float hf_max = s_minmax[1];            // bounds the solid columns from above (hand SDF pruning)
   const int J = sm.num_bodies;
   if (want_masks) {
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
@@ -112,11 +116,16 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
       for (int k = s0; k < s1; ++k) s_body[k] = j;
     }
     for (int i = threadIdx.x; i < S * 3; i += blockDim.x) s_lp[i] = __ldg(p.pts.points + i);
+    if (minh_smem)
+      for (int i = threadIdx.x; i < X * Y; i += blockDim.x) s_minh[i] = INFINITY;
   }
   const float* mc = p.terrain.min_center + b * p.terrain.min_center_stride;
   const float min_x = __ldg(mc), min_y = __ldg(mc + 1);
   const float dx = p.terrain.half_dx * 2.0f, dy = p.terrain.half_dy * 2.0f;   // exact: halves of fp32 values
+  // hoisted-reciprocal cell index: index-identical to the reference's true division (parc_selftest_grid_index)
+  const GridAxis gax = make_grid_axis(min_x, dx, X), gay = make_grid_axis(min_y, dy, Y);
   const float base = sample_base_z(p.terrain, b);
+  const TileSpacing spacing = tile_spacing(s_cx, s_cy, X, Y);
   const LaneBody lb = load_lane_body(sm, lane, 0);
   const int max_depth = sm.max_depth;
   __syncthreads();
@@ -136,8 +145,7 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
       if (p.body_pos) { float* o = p.body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
       if (p.body_rot) reinterpret_cast<float4*>(p.body_rot)[q * J + lane] = rot;
       if (p.body_hf) {
-        const int ix = grid_index_1d(pos.x, min_x, dx, X), iy = grid_index_1d(pos.y, min_y, dy, Y);
-        p.body_hf[q * J + lane] = s_hf[ix * Y + iy];
+        p.body_hf[q * J + lane] = s_hf[grid_index_fast(pos.x, gax) * Y + grid_index_fast(pos.y, gay)];
       }
     }
     if (want_masks && p.frame_mask)
@@ -156,7 +164,7 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
         c.x += p.keys.foot_offset[foot][0]; c.y += p.keys.foot_offset[foot][1]; c.z += p.keys.foot_offset[foot][2];
         const float3 r = quat_rotate(make_float4(t[3], t[4], t[5], t[6]), c);
         const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
-        const float h = s_hf[grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y)];
+        const float h = s_hf[grid_index_fast(wp.x, gax) * Y + grid_index_fast(wp.y, gay)];
         touch = wp.z < add_rn(h, p.contact_eps);            // box_points_z < cell_heights + contact_eps
         pen = sub_rn(wp.z, h);
       }
@@ -167,13 +175,14 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
       float corr = fminf(pen, 0.0f);
       corr = fminf(corr, __shfl_xor_sync(PARC_FULL_MASK, corr, 8));
       corr = fminf(corr, __shfl_xor_sync(PARC_FULL_MASK, corr, 16));
-      // ---- hands: lane = hand, exact min over cells of the solid rounded-box SDF at the body origin ----
+      // ---- hands: exact min over cells of the solid rounded-box SDF at the body origin; the cells within reach are
+      // split over the warp's lanes (one hand after the other), lane h keeps hand h's value ----
       float hand_sd = INFINITY;
-      if (lane < p.keys.num_hands) {
-        const float* t = s_bt + p.keys.hand_body[lane] * 8;
-        const SdfBest best = scan_cells<false, true>(s_hf, s_cx, s_cy, X, Y, p.terrain.half_dx, p.terrain.half_dy, base,
-                                                     hf_min, hf_max, make_float3(t[0], t[1], t[2]));
-        hand_sd = best.sol - p.keys.hand_radius[lane];      // sdRoundBox = sdBox - r (geom_util.py:113-120)
+      for (int h = 0; h < p.keys.num_hands; ++h) {
+        const float* t = s_bt + p.keys.hand_body[h] * 8;
+        const float sol = warp_min_solid_sdf(s_hf, s_cx, s_cy, X, Y, p.terrain.half_dx, p.terrain.half_dy, base, hf_max,
+                                             spacing, make_float3(t[0], t[1], t[2]), lane);
+        if (lane == h) hand_sd = sol - p.keys.hand_radius[h];   // sdRoundBox = sdBox - r (geom_util.py:113-120)
       }
       // ---- contact row: zeros, then feet / hands ----
       float* crow = p.contacts + q * J;
@@ -192,15 +201,25 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
         const float3 lp = make_float3(s_lp[k * 3], s_lp[k * 3 + 1], s_lp[k * 3 + 2]);
         const float3 r = quat_rotate(make_float4(t[3], t[4], t[5], t[6]), lp);
         const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
-        const int cell = grid_index_1d(wp.x, min_x, dx, X) * Y + grid_index_1d(wp.y, min_y, dy, Y);
+        const int cell = grid_index_fast(wp.x, gax) * Y + grid_index_fast(wp.y, gay);
         if (p.frame_mask) atomicOr(&s_mask[cell >> 5], 1u << (cell & 31));
-        if (p.min_body_heights) atomic_min_float(p.min_body_heights + b * (int64_t)X * Y + cell, wp.z);
+        if (minh_smem) atomic_min_float(s_minh + cell, wp.z);
+        else if (p.min_body_heights) atomic_min_float(p.min_body_heights + b * (int64_t)X * Y + cell, wp.z);
       }
       __syncwarp();
       if (p.frame_mask)
         for (int i = lane; i < p.mask_words; i += 32) p.frame_mask[q * p.mask_words + i] = s_mask[i];
     }
     __syncwarp();
+  }
+  if (minh_smem) {
+    // one global atomic per touched cell and CTA instead of one per surface point and frame
+    __syncthreads();
+    float* g = p.min_body_heights + b * (int64_t)X * Y;
+    for (int i = threadIdx.x; i < X * Y; i += blockDim.x) {
+      const float v = s_minh[i];
+      if (v < INFINITY) atomic_min_float(g + i, v);
+    }
   }
 }
 
@@ -269,9 +288,12 @@ extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frame
   p.mask_words = (cells + 31) / 32;
   const size_t S = (frame_mask_out || min_body_heights) ? (size_t)pts->num_points : 0;
   p.pts.num_points = (int)S;
-  const size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + S * 4 +
-                       (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words)) * 4;
+  size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + S * 4 +
+                 (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words)) * 4;
   if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;       // per-clip labelling terrains are small tiles (<= ~190 x 190)
+  // the per-cell minima are combined in shared memory when a second tile-sized array still fits
+  p.minh_in_smem = (min_body_heights && smem + (size_t)cells * 4 <= PARC_SMEM_LIMIT) ? 1 : 0;
+  if (p.minh_in_smem) smem += (size_t)cells * 4;
   static SmemOptIn opt;
   rc = ensure_dynamic_smem(clip_label_kernel, opt, smem);
   if (rc) return rc;

@@ -119,6 +119,71 @@ __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, cons
   return b;
 }
 
+// Inverse cell spacing of a tile whose centre coordinates are staged in cx / cy (evenly spaced torch.linspace nodes):
+// the same expressions scan_cells evaluates per call, hoisted for callers that scan many points of one tile.
+struct TileSpacing {
+  float isx, isy;
+};
+__device__ __forceinline__ TileSpacing tile_spacing(const float* __restrict__ cx, const float* __restrict__ cy, int X,
+                                                    int Y) {
+  const float sx = X > 1 ? (cx[X - 1] - cx[0]) / (float)(X - 1) : 1.0f;
+  const float sy = Y > 1 ? (cy[Y - 1] - cy[0]) / (float)(Y - 1) : 1.0f;
+  TileSpacing t;
+  t.isx = 1.0f / sx; t.isy = 1.0f / sy;
+  return t;
+}
+
+// Warp-cooperative form of scan_cells for the SOLID columns, value only (the labelling kernel thresholds it): every
+// lane evaluates the seed cell, the index window that is a superset of all cells within reach of the seed's value is
+// split over the 32 lanes, and the lanes' minima are combined.  The minimum of a set of floats does not depend on the
+// order it is taken in, so this is the same number scan_cells returns in `sol`.  Must be called by the whole warp.
+__device__ __forceinline__ float warp_min_solid_sdf(const float* __restrict__ hf, const float* __restrict__ cx,
+                                                    const float* __restrict__ cy, int X, int Y, float hx, float hy,
+                                                    float base, float hf_max, const TileSpacing& sp, float3 p,
+                                                    int lane) {
+  SdfBest b;
+  b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0x7fffffff; b.arg_sol = 0x7fffffff;
+  const float top = -base;
+  const float vzs = fmaxf(fmaxf(p.z - hf_max, base - p.z), 0.0f) * 0.999999f;
+  const float vz_sol2 = vzs * vzs;
+  const float isx = sp.isx, isy = sp.isy;
+  {
+    const int ix = to_index(rintf((p.x - cx[0]) * isx), X - 1);
+    const int iy = to_index(rintf((p.y - cy[0]) * isy), Y - 1);
+    const float qx = fabsf(p.x - cx[ix]) - hx, qy = fabsf(p.y - cy[iy]) - hy;
+    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    eval_cell<false, true>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b);
+  }
+  float thr = prune_thr2<false, true>(b, 0.0f, vz_sol2);
+  const float r = sqrtf(fmaxf(thr, 0.0f));
+  const int ix_lo = to_index(floorf((p.x - r - hx - cx[0]) * isx) - 1.0f, X - 1);
+  const int ix_hi = to_index(ceilf((p.x + r + hx - cx[0]) * isx) + 1.0f, X - 1);
+  const int iy_lo = to_index(floorf((p.y - r - hy - cy[0]) * isy) - 1.0f, Y - 1);
+  const int iy_hi = to_index(ceilf((p.y + r + hy - cy[0]) * isy) + 1.0f, Y - 1);
+  const int wy = iy_hi - iy_lo + 1;
+  const int window = (ix_hi - ix_lo + 1) * wy;
+  // c / wy through one multiplication: (c + 0.5) / wy is at least 0.5 / wy away from an integer and c < 2^24, so the
+  // truncated product is the exact quotient up to one unit, which the remainder check below repairs
+  const float inv_wy = 1.0f / (float)wy;
+  for (int c = lane; c < window; c += 32) {
+    int rx = (int)(((float)c + 0.5f) * inv_wy);
+    int ry = c - rx * wy;
+    if (ry < 0) { --rx; ry += wy; } else if (ry >= wy) { ++rx; ry -= wy; }
+    const int ix = ix_lo + rx, iy = iy_lo + ry;
+    const float qx = fabsf(p.x - cx[ix]) - hx, qy = fabsf(p.y - cy[iy]) - hy;
+    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    const float mxy2 = mx * mx + my * my;
+    if (mxy2 > 0.0f && mxy2 > thr) continue;       // outside the footprint and strictly out of reach
+    const float old = b.sol;
+    eval_cell<false, true>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b);
+    if (b.sol < old) thr = prune_thr2<false, true>(b, 0.0f, vz_sol2);
+  }
+  float m = b.sol;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(PARC_FULL_MASK, m, o));
+  return m;
+}
+
 __device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 
 // d sdBox(p - c, half) / d p for one cell, following autograd's sub-gradient conventions

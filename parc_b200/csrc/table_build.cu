@@ -5,8 +5,9 @@
 // (extract_frame_data, :405-423, with quat_pos on the joints), forward-difference root linear / angular
 // velocity with the last frame repeated (:281-288), KinCharModel.compute_frame_dof_vel
 // (anim/kin_char_model.py:543-581) and the interleaving into float4 rows (parc_pack_frames), for every frame of
-// every clip at once.  One warp per frame, lane = body; each lane converts its joint for the frame and for the
-// frame's difference partner (the next frame, or the previous one for a clip's last frame).
+// every clip at once.  One group of lanes per frame (two frames per warp for the humanoid), lane = body; a group walks a
+// run of consecutive frames so that a frame's difference partner (the next frame, or the previous one for a clip's last
+// frame) is converted only once.
 //
 // Values agree with the host-built tables to fp32 rounding of the transcendental calls; the finite differences
 // amplify that by fps (see tests).  Callers that need tables bit-identical to the reference keep the host build.
@@ -66,71 +67,101 @@ __device__ __forceinline__ float3 quat_to_exp_map(float4 q) {
   return make_float3(angle * (q.x / len), angle * (q.y / len), angle * (q.z / len));
 }
 
+// G lanes per frame (G = 16: two frames per warp whenever the character has <= 16 bodies), and every group walks RUNS of
+// consecutive frames: frame f's difference partner f + 1 is the next frame of the run, so each pose is converted once
+// per run instead of twice per frame (a run of 16 frames costs 17 conversions instead of 32).  The (earlier, later)
+// poses of the previous frame stay cached in registers; a clip's last frame finds both of its poses there.
+#define BUILD_RUN 16
+
+template <int G>
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
 build_tables_kernel(const __grid_constant__ BuildParams p, const __grid_constant__ ParcCharModel model_param) {
   __shared__ ParcCharModel sm;
   stage_model(&sm, model_param);
   __syncthreads();
+  constexpr int GROUPS = 32 / G;
   const int lane = threadIdx.x & 31;
+  const int l = lane & (G - 1);
   const int J = sm.num_bodies, D = sm.dof_size;
   const int rf = p.lay.row_floats;
   const int pose_f = p.lay.pose_slots * 4, contact_f = p.lay.contact_slot * 4;
-  const int64_t warp0 = (int64_t)blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * BUILD_WARPS;
-  for (int64_t f = warp0; f < p.total; f += nwarps) {
-    const int c = __ldg(p.frame_clip + f);
-    const int64_t start = __ldg(p.clip_start + c);
-    const int64_t n = __ldg(p.clip_num_frames + c);
-    const float fps = __ldg(p.clip_fps + c);
-    const float dt = __ldg(p.clip_dof_vel_dt + c);
-    const bool last = (f - start) == n - 1;
-    const bool pair = n >= 2;
-    // (a, b) = (earlier, later) frame of the difference: (f, f+1), or (f-1, f) for a clip's last frame
-    const int64_t fa = (pair && last) ? f - 1 : f;
-    const int64_t fb = pair ? fa + 1 : f;
-    float3 pa, pb;
-    float4 ra, rb;
-    lane_pose(sm, p.frames + fa * p.frame_stride, lane, pa, ra);
-    lane_pose(sm, p.frames + fb * p.frame_stride, lane, pb, rb);
-    const bool mine_b = pair && last;
-    const float3 pos = mine_b ? pb : pa;
-    const float4 rot = mine_b ? rb : ra;
-    float* __restrict__ row = p.rows + f * rf;
-    if (lane == 0) {
-      row[0] = pos.x; row[1] = pos.y; row[2] = pos.z; row[3] = 0.0f;
-      reinterpret_cast<float4*>(row)[1] = rot;
-      float3 v = make_float3(0.f, 0.f, 0.f), w = v;
-      if (pair) {
-        v = make_float3(mul_rn(fps, sub_rn(pb.x, pa.x)), mul_rn(fps, sub_rn(pb.y, pa.y)), mul_rn(fps, sub_rn(pb.z, pa.z)));
-        const float3 e = quat_to_exp_map(quat_mul(rb, quat_conj(ra)));      // quat_diff(q0, q1) = q1 * conj(q0)
-        w = make_float3(fps * e.x, fps * e.y, fps * e.z);
+  const int64_t g0 = ((int64_t)blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5)) * GROUPS + lane / G;
+  const int64_t ngroups = (int64_t)gridDim.x * BUILD_WARPS * GROUPS;
+  const int64_t runs = (p.total + BUILD_RUN - 1) / BUILD_RUN;
+  const int jt = (l >= 1 && l < J) ? sm.joint_type[l] : PARC_JOINT_FIXED;
+  const bool has_dof = jt == PARC_JOINT_HINGE || jt == PARC_JOINT_SPHERICAL;
+  for (int64_t r = g0; r < runs; r += ngroups) {
+    const int64_t f_begin = r * BUILD_RUN;
+    const int64_t f_end = f_begin + BUILD_RUN < p.total ? f_begin + BUILD_RUN : p.total;
+    int64_t ia = -1, ib = -1;                       // frames whose poses are cached in (pa, ra) / (pb, rb)
+    float3 pa = make_float3(0.f, 0.f, 0.f), pb = pa;
+    float4 ra = make_float4(0.f, 0.f, 0.f, 1.f), rb = ra;
+    // the clip record is re-read only when the run crosses into the next clip
+    int64_t start = 0, n = 0;
+    float fps = 0.0f, dt = 1.0f;
+    for (int64_t f = f_begin; f < f_end; ++f) {
+      if (f >= start + n) {
+        const int c = __ldg(p.frame_clip + f);
+        start = __ldg(p.clip_start + c);
+        n = __ldg(p.clip_num_frames + c);
+        fps = __ldg(p.clip_fps + c);
+        dt = __ldg(p.clip_dof_vel_dt + c);
       }
-      reinterpret_cast<float4*>(row + pose_f)[0] = make_float4(v.x, v.y, v.z, 0.0f);
-      reinterpret_cast<float4*>(row + pose_f)[1] = make_float4(w.x, w.y, w.z, 0.0f);
-    } else if (lane < J) {
-      reinterpret_cast<float4*>(row)[1 + lane] = rot;
-      const int jt = sm.joint_type[lane];
-      if (jt == PARC_JOINT_HINGE || jt == PARC_JOINT_SPHERICAL) {
+      const bool last = (f - start) == n - 1;
+      const bool pair = n >= 2;
+      // (a, b) = (earlier, later) frame of the difference: (f, f+1), or (f-1, f) for a clip's last frame
+      const int64_t fa = (pair && last) ? f - 1 : f;
+      const int64_t fb = pair ? fa + 1 : f;
+      float3 qa_p, qb_p;
+      float4 qa_r, qb_r;
+      if (fa == ib) { qa_p = pb; qa_r = rb; }
+      else if (fa == ia) { qa_p = pa; qa_r = ra; }
+      else lane_pose(sm, p.frames + fa * p.frame_stride, l, qa_p, qa_r);
+      if (fb == fa) { qb_p = qa_p; qb_r = qa_r; }
+      else if (fb == ib) { qb_p = pb; qb_r = rb; }
+      else lane_pose(sm, p.frames + fb * p.frame_stride, l, qb_p, qb_r);
+      ia = fa; ib = fb; pa = qa_p; ra = qa_r; pb = qb_p; rb = qb_r;
+      const bool mine_b = pair && last;
+      const float3 pos = mine_b ? pb : pa;
+      const float4 rot = mine_b ? rb : ra;
+      // One difference-quaternion / exp-map chain for every lane: the root takes quat_diff(q0, q1) = q1 * conj(q0)
+      // (angular velocity, anim/motion_lib.py:281-288), a joint takes quat_normalize(quat_pos(conj(q0) * q1))
+      // (compute_frame_dof_vel, anim/kin_char_model.py:543-581).
+      const float4 ca = quat_conj(ra);
+      float4 d = quat_mul(l == 0 ? rb : ca, l == 0 ? ca : rb);
+      if (l != 0) {
+        float nrm;
+        if (d.w < 0.0f) { d.x = -d.x; d.y = -d.y; d.z = -d.z; d.w = -d.w; }
+        d = normalize4(d, nrm);
+      }
+      float3 e = make_float3(0.f, 0.f, 0.f);
+      if (pair) e = quat_to_exp_map(d);
+      float* __restrict__ row = p.rows + f * rf;
+      if (l == 0) {
+        row[0] = pos.x; row[1] = pos.y; row[2] = pos.z; row[3] = 0.0f;
+        reinterpret_cast<float4*>(row)[1] = rot;
         float3 v = make_float3(0.f, 0.f, 0.f);
-        if (pair) {
-          float nrm;
-          float4 d = quat_mul(quat_conj(ra), rb);
-          if (d.w < 0.0f) { d.x = -d.x; d.y = -d.y; d.z = -d.z; d.w = -d.w; }
-          const float3 e = quat_to_exp_map(normalize4(d, nrm));               // quat_normalize, then exp map
-          v = make_float3(e.x / dt, e.y / dt, e.z / dt);
-        }
-        float* __restrict__ o = row + pose_f + 8 + sm.dof_idx[lane];
-        if (jt == PARC_JOINT_HINGE) {
-          o[0] = sm.joint_axis[lane][0] * v.x + sm.joint_axis[lane][1] * v.y + sm.joint_axis[lane][2] * v.z;
-        } else {
-          o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        if (pair)
+          v = make_float3(mul_rn(fps, sub_rn(pb.x, pa.x)), mul_rn(fps, sub_rn(pb.y, pa.y)), mul_rn(fps, sub_rn(pb.z, pa.z)));
+        reinterpret_cast<float4*>(row + pose_f)[0] = make_float4(v.x, v.y, v.z, 0.0f);
+        reinterpret_cast<float4*>(row + pose_f)[1] = make_float4(fps * e.x, fps * e.y, fps * e.z, 0.0f);
+      } else if (l < J) {
+        reinterpret_cast<float4*>(row)[1 + l] = rot;
+        if (has_dof) {
+          const float3 v = make_float3(e.x / dt, e.y / dt, e.z / dt);
+          float* __restrict__ o = row + pose_f + 8 + sm.dof_idx[l];
+          if (jt == PARC_JOINT_HINGE) {
+            o[0] = sm.joint_axis[l][0] * v.x + sm.joint_axis[l][1] * v.y + sm.joint_axis[l][2] * v.z;
+          } else {
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+          }
         }
       }
+      // contact flags (+ zero padding of the contact slots), zero padding after the DoF velocities
+      for (int k = l; k < pose_f - contact_f; k += G)
+        row[contact_f + k] = (k < J && p.contacts) ? __ldg(p.contacts + f * J + k) : 0.0f;
+      for (int k = pose_f + 8 + D + l; k < rf; k += G) row[k] = 0.0f;
     }
-    // contact flags (+ zero padding of the contact slots), zero padding after the DoF velocities
-    for (int k = lane; k < pose_f - contact_f; k += 32)
-      row[contact_f + k] = (k < J && p.contacts) ? __ldg(p.contacts + f * J + k) : 0.0f;
-    for (int k = pose_f + 8 + D + lane; k < rf; k += 32) row[k] = 0.0f;
   }
 }
 
@@ -157,8 +188,13 @@ extern "C" int parc_build_tables(const float* frames, int64_t total_frames, int3
   p.frames = frames; p.contacts = contacts; p.frame_clip = frame_clip; p.clip_start = clip_start;
   p.clip_num_frames = clip_num_frames; p.clip_fps = clip_fps; p.clip_dof_vel_dt = clip_dof_vel_dt;
   p.total = total_frames; p.frame_stride = frame_stride; p.rows = rows_out;
-  int64_t ctas = (total_frames + BUILD_WARPS - 1) / BUILD_WARPS;
-  if (ctas > 148 * 16) ctas = 148 * 16;
-  build_tables_kernel<<<(int)ctas, BUILD_WARPS * 32, 0, (cudaStream_t)stream>>>(p, *model);
+  const bool half = model->num_bodies <= 16;
+  const int64_t runs = (total_frames + BUILD_RUN - 1) / BUILD_RUN;
+  const int64_t groups_per_cta = BUILD_WARPS * (half ? 2 : 1);
+  // one run per group: the block scheduler balances the tail (a capped grid left half of the groups a second run)
+  int64_t ctas = (runs + groups_per_cta - 1) / groups_per_cta;
+  if (ctas > 0x7fffffff) ctas = 0x7fffffff;
+  if (half) build_tables_kernel<16><<<(int)ctas, BUILD_WARPS * 32, 0, (cudaStream_t)stream>>>(p, *model);
+  else build_tables_kernel<32><<<(int)ctas, BUILD_WARPS * 32, 0, (cudaStream_t)stream>>>(p, *model);
   return check_launch();
 }

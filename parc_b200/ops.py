@@ -399,6 +399,20 @@ class MotionQueryPlan:
             check(rc, "parc_motion_query_ex")
         return self.out
 
+    def redirect_output(self, name: str, address: int):
+        """Point output `name` ("body_pos" or "obs") of the prebuilt launch at a raw device address instead of
+        `self.out[name]` -- e.g. the NVSwitch multicast address of this rank's rows of a gathered tensor
+        (sharding.PeerGather.direct_ptr), so that the kernel's own stores are replicated into every GPU.  The caller
+        owns the memory behind the address and its lifetime."""
+        if name == "body_pos":
+            assert self._fk.body_pos, "the plan does not produce body_pos"
+            self._fk.body_pos = address
+        elif name == "obs":
+            assert self._qa.obs_out, "the plan does not produce obs"
+            self._qa.obs_out = address
+        else:
+            raise ValueError(name)
+
     def check_errors(self):
         """Raise IndexError if any launch since the last check saw an out-of-range clip id (synchronises)."""
         if self.error_flags is not None:

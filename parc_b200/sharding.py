@@ -4,7 +4,8 @@ The path has no exchange step: every (clip id, time) qu
 and every clip is independent, the frame tables and the global heightfield are replicated.  So the data
 path runs with NO collective; `torch.distributed` (NCCL over NVLink on the GPUs, gloo in the CPU tests)
 is used only
-  * to gather results onto one rank / all ranks when a caller wants them in one place, and
+  * to gather results onto one rank / all ranks when a caller wants them in one place (NCCL, or the library's own
+    peer-memory kernels: `PeerGather`), and
   * to reduce loss statistics (sum / min / max / count in fp64), mirroring what the reference's logger
     does with its all-reduce (util/logger.py:164-183, util/mp_util.py:90-105).
 """
@@ -98,6 +99,114 @@ class AllGatherPlan:
             lo, hi = shard_bounds(self.n_total, r, self.world)
             self.out[lo:hi].copy_(self._stage[r * self._per:r * self._per + (hi - lo)])
         return self.out
+
+
+class PeerGather:
+    """All-gather of query shards over NVLink / NVSwitch peer memory with the library's own kernels
+    (csrc/peer_gather.cu) instead of NCCL: the gathered tensors live in symmetric memory
+    (torch.distributed._symmetric_memory allocates and maps it; PyTorch is plumbing here), every rank stores its rows
+    into all ranks' copies -- one store to the NVSwitch MULTICAST address where the fabric has one, else one store per
+    peer pointer -- and a release / acquire hand-shake on per-block signal slots ends the launch.
+
+        pg = PeerGather({"body_pos": (J, 3), "obs": (P,)}, n_total, device)
+        pg.push({"body_pos": local_bp, "obs": local_obs})     # after the query, same stream
+        pg.out["body_pos"]                                    # [n_total, J, 3] on every rank
+    or, "direct": hand `pg.direct_ptr(name)` to `MotionQueryPlan.redirect_output` so that the query kernel's own
+    stores go to the multicast address, and call `pg.barrier()` after the launch.
+
+    Consecutive steps must alternate between two PeerGather objects when a consumer of step s may still be reading
+    while step s + 1 is pushed (a rank passes the hand-shake of step s + 1 only after every rank has launched its push
+    of step s + 1, which is stream-ordered behind that rank's consumer of step s)."""
+
+    def __init__(self, row_shapes: Dict[str, Tuple[int, ...]], n_total: int, device, group=None, num_blocks: int = 64,
+                 use_multicast: bool = True):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.rank, self.world = world()
+        assert self.world <= _lib.PARC_MAX_PEERS
+        self.device = torch.device(device)
+        self.n_total = int(n_total)
+        self.lo, self.hi = shard_bounds(self.n_total, self.rank, self.world)
+        self.num_blocks = int(num_blocks)
+        self.names = list(row_shapes)
+        assert 1 <= len(self.names) <= _lib.PARC_MAX_PUSH_SEGMENTS
+        off, self._off, self._row_bytes = 0, {}, {}
+        for k in self.names:
+            rb = 4
+            for d in row_shapes[k]:
+                rb *= int(d)
+            self._off[k], self._row_bytes[k] = off, rb
+            off = (off + self.n_total * rb + 255) // 256 * 256
+        self._slots = self.num_blocks + 1                     # last slot: the stand-alone barrier
+        self._sig_off = off
+        total = off + 8 * self._slots
+        grp = group if group is not None else dist.group.WORLD
+        name = grp if isinstance(grp, str) else grp.group_name
+        self.buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()
+        torch.cuda.synchronize(self.device)
+        try:
+            self.hdl = symm.rendezvous(self.buf, name)
+        except Exception:                                     # older releases want the group enabled first
+            symm.enable_symm_mem_for_group(name)
+            self.hdl = symm.rendezvous(self.buf, name)
+        self.hdl.barrier()
+        torch.cuda.synchronize(self.device)
+        mc = int(self.hdl.multicast_ptr) if (use_multicast and getattr(self.hdl, "has_multicast_support", False)) else 0
+        self.multicast = mc != 0
+        self._mc = mc
+        self._peers = [int(p) for p in self.hdl.buffer_ptrs]
+        assert self._peers[self.rank] == self.buf.data_ptr()
+        self.out = {k: self.buf[self._off[k]:self._off[k] + self.n_total * self._row_bytes[k]].view(torch.float32)
+                    .view(self.n_total, *row_shapes[k]) for k in self.names}
+        self.epoch = torch.zeros(self._slots, dtype=torch.int64, device=self.device)
+        sig = _lib.ParcPeerSignals()
+        sig.multicast_signal = (mc + self._sig_off) if mc else None
+        for r in range(self.world):
+            sig.peer_signal[r] = self._peers[r] + self._sig_off
+        sig.local_signal = self.buf.data_ptr() + self._sig_off
+        sig.epoch = self.epoch.data_ptr()
+        sig.world, sig.num_slots = self.world, self._slots
+        self._sig = sig
+        self._segs, self._segs_key = None, None
+        self._lib, self._C = _lib, C
+
+    def direct_ptr(self, name: str) -> int:
+        """Multicast address of THIS rank's rows of gathered tensor `name` (for stores issued by the producing kernel)."""
+        if not self.multicast:
+            raise RuntimeError("direct stores need an NVSwitch multicast mapping; use push()")
+        return self._mc + self._off[name] + self.lo * self._row_bytes[name]
+
+    def _stream(self, stream):
+        return torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+
+    def push(self, local: Dict[str, torch.Tensor], stream: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """Enqueue the push of this rank's shards (behind the work already on the stream); when it has run, `self.out`
+        holds every rank's rows on this rank."""
+        key = tuple((k, local[k].data_ptr()) for k in self.names)
+        if key != self._segs_key:
+            segs = (self._lib.ParcPeerSegment * len(self.names))()
+            for i, k in enumerate(self.names):
+                t = local[k]
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == self.hi - self.lo
+                assert t.numel() * 4 == (self.hi - self.lo) * self._row_bytes[k], (k, tuple(t.shape))
+                rel = self._off[k] + self.lo * self._row_bytes[k]
+                segs[i].src = t.data_ptr()
+                segs[i].dst_multicast = (self._mc + rel) if self.multicast else None
+                for r in range(self.world):
+                    segs[i].dst_peer[r] = self._peers[r] + rel
+                segs[i].bytes = t.numel() * 4
+            self._segs, self._segs_key, self._keep = segs, key, [local[k] for k in self.names]
+        rc = self._lib.load().parc_peer_push(self._segs, len(self.names), self._C.byref(self._sig), self.num_blocks,
+                                             self._stream(stream))
+        self._lib.check(rc, "parc_peer_push")
+        return self.out
+
+    def barrier(self, stream: Optional[int] = None):
+        """Hand-shake alone: every rank's earlier stores into the gathered tensors are visible once it has run."""
+        rc = self._lib.load().parc_peer_barrier(self._C.byref(self._sig), self.num_blocks, self._stream(stream))
+        self._lib.check(rc, "parc_peer_barrier")
 
 
 def gather_shards_to(local: torch.Tensor, n_total: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:

@@ -55,6 +55,44 @@ def _worker(rank, world_size, port, n, q):
         same = all(torch.equal(gathered[k], full[k]) for k in gathered)
         on0 = sharding.gather_shards_to(local["obs"], n, dst=0)
         ok0 = (on0 is None) if rank != 0 else torch.equal(on0, full["obs"])
+        # the library's own peer-memory gather (NVSwitch multicast where available, peer pointers otherwise) against the
+        # single-GPU result; ragged shards (n odd) exercise the 4-byte path, n_even the 16-byte one
+        peer = {}
+        J, P = km.get_num_joints(), int(tmpl.shape[0])
+        lb = {k: local[k].clone() for k in ("body_pos", "obs")}
+        for mode, mc in (("auto", True), ("p2p", False)):
+            pg = sharding.PeerGather({"body_pos": (J, 3), "obs": (P,)}, n, dev, use_multicast=mc)
+            for rep in range(3):                              # replays reuse the per-slot epochs
+                pg.push(lb)
+            torch.cuda.synchronize(dev)
+            peer[mode] = bool(torch.equal(pg.out["body_pos"], full["body_pos"]) and torch.equal(pg.out["obs"], full["obs"]))
+            peer["multicast"] = bool(pg.multicast) if mode == "auto" else peer["multicast"]
+            dist.barrier()
+        n_even = (n // (16 * world_size)) * 16 * world_size
+        lo2, hi2 = sharding.shard_bounds(n_even, rank, world_size)
+        pg = sharding.PeerGather({"body_pos": (J, 3), "obs": (P,)}, n_even, dev)
+        pg.push({"body_pos": full["body_pos"][lo2:hi2].contiguous(), "obs": full["obs"][lo2:hi2].contiguous()})
+        torch.cuda.synchronize(dev)
+        peer["vec16"] = bool(torch.equal(pg.out["body_pos"], full["body_pos"][:n_even]) and
+                             torch.equal(pg.out["obs"], full["obs"][:n_even]))
+        dist.barrier()
+        if pg.multicast:
+            # direct form: the query kernel's own body_pos / obs stores go to the multicast address of this rank's rows
+            pg.buf.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            plan = lib.make_query_plan(ids[lo2:hi2].contiguous(), times[lo2:hi2].contiguous(), hf_desc=hfd, obs_tmpl=tmpl)
+            plan.redirect_output("body_pos", pg.direct_ptr("body_pos"))
+            plan.redirect_output("obs", pg.direct_ptr("obs"))
+            for rep in range(2):
+                plan.launch()
+                pg.barrier()
+            torch.cuda.synchronize(dev)
+            peer["direct"] = bool(torch.equal(pg.out["body_pos"], full["body_pos"][:n_even]) and
+                                  torch.equal(pg.out["obs"], full["obs"][:n_even]))
+            dist.barrier()
+        else:
+            peer["direct"] = None
         # loss statistics of sharded samples (config 3's shape, small)
         B, F = 32, 24
         base = [synth.box_terrain(np.random.default_rng(100 + i)) for i in range(B)]
@@ -68,7 +106,7 @@ def _worker(rank, world_size, port, n, q):
                                       km.dof_to_rot(torch.tensor(s["joint_dof"][sl]).to(dev)),
                                       torch.tensor(s["contacts"][sl]).to(dev), 0.1, 0.1)
         st = sharding.reduce_loss_stats({"pen": pen, "con": con})
-        q.put((rank, bool(same), bool(ok0), st["pen"], st["con"]["count"], pen.double().sum().item()))
+        q.put((rank, bool(same), bool(ok0), st["pen"], st["con"]["count"], pen.double().sum().item(), peer))
     finally:
         dist.destroy_process_group()
 
@@ -88,6 +126,8 @@ def test_nccl_world2_sharded_query_and_loss_stats():
         assert p.exitcode == 0
     got = sorted([q.get(timeout=10) for _ in range(2)], key=lambda x: x[0])
     assert all(g[1] and g[2] for g in got)
+    for g in got:                                                # peer-memory gather == single-GPU query, every mode
+        assert g[6]["auto"] and g[6]["p2p"] and g[6]["vec16"] and g[6]["direct"] in (True, None), g[6]
     assert got[0][3] == got[1][3] and got[0][4] == got[1][4] == 32 * 1          # one loss value per sample
     assert abs(got[0][3]["sum"] - (got[0][5] + got[1][5])) <= 1e-9 * max(1.0, abs(got[0][3]["sum"]))
     assert got[0][3]["min"] >= 0.0 and got[0][3]["max"] >= got[0][3]["mean"] >= got[0][3]["min"]
