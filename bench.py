@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-soak", action="store_true", help="skip the clock-sampling soak loop (profiler runs)")
     ap.add_argument("--no-pdl", action="store_true", help="no programmatic dependent launch between the steps")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the 65 536-env (sharded) leg")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the penetration / contact loss leg")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the dataset-sweep leg")
     ap.add_argument("--cfg5-clips", type=int, default=CFG5_CLIPS_DEFAULT, help="clips of the dataset sweep (whole job)")
     ap.add_argument("--selfcheck", action="store_true", help="run the sharded == single-GPU check also at N = 1")
@@ -780,6 +781,64 @@ def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms):
     return res
 
 
+# ---- cfg3: penetration / contact loss forward + backward, samples sharded over the ranks -----------------------------
+CFG3_SAMPLES, CFG3_FRAMES = 1024, 200
+
+
+def leg_cfg3(ctx):
+    """BASELINE configs[2]: 1024 synthetic MDM samples x 200 frames on per-sample 16x16 box / stair terrains, 304 body
+    points: exp-map / DoF conversion -> FK -> body points -> exact heightfield SDF (air + solid columns) -> penetration
+    and contact terms, forward AND the gradient with respect to the pose leaves (one parc_body_loss launch + the
+    conversion VJPs).  Samples are split contiguously over the ranks; the per-sample losses are reduced at the end."""
+    from parc_b200 import ops, sharding
+    from parc_b200.tools.procgen.mdm_path import body_points_desc
+    from parc_b200.util import geom_util, synth
+    dev, km = ctx.dev, ctx.km
+    B, F = CFG3_SAMPLES, CFG3_FRAMES
+    lo, hi = sharding.shard_bounds(B, ctx.rank, ctx.world)
+    rng = np.random.default_rng(3)
+    base = [synth.box_terrain(rng) if i % 2 == 0 else synth.stairs_terrain(rng) for i in range(32)]
+    hfs = np.stack([base[i % 32] for i in range(lo, hi)])
+    nb = 64                                           # distinct synthetic samples, tiled (content does not change the cost)
+    smp = synth.synth_motion_samples(km, nb, F, base[0], (0.0, 0.0), (0.4, 0.4), seed=11)
+    tile = lambda a: torch.tensor(a).to(dev).repeat((hi - lo + nb - 1) // nb, *([1] * (a.ndim - 1)))[:hi - lo].contiguous()
+    leaves = [tile(smp[k]).requires_grad_(True) for k in ("root_pos", "root_exp", "joint_dof")]
+    contacts = tile(smp["contacts"])
+    pts = body_points_desc(km, geom_util.get_char_point_samples(km))
+    tb = ops.make_terrain_batch(torch.tensor(hfs).to(dev), torch.zeros(hi - lo, 2, device=dev), (0.4, 0.4), base_z=-10.0)
+    model = km.c_model()
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        total, pen, con = ops.body_loss(model, pts, tb, leaves[0], ops.exp_map_to_quat(leaves[1]),
+                                        km.dof_to_rot(leaves[2]), contacts, 0.1, 0.1)
+        total.sum().backward()
+        return pen, con
+
+    for _ in range(2):
+        step()
+    reps = 5
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(ctx)
+    e0.record(stream)
+    for _ in range(reps):
+        pen, con = step()
+    e1.record(stream)
+    barrier(ctx)
+    ms = dist_max(ctx, e0.elapsed_time(e1) / reps)
+    stats = sharding.reduce_loss_stats({"pen": pen.detach().reshape(hi - lo, -1).sum(-1),
+                                        "contact": con.detach().reshape(hi - lo, -1).sum(-1)})
+    S = int(pts.points.shape[0])
+    return {"samples_total": B, "samples_per_gpu": hi - lo, "frames": F, "body_points": S, "ms_fwd_bwd": ms,
+            "samples_per_s": B / (ms * 1e-3), "value": B * F * BODIES / (ms * 1e-3), "unit": UNIT,
+            "point_cell_evals_per_s": B * F * S * 256 * 2 / (ms * 1e-3),
+            "bound": "fp32 ALU (exact min over cells of two box SDFs per surface point), not HBM",
+            "what": "exp-map / DoF -> FK -> 304 body points -> exact hf SDF -> pen + contact loss, forward + pose gradients",
+            "stats": {k: {kk: v[kk] for kk in ("count", "mean", "min", "max")} for k, v in stats.items()}}
+
+
 # ---- cfg5: dataset sweep, clips sharded over the ranks ---------------------------------------------------------------
 CFG5_CHUNK = 12500
 
@@ -920,6 +979,7 @@ def main():
     tracker_step = leg_tracker_step(ctx)
     e2e = leg_e2e(ctx)
     cfg4 = leg_cfg4(ctx) if not args.no_cfg4 else None
+    cfg3 = leg_cfg3(ctx) if not args.no_cfg3 else None
     cfg5 = leg_cfg5(ctx) if not args.no_cfg5 else None
     selfcheck = leg_selfcheck(ctx) if (ctx.world > 1 or args.selfcheck) else None
 
@@ -995,7 +1055,7 @@ def main():
             heading="reference chain (atan2 -> cos/sin)", host_cpu_affinity=ctx.affinity),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_cfg2, "gpu_launches_all_legs": ctx.launches, "clocks": clocks,
-        "tracker_step": tracker_step, "cfg4": cfg4, "cfg5": cfg5, "selfcheck": selfcheck,
+        "tracker_step": tracker_step, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "selfcheck": selfcheck,
     }
     print(json.dumps(line))
     if ctx.world > 1:

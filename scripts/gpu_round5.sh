@@ -6,7 +6,7 @@ TAG="${2:-r2e}"
 mkdir -p gpurun_out
 nvidia-smi topo -m 2>/dev/null | head -12
 python -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -15 > gpurun_out/pytest_multi_${TAG}.log; tail -8 gpurun_out/pytest_multi_${TAG}.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --no-cfg5 > gpurun_out/bench_n${N}_${TAG}.log 2> gpurun_out/bench_n${N}_${TAG}.err; tail -5 gpurun_out/bench_n${N}_${TAG}.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 ${BENCH_EXTRA:-} > gpurun_out/bench_n${N}_${TAG}.log 2> gpurun_out/bench_n${N}_${TAG}.err; tail -5 gpurun_out/bench_n${N}_${TAG}.err
 python - <<PY
 import json
 try:
@@ -16,5 +16,6 @@ try:
 except Exception as e:
     print("unreadable", e)
 PY
+[ -n "${SKIP_SINGLE:-}" ] && exit 0
 python scripts/bench_sweep.py --cpu-clips 1 > gpurun_out/sweep_${TAG}.json 2> gpurun_out/sweep_${TAG}.err; tail -2 gpurun_out/sweep_${TAG}.err; cat gpurun_out/sweep_${TAG}.json
 python scripts/bench_loader.py > gpurun_out/loader_${TAG}.json 2> gpurun_out/loader_${TAG}.err; tail -2 gpurun_out/loader_${TAG}.err; cat gpurun_out/loader_${TAG}.json
