@@ -504,9 +504,10 @@ def leg_tracker_step(ctx):
 
 
 # ---- end to end through the public API with HOST buffers ------------------------------------------------------------
-def leg_e2e(ctx):
-    """Every step: H2D of that step's ids/times from pinned memory, one launch, D2H of EVERY output into pinned
-    memory, and the host waits for the result.  The plan's outputs are views of one contiguous device buffer so the
+def leg_e2e(ctx, only=None):
+    """Every step: H2D of that step's ids/times from pinned memory, one launch, D2H of EVERY output (or, with `only`,
+    of the named outputs -- the plan then neither stores nor returns the others) into pinned memory, and the host
+    waits for the result.  The plan's outputs are views of one contiguous device buffer so the
     read-back is a single copy; two buffer sets on two streams let step i's read-back overlap step i+1's upload +
     launch (a result is only counted once its copy has completed)."""
     args, dev = ctx.args, ctx.dev
@@ -518,6 +519,8 @@ def leg_e2e(ctx):
               ("root_ang_vel", (args.envs, 3)), ("joint_rot", (args.envs, J - 1, 4)), ("dof_vel", (args.envs, D)),
               ("contacts", (args.envs, J)), ("body_pos", (args.envs, J, 3)), ("body_rot", (args.envs, J, 4)),
               ("obs", (args.envs, RAY_POINTS)))
+    if only is not None:
+        fields = tuple(f for f in fields if f[0] in only)
 
     def carve(flat):
         views, off = {}, 0
@@ -537,7 +540,7 @@ def leg_e2e(ctx):
         flat_d = torch.empty(total, dtype=torch.float32, device=dev)
         flat_h = torch.empty(total, dtype=torch.float32).pin_memory()
         views = carve(flat_d)
-        plan = ctx.mlib.make_query_plan(ids_in, times_in, hf_desc=ctx.hfd, obs_tmpl=ctx.tmpl, out=views)
+        plan = ctx.mlib.make_query_plan(ids_in, times_in, hf_desc=ctx.hfd, obs_tmpl=ctx.tmpl, out=views, outputs=only)
         assert all(plan.out[k].data_ptr() == views[k].data_ptr() for k, _ in fields), "plan must write into the views"
         sets.append((st, ids_in, times_in, flat_d, flat_h, plan, torch.cuda.Event()))
 
@@ -578,7 +581,8 @@ def leg_e2e(ctx):
     return {"value": args.envs * ctx.world * BODIES * K / e2e_s, "unit": UNIT,
             "h2d_bytes_per_step": args.envs * (8 + 4), "d2h_bytes_per_step": total * 4,
             "d2h_probe_GBps": d2h_gbps, "ms_per_step": e2e_s / K * 1e3,
-            "bound": "host link: the read-back of every output (pinned, one copy per step, double-buffered)"}
+            "outputs": "all" if only is None else list(only),
+            "bound": "host link: the read-back of the outputs (pinned, one copy per step, double-buffered)"}
 
 
 # ---- cfg4: 65 536 envs, one GPU at N = 1, sharded contiguously over the ranks at N > 1 -------------------------------
@@ -978,6 +982,8 @@ def main():
     launches_cfg2 = K
     tracker_step = leg_tracker_step(ctx)
     e2e = leg_e2e(ctx)
+    # what output selection buys end to end: the metric's own outputs (FK positions + heightmap observation) only
+    e2e_sel = leg_e2e(ctx, only=("body_pos", "obs"))
     cfg4 = leg_cfg4(ctx) if not args.no_cfg4 else None
     cfg3 = leg_cfg3(ctx) if not args.no_cfg3 else None
     cfg5 = leg_cfg5(ctx) if not args.no_cfg5 else None
@@ -1053,7 +1059,7 @@ def main():
                     (" chained by programmatic dependent launch (a step's read side overlaps the previous step's tail; "
                      "its stores wait for it)" if pdl else "")),
             heading="reference chain (atan2 -> cos/sin)", host_cpu_affinity=ctx.affinity),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_body_pos_obs_only": e2e_sel,
         "gpu_launches": launches_cfg2, "gpu_launches_all_legs": ctx.launches, "clocks": clocks,
         "tracker_step": tracker_step, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "selfcheck": selfcheck,
     }

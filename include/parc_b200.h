@@ -208,11 +208,13 @@ int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_
  *                                          kernels earlier); the whole read side -- ids, clip records, frame rows,
  *                                          slerp -- then runs before the wait and only the stores are ordered
  *                                          behind the previous kernel.
- *   variant      0 = chosen by batch size; 1..4 force one instantiation (tuning / tests): 1 = two characters per warp,
+ *   variant      0 = chosen by batch size; 1..6 force one instantiation (tuning / tests): 1 = two characters per warp,
  *                whole template sweep in flight (<= 128 registers); 2 = quarter sweep in flight, 64 registers;
  *                3 = half sweep, 80 registers; 4 = one character per warp; 5 = as 1 with every store of a warp's first
  *                work item deferred behind its forward kinematics (for PARC_QUERY_PDL_EARLY_INPUTS: read AND compute
- *                side overlap the previous kernel, only the stores are ordered behind it). */
+ *                side overlap the previous kernel, only the stores are ordered behind it); 6 = as 5 with the
+ *                observation template staged by one TMA bulk copy (cp.async.bulk + mbarrier) instead of per-thread
+ *                loads (falls back to 5 when the template is not 16-byte aligned). */
 #define PARC_QUERY_FAST_HEADING 1u
 #define PARC_QUERY_PDL 2u
 #define PARC_QUERY_PDL_EARLY_INPUTS 4u

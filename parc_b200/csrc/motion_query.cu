@@ -43,6 +43,32 @@ struct QueryParams {
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk), completion counted on an mbarrier.  Used by the
+// TMA_TMPL instantiation to stage the observation template with one instruction from one thread instead of 7 loads +
+// 7 shared stores from each of the CTA's 64 threads.  dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // Work item -> (entry, step).  In the tracker-step form the items are ordered so that all step-0 queries -- the only
 // ones that sweep the observation template -- come first and share warps with each other: a warp then either sweeps
 // for both of its characters or for neither, instead of idling one half-warp through the other's sweep.
@@ -127,11 +153,14 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // gathers are in flight -- with an early-input PDL launch the whole read AND compute side then overlaps the previous
 // kernel of the stream, and only the stores are ordered behind it (the deferred values stay in registers, so this is
 // for the <= 128-register one-wave variant).
-template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM, bool DEFER = false>
+// TMA_TMPL: the observation template is staged by one cp.async.bulk (experiment behind variant 6).
+template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM, bool DEFER = false,
+          bool TMA_TMPL = false>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p) {
   __shared__ TreeSmem sm;
-  extern __shared__ float2 s_tmpl[];
+  __shared__ uint64_t s_bar;
+  extern __shared__ __align__(16) float2 s_tmpl[];
   constexpr int GROUPS = 32 / G;
   const int lane = threadIdx.x & 31;
   const int l = lane & (G - 1);
@@ -158,7 +187,17 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     id_pre = __ldg(p.ids + e0);
     if (BLEND) t_pre = __ldg(p.times + e0); else f_pre = __ldg(p.frame_idx + e0);
   }
-  if (tmpl_in_smem) {
+  if (TMA_TMPL && tmpl_in_smem) {
+    // whole 16-byte chunks of the template by one bulk copy; the odd tail and the padding up to a whole sweep
+    // (copies of point 0) by plain loads
+    const float2* __restrict__ g = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
+    const int bulk_pts = P & ~1;
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      bulk_g2s(s_tmpl, g, (uint32_t)bulk_pts * 8u, &s_bar);
+    }
+    for (int i = bulk_pts + threadIdx.x; i < P_pad; i += QUERY_CTA_THREADS) s_tmpl[i] = __ldg(g + (i < P ? i : 0));
+  } else if (tmpl_in_smem) {
     // all of a thread's template loads are issued before the first shared-memory store, so the cold misses
     // overlap instead of queueing one round trip per element
     const float2* __restrict__ g = reinterpret_cast<const float2*>(p.obs.tmpl_xy);
@@ -178,6 +217,7 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
   }
   stage_tree_global(&sm, p.tb.tree);
   __syncthreads();
+  if (TMA_TMPL && tmpl_in_smem) mbar_wait(&s_bar, 0);
 
   const int J = sm.num_bodies;
   const int D = sm.dof_size;
@@ -680,7 +720,7 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
   if (n_entries < 0 || a->num_steps < 0 || tables->num_clips <= 0 || tables->total_frames <= 0) return PARC_E_SIZE;
   if (num_steps > 1 && (!a->time_offsets || !blend)) return PARC_E_NULL;
   if (!blend && a->root_xy_offset) return PARC_E_SIZE;
-  if (a->variant < 0 || a->variant > 5) return PARC_E_SIZE;
+  if (a->variant < 0 || a->variant > 6) return PARC_E_SIZE;
   const int64_t n = n_entries * num_steps;
   if (n > 0 && (!a->motion_ids || (blend && !a->motion_times))) return PARC_E_NULL;
   QueryParams p;
@@ -751,7 +791,11 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
   const bool half = variant != 4;
   const int64_t warps = half ? (n + 1) / 2 : n;
   const int grid = query_grid(warps, sms);
-  const int inflight = (variant == 1 || variant == 5) ? 28 : (variant == 2 ? 7 : 14);
+  // 6 = 5 with the template staged by a TMA bulk copy (needs a 16-byte aligned template of >= 2 points)
+  if (variant == 6 && (!p.want_obs || p.obs.num_points < 2 || p.obs.num_points > PARC_TMPL_SMEM_MAX ||
+                       (reinterpret_cast<uintptr_t>(p.obs.tmpl_xy) & 15u) != 0))
+    variant = 5;
+  const int inflight = (variant == 1 || variant == 5 || variant == 6) ? 28 : (variant == 2 ? 7 : 14);
   size_t smem = 0;
   if (p.want_obs && p.obs.num_points <= PARC_TMPL_SMEM_MAX) {
     const int sweep = (half ? 16 : 32) * inflight;
@@ -772,12 +816,20 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
       launch_maybe_pdl(motion_query_kernel<B, GG, NF, RL, MB, false, DF>, grid, QUERY_CTA_THREADS, smem, st, pdl, p); \
   } while (0)
 #define PARC_LAUNCH_QUERY(B, GG, NF, RL, MB) PARC_LAUNCH_QUERY_D(B, GG, NF, RL, MB, false)
+#define PARC_LAUNCH_QUERY_TMA(RL)                                                                                    \
+  do {                                                                                                               \
+    if (step_form)                                                                                                   \
+      launch_maybe_pdl(motion_query_kernel<true, 16, 28, RL, 8, true, true, true>, grid, QUERY_CTA_THREADS, smem, st, pdl, p);  \
+    else                                                                                                             \
+      launch_maybe_pdl(motion_query_kernel<true, 16, 28, RL, 8, false, true, true>, grid, QUERY_CTA_THREADS, smem, st, pdl, p); \
+  } while (0)
   if (blend) {
     switch (variant) {
       case 1: if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); break;
       case 2: if (rel) PARC_LAUNCH_QUERY(true, 16, 7, true, 16); else PARC_LAUNCH_QUERY(true, 16, 7, false, 16); break;
       case 3: if (rel) PARC_LAUNCH_QUERY(true, 16, 14, true, 12); else PARC_LAUNCH_QUERY(true, 16, 14, false, 12); break;
       case 5: if (rel) PARC_LAUNCH_QUERY_D(true, 16, 28, true, 8, true); else PARC_LAUNCH_QUERY_D(true, 16, 28, false, 8, true); break;
+      case 6: if (rel) PARC_LAUNCH_QUERY_TMA(true); else PARC_LAUNCH_QUERY_TMA(false); break;
       default: if (rel) PARC_LAUNCH_QUERY(true, 32, 14, true, 8); else PARC_LAUNCH_QUERY(true, 32, 14, false, 8); break;
     }
   } else {
@@ -785,6 +837,7 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
   }
 #undef PARC_LAUNCH_QUERY
 #undef PARC_LAUNCH_QUERY_D
+#undef PARC_LAUNCH_QUERY_TMA
   return check_launch();
 }
 

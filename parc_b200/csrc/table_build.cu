@@ -191,9 +191,10 @@ extern "C" int parc_build_tables(const float* frames, int64_t total_frames, int3
   const bool half = model->num_bodies <= 16;
   const int64_t runs = (total_frames + BUILD_RUN - 1) / BUILD_RUN;
   const int64_t groups_per_cta = BUILD_WARPS * (half ? 2 : 1);
-  // one run per group: the block scheduler balances the tail (a capped grid left half of the groups a second run)
+  // at most 16 CTAs per SM, the groups stride over the runs: measured faster than one run per group (0.32 vs 0.36 ms
+  // for 2048 x 265 frames) -- every CTA stages the 1.4 KB model before its first run
   int64_t ctas = (runs + groups_per_cta - 1) / groups_per_cta;
-  if (ctas > 0x7fffffff) ctas = 0x7fffffff;
+  if (ctas > 148 * 16) ctas = 148 * 16;
   if (half) build_tables_kernel<16><<<(int)ctas, BUILD_WARPS * 32, 0, (cudaStream_t)stream>>>(p, *model);
   else build_tables_kernel<32><<<(int)ctas, BUILD_WARPS * 32, 0, (cudaStream_t)stream>>>(p, *model);
   return check_launch();

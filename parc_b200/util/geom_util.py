@@ -80,15 +80,29 @@ def _capsule_frame(geom, device):
     return torch_util.axis_angle_to_quat(axis, angle), centre
 
 
+class _HostGeom:
+    """A geom's tensors on the host.  The sample builders below are set-up code (a few hundred tiny ops per
+    character): they run on the CPU and their results are moved to the model's device once, instead of issuing
+    hundreds of one-element GPU launches (and a cuBLAS dot) per call."""
+
+    def __init__(self, g):
+        self._shape_type = g._shape_type
+        self._dims = g._dims.detach().cpu() if isinstance(g._dims, torch.Tensor) else g._dims
+        self._offset = g._offset.detach().cpu() if isinstance(g._offset, torch.Tensor) else g._offset
+        self._radius = getattr(g, "_radius", None)
+        if isinstance(self._radius, torch.Tensor):
+            self._radius = self._radius.detach().cpu()
+
+
 def get_char_point_samples(char_model, sphere_num_subdivisions=0, box_num_slices=2, box_dim_x=3, box_dim_y=6,
                            capsule_num_circle_points=4, capsule_num_sphere_subdivisons=0,
                            capsule_num_cylinder_slices=4):
     """Per-body lists of surface sample points in the body frame (util/geom_util.py:788-870)."""
     from ..anim.kin_char_model import GeomType
-    device = char_model._device
+    device = torch.device("cpu")
     out = []
     for b in range(char_model.get_num_joints()):
-        geoms = char_model.get_geoms(b)
+        geoms = [_HostGeom(g) for g in char_model.get_geoms(b)]
         pts = []
         for g in geoms:
             if g._shape_type == GeomType.SPHERE:
@@ -107,18 +121,18 @@ def get_char_point_samples(char_model, sphere_num_subdivisions=0, box_num_slices
                 pts.append(torch.zeros((1, 3), dtype=torch.float32, device=device))
         if len(geoms) == 0:
             pts.append(torch.zeros((1, 3), dtype=torch.float32, device=device))
-        out.append(torch.cat(pts, dim=0))
+        out.append(torch.cat(pts, dim=0).to(char_model._device))
     return out
 
 
 def get_minimal_char_point_samples(char_model):
     """Cheaper sample set (sphere centre, 2 capsule points, 8 box corners): util/geom_util.py:873-932."""
     from ..anim.kin_char_model import GeomType
-    device = char_model._device
+    device = torch.device("cpu")
     out = []
     for b in range(char_model.get_num_joints()):
         pts = []
-        for g in char_model.get_geoms(b):
+        for g in (_HostGeom(g_) for g_ in char_model.get_geoms(b)):
             if g._shape_type == GeomType.SPHERE:
                 pts.append(g._offset.clone().unsqueeze(0))
             elif g._shape_type == GeomType.CAPSULE:
@@ -130,7 +144,7 @@ def get_minimal_char_point_samples(char_model):
                 pts.append(get_box_point_surface_samples(g._dims, device, num_slices=2, dim_x=2, dim_y=2) + g._offset)
             else:
                 assert False
-        out.append(torch.cat(pts, dim=0))
+        out.append(torch.cat(pts, dim=0).to(char_model._device))
     return out
 
 

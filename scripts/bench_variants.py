@@ -23,16 +23,18 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--envs", default="2048,4096,8192,16384,32768,65536")
     ap.add_argument("--clips", type=int, default=2048)
+    ap.add_argument("--variants", default="0,1,2,3,4,5,6")
+    ap.add_argument("--repeat", type=int, default=1, help="repeat the whole sweep (box-to-box / run-to-run noise)")
     a = ap.parse_args()
     args = argparse.Namespace(envs=4096, clips=a.clips, steps=a.steps, warmup=3, no_pdl=False)
     ctx = bench.setup(args)
     ctx.peak = 6555.5
     out = {"steps": a.steps, "rows": []}
     NB = 16
-    for envs in [int(x) for x in a.envs.split(",")]:
+    for envs in [int(x) for x in a.envs.split(",")] * a.repeat:
         ids_h, times_h = bench.query_batches(NB, envs, a.clips, 264.0 / 30.0, seed=7)
         ids_d, times_d = ids_h.to(ctx.dev), times_h.to(ctx.dev)
-        for variant in (0, 1, 2, 3, 4, 5):
+        for variant in [int(v) for v in a.variants.split(",")]:
             for mode in ("serial", "pdl", "pdl_early", "pdl_early_fast_heading"):
                 kw = dict(variant=variant, pdl=mode != "serial", pdl_early_inputs=mode.startswith("pdl_early"),
                           fast_heading=mode.endswith("fast_heading"))

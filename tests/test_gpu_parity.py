@@ -437,11 +437,11 @@ def test_query_variants_pdl_and_output_selection_are_bit_identical(golden_lib):
     base = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl).launch()
     torch.cuda.synchronize()
     base = {k: v.clone() for k, v in base.items()}
-    for variant in (1, 2, 3, 4, 5):
+    for variant in (1, 2, 3, 4, 5, 6):
         got = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, variant=variant).launch()
         for k, v in base.items():
             assert torch.equal(got[k], v), f"variant {variant}: {k}"
-    for early, variant in ((False, 0), (True, 0), (True, 5), (True, 2)):
+    for early, variant in ((False, 0), (True, 0), (True, 5), (True, 6), (True, 2)):
         pl = golden_lib.make_query_plan(ids, times, hf_desc=t.hf_desc(), obs_tmpl=tmpl, pdl=True, pdl_early_inputs=early,
                                         variant=variant)
         for _ in range(3):                         # back to back: each launch overlaps the previous one's tail
