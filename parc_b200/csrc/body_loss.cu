@@ -42,6 +42,14 @@ points_hf_sdf_kernel(const float* __restrict__ points, int64_t n_points, const _
     hfp = t.hf + b * t.hf_batch_stride;
   }
   __syncthreads();
+  TileBlocks tb = {nullptr, nullptr, 0};
+  if (SMEM_TILE) {                       // per-block height ranges behind the tile
+    float* s_bmax = s_hf + X * Y;
+    float* s_bmin = s_bmax + sdf_blocks(X) * sdf_blocks(Y);
+    stage_tile_blocks(s_hf, X, Y, s_bmax, s_bmin);
+    tb.bmax = s_bmax; tb.bmin = s_bmin; tb.nby = sdf_blocks(Y);
+    __syncthreads();
+  }
   const float base = sample_base_z(t, b);
   const float hf_min = s_minmax[0], hf_max = s_minmax[1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += (int64_t)gridDim.x * blockDim.x) {
@@ -50,10 +58,10 @@ points_hf_sdf_kernel(const float* __restrict__ points, int64_t n_points, const _
     float v;
     int a;
     if (inverted) {
-      const SdfBest r = scan_cells<true, false>(hfp, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
+      const SdfBest r = scan_cells<true, false>(hfp, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p, true, tb);
       v = -1.0f * r.inv; a = r.arg_inv;
     } else {
-      const SdfBest r = scan_cells<false, true>(hfp, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p);
+      const SdfBest r = scan_cells<false, true>(hfp, s_cx, s_cy, X, Y, t.half_dx, t.half_dy, base, hf_min, hf_max, p, true, tb);
       v = r.sol; a = r.arg_sol;
     }
     sdf[b * n_points + i] = v;
@@ -165,6 +173,13 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
     for (int k = s0; k < s1; ++k) s_body[k] = j;
   }
   for (int i = threadIdx.x; i < S * 3; i += blockDim.x) s_lp[i] = __ldg(p.pts.points + i);
+  TileBlocks tb = {nullptr, nullptr, 0};
+  if (SMEM_TILE) {                       // per-block height ranges behind the tile (visible after the barrier below)
+    float* s_bmax = s_tile + X * Y;
+    float* s_bmin = s_bmax + sdf_blocks(X) * sdf_blocks(Y);
+    stage_tile_blocks(s_tile, X, Y, s_bmax, s_bmin);
+    tb.bmax = s_bmax; tb.bmin = s_bmin; tb.nby = sdf_blocks(Y);
+  }
   const float base = sample_base_z(p.terrain, b);
   const float hx = p.terrain.half_dx, hy = p.terrain.half_dy;
   const LaneBody lb = load_lane_body(sm, lane, 0);
@@ -209,13 +224,11 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
       const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
       // A body whose contact weight is exactly 0 contributes exactly 0 to the contact term and to its
       // gradient (closest * 0), so its solid-column scan is skipped.
-      SdfBest best;
-      if (t[7] != 0.0f) {
-        best = scan_cells<true, true>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp);
-      } else {
-        best = scan_cells<true, false>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp);
-        best.sol = 0.0f; best.arg_sol = 0;
-      }
+      // (one call for both cases: the lanes of a warp are consecutive points and may belong to bodies with and
+      // without a contact weight; two instantiations would run one after the other)
+      const bool sol_on = t[7] != 0.0f;
+      SdfBest best = scan_cells<true, true>(s_hf, s_cx, s_cy, X, Y, hx, hy, base, hf_min, hf_max, wp, sol_on, tb);
+      if (!sol_on) { best.sol = 0.0f; best.arg_sol = 0; }
       // penetration: sdf = -best.inv ; neg = min(sdf, 0) ; pen += -neg
       const float sdf_inv = -1.0f * best.inv;
       float* g7 = s_pt + (size_t)k * LOSS_PT;
@@ -305,7 +318,10 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
 }
 
 static size_t nodes_smem_bytes(const ParcTerrainBatch* t) { return ((size_t)t->dim_x + t->dim_y) * sizeof(float); }
-static size_t tile_smem_bytes(const ParcTerrainBatch* t) { return (size_t)t->dim_x * t->dim_y * sizeof(float); }
+// the tile plus its per-block (max, min) heights
+static size_t tile_smem_bytes(const ParcTerrainBatch* t) {
+  return ((size_t)t->dim_x * t->dim_y + 2 * (size_t)sdf_blocks(t->dim_x) * sdf_blocks(t->dim_y)) * sizeof(float);
+}
 
 static int check_terrain(const ParcTerrainBatch* t) {
   if (!t || !t->hf || !t->min_center || !t->x_nodes || !t->y_nodes) return PARC_E_NULL;

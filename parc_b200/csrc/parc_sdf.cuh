@@ -28,9 +28,9 @@ struct SdfBest {
 // mostly coincide.
 template <bool WANT_INV, bool WANT_SOL>
 __device__ __forceinline__ void eval_cell(const float* __restrict__ hf, int cell, float mxy2, float qxy, float pz,
-                                          float base, float top, SdfBest& b) {
+                                          float base, float top, SdfBest& b, bool do_inv = true, bool do_sol = true) {
   const float h = hf[cell];
-  if (WANT_INV) {
+  if (WANT_INV && do_inv) {
     const float cz = (h + top) * 0.5f;
     const float hz = (top - h) * 0.5f;
     const float qz = fabsf(pz - cz) - hz;
@@ -38,7 +38,7 @@ __device__ __forceinline__ void eval_cell(const float* __restrict__ hf, int cell
     const float sd = sqrtf(mxy2 + mz * mz) + fminf(fmaxf(qxy, qz), 0.0f);
     if (sd < b.inv || (sd == b.inv && cell < b.arg_inv)) { b.inv = sd; b.arg_inv = cell; }
   }
-  if (WANT_SOL) {
+  if (WANT_SOL && do_sol) {
     const float cz = (h + base) * 0.5f;
     const float hz = (h - base) * 0.5f;
     const float qz = fabsf(pz - cz) - hz;
@@ -69,13 +69,29 @@ __device__ __forceinline__ int to_index(float v, int hi) {
   return (int)fminf(fmaxf(v, 0.0f), (float)hi);
 }
 
+// Per-block height range of a tile (blocks of PARC_SDF_BLOCK x PARC_SDF_BLOCK cells): the vertical part of the pruning
+// bound taken per block instead of per tile.  On terrains with a few tall boxes the tile-wide maximum says nothing
+// about the flat ground around a point; the block maximum does, and whole blocks drop out of the scan.
+#define PARC_SDF_BLOCK 4
+struct TileBlocks {
+  const float* bmax;   // [nbx * nby] maximum height of each block, or nullptr: no per-block bounds
+  const float* bmin;   // [nbx * nby] minimum height
+  int nby;
+};
+__host__ __device__ __forceinline__ int sdf_blocks(int n) { return (n + PARC_SDF_BLOCK - 1) / PARC_SDF_BLOCK; }
+
+// one axis of max(|p - c| - half, 0) for a cell: the exact expression the per-cell test uses
+__device__ __forceinline__ float cell_q(float p, float c, float half) { return fabsf(p - c) - half; }
+
 template <bool WANT_INV, bool WANT_SOL>
 __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, const float* __restrict__ cx,
                                               const float* __restrict__ cy, int X, int Y, float hx, float hy,
-                                              float base, float hf_min, float hf_max, float3 p) {
+                                              float base, float hf_min, float hf_max, float3 p, bool sol_on = true,
+                                              TileBlocks tb = TileBlocks{nullptr, nullptr, 0}) {
   SdfBest b;
   b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0x7fffffff; b.arg_sol = 0x7fffffff;
   const float top = -base;
+  const bool want_sol = WANT_SOL && sol_on;
   // vertical lower bounds, shrunk by a relative 1e-6 so rounding in the per-cell evaluation cannot beat them
   const float vzs = fmaxf(fmaxf(p.z - hf_max, base - p.z), 0.0f) * 0.999999f;
   const float vzi = fmaxf(fmaxf(hf_min - p.z, p.z - top), 0.0f) * 0.999999f;
@@ -88,11 +104,14 @@ __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, cons
   {
     const int ix = to_index(rintf((p.x - cx[0]) * isx), X - 1);
     const int iy = to_index(rintf((p.y - cy[0]) * isy), Y - 1);
-    const float qx = fabsf(p.x - cx[ix]) - hx, qy = fabsf(p.y - cy[iy]) - hy;
+    const float qx = cell_q(p.x, cx[ix], hx), qy = cell_q(p.y, cy[iy], hy);
     const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
-    eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b);
+    eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b, true, want_sol);
   }
-  float thr = prune_thr2<WANT_INV, WANT_SOL>(b, vz_inv2, vz_sol2);
+  // One reach per mode: a cell is visited when EITHER mode can still use it, and each mode is evaluated only where its
+  // own bound allows -- the air-column SDF of a point above ground is settled by the cell under it (its value is
+  // negative), so the wide window a distant solid column needs does not drag the air evaluation along.
+  float thr = fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, want_sol ? prune_thr(b.sol) - vz_sol2 : -1.0f);
   // Index window that is a SUPERSET of every cell that can still matter: a cell further than r = sqrt(thr)
   // (+ its half width) from the point in x or in y is out of reach.  One extra cell of margin on each side
   // absorbs the rounding of the spacing; cells inside the window are still bound-checked one by one.
@@ -101,22 +120,80 @@ __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, cons
   const int ix_hi = to_index(ceilf((p.x + r + hx - cx[0]) * isx) + 1.0f, X - 1);
   const int iy_lo = to_index(floorf((p.y - r - hy - cy[0]) * isy) - 1.0f, Y - 1);
   const int iy_hi = to_index(ceilf((p.y + r + hy - cy[0]) * isy) + 1.0f, Y - 1);
-  for (int ix = ix_lo; ix <= ix_hi; ++ix) {
-    const float qx = fabsf(p.x - cx[ix]) - hx;
-    const float mx = fmaxf(qx, 0.0f);
-    const float mx2 = mx * mx;
-    if (mx2 > 0.0f && mx2 > thr) continue;         // whole row out of reach
-    for (int iy = iy_lo; iy <= iy_hi; ++iy) {
-      const float qy = fabsf(p.y - cy[iy]) - hy;
-      const float my = fmaxf(qy, 0.0f);
-      const float mxy2 = mx2 + my * my;
-      if (mxy2 > 0.0f && mxy2 > thr) continue;     // outside the footprint and strictly out of reach
-      const float old_inv = b.inv, old_sol = b.sol;
-      eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b);
-      if (b.inv < old_inv || b.sol < old_sol) thr = prune_thr2<WANT_INV, WANT_SOL>(b, vz_inv2, vz_sol2);
+  // The window is walked block by block.  Without per-block bounds a "block" is the whole window with the tile-wide
+  // height range, which is the plain cell-by-cell scan.
+  const bool blocked = tb.bmax != nullptr;
+  const int bk = blocked ? PARC_SDF_BLOCK : 0x3fffffff;
+  const int bx_lo = blocked ? ix_lo / PARC_SDF_BLOCK : 0, bx_hi = blocked ? ix_hi / PARC_SDF_BLOCK : 0;
+  const int by_lo = blocked ? iy_lo / PARC_SDF_BLOCK : 0, by_hi = blocked ? iy_hi / PARC_SDF_BLOCK : 0;
+  for (int bx = bx_lo; bx <= bx_hi; ++bx) {
+    const int x0 = blocked ? max(bx * bk, ix_lo) : ix_lo, x1 = blocked ? min(bx * bk + bk - 1, ix_hi) : ix_hi;
+    // distance in x to the block's footprint = the per-cell expression of its nearest column (same bits)
+    const float mbx = p.x < cx[x0] ? fmaxf(cell_q(p.x, cx[x0], hx), 0.0f)
+                                   : (p.x > cx[x1] ? fmaxf(cell_q(p.x, cx[x1], hx), 0.0f) : 0.0f);
+    const float mbx2 = mbx * mbx;
+    if (mbx2 > 0.0f && mbx2 > thr) continue;       // every column of the block is out of reach
+    for (int by = by_lo; by <= by_hi; ++by) {
+      const int y0 = blocked ? max(by * bk, iy_lo) : iy_lo, y1 = blocked ? min(by * bk + bk - 1, iy_hi) : iy_hi;
+      float vzs2_b = vz_sol2, vzi2_b = vz_inv2;
+      if (blocked) {
+        const float mby = p.y < cy[y0] ? fmaxf(cell_q(p.y, cy[y0], hy), 0.0f)
+                                       : (p.y > cy[y1] ? fmaxf(cell_q(p.y, cy[y1], hy), 0.0f) : 0.0f);
+        const float mb2 = mbx2 + mby * mby;
+        const float hmx = tb.bmax[bx * tb.nby + by], hmn = tb.bmin[bx * tb.nby + by];
+        const float vs = fmaxf(fmaxf(p.z - hmx, base - p.z), 0.0f) * 0.999999f;
+        const float vi = fmaxf(fmaxf(hmn - p.z, p.z - top), 0.0f) * 0.999999f;
+        vzs2_b = vs * vs; vzi2_b = vi * vi;
+        // every cell of the block is at least mb2 away in xy and its column ends at or below hmx / starts at or above hmn
+        const float reach = fmaxf(WANT_INV ? prune_thr(b.inv) - vzi2_b : -1.0f, want_sol ? prune_thr(b.sol) - vzs2_b : -1.0f);
+        if (mb2 > 0.0f && mb2 > reach) continue;
+      }
+      float ti = WANT_INV ? prune_thr(b.inv) - vzi2_b : -1.0f;
+      float ts = want_sol ? prune_thr(b.sol) - vzs2_b : -1.0f;
+      float tm = fmaxf(ti, ts);
+      for (int ix = x0; ix <= x1; ++ix) {
+        const float qx = cell_q(p.x, cx[ix], hx);
+        const float mx = fmaxf(qx, 0.0f);
+        const float mx2 = mx * mx;
+        if (mx2 > 0.0f && mx2 > tm) continue;       // whole column run out of reach
+        for (int iy = y0; iy <= y1; ++iy) {
+          const float qy = cell_q(p.y, cy[iy], hy);
+          const float my = fmaxf(qy, 0.0f);
+          const float mxy2 = mx2 + my * my;
+          if (mxy2 > 0.0f && mxy2 > tm) continue;   // outside the footprint and strictly out of reach
+          const bool inside = !(mxy2 > 0.0f);
+          const bool do_inv = WANT_INV && (inside || !(mxy2 > ti));
+          const bool do_sol = want_sol && (inside || !(mxy2 > ts));
+          const float old_inv = b.inv, old_sol = b.sol;
+          eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b, do_inv, do_sol);
+          if (b.inv < old_inv || b.sol < old_sol) {
+            ti = WANT_INV ? prune_thr(b.inv) - vzi2_b : -1.0f;
+            ts = want_sol ? prune_thr(b.sol) - vzs2_b : -1.0f;
+            tm = fmaxf(ti, ts);
+            thr = fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, want_sol ? prune_thr(b.sol) - vz_sol2 : -1.0f);
+          }
+        }
+      }
     }
   }
   return b;
+}
+
+// Block height ranges of the tile staged in s_hf -> s_bmax / s_bmin ([sdf_blocks(X) * sdf_blocks(Y)] each).  Call
+// after the tile is visible to the CTA (a __syncthreads() behind stage_terrain) and follow with another barrier.
+__device__ __forceinline__ void stage_tile_blocks(const float* __restrict__ s_hf, int X, int Y, float* s_bmax,
+                                                  float* s_bmin) {
+  const int nbx = sdf_blocks(X), nby = sdf_blocks(Y);
+  for (int i = threadIdx.x; i < nbx * nby; i += blockDim.x) {
+    const int bx = i / nby, by = i - bx * nby;
+    float hi = -INFINITY, lo = INFINITY;
+    for (int ix = bx * PARC_SDF_BLOCK; ix < min((bx + 1) * PARC_SDF_BLOCK, X); ++ix)
+      for (int iy = by * PARC_SDF_BLOCK; iy < min((by + 1) * PARC_SDF_BLOCK, Y); ++iy) {
+        const float h = s_hf[ix * Y + iy];
+        hi = fmaxf(hi, h); lo = fminf(lo, h);
+      }
+    s_bmax[i] = hi; s_bmin[i] = lo;
+  }
 }
 
 // Inverse cell spacing of a tile whose centre coordinates are staged in cx / cy (evenly spaced torch.linspace nodes):
