@@ -108,8 +108,13 @@ points_hf_sdf_bwd_kernel(const float* __restrict__ points, int64_t batch, int64_
 //   body sums     lane = body: fixed-order sums of its points' 7 floats; then the FK VJP in-warp
 // The warps of a CTA share one sample's terrain tile (read-only after staging).
 // ------------------------------------------------------------------------------------------------
-#define LOSS_WARPS 4
-#define LOSS_THREADS (LOSS_WARPS * 32)
+// Warps per CTA are chosen at launch.  Each warp owns a 10.6 KB slab (humanoid: 304 points x 8 floats + the body
+// transforms) next to ~6 KB shared by the CTA, and shared memory is what bounds the occupancy: 10 warps = 112 KB, two
+// CTAs = 20 warps per SM; 4 warps = 48 KB, four CTAs = 16 warps per SM -- the fallback when the 10-warp CTA would push
+// the terrain tile (or a character with more surface points) out of shared memory.
+#define LOSS_WARPS_MAX 10
+#define LOSS_WARPS_MIN 4
+#define LOSS_THREADS_MAX (LOSS_WARPS_MAX * 32)
 
 struct BodyLossParams {
   const float *root_pos, *root_rot, *joint_rot, *contacts;
@@ -124,19 +129,20 @@ struct BodyLossParams {
   int want_grad;
 };
 
-// WPF = warps per frame.  1: one warp per frame, LOSS_WARPS frames in flight per CTA, no block barrier in the frame
-// loop -- the throughput form for big batches.  LOSS_WARPS: the whole CTA works on ONE frame (surface points spread
+// CTA_TEAM = false: one warp per frame, blockDim / 32 frames in flight per CTA, no block barrier in the frame
+// loop -- the throughput form for big batches.  true: the whole CTA works on ONE frame (surface points spread
 // over 128 threads, the lane = body steps on warp 0 between block barriers) -- the latency form for a single clip
 // (the motion optimiser's 254 frames would otherwise occupy 254 warps of the 9 472 the GPU holds).  Both forms add
 // in the same order and give identical bits.
 #define LOSS_PT 8            // floats per surface point in the slab: 7 gradient slots + its penetration term
-template <bool SMEM_TILE, int WPF>
-__global__ void __launch_bounds__(LOSS_THREADS)
+template <bool SMEM_TILE, bool CTA_TEAM>
+__global__ void __launch_bounds__(LOSS_THREADS_MAX)
 body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
   __shared__ ParcCharModel sm;
   __shared__ float s_minmax[2];
-  constexpr int TEAMS = LOSS_WARPS / WPF;          // frames in flight per CTA
+  const int WPF = CTA_TEAM ? (int)(blockDim.x >> 5) : 1;     // warps per frame
+  const int TEAMS = CTA_TEAM ? 1 : (int)(blockDim.x >> 5);   // frames in flight per CTA
 
   const int X = p.terrain.dim_x, Y = p.terrain.dim_y;
   const int S = p.pts.num_points;
@@ -152,7 +158,7 @@ body_loss_kernel(const __grid_constant__ BodyLossParams p, const __grid_constant
   float* s_pt = slab + PARC_MAX_BODIES * 9;                          // [S][LOSS_PT]
   float* s_tile = s_lp + (size_t)S * 3 + (size_t)TEAMS * ((size_t)S * LOSS_PT + PARC_MAX_BODIES * 9);   // [X*Y] last
   auto team_sync = [&]() {
-    if (WPF == 1) __syncwarp(); else __syncthreads();              // WPF == LOSS_WARPS: the team is the CTA
+    if (!CTA_TEAM) __syncwarp(); else __syncthreads();             // CTA_TEAM: the team is the CTA
   };
 
   const int64_t b = blockIdx.y;
@@ -426,24 +432,30 @@ int parc::body_loss_launch(const float* root_pos, int64_t root_pos_stride, const
 
   const size_t S = (size_t)pts->num_points;
   // Few frames in total (a single clip being optimised): the whole CTA works on one frame, one frame per CTA.
-  // Otherwise one warp per frame, LOSS_WARPS frames in flight per CTA, the terrain staging amortised over several
+  // Otherwise one warp per frame, `warps` frames in flight per CTA, the terrain staging amortised over several
   // rounds when there is plenty of work.
   const bool team = batch * frames <= (int64_t)148 * 16;
-  const int teams = team ? 1 : LOSS_WARPS;
-  const size_t fixed = nodes_smem_bytes(terrain) + (S * (1 + 3) + teams * (S * LOSS_PT + PARC_MAX_BODIES * 9)) * sizeof(float);
+  auto fixed_bytes = [&](int teams) {
+    return nodes_smem_bytes(terrain) + (S * (1 + 3) + teams * (S * LOSS_PT + PARC_MAX_BODIES * 9)) * sizeof(float);
+  };
+  // CTA size: the large CTA while its slabs leave room for the tile in shared memory, else the small one
+  int warps = LOSS_WARPS_MAX;
+  if (!team && fixed_bytes(LOSS_WARPS_MAX) + tile_smem_bytes(terrain) > PARC_SMEM_LIMIT) warps = LOSS_WARPS_MIN;
+  const int teams = team ? 1 : warps;
+  const size_t fixed = fixed_bytes(teams);
   const bool smem_tile = fixed + tile_smem_bytes(terrain) <= PARC_SMEM_LIMIT;
   const size_t smem = fixed + (smem_tile ? tile_smem_bytes(terrain) : 0);
   if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;      // too many surface points for one CTA's slabs
   static SmemOptIn opt[4];
-  if (team) rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true, LOSS_WARPS>, opt[0], smem)
-                           : ensure_dynamic_smem(body_loss_kernel<false, LOSS_WARPS>, opt[1], smem);
-  else rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true, 1>, opt[2], smem)
-                      : ensure_dynamic_smem(body_loss_kernel<false, 1>, opt[3], smem);
+  if (team) rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true, true>, opt[0], smem)
+                           : ensure_dynamic_smem(body_loss_kernel<false, true>, opt[1], smem);
+  else rc = smem_tile ? ensure_dynamic_smem(body_loss_kernel<true, false>, opt[2], smem)
+                      : ensure_dynamic_smem(body_loss_kernel<false, false>, opt[3], smem);
   if (rc) return rc;
-  int64_t rounds = (batch * frames) / ((int64_t)148 * 16 * LOSS_WARPS);
+  int64_t rounds = (batch * frames) / ((int64_t)148 * 16 * warps);
   if (rounds < 1) rounds = 1;
   if (rounds > 8) rounds = 8;
-  const int64_t fpc = team ? 1 : rounds * LOSS_WARPS;
+  const int64_t fpc = team ? 1 : rounds * warps;
   p.frames_per_cta = (int)fpc;
   const int J = model->num_bodies;
   for (int64_t b0 = 0; b0 < batch; b0 += PARC_GRID_Y_MAX) {       // grid.y is limited to 65 535 samples per launch
@@ -460,11 +472,11 @@ int parc::body_loss_launch(const float* root_pos, int64_t root_pos_stride, const
     p.g_joint_rot = g_joint_rot ? g_joint_rot + q0 * (J - 1) * 4 : nullptr;
     dim3 grid((unsigned)((frames + fpc - 1) / fpc), (unsigned)nb);
     if (team) {
-      if (smem_tile) body_loss_kernel<true, LOSS_WARPS><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
-      else body_loss_kernel<false, LOSS_WARPS><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+      if (smem_tile) body_loss_kernel<true, true><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p, *model);
+      else body_loss_kernel<false, true><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p, *model);
     } else {
-      if (smem_tile) body_loss_kernel<true, 1><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
-      else body_loss_kernel<false, 1><<<grid, LOSS_THREADS, smem, (cudaStream_t)stream>>>(p, *model);
+      if (smem_tile) body_loss_kernel<true, false><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p, *model);
+      else body_loss_kernel<false, false><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p, *model);
     }
   }
   return check_launch();

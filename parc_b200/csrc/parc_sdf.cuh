@@ -23,7 +23,8 @@ struct SdfBest {
 // be negative).  The scan is seeded with the cell under the point.  Because evaluation order is no longer
 // index order, the first-index tie rule of torch.min is kept explicitly: a candidate replaces the best
 // iff it is smaller, or equal with a smaller flat index.  The bound test carries a 1e-6 relative margin
-// for the rounding of best^2 (evaluating too many cells is always safe).
+// for the rounding of the squares and sums (evaluating too many cells is always safe); the vertical part of the
+// bound is bit-exact (mz_bound_solid / mz_bound_air).
 // hf/cx/cy are shared-memory arrays; a warp's threads are points of the same body, so their skip patterns
 // mostly coincide.
 template <bool WANT_INV, bool WANT_SOL>
@@ -53,15 +54,22 @@ __device__ __forceinline__ float prune_thr(float best) {
   return best < 0.0f ? 0.0f : best * best * 1.000001f;
 }
 
-// Effective squared xy-reach for the wanted modes.  Every solid column tops out at or below the tile's
-// maximum height H and every air column starts at or above the tile's minimum height L, so for a cell whose
-// footprint does not contain the point
-//     sdf_solid >= sqrt(mxy^2 + vz_sol^2),  vz_sol = max(pz - H, base - pz, 0)
-//     sdf_air   >= sqrt(mxy^2 + vz_inv^2),  vz_inv = max(L - pz, pz - top, 0)
-// and the cell can be skipped when mxy^2 > best^2 - vz^2 for every wanted mode.
-template <bool WANT_INV, bool WANT_SOL>
-__device__ __forceinline__ float prune_thr2(const SdfBest& b, float vz_inv2, float vz_sol2) {
-  return fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, WANT_SOL ? prune_thr(b.sol) - vz_sol2 : -1.0f);
+// Lower bounds of the clamped vertical part mz = max(qz, 0) of sdBox, for EVERY column of a set whose heights are
+// bounded by h_ext, written as the very float expressions eval_cell evaluates: each step ((h + base) / 2, (h - base) / 2,
+// pz - cz, ... - hz) is a correctly rounded monotone function of h, so qz_float(h) >= qz_float(h_ext) holds bit for
+// bit -- no slack for the rounding of the evaluation is needed (a relative margin cannot cover it: cz and hz are ~5 m
+// when base is -10 m, so qz carries ~1e-6 m of absolute rounding whatever its size).
+//   solid column [base, h], h <= h_max: valid while the point is at or above the tallest column's centre
+//   air column   [h, top],  h >= h_min: valid while the point is at or below the shortest air column's centre
+__device__ __forceinline__ float mz_bound_solid(float pz, float h_max, float base) {
+  const float cz = (h_max + base) * 0.5f, hz = (h_max - base) * 0.5f;
+  const float d = pz - cz;
+  return d >= 0.0f ? fmaxf(fabsf(d) - hz, 0.0f) : 0.0f;
+}
+__device__ __forceinline__ float mz_bound_air(float pz, float h_min, float top) {
+  const float cz = (h_min + top) * 0.5f, hz = (top - h_min) * 0.5f;
+  const float d = pz - cz;
+  return d <= 0.0f ? fmaxf(fabsf(d) - hz, 0.0f) : 0.0f;
 }
 
 // clamp-then-convert so that huge / NaN intermediate values cannot overflow the int conversion
@@ -92,9 +100,8 @@ __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, cons
   b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0x7fffffff; b.arg_sol = 0x7fffffff;
   const float top = -base;
   const bool want_sol = WANT_SOL && sol_on;
-  // vertical lower bounds, shrunk by a relative 1e-6 so rounding in the per-cell evaluation cannot beat them
-  const float vzs = fmaxf(fmaxf(p.z - hf_max, base - p.z), 0.0f) * 0.999999f;
-  const float vzi = fmaxf(fmaxf(hf_min - p.z, p.z - top), 0.0f) * 0.999999f;
+  // tile-wide vertical bounds (squared)
+  const float vzs = mz_bound_solid(p.z, hf_max, base), vzi = mz_bound_air(p.z, hf_min, top);
   const float vz_sol2 = vzs * vzs, vz_inv2 = vzi * vzi;
   // cells are evenly spaced (torch.linspace nodes): spacing from the end points
   const float sx = X > 1 ? (cx[X - 1] - cx[0]) / (float)(X - 1) : 1.0f;
@@ -108,14 +115,18 @@ __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, cons
     const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
     eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b, true, want_sol);
   }
-  // One reach per mode: a cell is visited when EITHER mode can still use it, and each mode is evaluated only where its
-  // own bound allows -- the air-column SDF of a point above ground is settled by the cell under it (its value is
-  // negative), so the wide window a distant solid column needs does not drag the air evaluation along.
-  float thr = fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, want_sol ? prune_thr(b.sol) - vz_sol2 : -1.0f);
-  // Index window that is a SUPERSET of every cell that can still matter: a cell further than r = sqrt(thr)
-  // (+ its half width) from the point in x or in y is out of reach.  One extra cell of margin on each side
-  // absorbs the rounding of the spacing; cells inside the window are still bound-checked one by one.
-  const float r = sqrtf(fmaxf(thr, 0.0f));
+  // One reach per mode: a cell (block, column run) whose footprint does not contain the point is skipped for a mode when
+  //     mxy^2 + mz_bound^2  >  best^2 * (1 + 1e-6)          (lim = prune_thr(best); 0 for a negative best)
+  // i.e. when even the bound exceeds the best value; it is visited when EITHER mode can still use it, and each mode is
+  // evaluated only where its own bound allows -- the air-column SDF of a point above ground is settled by the cell
+  // under it (its value is negative), so the wide window a distant solid column needs does not drag the air
+  // evaluation along.
+  float lim_i = WANT_INV ? prune_thr(b.inv) : -1.0f;
+  float lim_s = want_sol ? prune_thr(b.sol) : -1.0f;
+  // Index window that is a SUPERSET of every cell that can still matter: a cell further than r (+ its half width)
+  // from the point in x or in y is out of reach.  One extra cell of margin on each side absorbs the rounding of the
+  // spacing; cells inside the window are still bound-checked one by one.
+  const float r = sqrtf(fmaxf(fmaxf(lim_i - vz_inv2, lim_s - vz_sol2), 0.0f)) * 1.000001f;
   const int ix_lo = to_index(floorf((p.x - r - hx - cx[0]) * isx) - 1.0f, X - 1);
   const int ix_hi = to_index(ceilf((p.x + r + hx - cx[0]) * isx) + 1.0f, X - 1);
   const int iy_lo = to_index(floorf((p.y - r - hy - cy[0]) * isy) - 1.0f, Y - 1);
@@ -123,59 +134,54 @@ __device__ __forceinline__ SdfBest scan_cells(const float* __restrict__ hf, cons
   // The window is walked block by block.  Without per-block bounds a "block" is the whole window with the tile-wide
   // height range, which is the plain cell-by-cell scan.
   const bool blocked = tb.bmax != nullptr;
-  const int bk = blocked ? PARC_SDF_BLOCK : 0x3fffffff;
-  const int bx_lo = blocked ? ix_lo / PARC_SDF_BLOCK : 0, bx_hi = blocked ? ix_hi / PARC_SDF_BLOCK : 0;
-  const int by_lo = blocked ? iy_lo / PARC_SDF_BLOCK : 0, by_hi = blocked ? iy_hi / PARC_SDF_BLOCK : 0;
+  const int bk = PARC_SDF_BLOCK;
+  const int bx_lo = blocked ? ix_lo / bk : 0, bx_hi = blocked ? ix_hi / bk : 0;
+  const int by_lo = blocked ? iy_lo / bk : 0, by_hi = blocked ? iy_hi / bk : 0;
+  // out(m2, v2, lim): xy distance^2 m2 > 0 and the bound m2 + v2 beyond reach
+#define PARC_OUT(m2, vi2, vs2) ((m2) > 0.0f && ((m2) + (vi2) > lim_i) && ((m2) + (vs2) > lim_s))
   for (int bx = bx_lo; bx <= bx_hi; ++bx) {
     const int x0 = blocked ? max(bx * bk, ix_lo) : ix_lo, x1 = blocked ? min(bx * bk + bk - 1, ix_hi) : ix_hi;
     // distance in x to the block's footprint = the per-cell expression of its nearest column (same bits)
     const float mbx = p.x < cx[x0] ? fmaxf(cell_q(p.x, cx[x0], hx), 0.0f)
                                    : (p.x > cx[x1] ? fmaxf(cell_q(p.x, cx[x1], hx), 0.0f) : 0.0f);
     const float mbx2 = mbx * mbx;
-    if (mbx2 > 0.0f && mbx2 > thr) continue;       // every column of the block is out of reach
+    if (PARC_OUT(mbx2, vz_inv2, vz_sol2)) continue;       // every column of the block row is out of reach
     for (int by = by_lo; by <= by_hi; ++by) {
       const int y0 = blocked ? max(by * bk, iy_lo) : iy_lo, y1 = blocked ? min(by * bk + bk - 1, iy_hi) : iy_hi;
-      float vzs2_b = vz_sol2, vzi2_b = vz_inv2;
+      float vs2 = vz_sol2, vi2 = vz_inv2;
       if (blocked) {
         const float mby = p.y < cy[y0] ? fmaxf(cell_q(p.y, cy[y0], hy), 0.0f)
                                        : (p.y > cy[y1] ? fmaxf(cell_q(p.y, cy[y1], hy), 0.0f) : 0.0f);
         const float mb2 = mbx2 + mby * mby;
-        const float hmx = tb.bmax[bx * tb.nby + by], hmn = tb.bmin[bx * tb.nby + by];
-        const float vs = fmaxf(fmaxf(p.z - hmx, base - p.z), 0.0f) * 0.999999f;
-        const float vi = fmaxf(fmaxf(hmn - p.z, p.z - top), 0.0f) * 0.999999f;
-        vzs2_b = vs * vs; vzi2_b = vi * vi;
-        // every cell of the block is at least mb2 away in xy and its column ends at or below hmx / starts at or above hmn
-        const float reach = fmaxf(WANT_INV ? prune_thr(b.inv) - vzi2_b : -1.0f, want_sol ? prune_thr(b.sol) - vzs2_b : -1.0f);
-        if (mb2 > 0.0f && mb2 > reach) continue;
+        const float vs = mz_bound_solid(p.z, tb.bmax[bx * tb.nby + by], base);
+        const float vi = mz_bound_air(p.z, tb.bmin[bx * tb.nby + by], top);
+        vs2 = vs * vs; vi2 = vi * vi;
+        // every cell of the block is at least mb2 away in xy; its column ends at or below the block's maximum and its
+        // air column starts at or above the block's minimum
+        if (PARC_OUT(mb2, vi2, vs2)) continue;
       }
-      float ti = WANT_INV ? prune_thr(b.inv) - vzi2_b : -1.0f;
-      float ts = want_sol ? prune_thr(b.sol) - vzs2_b : -1.0f;
-      float tm = fmaxf(ti, ts);
       for (int ix = x0; ix <= x1; ++ix) {
         const float qx = cell_q(p.x, cx[ix], hx);
         const float mx = fmaxf(qx, 0.0f);
         const float mx2 = mx * mx;
-        if (mx2 > 0.0f && mx2 > tm) continue;       // whole column run out of reach
+        if (PARC_OUT(mx2, vi2, vs2)) continue;            // whole column run out of reach
         for (int iy = y0; iy <= y1; ++iy) {
           const float qy = cell_q(p.y, cy[iy], hy);
           const float my = fmaxf(qy, 0.0f);
           const float mxy2 = mx2 + my * my;
-          if (mxy2 > 0.0f && mxy2 > tm) continue;   // outside the footprint and strictly out of reach
           const bool inside = !(mxy2 > 0.0f);
-          const bool do_inv = WANT_INV && (inside || !(mxy2 > ti));
-          const bool do_sol = want_sol && (inside || !(mxy2 > ts));
+          const bool do_inv = WANT_INV && (inside || !(mxy2 + vi2 > lim_i));
+          const bool do_sol = want_sol && (inside || !(mxy2 + vs2 > lim_s));
+          if (!do_inv && !do_sol) continue;               // outside the footprint and strictly out of reach
           const float old_inv = b.inv, old_sol = b.sol;
           eval_cell<WANT_INV, WANT_SOL>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b, do_inv, do_sol);
-          if (b.inv < old_inv || b.sol < old_sol) {
-            ti = WANT_INV ? prune_thr(b.inv) - vzi2_b : -1.0f;
-            ts = want_sol ? prune_thr(b.sol) - vzs2_b : -1.0f;
-            tm = fmaxf(ti, ts);
-            thr = fmaxf(WANT_INV ? prune_thr(b.inv) - vz_inv2 : -1.0f, want_sol ? prune_thr(b.sol) - vz_sol2 : -1.0f);
-          }
+          if (b.inv < old_inv) lim_i = prune_thr(b.inv);
+          if (b.sol < old_sol) lim_s = prune_thr(b.sol);
         }
       }
     }
   }
+#undef PARC_OUT
   return b;
 }
 
@@ -221,7 +227,7 @@ __device__ __forceinline__ float warp_min_solid_sdf(const float* __restrict__ hf
   SdfBest b;
   b.inv = INFINITY; b.sol = INFINITY; b.arg_inv = 0x7fffffff; b.arg_sol = 0x7fffffff;
   const float top = -base;
-  const float vzs = fmaxf(fmaxf(p.z - hf_max, base - p.z), 0.0f) * 0.999999f;
+  const float vzs = mz_bound_solid(p.z, hf_max, base);
   const float vz_sol2 = vzs * vzs;
   const float isx = sp.isx, isy = sp.isy;
   {
@@ -231,8 +237,8 @@ __device__ __forceinline__ float warp_min_solid_sdf(const float* __restrict__ hf
     const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
     eval_cell<false, true>(hf, ix * Y + iy, mx * mx + my * my, fmaxf(qx, qy), p.z, base, top, b);
   }
-  float thr = prune_thr2<false, true>(b, 0.0f, vz_sol2);
-  const float r = sqrtf(fmaxf(thr, 0.0f));
+  float lim = prune_thr(b.sol);                    // skip when mxy^2 + vz^2 > best^2 (1 + 1e-6)
+  const float r = sqrtf(fmaxf(lim - vz_sol2, 0.0f)) * 1.000001f;
   const int ix_lo = to_index(floorf((p.x - r - hx - cx[0]) * isx) - 1.0f, X - 1);
   const int ix_hi = to_index(ceilf((p.x + r + hx - cx[0]) * isx) + 1.0f, X - 1);
   const int iy_lo = to_index(floorf((p.y - r - hy - cy[0]) * isy) - 1.0f, Y - 1);
@@ -250,10 +256,10 @@ __device__ __forceinline__ float warp_min_solid_sdf(const float* __restrict__ hf
     const float qx = fabsf(p.x - cx[ix]) - hx, qy = fabsf(p.y - cy[iy]) - hy;
     const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
     const float mxy2 = mx * mx + my * my;
-    if (mxy2 > 0.0f && mxy2 > thr) continue;       // outside the footprint and strictly out of reach
+    if (mxy2 > 0.0f && mxy2 + vz_sol2 > lim) continue;       // outside the footprint and strictly out of reach
     const float old = b.sol;
     eval_cell<false, true>(hf, ix * Y + iy, mxy2, fmaxf(qx, qy), p.z, base, top, b);
-    if (b.sol < old) thr = prune_thr2<false, true>(b, 0.0f, vz_sol2);
+    if (b.sol < old) lim = prune_thr(b.sol);
   }
   float m = b.sol;
 #pragma unroll
