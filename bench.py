@@ -672,7 +672,11 @@ def leg_cfg4(ctx):
     piped = dist_max(ctx, p0.elapsed_time(p1) / K4)
     gather_bytes = CFG4_ENVS * (BODIES * 3 + RAY_POINTS) * 4
     kern, gath, both = dist_max(ctx, kern), dist_max(ctx, gath), dist_max(ctx, both)
-    peer = leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms)
+    # reference for the peer-memory legs: batch 0 queried and gathered by NCCL
+    plain[0].launch(); g_bp.run(); g_obs.run()
+    torch.cuda.synchronize(dev)
+    nccl_ref = {"body_pos": g_bp.out.clone(), "obs": g_obs.out.clone()}
+    peer = leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms, nccl_ref)
     res.update({"n1_ms_per_step": n1_ms, "efficiency": n1_ms / (ctx.world * shard_ms),
                 "speedup_vs_1gpu": n1_ms / shard_ms,
                 "gather": {"what": "all_gather_into_tensor of body_pos + obs shards (NCCL), every rank receives the full batch",
@@ -686,7 +690,7 @@ def leg_cfg4(ctx):
     return res
 
 
-def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms):
+def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms, nccl_ref):
     """The same exchange with the library's own kernels over NVLink peer memory (csrc/peer_gather.cu) instead of NCCL.
     push: query -> parc_peer_push (16-byte multicast stores of the L2-resident shard + in-kernel hand-shake).
     direct: the query kernel's body_pos / obs stores go straight to the multicast address, then parc_peer_barrier.
@@ -765,6 +769,11 @@ def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms):
     except Exception as e:
         res["push_only_peer_pointers"] = repr(e)[:200]
     ok = torch.equal(pgs[0].out["obs"][pgs[0].lo:pgs[0].hi], outs[0]["obs"])
+    # full-size check: batch 0 through query + push must equal the NCCL-gathered result bit for bit on every rank
+    plans[0][0].launch()
+    pgs[0].push({"body_pos": outs[0]["body_pos"], "obs": outs[0]["obs"]})
+    torch.cuda.synchronize(dev)
+    same = torch.equal(pgs[0].out["body_pos"], nccl_ref["body_pos"]) and torch.equal(pgs[0].out["obs"], nccl_ref["obs"])
     if pgs[0].multicast:
         dplans = [make_plans(ctx, ids_d, times_d, {}) for _ in range(2)]
         for i in range(2):
@@ -778,6 +787,19 @@ def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms):
             pgs[i].barrier()
 
         timed(direct_step, "direct")
+    if pgs[0].multicast:
+        for t in pgs[0].out.values():
+            t.zero_()                                    # so that the direct stores, not the push above, are checked
+        barrier(ctx)
+        dplans[0][0].launch()
+        pgs[0].barrier()
+        torch.cuda.synchronize(dev)
+        same_direct = (torch.equal(pgs[0].out["body_pos"], nccl_ref["body_pos"]) and
+                       torch.equal(pgs[0].out["obs"], nccl_ref["obs"]))
+        same = same and same_direct
+    flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
+    ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+    res["equals_nccl_gather_full_size"] = bool(flag.item() == 1.0)
     res["local_rows_intact"] = bool(ok)
     res["what"] = ("query + gather of body_pos / obs over NVLink peer memory with the library's own kernels; "
                    "push = 16-byte stores of the shard to the NVSwitch multicast address (or to each peer) + in-kernel "

@@ -648,6 +648,59 @@ def test_sdf_on_terrains_beyond_shared_memory_and_huge_batches(O):
         assert torch.equal(full[lo:lo + 1], one)
 
 
+def test_pruned_sdf_scan_equals_brute_force_on_adversarial_terrains(O):
+    """The scan visits blocks / cells only where a bound allows (parc_sdf.cuh::scan_cells): per-mode reach, per-block
+    height ranges, bit-exact monotone vertical bounds.  Against the oracle's brute-force min over ALL cells on terrains
+    built to stress that: dimensions that are not multiples of the 4-cell block, tall one-cell spikes and pits
+    (block max / min far from the neighbours), plateaus, points on cell
+    borders and corners, points inside the ground, far outside the tile, and a base plane close to the surface (where
+    the rounding of (h +- base) / 2 is smallest) as well as the usual -10 m.  Values to 1e-5; the arg-min cell must be the
+    oracle's wherever the runner-up is further than 1e-5 away, and must attain the minimum everywhere."""
+    from parc_b200 import ops
+    gen = torch.Generator().manual_seed(23)
+    for (X, Y), base_z in (((16, 16), -10.0), ((31, 31), -10.0), ((37, 50), -10.0), ((13, 9), -3.0), ((50, 50), -1000.0)):
+        hf = torch.zeros(1, X, Y)
+        for _ in range(12):                               # plateaus
+            x0, y0 = int(torch.randint(0, X - 3, (1,), generator=gen)), int(torch.randint(0, Y - 3, (1,), generator=gen))
+            hf[0, x0:x0 + int(torch.randint(2, 7, (1,), generator=gen)), y0:y0 + int(torch.randint(2, 7, (1,), generator=gen))] = \
+                float(torch.randint(-4, 8, (1,), generator=gen)) * 0.25
+        for _ in range(10):                               # one-cell spikes and pits
+            hf[0, int(torch.randint(0, X, (1,), generator=gen)), int(torch.randint(0, Y, (1,), generator=gen))] = \
+                float(torch.rand(1, generator=gen) * 4.0 - 2.0)
+        mc = torch.tensor([[0.7, -1.1]])
+        dxdy = torch.tensor([0.4, 0.4])
+        n = 1500
+        ext = torch.tensor([X * 0.4, Y * 0.4, 3.5])
+        p = torch.rand(1, n, 3, generator=gen) * (ext + torch.tensor([1.6, 1.6, 0.0])) + torch.tensor([-0.1, -1.9, -1.5])
+        # a third of the points snapped onto cell borders / corners in xy (exact ties between neighbouring columns)
+        k = n // 3
+        p[0, :k, 0] = torch.round((p[0, :k, 0] - 0.7) / 0.2) * 0.2 + 0.7
+        p[0, :k // 2, 1] = torch.round((p[0, :k // 2, 1] + 1.1) / 0.2) * 0.2 - 1.1
+        p[0, -8:, :2] += torch.tensor([40.0, -35.0])      # far outside the tile
+        tb = ops.make_terrain_batch(hf.cuda(), mc.cuda(), (0.4, 0.4), base_z=base_z)
+        centres, half = O.hf_cell_boxes(hf, mc, dxdy, base_z, False)
+        centres_i, half_i = O.hf_cell_boxes(hf, mc, dxdy, base_z, True)
+        for inverted, (cc, hh) in ((False, (centres, half)), (True, (centres_i, half_i))):
+            rel = p.unsqueeze(2) - cc.unsqueeze(1)
+            sd_all = O.sd_box(rel, hh.unsqueeze(1).expand_as(rel))[0]             # [n, M]
+            want, want_arg = torch.min(sd_all, dim=-1)
+            got, arg = ops.points_hf_sdf(p.cuda(), tb, inverted, want_arg=True)
+            got, arg = got[0].cpu(), arg[0].cpu().long()
+            sign = -1.0 if inverted else 1.0
+            tol = 1e-5 * want.abs() + 2e-6
+            assert ((got * sign - want).abs() <= tol).all(), f"{X}x{Y} base {base_z} inverted={inverted}: value"
+            # the reported cell attains the minimum ...
+            at_arg = sd_all.gather(1, arg.view(-1, 1))[:, 0]
+            assert ((at_arg - want).abs() <= tol).all(), f"{X}x{Y} base {base_z} inverted={inverted}: arg does not attain the min"
+            # ... and is the oracle's own first-index choice wherever the minimum is clearly separated
+            second = sd_all.scatter(1, want_arg.view(-1, 1), float("inf")).min(dim=-1)[0]
+            clear = (second - want) > 1e-5
+            assert clear.float().mean() > 0.3
+            assert torch.equal(arg[clear], want_arg[clear]), f"{X}x{Y} base {base_z} inverted={inverted}: arg-min cell"
+            # (exact ties -- plateaus, border points -- are covered by the golden gradient tests: which of two equal
+            # cells wins decides the sign of a gradient component there)
+
+
 def test_compute_motion_loss_vs_golden(gpu_model):
     from parc_b200.tools.procgen.mdm_path import compute_motion_loss
     from parc_b200.util import geom_util

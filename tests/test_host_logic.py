@@ -337,6 +337,44 @@ def test_packed_container_round_trip_and_rejections(tmp_path):
             pf.read_container(p)
 
 
+def test_peer_gather_entry_points_reject_bad_arguments():
+    """parc_peer_push / parc_peer_barrier validate before any launch (csrc/peer_gather.cu)."""
+    from parc_b200 import _lib
+    lib = _lib.load()
+    sig = _lib.ParcPeerSignals()
+    assert lib.parc_peer_barrier(None, 0, None) == -1
+    assert lib.parc_peer_barrier(C.byref(sig), 0, None) == -2                  # world < 1
+    sig.world, sig.num_slots = 2, 4
+    assert lib.parc_peer_barrier(C.byref(sig), 0, None) == -1                  # no local slots / epochs
+    sig.local_signal, sig.epoch = 4096, 8192
+    assert lib.parc_peer_barrier(C.byref(sig), 0, None) == -1                  # neither multicast nor peer addresses
+    assert lib.parc_peer_barrier(C.byref(sig), 4, None) == -2                  # slot beyond num_slots
+    assert lib.parc_peer_barrier(C.byref(sig), -1, None) == -2
+    sig.world = _lib.PARC_MAX_PEERS + 1
+    assert lib.parc_peer_barrier(C.byref(sig), 0, None) == -2
+    sig.world = 2
+    sig.peer_signal[0], sig.peer_signal[1] = 4096, 16384
+    sig.local_signal = 4100
+    assert lib.parc_peer_barrier(C.byref(sig), 0, None) == -4                  # 8-byte counters
+    sig.local_signal = 4096
+    seg = (_lib.ParcPeerSegment * 2)()
+    assert lib.parc_peer_push(None, 1, C.byref(sig), 4, None) == -1
+    assert lib.parc_peer_push(seg, 0, C.byref(sig), 4, None) == -2
+    assert lib.parc_peer_push(seg, _lib.PARC_MAX_PUSH_SEGMENTS + 1, C.byref(sig), 4, None) == -2
+    assert lib.parc_peer_push(seg, 1, C.byref(sig), 8, None) == -2             # more blocks than signal slots
+    seg[0].bytes = 64
+    assert lib.parc_peer_push(seg, 1, C.byref(sig), 4, None) == -1             # no source
+    seg[0].src = 4096
+    assert lib.parc_peer_push(seg, 1, C.byref(sig), 4, None) == -1             # no destination for rank 0
+    seg[0].dst_peer[0], seg[0].dst_peer[1] = 8192, 12288
+    seg[0].bytes = 66
+    assert lib.parc_peer_push(seg, 1, C.byref(sig), 4, None) == -2             # not a multiple of 4 bytes
+    seg[0].bytes, seg[0].src = 64, 4098
+    assert lib.parc_peer_push(seg, 1, C.byref(sig), 4, None) == -4             # misaligned for fp32
+    assert C.sizeof(_lib.ParcPeerSignals) == 8 + 8 * _lib.PARC_MAX_PEERS + 8 + 8 + 8
+    assert C.sizeof(_lib.ParcPeerSegment) == 8 + 8 + 8 * _lib.PARC_MAX_PEERS + 8
+
+
 def test_step_and_loader_entry_points_reject_bad_arguments(cpu_model):
     """Argument validation of the §8(f)-3 / §8(f)-4 entry points (no launch happens on any of these paths)."""
     from parc_b200 import _lib
