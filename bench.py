@@ -699,7 +699,8 @@ def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms, nccl_ref):
     dev = ctx.dev
     stream = torch.cuda.current_stream(dev)
     try:
-        pgs = [sharding.PeerGather({"body_pos": (BODIES, 3), "obs": (RAY_POINTS,)}, CFG4_ENVS, dev) for _ in range(2)]
+        pgs = [sharding.PeerGather({"body_pos": (BODIES, 3), "obs": (RAY_POINTS,)}, CFG4_ENVS, dev, use_multicast=True)
+               for _ in range(2)]
     except Exception as e:
         return {"unavailable": repr(e)[:300]}
     res = {"multicast": bool(pgs[0].multicast), "bytes_total": gather_bytes}

@@ -70,7 +70,7 @@ def _worker(rank, world_size, port, n, q):
             dist.barrier()
         n_even = (n // (16 * world_size)) * 16 * world_size
         lo2, hi2 = sharding.shard_bounds(n_even, rank, world_size)
-        pg = sharding.PeerGather({"body_pos": (J, 3), "obs": (P,)}, n_even, dev)
+        pg = sharding.PeerGather({"body_pos": (J, 3), "obs": (P,)}, n_even, dev, use_multicast=True)
         pg.push({"body_pos": full["body_pos"][lo2:hi2].contiguous(), "obs": full["obs"][lo2:hi2].contiguous()})
         torch.cuda.synchronize(dev)
         peer["vec16"] = bool(torch.equal(pg.out["body_pos"], full["body_pos"][:n_even]) and
