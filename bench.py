@@ -172,11 +172,15 @@ def cpu_reference_step_fn(frames, contacts, hf):
     return step, f"oracle port (torch CPU op chain of the reference) over the full {m}-clip table"
 
 
-def config_dict(args, **extra):
-    """The `config` object of the JSON line; both arms emit the same workload keys."""
-    c = {"workload": workload_name(args), "envs_per_gpu": args.envs, "clips": args.clips, "frames_per_clip": 265}
-    c.update(extra)
-    return c
+NUM_BATCHES = 64     # distinct resident (ids, times) batches: a batch's rows come round again after ~1.3 GB of traffic
+
+
+def config_dict(args):
+    """The `config` object of the JSON line: the workload and its input set -- identical in both arms (how each arm
+    launches and times it is in the line's `measurement` key)."""
+    return {"workload": workload_name(args), "envs_per_gpu": args.envs, "clips": args.clips, "frames_per_clip": 265,
+            "l2": f"inputs larger than L2, no flush: every step reads its own (ids, times) batch -- {NUM_BATCHES} "
+                  "distinct batches rotate -- and gathers its rows at random from the 260 MB frame table"}
 
 
 def run_reference_arm(args):
@@ -193,9 +197,9 @@ def run_reference_arm(args):
     km.load_char_file(os.path.join(ROOT, "parc_b200", "assets", "humanoid.xml"))
     hf, frames, contacts = make_inputs(args, km, seed=1234)
     step, desc = cpu_reference_step_fn(frames, contacts, hf)
-    NB = 8
-    ids, times = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77)
-    steps, warmup = args.steps, args.warmup
+    NB = NUM_BATCHES
+    ids, times = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77)       # rank 0's batches of the GPU arm
+    steps, warmup = args.steps, max(args.warmup, 3)
     for w in range(warmup):
         step(ids[w % NB], times[w % NB])
     t0 = time.perf_counter()
@@ -208,7 +212,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, arm="reference CPU path on the host cores (rank 0 only)"),
+        "config": config_dict(args),
+        "measurement": {"arm": "reference CPU path on the host cores (rank 0 only)", "timing": "time.perf_counter around the steps"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -464,7 +469,7 @@ def make_plans(ctx, ids_d, times_d, out, **kw):
 def leg_cfg2(ctx):
     args, dev = ctx.args, ctx.dev
     K, W = args.steps, max(args.warmup, 3)
-    NB = 64        # distinct resident input batches: a batch's rows come round again after 64 steps = ~1.3 GB of L2 traffic
+    NB = NUM_BATCHES
     ctx.ids_h, ctx.times_h = query_batches(NB, args.envs, args.clips, 264.0 / 30.0, seed=77 + ctx.rank)
     ids_d, times_d = ctx.ids_h.to(dev), ctx.times_h.to(dev)
     out = {}
@@ -1070,18 +1075,16 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": c2["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_dict(
-            args, l2="inputs larger than L2, no flush: every step reads its own (ids, times) batch -- 64 distinct "
-                     "batches rotate, a batch's frame rows come round again after ~1.3 GB of L2 traffic -- and gathers "
-                     "its rows at random from the 260 MB frame table; clip records, heightfield and template stay "
-                     "L2-resident as in a running tracker (the L2-flushed isolated-launch time is roofline."
-                     "isolated_flushed_launch_us)",
-            timing="one CUDA-event pair on the launch stream around the K steps, barrier + synchronize on both sides, "
-                   "max over ranks",
-            launch=("the K steps are ONE CUDA graph of K kernel nodes" +
-                    (" chained by programmatic dependent launch (a step's read side overlaps the previous step's tail; "
-                     "its stores wait for it)" if pdl else "")),
-            heading="reference chain (atan2 -> cos/sin)", host_cpu_affinity=ctx.affinity),
+        "config": config_dict(args),
+        "measurement": {
+            "l2": "clip records, heightfield and template stay L2-resident as in a running tracker; the L2-flushed "
+                  "isolated-launch time is roofline.isolated_flushed_launch_us",
+            "timing": "one CUDA-event pair on the launch stream around the K steps, barrier + synchronize on both sides, "
+                      "max over ranks",
+            "launch": ("the K steps are ONE CUDA graph of K kernel nodes" +
+                       (" chained by programmatic dependent launch (a step's read side overlaps the previous step's "
+                        "tail; its stores wait for it)" if pdl else "")),
+            "heading": "reference chain (atan2 -> cos/sin)", "host_cpu_affinity": ctx.affinity},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_body_pos_obs_only": e2e_sel,
         "gpu_launches": launches_cfg2, "gpu_launches_all_legs": ctx.launches, "clocks": clocks,
         "tracker_step": tracker_step, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "selfcheck": selfcheck,
