@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PARC_ABI_VERSION 2
+#define PARC_ABI_VERSION 3
 #define PARC_MAX_BODIES 24   /* position + rotation slots of a packed row must fit one warp: J + 1 <= 32 */
 #define PARC_MAX_DOF 96
 
@@ -221,6 +221,24 @@ int parc_get_motion_frame(const ParcMotionTables* tables, const int64_t* motion_
 #define PARC_QUERY_ERR_CLIP_ID 1
 #define PARC_QUERY_ERR_FRAME_IDX 2
 
+/* Fused compute_tar_obs (envs/ig_parkour/mgdm_dm_util.py:462-518) for the tracker-step form: with `tar_obs` set in
+ * ParcQueryArgs, every query of step k >= 1 (the future targets of fetch_tar_obs_data) also writes its observation row
+ *   root_pos_obs 3 | root tan-norm 6 | joint tan-norm 6 (J-1) | key bodies 3 K          (W = 9 + 6 (J-1) + 3 K floats)
+ * relative to the SIMULATED character's root (sim_root_pos / sim_root_rot, [n,3] / [n,4], read in place) into
+ * obs_out[env * out_env_stride + (k - 1) * W ...] -- the values parc_tar_obs produces from the stored targets, taken
+ * from the registers that hold them, without the extra launch and the re-read.  Needs num_steps >= 2 and fk outputs. */
+typedef struct ParcTarObsSpec {
+  const float* sim_root_pos;       /* [n,3] */
+  const float* sim_root_rot;       /* [n,4], 16-byte aligned (unused with global_obs) */
+  const int32_t* key_body_ids;     /* [num_keys] body indices, or NULL with num_keys == 0 */
+  float* obs_out;                  /* [n, out_env_stride] */
+  int64_t out_env_stride;          /* floats between consecutive envs; >= (num_steps - 1) * W */
+  int32_t num_keys;
+  int32_t global_obs;
+  int32_t global_tar_root_h;
+  int32_t reserved;
+} ParcTarObsSpec;
+
 typedef struct ParcQueryArgs {
   const ParcMotionTables* tables;
   const int64_t* motion_ids;      /* device [n] */
@@ -240,6 +258,7 @@ typedef struct ParcQueryArgs {
   uint32_t flags;
   int32_t variant;
   int32_t reserved;
+  const ParcTarObsSpec* tar_obs;  /* tracker-step form only, or NULL (appended in ABI version 3) */
 } ParcQueryArgs;
 
 int parc_motion_query_ex(const ParcQueryArgs* args, void* stream);

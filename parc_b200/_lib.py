@@ -81,7 +81,14 @@ class ParcQueryArgs(C.Structure):
                 ("frame_idxs", C.c_void_p), ("n", C.c_int64), ("time_offsets", C.c_void_p),
                 ("root_xy_offset", C.c_void_p), ("model", C.c_void_p), ("frame", C.c_void_p), ("fk", C.c_void_p),
                 ("hf", C.c_void_p), ("obs", C.c_void_p), ("obs_out", C.c_void_p), ("error_flags", C.c_void_p),
-                ("num_steps", C.c_int32), ("flags", C.c_uint32), ("variant", C.c_int32), ("reserved", C.c_int32)]
+                ("num_steps", C.c_int32), ("flags", C.c_uint32), ("variant", C.c_int32), ("reserved", C.c_int32),
+                ("tar_obs", C.c_void_p)]
+
+
+class ParcTarObsSpec(C.Structure):
+    _fields_ = [("sim_root_pos", C.c_void_p), ("sim_root_rot", C.c_void_p), ("key_body_ids", C.c_void_p),
+                ("obs_out", C.c_void_p), ("out_env_stride", C.c_int64), ("num_keys", C.c_int32),
+                ("global_obs", C.c_int32), ("global_tar_root_h", C.c_int32), ("reserved", C.c_int32)]
 
 
 PARC_QUERY_FAST_HEADING, PARC_QUERY_PDL, PARC_QUERY_PDL_EARLY_INPUTS = 1, 2, 4

@@ -198,7 +198,7 @@ class MotionLib:
 
     def make_query_plan(self, motion_ids, motion_times, hf_desc=None, obs_tmpl=None, obs_relative=True,
                         min_obs_h=-3.0, max_obs_h=3.0, want_fk=True, out=None, time_offsets=None, root_xy_offset=None,
-                        outputs=None, fast_heading=False, pdl=False, pdl_early_inputs=False, variant=0):
+                        outputs=None, fast_heading=False, pdl=False, pdl_early_inputs=False, variant=0, tar_obs=None):
         """Prebuilt launch of `calc_motion_frame_fk_obs` over fixed input/output buffers: returns an
         `ops.MotionQueryPlan` whose `.launch()` costs one C call.  Update `motion_ids` / `motion_times`
         in place between launches (as the tracker does with its time buffer).
@@ -211,13 +211,13 @@ class MotionLib:
         root_xy_offset [N,2] (fp32): added to root x,y of every step before FK and the observation -- where each
         env's motion sits on the shared terrain (DMEnv._move_to_motion_terrain, envs/ig_parkour/dm_env.py:604-615).
 
-        outputs / fast_heading / pdl / pdl_early_inputs / variant: see `ops.MotionQueryPlan`."""
+        outputs / fast_heading / pdl / pdl_early_inputs / variant / tar_obs: see `ops.MotionQueryPlan`."""
         return ops.MotionQueryPlan(self._packed, self._kin_char_model.c_model(), motion_ids, motion_times,
                                    want_contacts=self._contact_info, want_fk=want_fk, hf=hf_desc, obs_tmpl=obs_tmpl,
                                    obs_relative=obs_relative, obs_min_h=min_obs_h, obs_max_h=max_obs_h, out=out,
                                    time_offsets=time_offsets, root_xy_offset=root_xy_offset, outputs=outputs,
                                    fast_heading=fast_heading, pdl=pdl, pdl_early_inputs=pdl_early_inputs,
-                                   variant=variant, error_flags=self._error_word(motion_ids.device))
+                                   variant=variant, error_flags=self._error_word(motion_ids.device), tar_obs=tar_obs)
 
     def _calc_loop_offset(self, motion_ids, times):
         """floor(t / len) * root_pos_delta for WRAP clips, zero otherwise (ref :458-475).  Kept for callers that

@@ -11,6 +11,7 @@
 // envs/ig_parkour/mgdm_dm_util.py:158-179; util/terrain_util.py:113-130.
 #include <cstring>
 #include "parc_common.cuh"
+#include "parc_rotations.cuh"
 
 namespace parc {
 
@@ -35,6 +36,7 @@ struct QueryParams {
   int32_t* err;             // device error bits (PARC_QUERY_ERR_*) or nullptr
   int fast_heading;         // 0: heading -> atan2f -> sincosf as the reference; 1: cos/sin straight from the rotated x axis
   int pdl_early;            // 1: ids / times are safe to read before the previous kernel of the stream has finished
+  ParcTarObsSpec tar;       // fused compute_tar_obs for steps >= 1 of the tracker-step form (TAROBS instantiations)
 };
 
 // Programmatic dependent launch (sm_90+): `launch_dependents` lets the next kernel of the stream start its prologue
@@ -154,8 +156,15 @@ __device__ __forceinline__ int obs_cell(const ObsCtx& c, float2 tp) {
 // kernel of the stream, and only the stores are ordered behind it (the deferred values stay in registers, so this is
 // for the <= 128-register one-wave variant).
 // TMA_TMPL: the observation template is staged by one cp.async.bulk (experiment behind variant 6).
+// TAROBS (tracker-step form only): queries of steps >= 1 are the future targets; their observation relative to the
+// SIMULATED character's root (compute_tar_obs, envs/ig_parkour/mgdm_dm_util.py:462-518) is written from the registers
+// that hold the slerped rotations and the FK result -- no separate launch, no re-read of the target frames.
+// MEASURED SLOWER than the separate parc_tar_obs launch in the tracker's step (58.9-60.9 us against 55.1 us per 4096-env
+// step, profiles/r2_bench_tracker_step*.json): the stand-alone kernel runs beside parc_sim_step on a parallel branch
+// and takes the heading frame once per env, here it sits on the critical path and is taken once per (env, step).
+// Kept as an opt-in (TrackerStep(fuse_tar_obs=True)); the default is the separate launch.
 template <bool BLEND, int G, int INFLIGHT, bool RELATIVE, int MINB, bool STEPFORM, bool DEFER = false,
-          bool TMA_TMPL = false>
+          bool TMA_TMPL = false, bool TAROBS = false>
 __global__ void __launch_bounds__(QUERY_CTA_THREADS, MINB)
 motion_query_kernel(const __grid_constant__ QueryParams p) {
   __shared__ TreeSmem sm;
@@ -223,6 +232,11 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
   const int D = sm.dof_size;
   const LaneBody lb = load_lane_body(sm, l, /*lane_of_body0=*/1);
   const int max_depth = sm.max_depth;
+  int key_slot = -1;                                   // which key body this lane's body is (target observation)
+  if (TAROBS && lb.body >= 0)
+    for (int k = 0; k < p.tar.num_keys; ++k)
+      if (__ldg(p.tar.key_body_ids + k) == lb.body) key_slot = k;
+  const int tar_w = 9 + 6 * (J - 1) + 3 * p.tar.num_keys;
   const int row_f4 = p.lay.row_floats >> 2;
   const float4* __restrict__ rows = reinterpret_cast<const float4*>(p.tb.rows);
   const float2* __restrict__ tmpl = tmpl_in_smem ? s_tmpl : reinterpret_cast<const float2*>(p.obs.tmpl_xy);
@@ -251,6 +265,14 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     // where the env's motion sits on the shared terrain (_move_to_motion_terrain, dm_env.py:604-615): root lane only
     float2 xy_off = make_float2(0.0f, 0.0f);
     if (STEPFORM && p.xy_offset && l == 0) xy_off = __ldg(reinterpret_cast<const float2*>(p.xy_offset) + entry);
+    // target observation: the simulated character's root (the frame the targets are expressed in)
+    const bool tar_on = TAROBS && step > 0;
+    float3 cp = make_float3(0.f, 0.f, 0.f);
+    float4 cq = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (tar_on) {
+      cp = ld3(p.tar.sim_root_pos + entry * 3);
+      if (!p.tar.global_obs) cq = ld4(p.tar.sim_root_rot + entry * 4);
+    }
     if (id < 0 || id >= p.tb.num_clips) {         // the reference raises an IndexError / device assert here
       id = 0;
       if (p.err && l == 0) atomicOr(p.err, PARC_QUERY_ERR_CLIP_ID);
@@ -363,23 +385,40 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
         }
       }
     };
+    // target observation, pose part (root rotation on lane 1, joint rotations on lanes 2..J): the same device
+    // functions as tar_obs_kernel, fed from registers
+    float4 hinv = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (tar_on && !p.tar.global_obs) hinv = heading_inverse_quat(cq);
+    float* __restrict__ tar_o = nullptr;
+    if (tar_on) tar_o = p.tar.obs_out + entry * p.tar.out_env_stride + (int64_t)(step - 1) * tar_w;
+    auto store_tar_pose = [&]() {
+      if (tar_on && active && own) {
+        if (l >= 2) store_tan_norm(tar_o + 9 + 6 * (l - 2), R);
+        else if (l == 1) store_tan_norm(tar_o + 3, p.tar.global_obs ? R : quat_mul(hinv, R));
+      }
+    };
     // early-input PDL launches ran everything above -- immutable tables and caller-guaranteed inputs only -- while the
     // previous kernel of the stream was still draining; nothing may be written before it has finished
     if (!DEFER) {
       if (p.pdl_early && base == first) griddep_wait();
       store_frame();
+      store_tar_pose();
     }
 
     if (!p.want_fk && !p.want_obs) {
       if (DEFER) {
         if (p.pdl_early && base == first) griddep_wait();
         store_frame();
+        store_tar_pose();
       }
       continue;
     }
 
     // root position lives in group lane 0, root rotation in group lane 1 (= body 0's lane)
     const float3 rp = make_float3(shfl_g(R.x, 0, G), shfl_g(R.y, 0, G), shfl_g(R.z, 0, G));
+    // target observation, root offset in the character's heading frame (every lane: the key bodies add it below)
+    float3 tar_po = make_float3(rp.x - cp.x, rp.y - cp.y, rp.z - cp.z);
+    if (tar_on && !p.tar.global_obs) tar_po = quat_rotate(hinv, tar_po);
 
     // ---- heightmap observation, part 1: cells of the first G * INFLIGHT points, gathers issued ----
     ObsCtx oc;
@@ -446,6 +485,18 @@ motion_query_kernel(const __grid_constant__ QueryParams p) {
     if (DEFER) {
       if (p.pdl_early && base == first) griddep_wait();
       store_frame();
+      store_tar_pose();
+    }
+    if (tar_on && active) {
+      if (l == 0) st3(tar_o, make_float3(tar_po.x, tar_po.y, p.tar.global_tar_root_h ? rp.z : tar_po.z));
+      if (key_slot >= 0) {                        // key body relative to the target root, then + the root offset
+        float3 kp = make_float3(pos.x - rp.x, pos.y - rp.y, pos.z - rp.z);
+        if (!p.tar.global_obs) {
+          kp = quat_rotate(hinv, kp);
+          kp.x += tar_po.x; kp.y += tar_po.y; kp.z += tar_po.z;
+        }
+        st3(tar_o + 9 + 6 * (J - 1) + 3 * key_slot, kp);
+      }
     }
     if (p.want_fk && active && lb.body >= 0) {
       if (p.fk.body_pos) {
@@ -763,6 +814,21 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
     if ((int64_t)hf->dim_x * hf->dim_y >= (1ll << 31)) return PARC_E_SIZE;
     p.hf = *hf; p.obs = *obs;
   }
+  // fused target observation (tracker-step form)
+  ParcTarObsSpec tar0 = {};
+  p.tar = tar0;
+  const bool want_tar = a->tar_obs != nullptr;
+  if (want_tar) {
+    const ParcTarObsSpec* t = a->tar_obs;
+    if (!blend || num_steps < 2 || !p.want_fk) return PARC_E_SIZE;      // targets are steps >= 1 and need FK
+    if (t->num_keys < 0 || t->num_keys > PARC_MAX_BODIES) return PARC_E_SIZE;
+    if (!t->sim_root_pos || !t->obs_out || (!t->global_obs && !t->sim_root_rot) || (t->num_keys > 0 && !t->key_body_ids))
+      return PARC_E_NULL;
+    if (!t->global_obs && !aligned16(t->sim_root_rot)) return PARC_E_ALIGN;
+    const int64_t w = 9 + 6 * (int64_t)(model->num_bodies - 1) + 3 * (int64_t)t->num_keys;
+    if (t->out_env_stride < (int64_t)(num_steps - 1) * w) return PARC_E_SIZE;
+    p.tar = *t;
+  }
   if (n == 0) return PARC_OK;
   if (!aligned16(p.out.dof_vel)) return PARC_E_ALIGN;
   // Group size: two characters per warp (G = 16) whenever position + rotations fit 16 lanes; it halves
@@ -788,6 +854,13 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
     if (blend && p.want_obs && n <= (int64_t)sms * 16) variant = 4;
   }
   if (!blend && variant != 4) variant = 3;
+  // the fused target observation exists for the two-characters-per-warp step forms 3 and 5 (the 64-register form 2
+  // spills 164 bytes with it and measured slowest)
+  if (want_tar) {
+    if (!fits16) return PARC_E_MODEL;
+    if (variant == 1 || variant == 6) variant = 5;
+    if (variant == 4 || variant == 2) variant = 3;
+  }
   const bool half = variant != 4;
   const int64_t warps = half ? (n + 1) / 2 : n;
   const int grid = query_grid(warps, sms);
@@ -823,7 +896,14 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
     else                                                                                                             \
       launch_maybe_pdl(motion_query_kernel<true, 16, 28, RL, 8, false, true, true>, grid, QUERY_CTA_THREADS, smem, st, pdl, p); \
   } while (0)
-  if (blend) {
+#define PARC_LAUNCH_QUERY_TAR(NF, RL, MB, DF)                                                                        \
+  launch_maybe_pdl(motion_query_kernel<true, 16, NF, RL, MB, true, DF, false, true>, grid, QUERY_CTA_THREADS, smem, st, pdl, p)
+  if (want_tar) {
+    switch (variant) {
+      case 3: if (rel) PARC_LAUNCH_QUERY_TAR(14, true, 12, false); else PARC_LAUNCH_QUERY_TAR(14, false, 12, false); break;
+      default: if (rel) PARC_LAUNCH_QUERY_TAR(28, true, 8, true); else PARC_LAUNCH_QUERY_TAR(28, false, 8, true); break;
+    }
+  } else if (blend) {
     switch (variant) {
       case 1: if (rel) PARC_LAUNCH_QUERY(true, 16, 28, true, 8); else PARC_LAUNCH_QUERY(true, 16, 28, false, 8); break;
       case 2: if (rel) PARC_LAUNCH_QUERY(true, 16, 7, true, 16); else PARC_LAUNCH_QUERY(true, 16, 7, false, 16); break;
@@ -838,6 +918,7 @@ extern "C" int parc_motion_query_ex(const ParcQueryArgs* a, void* stream) {
 #undef PARC_LAUNCH_QUERY
 #undef PARC_LAUNCH_QUERY_D
 #undef PARC_LAUNCH_QUERY_TMA
+#undef PARC_LAUNCH_QUERY_TAR
   return check_launch();
 }
 

@@ -100,6 +100,38 @@ __device__ __forceinline__ float3 exp_map_to_quat_vjp(const float3& e, const flo
 }
 
 
+// ---- small helpers shared by the step-assembly kernels (tracker_step.cu) and the query kernel's fused target
+// observation (motion_query.cu) ----
+__device__ __forceinline__ float3 ld3(const float* __restrict__ p) {
+  return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st3(float* __restrict__ p, const float3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// util/torch_util.py:491-499: rotation about +z by -heading(q)
+__device__ __forceinline__ float4 heading_inverse_quat(const float4& q) {
+  return axis_angle_to_quat(make_float3(0.0f, 0.0f, 1.0f), -calc_heading(q));
+}
+
+// util/torch_util.py:361-373: rotated x axis, then rotated z axis.  quat_rotate (v + w t + q_v x t, t = 2 q_v x v)
+// written out for v = e_x and v = e_z: the terms the general form multiplies by an exact 0 are dropped -- they
+// contribute exact zeros for finite q -- which is a third of the instructions.
+__device__ __forceinline__ void store_tan_norm(float* __restrict__ o, const float4& q) {
+  // v = e_x: q_v x v = (0, z, -y), t = (0, 2z, -2y), q_v x t = (y ty... ) = (-2y^2 - 2z^2, 2xy, 2xz)
+  {
+    const float ty = 2.0f * q.z, tz = -2.0f * q.y;
+    st3(o, make_float3(1.0f + (q.y * tz - q.z * ty), q.w * ty + (-q.x * tz), q.w * tz + (q.x * ty)));
+  }
+  // v = e_z: q_v x v = (y, -x, 0), t = (2y, -2x, 0), q_v x t = (-z ty.. ) = (2xz, 2yz, -2x^2 - 2y^2)
+  {
+    const float tx = 2.0f * q.y, ty = -2.0f * q.x;
+    st3(o + 3, make_float3(q.w * tx + (-q.z * ty), q.w * ty + (q.z * tx), 1.0f + (q.x * ty - q.y * tx)));
+  }
+}
+
+
 // Joint j's quaternion from the pose's DoF vector (anim/kin_char_model.py:57-77).  Hinge and spherical joints
 // (and the root's exp-map) share ONE axis_angle_to_quat call site so that lanes holding different joint types
 // do not serialise two copies of the transcendental chain.

@@ -20,7 +20,10 @@ package, reading the simulator's state tensors in place:
 
 With `fused=True` (default) the simulated character's share -- DoF conversion, proprioceptive observation, reward
 terms, episode flags and both contact-flag blocks -- is ONE launch (`parc_sim_step`, same device code as the
-stand-alone kernels, joint rotations never leave registers): 4 launches per step in total.
+stand-alone kernels, joint rotations never leave registers): 4 launches per step in total.  With `fuse_tar_obs=True`
+the target observation is written by the query kernel itself from the registers that hold the targets
+(ParcTarObsSpec; 3 launches) -- an opt-in, because it measured slower than the separate launch, which runs beside
+`parc_sim_step` on a parallel branch.
 
 Every output buffer is allocated once, so the sequence can be captured in a CUDA graph (`capture()`), after
 which a step is one graph launch.  The Isaac Gym classes themselves (simulation, resets, actors) are out of
@@ -43,7 +46,8 @@ class TrackerStep:
                  pose_termination: bool = True, enable_early_termination: bool = True,
                  termination_height: float = 0.15, episode_length: float = 10.0,
                  root_pos_termination_dist: float = 0.6, root_rot_termination_angle: float = 1.309,
-                 min_obs_h: float = -3.0, max_obs_h: float = 3.0, fused: bool = True):
+                 min_obs_h: float = -3.0, max_obs_h: float = 3.0, fused: bool = True, fuse_tar_obs: bool = False,
+                 query_variant: int = 0):
         dev = mlib._device if hasattr(mlib, "_device") else ray_xy_points.device
         self.device = torch.device(dev)
         self.mlib, self.kcm, self.terrain = mlib, mlib._kin_char_model, terrain
@@ -74,8 +78,10 @@ class TrackerStep:
         self.S = int(steps.shape[0])
         # fetch_tar_obs_data forms timestep * tar_obs_steps in fp32 (mgdm_dm_util.py:289); step 0 = the reference frame
         self.time_offsets = torch.cat([torch.zeros(1), timestep * steps]).to(self.device)
+        self.query_variant = int(query_variant)          # tuning: instantiation of the query kernel (0 = by batch size)
         self._plan = mlib.make_query_plan(self.motion_ids, self.motion_times, want_fk=True,
-                                          time_offsets=self.time_offsets, root_xy_offset=self.motion_xy_offset)
+                                          time_offsets=self.time_offsets, root_xy_offset=self.motion_xy_offset,
+                                          variant=self.query_variant)
         K = int(self.key_body_ids.shape[0])
         self.char_w = (1 if root_height_obs else 0) + 12 + 6 * (J - 1) + D + 3 * K
         self.tar_w = 9 + 6 * (J - 1) + 3 * K
@@ -88,6 +94,10 @@ class TrackerStep:
         # fused=True: the simulated character's share of the step (DoF conversion, observation block, reward, done,
         # contact blocks) is ONE launch (parc_sim_step) instead of four launches and two copies
         self.fused = bool(fused)
+        # fuse_tar_obs=True (with fused): the query kernel itself writes the target observation of steps 1..S from its
+        # registers (ParcTarObsSpec) -- 3 launches per step, no re-read of the target frames.  Off by default: measured
+        # slower than the separate launch (58.9 vs 55.1 us per 4096-env step), which overlaps parc_sim_step.
+        self.fuse_tar_obs = bool(fuse_tar_obs) and self.fused
         self._sim_plan, self._sim_key = None, None
         self._side = torch.cuda.Stream(self.device)
         self._query_done = torch.cuda.Event()
@@ -175,8 +185,16 @@ class TrackerStep:
             ray = ops.hf_obs(self.terrain.hf_desc(), self.ray_xy_points, root_pos, None, relative=True,
                              min_h=c["min_obs_h"], max_h=c["max_obs_h"], root_rot=root_rot, root_offset=env_offsets,
                              out=blk("ray"), plan=True)
-            tarp = ops.tar_obs(root_pos, root_rot, tar["root_pos"], tar["root_rot"], tar["joint_rot"], tar["body_pos"],
-                               c["global_obs"], False, key_body_ids=self.key_body_ids, out=blk("tar"), plan=True)
+            if self.fuse_tar_obs:
+                # same buffers as self._plan (its `out` dict is reused), plus the target-observation block
+                tarp = self.mlib.make_query_plan(
+                    self.motion_ids, self.motion_times, want_fk=True, time_offsets=self.time_offsets,
+                    root_xy_offset=self.motion_xy_offset, out=self._plan.out, variant=self.query_variant,
+                    tar_obs=dict(sim_root_pos=root_pos, sim_root_rot=root_rot, key_body_ids=self.key_body_ids,
+                                 out=blk("tar"), global_obs=c["global_obs"], global_tar_root_h=False))
+            else:
+                tarp = ops.tar_obs(root_pos, root_rot, tar["root_pos"], tar["root_rot"], tar["joint_rot"], tar["body_pos"],
+                                   c["global_obs"], False, key_body_ids=self.key_body_ids, out=blk("tar"), plan=True)
             sim = dict(root_pos=root_pos, root_rot=root_rot, root_vel=root_vel, root_ang_vel=root_ang_vel,
                        dof_pos=dof_pos, dof_vel=dof_vel, body_pos=body_pos, contact_force=contact_forces, time=time_buf,
                        env_offsets=env_offsets, char_contacts=char_contacts)
@@ -202,6 +220,11 @@ class TrackerStep:
         cur, side = torch.cuda.current_stream(self.device), self._side
         side.wait_stream(cur)
         ray.launch(side.cuda_stream)
+        if self.fuse_tar_obs:
+            tarp.launch(cur.cuda_stream)                 # query + FK + target observation in one launch
+            simp.launch(cur.cuda_stream)
+            cur.wait_stream(side)
+            return self._fused_result
         self._plan.launch(cur.cuda_stream)
         self._query_done.record(cur)
         side.wait_event(self._query_done)

@@ -309,6 +309,9 @@ class MotionQueryPlan:
 
     outputs: names out of QUERY_OUTPUTS to produce (default: all the plan's options allow) -- a caller that only
         consumes e.g. ("body_pos", "obs") saves the other stores and, end to end, their read-back.
+    tar_obs: dict(sim_root_pos [E,3], sim_root_rot [E,4], key_body_ids, out [E, (S-1) * W] (may be a column block of
+        the policy-observation row), global_obs, global_tar_root_h) -- the step form then also writes compute_tar_obs
+        of the targets (steps 1..S-1) against the simulated character's root, from the kernel's registers.
     pdl: launch with programmatic stream serialisation (include/parc_b200.h: PARC_QUERY_PDL); with
         pdl_early_inputs=True the caller guarantees ids / times / offsets are not written by the previous kernel of
         the launch stream, and the whole read side overlaps that kernel's tail.
@@ -320,7 +323,7 @@ class MotionQueryPlan:
                  obs_max_h: float = 3.0, out: Optional[dict] = None, time_offsets: Optional[torch.Tensor] = None,
                  root_xy_offset: Optional[torch.Tensor] = None, outputs: Optional[Tuple[str, ...]] = None,
                  fast_heading: bool = False, pdl: bool = False, pdl_early_inputs: bool = False, variant: int = 0,
-                 error_flags: Optional[torch.Tensor] = None):
+                 error_flags: Optional[torch.Tensor] = None, tar_obs: Optional[dict] = None):
         require_cuda(ids, times, tables.rows, time_offsets, root_xy_offset, error_flags)
         assert ids.dtype == torch.int64 and times.dtype == torch.float32 and ids.is_contiguous() and times.is_contiguous()
         assert ids.shape == times.shape and ids.dim() == 1
@@ -384,6 +387,27 @@ class MotionQueryPlan:
         qa.flags = ((_lib.PARC_QUERY_FAST_HEADING if fast_heading else 0) | (_lib.PARC_QUERY_PDL if pdl else 0)
                     | (_lib.PARC_QUERY_PDL_EARLY_INPUTS if (pdl and pdl_early_inputs) else 0))
         qa.variant = int(variant)
+        if tar_obs is not None:
+            # fused compute_tar_obs for steps 1..S-1 (include/parc_b200.h: ParcTarObsSpec)
+            assert time_offsets is not None and S >= 2 and want_fk and self._fk.body_pos, "tar_obs needs the step form + FK"
+            rp, rr = tar_obs["sim_root_pos"], tar_obs["sim_root_rot"]
+            require_cuda(rp, rr, tar_obs["out"])
+            assert rp.dtype == torch.float32 and rp.is_contiguous() and tuple(rp.shape) == (E, 3)
+            assert rr.dtype == torch.float32 and rr.is_contiguous() and tuple(rr.shape) == (E, 4)
+            kid = _key_ids(tar_obs.get("key_body_ids"), self.device)
+            K = 0 if kid is None else int(kid.shape[0])
+            W = 9 + 6 * (J - 1) + 3 * K
+            blk, stride = _out_rows(tar_obs["out"], E, (S - 1) * W, self.device)
+            ts = _lib.ParcTarObsSpec()
+            ts.sim_root_pos, ts.sim_root_rot = rp.data_ptr(), rr.data_ptr()
+            ts.key_body_ids, ts.num_keys = (kid.data_ptr() if K else None), K
+            ts.obs_out, ts.out_env_stride = blk.data_ptr(), stride
+            ts.global_obs = int(bool(tar_obs.get("global_obs", False)))
+            ts.global_tar_root_h = int(bool(tar_obs.get("global_tar_root_h", False)))
+            self._tar = ts
+            self._keep += (rp, rr, kid, blk)
+            qa.tar_obs = C.addressof(ts)
+            self.tar_obs_out = blk                       # [E, (S-1) * W], row stride `stride` floats
         self._qa = qa
         self._fn = _lib.load().parc_motion_query_ex
         self._args = (C.byref(qa),)

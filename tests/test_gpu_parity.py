@@ -1666,8 +1666,47 @@ def test_step_assembly_matches_oracle_on_a_generic_tree():
     assert seen == {0, 1, 3}
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model, O, oracle_tables, oracle_model, fused):
+@pytest.mark.parametrize("variant", [3, 5])
+@pytest.mark.parametrize("global_obs", [False, True])
+def test_query_fused_target_observation_equals_the_standalone_operator(golden_lib, variant, global_obs):
+    """ParcTarObsSpec: the step-form query writes compute_tar_obs of steps 1..S from its registers.  Against parc_tar_obs
+    run on the query's own stored targets (same device functions, same inputs): every instantiation that carries it
+    (half / whole sweep in flight), local and global frames, a strided output block, envs that do not fill the
+    last warp."""
+    from parc_b200 import ops
+    gen = torch.Generator().manual_seed(31 + variant)
+    n, S = 333, 4
+    ids = torch.randint(0, golden_lib.num_motions(), (n,), generator=gen).cuda()
+    times = (torch.rand(n, generator=gen) * 9.0 - 0.5).cuda()
+    offs = torch.tensor([0.0, 1 / 30, 3 / 30, 0.7]).cuda()
+    sim_pos = (torch.randn(n, 3, generator=gen) * 0.5).cuda()
+    q = torch.randn(n, 4, generator=gen)
+    sim_rot = (q / q.norm(dim=-1, keepdim=True)).cuda()
+    keys = torch.tensor([4, 7, 10, 13], dtype=torch.int32).cuda()
+    J = 15
+    W = 9 + 6 * (J - 1) + 3 * 4
+    wide = torch.full((n, 7 + (S - 1) * W + 5), -7.0, device="cuda")
+    blk = wide[:, 7:7 + (S - 1) * W]
+    plan = golden_lib.make_query_plan(ids, times, time_offsets=offs, variant=variant,
+                                      tar_obs=dict(sim_root_pos=sim_pos, sim_root_rot=sim_rot, key_body_ids=keys, out=blk,
+                                                   global_obs=global_obs, global_tar_root_h=False))
+    out = plan.launch()
+    v = {k: t.view(n, S, *t.shape[1:]) for k, t in out.items() if k != "obs"}
+    want = ops.tar_obs(sim_pos, sim_rot, v["root_pos"][:, 1:], v["root_rot"][:, 1:], v["joint_rot"][:, 1:],
+                       v["body_pos"][:, 1:], global_obs, False, key_body_ids=keys)
+    got = blk.reshape(n, S - 1, W)
+    assert_close(got, want, rtol=1e-6, atol=1e-6, what=f"fused target observation variant {variant}")
+    assert (got - want).abs().max().item() <= 2e-6
+    assert (wide[:, :7] == -7.0).all() and (wide[:, 7 + (S - 1) * W:] == -7.0).all()      # stays inside its block
+    # the query's ordinary outputs are unchanged by the extra work
+    plain = golden_lib.make_query_plan(ids, times, time_offsets=offs, variant=variant).launch()
+    for k in ("root_pos", "root_rot", "joint_rot", "body_pos", "body_rot", "dof_vel"):
+        assert torch.equal(out[k], plain[k]), k
+
+
+@pytest.mark.parametrize("fused,fuse_tar", [(False, False), (True, False), (True, True)])
+def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model, O, oracle_tables, oracle_model, fused,
+                                                          fuse_tar):
     """The whole kinematic side of a control step (envs/ig_parkour/step_assembly.py): reference frame + 6 targets
     with the per-env terrain placement, simulated character's observation, ray heightmap, reward terms and done
     flags -- against the same sequence composed from the oracle; then the CUDA-graph replay against the eager run."""
@@ -1686,7 +1725,7 @@ def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model,
     jw, ptd = torch.as_tensor(g["joint_err_w"]), torch.as_tensor(g["pose_termination_dist"])
     feet = [int(i) for i in g["feet"]]
     ts = TrackerStep(golden_lib, terr, n, float(g["dt"]), g["steps"].tolist(), key_ids.tolist(), tmpl, joint_err_w=jw,
-                     pose_termination_dist=ptd, contact_body_ids=feet, fused=fused)
+                     pose_termination_dist=ptd, contact_body_ids=feet, fused=fused, fuse_tar_obs=fuse_tar)
     ids, times = torch.as_tensor(g["ids"]).long(), torch.as_tensor(g["times"])
     xy_off = torch.randn(n, 2, generator=gen) * 0.3
     env_off = torch.as_tensor(g["env_offsets"])

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/parc_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.parc_abi_version() == 2
+    assert lib.parc_abi_version() == 3
     assert lib.parc_error_string(-1).decode() == "a required pointer is NULL"
 
 
