@@ -80,9 +80,12 @@ struct LabelParams {
   int frames_per_cta;
   int mask_words;
   int minh_in_smem;             // 1: per-cell minimum body heights are combined in shared memory, flushed once per CTA
+  int mask_stride;              // mask_words rounded up to a multiple of 4: keeps every warp's slab 16-byte aligned
 };
 
-__global__ void __launch_bounds__(LABEL_THREADS)
+// 4 CTAs per SM (<= 64 registers): the kernel waits on shared-memory reads more than on anything else, and the fourth
+// CTA's 8 warps hide more of that than 8 more registers per thread buy.
+__global__ void __launch_bounds__(LABEL_THREADS, 4)
 clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__ ParcCharModel model_param) {
   extern __shared__ float smem[];
   __shared__ ParcCharModel sm;
@@ -92,16 +95,21 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
   const int S = p.pts.num_points;
   const bool want_masks = (p.frame_mask || p.min_body_heights) && S > 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* s_hf = smem;
+  // Shared memory, 16-byte aligned parts first so that body transforms and local points move as float4:
+  //   s_lp4 [S] float4 local points | per warp: s_bt [J][2] float4 (pos.xyz, rot.x | rot.yzw, -) + mask words (padded)
+  //   | s_hf [X*Y] | s_cx [X] | s_cy [Y] | s_body [S] | s_minh [X*Y]
+  float4* s_lp4 = reinterpret_cast<float4*>(smem);
+  const int slab_floats = PARC_MAX_BODIES * 8 + p.mask_stride;
+  float* slabs = smem + (size_t)S * 4;
+  float* slab = slabs + (size_t)warp * slab_floats;
+  float4* s_bt4 = reinterpret_cast<float4*>(slab);                             // [J][2]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(slab + PARC_MAX_BODIES * 8);  // [mask_words]
+  float* s_hf = slabs + (size_t)LABEL_WARPS * slab_floats;
   float* s_cx = s_hf + X * Y;
   float* s_cy = s_cx + X;
   int* s_body = reinterpret_cast<int*>(s_cy + Y);                              // [S]
-  float* s_lp = reinterpret_cast<float*>(s_body + S);                          // [S][3]
-  float* slab = s_lp + (size_t)S * 3 + (size_t)warp * (PARC_MAX_BODIES * 8 + p.mask_words);
-  float* s_bt = slab;                                                          // [J][8] pos(3) rot(4)
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(slab + PARC_MAX_BODIES * 8);  // [mask_words]
-  // [X*Y] per-cell minimum of the surface-point heights over this CTA's frames (after the warps' slabs)
-  float* s_minh = s_lp + (size_t)S * 3 + (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words);
+  // [X*Y] per-cell minimum of the surface-point heights over this CTA's frames
+  float* s_minh = reinterpret_cast<float*>(s_body + S);
   const bool minh_smem = p.min_body_heights && p.minh_in_smem;
 
   const int64_t b = blockIdx.y;
@@ -115,7 +123,8 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
       const int s0 = __ldg(p.pts.point_start + j), s1 = __ldg(p.pts.point_start + j + 1);
       for (int k = s0; k < s1; ++k) s_body[k] = j;
     }
-    for (int i = threadIdx.x; i < S * 3; i += blockDim.x) s_lp[i] = __ldg(p.pts.points + i);
+    for (int i = threadIdx.x; i < S; i += blockDim.x)
+      s_lp4[i] = make_float4(__ldg(p.pts.points + 3 * i), __ldg(p.pts.points + 3 * i + 1), __ldg(p.pts.points + 3 * i + 2), 0.0f);
     if (minh_smem)
       for (int i = threadIdx.x; i < X * Y; i += blockDim.x) s_minh[i] = INFINITY;
   }
@@ -140,8 +149,8 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
     frame_to_lane_pose(sm, p.frames + q * p.frame_stride, lane, pos, rot);
     fk_warp(lb, max_depth, pos, rot);
     if (lane < J) {
-      float* t = s_bt + lane * 8;
-      t[0] = pos.x; t[1] = pos.y; t[2] = pos.z; t[3] = rot.x; t[4] = rot.y; t[5] = rot.z; t[6] = rot.w;
+      s_bt4[lane * 2] = make_float4(pos.x, pos.y, pos.z, rot.x);
+      s_bt4[lane * 2 + 1] = make_float4(rot.y, rot.z, rot.w, 0.0f);
       if (p.body_pos) { float* o = p.body_pos + (q * J + lane) * 3; o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; }
       if (p.body_rot) reinterpret_cast<float4*>(p.body_rot)[q * J + lane] = rot;
       if (p.body_hf) {
@@ -158,12 +167,12 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
       bool touch = false;
       float pen = INFINITY;
       if (foot < p.keys.num_feet) {
-        const float* t = s_bt + p.keys.foot_body[foot] * 8;
+        const float4 ta = s_bt4[p.keys.foot_body[foot] * 2], tb4 = s_bt4[p.keys.foot_body[foot] * 2 + 1];
         const float hx = p.keys.foot_half[foot][0], hy = p.keys.foot_half[foot][1], hz = p.keys.foot_half[foot][2];
         float3 c = make_float3((corner & 1) ? hx : -hx, (corner & 2) ? hy : -hy, (corner & 4) ? hz : -hz);
         c.x += p.keys.foot_offset[foot][0]; c.y += p.keys.foot_offset[foot][1]; c.z += p.keys.foot_offset[foot][2];
-        const float3 r = quat_rotate(make_float4(t[3], t[4], t[5], t[6]), c);
-        const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
+        const float3 r = quat_rotate(make_float4(ta.w, tb4.x, tb4.y, tb4.z), c);
+        const float3 wp = make_float3(r.x + ta.x, r.y + ta.y, r.z + ta.z);
         const float h = s_hf[grid_index_fast(wp.x, gax) * Y + grid_index_fast(wp.y, gay)];
         touch = wp.z < add_rn(h, p.contact_eps);            // box_points_z < cell_heights + contact_eps
         pen = sub_rn(wp.z, h);
@@ -179,9 +188,9 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
       // split over the warp's lanes (one hand after the other), lane h keeps hand h's value ----
       float hand_sd = INFINITY;
       for (int h = 0; h < p.keys.num_hands; ++h) {
-        const float* t = s_bt + p.keys.hand_body[h] * 8;
+        const float4 ta = s_bt4[p.keys.hand_body[h] * 2];
         const float sol = warp_min_solid_sdf(s_hf, s_cx, s_cy, X, Y, p.terrain.half_dx, p.terrain.half_dy, base, hf_max,
-                                             spacing, make_float3(t[0], t[1], t[2]), lane);
+                                             spacing, make_float3(ta.x, ta.y, ta.z), lane);
         if (lane == h) hand_sd = sol - p.keys.hand_radius[h];   // sdRoundBox = sdBox - r (geom_util.py:113-120)
       }
       // ---- contact row: zeros, then feet / hands ----
@@ -197,10 +206,10 @@ clip_label_kernel(const __grid_constant__ LabelParams p, const __grid_constant__
     // ---- masks: lane = surface point ----
     if (want_masks) {
       for (int k = lane; k < S; k += 32) {
-        const float* t = s_bt + s_body[k] * 8;
-        const float3 lp = make_float3(s_lp[k * 3], s_lp[k * 3 + 1], s_lp[k * 3 + 2]);
-        const float3 r = quat_rotate(make_float4(t[3], t[4], t[5], t[6]), lp);
-        const float3 wp = make_float3(r.x + t[0], r.y + t[1], r.z + t[2]);
+        const int bj = s_body[k];
+        const float4 ta = s_bt4[bj * 2], tb4 = s_bt4[bj * 2 + 1], l4 = s_lp4[k];
+        const float3 r = quat_rotate(make_float4(ta.w, tb4.x, tb4.y, tb4.z), make_float3(l4.x, l4.y, l4.z));
+        const float3 wp = make_float3(r.x + ta.x, r.y + ta.y, r.z + ta.z);
         const int cell = grid_index_fast(wp.x, gax) * Y + grid_index_fast(wp.y, gay);
         if (p.frame_mask) atomicOr(&s_mask[cell >> 5], 1u << (cell & 31));
         if (minh_smem) atomic_min_float(s_minh + cell, wp.z);
@@ -286,10 +295,11 @@ extern "C" int parc_clip_label(const float* frames, int64_t batch, int64_t frame
   p.frame_mask = frame_mask_out; p.min_body_heights = min_body_heights; p.body_pos = body_pos; p.body_rot = body_rot;
   const int cells = terrain->dim_x * terrain->dim_y;
   p.mask_words = (cells + 31) / 32;
+  p.mask_stride = (p.mask_words + 3) / 4 * 4;
   const size_t S = (frame_mask_out || min_body_heights) ? (size_t)pts->num_points : 0;
   p.pts.num_points = (int)S;
-  size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + S * 4 +
-                 (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_words)) * 4;
+  size_t smem = ((size_t)cells + terrain->dim_x + terrain->dim_y + S * 5 +
+                 (size_t)LABEL_WARPS * (PARC_MAX_BODIES * 8 + p.mask_stride)) * 4;
   if (smem > PARC_SMEM_LIMIT) return PARC_E_SIZE;       // per-clip labelling terrains are small tiles (<= ~190 x 190)
   // the per-cell minima are combined in shared memory when a second tile-sized array still fits
   p.minh_in_smem = (min_body_heights && smem + (size_t)cells * 4 <= PARC_SMEM_LIMIT) ? 1 : 0;
