@@ -806,6 +806,7 @@ def leg_cfg4_peer(ctx, ids_d, times_d, K4, NB, gather_bytes, n1_ms, nccl_ref):
     flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
     ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
     res["equals_nccl_gather_full_size"] = bool(flag.item() == 1.0)
+    res["handshake_timeouts"] = int(sum(int(pg.timeout_flag.item()) for pg in pgs))
     res["local_rows_intact"] = bool(ok)
     res["what"] = ("query + gather of body_pos / obs over NVLink peer memory with the library's own kernels; "
                    "push = 16-byte stores of the shard to the NVSwitch multicast address (or to each peer) + in-kernel "

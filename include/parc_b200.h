@@ -731,6 +731,10 @@ typedef struct ParcPeerSignals {
   uint64_t* epoch;                         /* [num_slots] rank-private launch counters */
   int32_t world;
   int32_t num_slots;
+  int64_t timeout_ns;                      /* > 0: a hand-shake that waits longer gives up, ORs 1 into *timeout_flag and
+                                              lets the kernel finish (a peer that never launches must not hang the GPU);
+                                              0 = wait for ever */
+  int32_t* timeout_flag;                   /* device word, or NULL */
 } ParcPeerSignals;
 
 typedef struct ParcPeerSegment {

@@ -33,6 +33,8 @@ struct PeerSync {
   uint64_t* local_signal;                   // this rank's copy
   uint64_t* epoch;                          // [slots] private per-rank launch counters
   int world;
+  long long timeout_ns;                     // > 0: give up waiting after this long (and say so in *timeout_flag)
+  int32_t* timeout_flag;
 };
 
 __device__ __forceinline__ void st_mc_v4(float4* p, const float4& v) {
@@ -54,10 +56,19 @@ __device__ __forceinline__ void signal_and_wait(const PeerSync& s, int slot) {
       asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(s.peer_signal[r] + slot), "l"((uint64_t)1) : "memory");
   }
   const uint64_t want = e * (uint64_t)s.world;
-  uint64_t seen;
-  do {
+  uint64_t seen, t0 = 0, now;
+  if (s.timeout_ns > 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(s.local_signal + slot) : "memory");
-  } while (seen < want);
+    if (seen >= want) break;
+    if (s.timeout_ns > 0) {                  // a rank that never arrives must not hang this GPU
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > (uint64_t)s.timeout_ns) {
+        if (s.timeout_flag) atomicOr(s.timeout_flag, 1);
+        break;
+      }
+    }
+  }
   s.epoch[slot] = e;
 }
 
@@ -118,6 +129,10 @@ static int fill_sync(const ParcPeerSignals* sig, int slots_needed, PeerSync* out
   s.local_signal = sig->local_signal;
   s.epoch = sig->epoch;
   s.world = sig->world;
+  s.timeout_ns = sig->timeout_ns;
+  s.timeout_flag = sig->timeout_flag;
+  if (sig->timeout_ns < 0) return PARC_E_SIZE;
+  if (reinterpret_cast<uintptr_t>(s.timeout_flag) & 3u) return PARC_E_ALIGN;
   if (!s.mc_signal)
     for (int r = 0; r < sig->world; ++r) {
       if (!sig->peer_signal[r]) return PARC_E_NULL;

@@ -119,7 +119,7 @@ class PeerGather:
     of step s + 1, which is stream-ordered behind that rank's consumer of step s)."""
 
     def __init__(self, row_shapes: Dict[str, Tuple[int, ...]], n_total: int, device, group=None, num_blocks: int = 64,
-                 use_multicast: Optional[bool] = None):
+                 use_multicast: Optional[bool] = None, timeout_s: float = 10.0):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         from . import _lib
@@ -173,6 +173,9 @@ class PeerGather:
         sig.local_signal = self.buf.data_ptr() + self._sig_off
         sig.epoch = self.epoch.data_ptr()
         sig.world, sig.num_slots = self.world, self._slots
+        # a rank that never launches its side must not hang this GPU: the hand-shake gives up after `timeout_s`
+        self.timeout_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        sig.timeout_ns, sig.timeout_flag = int(timeout_s * 1e9), self.timeout_flag.data_ptr()
         self._sig = sig
         self._segs, self._segs_key = None, None
         self._lib, self._C = _lib, C
@@ -207,6 +210,12 @@ class PeerGather:
                                              self._stream(stream))
         self._lib.check(rc, "parc_peer_push")
         return self.out
+
+    def check(self):
+        """Raise if a hand-shake since the last check gave up waiting for a peer (synchronises)."""
+        if int(self.timeout_flag.item()):
+            self.timeout_flag.zero_()
+            raise RuntimeError("PeerGather: a rank did not arrive within the time-out; the gathered tensors are incomplete")
 
     def barrier(self, stream: Optional[int] = None):
         """Hand-shake alone: every rank's earlier stores into the gathered tensors are visible once it has run."""

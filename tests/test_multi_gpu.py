@@ -65,6 +65,7 @@ def _worker(rank, world_size, port, n, q):
             for rep in range(3):                              # replays reuse the per-slot epochs
                 pg.push(lb)
             torch.cuda.synchronize(dev)
+            pg.check()                                        # no hand-shake gave up waiting
             peer[mode] = bool(torch.equal(pg.out["body_pos"], full["body_pos"]) and torch.equal(pg.out["obs"], full["obs"]))
             peer["multicast"] = bool(pg.multicast) if mode == "auto" else peer["multicast"]
             dist.barrier()
