@@ -521,3 +521,15 @@ class MotionLib:
                                     self._motion_lengths, self._motion_root_pos_delta, self._device)
         self._packed = ops.PackedTables(rows=rows, clips=clips, total_frames=int(rows.shape[0]),
                                         num_clips=self.num_motions(), layout=lay)
+
+
+def calc_phase(times, motion_len, loop_mode):
+    """Module-level twin of `MotionLib.calc_motion_phase` with the reference's signature (anim/motion_lib.py:527-538):
+    phase = times / motion_len, fractional part for WRAP clips, clipped to [0, 1].  Elementwise torch on the tensors'
+    device (the fused query kernel evaluates the same chain internally, bit for bit: `frame_blend` in
+    csrc/motion_query.cu)."""
+    phase = times / motion_len
+    wrap = loop_mode == LoopMode.WRAP.value
+    phase = torch.where(wrap, phase - torch.floor(phase), phase)
+    return torch.clip(phase, 0.0, 1.0)
+

@@ -175,6 +175,19 @@ def sample_hf_z_on_terrain(terrain: SubTerrain, center_xy: torch.Tensor, heading
     return z.view(center_xy.shape[0], tmpl.shape[0], tmpl.shape[1])
 
 
+def points_boxes_sdf(points, box_centers, box_halfdims):
+    """[B,N,3] points against [B,M,3] arbitrary axis-aligned boxes -> the full [B,N,M] table of box SDFs
+    (util/terrain_util.py:1777-1804).  Kept with the reference's signature for callers that want the table itself;
+    it materialises B*N*M values in plain torch.  The heightfield case -- boxes on a grid, minimum over M -- is
+    `points_hf_sdf`, which never builds the table."""
+    assert points.dim() == box_centers.dim() == box_halfdims.dim()
+    if points.dim() == 2:
+        points, box_centers, box_halfdims = points.unsqueeze(0), box_centers.unsqueeze(0), box_halfdims.unsqueeze(0)
+    assert points.shape[0] == box_centers.shape[0]
+    rel = points.unsqueeze(2) - box_centers.unsqueeze(1)
+    return geom_util.sdBox(rel, box_halfdims.unsqueeze(1).expand_as(rel))
+
+
 def points_hf_sdf(points: torch.Tensor, hf: torch.Tensor, hf_min_box_center: torch.Tensor, hf_dxdy: torch.Tensor,
                   base_z=-10.0, inverted=True, radius: Optional[float] = None):
     """Exact signed distance from each point to the union-of-boxes heightfield: min over ALL cells of

@@ -180,3 +180,19 @@ def test_step_assembly_live(ref, model):
             assert torch.equal(got, want)
             seen |= set(want.tolist())
     assert seen == {0, 1, 3}
+
+
+def test_mirror_host_helpers_equal_the_live_reference(ref):
+    """The two module-level helpers SURVEY 8(a) names next to the kernels -- `motion_lib.calc_phase` (:527-538) and
+    `terrain_util.points_boxes_sdf` (:1777-1804) -- are plain torch in the mirror too: same bits as the reference."""
+    from parc_b200.anim import motion_lib as mirror_mlib
+    from parc_b200.util import terrain_util as mirror_tu
+    gen = torch.Generator().manual_seed(91)
+    t = torch.rand(4000, generator=gen) * 30.0 - 4.0
+    length = torch.rand(4000, generator=gen) * 8.0 + 0.3
+    loop = torch.randint(0, 2, (4000,), generator=gen)
+    assert torch.equal(mirror_mlib.calc_phase(t, length, loop), ref["mlib"].calc_phase(t.clone(), length, loop))
+    p, c = torch.randn(3, 40, 3, generator=gen), torch.randn(3, 17, 3, generator=gen)
+    h = torch.rand(3, 17, 3, generator=gen) + 0.05
+    assert torch.equal(mirror_tu.points_boxes_sdf(p, c, h), ref["tu"].points_boxes_sdf(p, c, h))
+    assert torch.equal(mirror_tu.points_boxes_sdf(p[0], c[0], h[0]), ref["tu"].points_boxes_sdf(p[0], c[0], h[0]))
