@@ -692,7 +692,18 @@ typedef struct ParcSimStep {
   float* reward_out;               /* [n, 5] */
   int32_t* done_out;               /* [n] */
   int64_t obs_stride;
+  int32_t phase;                   /* PARC_SIM_STEP_ALL, or one half of the step (see below); appended in ABI 3 */
+  int32_t reserved;
 } ParcSimStep;
+
+/* phase: the step splits where it starts to need the reference frame.  _PRE = DoF conversion (joint rotations to
+ * joint_rot_out, required), character observation, character contact block: depends on the simulator state only, so it
+ * can run BESIDE parc_motion_query_steps.  _POST = target contact block, reward terms, episode flag: reads
+ * joint_rot_out back (the same bits the single launch keeps in registers).  _PRE then _POST == _ALL: observations,
+ * contact blocks and episode flags bit for bit, reward terms to fp32 rounding. */
+#define PARC_SIM_STEP_ALL 0
+#define PARC_SIM_STEP_PRE 1
+#define PARC_SIM_STEP_POST 2
 
 int parc_sim_step(const ParcSimStep* args, int64_t n, const ParcCharModel* model, void* stream);
 

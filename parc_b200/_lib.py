@@ -187,9 +187,10 @@ class ParcSimStep(C.Structure):
                 ("root_height_obs", C.c_int32), ("track_root_h", C.c_int32), ("track_root", C.c_int32),
                 ("joint_rot_out", C.c_void_p), ("char_obs_out", C.c_void_p), ("tar_contacts_out", C.c_void_p),
                 ("char_contacts_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p),
-                ("obs_stride", C.c_int64)]
+                ("obs_stride", C.c_int64), ("phase", C.c_int32), ("reserved", C.c_int32)]
 
 
+PARC_SIM_STEP_ALL, PARC_SIM_STEP_PRE, PARC_SIM_STEP_POST = 0, 1, 2
 PARC_MAX_PEERS, PARC_MAX_PUSH_SEGMENTS = 16, 4
 
 

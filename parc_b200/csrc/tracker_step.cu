@@ -352,8 +352,14 @@ struct SimStepParams {
   DoneParams done;
 };
 
+// PHASE: PARC_SIM_STEP_ALL = the whole step in one launch.  _PRE = the share that does not depend on the reference
+// frame -- DoF conversion (joint rotations written to joint_rot_out), character observation, character contact block --
+// which a caller can run BESIDE the motion query; _POST = the share that needs it -- target contact block, reward
+// terms, episode flag -- reading the joint rotations _PRE stored (the same bits the single launch keeps in registers).
+
 // 7 CTAs x 4 warps per SM = 28 resident warps: exactly one wave for 4096 envs on 148 SMs (27.7 warps per SM); at 80
 // registers only 6 CTAs fit and the kernel needs a second wave (+8 us measured).
+template <int PHASE>
 __global__ void __launch_bounds__(STEP_THREADS, 7)
 sim_step_kernel(const __grid_constant__ SimStepParams p, const __grid_constant__ ParcCharModel model_param, int64_t n) {
   const int lane = threadIdx.x & 31;
@@ -362,7 +368,7 @@ sim_step_kernel(const __grid_constant__ SimStepParams p, const __grid_constant__
   // the whole 1.4 KB model through shared memory held 21 % of this kernel's stall samples)
   int jt = PARC_JOINT_FIXED, didx = 0;
   float axis[3] = {0.0f, 0.0f, 1.0f};
-  if (lane < Jm1) {
+  if (PHASE != PARC_SIM_STEP_POST && lane < Jm1) {
     jt = model_param.joint_type[lane + 1];
     didx = model_param.dof_idx[lane + 1];
     axis[0] = model_param.joint_axis[lane + 1][0];
@@ -372,22 +378,29 @@ sim_step_kernel(const __grid_constant__ SimStepParams p, const __grid_constant__
   const int64_t warp0 = (int64_t)blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * STEP_WARPS;
   for (int64_t e = warp0; e < n; e += nwarps) {
-    float dd[3] = {0.f, 0.f, 0.f};
-    const float* d = p.dof_pos + e * D + didx;
-    if (jt == PARC_JOINT_HINGE) dd[0] = __ldg(d);
-    else if (jt == PARC_JOINT_SPHERICAL) { dd[0] = __ldg(d); dd[1] = __ldg(d + 1); dd[2] = __ldg(d + 2); }
-    const float4 jr = joint_dof_to_quat(jt, dd, axis);
-    if (p.joint_rot_out && lane < Jm1) reinterpret_cast<float4*>(p.joint_rot_out)[e * Jm1 + lane] = jr;
-    char_obs_env<true>(p.sim, e, Jm1, D, p.K, p.global_obs, p.root_height_obs, p.char_obs_out + e * p.obs_stride, lane, jr);
-    if (p.tar_contacts_out) {
-      const float* __restrict__ src = p.tar_contacts + e * p.tar_env_stride * J;
-      float* __restrict__ dst = p.tar_contacts_out + e * p.obs_stride;
-      for (int i = lane; i < p.num_tar_steps * J; i += 32) dst[i] = __ldg(src + i);
+    float4 jr = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (PHASE == PARC_SIM_STEP_POST) {
+      if (lane < Jm1) jr = ld4(p.joint_rot_out + (e * Jm1 + lane) * 4);
+    } else {
+      float dd[3] = {0.f, 0.f, 0.f};
+      const float* d = p.dof_pos + e * D + didx;
+      if (jt == PARC_JOINT_HINGE) dd[0] = __ldg(d);
+      else if (jt == PARC_JOINT_SPHERICAL) { dd[0] = __ldg(d); dd[1] = __ldg(d + 1); dd[2] = __ldg(d + 2); }
+      jr = joint_dof_to_quat(jt, dd, axis);
+      if (p.joint_rot_out && lane < Jm1) reinterpret_cast<float4*>(p.joint_rot_out)[e * Jm1 + lane] = jr;
+      char_obs_env<true>(p.sim, e, Jm1, D, p.K, p.global_obs, p.root_height_obs, p.char_obs_out + e * p.obs_stride, lane, jr);
+      if (p.char_contacts_out && lane < J) p.char_contacts_out[e * p.obs_stride + lane] = __ldg(p.char_contacts + e * J + lane);
     }
-    if (p.char_contacts_out && lane < J) p.char_contacts_out[e * p.obs_stride + lane] = __ldg(p.char_contacts + e * J + lane);
-    reward_env<true>(p.sim, p.ref, e, Jm1, D, p.K, p.joint_w, p.dof_w, p.track_root_h, p.track_root,
-                     p.reward_out + e * 5, lane, jr);
-    done_env(p.done, e, p.done_out, nullptr, lane);
+    if (PHASE != PARC_SIM_STEP_PRE) {
+      if (p.tar_contacts_out) {
+        const float* __restrict__ src = p.tar_contacts + e * p.tar_env_stride * J;
+        float* __restrict__ dst = p.tar_contacts_out + e * p.obs_stride;
+        for (int i = lane; i < p.num_tar_steps * J; i += 32) dst[i] = __ldg(src + i);
+      }
+      reward_env<true>(p.sim, p.ref, e, Jm1, D, p.K, p.joint_w, p.dof_w, p.track_root_h, p.track_root,
+                       p.reward_out + e * 5, lane, jr);
+      done_env(p.done, e, p.done_out, nullptr, lane);
+    }
   }
 }
 
@@ -561,6 +574,13 @@ extern "C" int parc_sim_step(const ParcSimStep* a, int64_t n, const ParcCharMode
   p.tar_env_stride = a->tar_env_stride; p.num_tar_steps = a->num_tar_steps;
   p.K = a->num_keys; p.global_obs = a->global_obs; p.root_height_obs = a->root_height_obs;
   p.track_root_h = a->track_root_h; p.track_root = a->track_root;
-  sim_step_kernel<<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, *model, n);
+  if (a->phase < PARC_SIM_STEP_ALL || a->phase > PARC_SIM_STEP_POST) return PARC_E_SIZE;
+  if (a->phase != PARC_SIM_STEP_ALL && !a->joint_rot_out) return PARC_E_NULL;     // the two halves meet in joint_rot_out
+  if (a->phase == PARC_SIM_STEP_PRE)
+    sim_step_kernel<PARC_SIM_STEP_PRE><<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, *model, n);
+  else if (a->phase == PARC_SIM_STEP_POST)
+    sim_step_kernel<PARC_SIM_STEP_POST><<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, *model, n);
+  else
+    sim_step_kernel<PARC_SIM_STEP_ALL><<<warp_grid(n), STEP_THREADS, 0, (cudaStream_t)stream>>>(p, *model, n);
   return check_launch();
 }

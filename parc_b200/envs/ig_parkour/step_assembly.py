@@ -20,7 +20,9 @@ package, reading the simulator's state tensors in place:
 
 With `fused=True` (default) the simulated character's share -- DoF conversion, proprioceptive observation, reward
 terms, episode flags and both contact-flag blocks -- is ONE launch (`parc_sim_step`, same device code as the
-stand-alone kernels, joint rotations never leave registers): 4 launches per step in total.  With `fuse_tar_obs=True`
+stand-alone kernels, joint rotations never leave registers).  With `split_sim=True` (default) that launch is cut in two
+where it starts to need the reference frame: the first half runs beside the query on the side branch, only reward terms
+and episode flags remain behind it (5 launches, a shorter critical path); `split_sim=False` keeps the single launch (4).  With `fuse_tar_obs=True`
 the target observation is written by the query kernel itself from the registers that hold the targets
 (ParcTarObsSpec; 3 launches) -- an opt-in, because it measured slower than the separate launch, which runs beside
 `parc_sim_step` on a parallel branch.
@@ -47,7 +49,7 @@ class TrackerStep:
                  termination_height: float = 0.15, episode_length: float = 10.0,
                  root_pos_termination_dist: float = 0.6, root_rot_termination_angle: float = 1.309,
                  min_obs_h: float = -3.0, max_obs_h: float = 3.0, fused: bool = True, fuse_tar_obs: bool = False,
-                 query_variant: int = 0):
+                 query_variant: int = 0, split_sim: bool = True):
         dev = mlib._device if hasattr(mlib, "_device") else ray_xy_points.device
         self.device = torch.device(dev)
         self.mlib, self.kcm, self.terrain = mlib, mlib._kin_char_model, terrain
@@ -78,6 +80,10 @@ class TrackerStep:
         self.S = int(steps.shape[0])
         # fetch_tar_obs_data forms timestep * tar_obs_steps in fp32 (mgdm_dm_util.py:289); step 0 = the reference frame
         self.time_offsets = torch.cat([torch.zeros(1), timestep * steps]).to(self.device)
+        # split_sim=True (with fused): the simulated character's launch is cut where it starts to need the reference
+        # frame -- DoF conversion + observation run BESIDE the query on the side branch, reward terms + episode flags
+        # after it -- which takes ~40 % of that launch off the step's critical path
+        self.split_sim = bool(split_sim) and bool(fused)
         self.query_variant = int(query_variant)          # tuning: instantiation of the query kernel (0 = by batch size)
         self._plan = mlib.make_query_plan(self.motion_ids, self.motion_times, want_fk=True,
                                           time_offsets=self.time_offsets, root_xy_offset=self.motion_xy_offset,
@@ -206,8 +212,10 @@ class TrackerStep:
                 if char_contacts is not None:
                     out["char_contacts"] = blk("char_contacts")
             cfg = dict(c, pose_termination_dist=self.pose_termination_dist)
-            simp = ops.SimStepPlan(self.kcm.c_model(), sim, refd, self.key_body_ids, self.joint_err_w, self.dof_err_w,
-                                   self.terrain.hf_desc(), out, cfg=cfg, contact_body_ids=self.contact_body_ids)
+            mk = lambda phase: ops.SimStepPlan(self.kcm.c_model(), sim, refd, self.key_body_ids, self.joint_err_w,
+                                               self.dof_err_w, self.terrain.hf_desc(), out, cfg=cfg,
+                                               contact_body_ids=self.contact_body_ids, phase=phase)
+            simp = (mk(1), mk(2)) if self.split_sim else mk(0)
             self._sim_plan, self._sim_key = (ray, tarp, simp), key
             res = dict(obs=obs, reward_terms=self._reward, done=self._done, char_obs=blk("char"),
                        tar_obs=blk("tar").view(self.n, self.S, self.tar_w), ray_hfs=blk("ray"), joint_rot=self._joint_rot)
@@ -220,15 +228,20 @@ class TrackerStep:
         cur, side = torch.cuda.current_stream(self.device), self._side
         side.wait_stream(cur)
         ray.launch(side.cuda_stream)
+        pre, post = simp if self.split_sim else (None, simp)
+        if pre is not None:
+            pre.launch(side.cuda_stream)                 # beside the query: needs the simulator state only
         if self.fuse_tar_obs:
             tarp.launch(cur.cuda_stream)                 # query + FK + target observation in one launch
-            simp.launch(cur.cuda_stream)
+            if pre is not None:
+                cur.wait_stream(side)
+            post.launch(cur.cuda_stream)
             cur.wait_stream(side)
             return self._fused_result
         self._plan.launch(cur.cuda_stream)
         self._query_done.record(cur)
         side.wait_event(self._query_done)
-        simp.launch(side.cuda_stream)
+        post.launch(side.cuda_stream)                    # behind `pre` on the same stream, and behind the query
         tarp.launch(cur.cuda_stream)
         cur.wait_stream(side)
         return self._fused_result

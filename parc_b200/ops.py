@@ -1257,7 +1257,7 @@ class SimStepPlan:
     `done` [n] int32, optional `joint_rot` [n,J-1,4]."""
 
     def __init__(self, model: ParcCharModel, sim: dict, ref: dict, key_body_ids: torch.Tensor, joint_rot_err_w,
-                 dof_err_w, hf: HeightfieldDesc, out: dict, *, cfg: dict, contact_body_ids=()):
+                 dof_err_w, hf: HeightfieldDesc, out: dict, *, cfg: dict, contact_body_ids=(), phase: int = 0):
         J, D = model.num_bodies, model.dof_size
         self.model, self.device = model, sim["root_pos"].device
         n = int(sim["root_pos"].shape[0])
@@ -1331,6 +1331,10 @@ class SimStepPlan:
         if out.get("joint_rot") is not None:
             a.joint_rot_out = dense(out["joint_rot"], (n, J - 1, 4))
         keep += [blk, out["reward"], out["done"]]
+        # phase: 0 = the whole step; 1 / 2 = the half that does not / does need the reference frame (the halves meet in
+        # out["joint_rot"]; include/parc_b200.h: PARC_SIM_STEP_PRE / _POST)
+        assert phase in (0, 1, 2) and (phase == 0 or out.get("joint_rot") is not None)
+        a.phase = int(phase)
         self._args, self._keep = a, keep
         self._fn = _lib.load().parc_sim_step
 

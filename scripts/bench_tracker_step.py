@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--fuse-tar-obs", action="store_true", help="target observation written by the query kernel (3 launches)")
+    ap.add_argument("--single-sim-launch", action="store_true",
+                    help="the simulated character's share as ONE launch behind the query (round 1's 4-launch step)")
     ap.add_argument("--query-variant", type=int, default=0, help="instantiation of the query kernel (tuning)")
     args = ap.parse_args()
     import __graft_entry__ as entry
@@ -77,7 +79,8 @@ def main():
     ptd = torch.tensor([0.7, 1.0, 0.7, 0.7, 0.7, 0.7, 0.7, 0.7, 1.0, 1.2, 10.0, 1.0, 1.2, 10.0])
     steps = [1, 2, 3, 10, 20, 30]
     ts = TrackerStep(mlib, terrain, n, 1.0 / 30.0, steps, key_ids, tmpl, joint_err_w=jw, pose_termination_dist=ptd,
-                     contact_body_ids=feet, fuse_tar_obs=args.fuse_tar_obs, query_variant=args.query_variant)
+                     contact_body_ids=feet, fuse_tar_obs=args.fuse_tar_obs, query_variant=args.query_variant,
+                     split_sim=not args.single_sim_launch)
     g = torch.Generator().manual_seed(3)
     ids = torch.randint(0, args.clips, (n,), generator=g)
     times = torch.rand(n, generator=g) * (264.0 / 30.0)
@@ -148,6 +151,7 @@ def main():
                     f"FK, char/target observation (W = {b['obs_width']}), {P}-pt ray heightmap, reward terms, done flags",
         "parc_launches_per_step": launches, "target_observation": "fused into the query kernel" if args.fuse_tar_obs else "own launch",
         "query_variant": args.query_variant,
+        "sim_step": "one launch behind the query" if args.single_sim_launch else "split: observation half beside the query, reward / done behind it",
         "eager": {"ms_per_step": ms_eager, "env_steps_per_s": n / (ms_eager * 1e-3)},
         "cuda_graph": {"ms_per_step": ms_graph, "env_steps_per_s": n / (ms_graph * 1e-3),
                        "achieved_GBps": n * b["total"] / (ms_graph * 1e-3) / 1e9,

@@ -1704,9 +1704,10 @@ def test_query_fused_target_observation_equals_the_standalone_operator(golden_li
         assert torch.equal(out[k], plain[k]), k
 
 
-@pytest.mark.parametrize("fused,fuse_tar", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("fused,fuse_tar,split_sim", [(False, False, False), (True, False, False), (True, False, True),
+                                                      (True, True, False), (True, True, True)])
 def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model, O, oracle_tables, oracle_model, fused,
-                                                          fuse_tar):
+                                                          fuse_tar, split_sim):
     """The whole kinematic side of a control step (envs/ig_parkour/step_assembly.py): reference frame + 6 targets
     with the per-env terrain placement, simulated character's observation, ray heightmap, reward terms and done
     flags -- against the same sequence composed from the oracle; then the CUDA-graph replay against the eager run."""
@@ -1725,7 +1726,8 @@ def test_tracker_step_sequence_matches_oracle_composition(golden_lib, gpu_model,
     jw, ptd = torch.as_tensor(g["joint_err_w"]), torch.as_tensor(g["pose_termination_dist"])
     feet = [int(i) for i in g["feet"]]
     ts = TrackerStep(golden_lib, terr, n, float(g["dt"]), g["steps"].tolist(), key_ids.tolist(), tmpl, joint_err_w=jw,
-                     pose_termination_dist=ptd, contact_body_ids=feet, fused=fused, fuse_tar_obs=fuse_tar)
+                     pose_termination_dist=ptd, contact_body_ids=feet, fused=fused, fuse_tar_obs=fuse_tar,
+                     split_sim=split_sim)
     ids, times = torch.as_tensor(g["ids"]).long(), torch.as_tensor(g["times"])
     xy_off = torch.randn(n, 2, generator=gen) * 0.3
     env_off = torch.as_tensor(g["env_offsets"])
@@ -2108,6 +2110,24 @@ def test_sim_step_equals_the_standalone_operators(gpu_model, global_obs, root_h,
     assert torch.equal(out["tar_contacts"], big["contacts"][:, 1:].reshape(n, -1))
     assert torch.equal(out["char_contacts"], char_contacts)
     assert (obs[:, :3] == SENT).all() and (obs[:, -5:] == SENT).all()
+    # the two halves of the step (PARC_SIM_STEP_PRE beside the query, _POST behind it) == the single launch: observation,
+    # contact blocks and episode flags bit for bit, the reward terms to fp32 rounding (two instantiations of the same
+    # expressions; the compiler may contract their FMAs differently)
+    single = {k: v.clone() for k, v in out.items()}
+    whole_row = obs.clone()
+    obs.fill_(SENT); out["reward"].fill_(SENT); out["done"].fill_(-9); out["joint_rot"].fill_(SENT)
+    pre = ops.SimStepPlan(gpu_model.c_model(), simd, refd, kid, jw, dw, hfd, out, cfg=cfg, contact_body_ids=allowed, phase=1)
+    post = ops.SimStepPlan(gpu_model.c_model(), simd, refd, kid, jw, dw, hfd, out, cfg=cfg, contact_body_ids=allowed, phase=2)
+    pre.launch()
+    assert (out["reward"] == SENT).all() and (out["done"] == -9).all() and (out["tar_contacts"] == SENT).all()
+    assert torch.equal(out["char_obs"], single["char_obs"]) and torch.equal(out["joint_rot"], single["joint_rot"])
+    post.launch()
+    for k in single:
+        if k == "reward":
+            assert_close(out[k], single[k], rtol=1e-6, atol=1e-7, what="reward terms of the split step")
+        else:
+            assert torch.equal(out[k], single[k]), k
+    assert torch.equal(obs, whole_row)
 
 
 def test_query_accepts_any_leading_shape_and_int32_ids(golden_lib):
