@@ -124,7 +124,7 @@ class PeerGather:
         import torch.distributed._symmetric_memory as symm
         from . import _lib
         self.rank, self.world = world()
-        assert self.world <= _lib.PARC_MAX_PEERS
+        assert 2 <= self.world <= _lib.PARC_MAX_PEERS, "PeerGather needs an initialised process group of 2..16 ranks"
         self.device = torch.device(device)
         self.n_total = int(n_total)
         self.lo, self.hi = shard_bounds(self.n_total, self.rank, self.world)
