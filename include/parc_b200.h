@@ -746,6 +746,9 @@ typedef struct ParcPeerSignals {
                                               lets the kernel finish (a peer that never launches must not hang the GPU);
                                               0 = wait for ever */
   int32_t* timeout_flag;                   /* device word, or NULL */
+  int32_t rank;                            /* this rank: peer-pointer stores start at the next rank and go round, so that
+                                              the ranks do not all write into the same peer at the same moment */
+  int32_t reserved;
 } ParcPeerSignals;
 
 typedef struct ParcPeerSegment {

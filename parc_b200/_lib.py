@@ -197,7 +197,7 @@ PARC_MAX_PEERS, PARC_MAX_PUSH_SEGMENTS = 16, 4
 class ParcPeerSignals(C.Structure):
     _fields_ = [("multicast_signal", C.c_void_p), ("peer_signal", C.c_void_p * PARC_MAX_PEERS),
                 ("local_signal", C.c_void_p), ("epoch", C.c_void_p), ("world", C.c_int32), ("num_slots", C.c_int32),
-                ("timeout_ns", C.c_int64), ("timeout_flag", C.c_void_p)]
+                ("timeout_ns", C.c_int64), ("timeout_flag", C.c_void_p), ("rank", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ParcPeerSegment(C.Structure):

@@ -33,6 +33,7 @@ struct PeerSync {
   uint64_t* local_signal;                   // this rank's copy
   uint64_t* epoch;                          // [slots] private per-rank launch counters
   int world;
+  int rank;
   long long timeout_ns;                     // > 0: give up waiting after this long (and say so in *timeout_flag)
   int32_t* timeout_flag;
 };
@@ -102,7 +103,12 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_push_kernel(const __grid_co
       } else {
         for (int64_t i = t0; i < n; i += nt) {
           const float4 v = src[i];
-          for (int r = 0; r < p.sync.world; ++r) reinterpret_cast<float4*>(sg.dst_peer[r])[i] = v;
+          // start behind the own rank and go round: at any moment the ranks write into different peers
+          for (int k = 1; k <= p.sync.world; ++k) {
+            int r = p.sync.rank + k;
+            if (r >= p.sync.world) r -= p.sync.world;
+            reinterpret_cast<float4*>(sg.dst_peer[r])[i] = v;
+          }
         }
       }
     } else {
@@ -112,7 +118,11 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_push_kernel(const __grid_co
         const float v = src[i];
         if (sg.dst_multicast) st_mc_f32(reinterpret_cast<float*>(sg.dst_multicast) + i, v);
         else
-          for (int r = 0; r < p.sync.world; ++r) reinterpret_cast<float*>(sg.dst_peer[r])[i] = v;
+          for (int k = 1; k <= p.sync.world; ++k) {
+            int r = p.sync.rank + k;
+            if (r >= p.sync.world) r -= p.sync.world;
+            reinterpret_cast<float*>(sg.dst_peer[r])[i] = v;
+          }
       }
     }
   }
@@ -129,6 +139,8 @@ static int fill_sync(const ParcPeerSignals* sig, int slots_needed, PeerSync* out
   s.local_signal = sig->local_signal;
   s.epoch = sig->epoch;
   s.world = sig->world;
+  s.rank = sig->rank;
+  if (sig->rank < 0 || sig->rank >= sig->world) return PARC_E_SIZE;
   s.timeout_ns = sig->timeout_ns;
   s.timeout_flag = sig->timeout_flag;
   if (sig->timeout_ns < 0) return PARC_E_SIZE;

@@ -172,7 +172,7 @@ class PeerGather:
             sig.peer_signal[r] = self._peers[r] + self._sig_off
         sig.local_signal = self.buf.data_ptr() + self._sig_off
         sig.epoch = self.epoch.data_ptr()
-        sig.world, sig.num_slots = self.world, self._slots
+        sig.world, sig.num_slots, sig.rank = self.world, self._slots, self.rank
         # a rank that never launches its side must not hang this GPU: the hand-shake gives up after `timeout_s`
         self.timeout_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         sig.timeout_ns, sig.timeout_flag = int(timeout_s * 1e9), self.timeout_flag.data_ptr()

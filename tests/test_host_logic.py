@@ -371,7 +371,7 @@ def test_peer_gather_entry_points_reject_bad_arguments():
     assert lib.parc_peer_push(seg, 1, C.byref(sig), 4, None) == -2             # not a multiple of 4 bytes
     seg[0].bytes, seg[0].src = 64, 4098
     assert lib.parc_peer_push(seg, 1, C.byref(sig), 4, None) == -4             # misaligned for fp32
-    assert C.sizeof(_lib.ParcPeerSignals) == 8 + 8 * _lib.PARC_MAX_PEERS + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.ParcPeerSignals) == 8 + 8 * _lib.PARC_MAX_PEERS + 8 + 8 + 8 + 8 + 8 + 8
     sig.timeout_ns = -5
     assert lib.parc_peer_barrier(C.byref(sig), 0, None) == -2
     sig.timeout_ns = 0
