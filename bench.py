@@ -374,6 +374,16 @@ def barrier(ctx):
     torch.cuda.synchronize(ctx.dev)
 
 
+def stream_gate(ctx):
+    """A ~0.2 ms device-side delay ahead of a timed region: the first event, the graph launch and the last event are then
+    all ENQUEUED while the stream is still busy, so the device-timed interval holds the K steps and not the host's
+    enqueue latency between the event record and the graph launch (measured at N = 2: 18 us of a 120 us region when
+    the ranks share the host's cores; nothing at N = 1).  PARC_BENCH_GATE=0 disables it."""
+    cycles = int(os.environ.get("PARC_BENCH_GATE", "400000"))
+    if cycles > 0:
+        torch.cuda._sleep(cycles)
+
+
 def timed_graph_steps(ctx, plans, K, warm_steps):
     """K back-to-back steps as ONE CUDA graph of K kernel nodes (step s = plans[s % len(plans)], each over its own input
     batch), one event pair around the replay, barrier + synchronize on both sides.  -> milliseconds for the K steps
@@ -387,6 +397,7 @@ def timed_graph_steps(ctx, plans, K, warm_steps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.current_stream(ctx.dev)
     barrier(ctx)
+    stream_gate(ctx)
     e0.record(stream)
     graph.replay()
     e1.record(stream)
@@ -1081,7 +1092,8 @@ def main():
             "l2": "clip records, heightfield and template stay L2-resident as in a running tracker; the L2-flushed "
                   "isolated-launch time is roofline.isolated_flushed_launch_us",
             "timing": "one CUDA-event pair on the launch stream around the K steps, barrier + synchronize on both sides, "
-                      "max over ranks",
+                      "max over ranks; a 0.2 ms device-side delay ahead of the first event keeps the host's enqueue "
+                      "latency out of the device-timed region (events and graph launch are queued while it runs)",
             "launch": ("the K steps are ONE CUDA graph of K kernel nodes" +
                        (" chained by programmatic dependent launch (a step's read side overlaps the previous step's "
                         "tail; its stores wait for it)" if pdl else "")),
