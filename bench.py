@@ -378,8 +378,9 @@ def stream_gate(ctx):
     """A ~0.2 ms device-side delay ahead of a timed region: the first event, the graph launch and the last event are then
     all ENQUEUED while the stream is still busy, so the device-timed interval holds the K steps and not the host's
     enqueue latency between the event record and the graph launch (measured at N = 2: 18 us of a 120 us region when
-    the ranks share the host's cores; nothing at N = 1).  PARC_BENCH_GATE=0 disables it."""
-    cycles = int(os.environ.get("PARC_BENCH_GATE", "400000"))
+    the ranks share the host's cores).  Used at N > 1 only: a single process enqueues fast enough, and there the delay
+    kernel's own completion costs ~1 % of a 20-step region.  PARC_BENCH_GATE=<cycles> / 0 overrides."""
+    cycles = int(os.environ.get("PARC_BENCH_GATE", "400000" if ctx.world > 1 else "0"))
     if cycles > 0:
         torch.cuda._sleep(cycles)
 
@@ -1092,8 +1093,9 @@ def main():
             "l2": "clip records, heightfield and template stay L2-resident as in a running tracker; the L2-flushed "
                   "isolated-launch time is roofline.isolated_flushed_launch_us",
             "timing": "one CUDA-event pair on the launch stream around the K steps, barrier + synchronize on both sides, "
-                      "max over ranks; a 0.2 ms device-side delay ahead of the first event keeps the host's enqueue "
-                      "latency out of the device-timed region (events and graph launch are queued while it runs)",
+                      "max over ranks" + ("; a 0.2 ms device-side delay ahead of the first event keeps the host's enqueue "
+                      "latency out of the device-timed region (events and graph launch are queued while it runs)"
+                      if ctx.world > 1 else ""),
             "launch": ("the K steps are ONE CUDA graph of K kernel nodes" +
                        (" chained by programmatic dependent launch (a step's read side overlaps the previous step's "
                         "tail; its stores wait for it)" if pdl else "")),
