@@ -11,13 +11,20 @@ own input batch.  N > 1: every rank runs the same per-GPU workload on its own GP
 collective); NCCL only carries the barrier and the max-reduce of the elapsed time.
 
 Extra keys of the same JSON line (each a leg of this script, see DESIGN.md "Measurement"):
+  e2e / e2e_body_pos_obs_only   the same query through the public API with pinned host buffers: H2D of the inputs,
+               launch, D2H of every output / of the two outputs the metric names, host wait -- all inside the timed region
+  cfg3         BASELINE configs[2]: 1024 samples x 200 frames, penetration / contact loss forward + pose gradients,
+               samples sharded over the ranks
   cfg4         BASELINE configs[3]: 65 536 envs -- one GPU at N = 1, split contiguously over the ranks at N > 1 with the
-               NCCL all-gather of body_pos + obs timed alone and inside a per-step figure, and the strong-scaling
-               efficiency against the same batch on one GPU measured in the same run
+               NCCL all-gather of body_pos + obs timed alone and inside a per-step figure, the same exchange with the
+               library's own NVLink kernels (peer_gather: multicast / peer-pointer push, direct stores), and the
+               strong-scaling efficiency against the same batch on one GPU measured in the same run
   cfg5         BASELINE configs[4]: 100 000 clips x 265 frames sharded over the ranks: GPU table build + FK + contact
                labels + heightfield samples / masks, label statistics reduced over the ranks at the end
   tracker_step the tracker's real per-step shape (current frame + 6 look-ahead targets per env in one launch)
-  selfcheck    (N > 1) the sharded + NCCL-gathered query equals the single-GPU query bit for bit
+  selfcheck    (N > 1) the sharded query gathered by NCCL and by the peer-memory kernels equals the single-GPU query
+               bit for bit
+  measurement  how this arm launches and times the steps (`config` itself is identical in both arms)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--clips M] [--impl reference]
 
